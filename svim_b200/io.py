@@ -1,0 +1,273 @@
+"""pysam-free readers/writers: SAM text, BAM (BGZF via zlib), FASTA (+ .fai).
+
+The reference reads its input through pysam/htslib (SVIM_COLLECT.py:133,
+SVIM_clustering.py:377), which is not available here.  These readers decode
+straight into the flattened record buffer (`records.AlignmentBatch`) – there is
+no per-record Python object on the product path.
+
+File formats follow the SAM/BAM specification (SAMv1 §1.4, §4.2).
+"""
+from __future__ import annotations
+
+import os
+import struct
+import zlib
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from .records import AlignmentBatch, BatchBuilder, CIGAR_OPS, SEQ_NT16, parse_cigar_string
+
+
+# --------------------------------------------------------------------------
+# SAM text
+# --------------------------------------------------------------------------
+def _parse_sam_header(lines) -> Tuple[List[str], List[int], str]:
+    names, lengths, so = [], [], "unknown"
+    for ln in lines:
+        f = ln.rstrip("\n").split("\t")
+        if f[0] == "@SQ":
+            d = dict(x.split(":", 1) for x in f[1:] if ":" in x)
+            names.append(d["SN"]); lengths.append(int(d.get("LN", 0)))
+        elif f[0] == "@HD":
+            d = dict(x.split(":", 1) for x in f[1:] if ":" in x)
+            so = d.get("SO", "unknown")
+    return names, lengths, so
+
+
+def read_sam(path: str) -> AlignmentBatch:
+    with open(path, "r") as fh:
+        text = fh.read().split("\n")
+    header = [l for l in text if l.startswith("@")]
+    names, lengths, so = _parse_sam_header(header)
+    tid_of = {n: i for i, n in enumerate(names)}
+    b = BatchBuilder(names, lengths, so)
+    for ln in text:
+        if not ln or ln.startswith("@"):
+            continue
+        f = ln.split("\t")
+        sa = None
+        for tag in f[11:]:
+            if tag.startswith("SA:Z:"):
+                sa = tag[5:]
+        tid = -1 if f[2] == "*" else tid_of.get(f[2], -1)
+        b.add(f[0], int(f[1]), tid, int(f[3]) - 1, int(f[4]), parse_cigar_string(f[5]),
+              None if f[9] == "*" else f[9], sa)
+    return b.finish()
+
+
+def write_sam(path: str, batch: AlignmentBatch):
+    with open(path, "w") as fh:
+        fh.write("@HD\tVN:1.6\tSO:%s\n" % batch.sort_order)
+        for n, l in zip(batch.contig_names, batch.contig_lengths):
+            fh.write("@SQ\tSN:%s\tLN:%d\n" % (n, l))
+        for i in range(batch.n):
+            tid = int(batch.tid[i])
+            cig = batch.cigartuples(i)
+            seq = batch.sequence(i)
+            cols = [batch.qname(int(batch.qname_id[i])), str(int(batch.flag[i])),
+                    batch.contig_names[tid] if tid >= 0 else "*", str(int(batch.pos[i]) + 1),
+                    str(int(batch.mapq[i])),
+                    "".join("%d%s" % (n, CIGAR_OPS[o]) for o, n in cig) or "*",
+                    "*", "0", "0", seq if seq else "*", "*"]
+            sa = batch.sa_tag(i)
+            if sa:
+                cols.append("SA:Z:" + sa)
+            fh.write("\t".join(cols) + "\n")
+
+
+# --------------------------------------------------------------------------
+# BGZF / BAM
+# --------------------------------------------------------------------------
+_BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _bgzf_blocks(fh):
+    while True:
+        head = fh.read(12)
+        if len(head) < 12:
+            return
+        if head[:4] != b"\x1f\x8b\x08\x04":
+            raise ValueError("not a BGZF file")
+        xlen = struct.unpack("<H", head[10:12])[0]
+        extra = fh.read(xlen)
+        bsize = None
+        o = 0
+        while o + 4 <= xlen:
+            si1, si2, slen = extra[o], extra[o + 1], struct.unpack("<H", extra[o + 2:o + 4])[0]
+            if si1 == 66 and si2 == 67:
+                bsize = struct.unpack("<H", extra[o + 4:o + 6])[0]
+            o += 4 + slen
+        if bsize is None:
+            raise ValueError("BGZF block without BC field")
+        cdata = fh.read(bsize - xlen - 19)
+        fh.read(8)  # crc32, isize
+        yield zlib.decompress(cdata, -15)
+
+
+def _bgzf_inflate_all(path: str) -> bytes:
+    with open(path, "rb") as fh:
+        return b"".join(_bgzf_blocks(fh))
+
+
+def _aux_find_sa(aux: bytes) -> Optional[bytes]:
+    """Walk BAM aux fields, return the SA:Z payload (without NUL) if present."""
+    o, n = 0, len(aux)
+    sizes = {ord("A"): 1, ord("c"): 1, ord("C"): 1, ord("s"): 2, ord("S"): 2,
+             ord("i"): 4, ord("I"): 4, ord("f"): 4}
+    while o + 3 <= n:
+        tag, typ = aux[o:o + 2], aux[o + 2]
+        o += 3
+        if typ in sizes:
+            o += sizes[typ]
+        elif typ in (ord("Z"), ord("H")):
+            e = aux.index(b"\x00", o)
+            if tag == b"SA" and typ == ord("Z"):
+                return aux[o:e]
+            o = e + 1
+        elif typ == ord("B"):
+            sub = aux[o]; cnt = struct.unpack("<I", aux[o + 1:o + 5])[0]
+            o += 5 + cnt * sizes[sub]
+        else:
+            raise ValueError("bad aux type %r" % typ)
+    return None
+
+
+def read_bam(path: str) -> AlignmentBatch:
+    data = _bgzf_inflate_all(path)
+    if data[:4] != b"BAM\x01":
+        raise ValueError("not a BAM file")
+    l_text = struct.unpack("<i", data[4:8])[0]
+    text = data[8:8 + l_text].split(b"\x00")[0].decode("ascii", "replace")
+    _, _, so = _parse_sam_header(text.split("\n"))
+    o = 8 + l_text
+    n_ref = struct.unpack("<i", data[o:o + 4])[0]; o += 4
+    names, lengths = [], []
+    for _ in range(n_ref):
+        l_name = struct.unpack("<i", data[o:o + 4])[0]; o += 4
+        names.append(data[o:o + l_name - 1].decode("ascii")); o += l_name
+        lengths.append(struct.unpack("<i", data[o:o + 4])[0]); o += 4
+    b = BatchBuilder(names, lengths, so)
+    n = len(data)
+    while o + 4 <= n:
+        bs = struct.unpack("<i", data[o:o + 4])[0]; o += 4
+        rec = data[o:o + bs]; o += bs
+        (tid, pos, l_rn, mapq, _bin, n_cig, flag, l_seq, _nt, _np, _tl) = struct.unpack("<iiBBHHHiiii", rec[:32])
+        p = 32
+        qname = rec[p:p + l_rn - 1].decode("ascii"); p += l_rn
+        cigar = np.frombuffer(rec, dtype="<u4", count=n_cig, offset=p).copy(); p += 4 * n_cig
+        nb = (l_seq + 1) // 2
+        packed = np.frombuffer(rec, dtype=np.uint8, count=nb, offset=p).copy(); p += nb
+        p += l_seq  # qual
+        sa = _aux_find_sa(rec[p:])
+        b.add(qname, flag, tid, pos, mapq, cigar, None, sa.decode("ascii") if sa else None,
+              packed_seq=packed, l_seq=l_seq)
+    return b.finish()
+
+
+def _reg2bin(beg: int, end: int) -> int:
+    end -= 1
+    if beg >> 14 == end >> 14: return ((1 << 15) - 1) // 7 + (beg >> 14)
+    if beg >> 17 == end >> 17: return ((1 << 12) - 1) // 7 + (beg >> 17)
+    if beg >> 20 == end >> 20: return ((1 << 9) - 1) // 7 + (beg >> 20)
+    if beg >> 23 == end >> 23: return ((1 << 6) - 1) // 7 + (beg >> 23)
+    if beg >> 26 == end >> 26: return ((1 << 3) - 1) // 7 + (beg >> 26)
+    return 0
+
+
+def write_bam(path: str, batch: AlignmentBatch, level: int = 1):
+    """Write the batch as a BAM file (one BGZF block per <=64 KiB of payload)."""
+    out = bytearray()
+    text = "@HD\tVN:1.6\tSO:%s\n" % batch.sort_order
+    for nm, ln in zip(batch.contig_names, batch.contig_lengths):
+        text += "@SQ\tSN:%s\tLN:%d\n" % (nm, ln)
+    tb = text.encode("ascii")
+    out += b"BAM\x01" + struct.pack("<i", len(tb)) + tb + struct.pack("<i", len(batch.contig_names))
+    for nm, ln in zip(batch.contig_names, batch.contig_lengths):
+        nb = nm.encode("ascii") + b"\x00"
+        out += struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(ln))
+    ref_adv = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1], dtype=np.int64)
+    for i in range(batch.n):
+        o = int(batch.cigar_off[i]); nc = int(batch.n_cigar[i])
+        cig = batch.cigar[o:o + nc]
+        rlen = int(((cig >> 4).astype(np.int64) * ref_adv[cig & 15]).sum()) if nc else 0
+        pos = int(batch.pos[i])
+        qn = batch.qname(int(batch.qname_id[i])).encode("ascii") + b"\x00"
+        l_seq = int(batch.l_seq[i]); so = int(batch.seq_off[i])
+        rec = struct.pack("<iiBBHHHiiii", int(batch.tid[i]), pos, len(qn), int(batch.mapq[i]),
+                          _reg2bin(max(pos, 0), max(pos, 0) + max(rlen, 1)), nc, int(batch.flag[i]), l_seq, -1, -1, 0)
+        rec += qn + cig.astype("<u4").tobytes() + batch.seq[so:so + (l_seq + 1) // 2].tobytes() + b"\xff" * l_seq
+        sa = batch.sa_tag(i)
+        if sa:
+            rec += b"SAZ" + sa.encode("ascii") + b"\x00"
+        out += struct.pack("<i", len(rec)) + rec
+    with open(path, "wb") as fh:
+        view = memoryview(out)
+        for s in range(0, len(out), 0xff00):
+            chunk = bytes(view[s:s + 0xff00])
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            cdata = co.compress(chunk) + co.flush()
+            fh.write(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00"
+                     + struct.pack("<H", len(cdata) + 25) + cdata
+                     + struct.pack("<II", zlib.crc32(chunk) & 0xffffffff, len(chunk)))
+        fh.write(_BGZF_EOF)
+
+
+def read_alignments(path: str) -> AlignmentBatch:
+    with open(path, "rb") as fh:
+        magic = fh.read(4)
+    if magic[:2] == b"\x1f\x8b":
+        return read_bam(path)
+    return read_sam(path)
+
+
+# --------------------------------------------------------------------------
+# FASTA
+# --------------------------------------------------------------------------
+class Genome:
+    """Whole reference in memory: one uint8 blob + per-contig offsets.
+
+    Stands in for `pysam.FastaFile` (SVIM_clustering.py:377): `fetch(contig,
+    start, end)` returns `seq[start:end]`, clamped at the contig end, case
+    preserved (htslib faidx semantics; parity unpinned – no reference test
+    fetches from a FASTA)."""
+
+    def __init__(self, names: List[str], seqs: List[np.ndarray]):
+        self.names = list(names)
+        self.lengths = np.array([len(s) for s in seqs], dtype=np.int64)
+        self.offsets = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(self.lengths, out=self.offsets[1:])
+        self.blob = np.concatenate(seqs).astype(np.uint8) if seqs else np.zeros(0, np.uint8)
+        self._idx = {n: i for i, n in enumerate(self.names)}
+
+    @classmethod
+    def from_fasta(cls, path: str) -> "Genome":
+        names, seqs, cur = [], [], []
+        with open(path, "rb") as fh:
+            for ln in fh:
+                if ln.startswith(b">"):
+                    if names:
+                        seqs.append(np.frombuffer(b"".join(cur), dtype=np.uint8))
+                    names.append(ln[1:].split()[0].decode("ascii")); cur = []
+                else:
+                    cur.append(ln.strip())
+        if names:
+            seqs.append(np.frombuffer(b"".join(cur), dtype=np.uint8))
+        return cls(names, seqs)
+
+    def fetch(self, contig: str, start: int, end: int) -> str:
+        i = self._idx[contig]
+        L = int(self.lengths[i])
+        start = max(0, min(start, L)); end = max(start, min(end, L))
+        o = int(self.offsets[i])
+        return self.blob[o + start:o + end].tobytes().decode("ascii")
+
+    def write_fasta(self, path: str, width: int = 60):
+        with open(path, "wb") as fh, open(path + ".fai", "w") as fai:
+            for i, nm in enumerate(self.names):
+                fh.write(b">" + nm.encode() + b"\n")
+                off = fh.tell()
+                s = self.blob[self.offsets[i]:self.offsets[i + 1]].tobytes()
+                for k in range(0, len(s), width):
+                    fh.write(s[k:k + width] + b"\n")
+                fai.write("%s\t%d\t%d\t%d\t%d\n" % (nm, len(s), off, width, width + 1))

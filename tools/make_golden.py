@@ -1,0 +1,181 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported from
+/root/reference through tools/ref_shim) on seeded synthetic inputs, and check that
+oracle/svim_oracle.py reproduces every output exactly.
+
+Run in the build container only:   python tools/make_golden.py
+The committed fixtures (inputs as .npz, reference outputs as .json.gz) are what
+tests/ and the GPU box use; /root/reference is never read at test time.
+"""
+import gzip
+import json
+import os
+import sys
+import tempfile
+import argparse
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refenv  # noqa: E402
+
+refenv.activate()
+
+import numpy as np  # noqa: E402
+import pysam  # the shim  # noqa: E402
+from svim.SVIM_COLLECT import analyze_alignment_file_coordsorted  # noqa: E402
+from svim.SVIM_CLUSTER import cluster_sv_signatures  # noqa: E402
+from svim.SVIM_input_parsing import parse_arguments  # noqa: E402
+
+from svim_b200 import synth  # noqa: E402
+from svim_b200.records import AlignmentBatch  # noqa: E402
+from svim_b200.io import Genome  # noqa: E402
+from oracle import svim_oracle as orc  # noqa: E402
+
+GOLDEN = os.path.join(refenv.ROOT, "tests", "golden")
+SIG_FIELDS = orc.Sig.__slots__
+
+
+def ref_sig_tuple(s):
+    t = s.type
+    d = dict.fromkeys(SIG_FIELDS)
+    d.update(type=t, signature=s.signature, read=s.read)
+    if t in ("DEL", "INS", "INV", "DUP_TAN"):
+        d.update(contig=s.contig, start=s.start, end=s.end)
+        if t == "INS":
+            d["sequence"] = s.sequence
+        if t == "INV":
+            d["direction"] = s.direction
+        if t == "DUP_TAN":
+            d.update(copies=s.copies, fully_covered=s.fully_covered)
+    elif t == "DUP_INT":
+        d.update(contig=s.contig1, start=s.start, end=s.end, contig2=s.contig2, pos=s.pos)
+    elif t == "BND":
+        d.update(contig=s.contig1, start=s.pos1, end=s.pos1 + 1, contig2=s.contig2, pos=s.pos2,
+                 dir1=s.direction1, dir2=s.direction2)
+    return [d[f] for f in SIG_FIELDS]
+
+
+def ref_cluster_tuple(c, index_of):
+    members = [index_of[id(m)] for m in c.members]
+    if hasattr(c, "source_contig"):
+        return [c.type, c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end,
+                c.score, c.size, c.std_span, c.std_pos, getattr(c, "direction1", None), getattr(c, "direction2", None), members]
+    return [c.type, c.contig, c.start, c.end, None, None, None, c.score, c.size, c.std_span, c.std_pos, None, None, members]
+
+
+def oracle_cluster_tuple(c, index_of):
+    return [c.type, c.contig, c.start, c.end, c.dest_contig, c.dest_start, c.dest_end, c.score, c.size,
+            c.std_span, c.std_pos, c.dir1, c.dir2, [index_of[id(m)] for m in c.members]]
+
+
+def run_reference(batch, genome, overrides):
+    with tempfile.TemporaryDirectory() as td:
+        gpath = os.path.join(td, "genome.fa")
+        pysam.register_genome(gpath, genome)
+        argv = ["alignment", td, "in.bam", gpath]
+        for k, v in overrides.items():
+            if v is True:
+                argv.append("--" + k)
+            else:
+                argv += ["--" + k, str(v)]
+        options = parse_arguments("2.0.0", argv)
+        bam = pysam.AlignmentFile.from_batch(batch)
+        sigs, twins = analyze_alignment_file_coordsorted(bam, options)
+        out = {"signatures": [ref_sig_tuple(s) for s in sigs], "all_bnds_signatures": [ref_sig_tuple(s) for s in twins]}
+        for key, lst in (("clusters", sigs), ("all_bnds_clusters", twins)):
+            index_of = {id(s): i for i, s in enumerate(lst)}
+            res = cluster_sv_signatures(lst, options)
+            out[key] = {name: [ref_cluster_tuple(c, index_of) for c in cl]
+                        for name, cl in zip(("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"), res)}
+        return out
+
+
+def run_oracle(batch, genome, overrides):
+    p = orc.Params(**overrides)
+    sigs, twins = orc.collect(batch, p)
+    out = {"signatures": [list(s.as_tuple()) for s in sigs], "all_bnds_signatures": [list(s.as_tuple()) for s in twins]}
+    for key, lst in (("clusters", sigs), ("all_bnds_clusters", twins)):
+        index_of = {id(s): i for i, s in enumerate(lst)}
+        res = orc.cluster(lst, genome, p)
+        out[key] = {name: [oracle_cluster_tuple(c, index_of) for c in cl]
+                    for name, cl in zip(("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"), res)}
+    return out
+
+
+def save_input(path, batch, genome):
+    arrays = {name: getattr(batch, name) for name, _ in AlignmentBatch.FIELDS}
+    np.savez_compressed(path, contig_names=np.array(batch.contig_names), contig_lengths=batch.contig_lengths,
+                        cigar=batch.cigar, seq=batch.seq, sa=batch.sa, genome_blob=genome.blob, **arrays)
+
+
+def fixtures():
+    """name -> (batch, genome, option overrides)."""
+    out = {}
+    # 1. DEL/INS only, one contig (BASELINE config 1 in miniature)
+    names, L = ["chr1"], [200_000]
+    svs, al = synth.plant_svs(L, 11, spacing=8000, mix={"DEL": 0.5, "INS": 0.5}, size_range=(50, 1500))
+    out["mini_indel"] = (synth.generate(names, L, 400, 11, svs, al, len_mean=5000, len_sd=800, len_min=1000, len_max=9000),
+                         synth.random_genome(names, L, 11), {})
+    # 2. every SV class, contig names chosen so string order != numeric order
+    names, L = ["chr1", "chr10", "chr2"], [150_000, 120_000, 130_000]
+    svs, al = synth.plant_svs(L, 12, spacing=5000, size_range=(50, 1200),
+                              mix={"DEL": 0.2, "INS": 0.2, "INV": 0.15, "DUP_TAN": 0.15, "BND": 0.15, "DUP_INT": 0.15})
+    b2 = synth.generate(names, L, 700, 12, svs, al, len_mean=6000, len_sd=1500, len_min=1500, len_max=12000, p_ins=0.03, p_del=0.02)
+    g2 = synth.random_genome(names, L, 12)
+    out["mini_mixed"] = (b2, g2, {})
+    out["mini_mixed_allbnds"] = (b2, g2, {"all_bnds": True, "min_mapq": 1, "max_sv_size": 3000})
+    # 3. insertion heavy (haplotype edit distance)
+    names, L = ["chr1"], [120_000]
+    svs, al = synth.plant_svs(L, 13, spacing=4000, mix={"INS": 1.0}, ins_size_uniform=(60, 700))
+    out["mini_ins"] = (synth.generate(names, L, 500, 13, svs, al, len_mean=4000, len_sd=800, len_min=1000, len_max=8000, p_ins=0.03, p_del=0.02),
+                       synth.random_genome(names, L, 13), {})
+    # 4. partitions above 100 signatures (host RNG sampling) + dedup
+    names, L = ["chr1"], [60_000]
+    svs, al = synth.plant_svs(L, 14, spacing=6000, hotspots=2, hotspot_svs=(8, 14), size_range=(50, 400))
+    out["mini_hotspot"] = (synth.generate(names, L, 2600, 14, svs, al, len_mean=3000, len_sd=500, len_min=1000, len_max=6000, p_ins=0.02, p_del=0.01),
+                           synth.random_genome(names, L, 14), {})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, (batch, genome, overrides) in fixtures().items():
+        if args.only and name != args.only:
+            continue
+        ref = run_reference(batch, genome, overrides)
+        mine = run_oracle(batch, genome, overrides)
+        for key in ref:
+            if ref[key] != mine[key]:
+                a, b = ref[key], mine[key]
+                if isinstance(a, dict):
+                    for t in a:
+                        if a[t] != b[t]:
+                            for i, (x, y) in enumerate(zip(a[t], b[t])):
+                                if x != y:
+                                    print("first diff", name, key, t, i, "\n ref", x, "\n orc", y); break
+                            print("len", len(a[t]), len(b[t]))
+                else:
+                    for i, (x, y) in enumerate(zip(a, b)):
+                        if x != y:
+                            print("first diff", name, key, i, "\n ref", x, "\n orc", y); break
+                    print("len", len(a), len(b))
+                raise SystemExit("ORACLE != REFERENCE on %s/%s" % (name, key))
+        ref["params"] = overrides
+        ref["n_records"] = batch.n
+        inp = name.replace("_allbnds", "")
+        if inp == name:
+            save_input(os.path.join(GOLDEN, inp + ".input.npz"), batch, genome)
+        ref["input"] = inp + ".input.npz"
+        with gzip.open(os.path.join(GOLDEN, name + ".golden.json.gz"), "wt") as fh:
+            json.dump(ref, fh)
+        from collections import Counter
+        print(name, "records", batch.n, "signatures", dict(Counter(s[0] for s in ref["signatures"])),
+              "twins", len(ref["all_bnds_signatures"]),
+              "clusters", {t: len(v) for t, v in ref["clusters"].items()})
+
+
+if __name__ == "__main__":
+    main()
