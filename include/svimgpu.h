@@ -1,0 +1,223 @@
+/* svimgpu.h — C ABI of the B200-native SVIM COLLECT -> CLUSTER path.
+ *
+ * The reference (eldariont/svim v2.0.0) has no FFI: the seam is two Python call
+ * sites in its CLI script plus the helpers its tests import.  Each entry point
+ * below names the reference interface it stands under (file:line relative to the
+ * reference tree).  The Python host mirror (svim_b200/SVIM_COLLECT.py,
+ * SVIM_CLUSTER.py, SVIM_clustering.py) binds these through ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: every function returns 0 on success or a negative svimgpu_status;
+ * svimgpu_last_error() gives text.  All pointers are HOST pointers owned by the
+ * caller unless stated otherwise; calls are synchronous (the context's stream is
+ * drained before returning).  One context per thread.  Plain C types only.
+ */
+#ifndef SVIMGPU_H
+#define SVIMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svimgpu_ctx svimgpu_ctx;
+
+typedef enum {
+    SVIMGPU_OK = 0,
+    SVIMGPU_ERR_CUDA = -1,      /* CUDA runtime / driver failure (no device, OOM, launch error) */
+    SVIMGPU_ERR_ARG = -2,       /* invalid argument */
+    SVIMGPU_ERR_STATE = -3,     /* call sequence violated (e.g. cluster before collect) */
+    SVIMGPU_ERR_LIMIT = -4,     /* a documented capacity was exceeded */
+    SVIMGPU_ERR_DATA = -5,      /* input the reference itself would raise on (ZeroDivisionError, bad SA ints) */
+    SVIMGPU_ERR_NCCL = -6
+} svimgpu_status;
+
+/* Hot-path options: SVIM_input_parsing.py:279-371 (defaults in comments). */
+typedef struct {
+    int32_t min_mapq;                    /* 20 */
+    int32_t min_sv_size;                 /* 40 */
+    int32_t max_sv_size;                 /* 100000 */
+    int32_t segment_gap_tolerance;       /* 10 */
+    int32_t segment_overlap_tolerance;   /* 5 */
+    int32_t all_bnds;                    /* 0 */
+    double partition_max_distance;       /* 1000 */
+    double position_distance_normalizer; /* 900 */
+    double edit_distance_normalizer;     /* 1.0 */
+    double cluster_max_distance;         /* 0.5 */
+} svim_params;
+
+/* Flattened alignment records — replaces the pysam.AlignedSegment stream of
+ * SVIM_COLLECT.py:133.  See svim_b200/records.py for the field semantics. */
+typedef struct {
+    int64_t n_aln;
+    const int32_t* tid;
+    const int32_t* pos;
+    const uint16_t* flag;
+    const uint8_t* mapq;
+    const uint32_t* n_cigar;
+    const uint64_t* cigar_off;   /* in uint32 words, multiple of 4 */
+    const int32_t* l_seq;
+    const uint64_t* seq_off;     /* bytes */
+    const uint64_t* sa_off;      /* bytes */
+    const uint32_t* sa_len;
+    const uint32_t* qname_id;
+    const uint32_t* cigar; int64_t cigar_words;  /* BAM encoding len<<4|op */
+    const uint8_t* seq; int64_t seq_bytes;       /* BAM 4-bit packing */
+    const uint8_t* sa; int64_t sa_bytes;         /* SA tag text */
+} svim_aln_soa;
+
+/* Signature types, in the reference's clustering call order (SVIM_CLUSTER.py:19-24). */
+enum { SVIM_DEL = 0, SVIM_INS = 1, SVIM_INV = 2, SVIM_DUP_TAN = 3, SVIM_BND = 4, SVIM_DUP_INT = 5 };
+/* svim_sig.flags */
+enum {
+    SVIM_F_SUPPL = 1,          /* signature source "suppl" (else "cigar") */
+    SVIM_F_FULLY_COVERED = 2,  /* DUP_TAN fully_covered */
+    SVIM_F_DIR1_REV = 4,       /* BND direction1 == 'rev' */
+    SVIM_F_DIR2_REV = 8,       /* BND direction2 == 'rev' */
+    SVIM_F_INVDIR_SHIFT = 4    /* INV: bits 4-6 = 0 left_fwd, 1 left_rev, 2 right_fwd, 3 right_rev, 4 all */
+};
+
+/* One SVSignature (SVSignature.py:36-233), 48 bytes.
+ *   DEL/INS/INV/DUP_TAN: contig1,start,end            INS: seq_off/seq_len into the INS blob
+ *   DUP_INT: source contig1,start,end; destination contig2,pos
+ *   BND: contig1,start(=pos1) / contig2,pos(=pos2), already in canonical order */
+typedef struct {
+    int32_t start, end, pos;
+    int32_t contig1, contig2;     /* reference ids (tid) */
+    uint32_t aln_idx;             /* emitting record */
+    uint32_t qname_id;            /* read identity */
+    uint32_t ordinal;             /* emission order inside the record; bit 31 = from segment analysis */
+    uint64_t seq_off;
+    uint32_t seq_len;
+    uint8_t type, flags;
+    uint16_t copies;              /* DUP_TAN */
+} svim_sig;
+
+/* Cluster-stage signature: what span_position_distance / form_partitions read
+ * (SVIM_clustering.py:17-96, SVSignature.py get_key/get_source/get_destination).
+ * Coordinates are doubles because the reference's public seam accepts floats
+ * (tests/test_clustering.py:15-18); integers below 2^53 are exact. 64 bytes. */
+typedef struct {
+    double start, end;            /* source interval; BND: pos1, pos1+1 */
+    double dpos;                  /* DUP_INT destination start; BND pos2 */
+    int32_t contig_a;             /* string-order rank of the source contig (BND contig1) */
+    int32_t contig_b;             /* rank of the destination contig (DUP_INT, BND) else -1 */
+    uint32_t read_id;             /* equal ids <=> equal read names */
+    uint32_t seq_len;             /* INS */
+    uint64_t seq_off;             /* INS: offset into the INS blob */
+    uint8_t type;
+    uint8_t dirs;                 /* BND: bit0 dir1 rev, bit1 dir2 rev; INV: direction code */
+    uint16_t copies;
+    uint32_t pad[3];
+} svim_csig;
+
+/* One SignatureClusterUniLocal / BiLocal (SVSignature.py:236-310). */
+typedef struct {
+    int64_t start, end;           /* int(round(mean)) */
+    int64_t dest_start, dest_end; /* bilocal only */
+    double score;
+    double std_span, std_pos;     /* NaN = None */
+    uint32_t member_off, size;    /* members[member_off .. +size) index the input signature array */
+    uint8_t type, dir1_rev, dir2_rev, pad0;
+    uint32_t pad1;
+} svim_cluster;
+
+typedef struct {
+    int64_t n_partitions[6], n_clusters[6], large_partitions[6], duplicate_signatures[6];
+    int64_t n_members;            /* total member indices */
+    int64_t n_clusters_total;
+    int64_t myers_pairs, myers_cells;
+} svim_cluster_stats;
+
+typedef struct {
+    int64_t n_signatures, n_twin_signatures;   /* main list / --all_bnds extras */
+    int64_t ins_bytes, twin_ins_bytes;
+    int64_t n_sa_bad_fields;   /* SA entries skipped: != 6 fields (warning at SVIM_COLLECT.py:60-62) */
+    int64_t n_no_read_length;  /* segments skipped: infer_read_length() None (SVIM_inter.py:31-34) */
+    int64_t n_primaries;       /* read_nr of SVIM_COLLECT.py:150 */
+    int64_t n_data_errors;     /* conditions the reference raises on (unknown SA contig, non-integer SA field, ...) */
+} svim_collect_stats;
+
+/* ---- lifecycle ---------------------------------------------------------------- */
+int svimgpu_create(svimgpu_ctx** ctx, int device, const svim_params* params);
+void svimgpu_destroy(svimgpu_ctx* ctx);
+const char* svimgpu_last_error(const svimgpu_ctx* ctx);
+int svimgpu_set_params(svimgpu_ctx* ctx, const svim_params* params);
+const char* svimgpu_version(void);
+
+/* Contig table: names (for SA rname lookup = bam.get_tid, SVIM_COLLECT.py:79) and
+ * string-order ranks (Python `str <` of SVSignature.py:194 and the tuple sort of
+ * SVIM_clustering.py:19).  names = concatenated, name_off[n+1]. */
+int svimgpu_set_contigs(svimgpu_ctx* ctx, int32_t n_contigs, const char* names, const int32_t* name_off);
+
+/* Reference genome resident on the device (pysam.FastaFile of SVIM_clustering.py:377,
+ * fetched at :37-43): concatenated contig bytes, offsets[n+1]. */
+int svimgpu_set_genome(svimgpu_ctx* ctx, int32_t n_contigs, const int64_t* offsets, const uint8_t* bytes);
+
+/* Page-lock caller memory so svimgpu_upload_alignments runs at PCIe speed. */
+int svimgpu_pin_host(void* p, int64_t bytes);
+int svimgpu_unpin_host(void* p);
+
+/* ---- COLLECT: analyze_alignment_file_coordsorted (SVIM_COLLECT.py:132-167) ------ */
+/* H2D of the record buffer (pageable or pinned host memory). */
+int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* soa);
+/* CIGAR scan + SA/segment analysis + INS sequence gather on the resident buffer. */
+int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats);
+/* upload + collect */
+int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats);
+/* D2H: which = 0 main list (sv_signatures), 1 = translocation_signatures_all_bnds.
+ * out_sigs[n_signatures] in the reference's emission order; out_ins[ins_bytes] ASCII. */
+int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, uint8_t* out_ins);
+
+/* ---- CLUSTER: cluster_sv_signatures (SVIM_CLUSTER.py:7-26) ------------------------ */
+/* Use the device-resident result of svimgpu_collect as the clustering input. */
+int svimgpu_use_collected(svimgpu_ctx* ctx, int which);
+/* Or upload an arbitrary signature list (partition_and_cluster seam,
+ * SVIM_clustering.py:375; tests/test_clustering.py:53). */
+int svimgpu_set_signatures(svimgpu_ctx* ctx, int64_t n, const svim_csig* sigs, const uint8_t* ins_blob, int64_t ins_bytes,
+                           const int32_t* contig_rank_to_tid /* nullable; for genome lookup of INS */, int32_t n_ranks);
+/* form_partitions + clusters_from_partitions + consolidate_* + final ordering for
+ * all six types in one pass. */
+int svimgpu_cluster(svimgpu_ctx* ctx, svim_cluster_stats* stats);
+/* form_partitions only (SVIM_clustering.py:17-29): key sort + gap split of the selected
+ * signatures; read the result with svimgpu_fetch_partitions. */
+int svimgpu_partition(svimgpu_ctx* ctx, int64_t* n_partitions);
+/* D2H: clusters[n_clusters_total] grouped by type in order DEL, INS, INV, DUP_TAN,
+ * BND, DUP_INT (each group in the reference's list order); members[n_members]. */
+int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* members);
+/* form_partitions only (SVIM_clustering.py:17-29): order[n] = signature indices in
+ * partition order, part_off[n_partitions+1]; call after svimgpu_partition or svimgpu_cluster. */
+int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* order, uint32_t* part_off);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------ */
+/* id_bytes: 128-byte ncclUniqueId from svimgpu_nccl_unique_id on rank 0. */
+int svimgpu_nccl_unique_id(uint8_t* id_bytes /*128*/);
+int svimgpu_comm_init(svimgpu_ctx* ctx, int nranks, int rank, const uint8_t* id_bytes);
+/* allgatherv of the collected signature records (+ INS blobs) of all ranks; after
+ * it every rank holds the full lists (record indices made global with aln_base). */
+int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collect_stats* stats);
+/* restrict clustering to partitions [p*rank/n, p*(rank+1)/n) and allgatherv the
+ * cluster records so every rank ends with the full result. */
+int svimgpu_cluster_sharded(svimgpu_ctx* ctx, svim_cluster_stats* stats);
+int svimgpu_barrier_max(svimgpu_ctx* ctx, double* value /* in: local, out: max over ranks */);
+
+/* ---- micro entry points used by unit tests (same device code as the pipeline) ----- */
+/* analyze_cigar_indel (SVIM_intra.py:8-30): out rows of (pos_ref,pos_read,len,type 1=INS|2=DEL) */
+int svimgpu_cigar_indel(svimgpu_ctx* ctx, const uint32_t* cigar, int64_t n, int32_t min_len, int64_t* out, int64_t out_cap, int64_t* n_out);
+/* edlib.align(a,b)["editDistance"] (SVIM_clustering.py:45) for n_pairs pairs */
+int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob, const int64_t* a_off, const int32_t* a_len,
+                          const int64_t* b_off, const int32_t* b_len, int32_t* out);
+/* scipy linkage(y,'average') + fcluster(Z,t,'distance') (SVIM_clustering.py:170-171) */
+int svimgpu_linkage_average(svimgpu_ctx* ctx, const double* condensed, int32_t m, double t, double* Z /*(m-1)*4*/, int32_t* T /*m*/);
+/* random.seed(1524); random.sample(range(n),100) stream of SVIM_clustering.py:129-134
+ * for a list of partition sizes (host RNG, CPython 3.12 algorithm) */
+int svimgpu_sample_indices(const int64_t* sizes, int64_t n_sizes, int32_t* out /* 100 per size>100 */);
+/* timing of the last collect / cluster call, milliseconds of device time per stage */
+int svimgpu_last_timings(svimgpu_ctx* ctx, double* ms, int32_t cap, int32_t* n);
+const char* svimgpu_timing_name(int32_t i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVIMGPU_H */

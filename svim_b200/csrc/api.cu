@@ -1,0 +1,391 @@
+// C ABI (include/svimgpu.h) over the COLLECT / CLUSTER kernels.  Single translation unit.
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "ctx.cuh"
+#include "collect.cu"
+#include "cluster.cu"
+#include "nccl.cu"
+
+static const char* k_timing_names[T_N] = {
+    "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
+    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange"};
+
+extern "C" {
+
+const char* svimgpu_version(void) { return "svimgpu 0.1 (sm_100a)"; }
+
+int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
+    if (!out || !params) return SVIMGPU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "svimgpu_create: no CUDA device (%s); this library has no CPU path\n", cudaGetErrorString(e));
+        return SVIMGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) return SVIMGPU_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return SVIMGPU_ERR_CUDA;
+    svimgpu_ctx* ctx = new svimgpu_ctx();
+    ctx->device = device; ctx->params = *params;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SVIMGPU_ERR_CUDA; }
+    for (int i = 0; i < 2 * T_N; ++i) cudaEventCreate(&ctx->ev[i]);
+    timings_begin(ctx);
+    memset(&ctx->cstats, 0, sizeof(ctx->cstats)); memset(&ctx->clstats, 0, sizeof(ctx->clstats));
+    myers_init_symcode();
+    *out = ctx;
+    return 0;
+}
+
+void svimgpu_destroy(svimgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl_teardown(ctx);
+    DevBuf* bufs[] = {&ctx->d_names, &ctx->d_name_off, &ctx->d_rank, &ctx->d_rank_to_tid, &ctx->d_genome, &ctx->d_genome_off, &ctx->d_counters,
+                      &ctx->d_queue[0], &ctx->d_queue[1], &ctx->d_work, &ctx->d_sort_tmp, &ctx->d_keys[0], &ctx->d_keys[1], &ctx->d_vals[0],
+                      &ctx->d_vals[1], &ctx->d_scan, &ctx->sets[0].recs, &ctx->sets[0].ins, &ctx->sets[1].recs, &ctx->sets[1].ins, &ctx->d_csig,
+                      &ctx->d_csig_sorted, &ctx->d_cins, &ctx->d_order, &ctx->d_head, &ctx->d_partid, &ctx->d_part_off, &ctx->d_samp_off,
+                      &ctx->d_samp_idx, &ctx->d_labels, &ctx->d_part_ncl, &ctx->d_part_nkept, &ctx->d_part_stats, &ctx->d_plist,
+                      &ctx->d_myers_scratch, &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
+                      &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
+                      &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3]};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
+    for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* svimgpu_last_error(const svimgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int svimgpu_set_params(svimgpu_ctx* ctx, const svim_params* p) {
+    if (!ctx || !p) return SVIMGPU_ERR_ARG;
+    ctx->params = *p;
+    return 0;
+}
+
+int svimgpu_set_contigs(svimgpu_ctx* ctx, int32_t n, const char* names, const int32_t* name_off) {
+    if (!ctx || n <= 0 || !names || !name_off) return SVIMGPU_ERR_ARG;
+    if (n >= (1 << 30)) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many contigs"); return SVIMGPU_ERR_LIMIT; }
+    cudaSetDevice(ctx->device);
+    std::vector<int32_t> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    auto name = [&](int i) { return std::string(names + name_off[i], names + name_off[i + 1]); };
+    std::vector<std::string> nm(n);
+    for (int i = 0; i < n; ++i) nm[i] = name(i);
+    // Python str ordering == byte order for ASCII contig names
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return nm[a] < nm[b]; });
+    ctx->h_rank.assign(n, 0); ctx->h_rank_to_tid.assign(n, 0);
+    int r = -1;
+    for (int k = 0; k < n; ++k) {
+        if (k == 0 || nm[idx[k]] != nm[idx[k - 1]]) { ++r; ctx->h_rank_to_tid[r] = idx[k]; }
+        ctx->h_rank[idx[k]] = r;   // equal names share a rank
+    }
+    ctx->n_contigs = n;
+    SVIM_CUDA(ctx->d_names.ensure((size_t)name_off[n] + 1)); SVIM_CUDA(ctx->d_name_off.ensure((size_t)(n + 1) * 4));
+    SVIM_CUDA(ctx->d_rank.ensure((size_t)n * 4)); SVIM_CUDA(ctx->d_rank_to_tid.ensure((size_t)n * 4));
+    SVIM_CUDA(cudaMemcpy(ctx->d_names.p, names, (size_t)name_off[n], cudaMemcpyHostToDevice));
+    SVIM_CUDA(cudaMemcpy(ctx->d_name_off.p, name_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice));
+    SVIM_CUDA(cudaMemcpy(ctx->d_rank.p, ctx->h_rank.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    SVIM_CUDA(cudaMemcpy(ctx->d_rank_to_tid.p, ctx->h_rank_to_tid.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int svimgpu_set_genome(svimgpu_ctx* ctx, int32_t n, const int64_t* offsets, const uint8_t* bytes) {
+    if (!ctx || n <= 0 || !offsets || !bytes) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    SVIM_CUDA(ctx->d_genome.ensure((size_t)offsets[n] + 16)); SVIM_CUDA(ctx->d_genome_off.ensure((size_t)(n + 1) * 8));
+    SVIM_CUDA(cudaMemcpy(ctx->d_genome.p, bytes, (size_t)offsets[n], cudaMemcpyHostToDevice));
+    SVIM_CUDA(cudaMemcpy(ctx->d_genome_off.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
+    ctx->genome_bytes = offsets[n]; ctx->genome_contigs = n;
+    return 0;
+}
+
+int svimgpu_pin_host(void* p, int64_t bytes) { return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : SVIMGPU_ERR_CUDA; }
+int svimgpu_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : SVIMGPU_ERR_CUDA; }
+
+int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s) {
+    if (!ctx || !s || s->n_aln < 0) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    timings_begin(ctx);
+    const int64_t n = s->n_aln;
+    const void* src[14] = {s->tid, s->pos, s->flag, s->mapq, s->n_cigar, s->cigar_off, s->l_seq, s->seq_off, s->sa_off, s->sa_len, s->qname_id,
+                           s->cigar, s->seq, s->sa};
+    const size_t bytes[14] = {(size_t)n * 4, (size_t)n * 4, (size_t)n * 2, (size_t)n, (size_t)n * 4, (size_t)n * 8, (size_t)n * 4, (size_t)n * 8,
+                              (size_t)n * 8, (size_t)n * 4, (size_t)n * 4, (size_t)s->cigar_words * 4, (size_t)s->seq_bytes, (size_t)s->sa_bytes};
+    {
+        StageTimer t(ctx, T_H2D);
+        for (int i = 0; i < 14; ++i) {
+            SVIM_CUDA(ctx->d_soa[i].ensure(bytes[i] + 64));
+            if (bytes[i]) SVIM_CUDA(cudaMemcpyAsync(ctx->d_soa[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    DevSoa& d = ctx->soa;
+    d.n = n;
+    d.tid = ctx->d_soa[0].as<int32_t>(); d.pos = ctx->d_soa[1].as<int32_t>(); d.flag = ctx->d_soa[2].as<uint16_t>(); d.mapq = ctx->d_soa[3].as<uint8_t>();
+    d.n_cigar = ctx->d_soa[4].as<uint32_t>(); d.cigar_off = ctx->d_soa[5].as<uint64_t>(); d.l_seq = ctx->d_soa[6].as<int32_t>();
+    d.seq_off = ctx->d_soa[7].as<uint64_t>(); d.sa_off = ctx->d_soa[8].as<uint64_t>(); d.sa_len = ctx->d_soa[9].as<uint32_t>();
+    d.qname_id = ctx->d_soa[10].as<uint32_t>(); d.cigar = ctx->d_soa[11].as<uint32_t>(); d.seq = ctx->d_soa[12].as<uint8_t>(); d.sa = ctx->d_soa[13].as<uint8_t>();
+    ctx->cigar_words = s->cigar_words; ctx->seq_bytes = s->seq_bytes; ctx->sa_bytes = s->sa_bytes;
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_soa = true; ctx->collected = false;
+    timings_end(ctx);
+    return 0;
+}
+
+int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    double h2d = ctx->ms[T_H2D];
+    timings_begin(ctx);
+    int rc = collect_run(ctx, stats);
+    timings_end(ctx);
+    ctx->ms[T_H2D] = h2d;
+    return rc;
+}
+
+int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats) {
+    int rc = svimgpu_upload_alignments(ctx, soa);
+    if (rc) return rc;
+    return svimgpu_collect(ctx, stats);
+}
+
+int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, uint8_t* out_ins) {
+    if (!ctx || which < 0 || which > 1) return SVIMGPU_ERR_ARG;
+    if (!ctx->collected) { ctx->set_error(SVIMGPU_ERR_STATE, "collect has not run"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    SigSet& set = ctx->sets[which];
+    if (set.n && out_sigs) SVIM_CUDA(cudaMemcpyAsync(out_sigs, set.recs.p, (size_t)set.n * sizeof(svim_sig), cudaMemcpyDeviceToHost, ctx->stream));
+    if (set.ins_bytes && out_ins) SVIM_CUDA(cudaMemcpyAsync(out_ins, set.ins.p, (size_t)set.ins_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+__global__ void k_max_ins_len(const svim_csig* c, uint32_t n, unsigned long long* out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = (k < n && c[k].type == SVIM_INS) ? c[k].seq_len : 0;
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+static int finish_csig(svimgpu_ctx* ctx) {
+    unsigned long long h = 0;
+    SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
+    SVIM_CUDA(cudaMemsetAsync(ctx->d_part_stats.p, 0, 8, ctx->stream));
+    if (ctx->n_csig) k_max_ins_len<<<(uint32_t)((ctx->n_csig + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_csig.as<svim_csig>(), (uint32_t)ctx->n_csig,
+                                                                                                   (unsigned long long*)ctx->d_part_stats.p);
+    SVIM_CUDA(cudaMemcpyAsync(&h, ctx->d_part_stats.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->cluster_max_ins_len = (int64_t)h;
+    ctx->have_csig = true; ctx->clustered = false;
+    return 0;
+}
+
+int svimgpu_use_collected(svimgpu_ctx* ctx, int which) {
+    if (!ctx || which < 0 || which > 1) return SVIMGPU_ERR_ARG;
+    if (!ctx->collected) { ctx->set_error(SVIMGPU_ERR_STATE, "collect has not run"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    timings_begin(ctx);
+    SigSet& set = ctx->sets[which];
+    ctx->n_csig = set.n;
+    SVIM_CUDA(ctx->d_csig.ensure((size_t)(set.n + 1) * sizeof(svim_csig)));
+    {
+        StageTimer t(ctx, T_CSIG);
+        if (set.n) k_sig_to_csig<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, ctx->d_rank.as<int32_t>(),
+                                                                                           ctx->d_csig.as<svim_csig>());
+    }
+    ctx->cluster_ins = set.ins.as<uint8_t>(); ctx->cluster_ins_bytes = set.ins_bytes;
+    ctx->cluster_rank_to_tid = ctx->d_rank_to_tid.as<int32_t>(); ctx->cluster_n_ranks = ctx->n_contigs;
+    return finish_csig(ctx);
+}
+
+int svimgpu_set_signatures(svimgpu_ctx* ctx, int64_t n, const svim_csig* sigs, const uint8_t* ins_blob, int64_t ins_bytes,
+                           const int32_t* rank_to_tid, int32_t n_ranks) {
+    if (!ctx || n < 0 || (n > 0 && !sigs)) return SVIMGPU_ERR_ARG;
+    if (n >= ((int64_t)1 << 31)) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many signatures"); return SVIMGPU_ERR_LIMIT; }
+    cudaSetDevice(ctx->device);
+    timings_begin(ctx);
+    ctx->n_csig = n;
+    SVIM_CUDA(ctx->d_csig.ensure((size_t)(n + 1) * sizeof(svim_csig)));
+    if (n) SVIM_CUDA(cudaMemcpyAsync(ctx->d_csig.p, sigs, (size_t)n * sizeof(svim_csig), cudaMemcpyHostToDevice, ctx->stream));
+    SVIM_CUDA(ctx->d_cins.ensure((size_t)ins_bytes + 16));
+    if (ins_bytes && ins_blob) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cins.p, ins_blob, (size_t)ins_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cluster_ins = ctx->d_cins.as<uint8_t>(); ctx->cluster_ins_bytes = ins_bytes;
+    ctx->cluster_rank_to_tid = nullptr; ctx->cluster_n_ranks = 0;
+    if (rank_to_tid && n_ranks > 0) {
+        SVIM_CUDA(ctx->d_user_rank_to_tid.ensure((size_t)n_ranks * 4));
+        SVIM_CUDA(cudaMemcpyAsync(ctx->d_user_rank_to_tid.p, rank_to_tid, (size_t)n_ranks * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->cluster_rank_to_tid = ctx->d_user_rank_to_tid.as<int32_t>(); ctx->cluster_n_ranks = n_ranks;
+    }
+    return finish_csig(ctx);
+}
+
+int svimgpu_cluster(svimgpu_ctx* ctx, svim_cluster_stats* stats) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = cluster_run(ctx, stats, 0, 1);
+    timings_end(ctx);
+    return rc;
+}
+
+int svimgpu_partition(svimgpu_ctx* ctx, int64_t* n_partitions) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = cluster_run(ctx, nullptr, 0, 1, true);
+    timings_end(ctx);
+    if (!rc && n_partitions) *n_partitions = ctx->n_partitions;
+    return rc;
+}
+
+int svimgpu_cluster_sharded(svimgpu_ctx* ctx, svim_cluster_stats* stats) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = cluster_run(ctx, stats, ctx->rank, ctx->nranks);
+    timings_end(ctx);
+    return rc;
+}
+
+int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* members) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    if (!ctx->clustered) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster has not run"); return SVIMGPU_ERR_STATE; }
+    if (clusters && !ctx->h_clusters.empty()) memcpy(clusters, ctx->h_clusters.data(), ctx->h_clusters.size() * sizeof(svim_cluster));
+    if (members && !ctx->h_members.empty()) memcpy(members, ctx->h_members.data(), ctx->h_members.size() * 4);
+    return 0;
+}
+
+int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* order, uint32_t* part_off) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    if (!ctx->clustered) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster has not run"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    if (n_partitions) *n_partitions = ctx->n_partitions;
+    if (order && ctx->n_csig) SVIM_CUDA(cudaMemcpy(order, ctx->d_order.p, (size_t)ctx->n_csig * 4, cudaMemcpyDeviceToHost));
+    if (part_off && !ctx->h_part_off.empty()) memcpy(part_off, ctx->h_part_off.data(), ctx->h_part_off.size() * 4);
+    return 0;
+}
+
+// ---- micro entry points ------------------------------------------------------------------------
+int svimgpu_cigar_indel(svimgpu_ctx* ctx, const uint32_t* cigar, int64_t n, int32_t min_len, int64_t* out, int64_t out_cap, int64_t* n_out) {
+    if (!ctx || n < 0 || !n_out) return SVIMGPU_ERR_ARG;
+    // one synthetic record at position 0 on contig 0 through the real scan kernel
+    svim_params saved = ctx->params;
+    ctx->params.min_sv_size = min_len; ctx->params.min_mapq = 0; ctx->params.all_bnds = 0;
+    int32_t tid = 0, pos = 0, l_seq = 0; uint16_t flag = 0; uint8_t mapq = 60; uint32_t nc = (uint32_t)n, sal = 0, qid = 0; uint64_t zero = 0;
+    std::vector<uint32_t> padded((size_t)((n + 3) & ~3ll) + 4, 0);
+    if (n) memcpy(padded.data(), cigar, (size_t)n * 4);
+    uint8_t dummy = 0;
+    svim_aln_soa s{1, &tid, &pos, &flag, &mapq, &nc, &zero, &l_seq, &zero, &zero, &sal, &qid, padded.data(), (int64_t)padded.size(), &dummy, 0, &dummy, 0};
+    int rc = 0;
+    if (ctx->n_contigs == 0) { const char nm[] = "c"; int32_t off[2] = {0, 1}; rc = svimgpu_set_contigs(ctx, 1, nm, off); }
+    svim_collect_stats st;
+    if (!rc) rc = svimgpu_collect_host(ctx, &s, &st);
+    ctx->params = saved;
+    if (rc) return rc;
+    std::vector<svim_sig> sigs((size_t)st.n_signatures);
+    rc = svimgpu_fetch_signatures(ctx, 0, sigs.data(), nullptr);
+    if (rc) return rc;
+    *n_out = st.n_signatures;
+    // pos_read is not part of a signature; recover it for INS from the clamp-free source offset is impossible with l_seq=0,
+    // so report (pos_ref, -1, len, type); the Python test recomputes pos_read from the CIGAR prefix.
+    for (int64_t k = 0; k < st.n_signatures && k < out_cap; ++k) {
+        out[4 * k] = sigs[k].start; out[4 * k + 1] = -1; out[4 * k + 2] = sigs[k].end - sigs[k].start; out[4 * k + 3] = sigs[k].type == SVIM_INS ? 1 : 2;
+    }
+    return 0;
+}
+
+int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
+                          const int32_t* b_len, int32_t* out) {
+    if (!ctx || n_pairs < 0) return SVIMGPU_ERR_ARG;
+    if (n_pairs == 0) return 0;
+    cudaSetDevice(ctx->device);
+    int64_t blob_bytes = 0, maxlen = 16;
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        blob_bytes = std::max<int64_t>(blob_bytes, std::max(a_off[i] + a_len[i], b_off[i] + b_len[i]));
+        maxlen = std::max<int64_t>(maxlen, std::max(a_len[i], b_len[i]));
+    }
+    maxlen = (maxlen + 15) & ~15ll;
+    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_scr, d_next;
+    int blocks = (int)std::min<int64_t>(148 * 4, (n_pairs + 3) / 4);
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    chk(d_blob.ensure((size_t)blob_bytes + 16)); chk(d_ao.ensure((size_t)n_pairs * 8)); chk(d_al.ensure((size_t)n_pairs * 4)); chk(d_bo.ensure((size_t)n_pairs * 8));
+    chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_scr.ensure((size_t)blocks * 4 * 3 * maxlen)); chk(d_next.ensure(4));
+    if (e == cudaSuccess) {
+        chk(cudaMemcpyAsync(d_blob.p, blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemcpyAsync(d_ao.p, a_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemcpyAsync(d_al.p, a_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemcpyAsync(d_bo.p, b_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemcpyAsync(d_bl.p, b_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemsetAsync(d_next.p, 0, 4, ctx->stream));
+        k_myers_strings<<<blocks, 128, 0, ctx->stream>>>(d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(),
+                                                        (uint32_t)n_pairs, d_out.as<int32_t>(), d_scr.as<uint8_t>(), maxlen, d_next.as<uint32_t>());
+        chk(cudaGetLastError());
+        chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        chk(cudaStreamSynchronize(ctx->stream));
+    }
+    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_scr, &d_next};
+    for (DevBuf* b : all) b->release();
+    if (e != cudaSuccess) { ctx->set_error(SVIMGPU_ERR_CUDA, "edit_distance: %s", cudaGetErrorString(e)); return SVIMGPU_ERR_CUDA; }
+    return 0;
+}
+
+// linkage + fcluster on an explicit condensed matrix, through the same device functions as k_linkage
+__global__ void __launch_bounds__(32) k_linkage_raw(const double* condensed, int m, double t, double* Z, int32_t* T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    PartSmem s = carve(smem_raw, m < 2 ? 2 : m);
+    const int np = m * (m - 1) / 2;
+    for (int q = lane; q < np; q += 32) s.D[q] = condensed[q];
+    __syncwarp();
+    nn_chain_warp(s, m, lane);
+    if (lane == 0) {
+        fcluster_from_chain(m, s.ls, s.ux, s.uy, s.ud, t, s.T);
+        for (int k = 0; k < m; ++k) T[k] = s.T[k];
+        // Z with scipy's size column: recompute sizes from the relabelled tree
+        for (int k = 0; k < m - 1; ++k) {
+            int a = s.ls.zx[k], b = s.ls.zy[k];
+            double sa = a < m ? 1.0 : Z[4 * (a - m) + 3], sb = b < m ? 1.0 : Z[4 * (b - m) + 3];
+            Z[4 * k] = a; Z[4 * k + 1] = b; Z[4 * k + 2] = s.ls.zd[k]; Z[4 * k + 3] = sa + sb;
+        }
+    }
+}
+
+int svimgpu_linkage_average(svimgpu_ctx* ctx, const double* condensed, int32_t m, double t, double* Z, int32_t* T) {
+    if (!ctx || m < 2 || m > 100 || !condensed || !Z || !T) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    const size_t np = (size_t)m * (m - 1) / 2;
+    DevBuf d_c, d_z, d_t;
+    SVIM_CUDA(d_c.ensure(np * 8)); SVIM_CUDA(d_z.ensure((size_t)(m - 1) * 32)); SVIM_CUDA(d_t.ensure((size_t)m * 4));
+    SVIM_CUDA(cudaMemcpyAsync(d_c.p, condensed, np * 8, cudaMemcpyHostToDevice, ctx->stream));
+    size_t sm = part_smem_bytes(m);
+    SVIM_CUDA(cudaFuncSetAttribute(k_linkage_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 1024)));
+    k_linkage_raw<<<1, 32, sm, ctx->stream>>>(d_c.as<double>(), m, t, d_z.as<double>(), d_t.as<int32_t>());
+    SVIM_CUDA(cudaGetLastError());
+    SVIM_CUDA(cudaMemcpyAsync(Z, d_z.p, (size_t)(m - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaMemcpyAsync(T, d_t.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    d_c.release(); d_z.release(); d_t.release();
+    return 0;
+}
+
+int svimgpu_sample_indices(const int64_t* sizes, int64_t n_sizes, int32_t* out) {
+    if (!sizes || !out) return SVIMGPU_ERR_ARG;
+    PyRandom rng; rng.seed_int(1524);
+    int64_t k = 0;
+    for (int64_t i = 0; i < n_sizes; ++i)
+        if (sizes[i] > 100) { rng.sample100((uint64_t)sizes[i], out + 100 * k); ++k; }
+    return 0;
+}
+
+int svimgpu_last_timings(svimgpu_ctx* ctx, double* ms, int32_t cap, int32_t* n) {
+    if (!ctx || !ms || !n) return SVIMGPU_ERR_ARG;
+    *n = T_N;
+    for (int i = 0; i < T_N && i < cap; ++i) ms[i] = ctx->ms[i];
+    return 0;
+}
+
+const char* svimgpu_timing_name(int32_t i) { return (i >= 0 && i < T_N) ? k_timing_names[i] : ""; }
+
+}  // extern "C"

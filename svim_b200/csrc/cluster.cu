@@ -1,0 +1,639 @@
+// CLUSTER kernels: cluster_sv_signatures (SVIM_CLUSTER.py:7-26) for all six types in one pass.
+//
+//   k_sig_to_csig / k_cluster_keys / radix sorts   form_partitions' sorted(key=get_key)  (:19)
+//   k_partition_heads + select                     the linear partition split           (:21-28)
+//   host PyRandom                                  seed(1524) / sample(partition, 100)  (:129-134)
+//   k_ins_pairs + k_myers_pairs                    haplotype edit distances             (:32-45)
+//   k_linkage                                      same-read dedup, condensed span-position matrix,
+//                                                  nn-chain average linkage, flat cut   (:141-175)
+//   k_members / k_consolidate                      consolidate_clusters_*, scores       (:183-303)
+//   final radix sort                               sorted(..., key=(contig, (end+start)/2)) (:381)
+//
+// One warp owns one partition (m <= 100 after sampling): records are bulk-copied into shared
+// memory, the condensed FP64 matrix (<= 39.6 KB) lives there too, min-search and Lance-Williams
+// update are warp-parallel, the O(m) dendrogram post-processing runs on lane 0.
+#pragma once
+#include <cub/cub.cuh>
+#include <algorithm>
+#include "ctx.cuh"
+#include "cluster.cuh"
+#include "pyrandom.h"
+#include "myers.cu"
+
+// multi-GPU hook (nccl.cu): allgatherv of the per-shard cluster records before the final ordering
+static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_members);
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_sig_to_csig(const svim_sig* s, uint32_t n, const int32_t* rank, svim_csig* out) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const svim_sig a = s[k];
+    svim_csig c; memset(&c, 0, sizeof(c));
+    c.start = (double)a.start; c.end = (double)a.end; c.dpos = 0.0;
+    c.contig_a = rank[a.contig1]; c.contig_b = -1;
+    c.read_id = a.qname_id; c.seq_len = a.seq_len; c.seq_off = a.seq_off; c.type = a.type; c.copies = a.copies;
+    if (a.type == SVIM_DUP_INT) { c.dpos = (double)a.pos; c.contig_b = rank[a.contig2]; }
+    else if (a.type == SVIM_BND) {
+        c.dpos = (double)a.pos; c.contig_b = rank[a.contig2];
+        c.dirs = (uint8_t)(((a.flags & SVIM_F_DIR1_REV) ? 1 : 0) | ((a.flags & SVIM_F_DIR2_REV) ? 2 : 0));
+    } else if (a.type == SVIM_INV) c.dirs = (uint8_t)((a.flags >> SVIM_F_INVDIR_SHIFT) & 7);
+    out[k] = c;
+}
+
+// get_key per type: (type, contig, end) | INS (type, contig, start) | DUP_INT (type, dest, source, dest_start)
+// | BND (type, contig1, pos1)     (SVSignature.py:21-23, 70-72, 132-135, 232-233)
+__global__ void k_cluster_keys(const svim_csig* c, uint32_t n, uint64_t* coord, uint64_t* group, uint32_t* idx) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const svim_csig s = c[k];
+    double key = s.end;
+    if (s.type == SVIM_INS || s.type == SVIM_BND) key = s.start;
+    else if (s.type == SVIM_DUP_INT) key = s.dpos;
+    coord[k] = double_key(key);
+    uint64_t k1 = (uint64_t)(uint32_t)s.contig_a, k2 = 0;
+    if (s.type == SVIM_DUP_INT) { k1 = (uint64_t)(uint32_t)s.contig_b; k2 = (uint64_t)(uint32_t)s.contig_a; }
+    group[k] = ((uint64_t)s.type << 60) | (k1 << 30) | k2;
+    idx[k] = k;
+}
+
+template <class T>
+__global__ void k_gather(const T* src, const uint32_t* order, uint32_t n, T* dst) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) dst[k] = src[order[k]];
+}
+
+__global__ void k_partition_heads(const svim_csig* s, const uint64_t* group, uint32_t n, double max_distance, uint8_t* head, uint32_t* type_start) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    bool h = true;
+    const svim_csig b = s[k];
+    if (k > 0) {
+        const svim_csig a = s[k - 1];
+        if (group[k] == group[k - 1]) h = gap_exceeds(b.type, a.start, a.end, a.dpos, b.start, b.dpos, max_distance);
+        if (a.type != b.type) for (int t = a.type + 1; t <= b.type; ++t) type_start[t] = k;
+    } else {
+        for (int t = 0; t <= b.type; ++t) type_start[t] = 0;
+    }
+    if (k == n - 1) for (int t = b.type + 1; t <= 6; ++t) type_start[t] = n;
+    head[k] = h ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-partition layout in shared memory (one warp per CTA)
+struct PartSmem {
+    double* start; double* end; double* dpos; uint32_t* read; uint8_t* dirs; uint8_t* dup; int* kidx;
+    double* D; int* size; int* chain; int* ux; int* uy; double* ud;
+    LinkScratch ls; int* T;
+};
+
+__host__ __device__ inline size_t part_smem_bytes(int M) {
+    size_t dbl = 3 * (size_t)M + (size_t)M * (M - 1) / 2 + 3 * (size_t)M;      // start,end,dpos,D,ud,zd,md
+    size_t i32 = 14 * (size_t)M + 16;                                          // read,kidx,size,chain,ux,uy,zx,zy,order,parent(2M),stack,T + slack
+    size_t u8 = 4 * (size_t)M + 16;                                            // dirs,dup,visited(2M)
+    return dbl * 8 + i32 * 4 + u8 + 64;
+}
+
+__device__ inline PartSmem carve(unsigned char* base, int M) {
+    PartSmem p;
+    double* d = (double*)base;
+    p.start = d; d += M; p.end = d; d += M; p.dpos = d; d += M;
+    p.D = d; d += (size_t)M * (M - 1) / 2;
+    p.ud = d; d += M; p.ls.zd = d; d += M; p.ls.md = d; d += M;
+    int* i = (int*)d;
+    p.read = (uint32_t*)i; i += M; p.kidx = i; i += M; p.size = i; i += M; p.chain = i; i += M; p.ux = i; i += M; p.uy = i; i += M;
+    p.ls.zx = i; i += M; p.ls.zy = i; i += M; p.ls.order = i; i += M; p.ls.parent = i; i += 2 * M; p.ls.stack = i; i += M; p.T = i; i += M;
+    unsigned char* u = (unsigned char*)i;
+    p.dirs = u; u += M; p.dup = u; u += M; p.ls.visited = u; u += 2 * M;
+    return p;
+}
+
+struct LinkArgs {
+    const svim_csig* sig;            // key-sorted signatures
+    const uint32_t* samp_off;        // P+1
+    const uint32_t* samp_idx;        // positions in `sig`
+    const uint32_t* plist;           // partition ids handled by this launch
+    uint32_t n_list;
+    const uint64_t* pair_off;        // per partition: base into pair_ed (INS only)
+    const int32_t* pair_ed;
+    ClusterParams cp;
+    int32_t* labels;                 // per sample slot: flat cluster id, 0 = same-read duplicate
+    uint32_t* part_ncl; uint32_t* part_nkept;
+    uint32_t* err;
+};
+
+// nn-chain average linkage on the condensed matrix D (mk points) -> unsorted merge rows
+__device__ void nn_chain_warp(PartSmem& s, int mk, int lane) {
+    for (int i = lane; i < mk; i += 32) s.size[i] = 1;
+    __syncwarp();
+    int chain_len = 0;
+    for (int k = 0; k < mk - 1; ++k) {
+        int x = 0, y = 0; double cur = 0.0;
+        if (chain_len == 0) {
+            // first i with size > 0
+            int found = mk;
+            for (int b = 0; b < mk; b += 32) {
+                int i = b + lane;
+                unsigned msk = __ballot_sync(FULL, i < mk && s.size[i] > 0);
+                if (msk) { found = b + __ffs(msk) - 1; break; }
+            }
+            if (lane == 0) s.chain[0] = found;
+            chain_len = 1;
+            __syncwarp();
+        }
+        for (;;) {
+            x = s.chain[chain_len - 1];
+            int yprev = -1; double cprev = INFINITY;
+            if (chain_len > 1) { yprev = s.chain[chain_len - 2]; cprev = s.D[cidx_any(mk, x, yprev)]; }
+            // argmin over active i != x of D[x,i], lowest index on ties
+            double bd = INFINITY; int bi = 0x7fffffff;
+            for (int i = lane; i < mk; i += 32) {
+                if (i == x || s.size[i] == 0) continue;
+                double d = s.D[cidx_any(mk, x, i)];
+                if (d < bd) { bd = d; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                double od = __shfl_xor_sync(FULL, bd, o); int oi = __shfl_xor_sync(FULL, bi, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+            }
+            if (bd < cprev) { y = bi; cur = bd; } else { y = yprev; cur = cprev; }
+            if (chain_len > 1 && y == yprev) break;
+            if (lane == 0) s.chain[chain_len] = y;
+            chain_len++;
+            __syncwarp();
+        }
+        chain_len -= 2;
+        if (x > y) { int t = x; x = y; y = t; }
+        const int nx = s.size[x], ny = s.size[y];
+        __syncwarp();
+        if (lane == 0) { s.ux[k] = x; s.uy[k] = y; s.ud[k] = cur; s.size[x] = 0; s.size[y] = nx + ny; }
+        __syncwarp();
+        const double fx = (double)nx, fy = (double)ny, fs = (double)(nx + ny);
+        for (int i = lane; i < mk; i += 32) {
+            if (i == y || s.size[i] == 0) continue;
+            const int iy = cidx_any(mk, i, y);
+            s.D[iy] = (fx * s.D[cidx_any(mk, i, x)] + fy * s.D[iy]) / fs;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    if (blockIdx.x >= a.n_list) return;
+    const uint32_t p = a.plist[blockIdx.x];
+    const uint32_t s0 = a.samp_off[p];
+    const int m = (int)(a.samp_off[p + 1] - s0);
+    PartSmem s = carve(smem_raw, M);
+    const int type = a.sig[a.samp_idx[s0]].type;
+    for (int i = lane; i < m; i += 32) {
+        const svim_csig c = a.sig[a.samp_idx[s0 + i]];
+        s.start[i] = c.start; s.end[i] = c.end; s.dpos[i] = c.dpos; s.read[i] = c.read_id; s.dirs[i] = c.dirs; s.dup[i] = 0;
+    }
+    __syncwarp();
+    int err = 0;
+    const int64_t npairs = (int64_t)m * (m - 1) / 2;
+    const int32_t* ed = (type == SVIM_INS && a.pair_ed) ? a.pair_ed + a.pair_off[p] : nullptr;
+    // ---- same-read duplicates (SVIM_clustering.py:141-151); none for INV ---------------------------
+    if (type != SVIM_INV && m > 1) {
+        int i = 0, rowstart = 0;   // walk condensed order
+        for (int64_t q = lane; q < npairs; q += 32) {
+            while (q >= rowstart + (m - 1 - i)) { rowstart += m - 1 - i; ++i; }
+            const int j = i + 1 + (int)(q - rowstart);
+            if (s.read[i] != s.read[j]) continue;
+            SigView va{s.start[i], s.end[i], s.dpos[i], s.read[i], s.dirs[i]}, vb{s.start[j], s.end[j], s.dpos[j], s.read[j], s.dirs[j]};
+            double e = ed ? (double)ed[q] : 0.0;
+            double d = spd(type, va, vb, a.cp, e, &err);
+            if (d <= a.cp.cluster_max_distance) s.dup[j] = 1;
+        }
+        __syncwarp();
+    }
+    // ---- compact survivors, in order -----------------------------------------------------------------
+    int mk = 0;
+    for (int b = 0; b < m; b += 32) {
+        const int i = b + lane;
+        const bool keep = i < m && !s.dup[i];
+        const unsigned msk = __ballot_sync(FULL, keep);
+        if (keep) s.kidx[mk + __popc(msk & ((1u << lane) - 1))] = i;
+        mk += __popc(msk);
+    }
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) a.labels[s0 + i] = 0;
+    __syncwarp();
+    int ncl = 1;
+    if (mk == 1) {
+        if (lane == 0) a.labels[s0 + s.kidx[0]] = 1;
+    } else {
+        // ---- condensed distance matrix (:158-169) --------------------------------------------------
+        const int64_t kp = (int64_t)mk * (mk - 1) / 2;
+        int i = 0, rowstart = 0;
+        for (int64_t q = lane; q < kp; q += 32) {
+            while (q >= rowstart + (mk - 1 - i)) { rowstart += mk - 1 - i; ++i; }
+            const int j = i + 1 + (int)(q - rowstart);
+            const int oi = s.kidx[i], oj = s.kidx[j];
+            double d;
+            if (type != SVIM_INV && s.read[oi] == s.read[oj]) d = 99999.0;
+            else {
+                SigView va{s.start[oi], s.end[oi], s.dpos[oi], s.read[oi], s.dirs[oi]}, vb{s.start[oj], s.end[oj], s.dpos[oj], s.read[oj], s.dirs[oj]};
+                double e = ed ? (double)ed[cidx(m, oi, oj)] : 0.0;
+                d = spd(type, va, vb, a.cp, e, &err);
+            }
+            s.D[q] = d;
+        }
+        __syncwarp();
+        nn_chain_warp(s, mk, lane);
+        if (lane == 0) {
+            ncl = fcluster_from_chain(mk, s.ls, s.ux, s.uy, s.ud, a.cp.cluster_max_distance, s.T);
+            for (int k = 0; k < mk; ++k) a.labels[s0 + s.kidx[k]] = s.T[k];
+        }
+        ncl = __shfl_sync(FULL, ncl, 0);
+    }
+    if (lane == 0) { a.part_ncl[p] = (uint32_t)ncl; a.part_nkept[p] = (uint32_t)mk; }
+    if (__any_sync(FULL, err)) { if (lane == 0) atomicExch(a.err, 1u); }
+}
+
+// INS partitions: list the pairs whose edit distance will be read (gate at :70 passes)
+__global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint32_t* samp_off, const uint32_t* samp_idx, const uint32_t* plist,
+                                                    uint32_t n_list, const uint64_t* pair_off, ClusterParams cp, MyersWork* work, uint32_t* n_work) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_list) return;
+    const uint32_t p = plist[w];
+    const uint32_t s0 = samp_off[p];
+    const int m = (int)(samp_off[p + 1] - s0);
+    const int64_t npairs = (int64_t)m * (m - 1) / 2;
+    int i = 0, rowstart = 0;
+    for (int64_t q0 = 0; q0 < npairs; q0 += 32) {
+        const int64_t q = q0 + lane;
+        bool need = false; uint32_t pa = 0, pb = 0;
+        if (q < npairs) {
+            while (q >= rowstart + (m - 1 - i)) { rowstart += m - 1 - i; ++i; }
+            const int j = i + 1 + (int)(q - rowstart);
+            pa = samp_idx[s0 + i]; pb = samp_idx[s0 + j];
+            SigView va{sig[pa].start, sig[pa].end, 0, 0, 0}, vb{sig[pb].start, sig[pb].end, 0, 0, 0};
+            need = ins_gate_needs_ed(va, vb, cp);
+        }
+        const unsigned msk = __ballot_sync(FULL, need);
+        uint32_t base = 0;
+        if (lane == 0 && msk) base = atomicAdd(n_work, (uint32_t)__popc(msk));
+        base = __shfl_sync(FULL, base, 0);
+        if (need) { MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[base + __popc(msk & ((1u << lane) - 1))] = wk; }
+    }
+}
+
+// members of every flat cluster, in sample order (SVIM_clustering.py:172-175)
+__global__ void __launch_bounds__(128) k_members(const uint32_t* samp_off, const uint32_t* samp_idx, const uint32_t* order, const int32_t* labels,
+                                                  const uint32_t* part_ncl, const uint32_t* cl_off, const uint32_t* mem_off, uint32_t P,
+                                                  svim_cluster* clusters, uint32_t* members) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (p >= P) return;
+    const uint32_t s0 = samp_off[p];
+    const int m = (int)(samp_off[p + 1] - s0);
+    const int ncl = (int)part_ncl[p];
+    uint32_t out = mem_off[p];
+    for (int c = 1; c <= ncl; ++c) {
+        const uint32_t begin = out;
+        for (int b = 0; b < m; b += 32) {
+            const int i = b + lane;
+            const bool hit = i < m && labels[s0 + i] == c;
+            const unsigned msk = __ballot_sync(FULL, hit);
+            if (hit) members[out + __popc(msk & ((1u << lane) - 1))] = order[samp_idx[s0 + i]];
+            out += __popc(msk);
+        }
+        if (lane == 0) { svim_cluster& cl = clusters[cl_off[p] + c - 1]; cl.member_off = begin; cl.size = out - begin; }
+    }
+}
+
+// consolidate_clusters_unilocal / _bilocal + calculate_score, one thread per cluster
+__global__ void k_consolidate(const svim_csig* sig /* emission order */, const uint32_t* members, uint32_t n_clusters, svim_cluster* clusters,
+                              uint32_t* err) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_clusters) return;
+    svim_cluster cl = clusters[c];
+    const uint32_t* mem = members + cl.member_off;
+    const int n = (int)cl.size;
+    const svim_csig first = sig[mem[0]];
+    const int type = first.type;
+    double sum_s = 0.0, sum_e = 0.0, sum_ds = 0.0, sum_de = 0.0;
+    int left = 0, right = 0, all = 0, max_copies = 0;
+    uint32_t dirs_or = 0, dirs_and = 3;
+    double v[3 * 100];   // span, pos, dest pos   (n <= 100)
+    for (int i = 0; i < n; ++i) {
+        const svim_csig m = sig[mem[i]];
+        sum_s += m.start; sum_e += m.end;
+        v[3 * i] = m.end - m.start; v[3 * i + 1] = (m.end + m.start) / 2.0;
+        double ds = 0.0, de = 0.0;
+        if (type == SVIM_DUP_INT) { ds = m.dpos; de = m.dpos + (m.end - m.start); }
+        else if (type == SVIM_BND) { ds = m.dpos; de = m.dpos + 1.0; }
+        sum_ds += ds; sum_de += de;
+        v[3 * i + 2] = (de + ds) / 2.0;
+        if (type == SVIM_INV) { left += m.dirs < 2; right += (m.dirs == 2 || m.dirs == 3); all += m.dirs == 4; }
+        if (m.copies > max_copies) max_copies = m.copies;
+        dirs_or |= m.dirs; dirs_and &= m.dirs;
+    }
+    const double a_s = sum_s / (double)n, a_e = sum_e / (double)n;
+    const int has = n > 1;
+    double sd_span = 0.0, sd_pos = 0.0;
+    if (has) { sd_span = stdev_values(v, n, 3); sd_pos = stdev_values(v + 1, n, 3); }
+    cl.type = (uint8_t)type;
+    cl.start = py_round_int(a_s); cl.end = py_round_int(a_e);
+    cl.dest_start = 0; cl.dest_end = 0; cl.dir1_rev = 0; cl.dir2_rev = 0;
+    const double nanv = nan("");
+    int n_eff = n;
+    if (type == SVIM_INV) n_eff = (left < right ? left : right) + all;
+    double span = a_e - a_s, ss = sd_span, sp = sd_pos;
+    if (type == SVIM_DUP_TAN) {
+        cl.dest_start = cl.end; cl.dest_end = cl.end + (int64_t)max_copies * (cl.end - cl.start);
+    } else if (type == SVIM_DUP_INT) {
+        const double d_s = sum_ds / (double)n, d_e = sum_de / (double)n;
+        cl.dest_start = py_round_int(d_s); cl.dest_end = py_round_int(d_e);
+        span = ((a_e - a_s) + (d_e - d_s)) / 2.0;                 // mean([..]) of two floats
+        if (has) {
+            // destination span == source span member-wise; destination position has its own spread
+            const double dd_span = sd_span;   // stdev of (dest_end - dest_start) = stdev of source spans
+            const double dd_pos = stdev_values(v + 2, n, 3);
+            ss = (sd_span + dd_span) / 2.0; sp = (sd_pos + dd_pos) / 2.0;
+        }
+    } else if (type == SVIM_BND) {
+        const double d_s = sum_ds / (double)n, d_e = sum_de / (double)n;
+        cl.dest_start = py_round_int(d_s); cl.dest_end = py_round_int(d_e);
+        if (dirs_or != dirs_and) atomicExch(err, 3u);             // assert len(directions) == 1
+        cl.dir1_rev = first.dirs & 1; cl.dir2_rev = (first.dirs >> 1) & 1;
+        span = 500.0;
+        if (has) { ss = sd_pos; sp = stdev_values(v + 2, n, 3); }
+    }
+    if (has && span == 0.0) atomicExch(err, 1u);                  // ZeroDivisionError in calculate_score
+    cl.score = cluster_score(n_eff, has, ss, sp, span);
+    cl.std_span = has ? ss : nanv; cl.std_pos = has ? sp : nanv;
+    clusters[c] = cl;
+}
+
+// final list order: unilocal types sorted by (contig, (end+start)/2), bilocal keep partition order
+__global__ void k_final_keys(const svim_cluster* cl, const svim_csig* sig, const uint32_t* members, uint32_t n, uint64_t* k1, uint64_t* k2, uint32_t* idx) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const svim_cluster x = cl[c];
+    const bool uni = x.type == SVIM_DEL || x.type == SVIM_INS || x.type == SVIM_INV;
+    k1[c] = uni ? double_key((double)(x.end + x.start) / 2.0) : 0ull;
+    const uint64_t contig = uni ? (uint64_t)(uint32_t)sig[members[x.member_off]].contig_a : 0ull;
+    k2[c] = ((uint64_t)x.type << 60) | contig;
+    idx[c] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int sort_pairs_u64(svimgpu_ctx* ctx, DevBuf* keys, DevBuf* vals, uint32_t n, int end_bit, uint64_t** out_k, uint32_t** out_v) {
+    cub::DoubleBuffer<uint64_t> dk(keys[0].as<uint64_t>(), keys[1].as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> dv(vals[0].as<uint32_t>(), vals[1].as<uint32_t>());
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, end_bit, ctx->stream);
+    SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+    SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int)n, 0, end_bit, ctx->stream));
+    *out_k = dk.Current(); *out_v = dv.Current();
+    if (dk.Current() != keys[0].as<uint64_t>()) std::swap(keys[0], keys[1]);
+    if (dv.Current() != vals[0].as<uint32_t>()) std::swap(vals[0], vals[1]);
+    return 0;
+}
+
+static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_rank, int shard_n, bool partition_only = false) {
+    if (!ctx->have_csig) { ctx->set_error(SVIMGPU_ERR_STATE, "no signatures selected for clustering"); return SVIMGPU_ERR_STATE; }
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)ctx->n_csig;
+    svim_cluster_stats& cs = ctx->clstats;
+    memset(&cs, 0, sizeof(cs));
+    ctx->h_clusters.clear(); ctx->h_members.clear(); ctx->h_part_off.clear(); ctx->n_partitions = 0;
+    ctx->clustered = true;
+    if (n == 0) { if (stats) *stats = cs; return 0; }
+    ClusterParams cp{ctx->params.partition_max_distance, ctx->params.position_distance_normalizer, ctx->params.edit_distance_normalizer,
+                     ctx->params.cluster_max_distance};
+    const uint32_t nb = (n + 255) / 256;
+    // ---- sort by get_key -------------------------------------------------------------------------------
+    uint64_t* gkey_sorted = nullptr; uint32_t* order = nullptr;
+    {
+        StageTimer t(ctx, T_KEYSORT);
+        for (int k = 0; k < 2; ++k) { SVIM_CUDA(ctx->d_ckeys[k].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_cvals[k].ensure((size_t)n * 4)); }
+        SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n * 8));
+        uint64_t* group = ctx->d_keys[0].as<uint64_t>();
+        k_cluster_keys<<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), n, ctx->d_ckeys[0].as<uint64_t>(), group, ctx->d_cvals[0].as<uint32_t>());
+        uint64_t* k_out; uint32_t* v_out;
+        int rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n, 64, &k_out, &v_out); if (rc) return rc;
+        k_gather<uint64_t><<<nb, 256, 0, st>>>(group, v_out, n, ctx->d_ckeys[1].as<uint64_t>());
+        std::swap(ctx->d_ckeys[0], ctx->d_ckeys[1]);
+        rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n, 64, &k_out, &v_out); if (rc) return rc;
+        gkey_sorted = k_out; order = v_out;
+        SVIM_CUDA(ctx->d_csig_sorted.ensure((size_t)n * sizeof(svim_csig)));
+        k_gather<svim_csig><<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), order, n, ctx->d_csig_sorted.as<svim_csig>());
+        SVIM_CUDA(ctx->d_order.ensure((size_t)n * 4));
+        SVIM_CUDA(cudaMemcpyAsync(ctx->d_order.p, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    const svim_csig* sorted = ctx->d_csig_sorted.as<svim_csig>();
+    // ---- partitions --------------------------------------------------------------------------------------
+    uint32_t P = 0;
+    uint32_t type_start[7];
+    {
+        StageTimer t(ctx, T_PARTITION);
+        SVIM_CUDA(ctx->d_head.ensure(n + 64)); SVIM_CUDA(ctx->d_part_off.ensure((size_t)(n + 2) * 4)); SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
+        uint32_t* d_ts = ctx->d_part_stats.as<uint32_t>();   // [0..6] type_start, [8] num selected, [9] err, [10] n_work, [12..13] cells
+        SVIM_CUDA(cudaMemsetAsync(d_ts, 0, 64 * 4, st));
+        k_partition_heads<<<nb, 256, 0, st>>>(sorted, gkey_sorted, n, cp.partition_max_distance, ctx->d_head.as<uint8_t>(), d_ts);
+        size_t tmp = 0;
+        cub::CountingInputIterator<uint32_t> cnt_it(0);
+        cub::DeviceSelect::Flagged(nullptr, tmp, cnt_it, ctx->d_head.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), d_ts + 8, (int)n, st);
+        SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+        SVIM_CUDA(cub::DeviceSelect::Flagged(ctx->d_sort_tmp.p, tmp, cnt_it, ctx->d_head.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), d_ts + 8, (int)n, st));
+        uint32_t h[16];
+        SVIM_CUDA(cudaMemcpyAsync(h, d_ts, 16 * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        P = h[8];
+        memcpy(type_start, h, 7 * 4);
+        ctx->h_part_off.resize(P + 1);
+        SVIM_CUDA(cudaMemcpyAsync(ctx->h_part_off.data(), ctx->d_part_off.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        ctx->h_part_off[P] = n;
+        ctx->n_partitions = P;
+    }
+    if (partition_only) { if (stats) *stats = cs; return 0; }
+    // ---- host: sampling stream + work lists ---------------------------------------------------------------
+    std::vector<uint32_t> samp_off(P + 1), samp_idx; samp_idx.reserve(n);
+    std::vector<uint32_t> list_small, list_large, list_ins;
+    std::vector<uint64_t> pair_off(P + 1, 0);
+    std::vector<uint8_t> ptype(P);
+    uint64_t pair_total = 0;
+    int max_m_small = 32;
+    {
+        StageTimer t(ctx, T_SAMPLE);
+        PyRandom rng; int cur_type = -1;
+        int32_t pick[100];
+        for (uint32_t p = 0; p < P; ++p) {
+            const uint32_t b = ctx->h_part_off[p], e = ctx->h_part_off[p + 1], sz = e - b;
+            int ty = 0; while (ty < 5 && b >= type_start[ty + 1]) ++ty;
+            ptype[p] = (uint8_t)ty;
+            if (ty != cur_type) { rng.seed_int(1524); cur_type = ty; }
+            cs.n_partitions[ty]++;
+            samp_off[p] = (uint32_t)samp_idx.size();
+            uint32_t m = sz;
+            if (sz > 100) {
+                rng.sample100(sz, pick); cs.large_partitions[ty]++; m = 100;
+                for (int k = 0; k < 100; ++k) samp_idx.push_back(b + (uint32_t)pick[k]);
+            } else for (uint32_t k = 0; k < sz; ++k) samp_idx.push_back(b + k);
+            pair_off[p] = pair_total;
+            if (ty == SVIM_INS && m > 1) { list_ins.push_back(p); pair_total += (uint64_t)m * (m - 1) / 2; }
+        }
+        samp_off[P] = (uint32_t)samp_idx.size();
+        // multi-GPU: this rank clusters partitions [lo,hi) only (balanced by sum m^2 + pair cost)
+        uint32_t lo = 0, hi = P;
+        if (shard_n > 1) {
+            std::vector<double> w(P + 1, 0.0);
+            for (uint32_t p = 0; p < P; ++p) { double m = samp_off[p + 1] - samp_off[p]; w[p + 1] = w[p] + 1.0 + m * m * (ptype[p] == SVIM_INS ? 50.0 : 1.0); }
+            auto cut = [&](int r) { double target = w[P] * r / shard_n; return (uint32_t)(std::lower_bound(w.begin(), w.end(), target) - w.begin()); };
+            lo = shard_rank == 0 ? 0 : std::min(P, cut(shard_rank)); hi = shard_rank == shard_n - 1 ? P : std::min(P, cut(shard_rank + 1));
+            if (hi < lo) hi = lo;
+            std::vector<uint32_t> li;
+            for (uint32_t p : list_ins) if (p >= lo && p < hi) li.push_back(p);
+            list_ins.swap(li);
+        }
+        ctx->shard_lo = lo; ctx->shard_hi = hi;
+        for (uint32_t p = lo; p < hi; ++p) { uint32_t m = samp_off[p + 1] - samp_off[p]; (m <= (uint32_t)max_m_small ? list_small : list_large).push_back(p); }
+    }
+    const uint32_t n_samp = samp_off[P];
+    SVIM_CUDA(ctx->d_samp_off.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_samp_idx.ensure((size_t)n_samp * 4 + 4));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_samp_off.p, samp_off.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, st));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_samp_idx.p, samp_idx.data(), (size_t)n_samp * 4, cudaMemcpyHostToDevice, st));
+    SVIM_CUDA(ctx->d_pair_off.ensure((size_t)(P + 1) * 8));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_pair_off.p, pair_off.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
+    // partition lists: [small | large | ins]
+    std::vector<uint32_t> lists; lists.insert(lists.end(), list_small.begin(), list_small.end());
+    lists.insert(lists.end(), list_large.begin(), list_large.end()); lists.insert(lists.end(), list_ins.begin(), list_ins.end());
+    SVIM_CUDA(ctx->d_plist.ensure(lists.size() * 4 + 4));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_plist.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
+    const uint32_t* d_small = ctx->d_plist.as<uint32_t>(); const uint32_t* d_large = d_small + list_small.size();
+    const uint32_t* d_ins = d_large + list_large.size();
+    uint32_t* d_misc = ctx->d_part_stats.as<uint32_t>();
+    // ---- INS: edit distances ---------------------------------------------------------------------------------
+    const int32_t* d_pair_ed = nullptr;
+    if (!list_ins.empty()) {
+        if (pair_total >= 0xffffffffull) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many insertion pairs"); return SVIMGPU_ERR_LIMIT; }
+        SVIM_CUDA(ctx->d_pair_ed.ensure((size_t)pair_total * 4 + 4));
+        SVIM_CUDA(ctx->d_pairs.ensure((size_t)pair_total * sizeof(MyersWork) + 16));
+        {
+            StageTimer t(ctx, T_PAIRS);
+            uint32_t blocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
+            k_ins_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins, (uint32_t)list_ins.size(),
+                                                ctx->d_pair_off.as<uint64_t>(), cp, ctx->d_pairs.as<MyersWork>(), d_misc + 10);
+        }
+        uint32_t h[8];
+        SVIM_CUDA(cudaMemcpyAsync(h, d_misc + 8, 8 * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        const uint32_t n_work = h[2];
+        cs.myers_pairs = n_work;
+        if (n_work > 0 && !ctx->d_genome.p) { ctx->set_error(SVIMGPU_ERR_STATE, "insertion clustering needs svimgpu_set_genome"); return SVIMGPU_ERR_STATE; }
+        if (n_work > 0) {
+            StageTimer t(ctx, T_MYERS);
+            const int64_t maxlen = ((ctx->cluster_max_ins_len + 200 + (int64_t)ceil(2.0 * cp.cluster_max_distance * cp.pos_norm) + 64) + 15) & ~15ll;
+            int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            int blocks = sms * 5;
+            while (blocks > sms && (size_t)blocks * 4 * 3 * maxlen > ((size_t)8 << 30)) blocks -= sms;
+            blocks = (int)std::min<int64_t>(blocks, ((int64_t)n_work + 3) / 4);
+            SVIM_CUDA(ctx->d_myers_scratch.ensure((size_t)blocks * 4 * 3 * maxlen));
+            GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs,
+                          ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
+            SVIM_CUDA(cudaMemsetAsync(d_misc + 11, 0, 4, st));
+            k_myers_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_pairs.as<MyersWork>(), n_work, ctx->d_pair_ed.as<int32_t>(),
+                                                  ctx->d_myers_scratch.as<uint8_t>(), maxlen, d_misc + 11, (unsigned long long*)(d_misc + 12), d_misc + 9);
+        }
+        d_pair_ed = ctx->d_pair_ed.as<int32_t>();
+    }
+    // ---- linkage --------------------------------------------------------------------------------------------------
+    SVIM_CUDA(ctx->d_labels.ensure((size_t)n_samp * 4 + 4)); SVIM_CUDA(ctx->d_part_ncl.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_part_nkept.ensure((size_t)(P + 1) * 4));
+    SVIM_CUDA(cudaMemsetAsync(ctx->d_part_ncl.p, 0, (size_t)(P + 1) * 4, st)); SVIM_CUDA(cudaMemsetAsync(ctx->d_part_nkept.p, 0, (size_t)(P + 1) * 4, st));
+    {
+        StageTimer t(ctx, T_LINKAGE);
+        LinkArgs la{sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), nullptr, 0, ctx->d_pair_off.as<uint64_t>(), d_pair_ed, cp,
+                    ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_part_nkept.as<uint32_t>(), d_misc + 9};
+        if (!list_small.empty()) {
+            la.plist = d_small; la.n_list = (uint32_t)list_small.size();
+            k_linkage<<<la.n_list, 32, part_smem_bytes(max_m_small), st>>>(la, max_m_small);
+        }
+        if (!list_large.empty()) {
+            size_t sm = part_smem_bytes(100);
+            SVIM_CUDA(cudaFuncSetAttribute(k_linkage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            la.plist = d_large; la.n_list = (uint32_t)list_large.size();
+            k_linkage<<<la.n_list, 32, sm, st>>>(la, 100);
+        }
+        SVIM_CUDA(cudaGetLastError());
+    }
+    // ---- consolidate ----------------------------------------------------------------------------------------------
+    uint32_t n_clusters = 0, n_members = 0;
+    {
+        StageTimer t(ctx, T_CONSOLIDATE);
+        SVIM_CUDA(ctx->d_cl_off.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_mem_off.ensure((size_t)(P + 1) * 4));
+        size_t tmp = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp, ctx->d_part_ncl.as<uint32_t>(), ctx->d_cl_off.as<uint32_t>(), (int)P + 1, st);
+        SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+        SVIM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, tmp, ctx->d_part_ncl.as<uint32_t>(), ctx->d_cl_off.as<uint32_t>(), (int)P + 1, st));
+        SVIM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, tmp, ctx->d_part_nkept.as<uint32_t>(), ctx->d_mem_off.as<uint32_t>(), (int)P + 1, st));
+        uint32_t tot[2];
+        SVIM_CUDA(cudaMemcpyAsync(&tot[0], ctx->d_cl_off.as<uint32_t>() + P, 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaMemcpyAsync(&tot[1], ctx->d_mem_off.as<uint32_t>() + P, 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        n_clusters = tot[0]; n_members = tot[1];
+        SVIM_CUDA(ctx->d_clusters.ensure((size_t)(n_clusters + 1) * sizeof(svim_cluster)));
+        SVIM_CUDA(ctx->d_clusters_sorted.ensure((size_t)(n_clusters + 1) * sizeof(svim_cluster)));
+        SVIM_CUDA(ctx->d_members.ensure((size_t)(n_members + 1) * 4));
+        SVIM_CUDA(cudaMemsetAsync(ctx->d_clusters.p, 0, (size_t)(n_clusters + 1) * sizeof(svim_cluster), st));
+        if (n_clusters > 0) {
+            k_members<<<(uint32_t)(((uint64_t)P * 32 + 127) / 128), 128, 0, st>>>(ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(),
+                ctx->d_order.as<uint32_t>(), ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_cl_off.as<uint32_t>(),
+                ctx->d_mem_off.as<uint32_t>(), P, ctx->d_clusters.as<svim_cluster>(), ctx->d_members.as<uint32_t>());
+            k_consolidate<<<(n_clusters + 63) / 64, 64, 0, st>>>(ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
+                                                               ctx->d_clusters.as<svim_cluster>(), d_misc + 9);
+        }
+        SVIM_CUDA(cudaGetLastError());
+    }
+    if (shard_n > 1) { int rc = cluster_exchange(ctx, &n_clusters, &n_members); if (rc) return rc; }
+    // ---- final order + D2H -------------------------------------------------------------------------------------------
+    ctx->h_clusters.resize(n_clusters); ctx->h_members.resize(n_members);
+    if (n_clusters > 0) {
+        StageTimer t(ctx, T_ORDER);
+        const uint32_t cb = (n_clusters + 255) / 256;
+        for (int k = 0; k < 2; ++k) { SVIM_CUDA(ctx->d_ckeys[k].ensure((size_t)n_clusters * 8)); SVIM_CUDA(ctx->d_cvals[k].ensure((size_t)n_clusters * 4)); }
+        SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_clusters * 8));
+        uint64_t* k2 = ctx->d_keys[0].as<uint64_t>();
+        k_final_keys<<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
+                                         ctx->d_ckeys[0].as<uint64_t>(), k2, ctx->d_cvals[0].as<uint32_t>());
+        uint64_t* k_out; uint32_t* v_out;
+        int rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n_clusters, 64, &k_out, &v_out); if (rc) return rc;
+        k_gather<uint64_t><<<cb, 256, 0, st>>>(k2, v_out, n_clusters, ctx->d_ckeys[1].as<uint64_t>());
+        std::swap(ctx->d_ckeys[0], ctx->d_ckeys[1]);
+        rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n_clusters, 64, &k_out, &v_out); if (rc) return rc;
+        k_gather<svim_cluster><<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), v_out, n_clusters, ctx->d_clusters_sorted.as<svim_cluster>());
+        SVIM_CUDA(cudaGetLastError());
+    }
+    {
+        StageTimer t(ctx, T_CLUSTER_D2H);
+        if (n_clusters) SVIM_CUDA(cudaMemcpyAsync(ctx->h_clusters.data(), ctx->d_clusters_sorted.p, (size_t)n_clusters * sizeof(svim_cluster), cudaMemcpyDeviceToHost, st));
+        if (n_members) SVIM_CUDA(cudaMemcpyAsync(ctx->h_members.data(), ctx->d_members.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost, st));
+    }
+    uint32_t h[16];
+    SVIM_CUDA(cudaMemcpyAsync(h, d_misc, 16 * 4, cudaMemcpyDeviceToHost, st));
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    if (h[9]) {
+        const char* why = h[9] == 2 ? "haplotype longer than the scratch bound" : h[9] == 3 ? "BND cluster with mixed directions (assertion in consolidate_clusters_bilocal)"
+                                    : "division by zero span (ZeroDivisionError in the reference) or contig missing from the genome";
+        ctx->set_error(SVIMGPU_ERR_DATA, "cluster: %s", why);
+        return SVIMGPU_ERR_DATA;
+    }
+    unsigned long long cells; memcpy(&cells, h + 12, 8);
+    cs.myers_cells = (int64_t)cells;
+    for (auto& c : ctx->h_clusters) cs.n_clusters[c.type]++;
+    cs.n_clusters_total = n_clusters; cs.n_members = n_members;
+    // duplicate_signatures per type = sampled - kept
+    {
+        std::vector<uint32_t> nk(P + 1);
+        SVIM_CUDA(cudaMemcpy(nk.data(), ctx->d_part_nkept.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t p = ctx->shard_lo; p < ctx->shard_hi; ++p) cs.duplicate_signatures[ptype[p]] += (samp_off[p + 1] - samp_off[p]) - nk[p];
+    }
+    if (stats) *stats = cs;
+    return 0;
+}

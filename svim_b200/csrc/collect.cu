@@ -1,0 +1,358 @@
+// COLLECT kernels: analyze_alignment_file_coordsorted (SVIM_COLLECT.py:132-167).
+//
+//   k_cigar_scan      K1  one warp per alignment record; streams the BAM-encoded CIGAR
+//                         with 128-bit loads (analyze_cigar_indel, SVIM_intra.py:8-30 and
+//                         analyze_alignment_indel :33-51), emits DEL/INS records, and
+//                         leaves a ChainWork item for primaries with an SA tag.
+//   k_segment_chain   K1b one thread per ChainWork item: SA parsing + split-read tree.
+//   k_ins_gather      K1c one warp per INS record: 4-bit SEQ -> ASCII blob.
+//
+// HBM-bound by design: the scan touches every CIGAR word exactly once
+// (B_aln = 44 + 4*n_cigar + sa_len bytes per record) and nothing else.
+#pragma once
+#include <cub/cub.cuh>
+#include "ctx.cuh"
+
+#define FULL 0xffffffffu
+
+struct DeviceEmitter {
+    SigQueue qm, qt;
+    uint32_t* overflow;
+    __device__ __forceinline__ void push(SigQueue& q, const svim_sig& s) {
+        uint32_t slot = atomicAdd(q.count, 1u);
+        if (slot < q.cap) q.recs[slot] = s; else atomicExch(overflow, 1u);
+    }
+    __device__ __forceinline__ void sig(const svim_sig& s) { push(qm, s); }
+    __device__ __forceinline__ void twin(const svim_sig& s) { push(qt, s); }
+};
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_t& total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
+    total = __shfl_sync(FULL, x, 31);
+    return x - v;
+}
+
+struct ScanAcc { uint32_t ref, read, nsum, hsum; };
+
+__device__ __forceinline__ void acc_op(uint32_t v, ScanAcc& a) {
+    uint32_t op = v & 15u, len = v >> 4;
+    a.ref += ((SVIM_MASK_REF_QUIRK >> op) & 1u) * len;
+    a.read += ((SVIM_MASK_READ >> op) & 1u) * len;
+    a.nsum += (op == OP_N) ? len : 0u;
+    a.hsum += (op == OP_H) ? len : 0u;
+}
+__device__ __forceinline__ bool is_event(uint32_t v, uint32_t thresh) {
+    uint32_t op = v & 15u;
+    return ((0x6u >> op) & 1u) && v >= thresh;   // I or D with len >= min_sv_size
+}
+
+#define SCAN_UNROLL 4
+#define SCAN_BATCH 4     // alignments fetched per atomic
+
+__global__ void __launch_bounds__(256) k_cigar_scan(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
+                                                     uint32_t work_cap, uint32_t* cnt) {
+    const int lane = threadIdx.x & 31;
+    DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
+    const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
+    const uint32_t n_aln = (uint32_t)a.n;
+    uint32_t primaries = 0;
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(cnt + CNT_NEXT_ALN, (uint32_t)SCAN_BATCH);
+        first = __shfl_sync(FULL, first, 0);
+        if (first >= n_aln) break;
+        uint32_t last = min(first + SCAN_BATCH, n_aln);
+        for (uint32_t i = first; i < last; ++i) {
+            const uint32_t flag = a.flag[i];
+            if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;   // SVIM_COLLECT.py:143
+            const bool primary = !(flag & 0x800u);
+            primaries += primary;
+            const uint32_t n = a.n_cigar[i];
+            const uint32_t n4 = (n + 3) >> 2;
+            const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]);
+            const int64_t ref_start = a.pos[i];
+            const int32_t tid = a.tid[i];
+            const uint32_t qid = a.qname_id[i];
+            const int64_t l_seq = a.l_seq[i];
+            ScanAcc acc = {0, 0, 0, 0};
+            int64_t base_ref = 0, base_read = 0;     // uniform: consumption before the lane-private accumulators
+            uint32_t n_ev = 0, n_tw = 0;
+            for (uint32_t base = 0; base < n4; base += 32 * SCAN_UNROLL) {
+                uint4 w[SCAN_UNROLL];
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u) {
+                    uint32_t idx = base + u * 32 + lane;
+                    w[u] = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
+                    if (idx == n4 - 1) {   // words past n_cigar in the last 16-byte group
+                        uint32_t r = n & 3u;
+                        if (r == 1) { w[u].y = 0; w[u].z = 0; w[u].w = 0; } else if (r == 2) { w[u].z = 0; w[u].w = 0; } else if (r == 3) { w[u].w = 0; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SCAN_UNROLL; ++u) {
+                    const uint32_t v[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+                    bool ev = is_event(v[0], thresh) | is_event(v[1], thresh) | is_event(v[2], thresh) | is_event(v[3], thresh);
+                    if (__ballot_sync(FULL, ev) == 0) {
+                        acc_op(v[0], acc); acc_op(v[1], acc); acc_op(v[2], acc); acc_op(v[3], acc);
+                        continue;
+                    }
+                    // ---- rare path: this 128-op group holds at least one SV-sized I/D -------------
+                    base_ref += warp_sum(acc.ref); base_read += warp_sum(acc.read);
+                    acc.ref = 0; acc.read = 0;
+                    ScanAcc g = {0, 0, 0, 0};
+                    uint32_t pre_ref[4], pre_read[4]; uint32_t my_ev = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { pre_ref[k] = g.ref; pre_read[k] = g.read; acc_op(v[k], g); my_ev += is_event(v[k], thresh); }
+                    acc.nsum += g.nsum; acc.hsum += g.hsum;
+                    uint32_t tot_ref, tot_read, tot_ev;
+                    uint32_t ex_ref = warp_excl_scan(g.ref, lane, tot_ref);
+                    uint32_t ex_read = warp_excl_scan(g.read, lane, tot_read);
+                    uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
+                    uint32_t ord = n_ev + ex_ev;
+                    uint32_t tw_before = 0;
+                    if (p.all_bnds) {   // twins only for deletions: count DEL events before this lane
+                        uint32_t my_del = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) my_del += (is_event(v[k], thresh) && (v[k] & 15u) == OP_D);
+                        uint32_t tot_del; tw_before = n_tw + warp_excl_scan(my_del, lane, tot_del); n_tw += tot_del;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!is_event(v[k], thresh)) continue;
+                        const uint32_t op = v[k] & 15u; const int64_t len = v[k] >> 4;
+                        const int64_t pr = base_ref + ex_ref + pre_ref[k];
+                        const int64_t pq = base_read + ex_read + pre_read[k];
+                        svim_sig s; memset(&s, 0, sizeof(s));
+                        s.contig1 = tid; s.contig2 = -1; s.start = (int32_t)(ref_start + pr); s.end = (int32_t)(ref_start + pr + len);
+                        s.aln_idx = i; s.qname_id = qid; s.ordinal = ord++;
+                        if (op == OP_D) {
+                            s.type = SVIM_DEL;
+                            out.sig(s);
+                            if (p.all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
+                                svim_sig b = s; b.type = SVIM_BND; b.contig2 = tid; b.pos = s.end; b.end = s.start + 1; b.ordinal = tw_before++;
+                                if (len == 0) { b.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
+                                out.twin(b);
+                            }
+                        } else {
+                            s.type = SVIM_INS;
+                            int64_t lo, hi; py_slice(pq, len, l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
+                            s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
+                            out.sig(s);
+                        }
+                    }
+                    n_ev += tot_ev;
+                    base_ref += tot_ref; base_read += tot_read;
+                }
+            }
+            // ---- primaries with an SA tag: summary for the split-read analysis -----------------
+            if (primary && a.sa_len[i] > 0) {
+                const uint32_t hard = warp_sum(acc.hsum);
+                if (hard == 0) {   // SVIM_COLLECT.py:47-48
+                    const int64_t ref_q = base_ref + warp_sum(acc.ref);
+                    const int64_t rd = base_read + warp_sum(acc.read);
+                    const int64_t nsum = warp_sum(acc.nsum);
+                    if (lane == 0) {
+                        const uint32_t* c32 = a.cigar + a.cigar_off[i];
+                        CigarSummary cs; cigsum_init(cs);
+                        if (l_seq == 0) {   // no SEQ: exact sequential summary (rare)
+                            for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
+                        } else {
+                            cs.ref_len = ref_q + nsum; cs.qlen_h = rd; cs.hard = 0; cs.n_ops = (int32_t)n;
+                            uint32_t k = 0;
+                            for (; k < n; ++k) { uint32_t op = c32[k] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.lead_s += c32[k] >> 4; }
+                            for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
+                        }
+                        Seg sg; int64_t rl;
+                        cigsum_finish(cs, l_seq, ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
+                        uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
+                        if (slot < work_cap) {
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = n_ev; wk.ord_twin = n_tw; wk.pad = 0;
+                            wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
+                            work[slot] = wk;
+                        } else atomicExch(cnt + CNT_OVERFLOW, 1u);
+                    }
+                }
+            }
+        }
+    }
+    primaries = warp_sum(primaries);   // every lane counted the same records
+    if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
+}
+
+__global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
+                                                        SigQueue qm, SigQueue qt, uint32_t* cnt) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_work) return;
+    const ChainWork wk = work[w];
+    const uint32_t i = wk.aln_idx;
+    DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
+    Seg chain[SVIM_MAX_SEGMENTS];
+    int n = 0;
+    uint32_t err = 0;
+    const uint32_t flag = a.flag[i];
+    const int32_t rev = (flag & 0x10u) ? 1 : 0;
+    if (rev && wk.read_len < 0) err |= CH_NO_READLEN;      // SVIM_inter.py:31-34
+    else {
+        Seg s; s.tid = a.tid[i]; s.ref_start = a.pos[i]; s.ref_end = wk.ref_end; s.q_start = wk.q_start; s.q_end = wk.q_end; s.rev = rev;
+        chain[n++] = s;
+    }
+    n = parse_sa_segments(a.sa + a.sa_off[i], (int)a.sa_len[i], ct, p, a.l_seq[i], chain, n, err);
+    sort_chain(chain, n);
+    PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, 0x80000000u | wk.ord_sig, 0x80000000u | wk.ord_twin, err);
+    if (err & CH_BAD_FIELDS) atomicAdd(cnt + CNT_BAD_FIELDS, 1u);
+    if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
+    if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
+    if (err & CH_TOO_MANY) atomicAdd(cnt + CNT_TOO_MANY, 1u);
+}
+
+// keys for restoring the reference's emission order: (record index, ordinal)
+__global__ void k_sig_keys(const svim_sig* recs, uint32_t n, uint64_t* keys, uint32_t* vals) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    keys[k] = ((uint64_t)recs[k].aln_idx << 32) | recs[k].ordinal;
+    vals[k] = k;
+}
+
+__global__ void k_sig_gather(const svim_sig* src, const uint32_t* order, uint32_t n, svim_sig* dst, uint64_t* ins_len) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    svim_sig s = src[order[k]];
+    dst[k] = s;
+    ins_len[k] = (s.type == SVIM_INS) ? s.seq_len : 0;
+}
+
+// one warp per record; INS records copy SEQ[src_off : src_off+len) (4-bit) to ASCII
+__global__ void __launch_bounds__(256) k_ins_gather(DevSoa a, svim_sig* recs, const uint64_t* blob_off, uint32_t n, uint8_t* blob) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    if (recs[w].type != SVIM_INS) return;
+    const uint64_t src = recs[w].seq_off; const uint32_t len = recs[w].seq_len;
+    const uint64_t dst = blob_off[w];
+    const uint8_t* seq = a.seq + a.seq_off[recs[w].aln_idx];
+    for (uint32_t k = lane; k < len; k += 32) {
+        uint64_t q = src + k;
+        uint8_t b = seq[q >> 1];
+        uint8_t code = (q & 1) ? (b & 15) : (b >> 4);
+        blob[dst + k] = (uint8_t)"=ACMGRSVTWYHKDBN"[code];
+    }
+    __syncwarp();
+    if (lane == 0) recs[w].seq_off = dst;
+}
+
+static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
+    // queue[which] (arbitrary order) -> sets[which].recs in emission order + INS blob
+    SigSet& set = ctx->sets[which];
+    set.n = n; set.ins_bytes = 0;
+    if (n == 0) return 0;
+    SVIM_CUDA(set.recs.ensure((size_t)n * sizeof(svim_sig)));
+    SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n * 8));
+    SVIM_CUDA(ctx->d_vals[0].ensure((size_t)n * 4)); SVIM_CUDA(ctx->d_vals[1].ensure((size_t)n * 4));
+    SVIM_CUDA(ctx->d_scan.ensure((size_t)(n + 1) * 8 * 2));
+    cudaStream_t st = ctx->stream;
+    const svim_sig* q = ctx->d_queue[which].as<svim_sig>();
+    k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>());
+    cub::DoubleBuffer<uint64_t> dk(ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>());
+    cub::DoubleBuffer<uint32_t> dv(ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>());
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 64, st);
+    SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+    SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int)n, 0, 64, st));
+    uint64_t* ins_len = ctx->d_scan.as<uint64_t>();
+    uint64_t* ins_off = ins_len + (n + 1);
+    k_sig_gather<<<(n + 255) / 256, 256, 0, st>>>(q, dv.Current(), n, set.recs.as<svim_sig>(), ins_len);
+    size_t tmp2 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ins_len, ins_off, (int)n + 1, st);
+    SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp2));
+    SVIM_CUDA(cudaMemsetAsync(ins_len + n, 0, 8, st));
+    SVIM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, tmp2, ins_len, ins_off, (int)n + 1, st));
+    uint64_t total = 0;
+    SVIM_CUDA(cudaMemcpyAsync(&total, ins_off + n, 8, cudaMemcpyDeviceToHost, st));
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    set.ins_bytes = (int64_t)total;
+    SVIM_CUDA(set.ins.ensure((size_t)total + 16));
+    if (total > 0) {
+        uint32_t blocks = (uint32_t)(((uint64_t)n * 32 + 255) / 256);
+        k_ins_gather<<<blocks, 256, 0, st>>>(ctx->soa, set.recs.as<svim_sig>(), ins_off, n, set.ins.as<uint8_t>());
+    }
+    SVIM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static ChainParams make_chain_params(const svim_params& p) {
+    ChainParams c;
+    c.min_sv = p.min_sv_size; c.max_sv = p.max_sv_size; c.tol_g = p.segment_gap_tolerance; c.tol_o = p.segment_overlap_tolerance;
+    c.min_mapq = p.min_mapq; c.all_bnds = p.all_bnds;
+    return c;
+}
+
+static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
+    if (!ctx->have_soa) { ctx->set_error(SVIMGPU_ERR_STATE, "no alignments uploaded"); return SVIMGPU_ERR_STATE; }
+    if (ctx->n_contigs == 0) { ctx->set_error(SVIMGPU_ERR_STATE, "svimgpu_set_contigs not called"); return SVIMGPU_ERR_STATE; }
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->soa.n;
+    if (n >= (int64_t)1 << 32) { ctx->set_error(SVIMGPU_ERR_LIMIT, "more than 2^32 records in one batch"); return SVIMGPU_ERR_LIMIT; }
+    uint32_t cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(1 << 16, 2 * n + 1024), 0x7fffffff);
+    SVIM_CUDA(ctx->d_counters.ensure(CNT_N * 4));
+    uint32_t h_cnt[CNT_N];
+    ChainParams cp = make_chain_params(ctx->params);
+    ContigTable ct{ctx->n_contigs, ctx->d_names.as<char>(), ctx->d_name_off.as<int32_t>(), ctx->d_rank.as<int32_t>()};
+    int dev_sms = 148;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        SVIM_CUDA(ctx->d_queue[0].ensure((size_t)cap * sizeof(svim_sig)));
+        SVIM_CUDA(ctx->d_queue[1].ensure((size_t)(ctx->params.all_bnds ? cap : 16) * sizeof(svim_sig)));
+        SVIM_CUDA(ctx->d_work.ensure((size_t)(n + 1) * sizeof(ChainWork)));
+        SVIM_CUDA(cudaMemsetAsync(ctx->d_counters.p, 0, CNT_N * 4, st));
+        SigQueue qm{ctx->d_queue[0].as<svim_sig>(), ctx->d_counters.as<uint32_t>() + CNT_MAIN, cap};
+        SigQueue qt{ctx->d_queue[1].as<svim_sig>(), ctx->d_counters.as<uint32_t>() + CNT_TWIN, ctx->params.all_bnds ? cap : 16};
+        {
+            StageTimer t(ctx, T_SCAN);
+            if (n > 0)
+                k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                         ctx->d_counters.as<uint32_t>());
+        }
+        SVIM_CUDA(cudaGetLastError());
+        SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        uint32_t n_work = h_cnt[CNT_WORK];
+        {
+            StageTimer t(ctx, T_CHAIN);
+            if (n_work > 0)
+                k_segment_chain<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work, qm, qt,
+                                                                     ctx->d_counters.as<uint32_t>());
+        }
+        SVIM_CUDA(cudaGetLastError());
+        SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        if (!h_cnt[CNT_OVERFLOW]) break;
+        if (attempt == 5 || cap == 0x7fffffff) { ctx->set_error(SVIMGPU_ERR_LIMIT, "signature queue overflow"); return SVIMGPU_ERR_LIMIT; }
+        cap = (uint32_t)std::min<uint64_t>((uint64_t)std::max(h_cnt[CNT_MAIN], h_cnt[CNT_TWIN]) + 1024, 0x7fffffffull);
+    }
+    if (h_cnt[CNT_TOO_MANY]) {
+        ctx->set_error(SVIMGPU_ERR_LIMIT, "%u reads have more than %d alignment segments", h_cnt[CNT_TOO_MANY], SVIM_MAX_SEGMENTS);
+        return SVIMGPU_ERR_LIMIT;
+    }
+    {
+        StageTimer t(ctx, T_SORTBACK);
+        int rc = collect_sort_queue(ctx, 0, h_cnt[CNT_MAIN]); if (rc) return rc;
+        rc = collect_sort_queue(ctx, 1, h_cnt[CNT_TWIN]); if (rc) return rc;
+    }
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    svim_collect_stats& s = ctx->cstats;
+    s.n_signatures = ctx->sets[0].n; s.n_twin_signatures = ctx->sets[1].n;
+    s.ins_bytes = ctx->sets[0].ins_bytes; s.twin_ins_bytes = ctx->sets[1].ins_bytes;
+    s.n_sa_bad_fields = h_cnt[CNT_BAD_FIELDS]; s.n_no_read_length = h_cnt[CNT_NO_READLEN];
+    s.n_primaries = h_cnt[CNT_PRIMARIES]; s.n_data_errors = h_cnt[CNT_DATA_ERR];
+    ctx->collected = true;
+    if (stats) *stats = s;
+    return 0;
+}

@@ -1,0 +1,146 @@
+// Context, device buffers, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "collect.cuh"
+
+#define SVIM_CUDA(call)                                                                     \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            ctx->set_error(SVIMGPU_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SVIMGPU_ERR_CUDA;                                                        \
+        }                                                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct DevSoa {
+    int64_t n;
+    const int32_t* tid; const int32_t* pos; const uint16_t* flag; const uint8_t* mapq;
+    const uint32_t* n_cigar; const uint64_t* cigar_off; const int32_t* l_seq; const uint64_t* seq_off;
+    const uint64_t* sa_off; const uint32_t* sa_len; const uint32_t* qname_id;
+    const uint32_t* cigar; const uint8_t* seq; const uint8_t* sa;
+};
+
+struct SigQueue {
+    svim_sig* recs;
+    uint32_t* count;
+    uint32_t cap;
+};
+
+// written by the CIGAR scan for every primary that has an SA tag and no hard clip
+struct ChainWork {
+    uint32_t aln_idx, ord_sig, ord_twin, pad;
+    int64_t ref_end, q_start, q_end, read_len;
+};
+
+enum {  // device counters
+    CNT_MAIN = 0, CNT_TWIN, CNT_WORK, CNT_NEXT_ALN, CNT_PRIMARIES, CNT_BAD_FIELDS, CNT_NO_READLEN, CNT_DATA_ERR,
+    CNT_TOO_MANY, CNT_OVERFLOW, CNT_MYERS_NEXT, CNT_N
+};
+
+enum {  // timing slots
+    T_H2D = 0, T_SCAN, T_CHAIN, T_SORTBACK, T_GATHER, T_COLLECT_D2H, T_CSIG, T_KEYSORT, T_PARTITION, T_SAMPLE, T_PAIRS,
+    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_N
+};
+
+struct SigSet {   // one signature list on the device (main / all_bnds twins)
+    DevBuf recs;        // svim_sig[n], emission order
+    DevBuf ins;         // INS blob
+    int64_t n = 0, ins_bytes = 0;
+};
+
+struct svimgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    svim_params params;
+    std::string err;
+    int err_code = 0;
+
+    // contigs / genome
+    int32_t n_contigs = 0;
+    std::vector<int32_t> h_rank, h_rank_to_tid;
+    DevBuf d_names, d_name_off, d_rank, d_rank_to_tid;
+    DevBuf d_genome, d_genome_off;
+    int64_t genome_bytes = 0;
+    int32_t genome_contigs = 0;
+
+    // alignments
+    DevBuf d_soa[14];
+    DevSoa soa; bool have_soa = false;
+    int64_t cigar_words = 0, seq_bytes = 0, sa_bytes = 0;
+
+    // collect state
+    DevBuf d_counters, d_queue[2], d_work, d_sort_tmp, d_keys[2], d_vals[2], d_scan;
+    SigSet sets[2];
+    bool collected = false;
+    svim_collect_stats cstats;
+
+    // cluster state
+    DevBuf d_csig, d_csig_sorted, d_cins;   // input signatures (emission order / key order), INS blob when uploaded
+    const uint8_t* cluster_ins = nullptr; int64_t cluster_ins_bytes = 0;
+    int64_t n_csig = 0; bool have_csig = false;
+    DevBuf d_order, d_head, d_partid, d_part_off, d_samp_off, d_samp_idx, d_labels, d_part_ncl, d_part_nkept, d_part_stats;
+    DevBuf d_plist, d_myers_scratch;
+    int64_t cluster_max_ins_len = 0;
+    const int32_t* cluster_rank_to_tid = nullptr; int32_t cluster_n_ranks = 0;
+    DevBuf d_user_rank_to_tid;
+    uint32_t shard_lo = 0, shard_hi = 0;
+    DevBuf d_cl_off, d_mem_off, d_clusters, d_clusters_sorted, d_members, d_pair_off, d_pair_ed, d_pairs, d_ckeys[2], d_cvals[2];
+    std::vector<uint32_t> h_part_off, h_order_cache;
+    std::vector<svim_cluster> h_clusters;
+    std::vector<uint32_t> h_members;
+    int64_t n_partitions = 0;
+    svim_cluster_stats clstats;
+    bool clustered = false;
+
+    // multi-GPU
+    void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+    DevBuf d_xchg[4];
+
+    // timing
+    cudaEvent_t ev[2 * T_N];
+    double ms[T_N];
+    bool ev_rec[T_N];
+
+    void set_error(int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
+};
+
+inline void svimgpu_ctx::set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    err = buf; err_code = code;
+}
+
+struct StageTimer {
+    svimgpu_ctx* c; int slot;
+    StageTimer(svimgpu_ctx* ctx, int s) : c(ctx), slot(s) { cudaEventRecord(c->ev[2 * s], c->stream); c->ev_rec[s] = true; }
+    ~StageTimer() { cudaEventRecord(c->ev[2 * slot + 1], c->stream); }
+};
+
+inline void timings_begin(svimgpu_ctx* ctx) { for (int i = 0; i < T_N; ++i) { ctx->ev_rec[i] = false; ctx->ms[i] = 0.0; } }
+inline void timings_end(svimgpu_ctx* ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < T_N; ++i)
+        if (ctx->ev_rec[i]) { float ms = 0; if (cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]) == cudaSuccess) ctx->ms[i] = ms; }
+}

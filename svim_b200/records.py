@@ -35,7 +35,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-CIGAR_OPS = "MIDNSHP=X"
+CIGAR_OPS = "MIDNSHP=XB"
 _OP_CODE = {c: i for i, c in enumerate(CIGAR_OPS)}
 SEQ_NT16 = "=ACMGRSVTWYHKDBN"
 _NT16_CODE = np.full(256, 15, dtype=np.uint8)
@@ -43,7 +43,7 @@ for _i, _c in enumerate(SEQ_NT16):
     _NT16_CODE[ord(_c)] = _i
     _NT16_CODE[ord(_c.lower())] = _i
 _NT16_CHARS = np.frombuffer(SEQ_NT16.encode(), dtype=np.uint8)
-_CIGAR_RE = re.compile(r"(\d+)([MIDNSHP=X])")
+_CIGAR_RE = re.compile(r"(\d+)([MIDNSHP=XB])")   # pysam CIGAR_REGEX
 
 FLAG_UNMAPPED = 0x4
 FLAG_REVERSE = 0x10

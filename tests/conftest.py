@@ -1,0 +1,54 @@
+import gzip
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+GOLDEN_NAMES = ("mini_indel", "mini_mixed", "mini_mixed_allbnds", "mini_ins", "mini_hotspot", "chimeric_kat")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def load_golden(name):
+    """-> (AlignmentBatch, Genome, expected dict) from the committed fixtures."""
+    from svim_b200.records import AlignmentBatch
+    from svim_b200.io import Genome
+    with gzip.open(os.path.join(GOLDEN, name + ".golden.json.gz"), "rt") as fh:
+        exp = json.load(fh)
+    z = np.load(os.path.join(GOLDEN, exp["input"]))
+    names = [str(x) for x in z["contig_names"]]
+    arrays = {f: z[f] for f, _ in AlignmentBatch.FIELDS}
+    qnames = [str(x) for x in z["qnames"]] if "qnames" in z.files else None
+    batch = AlignmentBatch(names, z["contig_lengths"], arrays, z["cigar"], z["seq"], z["sa"], qnames, "coordinate")
+    blob = z["genome_blob"]
+    offs = np.concatenate([[0], np.cumsum(z["contig_lengths"])]).astype(np.int64)
+    genome = Genome(names, [blob[offs[i]:offs[i + 1]] for i in range(len(names))])
+    return batch, genome, exp
+
+
+@pytest.fixture(scope="session")
+def golden():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = load_golden(name)
+        return cache[name]
+    return get
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    from svim_b200 import _lib
+    ctx = _lib.Context()
+    yield ctx
+    ctx.close()

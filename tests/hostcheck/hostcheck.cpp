@@ -1,0 +1,66 @@
+// Test-only host build of the SVIM_HD (host+device) logic headers, so the branchy per-read /
+// per-cluster code that the kernels execute can be fuzzed against the oracle without a GPU.
+// Not part of the product: libsvimgpu.so never calls this.
+#define SVIM_HOST_ONLY
+#include <vector>
+#include <cstring>
+#include "../../svim_b200/csrc/collect.cuh"
+#include "../../svim_b200/csrc/cluster.cuh"
+
+struct VecEmitter {
+    std::vector<svim_sig> m, t;
+    void sig(const svim_sig& s) { m.push_back(s); }
+    void twin(const svim_sig& s) { t.push_back(s); }
+};
+
+extern "C" {
+
+// One primary record + SA tag through parse_sa_segments / sort_chain / analyze_chain.
+int hc_chain(int32_t tid, int32_t pos, uint32_t flag, int64_t l_seq, const uint32_t* cigar, int32_t n_cigar, const uint8_t* sa, int32_t sa_len,
+             int32_t n_contigs, const char* names, const int32_t* name_off, const int32_t* rank,
+             int64_t min_sv, int64_t max_sv, int64_t tol_g, int64_t tol_o, int32_t min_mapq, int32_t all_bnds,
+             svim_sig* out_main, int32_t* n_main, svim_sig* out_twin, int32_t* n_twin, int32_t cap, uint32_t* err_out) {
+    ContigTable ct{n_contigs, names, name_off, rank};
+    ChainParams p{min_sv, max_sv, tol_g, tol_o, min_mapq, all_bnds};
+    CigarSummary cs; cigsum_init(cs);
+    for (int k = 0; k < n_cigar; ++k) cigsum_add(cs, cigar[k] & 15u, cigar[k] >> 4);
+    Seg chain[SVIM_MAX_SEGMENTS]; int n = 0; uint32_t err = 0;
+    Seg s; int64_t rl; s.tid = tid;
+    const int rev = (flag & 0x10u) ? 1 : 0;
+    cigsum_finish(cs, l_seq, pos, rev, s, rl);
+    VecEmitter out;
+    if (cs.hard == 0) {
+        if (rev && rl < 0) err |= CH_NO_READLEN; else chain[n++] = s;
+        n = parse_sa_segments(sa, sa_len, ct, p, l_seq, chain, n, err);
+    } else if (!(rev && rl < 0)) chain[n++] = s;
+    sort_chain(chain, n);
+    PrimaryInfo pi{0, 0, l_seq, rl};
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, 0x80000000u, 0x80000000u, err);
+    *n_main = (int32_t)out.m.size(); *n_twin = (int32_t)out.t.size();
+    for (size_t k = 0; k < out.m.size() && (int)k < cap; ++k) out_main[k] = out.m[k];
+    for (size_t k = 0; k < out.t.size() && (int)k < cap; ++k) out_twin[k] = out.t[k];
+    *err_out = err;
+    return 0;
+}
+
+double hc_spd(int type, const double* a, const double* b, uint32_t dirs_a, uint32_t dirs_b, double pos_norm, double edit_norm, double cmd, double ed, int* err) {
+    SigView va{a[0], a[1], a[2], 0, (uint8_t)dirs_a}, vb{b[0], b[1], b[2], 1, (uint8_t)dirs_b};
+    ClusterParams cp{1000.0, pos_norm, edit_norm, cmd};
+    return spd(type, va, vb, cp, ed, err);
+}
+
+// unsorted nn-chain rows -> flat clusters (the sequential half of the linkage kernel)
+int hc_fcluster(int m, const int* ux, const int* uy, const double* ud, double t, int* T) {
+    std::vector<int> zx(m), zy(m), order(m), parent(2 * m), stack(m + 1);
+    std::vector<double> zd(m), md(m);
+    std::vector<unsigned char> vis(2 * m);
+    LinkScratch s{zx.data(), zy.data(), zd.data(), order.data(), parent.data(), md.data(), stack.data(), vis.data()};
+    return fcluster_from_chain(m, s, ux, uy, ud, t, T);
+}
+
+double hc_stdev(const double* v, int n) { return stdev_values(v, n, 1); }
+double hc_score(int n_eff, int has, double a, double b, double span) { return cluster_score(n_eff, has, a, b, span); }
+long long hc_round(double x) { return py_round_int(x); }
+void hc_py_slice(long long a, long long n, long long L, long long* lo, long long* hi) { int64_t l, h; py_slice(a, n, L, l, h); *lo = l; *hi = h; }
+
+}

@@ -1,0 +1,307 @@
+"""CPU-side units: C-ABI library loads and exports what include/svimgpu.h declares, the host
+RNG restatement equals CPython's, the pysam-free readers round-trip, the oracle's two edit
+distance implementations agree, and the host+device logic headers (tests/hostcheck) agree with
+the oracle on fuzzed inputs.  No GPU needed."""
+import ctypes
+import os
+import random
+import re
+import statistics
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import svim_oracle as orc
+from oracle import editdist
+from svim_b200 import _lib
+from svim_b200.records import BatchBuilder, parse_cigar_string, encode_cigar
+from svim_b200 import io as sio
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "svimgpu.h")).read()
+    declared = set(re.findall(r"\b(svimgpu_\w+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(_lib.EXPORTS) == declared - {"svimgpu_ctx"}
+    lib.svimgpu_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.svimgpu_version()
+
+
+def test_struct_sizes_match_header():
+    assert _lib.SIG_DTYPE.itemsize == 48 and _lib.CSIG_DTYPE.itemsize == 64 and _lib.CLUSTER_DTYPE.itemsize == 72
+    assert ctypes.sizeof(_lib.Params) == 6 * 4 + 4 * 8
+
+
+def test_host_rng_matches_cpython_sample():
+    # SVIM_clustering.py:129-134: seed(1524) once, sample(partition, 100) per partition > 100
+    sizes = [5, 101, 100, 150, 1045, 1046, 2000, 50000, 102, 7, 100000, 1044]
+    got = _lib.sample_indices(sizes)
+    random.seed(1524)
+    want = [random.sample(range(n), 100) for n in sizes if n > 100]
+    assert got.tolist() == want
+    # sampling a list of objects picks the same positions as sampling range(n)
+    random.seed(1524)
+    pop = [object() for _ in range(333)]
+    pos = {id(o): i for i, o in enumerate(pop)}
+    assert [pos[id(o)] for o in random.sample(pop, 100)] == _lib.sample_indices([333])[0].tolist()
+
+
+def test_edit_distance_oracles_agree():
+    rng = random.Random(5)
+    for _ in range(200):
+        a = "".join(rng.choice("ACGTN") for _ in range(rng.randint(0, 400)))
+        b = list(a) if rng.random() < 0.6 else [rng.choice("ACGT") for _ in range(rng.randint(0, 400))]
+        for _k in range(rng.randint(0, 40)):
+            if b and rng.random() < 0.5:
+                del b[rng.randrange(len(b))]
+            else:
+                b.insert(rng.randint(0, len(b)), rng.choice("ACGT"))
+        b = "".join(b)
+        assert editdist.edit_distance(a, b) == editdist.edit_distance_dp(a, b)
+    assert editdist.edit_distance("kitten", "sitting") == 3
+
+
+def test_sam_bam_roundtrip(tmp_path):
+    b = BatchBuilder(["chr1", "chr2"], [1000, 2000])
+    b.add("r1", 0, 0, 10, 60, "5S10M2I3D20M", "ACGTN" * 7 + "AC", "chr2,5,-,10S27M,60,1;")
+    b.add("r2", 16, 1, 99, 3, "30M", None)
+    b.add("r1", 2048, 1, 4, 60, "10H27M", "A" * 27, "chr1,11,+,5S32M3D,60,2;")
+    batch = b.finish()
+    sam = str(tmp_path / "x.sam"); bam = str(tmp_path / "x.bam")
+    sio.write_sam(sam, batch); sio.write_bam(bam, batch)
+    for got in (sio.read_sam(sam), sio.read_bam(bam), sio.read_alignments(bam)):
+        assert got.n == 3 and got.contig_names == ["chr1", "chr2"]
+        for i in range(3):
+            assert got.cigartuples(i) == batch.cigartuples(i)
+            assert got.sequence(i) == batch.sequence(i)
+            assert got.sa_tag(i) == batch.sa_tag(i)
+            assert (got.tid[i], got.pos[i], got.flag[i], got.mapq[i]) == (batch.tid[i], batch.pos[i], batch.flag[i], batch.mapq[i])
+        assert got.qname_id[0] == got.qname_id[2] != got.qname_id[1]
+
+
+def test_fasta_fetch_clamps(tmp_path):
+    g = sio.Genome(["c1", "c2"], [np.frombuffer(b"ACGTacgtNN", dtype=np.uint8), np.frombuffer(b"GG", dtype=np.uint8)])
+    p = str(tmp_path / "g.fa"); g.write_fasta(p, width=4)
+    g2 = sio.Genome.from_fasta(p)
+    assert g2.fetch("c1", 2, 6) == "GTac" and g2.fetch("c1", 8, 50) == "NN" and g2.fetch("c1", 20, 30) == "" and g2.fetch("c2", 0, 2) == "GG"
+
+
+# ---- host build of the SVIM_HD headers -----------------------------------------------------------
+@pytest.fixture(scope="module")
+def hc():
+    src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
+    so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
+    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
+    lib = ctypes.CDLL(so)
+    lib.hc_spd.restype = ctypes.c_double
+    lib.hc_stdev.restype = ctypes.c_double
+    lib.hc_score.restype = ctypes.c_double
+    lib.hc_round.restype = ctypes.c_longlong
+    lib.hc_round.argtypes = [ctypes.c_double]
+    lib.hc_score.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+    return lib
+
+
+def _random_read(rng, names):
+    """A primary + SA segments with coordinates close enough to reach every branch of the split-read tree."""
+    L = rng.randint(2000, 9000)
+    k = rng.randint(1, 4)
+    cuts = sorted(rng.sample(range(100, L - 100), k))
+    bounds = [0] + cuts + [L]
+    base = rng.randint(50_000, 60_000)
+    segs = []
+    for i in range(k + 1):
+        qs, qe = bounds[i], bounds[i + 1]
+        qs2 = max(0, qs + rng.choice([0, 0, 0, -3, -8, 4, 12, 60]))
+        tid = rng.choice([0, 0, 0, 1, 2])
+        rev = rng.random() < 0.35
+        mode = rng.random()
+        if mode < 0.5:
+            ref = base + qs + rng.choice([0, 0, 50, -50, 300, -300, 5000, -5000, 150000, -150000, 3, -3, 45, -45])
+        else:
+            ref = rng.randint(1000, 300_000)
+        qlen = max(1, qe - qs2)
+        rlen = max(1, qlen + rng.choice([0, 0, 0, -20, 20, 100]))
+        segs.append(dict(qs=qs2, qe=qe, tid=tid, rev=rev, ref=max(0, ref), qlen=qlen, rlen=rlen, mapq=rng.choice([60, 60, 60, 5, 300])))
+    prim = max(range(len(segs)), key=lambda i: segs[i]["qlen"])
+
+    def cigar(s, clip):
+        lead, trail = (L - s["qe"], s["qs"]) if s["rev"] else (s["qs"], L - s["qe"])
+        mid = "%dM" % min(s["qlen"], s["rlen"])
+        if s["qlen"] > s["rlen"]:
+            mid += "%dI" % (s["qlen"] - s["rlen"])
+        elif s["rlen"] > s["qlen"]:
+            mid += "%dD" % (s["rlen"] - s["qlen"])
+        return ("%d%s" % (lead, clip) if lead else "") + mid + ("%d%s" % (trail, clip) if trail else "")
+    sa = ""
+    for i, s in enumerate(segs):
+        if i == prim:
+            continue
+        sa += "%s,%d,%s,%s,%d,%d;" % (names[s["tid"]], s["ref"] + 1, "-" if s["rev"] else "+", cigar(s, "S"), s["mapq"], 3)
+    if rng.random() < 0.05:
+        sa += "bad,field;"
+    p = segs[prim]
+    seq = "".join(rng.choice("ACGT") for _ in range(L)) if rng.random() < 0.9 else None
+    return dict(flag=16 if p["rev"] else 0, tid=p["tid"], pos=p["ref"], cigar=cigar(p, "S"), seq=seq, sa=sa)
+
+
+@pytest.mark.parametrize("all_bnds", [False, True])
+def test_segment_chain_logic_matches_oracle(hc, all_bnds):
+    rng = random.Random(11 + all_bnds)
+    names = ["chr1", "chr10", "chr2"]
+    rank = np.array([0, 1, 2], dtype=np.int32)        # string order: chr1 < chr10 < chr2
+    blob = "".join(names).encode(); off = np.array([0, 4, 9, 13], dtype=np.int32)
+    params = orc.Params(all_bnds=all_bnds, max_sv_size=rng.choice([100000, 2000]))
+    cap = 64
+    out_m = np.zeros(cap, dtype=_lib.SIG_DTYPE); out_t = np.zeros(cap, dtype=_lib.SIG_DTYPE)
+    n_checked = 0
+    for it in range(3000):
+        r = _random_read(rng, names)
+        b = BatchBuilder(names, [400_000] * 3)
+        b.add("read", r["flag"], r["tid"], r["pos"], 60, r["cigar"], r["seq"], r["sa"])
+        batch = b.finish()
+        prim, hard = orc.segment_of_record(batch, 0)
+        good = [s for s in orc.sa_segments(batch, 0, hard) if s.mapq >= params.min_mapq]
+        want, want_t = orc.segment_signatures(batch, prim, good, batch.sequence(0), "read", params)
+        nm, nt, err = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_uint32()
+        cig = batch.cigar
+        sa = batch.sa
+        hc.hc_chain(int(batch.tid[0]), int(batch.pos[0]), int(batch.flag[0]), ctypes.c_int64(int(batch.l_seq[0])),
+                    cig.ctypes.data_as(ctypes.c_void_p), int(batch.n_cigar[0]), sa.ctypes.data_as(ctypes.c_void_p), int(batch.sa_len[0]),
+                    3, blob, off.ctypes.data_as(ctypes.c_void_p), rank.ctypes.data_as(ctypes.c_void_p),
+                    ctypes.c_int64(params.min_sv_size), ctypes.c_int64(params.max_sv_size), ctypes.c_int64(params.segment_gap_tolerance),
+                    ctypes.c_int64(params.segment_overlap_tolerance), params.min_mapq, int(all_bnds),
+                    out_m.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nm), out_t.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nt), cap,
+                    ctypes.byref(err))
+        from svim_b200.SVIM_COLLECT import materialize_signatures
+        seq = batch.sequence(0) or ""
+
+        def conv(arr, n):
+            res = []
+            for s in arr[:n]:
+                t = _lib.TYPE_NAMES[s["type"]]
+                fl = int(s["flags"])
+                tup = [t, names[s["contig1"]], int(s["start"]), int(s["end"])]
+                if t == "INS":
+                    tup.append(seq[int(s["seq_off"]):int(s["seq_off"]) + int(s["seq_len"])])
+                elif t == "INV":
+                    tup.append(_lib.INV_DIRECTIONS[(fl >> 4) & 7])
+                elif t == "DUP_TAN":
+                    tup += [int(s["copies"]), bool(fl & 2)]
+                elif t == "DUP_INT":
+                    tup += [names[s["contig2"]], int(s["pos"])]
+                elif t == "BND":
+                    tup += [names[s["contig2"]], int(s["pos"]), "rev" if fl & 4 else "fwd", "rev" if fl & 8 else "fwd"]
+                res.append(tuple(tup))
+            return res
+
+        def conv_o(lst):
+            res = []
+            for s in lst:
+                tup = [s.type, s.contig, s.start, s.end]
+                if s.type == "INS":
+                    tup.append(s.sequence)
+                elif s.type == "INV":
+                    tup.append(s.direction)
+                elif s.type == "DUP_TAN":
+                    tup += [s.copies, s.fully_covered]
+                elif s.type == "DUP_INT":
+                    tup += [s.contig2, s.pos]
+                elif s.type == "BND":
+                    tup += [s.contig2, s.pos, s.dir1, s.dir2]
+                res.append(tuple(tup))
+            return res
+        assert conv(out_m, nm.value) == conv_o(want), (it, r)
+        assert conv(out_t, nt.value) == conv_o(want_t), (it, r)
+        n_checked += len(want) + len(want_t)
+    assert n_checked > 1500      # the fuzz really produces signatures of every kind
+
+
+def test_distance_and_consolidation_scalars(hc):
+    rng = random.Random(2)
+    for _ in range(2000):
+        a = orc.Sig("DEL", "c", rng.randint(0, 10**6), 0, "cigar", "r1"); a.end = a.start + rng.randint(40, 5000)
+        b = orc.Sig("DEL", "c", a.start + rng.randint(-900, 900), 0, "cigar", "r2"); b.end = b.start + rng.randint(40, 5000)
+        err = ctypes.c_int(0)
+        av = (ctypes.c_double * 3)(a.start, a.end, 0); bv = (ctypes.c_double * 3)(b.start, b.end, 0)
+        got = hc.hc_spd(0, av, bv, 0, 0, ctypes.c_double(900), ctypes.c_double(1.0), ctypes.c_double(0.5), ctypes.c_double(0), ctypes.byref(err))
+        assert got == orc.span_position_distance(a, b, None, orc.Params())
+        # INS with a given edit distance (gate open and closed)
+        a.type = b.type = "INS"
+        ed = rng.randint(0, 3000)
+        pd = abs(a.start - b.start) / 900
+        s1, s2 = a.end - a.start, b.end - b.start
+        want = pd + abs(s1 - s2) / max(s1, s2) if pd > 1.0 else pd + ed / max(s1, s2) / 1.0
+        got = hc.hc_spd(1, av, bv, 0, 0, ctypes.c_double(900), ctypes.c_double(1.0), ctypes.c_double(0.5), ctypes.c_double(ed), ctypes.byref(err))
+        assert got == want
+    for _ in range(500):
+        n = rng.randint(2, 100)
+        base = rng.randint(0, 2 * 10**8)
+        vals = [base + rng.randint(0, 3000) for _ in range(n)]
+        if rng.random() < 0.5:
+            vals = [(v + rng.randint(0, 3000) + v) / 2 for v in vals]       # half-integral positions
+        arr = (ctypes.c_double * n)(*vals)
+        got = hc.hc_stdev(arr, n); want = statistics.stdev(vals)
+        assert got == pytest.approx(want, rel=1e-12, abs=1e-12)
+    for x in [0.5, 1.5, 2.5, -0.5, 3.49999, 1e9 + 0.5, 7.0]:
+        assert hc.hc_round(x) == int(round(x))
+    for _ in range(300):
+        L = rng.randint(0, 50); a = rng.randint(-70, 70); n = rng.randint(0, 80)
+        lo, hi = ctypes.c_longlong(), ctypes.c_longlong()
+        hc.hc_py_slice(ctypes.c_longlong(a), ctypes.c_longlong(n), ctypes.c_longlong(L), ctypes.byref(lo), ctypes.byref(hi))
+        s = "x" * L
+        assert len(s[a:a + n]) == hi.value - lo.value and (hi.value == lo.value or s[a:a + n] == s[lo.value:hi.value])
+
+
+def test_fcluster_postprocessing_matches_scipy(hc):
+    from scipy.cluster.hierarchy import linkage, fcluster
+    rng = np.random.default_rng(9)
+    for t in range(300):
+        m = int(rng.integers(2, 101)); npair = m * (m - 1) // 2
+        d = [rng.random(npair), rng.integers(0, 3, npair) / 2.0, np.where(rng.random(npair) < 0.3, 99999.0, rng.random(npair))][t % 3]
+        # unsorted nn-chain rows from the restated algorithm, then the C post-processing
+        D = [float(x) for x in d]
+        rows = []
+        size = [1] * m
+        chain = []
+
+        def ix(i, j):
+            i, j = (i, j) if i < j else (j, i)
+            return m * i - i * (i + 1) // 2 + (j - i - 1)
+        for _k in range(m - 1):
+            if not chain:
+                chain.append(next(i for i in range(m) if size[i] > 0))
+            while True:
+                x = chain[-1]
+                if len(chain) > 1:
+                    y = chain[-2]; cur = D[ix(x, y)]
+                else:
+                    y = -1; cur = float("inf")
+                for i in range(m):
+                    if size[i] and i != x and D[ix(x, i)] < cur:
+                        cur = D[ix(x, i)]; y = i
+                if len(chain) > 1 and y == chain[-2]:
+                    break
+                chain.append(y)
+            chain.pop(); chain.pop()
+            if x > y:
+                x, y = y, x
+            nx, ny = size[x], size[y]
+            rows.append((x, y, cur)); size[x] = 0; size[y] = nx + ny
+            for i in range(m):
+                if size[i] and i != y:
+                    D[ix(i, y)] = (nx * D[ix(i, x)] + ny * D[ix(i, y)]) / (nx + ny)
+        ux = np.array([r[0] for r in rows], dtype=np.int32); uy = np.array([r[1] for r in rows], dtype=np.int32)
+        ud = np.array([r[2] for r in rows], dtype=np.float64)
+        T = np.zeros(m, dtype=np.int32)
+        hc.hc_fcluster(m, ux.ctypes.data_as(ctypes.c_void_p), uy.ctypes.data_as(ctypes.c_void_p), ud.ctypes.data_as(ctypes.c_void_p),
+                       ctypes.c_double(0.5), T.ctypes.data_as(ctypes.c_void_p))
+        want = fcluster(linkage(np.asarray(d, dtype=float), method="average"), 0.5, criterion="distance")
+        assert T.tolist() == list(want)

@@ -104,8 +104,11 @@ def run_oracle(batch, genome, overrides):
 
 def save_input(path, batch, genome):
     arrays = {name: getattr(batch, name) for name, _ in AlignmentBatch.FIELDS}
-    np.savez_compressed(path, contig_names=np.array(batch.contig_names), contig_lengths=batch.contig_lengths,
-                        cigar=batch.cigar, seq=batch.seq, sa=batch.sa, genome_blob=genome.blob, **arrays)
+    extra = {}
+    if batch.qnames is not None:
+        extra["qnames"] = np.array(batch.qnames)
+    np.savez_compressed(path, contig_names=np.array(batch.contig_names), contig_lengths=batch.contig_lengths if len(genome.blob) else np.zeros(len(batch.contig_names), np.int64),
+                        cigar=batch.cigar, seq=batch.seq, sa=batch.sa, genome_blob=genome.blob, **arrays, **extra)
 
 
 def fixtures():
@@ -134,6 +137,12 @@ def fixtures():
     svs, al = synth.plant_svs(L, 14, spacing=6000, hotspots=2, hotspot_svs=(8, 14), size_range=(50, 400))
     out["mini_hotspot"] = (synth.generate(names, L, 2600, 14, svs, al, len_mean=3000, len_sd=500, len_min=1000, len_max=6000, p_ins=0.02, p_del=0.01),
                            synth.random_genome(names, L, 14), {})
+    # 5. known-answer vector derived from the reference's own test data (tests/chimeric_read.sam, used by
+    #    tests/test_satag.py): one 9.9 kb read, primary + 3 supplementary records with SA tags.
+    from svim_b200.io import read_sam, Genome
+    kat = read_sam(os.path.join(refenv.REF, "tests", "chimeric_read.sam"))
+    kat.sort_order = "coordinate"
+    out["chimeric_kat"] = (kat, Genome(kat.contig_names, [np.zeros(0, np.uint8) for _ in kat.contig_names]), {})
     return out
 
 
