@@ -333,9 +333,9 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
 
 // linkage + fcluster on an explicit condensed matrix, through the same device functions as k_linkage
 __global__ void __launch_bounds__(32) k_linkage_raw(const double* condensed, int m, double t, double* Z, int32_t* T) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw2[];
     const int lane = threadIdx.x;
-    PartSmem s = carve(smem_raw, m < 2 ? 2 : m);
+    PartSmem s = carve(smem_raw2, m < 2 ? 2 : m);
     const int np = m * (m - 1) / 2;
     for (int q = lane; q < np; q += 32) s.D[q] = condensed[q];
     __syncwarp();
