@@ -1,0 +1,299 @@
+#!/usr/bin/env python3
+"""bench.py — alignments/sec through COLLECT+CLUSTER (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # N>1: launched by torchrun, one rank per GPU
+    python bench.py --impl reference ...                    # the CPU path (oracle port of the reference) on a bounded sample
+
+A "step" is one pass of the hot path over one batch of synthetic alignments: BASELINE.json
+configs[1] (1 contig, 500 k alignments, 15 kb CLR-like reads) per GPU; with N GPUs every rank
+holds one such contig (weak scaling), the ranks exchange signature records once after COLLECT
+and cluster records once at the end (NCCL all-gather-v).
+
+Printed JSON (rank 0, one line):
+  value     whole-job alignments/s with the record buffer already resident in HBM
+            (CUDA events around collect -> [exchange] -> cluster, max over ranks)
+  e2e       same metric through the C ABI with HOST buffers: H2D of the record buffer and D2H of
+            the signature + cluster records inside the timed region, every step
+  roofline  the CIGAR-scan kernel: algorithmic bytes / its CUDA-event duration vs measured HBM peak
+  cpu_baseline  oracle port of the reference, 1 host thread, bounded genomic slice of the same input
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "alignments/sec through COLLECT+CLUSTER"
+UNIT = "alignments/s"
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def make_rank_input(workload, scale, rank, world):
+    """Rank r's shard: one contig 'chr<r+1>' of the workload (records are contiguous in coordinate order)."""
+    from svim_b200 import synth
+    c = dict(synth.CONFIGS[workload])
+    G = int(c.pop("genome") * scale); reads = max(10, int(c.pop("reads") * scale)); seed = c.pop("seed") + 100 * rank
+    c.pop("contigs")
+    hotspots = int(round(c.pop("hotspots", 0) * scale)) if "hotspots" in c else 0
+    plant_kw = {k: c.pop(k) for k in ("spacing", "mix", "ins_size_uniform", "hotspot_svs") if k in c}
+    names = ["chr%d" % (r + 1) for r in range(world)]
+    lengths = [G] * world
+    svs, alleles = synth.plant_svs([G], seed, hotspots=hotspots, **plant_kw)
+    batch = synth.generate([names[rank]], [G], reads, seed, svs, alleles, **c)
+    batch.contig_names = names; batch.contig_lengths = np.asarray(lengths, dtype=np.int64)
+    batch._tid_of = {n: i for i, n in enumerate(names)}
+    batch.tid[batch.tid >= 0] = rank
+    batch.qname_id += np.uint32(rank << 26)
+    genomes = [synth.random_genome([names[r]], [G], 1524 + synth.CONFIGS[workload]["seed"] + 100 * r) for r in range(world)]
+    from svim_b200.io import Genome
+    genome = Genome(names, [g.blob for g in genomes])
+    return batch, genome
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device = device; self.proc = None; self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline(batch, genome, target_seconds=15.0):
+    """Oracle port of the reference on a contiguous genomic prefix of the same input, 1 host thread."""
+    from oracle import svim_oracle as orc
+    p = orc.Params()
+    # calibrate on 300 records, then size the slice for ~target_seconds of COLLECT (+ CLUSTER on what it emits)
+    n0 = min(300, batch.n)
+    t0 = time.perf_counter(); orc.collect(batch.slice(0, n0), p); dt = max(1e-4, time.perf_counter() - t0)
+    n = int(min(batch.n, max(n0, 0.6 * target_seconds / dt * n0)))
+    sl = batch.slice(0, n)
+    t0 = time.perf_counter()
+    sigs, _ = orc.collect(sl, p)
+    t1 = time.perf_counter()
+    orc.cluster(sigs, genome, p)
+    t2 = time.perf_counter()
+    return {"value": n / (t2 - t0), "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "first %d of %d coordinate-sorted records (%.1f s COLLECT + %.1f s CLUSTER, %d signatures); "
+                      "edit distance by oracle/editdist.c Myers (edlib stand-in)" % (n, batch.n, t1 - t0, t2 - t1, len(sigs))}
+
+
+def run_reference(args):
+    rank, local_rank, world = env_rank()
+    if rank != 0:
+        return
+    batch, genome = make_rank_input(args.workload, args.scale, 0, 1)
+    vals = []
+    base = None
+    for s in range(args.warmup + args.steps):
+        base = cpu_baseline(batch, genome, target_seconds=args.ref_seconds)
+        if s >= args.warmup:
+            vals.append(base["value"])
+    v = float(np.mean(vals))
+    base["value"] = v
+    n_s = int(base["sample"].split()[1])
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1000.0 * n_s / v, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+                      "config": {"workload": workload_name(args), "note": "reference is single-threaded pure Python (README.rst:73); "
+                                 "each step is a bounded sample of the workload"},
+                      "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def workload_name(args):
+    return "%s x%g per GPU (BASELINE.json configs[1]: 1 contig, 500k alignments, 15 kb CLR-like reads)" % (args.workload, args.scale)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink genome and read count together (testing only)")
+    ap.add_argument("--ref-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.warmup < 3 and not args.profile_steps:
+        args.warmup = 3
+
+    rank, local_rank, world = env_rank()
+    from svim_b200 import _lib
+    t_gen = time.perf_counter()
+    batch, genome = make_rank_input(args.workload, args.scale, rank, world)
+    t_gen = time.perf_counter() - t_gen
+
+    ctx = _lib.Context(device=local_rank)
+    ctx.set_contigs(batch.contig_names)
+    ctx.set_genome(genome)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        ids = [None]
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert ctx.lib.svimgpu_nccl_unique_id(buf) == 0
+            ids = [bytes(buf)]
+        dist.broadcast_object_list(ids, src=0)
+        idb = (C.c_ubyte * 128).from_buffer_copy(ids[0])
+        ctx._check(ctx.lib.svimgpu_comm_init(ctx.h, world, rank, idb))
+        sizes = [None] * world
+        dist.all_gather_object(sizes, batch.n)
+        aln_base = int(sum(sizes[:rank])); total_aln = int(sum(sizes))
+    else:
+        aln_base = 0; total_aln = batch.n
+
+    def barrier_max(x):
+        v = C.c_double(x)
+        ctx._check(ctx.lib.svimgpu_barrier_max(ctx.h, C.byref(v)))
+        return v.value
+
+    def cluster_step():
+        if world > 1:
+            st = _lib.CollectStats()
+            ctx._check(ctx.lib.svimgpu_exchange_signatures(ctx.h, aln_base, C.byref(st)))
+            ctx.use_collected(0)
+            return st, ctx.cluster(sharded=True)
+        ctx.use_collected(0)
+        return None, ctx.cluster()
+
+    # ---------------- resident: record buffer already in HBM -------------------------------------
+    ctx.upload(batch)
+    stage_ms = {}
+    launches0 = 0
+    res_ms = []
+    sampler = ClockSampler(local_rank)
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier_max(0.0); sampler.start(); launches0 = ctx.launch_count()
+        ctx.timer_start()
+        cst = ctx.collect()
+        tm = dict(ctx.timings())
+        xst, (clst, clusters, members) = cluster_step()
+        ms = ctx.timer_stop()
+        for k, v in list(tm.items()) + list(ctx.timings().items()):
+            if v and s >= args.warmup:
+                stage_ms.setdefault(k, []).append(v)
+        if s >= args.warmup:
+            res_ms.append(barrier_max(ms))
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - launches0
+    n_sigs = (xst.n_signatures if xst else cst.n_signatures)
+    if args.profile_steps:
+        return
+
+    # ---------------- e2e: host buffers through the C ABI, copies inside the timed region --------
+    pinned = [batch.cigar, batch.seq, batch.sa] + [getattr(batch, f) for f, _ in batch.FIELDS]
+    for a in pinned:
+        ctx.pin(a)
+    h2d = int(sum(a.nbytes for a in pinned))
+    e2e_ms = []
+    d2h = 0
+    for s in range(args.warmup + args.steps):
+        if s == args.warmup:
+            barrier_max(0.0)
+        ctx.timer_start()
+        cst = ctx.collect_host(batch)
+        xst, (clst, clusters, members) = cluster_step()
+        fst = xst or cst
+        sigs, ins = ctx.fetch_signatures(0, fst)
+        ms = ctx.timer_stop()
+        d2h = sigs.nbytes + ins.nbytes + clusters.nbytes + members.nbytes
+        if s >= args.warmup:
+            e2e_ms.append(barrier_max(ms))
+    # same, plus materialising the Python SVSignature / SignatureCluster objects (what `svim alignment` consumes)
+    obj_s = None
+    if world == 1:
+        from svim_b200.SVIM_COLLECT import materialize_signatures
+        from svim_b200.SVIM_clustering import build_clusters
+        t0 = time.perf_counter()
+        objs = materialize_signatures(sigs, ins, batch)
+        build_clusters(clusters, members, objs)
+        obj_s = time.perf_counter() - t0
+    for a in pinned:
+        ctx.unpin(a)
+
+    if rank != 0:
+        return
+    ms_step = float(np.mean(res_ms)); e2e_step = float(np.mean(e2e_ms))
+    scan_ms = float(np.mean(stage_ms.get("cigar_scan", [float("nan")])))
+    alg_bytes = batch.algorithmic_bytes() + int(cst.n_signatures) * 48
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    out = {
+        "metric": METRIC, "value": total_aln / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 CIGAR words / i64 coordinates / f64 distances",
+        "data": "synthetic", "gpu_launches": int(launches),
+        "config": {"workload": workload_name(args), "alignments_per_gpu": batch.n, "signatures": int(n_sigs), "clusters": int(clst.n_clusters_total),
+                   "myers_pairs": int(clst.myers_pairs), "myers_cells": int(clst.myers_cells),
+                   "l2": "inputs larger than L2 (%.2f GB CIGAR per GPU vs 126 MB)" % (batch.cigar.nbytes / 1e9),
+                   "parallelism": "records sharded by contig; 2 NCCL allgatherv" if world > 1 else "single GPU",
+                   "input_generation_s": round(t_gen, 1)},
+        "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_step, "python_object_materialisation_s": obj_s},
+        "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
+        "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
+        "clocks": clocks,
+    }
+    if clst.myers_cells and "myers_edit_distance" in out["stages_ms"]:
+        out["myers"] = {"kernel": "k_myers_pairs", "bound": "int-alu", "gcups": clst.myers_cells / (out["stages_ms"]["myers_edit_distance"] * 1e-3) / 1e9}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(batch, genome, target_seconds=args.ref_seconds)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -216,6 +216,11 @@ int svimgpu_sample_indices(const int64_t* sizes, int64_t n_sizes, int32_t* out /
 /* timing of the last collect / cluster call, milliseconds of device time per stage */
 int svimgpu_last_timings(svimgpu_ctx* ctx, double* ms, int32_t cap, int32_t* n);
 const char* svimgpu_timing_name(int32_t i);
+/* CUDA events on the context's stream around an arbitrary sequence of calls (bench.py) */
+int svimgpu_timer_start(svimgpu_ctx* ctx);
+int svimgpu_timer_stop(svimgpu_ctx* ctx, double* ms);
+/* kernels of this library launched so far on this context (CUB/NCCL launches not counted) */
+int64_t svimgpu_launch_count(svimgpu_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,9 @@ EXPORTS = {
     "svimgpu_sample_indices": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     "svimgpu_last_timings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
     "svimgpu_timing_name": (C.c_char_p, [C.c_int32]),
+    "svimgpu_timer_start": (C.c_int, [C.c_void_p]),
+    "svimgpu_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "svimgpu_launch_count": (C.c_int64, [C.c_void_p]),
 }
 
 _lib = None
@@ -258,6 +261,17 @@ class Context:
         n = C.c_int32()
         self._check(self.lib.svimgpu_last_timings(self.h, ms.ctypes.data, 32, C.byref(n)))
         return {self.lib.svimgpu_timing_name(i).decode(): float(ms[i]) for i in range(n.value)}
+
+    def timer_start(self):
+        self._check(self.lib.svimgpu_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.lib.svimgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.svimgpu_launch_count(self.h))
 
     # ---- micro entry points (unit tests) ----
     def cigar_indel(self, cigar_u32, min_len):

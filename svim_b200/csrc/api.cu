@@ -32,6 +32,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     ctx->device = device; ctx->params = *params;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SVIMGPU_ERR_CUDA; }
     for (int i = 0; i < 2 * T_N; ++i) cudaEventCreate(&ctx->ev[i]);
+    cudaEventCreate(&ctx->user_ev[0]); cudaEventCreate(&ctx->user_ev[1]);
     timings_begin(ctx);
     memset(&ctx->cstats, 0, sizeof(ctx->cstats)); memset(&ctx->clstats, 0, sizeof(ctx->clstats));
     myers_init_symcode();
@@ -175,8 +176,8 @@ static int finish_csig(svimgpu_ctx* ctx) {
     unsigned long long h = 0;
     SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
     SVIM_CUDA(cudaMemsetAsync(ctx->d_part_stats.p, 0, 8, ctx->stream));
-    if (ctx->n_csig) k_max_ins_len<<<(uint32_t)((ctx->n_csig + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_csig.as<svim_csig>(), (uint32_t)ctx->n_csig,
-                                                                                                   (unsigned long long*)ctx->d_part_stats.p);
+    if (ctx->n_csig) { ctx->launches++; k_max_ins_len<<<(uint32_t)((ctx->n_csig + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_csig.as<svim_csig>(), (uint32_t)ctx->n_csig,
+                                                                                                   (unsigned long long*)ctx->d_part_stats.p); }
     SVIM_CUDA(cudaMemcpyAsync(&h, ctx->d_part_stats.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->cluster_max_ins_len = (int64_t)h;
@@ -194,8 +195,8 @@ int svimgpu_use_collected(svimgpu_ctx* ctx, int which) {
     SVIM_CUDA(ctx->d_csig.ensure((size_t)(set.n + 1) * sizeof(svim_csig)));
     {
         StageTimer t(ctx, T_CSIG);
-        if (set.n) k_sig_to_csig<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, ctx->d_rank.as<int32_t>(),
-                                                                                           ctx->d_csig.as<svim_csig>());
+        if (set.n) { ctx->launches++; k_sig_to_csig<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, ctx->d_rank.as<int32_t>(),
+                                                                                           ctx->d_csig.as<svim_csig>()); }
     }
     ctx->cluster_ins = set.ins.as<uint8_t>(); ctx->cluster_ins_bytes = set.ins_bytes;
     ctx->cluster_rank_to_tid = ctx->d_rank_to_tid.as<int32_t>(); ctx->cluster_n_ranks = ctx->n_contigs;
@@ -319,8 +320,8 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         chk(cudaMemcpyAsync(d_bo.p, b_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bl.p, b_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemsetAsync(d_next.p, 0, 4, ctx->stream));
-        k_myers_strings<<<blocks, 128, 0, ctx->stream>>>(d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(),
-                                                        (uint32_t)n_pairs, d_out.as<int32_t>(), d_scr.as<uint8_t>(), maxlen, d_next.as<uint32_t>());
+        { ctx->launches++; k_myers_strings<<<blocks, 128, 0, ctx->stream>>>(d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(),
+                                                        (uint32_t)n_pairs, d_out.as<int32_t>(), d_scr.as<uint8_t>(), maxlen, d_next.as<uint32_t>()); }
         chk(cudaGetLastError());
         chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaStreamSynchronize(ctx->stream));
@@ -361,7 +362,7 @@ int svimgpu_linkage_average(svimgpu_ctx* ctx, const double* condensed, int32_t m
     SVIM_CUDA(cudaMemcpyAsync(d_c.p, condensed, np * 8, cudaMemcpyHostToDevice, ctx->stream));
     size_t sm = part_smem_bytes(m);
     SVIM_CUDA(cudaFuncSetAttribute(k_linkage_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 1024)));
-    k_linkage_raw<<<1, 32, sm, ctx->stream>>>(d_c.as<double>(), m, t, d_z.as<double>(), d_t.as<int32_t>());
+    { ctx->launches++; k_linkage_raw<<<1, 32, sm, ctx->stream>>>(d_c.as<double>(), m, t, d_z.as<double>(), d_t.as<int32_t>()); }
     SVIM_CUDA(cudaGetLastError());
     SVIM_CUDA(cudaMemcpyAsync(Z, d_z.p, (size_t)(m - 1) * 32, cudaMemcpyDeviceToHost, ctx->stream));
     SVIM_CUDA(cudaMemcpyAsync(T, d_t.p, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -385,6 +386,27 @@ int svimgpu_last_timings(svimgpu_ctx* ctx, double* ms, int32_t cap, int32_t* n) 
     for (int i = 0; i < T_N && i < cap; ++i) ms[i] = ctx->ms[i];
     return 0;
 }
+
+int svimgpu_timer_start(svimgpu_ctx* ctx) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    SVIM_CUDA(cudaEventRecord(ctx->user_ev[0], ctx->stream));
+    return 0;
+}
+
+int svimgpu_timer_stop(svimgpu_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    SVIM_CUDA(cudaEventRecord(ctx->user_ev[1], ctx->stream));
+    SVIM_CUDA(cudaEventSynchronize(ctx->user_ev[1]));
+    float f = 0;
+    SVIM_CUDA(cudaEventElapsedTime(&f, ctx->user_ev[0], ctx->user_ev[1]));
+    *ms = f;
+    return 0;
+}
+
+int64_t svimgpu_launch_count(svimgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 const char* svimgpu_timing_name(int32_t i) { return (i >= 0 && i < T_N) ? k_timing_names[i] : ""; }
 

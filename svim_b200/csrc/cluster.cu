@@ -415,15 +415,15 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         for (int k = 0; k < 2; ++k) { SVIM_CUDA(ctx->d_ckeys[k].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_cvals[k].ensure((size_t)n * 4)); }
         SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n * 8));
         uint64_t* group = ctx->d_keys[0].as<uint64_t>();
-        k_cluster_keys<<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), n, ctx->d_ckeys[0].as<uint64_t>(), group, ctx->d_cvals[0].as<uint32_t>());
+        { ctx->launches++; k_cluster_keys<<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), n, ctx->d_ckeys[0].as<uint64_t>(), group, ctx->d_cvals[0].as<uint32_t>()); }
         uint64_t* k_out; uint32_t* v_out;
         int rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n, 64, &k_out, &v_out); if (rc) return rc;
-        k_gather<uint64_t><<<nb, 256, 0, st>>>(group, v_out, n, ctx->d_ckeys[1].as<uint64_t>());
+        { ctx->launches++; k_gather<uint64_t><<<nb, 256, 0, st>>>(group, v_out, n, ctx->d_ckeys[1].as<uint64_t>()); }
         std::swap(ctx->d_ckeys[0], ctx->d_ckeys[1]);
         rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n, 64, &k_out, &v_out); if (rc) return rc;
         gkey_sorted = k_out; order = v_out;
         SVIM_CUDA(ctx->d_csig_sorted.ensure((size_t)n * sizeof(svim_csig)));
-        k_gather<svim_csig><<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), order, n, ctx->d_csig_sorted.as<svim_csig>());
+        { ctx->launches++; k_gather<svim_csig><<<nb, 256, 0, st>>>(ctx->d_csig.as<svim_csig>(), order, n, ctx->d_csig_sorted.as<svim_csig>()); }
         SVIM_CUDA(ctx->d_order.ensure((size_t)n * 4));
         SVIM_CUDA(cudaMemcpyAsync(ctx->d_order.p, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
     }
@@ -436,7 +436,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         SVIM_CUDA(ctx->d_head.ensure(n + 64)); SVIM_CUDA(ctx->d_part_off.ensure((size_t)(n + 2) * 4)); SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
         uint32_t* d_ts = ctx->d_part_stats.as<uint32_t>();   // [0..6] type_start, [8] num selected, [9] err, [10] n_work, [12..13] cells
         SVIM_CUDA(cudaMemsetAsync(d_ts, 0, 64 * 4, st));
-        k_partition_heads<<<nb, 256, 0, st>>>(sorted, gkey_sorted, n, cp.partition_max_distance, ctx->d_head.as<uint8_t>(), d_ts);
+        { ctx->launches++; k_partition_heads<<<nb, 256, 0, st>>>(sorted, gkey_sorted, n, cp.partition_max_distance, ctx->d_head.as<uint8_t>(), d_ts); }
         size_t tmp = 0;
         cub::CountingInputIterator<uint32_t> cnt_it(0);
         cub::DeviceSelect::Flagged(nullptr, tmp, cnt_it, ctx->d_head.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), d_ts + 8, (int)n, st);
@@ -519,8 +519,8 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         {
             StageTimer t(ctx, T_PAIRS);
             uint32_t blocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
-            k_ins_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins, (uint32_t)list_ins.size(),
-                                                ctx->d_pair_off.as<uint64_t>(), cp, ctx->d_pairs.as<MyersWork>(), d_misc + 10);
+            { ctx->launches++; k_ins_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins, (uint32_t)list_ins.size(),
+                                                ctx->d_pair_off.as<uint64_t>(), cp, ctx->d_pairs.as<MyersWork>(), d_misc + 10); }
         }
         uint32_t h[8];
         SVIM_CUDA(cudaMemcpyAsync(h, d_misc + 8, 8 * 4, cudaMemcpyDeviceToHost, st));
@@ -539,8 +539,8 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs,
                           ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
             SVIM_CUDA(cudaMemsetAsync(d_misc + 11, 0, 4, st));
-            k_myers_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_pairs.as<MyersWork>(), n_work, ctx->d_pair_ed.as<int32_t>(),
-                                                  ctx->d_myers_scratch.as<uint8_t>(), maxlen, d_misc + 11, (unsigned long long*)(d_misc + 12), d_misc + 9);
+            { ctx->launches++; k_myers_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_pairs.as<MyersWork>(), n_work, ctx->d_pair_ed.as<int32_t>(),
+                                                  ctx->d_myers_scratch.as<uint8_t>(), maxlen, d_misc + 11, (unsigned long long*)(d_misc + 12), d_misc + 9); }
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();
     }
@@ -553,13 +553,13 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
                     ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_part_nkept.as<uint32_t>(), d_misc + 9};
         if (!list_small.empty()) {
             la.plist = d_small; la.n_list = (uint32_t)list_small.size();
-            k_linkage<<<la.n_list, 32, part_smem_bytes(max_m_small), st>>>(la, max_m_small);
+            { ctx->launches++; k_linkage<<<la.n_list, 32, part_smem_bytes(max_m_small), st>>>(la, max_m_small); }
         }
         if (!list_large.empty()) {
             size_t sm = part_smem_bytes(100);
             SVIM_CUDA(cudaFuncSetAttribute(k_linkage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             la.plist = d_large; la.n_list = (uint32_t)list_large.size();
-            k_linkage<<<la.n_list, 32, sm, st>>>(la, 100);
+            { ctx->launches++; k_linkage<<<la.n_list, 32, sm, st>>>(la, 100); }
         }
         SVIM_CUDA(cudaGetLastError());
     }
@@ -583,11 +583,11 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         SVIM_CUDA(ctx->d_members.ensure((size_t)(n_members + 1) * 4));
         SVIM_CUDA(cudaMemsetAsync(ctx->d_clusters.p, 0, (size_t)(n_clusters + 1) * sizeof(svim_cluster), st));
         if (n_clusters > 0) {
-            k_members<<<(uint32_t)(((uint64_t)P * 32 + 127) / 128), 128, 0, st>>>(ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(),
+            { ctx->launches++; k_members<<<(uint32_t)(((uint64_t)P * 32 + 127) / 128), 128, 0, st>>>(ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(),
                 ctx->d_order.as<uint32_t>(), ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_cl_off.as<uint32_t>(),
-                ctx->d_mem_off.as<uint32_t>(), P, ctx->d_clusters.as<svim_cluster>(), ctx->d_members.as<uint32_t>());
-            k_consolidate<<<(n_clusters + 63) / 64, 64, 0, st>>>(ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
-                                                               ctx->d_clusters.as<svim_cluster>(), d_misc + 9);
+                ctx->d_mem_off.as<uint32_t>(), P, ctx->d_clusters.as<svim_cluster>(), ctx->d_members.as<uint32_t>()); }
+            { ctx->launches++; k_consolidate<<<(n_clusters + 63) / 64, 64, 0, st>>>(ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
+                                                               ctx->d_clusters.as<svim_cluster>(), d_misc + 9); }
         }
         SVIM_CUDA(cudaGetLastError());
     }
@@ -600,14 +600,14 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         for (int k = 0; k < 2; ++k) { SVIM_CUDA(ctx->d_ckeys[k].ensure((size_t)n_clusters * 8)); SVIM_CUDA(ctx->d_cvals[k].ensure((size_t)n_clusters * 4)); }
         SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_clusters * 8));
         uint64_t* k2 = ctx->d_keys[0].as<uint64_t>();
-        k_final_keys<<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
-                                         ctx->d_ckeys[0].as<uint64_t>(), k2, ctx->d_cvals[0].as<uint32_t>());
+        { ctx->launches++; k_final_keys<<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
+                                         ctx->d_ckeys[0].as<uint64_t>(), k2, ctx->d_cvals[0].as<uint32_t>()); }
         uint64_t* k_out; uint32_t* v_out;
         int rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n_clusters, 64, &k_out, &v_out); if (rc) return rc;
-        k_gather<uint64_t><<<cb, 256, 0, st>>>(k2, v_out, n_clusters, ctx->d_ckeys[1].as<uint64_t>());
+        { ctx->launches++; k_gather<uint64_t><<<cb, 256, 0, st>>>(k2, v_out, n_clusters, ctx->d_ckeys[1].as<uint64_t>()); }
         std::swap(ctx->d_ckeys[0], ctx->d_ckeys[1]);
         rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n_clusters, 64, &k_out, &v_out); if (rc) return rc;
-        k_gather<svim_cluster><<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), v_out, n_clusters, ctx->d_clusters_sorted.as<svim_cluster>());
+        { ctx->launches++; k_gather<svim_cluster><<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), v_out, n_clusters, ctx->d_clusters_sorted.as<svim_cluster>()); }
         SVIM_CUDA(cudaGetLastError());
     }
     {

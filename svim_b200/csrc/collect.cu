@@ -259,7 +259,7 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     SVIM_CUDA(ctx->d_scan.ensure((size_t)(n + 1) * 8 * 2));
     cudaStream_t st = ctx->stream;
     const svim_sig* q = ctx->d_queue[which].as<svim_sig>();
-    k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>());
+    { ctx->launches++; k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>()); }
     cub::DoubleBuffer<uint64_t> dk(ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>());
     cub::DoubleBuffer<uint32_t> dv(ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>());
     size_t tmp = 0;
@@ -268,7 +268,7 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int)n, 0, 64, st));
     uint64_t* ins_len = ctx->d_scan.as<uint64_t>();
     uint64_t* ins_off = ins_len + (n + 1);
-    k_sig_gather<<<(n + 255) / 256, 256, 0, st>>>(q, dv.Current(), n, set.recs.as<svim_sig>(), ins_len);
+    { ctx->launches++; k_sig_gather<<<(n + 255) / 256, 256, 0, st>>>(q, dv.Current(), n, set.recs.as<svim_sig>(), ins_len); }
     size_t tmp2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ins_len, ins_off, (int)n + 1, st);
     SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp2));
@@ -281,7 +281,7 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     SVIM_CUDA(set.ins.ensure((size_t)total + 16));
     if (total > 0) {
         uint32_t blocks = (uint32_t)(((uint64_t)n * 32 + 255) / 256);
-        k_ins_gather<<<blocks, 256, 0, st>>>(ctx->soa, set.recs.as<svim_sig>(), ins_off, n, set.ins.as<uint8_t>());
+        { ctx->launches++; k_ins_gather<<<blocks, 256, 0, st>>>(ctx->soa, set.recs.as<svim_sig>(), ins_off, n, set.ins.as<uint8_t>()); }
     }
     SVIM_CUDA(cudaGetLastError());
     return 0;
@@ -317,8 +317,8 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         {
             StageTimer t(ctx, T_SCAN);
             if (n > 0)
-                k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                         ctx->d_counters.as<uint32_t>());
+                { ctx->launches++; k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                         ctx->d_counters.as<uint32_t>()); }
         }
         SVIM_CUDA(cudaGetLastError());
         SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));
@@ -327,8 +327,8 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         {
             StageTimer t(ctx, T_CHAIN);
             if (n_work > 0)
-                k_segment_chain<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work, qm, qt,
-                                                                     ctx->d_counters.as<uint32_t>());
+                { ctx->launches++; k_segment_chain<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work, qm, qt,
+                                                                     ctx->d_counters.as<uint32_t>()); }
         }
         SVIM_CUDA(cudaGetLastError());
         SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));

@@ -122,6 +122,8 @@ struct svimgpu_ctx {
     cudaEvent_t ev[2 * T_N];
     double ms[T_N];
     bool ev_rec[T_N];
+    int64_t launches = 0;
+    cudaEvent_t user_ev[2];
 
     void set_error(int code, const char* fmt, ...) __attribute__((format(printf, 3, 4)));
 };

@@ -70,7 +70,7 @@ static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_
     for (int r = 0; r < R; ++r) { co[r] = ct * (int64_t)sizeof(svim_cluster); cb[r] = all[2 * r] * (int64_t)sizeof(svim_cluster); mo[r] = mt * 4; mb[r] = all[2 * r + 1] * 4; ct += all[2 * r]; mt += all[2 * r + 1]; }
     // rebase this rank's member offsets to the global member array, then gather both arrays
     const uint32_t my_mem_base = (uint32_t)(mo[ctx->rank] / 4);
-    if (*n_clusters) k_rebase_clusters<<<(*n_clusters + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_clusters.as<svim_cluster>(), *n_clusters, my_mem_base);
+    if (*n_clusters) { ctx->launches++; k_rebase_clusters<<<(*n_clusters + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_clusters.as<svim_cluster>(), *n_clusters, my_mem_base); }
     SVIM_CUDA(ctx->d_xchg[0].ensure((size_t)(ct + 1) * sizeof(svim_cluster))); SVIM_CUDA(ctx->d_xchg[1].ensure((size_t)(mt + 1) * 4));
     rc = nccl_allgatherv_bytes(ctx, ctx->d_clusters.p, cb, co, ctx->d_xchg[0].as<uint8_t>()); if (rc) return rc;
     rc = nccl_allgatherv_bytes(ctx, ctx->d_members.p, mb, mo, ctx->d_xchg[1].as<uint8_t>()); if (rc) return rc;
@@ -125,7 +125,7 @@ int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collec
                 nt += all[12 * r + 2 * w]; it += all[12 * r + 2 * w + 1];
             }
             // make local records global before sending: record index += aln_base, INS offset += blob base
-            if (set.n) k_rebase_sigs<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, aln_base, (uint64_t)io[ctx->rank]);
+            if (set.n) { ctx->launches++; k_rebase_sigs<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, aln_base, (uint64_t)io[ctx->rank]); }
             SVIM_CUDA(ctx->d_xchg[0].ensure((size_t)(nt + 1) * sizeof(svim_sig))); SVIM_CUDA(ctx->d_xchg[1].ensure((size_t)it + 16));
             rc = nccl_allgatherv_bytes(ctx, set.recs.p, rb, ro, ctx->d_xchg[0].as<uint8_t>()); if (rc) return rc;
             rc = nccl_allgatherv_bytes(ctx, set.ins.p, ib, io, ctx->d_xchg[1].as<uint8_t>()); if (rc) return rc;
