@@ -253,9 +253,11 @@ __global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
     if (__any_sync(FULL, err)) { if (lane == 0) atomicExch(a.err, 1u); }
 }
 
-// INS partitions: list the pairs whose edit distance will be read (gate at :70 passes)
-__global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint32_t* samp_off, const uint32_t* samp_idx, const uint32_t* plist,
-                                                    uint32_t n_list, const uint64_t* pair_off, ClusterParams cp, MyersWork* work, uint32_t* n_work) {
+// INS partitions: list the pairs whose edit distance will be read (gate at :70 passes), binned by the
+// length of the longer haplotype.  mode 0 counts per bin, mode 1 fills `work` at the bin cursors.
+__global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint8_t* ins_blob, GenomeView g, const uint32_t* samp_off,
+                                                    const uint32_t* samp_idx, const uint32_t* plist, uint32_t n_list, const uint64_t* pair_off,
+                                                    ClusterParams cp, int mode, MyersWork* work, uint32_t* bin_cursor, uint32_t* err) {
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_list) return;
@@ -266,19 +268,30 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
     int i = 0, rowstart = 0;
     for (int64_t q0 = 0; q0 < npairs; q0 += 32) {
         const int64_t q = q0 + lane;
-        bool need = false; uint32_t pa = 0, pb = 0;
+        int bin = -1; uint32_t pa = 0, pb = 0;
         if (q < npairs) {
             while (q >= rowstart + (m - 1 - i)) { rowstart += m - 1 - i; ++i; }
             const int j = i + 1 + (int)(q - rowstart);
             pa = samp_idx[s0 + i]; pb = samp_idx[s0 + j];
-            SigView va{sig[pa].start, sig[pa].end, 0, 0, 0}, vb{sig[pb].start, sig[pb].end, 0, 0, 0};
-            need = ins_gate_needs_ed(va, vb, cp);
+            const svim_csig a = sig[pa], b = sig[pb];
+            SigView va{a.start, a.end, 0, 0, 0}, vb{b.start, b.end, 0, 0, 0};
+            if (ins_gate_needs_ed(va, vb, cp)) {
+                HapSource ha, hb;
+                if (pair_haps(a, b, ins_blob, g, ha, hb)) {
+                    const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
+                    bin = myers_bin_of(la > lb ? la : lb);
+                } else { atomicExch(err, 1u); }
+            }
         }
-        const unsigned msk = __ballot_sync(FULL, need);
-        uint32_t base = 0;
-        if (lane == 0 && msk) base = atomicAdd(n_work, (uint32_t)__popc(msk));
-        base = __shfl_sync(FULL, base, 0);
-        if (need) { MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[base + __popc(msk & ((1u << lane) - 1))] = wk; }
+#pragma unroll
+        for (int bb = 0; bb < MYERS_BINS; ++bb) {
+            const unsigned msk = __ballot_sync(FULL, bin == bb);
+            if (!msk) continue;
+            uint32_t base = 0;
+            if (lane == (__ffs(msk) - 1)) base = atomicAdd(bin_cursor + bb, (uint32_t)__popc(msk));
+            base = __shfl_sync(FULL, base, __ffs(msk) - 1);
+            if (mode == 1 && bin == bb) { MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[base + __popc(msk & ((1u << lane) - 1))] = wk; }
+        }
     }
 }
 
@@ -515,32 +528,51 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     if (!list_ins.empty()) {
         if (pair_total >= 0xffffffffull) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many insertion pairs"); return SVIMGPU_ERR_LIMIT; }
         SVIM_CUDA(ctx->d_pair_ed.ensure((size_t)pair_total * 4 + 4));
-        SVIM_CUDA(ctx->d_pairs.ensure((size_t)pair_total * sizeof(MyersWork) + 16));
+        const int64_t maxlen = ((ctx->cluster_max_ins_len + 200 + (int64_t)ceil(2.0 * cp.cluster_max_distance * cp.pos_norm) + 64) + 15) & ~15ll;
+        GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs, ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
+        if (!ctx->d_genome.p) { gv.n = 0; }
+        uint32_t* d_bins = d_misc + 16;        // [16..22) bin cursors, [24] n_fallback
+        uint32_t bin_cnt[8] = {0};
+        const uint32_t pblocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
         {
             StageTimer t(ctx, T_PAIRS);
-            uint32_t blocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
-            { ctx->launches++; k_ins_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins, (uint32_t)list_ins.size(),
-                                                ctx->d_pair_off.as<uint64_t>(), cp, ctx->d_pairs.as<MyersWork>(), d_misc + 10); }
+            SVIM_CUDA(cudaMemsetAsync(d_bins, 0, 16 * 4, st));
+            { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
+                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, d_bins, d_misc + 9); }
+            SVIM_CUDA(cudaMemcpyAsync(bin_cnt, d_bins, 8 * 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaStreamSynchronize(st));
         }
-        uint32_t h[8];
-        SVIM_CUDA(cudaMemcpyAsync(h, d_misc + 8, 8 * 4, cudaMemcpyDeviceToHost, st));
-        SVIM_CUDA(cudaStreamSynchronize(st));
-        const uint32_t n_work = h[2];
+        uint32_t bin_off[MYERS_BINS + 1] = {0};
+        for (int bb = 0; bb < MYERS_BINS; ++bb) bin_off[bb + 1] = bin_off[bb] + bin_cnt[bb];
+        const uint32_t n_work = bin_off[MYERS_BINS];
         cs.myers_pairs = n_work;
         if (n_work > 0 && !ctx->d_genome.p) { ctx->set_error(SVIMGPU_ERR_STATE, "insertion clustering needs svimgpu_set_genome"); return SVIMGPU_ERR_STATE; }
         if (n_work > 0) {
+            SVIM_CUDA(ctx->d_pairs.ensure((size_t)n_work * 2 * sizeof(MyersWork) + 16));   // work list + fallback list
+            MyersWork* d_work = ctx->d_pairs.as<MyersWork>();
+            {
+                StageTimer t(ctx, T_PAIRS);
+                SVIM_CUDA(cudaMemcpyAsync(d_bins, bin_off, MYERS_BINS * 4, cudaMemcpyHostToDevice, st));
+                { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
+                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_work, d_bins, d_misc + 9); }
+            }
             StageTimer t(ctx, T_MYERS);
-            const int64_t maxlen = ((ctx->cluster_max_ins_len + 200 + (int64_t)ceil(2.0 * cp.cluster_max_distance * cp.pos_norm) + 64) + 15) & ~15ll;
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            int blocks = sms * 5;
-            while (blocks > sms && (size_t)blocks * 4 * 3 * maxlen > ((size_t)8 << 30)) blocks -= sms;
-            blocks = (int)std::min<int64_t>(blocks, ((int64_t)n_work + 3) / 4);
-            SVIM_CUDA(ctx->d_myers_scratch.ensure((size_t)blocks * 4 * 3 * maxlen));
-            GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs,
-                          ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
-            SVIM_CUDA(cudaMemsetAsync(d_misc + 11, 0, 4, st));
-            { ctx->launches++; k_myers_pairs<<<blocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_pairs.as<MyersWork>(), n_work, ctx->d_pair_ed.as<int32_t>(),
-                                                  ctx->d_myers_scratch.as<uint8_t>(), maxlen, d_misc + 11, (unsigned long long*)(d_misc + 12), d_misc + 9); }
+            SVIM_CUDA(cudaMemsetAsync(d_misc + 24, 0, 16 * 4, st));      // [24] n_fallback, [25..31] per-bin cursors
+            MyersArgs ma{sorted, ctx->cluster_ins, gv, nullptr, 0, ctx->d_pair_ed.as<int32_t>(), nullptr, maxlen, nullptr, d_work + n_work, d_misc + 24,
+                         (unsigned long long*)(d_misc + 12), d_misc + 9};
+            // longest bins first so the tail of the launch sequence is made of short pairs
+            for (int bb = MYERS_BINS - 1; bb >= 0; --bb) {
+                ma.work = d_work + bin_off[bb]; ma.n_work = bin_cnt[bb]; ma.next = d_misc + 25 + bb; ma.maxlen = maxlen;
+                SVIM_CUDA(myers_launch_bin(ctx, bb, ma, ctx->d_myers_scratch[bb], sms));
+            }
+            uint32_t n_fb = 0;
+            SVIM_CUDA(cudaMemcpyAsync(&n_fb, d_misc + 24, 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaStreamSynchronize(st));
+            if (n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
+                ma.work = d_work + n_work; ma.n_work = n_fb; ma.next = d_misc + 31; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+                SVIM_CUDA(myers_launch_bin(ctx, 6, ma, ctx->d_myers_scratch[6], sms));
+            }
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();
     }

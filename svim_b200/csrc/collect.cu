@@ -39,25 +39,133 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, int lane, uint32_
     return x - v;
 }
 
-struct ScanAcc { uint32_t ref, read, nsum, hsum; };
+// class bit of a CIGAR word: 1 << op
+__device__ __forceinline__ uint32_t op_bit(uint32_t v) { return 1u << (v & 15u); }
 
-__device__ __forceinline__ void acc_op(uint32_t v, ScanAcc& a) {
-    uint32_t op = v & 15u, len = v >> 4;
-    a.ref += ((SVIM_MASK_REF_QUIRK >> op) & 1u) * len;
-    a.read += ((SVIM_MASK_READ >> op) & 1u) * len;
-    a.nsum += (op == OP_N) ? len : 0u;
-    a.hsum += (op == OP_H) ? len : 0u;
+// SUM: also accumulate N / H bases (only primaries with an SA tag need reference_end and the hard-clip test)
+template <bool SUM>
+__device__ __forceinline__ void acc_op(uint32_t v, uint32_t B, uint32_t& ref, uint32_t& read, uint32_t& nsum, uint32_t& hsum) {
+    const uint32_t len = v >> 4;
+    if (B & SVIM_MASK_REF_QUIRK) ref += len;
+    if (B & SVIM_MASK_READ) read += len;
+    if (SUM) {
+        if (B & (1u << OP_N)) nsum += len;
+        if (B & (1u << OP_H)) hsum += len;
+    }
 }
-__device__ __forceinline__ bool is_event(uint32_t v, uint32_t thresh) {
-    uint32_t op = v & 15u;
-    return ((0x6u >> op) & 1u) && v >= thresh;   // I or D with len >= min_sv_size
-}
+// SV-sized insertion or deletion: op in {I, D} and len >= min_sv_size (thresh = min_sv_size << 4)
+__device__ __forceinline__ bool is_event(uint32_t v, uint32_t B, uint32_t thresh) { return (B & 0x6u) && v >= thresh; }
 
 #define SCAN_UNROLL 4
 #define SCAN_BATCH 4     // alignments fetched per atomic
 
-__global__ void __launch_bounds__(256) k_cigar_scan(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
-                                                     uint32_t work_cap, uint32_t* cnt) {
+struct ScanRec { uint32_t i, qid; int32_t tid; int64_t ref_start, l_seq; };
+struct EvState { int64_t base_ref, base_read; uint32_t n_ev, n_tw, nsum, hsum; };
+
+// one 128-op group (a uint4 per lane) that holds at least one SV-sized I/D: exact positions via warp scans.
+// acc_ref/acc_read: lane-private consumption since the last fold; returned state has them folded in.
+template <bool SUM>
+__device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int lane, const ChainParams& p, const ScanRec& r, EvState st,
+                                            uint32_t acc_ref, uint32_t acc_read, DeviceEmitter out) {
+    const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+    st.base_ref += warp_sum(acc_ref); st.base_read += warp_sum(acc_read);
+    uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0;
+    uint32_t pre_ref[4], pre_read[4]; uint32_t my_ev = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t B = op_bit(v[k]);
+        pre_ref[k] = g_ref; pre_read[k] = g_read;
+        acc_op<SUM>(v[k], B, g_ref, g_read, g_n, g_h);
+        my_ev += is_event(v[k], B, thresh);
+    }
+    st.nsum += g_n; st.hsum += g_h;
+    uint32_t tot_ref, tot_read, tot_ev;
+    const uint32_t ex_ref = warp_excl_scan(g_ref, lane, tot_ref);
+    const uint32_t ex_read = warp_excl_scan(g_read, lane, tot_read);
+    const uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
+    uint32_t ord = st.n_ev + ex_ev;
+    uint32_t tw_before = 0;
+    if (p.all_bnds) {   // twins only for deletions: count DEL events before this lane
+        uint32_t my_del = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) my_del += (is_event(v[k], op_bit(v[k]), thresh) && (v[k] & 15u) == OP_D);
+        uint32_t tot_del; tw_before = st.n_tw + warp_excl_scan(my_del, lane, tot_del); st.n_tw += tot_del;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!is_event(v[k], op_bit(v[k]), thresh)) continue;
+        const uint32_t op = v[k] & 15u; const int64_t len = v[k] >> 4;
+        const int64_t pr = st.base_ref + ex_ref + pre_ref[k];
+        const int64_t pq = st.base_read + ex_read + pre_read[k];
+        svim_sig s; memset(&s, 0, sizeof(s));
+        s.contig1 = r.tid; s.contig2 = -1; s.start = (int32_t)(r.ref_start + pr); s.end = (int32_t)(r.ref_start + pr + len);
+        s.aln_idx = r.i; s.qname_id = r.qid; s.ordinal = ord++;
+        if (op == OP_D) {
+            s.type = SVIM_DEL;
+            out.sig(s);
+            if (p.all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
+                svim_sig b = s; b.type = SVIM_BND; b.contig2 = r.tid; b.pos = s.end; b.end = s.start + 1; b.ordinal = tw_before++;
+                if (len == 0) { b.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
+                out.twin(b);
+            }
+        } else {
+            s.type = SVIM_INS;
+            int64_t lo, hi; py_slice(pq, len, r.l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
+            s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
+            out.sig(s);
+        }
+    }
+    st.n_ev += tot_ev;
+    st.base_ref += tot_ref; st.base_read += tot_read;
+    return st;
+}
+
+// one uint4 (4 ops) of the lane: fast path accumulates into registers, rare path goes through scan_events
+#define SCAN_GROUP(W)                                                                                              \
+    {                                                                                                              \
+        const uint32_t B0 = op_bit((W).x), B1 = op_bit((W).y), B2 = op_bit((W).z), B3 = op_bit((W).w);             \
+        const bool ev = is_event((W).x, B0, thresh) | is_event((W).y, B1, thresh) | is_event((W).z, B2, thresh) |  \
+                        is_event((W).w, B3, thresh);                                                               \
+        if (__ballot_sync(FULL, ev) == 0) {                                                                        \
+            acc_op<SUM>((W).x, B0, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).y, B1, a_ref, a_read, a_n, a_h);      \
+            acc_op<SUM>((W).z, B2, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).w, B3, a_ref, a_read, a_n, a_h);      \
+        } else {                                                                                                   \
+            st = scan_events<SUM>((W), thresh, lane, p, r, st, a_ref, a_read, out);                                \
+            a_ref = 0; a_read = 0;                                                                                 \
+        }                                                                                                          \
+    }
+
+// stream one record's CIGAR.  Main loop: whole 512-op blocks without any bounds test.
+template <bool SUM>
+__device__ __forceinline__ void scan_cigar(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, const ChainParams& p, const ScanRec& r,
+                                           EvState& st_out, uint32_t& acc_ref_out, uint32_t& acc_read_out, const DeviceEmitter& out) {
+    const uint32_t n4 = (n + 3) >> 2;
+    const uint32_t full = (n >> 2) / (32 * SCAN_UNROLL) * (32 * SCAN_UNROLL);   // uint4 groups in complete 512-op blocks
+    EvState st = st_out;
+    uint32_t a_ref = 0, a_read = 0, a_n = 0, a_h = 0;
+    uint32_t base = 0;
+    for (; base < full; base += 32 * SCAN_UNROLL) {
+        uint4 w[SCAN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < SCAN_UNROLL; ++u) SCAN_GROUP(w[u])
+    }
+    for (; base < n4; base += 32) {   // ragged tail: bounds-checked, words past n_cigar zeroed
+        const uint32_t idx = base + lane;
+        uint4 w = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
+        if (idx == n4 - 1) {
+            const uint32_t rr = n & 3u;
+            if (rr == 1) { w.y = 0; w.z = 0; w.w = 0; } else if (rr == 2) { w.z = 0; w.w = 0; } else if (rr == 3) { w.w = 0; }
+        }
+        SCAN_GROUP(w)
+    }
+    st.nsum += a_n; st.hsum += a_h;    // lane-private partial sums (warp-reduced by the caller when needed)
+    st_out = st; acc_ref_out = a_ref; acc_read_out = a_read;
+}
+
+__global__ void __launch_bounds__(256, 3) k_cigar_scan(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
+                                                        uint32_t work_cap, uint32_t* cnt) {
     const int lane = threadIdx.x & 31;
     DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
     const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
@@ -68,98 +176,30 @@ __global__ void __launch_bounds__(256) k_cigar_scan(DevSoa a, ChainParams p, Sig
         if (lane == 0) first = atomicAdd(cnt + CNT_NEXT_ALN, (uint32_t)SCAN_BATCH);
         first = __shfl_sync(FULL, first, 0);
         if (first >= n_aln) break;
-        uint32_t last = min(first + SCAN_BATCH, n_aln);
+        const uint32_t last = min(first + SCAN_BATCH, n_aln);
         for (uint32_t i = first; i < last; ++i) {
             const uint32_t flag = a.flag[i];
             if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;   // SVIM_COLLECT.py:143
             const bool primary = !(flag & 0x800u);
             primaries += primary;
             const uint32_t n = a.n_cigar[i];
-            const uint32_t n4 = (n + 3) >> 2;
             const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]);
-            const int64_t ref_start = a.pos[i];
-            const int32_t tid = a.tid[i];
-            const uint32_t qid = a.qname_id[i];
-            const int64_t l_seq = a.l_seq[i];
-            ScanAcc acc = {0, 0, 0, 0};
-            int64_t base_ref = 0, base_read = 0;     // uniform: consumption before the lane-private accumulators
-            uint32_t n_ev = 0, n_tw = 0;
-            for (uint32_t base = 0; base < n4; base += 32 * SCAN_UNROLL) {
-                uint4 w[SCAN_UNROLL];
-#pragma unroll
-                for (int u = 0; u < SCAN_UNROLL; ++u) {
-                    uint32_t idx = base + u * 32 + lane;
-                    w[u] = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
-                    if (idx == n4 - 1) {   // words past n_cigar in the last 16-byte group
-                        uint32_t r = n & 3u;
-                        if (r == 1) { w[u].y = 0; w[u].z = 0; w[u].w = 0; } else if (r == 2) { w[u].z = 0; w[u].w = 0; } else if (r == 3) { w[u].w = 0; }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < SCAN_UNROLL; ++u) {
-                    const uint32_t v[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
-                    bool ev = is_event(v[0], thresh) | is_event(v[1], thresh) | is_event(v[2], thresh) | is_event(v[3], thresh);
-                    if (__ballot_sync(FULL, ev) == 0) {
-                        acc_op(v[0], acc); acc_op(v[1], acc); acc_op(v[2], acc); acc_op(v[3], acc);
-                        continue;
-                    }
-                    // ---- rare path: this 128-op group holds at least one SV-sized I/D -------------
-                    base_ref += warp_sum(acc.ref); base_read += warp_sum(acc.read);
-                    acc.ref = 0; acc.read = 0;
-                    ScanAcc g = {0, 0, 0, 0};
-                    uint32_t pre_ref[4], pre_read[4]; uint32_t my_ev = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { pre_ref[k] = g.ref; pre_read[k] = g.read; acc_op(v[k], g); my_ev += is_event(v[k], thresh); }
-                    acc.nsum += g.nsum; acc.hsum += g.hsum;
-                    uint32_t tot_ref, tot_read, tot_ev;
-                    uint32_t ex_ref = warp_excl_scan(g.ref, lane, tot_ref);
-                    uint32_t ex_read = warp_excl_scan(g.read, lane, tot_read);
-                    uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
-                    uint32_t ord = n_ev + ex_ev;
-                    uint32_t tw_before = 0;
-                    if (p.all_bnds) {   // twins only for deletions: count DEL events before this lane
-                        uint32_t my_del = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) my_del += (is_event(v[k], thresh) && (v[k] & 15u) == OP_D);
-                        uint32_t tot_del; tw_before = n_tw + warp_excl_scan(my_del, lane, tot_del); n_tw += tot_del;
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (!is_event(v[k], thresh)) continue;
-                        const uint32_t op = v[k] & 15u; const int64_t len = v[k] >> 4;
-                        const int64_t pr = base_ref + ex_ref + pre_ref[k];
-                        const int64_t pq = base_read + ex_read + pre_read[k];
-                        svim_sig s; memset(&s, 0, sizeof(s));
-                        s.contig1 = tid; s.contig2 = -1; s.start = (int32_t)(ref_start + pr); s.end = (int32_t)(ref_start + pr + len);
-                        s.aln_idx = i; s.qname_id = qid; s.ordinal = ord++;
-                        if (op == OP_D) {
-                            s.type = SVIM_DEL;
-                            out.sig(s);
-                            if (p.all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
-                                svim_sig b = s; b.type = SVIM_BND; b.contig2 = tid; b.pos = s.end; b.end = s.start + 1; b.ordinal = tw_before++;
-                                if (len == 0) { b.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
-                                out.twin(b);
-                            }
-                        } else {
-                            s.type = SVIM_INS;
-                            int64_t lo, hi; py_slice(pq, len, l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
-                            s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
-                            out.sig(s);
-                        }
-                    }
-                    n_ev += tot_ev;
-                    base_ref += tot_ref; base_read += tot_read;
-                }
-            }
+            ScanRec r; r.i = i; r.qid = a.qname_id[i]; r.tid = a.tid[i]; r.ref_start = a.pos[i]; r.l_seq = a.l_seq[i];
+            EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = 0; st.n_tw = 0; st.nsum = 0; st.hsum = 0;
+            uint32_t acc_ref = 0, acc_read = 0;
+            const bool need_summary = primary && a.sa_len[i] > 0;
+            if (need_summary) scan_cigar<true>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
+            else scan_cigar<false>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
             // ---- primaries with an SA tag: summary for the split-read analysis -----------------
-            if (primary && a.sa_len[i] > 0) {
-                const uint32_t hard = warp_sum(acc.hsum);
+            if (need_summary) {
+                const uint32_t hard = warp_sum(st.hsum);
                 if (hard == 0) {   // SVIM_COLLECT.py:47-48
-                    const int64_t ref_q = base_ref + warp_sum(acc.ref);
-                    const int64_t rd = base_read + warp_sum(acc.read);
-                    const int64_t nsum = warp_sum(acc.nsum);
+                    const int64_t ref_q = st.base_ref + warp_sum(acc_ref);
+                    const int64_t rd = st.base_read + warp_sum(acc_read);
+                    const int64_t nsum = warp_sum(st.nsum);
                     if (lane == 0) {
                         const uint32_t* c32 = a.cigar + a.cigar_off[i];
+                        const int64_t l_seq = r.l_seq;
                         CigarSummary cs; cigsum_init(cs);
                         if (l_seq == 0) {   // no SEQ: exact sequential summary (rare)
                             for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
@@ -170,10 +210,10 @@ __global__ void __launch_bounds__(256) k_cigar_scan(DevSoa a, ChainParams p, Sig
                             for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
                         }
                         Seg sg; int64_t rl;
-                        cigsum_finish(cs, l_seq, ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
+                        cigsum_finish(cs, l_seq, r.ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
                         uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
                         if (slot < work_cap) {
-                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = n_ev; wk.ord_twin = n_tw; wk.pad = 0;
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
                             wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
                             work[slot] = wk;
                         } else atomicExch(cnt + CNT_OVERFLOW, 1u);

@@ -1,21 +1,24 @@
 // K2b: haplotype edit distance (compute_haplotype_edit_distance, SVIM_clustering.py:32-45;
 // edlib.align NW distance) as a bit-parallel Myers/Hyyro kernel.
 //
-// One warp per insertion pair.  The longer haplotype is the pattern: its rows are cut into
-// 64-bit words, WPL consecutive words per lane, 32 lanes = one strip of 32*WPL*64 rows; longer
-// patterns take several strips with the horizontal deltas of the strip's bottom row parked in a
-// per-warp column buffer.  Lanes run as a systolic wavefront: at step s lane l handles text
-// column s-l and hands its bottom horizontal delta to lane l+1 with one shuffle.
-// Symbol equality is computed from bit-planes of a compact bijective symbol code (no
-// shared-memory Peq table): 2 planes when both haplotypes are pure ACGT, 3 with N, 8 otherwise,
-// so arbitrary bytes stay exact.
+// The longer haplotype of a pair is the pattern: its rows are cut into 64-bit words that live
+// in registers, one lane per word (or WPL consecutive words per lane for long patterns).  Lanes
+// run as a systolic wavefront: at step s lane l handles text column s-l and hands the horizontal
+// delta of its bottom row to lane l+1 with one shuffle.  Pairs are binned by pattern length so
+// that short patterns share a warp: a group of G = 4/8/16/32 lanes owns one pair, 32/G pairs per
+// warp (bins 0-3, one word per lane); bins 4/5 give a whole warp 2/4 words per lane, and bin 5
+// strip-mines patterns longer than 8192 rows, parking the horizontal deltas of a strip's bottom
+// row in a per-warp column buffer.
+// Symbol equality comes from bit-planes of a compact bijective symbol code (no shared-memory Peq
+// table): 3 planes cover A,C,G,T,N (+3 more codes); pairs containing any other byte take an
+// 8-plane kernel, so arbitrary bytes stay exact.
 //
 // Integer-ALU bound (~30 instructions per 64-cell word step); DRAM traffic is the two
 // haplotypes per pair.  No tensor cores: there is no dense contraction here.
 #pragma once
 #include "ctx.cuh"
 
-#define MYERS_WPL 4
+#define MYERS_BINS 6
 
 struct MyersWork { uint32_t a, b, slot, pad; };
 
@@ -25,20 +28,21 @@ struct HapSource {
     const uint8_t* p3; int64_t l3;   // reference right of it
 };
 
+struct GenomeView { const uint8_t* bytes; const int64_t* off; int32_t n; const int32_t* rank_to_tid; int32_t n_ranks; };
+
 __constant__ uint8_t c_symcode[256];
 
 static void myers_init_symcode() {
     uint8_t t[256];
     for (int i = 0; i < 256; ++i) t[i] = (uint8_t)i;
     const uint8_t acgtn[5] = {'A', 'C', 'G', 'T', 'N'};
-    for (int k = 0; k < 5; ++k) { uint8_t x = t[k]; t[k] = t[acgtn[k]]; t[acgtn[k]] = x; }   // swap -> bijection
-    // after the swaps t['A']=0.. and t[0]='A'..; apply .upper() folding on the input side
+    for (int k = 0; k < 5; ++k) { uint8_t x = t[k]; t[k] = t[acgtn[k]]; t[acgtn[k]] = x; }   // swaps keep it a bijection
     uint8_t lut[256];
-    for (int i = 0; i < 256; ++i) { int c = (i >= 'a' && i <= 'z') ? i - 32 : i; lut[i] = t[c]; }
+    for (int i = 0; i < 256; ++i) { int c = (i >= 'a' && i <= 'z') ? i - 32 : i; lut[i] = t[c]; }   // .upper()
     cudaMemcpyToSymbol(c_symcode, lut, 256);
 }
 
-__device__ __forceinline__ int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__host__ __device__ __forceinline__ int64_t clampi(int64_t v, int64_t lo, int64_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // hap = ref[max(0,ws):max(0,st)] + seq + ref[max(0,st):max(0,we)], fetch clamped to the contig
 __device__ __forceinline__ HapSource make_hap(const uint8_t* contig, int64_t clen, int64_t ws, int64_t we, int64_t st,
@@ -51,51 +55,129 @@ __device__ __forceinline__ HapSource make_hap(const uint8_t* contig, int64_t cle
     return h;
 }
 
-// materialise symbol codes; returns OR of all codes (warp-uniform)
-__device__ __forceinline__ uint32_t hap_write_codes(const HapSource& h, uint8_t* dst, int lane) {
+// both haplotypes of an insertion pair; false if the contig is not in the genome table
+__device__ __forceinline__ bool pair_haps(const svim_csig& a, const svim_csig& b, const uint8_t* ins_blob, const GenomeView& g,
+                                          HapSource& ha, HapSource& hb) {
+    const int32_t rank = a.contig_a;
+    const int32_t tid = (g.rank_to_tid && rank >= 0 && rank < g.n_ranks) ? g.rank_to_tid[rank] : -1;
+    if (tid < 0 || tid >= g.n) return false;
+    const uint8_t* contig = g.bytes + g.off[tid];
+    const int64_t clen = g.off[tid + 1] - g.off[tid];
+    const int64_t s1 = (int64_t)a.start, s2 = (int64_t)b.start;
+    const int64_t ws = (s1 < s2 ? s1 : s2) - 100, we = (s1 > s2 ? s1 : s2) + 100;
+    ha = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s1 < 0 ? 0 : s1, ins_blob + a.seq_off, a.seq_len);
+    hb = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s2 < 0 ? 0 : s2, ins_blob + b.seq_off, b.seq_len);
+    return true;
+}
+
+__host__ __device__ __forceinline__ int myers_bin_of(int64_t m) {
+    const int64_t W = (m + 63) >> 6;
+    return W <= 4 ? 0 : W <= 8 ? 1 : W <= 16 ? 2 : W <= 32 ? 3 : W <= 64 ? 4 : 5;
+}
+
+// materialise symbol codes with the G lanes of a group; returns OR of all codes (group-uniform)
+template <int G>
+__device__ __forceinline__ uint32_t hap_write_codes(const HapSource& h, uint8_t* dst, int gl, bool valid) {
     uint32_t orall = 0;
-    const int64_t n = h.l1 + h.l2 + h.l3;
-    for (int64_t k = lane; k < n; k += 32) {
-        uint8_t c = k < h.l1 ? h.p1[k] : (k < h.l1 + h.l2 ? h.p2[k - h.l1] : h.p3[k - h.l1 - h.l2]);
-        uint8_t code = c_symcode[c];
-        dst[k] = code; orall |= code;
+    if (valid) {
+        const int64_t n = h.l1 + h.l2 + h.l3;
+        for (int64_t k = gl; k < n; k += G) {
+            uint8_t c = k < h.l1 ? h.p1[k] : (k < h.l1 + h.l2 ? h.p2[k - h.l1] : h.p3[k - h.l1 - h.l2]);
+            uint8_t code = c_symcode[c];
+            dst[k] = code; orall |= code;
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) orall |= __shfl_xor_sync(0xffffffffu, orall, o);
+    for (int o = G / 2; o > 0; o >>= 1) orall |= __shfl_xor_sync(0xffffffffu, orall, o, G);
     return orall;
 }
 
+// one Myers word step (Hyyro): updates Pv/Mv, returns hout; ph/mh are the pre-shift horizontal vectors
+__device__ __forceinline__ int myers_word(uint64_t Eq, uint64_t& Pv, uint64_t& Mv, int hin, uint64_t& ph_out, uint64_t& mh_out) {
+    const uint64_t pv = Pv, mv = Mv;
+    const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
+    const uint64_t Xv = Eq | mv;
+    Eq |= hneg;
+    const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+    uint64_t Ph = mv | ~(Xh | pv);
+    uint64_t Mh = pv & Xh;
+    ph_out = Ph; mh_out = Mh;
+    const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+    Ph = (Ph << 1) | hpos; Mh = (Mh << 1) | hneg;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+    return hout;
+}
+
 template <int NP>
+__device__ __forceinline__ void build_planes(const uint8_t* __restrict__ pat, int64_t m, int64_t row0, uint64_t (&pl)[NP], uint64_t& vm) {
+    vm = 0;
+#pragma unroll
+    for (int b = 0; b < NP; ++b) pl[b] = 0;
+    if (row0 < m) {
+        const int cnt = (m - row0) < 64 ? (int)(m - row0) : 64;
+        for (int r = 0; r < cnt; ++r) {
+            const uint64_t code = pat[row0 + r];
+#pragma unroll
+            for (int b = 0; b < NP; ++b) pl[b] |= ((code >> b) & 1ull) << r;
+        }
+        vm = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
+    }
+}
+
+// ---- bins 0-3: groups of G lanes, one word per lane, pattern <= 64*G rows -------------------------
+template <int G, int NP>
+__device__ int32_t myers_small(const uint8_t* __restrict__ pat, int64_t m, const uint8_t* __restrict__ txt, int64_t n, int gl, bool valid) {
+    uint64_t pl[NP], vm, Pv = ~0ull, Mv = 0;
+    const int nl = valid ? (int)((m + 63) >> 6) : 0;
+    if (valid) build_planes<NP>(pat, m, (int64_t)gl * 64, pl, vm);
+    else { vm = 0; for (int b = 0; b < NP; ++b) pl[b] = 0; }
+    const int l_last = nl - 1, bit_last = (int)((m - 1) & 63);
+    int steps = valid ? (int)(n + nl - 1) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
+    int carry = 0, score = 0;
+    const bool lane_on = valid && gl < nl;
+    uint8_t c_next = (lane_on && gl == 0) ? txt[0] : 0;
+    for (int s = 0; s < steps; ++s) {
+        const int recv = __shfl_up_sync(0xffffffffu, carry, 1, G);
+        const int j = s - gl;
+        const uint8_t c = c_next;
+        if (lane_on && j + 1 >= 0 && j + 1 < n) c_next = txt[j + 1];
+        if (lane_on && j >= 0 && j < n) {
+            uint64_t Eq = vm;
+#pragma unroll
+            for (int b = 0; b < NP; ++b) Eq &= ~(pl[b] ^ (0ull - (uint64_t)((c >> b) & 1u)));
+            uint64_t ph, mh;
+            const int hout = myers_word(Eq, Pv, Mv, gl == 0 ? 1 : recv, ph, mh);
+            if (gl == l_last) score += (int)((ph >> bit_last) & 1ull) - (int)((mh >> bit_last) & 1ull);
+            carry = hout;
+        }
+    }
+    score = __shfl_sync(0xffffffffu, score, l_last < 0 ? 0 : l_last, G);
+    return (int32_t)(m + score);
+}
+
+// ---- bins 4-5 and the 8-plane kernel: a whole warp per pair, WPL words per lane, strip-mined -----------
+template <int WPL, int NP>
 __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const uint8_t* __restrict__ txt, int64_t n,
                              int8_t* __restrict__ hbuf, int lane) {
     const int64_t W = (m + 63) >> 6;
     int64_t score = 0;
-    const int64_t STRIP = 32 * MYERS_WPL;
+    const int64_t STRIP = 32 * WPL;
     for (int64_t sb = 0; sb < W; sb += STRIP) {
         const bool first_strip = (sb == 0), last_strip = (sb + STRIP >= W);
         const int64_t ws_cnt = (W - sb) < STRIP ? (W - sb) : STRIP;
-        const int nl = (int)((ws_cnt + MYERS_WPL - 1) / MYERS_WPL);   // active lanes
-        uint64_t pl[MYERS_WPL][NP], vm[MYERS_WPL], Pv[MYERS_WPL], Mv[MYERS_WPL];
+        const int nl = (int)((ws_cnt + WPL - 1) / WPL);   // active lanes
+        uint64_t pl[WPL][NP], vm[WPL], Pv[WPL], Mv[WPL];
 #pragma unroll
-        for (int k = 0; k < MYERS_WPL; ++k) {
-            const int64_t row0 = (sb + (int64_t)lane * MYERS_WPL + k) * 64;
-            vm[k] = 0; Pv[k] = ~0ull; Mv[k] = 0;
-#pragma unroll
-            for (int b = 0; b < NP; ++b) pl[k][b] = 0;
-            if (row0 < m) {
-                const int cnt = (m - row0) < 64 ? (int)(m - row0) : 64;
-                for (int r = 0; r < cnt; ++r) {
-                    const uint64_t code = pat[row0 + r];
-#pragma unroll
-                    for (int b = 0; b < NP; ++b) pl[k][b] |= ((code >> b) & 1ull) << r;
-                }
-                vm[k] = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
-            }
+        for (int k = 0; k < WPL; ++k) {
+            build_planes<NP>(pat, m, (sb + (int64_t)lane * WPL + k) * 64, pl[k], vm[k]);
+            Pv[k] = ~0ull; Mv[k] = 0;
         }
-        // where the pattern's last row lives (last strip only)
-        const int64_t wl = W - 1 - sb;
-        const int l_last = (int)(wl / MYERS_WPL), k_last = (int)(wl % MYERS_WPL), bit_last = (int)((m - 1) & 63);
-        int carry = 0;      // hout of this lane's last word at the previous step, for lane+1
+        const int64_t wl = W - 1 - sb;   // where the pattern's last row lives (last strip only)
+        const int l_last = (int)(wl / WPL), k_last = (int)(wl % WPL), bit_last = (int)((m - 1) & 63);
+        int carry = 0;
         const int64_t steps = n + nl - 1;
         uint8_t c_next = (lane == 0 && n > 0) ? txt[0] : 0;
         int8_t h_next = (!first_strip && lane == 0 && n > 0) ? hbuf[0] : 0;
@@ -104,7 +186,6 @@ __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const u
             const int64_t j = s - lane;
             const bool act = (lane < nl) && j >= 0 && j < n;
             const uint8_t c = c_next; const int8_t hb = h_next;
-            // prefetch for the next step (column j+1)
             if (lane < nl && j + 1 >= 0 && j + 1 < n) {
                 c_next = txt[j + 1];
                 if (!first_strip && lane == 0) h_next = hbuf[j + 1];
@@ -115,22 +196,13 @@ __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const u
 #pragma unroll
                 for (int b = 0; b < NP; ++b) mk[b] = 0ull - (uint64_t)((c >> b) & 1u);
 #pragma unroll
-                for (int k = 0; k < MYERS_WPL; ++k) {
+                for (int k = 0; k < WPL; ++k) {
                     uint64_t Eq = vm[k];
 #pragma unroll
                     for (int b = 0; b < NP; ++b) Eq &= ~(pl[k][b] ^ mk[b]);
-                    const uint64_t pv = Pv[k], mv = Mv[k];
-                    const uint64_t hneg = hin < 0 ? 1ull : 0ull, hpos = hin > 0 ? 1ull : 0ull;
-                    const uint64_t Xv = Eq | mv;
-                    Eq |= hneg;
-                    const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-                    uint64_t Ph = mv | ~(Xh | pv);
-                    uint64_t Mh = pv & Xh;
-                    if (last_strip && lane == l_last && k == k_last) score += (int64_t)((Ph >> bit_last) & 1ull) - (int64_t)((Mh >> bit_last) & 1ull);
-                    const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-                    Ph = (Ph << 1) | hpos; Mh = (Mh << 1) | hneg;
-                    Pv[k] = Mh | ~(Xv | Ph);
-                    Mv[k] = Ph & Xv;
+                    uint64_t ph, mh;
+                    const int hout = myers_word(Eq, Pv[k], Mv[k], hin, ph, mh);
+                    if (last_strip && lane == l_last && k == k_last) score += (int64_t)((ph >> bit_last) & 1ull) - (int64_t)((mh >> bit_last) & 1ull);
                     hin = hout;
                 }
                 carry = hin;
@@ -139,80 +211,184 @@ __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const u
         }
         __syncwarp();
     }
-    // score lives on lane l_last of the last strip
     const int64_t wl = (W - 1) % STRIP;
-    const int src = (int)(wl / MYERS_WPL);
-    score = __shfl_sync(0xffffffffu, score, src);
+    score = __shfl_sync(0xffffffffu, score, (int)(wl / WPL));
     return (int32_t)(m + score);
 }
 
-// haplotype pair -> edit distance; both haplotypes materialised as symbol codes in `scratch`
-__device__ int32_t myers_pair(const HapSource& ha, const HapSource& hb, uint8_t* scratch, int64_t maxlen, int lane) {
-    const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
-    if (la == 0) return (int32_t)lb;
-    if (lb == 0) return (int32_t)la;
-    const bool a_is_pat = la >= lb;
-    const HapSource& hp = a_is_pat ? ha : hb;
-    const HapSource& ht = a_is_pat ? hb : ha;
-    const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-    uint8_t* pat = scratch; uint8_t* txt = scratch + maxlen; int8_t* hbuf = (int8_t*)(scratch + 2 * maxlen);
-    uint32_t orall = hap_write_codes(hp, pat, lane) | hap_write_codes(ht, txt, lane);
-    __syncwarp();
-    if (orall < 4) return myers_run<2>(pat, m, txt, n, hbuf, lane);
-    if (orall < 8) return myers_run<3>(pat, m, txt, n, hbuf, lane);
-    return myers_run<8>(pat, m, txt, n, hbuf, lane);
+// ---- kernels -------------------------------------------------------------------------------------
+struct MyersArgs {
+    const svim_csig* sig; const uint8_t* ins_blob; GenomeView g;
+    const MyersWork* work; uint32_t n_work;
+    int32_t* ed_out;
+    uint8_t* scratch; int64_t maxlen;         // per group: 2*maxlen (3*maxlen for the whole-warp kernels)
+    uint32_t* next;                           // work cursor
+    MyersWork* fallback; uint32_t* n_fallback;   // pairs that need the 8-plane kernel
+    unsigned long long* cells; uint32_t* err;
+};
+
+template <int G>
+__global__ void __launch_bounds__(128) k_myers_small(MyersArgs a) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 2 * a.maxlen;
+    unsigned long long my_cells = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.next, (uint32_t)GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.n_work) break;
+        const uint32_t w = base + grp;
+        bool valid = w < a.n_work;
+        MyersWork wk{0, 0, 0, 0};
+        HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
+        if (valid) {
+            wk = a.work[w];
+            if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (gl == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } valid = false; }
+        }
+        const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
+        if (valid && (la == 0 || lb == 0)) { if (gl == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
+        uint8_t* pat = my; uint8_t* txt = my + a.maxlen;
+        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_codes<G>(ht, txt, gl, valid);
+        __syncwarp();
+        if (valid && orall >= 8) {   // symbols outside the 3-plane code space: defer to the 8-plane kernel
+            if (gl == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
+            valid = false;
+        }
+        const int32_t ed = myers_small<G, 3>(pat, m, txt, n, gl, valid);
+        if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
+        __syncwarp();
+    }
+    if (my_cells) atomicAdd(a.cells, my_cells);
 }
 
-struct GenomeView { const uint8_t* bytes; const int64_t* off; int32_t n; const int32_t* rank_to_tid; int32_t n_ranks; };
-
-// pairs between cluster-stage INS signatures (positions in the key-sorted array)
-__global__ void __launch_bounds__(128) k_myers_pairs(const svim_csig* sig, const uint8_t* ins_blob, GenomeView g, const MyersWork* work,
-                                                      uint32_t n_work, int32_t* ed_out, uint8_t* scratch, int64_t maxlen, uint32_t* next,
-                                                      unsigned long long* cells, uint32_t* err) {
+template <int WPL, int NP>
+__global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = scratch + (size_t)warp * 3 * maxlen;
+    uint8_t* my = a.scratch + (size_t)warp * 3 * a.maxlen;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(next, 1u);
+        if (lane == 0) w = atomicAdd(a.next, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_work) break;
-        const MyersWork wk = work[w];
-        const svim_csig a = sig[wk.a], b = sig[wk.b];
-        // contig of both signatures is the same (same partition)
-        const int32_t rank = a.contig_a;
-        int32_t tid = (g.rank_to_tid && rank >= 0 && rank < g.n_ranks) ? g.rank_to_tid[rank] : -1;
-        if (tid < 0 || tid >= g.n) { if (lane == 0) { atomicExch(err, 1u); ed_out[wk.slot] = 0; } continue; }
-        const uint8_t* contig = g.bytes + g.off[tid];
-        const int64_t clen = g.off[tid + 1] - g.off[tid];
-        const int64_t s1 = (int64_t)a.start, s2 = (int64_t)b.start;
-        const int64_t ws = (s1 < s2 ? s1 : s2) - 100, we = (s1 > s2 ? s1 : s2) + 100;
-        HapSource ha = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s1 < 0 ? 0 : s1, ins_blob + a.seq_off, a.seq_len);
-        HapSource hb = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s2 < 0 ? 0 : s2, ins_blob + b.seq_off, b.seq_len);
+        if (w >= a.n_work) break;
+        const MyersWork wk = a.work[w];
+        HapSource ha, hb;
+        if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (lane == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } continue; }
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
-        if (la > maxlen || lb > maxlen) { if (lane == 0) { atomicExch(err, 2u); ed_out[wk.slot] = 0; } continue; }
-        int32_t ed = myers_pair(ha, hb, my, maxlen, lane);
-        if (lane == 0) { ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
+        if (la > a.maxlen || lb > a.maxlen) { if (lane == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } continue; }
+        if (la == 0 || lb == 0) { if (lane == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); continue; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
+        uint8_t* pat = my; uint8_t* txt = my + a.maxlen; int8_t* hbuf = (int8_t*)(my + 2 * a.maxlen);
+        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_codes<32>(ht, txt, lane, true);
+        __syncwarp();
+        if (NP < 8 && orall >= (1u << NP)) {
+            if (lane == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
+            continue;
+        }
+        const int32_t ed = myers_run<WPL, NP>(pat, m, txt, n, hbuf, lane);
+        if (lane == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
+        __syncwarp();
     }
-    if (lane == 0 && my_cells) atomicAdd(cells, my_cells);
+    if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
 }
 
-// unit-test entry: explicit string pairs
-__global__ void __launch_bounds__(128) k_myers_strings(const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
-                                                        const int32_t* b_len, uint32_t n_pairs, int32_t* out, uint8_t* scratch, int64_t maxlen,
-                                                        uint32_t* next) {
+// unit-test entry: explicit string pairs, routed through the same bins as the pipeline
+template <int G>
+__global__ void __launch_bounds__(128) k_myers_strings_small(const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
+                                                              const int32_t* b_len, const uint32_t* list, uint32_t n_list, int32_t* out,
+                                                              uint8_t* scratch, int64_t maxlen, uint32_t* next) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t* my = scratch + ((size_t)warp * GPW + grp) * 2 * maxlen;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(next, (uint32_t)GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_list) break;
+        bool valid = base + grp < n_list;
+        const uint32_t w = valid ? list[base + grp] : 0;
+        HapSource ha{blob, 0, blob + a_off[w], valid ? a_len[w] : 0, blob, 0};
+        HapSource hb{blob, 0, blob + b_off[w], valid ? b_len[w] : 0, blob, 0};
+        const int64_t la = ha.l2, lb = hb.l2;
+        if (valid && (la == 0 || lb == 0)) { if (gl == 0) out[w] = (int32_t)(la + lb); valid = false; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
+        uint8_t* pat = my; uint8_t* txt = my + maxlen;
+        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_codes<G>(ht, txt, gl, valid);
+        __syncwarp();
+        int32_t ed;
+        if (__any_sync(0xffffffffu, valid && orall >= 8)) ed = myers_small<G, 8>(pat, m, txt, n, gl, valid);
+        else ed = myers_small<G, 3>(pat, m, txt, n, gl, valid);
+        if (valid && gl == 0) out[w] = ed;
+        __syncwarp();
+    }
+}
+
+template <int WPL>
+__global__ void __launch_bounds__(128) k_myers_strings_warp(const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
+                                                             const int32_t* b_len, const uint32_t* list, uint32_t n_list, int32_t* out,
+                                                             uint8_t* scratch, int64_t maxlen, uint32_t* next) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t* my = scratch + (size_t)warp * 3 * maxlen;
     for (;;) {
-        uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(next, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_pairs) break;
+        uint32_t i = 0;
+        if (lane == 0) i = atomicAdd(next, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n_list) break;
+        const uint32_t w = list[i];
         HapSource ha{blob, 0, blob + a_off[w], a_len[w], blob, 0};
         HapSource hb{blob, 0, blob + b_off[w], b_len[w], blob, 0};
-        int32_t ed = myers_pair(ha, hb, my, maxlen, lane);
+        const int64_t la = ha.l2, lb = hb.l2;
+        if (la == 0 || lb == 0) { if (lane == 0) out[w] = (int32_t)(la + lb); continue; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
+        uint8_t* pat = my; uint8_t* txt = my + maxlen; int8_t* hbuf = (int8_t*)(my + 2 * maxlen);
+        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_codes<32>(ht, txt, lane, true);
+        __syncwarp();
+        int32_t ed = orall < 8 ? myers_run<WPL, 3>(pat, m, txt, n, hbuf, lane) : myers_run<WPL, 8>(pat, m, txt, n, hbuf, lane);
         if (lane == 0) out[w] = ed;
+        __syncwarp();
     }
+}
+
+// launch one bin of pairs; bins 0-3 -> groups, 4/5 -> whole warp with 2/4 words per lane
+static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, DevBuf& scratch, int sms) {
+    if (a.n_work == 0) return cudaSuccess;
+    const int64_t cap = bin < 5 ? (int64_t)64 * (4 << bin) : a.maxlen;   // longest haplotype in the bin
+    a.maxlen = (cap + 15) & ~15ll;
+    int blocks = sms * 6;
+    const int per_warp_items = bin < 3 ? (8 >> bin) : 1;
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * per_warp_items - 1) / (4 * per_warp_items));
+    const size_t per_warp = (size_t)(bin < 4 ? 2 * per_warp_items : 3) * a.maxlen;
+    while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)8 << 30)) blocks -= sms;
+    cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
+    if (e != cudaSuccess) return e;
+    a.scratch = scratch.as<uint8_t>();
+    ctx->launches++;
+    switch (bin) {
+        case 0: k_myers_small<4><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case 1: k_myers_small<8><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case 2: k_myers_small<16><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case 3: k_myers_small<32><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case 4: k_myers_warp<2, 3><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        case 5: k_myers_warp<4, 3><<<blocks, 128, 0, ctx->stream>>>(a); break;
+        default: k_myers_warp<4, 8><<<blocks, 128, 0, ctx->stream>>>(a); break;   // 6: fallback, any bytes
+    }
+    return cudaGetLastError();
 }
