@@ -1,0 +1,40 @@
+"""Rebind the reference's two hot-path call sites to the B200 path.
+
+    import svim_b200.patch; svim_b200.patch.install()      # before the `svim` script imports its modules
+or  python -m svim_b200.patch alignment <workdir> <bam> <genome> [...]   # runs the installed `svim` CLI patched
+
+What is replaced (and nothing else):
+  svim.SVIM_COLLECT.analyze_alignment_file_coordsorted   (svim:102)
+  svim.SVIM_CLUSTER.cluster_sv_signatures                (svim:132,135)
+COMBINE / genotyping / VCF keep running on the objects returned here (same attribute surface).
+"""
+import runpy
+import shutil
+import sys
+
+
+def install():
+    import svim.SVIM_COLLECT as ref_collect      # the reference package must be importable
+    import svim.SVIM_CLUSTER as ref_cluster
+    from . import SVIM_COLLECT, SVIM_CLUSTER
+    from .io import read_alignments
+
+    def analyze_alignment_file_coordsorted(bam, options):
+        # `bam` is the pysam.AlignmentFile the CLI opened; decode the same file into the flattened buffer
+        return SVIM_COLLECT.analyze_alignment_file_coordsorted(read_alignments(options.bam_file), options)
+
+    ref_collect.analyze_alignment_file_coordsorted = analyze_alignment_file_coordsorted
+    ref_cluster.cluster_sv_signatures = SVIM_CLUSTER.cluster_sv_signatures
+
+
+def main():
+    install()
+    script = shutil.which("svim")
+    if script is None:
+        raise SystemExit("the reference's `svim` script is not on PATH")
+    sys.argv = [script] + sys.argv[1:]
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()
