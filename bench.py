@@ -180,18 +180,10 @@ def main():
     ctx.set_genome(genome)
     if world > 1:
         import torch.distributed as dist
+        from svim_b200 import parallel
         dist.init_process_group("gloo")
-        ids = [None]
-        if rank == 0:
-            buf = (C.c_ubyte * 128)()
-            assert ctx.lib.svimgpu_nccl_unique_id(buf) == 0
-            ids = [bytes(buf)]
-        dist.broadcast_object_list(ids, src=0)
-        idb = (C.c_ubyte * 128).from_buffer_copy(ids[0])
-        ctx._check(ctx.lib.svimgpu_comm_init(ctx.h, world, rank, idb))
-        sizes = [None] * world
-        dist.all_gather_object(sizes, batch.n)
-        aln_base = int(sum(sizes[:rank])); total_aln = int(sum(sizes))
+        parallel.init_comm(ctx)
+        aln_base, total_aln, _sizes = parallel.exchange_layout(batch.n)
     else:
         aln_base = 0; total_aln = batch.n
 
