@@ -117,6 +117,23 @@ EXPORTS = {
 _lib = None
 
 
+def _preload_nccl():
+    """libsvimgpu.so links libnccl.so.2 by soname.  PyTorch bundles a newer NCCL under the same soname; whichever
+    is loaded first wins for the whole process, and torch cannot run on the older system copy.  Load the bundled
+    one first (when present) so that `import torch` keeps working in either import order."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (spec.submodule_search_locations if spec else []):
+            p = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                C.CDLL(p, mode=C.RTLD_GLOBAL)
+                return p
+    except Exception:
+        pass
+    return None
+
+
 def load():
     """dlopen libsvimgpu.so and bind every export declared in include/svimgpu.h."""
     global _lib
@@ -124,6 +141,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise ImportError("libsvimgpu.so is missing: run `python -m svim_b200.build` (needs nvcc); "
                               "svim_b200 has no CPU fallback")
+        _preload_nccl()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)
