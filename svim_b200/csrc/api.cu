@@ -331,7 +331,7 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
             const int64_t cap = bin < 5 ? (int64_t)64 * (4 << bin) : maxlen;
             const int items = bin < 3 ? (8 >> bin) : 1;
             const int blocks = (int)std::min<int64_t>(148 * 4, ((int64_t)nl + 4 * items - 1) / (4 * items));
-            chk(d_scr.ensure((size_t)blocks * 4 * (bin < 4 ? 2 * items : 3) * cap));
+            chk(d_scr.ensure((size_t)blocks * 4 * (bin < 4 ? 5 * items : 6) * cap));
             if (e != cudaSuccess) break;
             uint32_t* nx = d_next.as<uint32_t>() + bin;
 #define SVIM_STR_ARGS d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), dl, nl, d_out.as<int32_t>(), d_scr.as<uint8_t>(), cap, nx

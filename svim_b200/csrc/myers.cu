@@ -216,12 +216,149 @@ __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const u
     return (int32_t)(m + score);
 }
 
+// ---- fast path (3 bit-planes, 32-bit halves, text masks travel with the carry) -------------------------
+// Text is pre-expanded to one uint32 per column: byte b = 0xFF if bit b of the symbol code is set.  Lane 0
+// injects it together with the incoming horizontal delta (+1 at the top boundary, or the previous strip's
+// bottom delta), every lane forwards the same word with its own bottom delta in the top byte, so each step
+// costs one shuffle and no per-lane text load.  The distance is read at the end from the vertical deltas of
+// the last column:  D[m][n] = n + sum_rows (Pv - Mv).
+template <int G>
+__device__ __forceinline__ uint32_t hap_write_txt32(const HapSource& h, uint32_t* dst, int gl, bool valid) {
+    uint32_t orall = 0;
+    if (valid) {
+        const int64_t n = h.l1 + h.l2 + h.l3;
+        for (int64_t k = gl; k < n; k += G) {
+            const uint8_t c = k < h.l1 ? h.p1[k] : (k < h.l1 + h.l2 ? h.p2[k - h.l1] : h.p3[k - h.l1 - h.l2]);
+            const uint32_t code = c_symcode[c];
+            dst[k] = ((code & 1u) ? 0xFFu : 0u) | ((code & 2u) ? 0xFF00u : 0u) | ((code & 4u) ? 0xFF0000u : 0u);
+            orall |= code;
+        }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) orall |= __shfl_xor_sync(0xffffffffu, orall, o, G);
+    return orall;
+}
+
+struct Word32 { uint32_t p0l, p0h, p1l, p1h, p2l, p2h, pvl, pvh, mvl, mvh; };
+
+__device__ __forceinline__ void word_init(Word32& w, const uint8_t* __restrict__ pat, int64_t m, int64_t row0) {
+    uint64_t pl[3], vm;
+    build_planes<3>(pat, m, row0, pl, vm);
+    w.p0l = (uint32_t)pl[0]; w.p0h = (uint32_t)(pl[0] >> 32); w.p1l = (uint32_t)pl[1]; w.p1h = (uint32_t)(pl[1] >> 32);
+    w.p2l = (uint32_t)pl[2]; w.p2h = (uint32_t)(pl[2] >> 32);
+    w.pvl = w.pvh = 0xffffffffu; w.mvl = w.mvh = 0u;
+}
+
+// vertical-delta sum of the rows of this word that belong to the pattern
+__device__ __forceinline__ int word_vsum(const Word32& w, int64_t m, int64_t row0) {
+    if (row0 >= m) return 0;
+    const int cnt = (m - row0) < 64 ? (int)(m - row0) : 64;
+    const uint64_t vm = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
+    const uint64_t pv = ((uint64_t)w.pvh << 32) | w.pvl, mv = ((uint64_t)w.mvh << 32) | w.mvl;
+    return __popcll(pv & vm) - __popcll(mv & vm);
+}
+
+// one word step; e = hin + 1 in {0,1,2}; returns hout + 1
+__device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t e) {
+    const uint32_t hneg = 1u >> e, hpos = e >> 1;
+    const uint32_t eql = ~((w.p0l ^ m0) | (w.p1l ^ m1) | (w.p2l ^ m2));
+    const uint32_t eqh = ~((w.p0h ^ m0) | (w.p1h ^ m1) | (w.p2h ^ m2));
+    const uint32_t xvl = eql | w.mvl, xvh = eqh | w.mvh;
+    const uint32_t el = eql | hneg;
+    uint32_t sl, sh;
+    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(sl), "=r"(sh) : "r"(el & w.pvl), "r"(w.pvl), "r"(eqh & w.pvh), "r"(w.pvh));
+    const uint32_t xhl = (sl ^ w.pvl) | el, xhh = (sh ^ w.pvh) | eqh;
+    const uint32_t phl = w.mvl | ~(xhl | w.pvl), phh = w.mvh | ~(xhh | w.pvh);
+    const uint32_t mhl = w.pvl & xhl, mhh = w.pvh & xhh;
+    const uint32_t eout = 1u + (phh >> 31) - (mhh >> 31);
+    const uint32_t phl2 = (phl << 1) | hpos, phh2 = __funnelshift_l(phl, phh, 1);
+    const uint32_t mhl2 = (mhl << 1) | hneg, mhh2 = __funnelshift_l(mhl, mhh, 1);
+    w.pvl = mhl2 | ~(xvl | phl2); w.pvh = mhh2 | ~(xvh | phh2);
+    w.mvl = phl2 & xvl; w.mvh = phh2 & xvh;
+    return eout;
+}
+
+// bins 0-3: G lanes per pair, one word per lane
+template <int G>
+__device__ int32_t myers_fast_small(const uint8_t* __restrict__ pat, int m, const uint32_t* __restrict__ txt32, int n, int gl, bool valid) {
+    Word32 w;
+    const int nl = valid ? ((m + 63) >> 6) : 0;
+    if (valid) word_init(w, pat, m, (int64_t)gl * 64);
+    else { w.p0l = w.p0h = w.p1l = w.p1h = w.p2l = w.p2h = 0; w.pvl = w.pvh = w.mvl = w.mvh = 0; }
+    int steps = valid ? (n + nl - 1) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
+    const bool lane_on = valid && gl < nl;
+    const bool head = lane_on && gl == 0;
+    uint32_t pk_out = 0;
+    uint32_t t_nxt = head ? txt32[0] : 0u;
+    for (int s = 0; s < steps; ++s) {
+        const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1, G);
+        const uint32_t t_cur = t_nxt;
+        if (head && s + 1 < n) t_nxt = txt32[s + 1];
+        const uint32_t pk = gl == 0 ? (t_cur | (2u << 24)) : recv;
+        const int j = s - gl;
+        if (lane_on && (unsigned)j < (unsigned)n) {
+            const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111), m2 = __byte_perm(pk, 0, 0x2222);
+            const uint32_t eout = word_step(w, m0, m1, m2, pk >> 24);
+            pk_out = (pk & 0x00ffffffu) | (eout << 24);
+        }
+    }
+    int v = lane_on ? word_vsum(w, m, (int64_t)gl * 64) : 0;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
+    return n + v;
+}
+
+// bins 4-5: a warp per pair, WPL words per lane, strips of 32*WPL words
+template <int WPL>
+__device__ int32_t myers_fast_warp(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
+                                   uint8_t* __restrict__ hbuf, int lane) {
+    const int64_t W = (m + 63) >> 6;
+    const int64_t STRIP = 32 * WPL;
+    int vsum = 0;
+    for (int64_t sb = 0; sb < W; sb += STRIP) {
+        const bool first_strip = (sb == 0), last_strip = (sb + STRIP >= W);
+        const int64_t ws_cnt = (W - sb) < STRIP ? (W - sb) : STRIP;
+        const int nl = (int)((ws_cnt + WPL - 1) / WPL);
+        Word32 w[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) word_init(w[k], pat, m, (sb + (int64_t)lane * WPL + k) * 64);
+        const int steps = n + nl - 1;
+        const bool lane_on = lane < nl, head = lane == 0;
+        uint32_t pk_out = 0;
+        uint32_t t_nxt = head ? txt32[0] : 0u;
+        uint32_t h_nxt = (head && !first_strip) ? hbuf[0] : 2u;
+        for (int s = 0; s < steps; ++s) {
+            const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1);
+            const uint32_t t_cur = t_nxt, h_cur = h_nxt;
+            if (head && s + 1 < n) { t_nxt = txt32[s + 1]; if (!first_strip) h_nxt = hbuf[s + 1]; }
+            const uint32_t pk = head ? (t_cur | (h_cur << 24)) : recv;
+            const int j = s - lane;
+            if (lane_on && (unsigned)j < (unsigned)n) {
+                const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111), m2 = __byte_perm(pk, 0, 0x2222);
+                uint32_t e = pk >> 24;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) e = word_step(w[k], m0, m1, m2, e);
+                pk_out = (pk & 0x00ffffffu) | (e << 24);
+                if (!last_strip && lane == 31) hbuf[j] = (uint8_t)e;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) vsum += lane_on ? word_vsum(w[k], m, (sb + (int64_t)lane * WPL + k) * 64) : 0;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+    return n + vsum;
+}
+
 // ---- kernels -------------------------------------------------------------------------------------
 struct MyersArgs {
     const svim_csig* sig; const uint8_t* ins_blob; GenomeView g;
     const MyersWork* work; uint32_t n_work;
     int32_t* ed_out;
-    uint8_t* scratch; int64_t maxlen;         // per group: 2*maxlen (3*maxlen for the whole-warp kernels)
+    uint8_t* scratch; int64_t maxlen;         // per group: 5*maxlen (pattern codes + 4-byte text masks), +1 column buffer for the whole-warp kernels
     uint32_t* next;                           // work cursor
     MyersWork* fallback; uint32_t* n_fallback;   // pairs that need the 8-plane kernel
     unsigned long long* cells; uint32_t* err;
@@ -232,7 +369,7 @@ __global__ void __launch_bounds__(128) k_myers_small(MyersArgs a) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 2 * a.maxlen;
+    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 5 * a.maxlen;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t base = 0;
@@ -253,14 +390,14 @@ __global__ void __launch_bounds__(128) k_myers_small(MyersArgs a) {
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + a.maxlen;
-        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_codes<G>(ht, txt, gl, valid);
+        uint8_t* pat = my; uint32_t* txt32 = (uint32_t*)(my + a.maxlen);
+        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_txt32<G>(ht, txt32, gl, valid);
         __syncwarp();
         if (valid && orall >= 8) {   // symbols outside the 3-plane code space: defer to the 8-plane kernel
             if (gl == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
             valid = false;
         }
-        const int32_t ed = myers_small<G, 3>(pat, m, txt, n, gl, valid);
+        const int32_t ed = myers_fast_small<G>(pat, (int)m, txt32, (int)n, gl, valid);
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
@@ -271,7 +408,7 @@ template <int WPL, int NP>
 __global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = a.scratch + (size_t)warp * 3 * a.maxlen;
+    uint8_t* my = a.scratch + (size_t)warp * 6 * a.maxlen;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t w = 0;
@@ -288,14 +425,22 @@ __global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + a.maxlen; int8_t* hbuf = (int8_t*)(my + 2 * a.maxlen);
-        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_codes<32>(ht, txt, lane, true);
-        __syncwarp();
-        if (NP < 8 && orall >= (1u << NP)) {
-            if (lane == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
-            continue;
+        uint8_t* pat = my; uint8_t* txt = my + a.maxlen; int8_t* hbuf = (int8_t*)(my + 5 * a.maxlen);
+        int32_t ed;
+        if (NP == 3) {
+            uint32_t* txt32 = (uint32_t*)(my + a.maxlen);
+            uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_txt32<32>(ht, txt32, lane, true);
+            __syncwarp();
+            if (orall >= 8) {
+                if (lane == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
+                continue;
+            }
+            ed = myers_fast_warp<WPL>(pat, m, txt32, (int)n, (uint8_t*)hbuf, lane);
+        } else {
+            hap_write_codes<32>(hp, pat, lane, true); hap_write_codes<32>(ht, txt, lane, true);
+            __syncwarp();
+            ed = myers_run<WPL, NP>(pat, m, txt, n, hbuf, lane);
         }
-        const int32_t ed = myers_run<WPL, NP>(pat, m, txt, n, hbuf, lane);
         if (lane == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
@@ -310,7 +455,7 @@ __global__ void __launch_bounds__(128) k_myers_strings_small(const uint8_t* blob
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = scratch + ((size_t)warp * GPW + grp) * 2 * maxlen;
+    uint8_t* my = scratch + ((size_t)warp * GPW + grp) * 5 * maxlen;
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(next, (uint32_t)GPW);
@@ -326,12 +471,15 @@ __global__ void __launch_bounds__(128) k_myers_strings_small(const uint8_t* blob
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + maxlen;
-        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_codes<G>(ht, txt, gl, valid);
+        uint8_t* pat = my; uint8_t* txt = my + maxlen; uint32_t* txt32 = (uint32_t*)(my + maxlen);
+        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_txt32<G>(ht, txt32, gl, valid);
         __syncwarp();
         int32_t ed;
-        if (__any_sync(0xffffffffu, valid && orall >= 8)) ed = myers_small<G, 8>(pat, m, txt, n, gl, valid);
-        else ed = myers_small<G, 3>(pat, m, txt, n, gl, valid);
+        if (__any_sync(0xffffffffu, valid && orall >= 8)) {   // some pair of this warp needs 8 planes: generic kernel for all of them
+            hap_write_codes<G>(ht, txt, gl, valid);
+            __syncwarp();
+            ed = myers_small<G, 8>(pat, m, txt, n, gl, valid);
+        } else ed = myers_fast_small<G>(pat, (int)m, txt32, (int)n, gl, valid);
         if (valid && gl == 0) out[w] = ed;
         __syncwarp();
     }
@@ -343,7 +491,7 @@ __global__ void __launch_bounds__(128) k_myers_strings_warp(const uint8_t* blob,
                                                              uint8_t* scratch, int64_t maxlen, uint32_t* next) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = scratch + (size_t)warp * 3 * maxlen;
+    uint8_t* my = scratch + (size_t)warp * 6 * maxlen;
     for (;;) {
         uint32_t i = 0;
         if (lane == 0) i = atomicAdd(next, 1u);
@@ -358,10 +506,12 @@ __global__ void __launch_bounds__(128) k_myers_strings_warp(const uint8_t* blob,
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + maxlen; int8_t* hbuf = (int8_t*)(my + 2 * maxlen);
-        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_codes<32>(ht, txt, lane, true);
+        uint8_t* pat = my; uint8_t* txt = my + maxlen; uint32_t* txt32 = (uint32_t*)(my + maxlen); int8_t* hbuf = (int8_t*)(my + 5 * maxlen);
+        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_txt32<32>(ht, txt32, lane, true);
         __syncwarp();
-        int32_t ed = orall < 8 ? myers_run<WPL, 3>(pat, m, txt, n, hbuf, lane) : myers_run<WPL, 8>(pat, m, txt, n, hbuf, lane);
+        int32_t ed;
+        if (orall < 8) ed = myers_fast_warp<WPL>(pat, m, txt32, (int)n, (uint8_t*)hbuf, lane);
+        else { hap_write_codes<32>(ht, txt, lane, true); __syncwarp(); ed = myers_run<WPL, 8>(pat, m, txt, n, hbuf, lane); }
         if (lane == 0) out[w] = ed;
         __syncwarp();
     }
@@ -375,7 +525,7 @@ static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, DevB
     int blocks = sms * 6;
     const int per_warp_items = bin < 3 ? (8 >> bin) : 1;
     blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * per_warp_items - 1) / (4 * per_warp_items));
-    const size_t per_warp = (size_t)(bin < 4 ? 2 * per_warp_items : 3) * a.maxlen;
+    const size_t per_warp = (size_t)(bin < 4 ? 5 * per_warp_items : 6) * a.maxlen;
     while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)8 << 30)) blocks -= sms;
     cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
     if (e != cudaSuccess) return e;
