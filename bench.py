@@ -264,6 +264,12 @@ def main():
     alg_bytes = batch.algorithmic_bytes() + int(cst.n_signatures) * 48
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    traffic = None      # dram__bytes_read+write of k_cigar_scan from the committed ncu capture of this same workload
+    tp = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        if t.get("workload") == args.workload and abs(t.get("scale", 0) - args.scale) < 1e-9:
+            traffic = t["dram_bytes_per_launch"]
     out = {
         "metric": METRIC, "value": total_aln / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 CIGAR words / i64 coordinates / f64 distances",
@@ -276,7 +282,7 @@ def main():
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "python_object_materialisation_s": obj_s},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
         "clocks": clocks,
     }

@@ -50,11 +50,12 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_vals[1], &ctx->d_scan, &ctx->sets[0].recs, &ctx->sets[0].ins, &ctx->sets[1].recs, &ctx->sets[1].ins, &ctx->d_csig,
                       &ctx->d_csig_sorted, &ctx->d_cins, &ctx->d_order, &ctx->d_head, &ctx->d_partid, &ctx->d_part_off, &ctx->d_samp_off,
                       &ctx->d_samp_idx, &ctx->d_labels, &ctx->d_part_ncl, &ctx->d_part_nkept, &ctx->d_part_stats, &ctx->d_plist,
-                      &ctx->d_myers_scratch[0], &ctx->d_myers_scratch[1], &ctx->d_myers_scratch[2], &ctx->d_myers_scratch[3], &ctx->d_myers_scratch[4], &ctx->d_myers_scratch[5], &ctx->d_myers_scratch[6], &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
+                      &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
                       &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
                       &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3]};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
+    for (int i = 0; i < 12; ++i) ctx->d_myers_scratch[i].release();
     for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -310,50 +311,49 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         lists[myers_bin_of(m)].push_back((uint32_t)i);   // same binning as the pipeline (k_ins_pairs)
     }
     maxlen = (maxlen + 15) & ~15ll;
-    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_scr, d_next, d_list;
+    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_next, d_list, d_fb, d_misc;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     chk(d_blob.ensure((size_t)blob_bytes + 16)); chk(d_ao.ensure((size_t)n_pairs * 8)); chk(d_al.ensure((size_t)n_pairs * 4)); chk(d_bo.ensure((size_t)n_pairs * 8));
-    chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_next.ensure(64)); chk(d_list.ensure((size_t)n_pairs * 4));
+    chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_next.ensure(64 * 4)); chk(d_list.ensure((size_t)n_pairs * 4));
+    chk(d_fb.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_misc.ensure(64));
+    uint32_t h_err = 0;
     if (e == cudaSuccess) {
         chk(cudaMemcpyAsync(d_blob.p, blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_ao.p, a_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_al.p, a_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bo.p, b_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bl.p, b_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
-        chk(cudaMemsetAsync(d_next.p, 0, 64, ctx->stream));
+        chk(cudaMemsetAsync(d_next.p, 0, 64 * 4, ctx->stream)); chk(cudaMemsetAsync(d_misc.p, 0, 64, ctx->stream));
+        uint32_t* nx = d_next.as<uint32_t>();
+        MyersArgs ma{nullptr, nullptr, GenomeView{nullptr, nullptr, 0, nullptr, 0}, nullptr, 0, d_out.as<int32_t>(), nullptr, maxlen, nullptr,
+                     d_fb.as<MyersWork>(), nx + 32, (unsigned long long*)d_misc.p, (uint32_t*)d_misc.p + 4};
         uint32_t off = 0;
         for (int bin = 0; bin < MYERS_BINS && e == cudaSuccess; ++bin) {
             const uint32_t nl = (uint32_t)lists[bin].size();
             if (!nl) continue;
             uint32_t* dl = d_list.as<uint32_t>() + off; off += nl;
             chk(cudaMemcpyAsync(dl, lists[bin].data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
-            const int64_t cap = bin < 5 ? (int64_t)64 * (4 << bin) : maxlen;
-            const int items = bin < 3 ? (8 >> bin) : 1;
-            const int blocks = (int)std::min<int64_t>(148 * 4, ((int64_t)nl + 4 * items - 1) / (4 * items));
-            chk(d_scr.ensure((size_t)blocks * 4 * (bin < 4 ? 5 * items : 6) * cap));
-            if (e != cudaSuccess) break;
-            uint32_t* nx = d_next.as<uint32_t>() + bin;
-#define SVIM_STR_ARGS d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), dl, nl, d_out.as<int32_t>(), d_scr.as<uint8_t>(), cap, nx
-            ctx->launches++;
-            switch (bin) {
-                case 0: k_myers_strings_small<4><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-                case 1: k_myers_strings_small<8><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-                case 2: k_myers_strings_small<16><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-                case 3: k_myers_strings_small<32><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-                case 4: k_myers_strings_warp<2><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-                default: k_myers_strings_warp<4><<<blocks, 128, 0, ctx->stream>>>(SVIM_STR_ARGS); break;
-            }
-#undef SVIM_STR_ARGS
-            chk(cudaGetLastError());
-            chk(cudaStreamSynchronize(ctx->stream));   // d_scr is re-used by the next bin
+            StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), dl};
+            ma.n_work = nl; ma.next = nx + bin; ma.maxlen = maxlen;
+            chk(myers_launch_bin<true>(ctx, bin, ma, sp, ctx->d_myers_scratch[bin], 148));
+        }
+        uint32_t n_fb = 0;
+        chk(cudaMemcpyAsync(&n_fb, nx + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        chk(cudaStreamSynchronize(ctx->stream));
+        if (e == cudaSuccess && n_fb > 0) {   // pairs with bytes outside the 3-plane code space
+            StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
+            ma.work = d_fb.as<MyersWork>(); ma.n_work = n_fb; ma.next = nx + 40; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+            chk(myers_launch_bin<true>(ctx, MYERS_BINS, ma, sp, ctx->d_myers_scratch[MYERS_BINS], 148));
         }
         chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        chk(cudaMemcpyAsync(&h_err, (uint32_t*)d_misc.p + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaStreamSynchronize(ctx->stream));
     }
-    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_scr, &d_next, &d_list};
+    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_next, &d_list, &d_fb, &d_misc};
     for (DevBuf* b : all) b->release();
     if (e != cudaSuccess) { ctx->set_error(SVIMGPU_ERR_CUDA, "edit_distance: %s", cudaGetErrorString(e)); return SVIMGPU_ERR_CUDA; }
+    if (h_err) { ctx->set_error(SVIMGPU_ERR_LIMIT, "edit_distance: internal length bound exceeded (%u)", h_err); return SVIMGPU_ERR_LIMIT; }
     return 0;
 }
 

@@ -528,18 +528,18 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     if (!list_ins.empty()) {
         if (pair_total >= 0xffffffffull) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many insertion pairs"); return SVIMGPU_ERR_LIMIT; }
         SVIM_CUDA(ctx->d_pair_ed.ensure((size_t)pair_total * 4 + 4));
-        const int64_t maxlen = ((ctx->cluster_max_ins_len + 200 + (int64_t)ceil(2.0 * cp.cluster_max_distance * cp.pos_norm) + 64) + 15) & ~15ll;
+        const int64_t maxlen = ((ctx->cluster_max_ins_len + (int64_t)ceil(fabs(2.0 * cp.cluster_max_distance * cp.pos_norm)) + 64) + 15) & ~15ll;
         GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs, ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
         if (!ctx->d_genome.p) { gv.n = 0; }
-        uint32_t* d_bins = d_misc + 16;        // [16..22) bin cursors, [24] n_fallback
-        uint32_t bin_cnt[8] = {0};
+        uint32_t* d_bins = d_misc + 16;        // [16..26) bin cursors; [32] n_fallback, [33..44) per-bin work cursors
+        uint32_t bin_cnt[MYERS_BINS] = {0};
         const uint32_t pblocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
         {
             StageTimer t(ctx, T_PAIRS);
             SVIM_CUDA(cudaMemsetAsync(d_bins, 0, 16 * 4, st));
             { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
                                                 (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, d_bins, d_misc + 9); }
-            SVIM_CUDA(cudaMemcpyAsync(bin_cnt, d_bins, 8 * 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaMemcpyAsync(bin_cnt, d_bins, MYERS_BINS * 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
         }
         uint32_t bin_off[MYERS_BINS + 1] = {0};
@@ -558,20 +558,21 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             }
             StageTimer t(ctx, T_MYERS);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            SVIM_CUDA(cudaMemsetAsync(d_misc + 24, 0, 16 * 4, st));      // [24] n_fallback, [25..31] per-bin cursors
-            MyersArgs ma{sorted, ctx->cluster_ins, gv, nullptr, 0, ctx->d_pair_ed.as<int32_t>(), nullptr, maxlen, nullptr, d_work + n_work, d_misc + 24,
+            SVIM_CUDA(cudaMemsetAsync(d_misc + 32, 0, 16 * 4, st));
+            MyersArgs ma{sorted, ctx->cluster_ins, gv, nullptr, 0, ctx->d_pair_ed.as<int32_t>(), nullptr, maxlen, nullptr, d_work + n_work, d_misc + 32,
                          (unsigned long long*)(d_misc + 12), d_misc + 9};
+            StringPairs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             // longest bins first so the tail of the launch sequence is made of short pairs
             for (int bb = MYERS_BINS - 1; bb >= 0; --bb) {
-                ma.work = d_work + bin_off[bb]; ma.n_work = bin_cnt[bb]; ma.next = d_misc + 25 + bb; ma.maxlen = maxlen;
-                SVIM_CUDA(myers_launch_bin(ctx, bb, ma, ctx->d_myers_scratch[bb], sms));
+                ma.work = d_work + bin_off[bb]; ma.n_work = bin_cnt[bb]; ma.next = d_misc + 33 + bb; ma.maxlen = maxlen;
+                SVIM_CUDA(myers_launch_bin<false>(ctx, bb, ma, none, ctx->d_myers_scratch[bb], sms));
             }
             uint32_t n_fb = 0;
-            SVIM_CUDA(cudaMemcpyAsync(&n_fb, d_misc + 24, 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaMemcpyAsync(&n_fb, d_misc + 32, 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
             if (n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
-                ma.work = d_work + n_work; ma.n_work = n_fb; ma.next = d_misc + 31; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
-                SVIM_CUDA(myers_launch_bin(ctx, 6, ma, ctx->d_myers_scratch[6], sms));
+                ma.work = d_work + n_work; ma.n_work = n_fb; ma.next = d_misc + 33 + MYERS_BINS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+                SVIM_CUDA(myers_launch_bin<false>(ctx, MYERS_BINS, ma, none, ctx->d_myers_scratch[MYERS_BINS], sms));
             }
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();

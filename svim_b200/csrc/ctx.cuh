@@ -101,7 +101,7 @@ struct svimgpu_ctx {
     const uint8_t* cluster_ins = nullptr; int64_t cluster_ins_bytes = 0;
     int64_t n_csig = 0; bool have_csig = false;
     DevBuf d_order, d_head, d_partid, d_part_off, d_samp_off, d_samp_idx, d_labels, d_part_ncl, d_part_nkept, d_part_stats;
-    DevBuf d_plist, d_myers_scratch[7];
+    DevBuf d_plist, d_myers_scratch[12];
     int64_t cluster_max_ins_len = 0;
     const int32_t* cluster_rank_to_tid = nullptr; int32_t cluster_n_ranks = 0;
     DevBuf d_user_rank_to_tid;

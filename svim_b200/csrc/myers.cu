@@ -18,7 +18,7 @@
 #pragma once
 #include "ctx.cuh"
 
-#define MYERS_BINS 6
+#define MYERS_BINS 10
 
 struct MyersWork { uint32_t a, b, slot, pad; };
 
@@ -64,15 +64,28 @@ __device__ __forceinline__ bool pair_haps(const svim_csig& a, const svim_csig& b
     const uint8_t* contig = g.bytes + g.off[tid];
     const int64_t clen = g.off[tid + 1] - g.off[tid];
     const int64_t s1 = (int64_t)a.start, s2 = (int64_t)b.start;
-    const int64_t ws = (s1 < s2 ? s1 : s2) - 100, we = (s1 > s2 ? s1 : s2) + 100;
-    ha = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s1 < 0 ? 0 : s1, ins_blob + a.seq_off, a.seq_len);
-    hb = make_hap(contig, clen, ws < 0 ? 0 : ws, we < 0 ? 0 : we, s2 < 0 ? 0 : s2, ins_blob + b.seq_off, b.seq_len);
+    // The reference pads both haplotypes with the same 100 bp of genome on either side (window_start/window_end,
+    // SVIM_clustering.py:33-34).  A common prefix and a common suffix never change a Levenshtein distance, so the
+    // window is cut down to [min(start), max(start)] — exact, and (200+L)^2 -> L^2 cells for co-located insertions.
+    const int64_t lo = s1 < s2 ? s1 : s2, hi = s1 > s2 ? s1 : s2;
+    ha = make_hap(contig, clen, lo < 0 ? 0 : lo, hi < 0 ? 0 : hi, s1 < 0 ? 0 : s1, ins_blob + a.seq_off, a.seq_len);
+    hb = make_hap(contig, clen, lo < 0 ? 0 : lo, hi < 0 ? 0 : hi, s2 < 0 ? 0 : s2, ins_blob + b.seq_off, b.seq_len);
     return true;
 }
 
+// Bins of pairs by pattern length: a group of G lanes owns one pair with WPL words per lane (capacity G*WPL words);
+// small G with several words per lane packs more pairs into a warp and amortises the per-step overhead.
+struct MyersBin { int G, WPL, capW; };
+__host__ __device__ __forceinline__ MyersBin myers_bin_spec(int b) {
+    switch (b) {
+        case 0: return {4, 1, 4};   case 1: return {4, 2, 8};   case 2: return {4, 3, 12};  case 3: return {4, 4, 16};
+        case 4: return {8, 3, 24};  case 5: return {8, 4, 32};  case 6: return {16, 3, 48}; case 7: return {16, 4, 64};
+        case 8: return {32, 3, 96}; default: return {32, 4, 1 << 30};   // bin 9 strip-mines beyond 128 words
+    }
+}
 __host__ __device__ __forceinline__ int myers_bin_of(int64_t m) {
     const int64_t W = (m + 63) >> 6;
-    return W <= 4 ? 0 : W <= 8 ? 1 : W <= 16 ? 2 : W <= 32 ? 3 : W <= 64 ? 4 : 5;
+    return W <= 4 ? 0 : W <= 8 ? 1 : W <= 12 ? 2 : W <= 16 ? 3 : W <= 24 ? 4 : W <= 32 ? 5 : W <= 48 ? 6 : W <= 64 ? 7 : W <= 96 ? 8 : 9;
 }
 
 // materialise symbol codes with the G lanes of a group; returns OR of all codes (group-uniform)
@@ -278,78 +291,56 @@ __device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m
     return eout;
 }
 
-// bins 0-3: G lanes per pair, one word per lane
-template <int G>
-__device__ int32_t myers_fast_small(const uint8_t* __restrict__ pat, int m, const uint32_t* __restrict__ txt32, int n, int gl, bool valid) {
-    Word32 w;
-    const int nl = valid ? ((m + 63) >> 6) : 0;
-    if (valid) word_init(w, pat, m, (int64_t)gl * 64);
-    else { w.p0l = w.p0h = w.p1l = w.p1h = w.p2l = w.p2h = 0; w.pvl = w.pvh = w.mvl = w.mvh = 0; }
-    int steps = valid ? (n + nl - 1) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
-    const bool lane_on = valid && gl < nl;
-    const bool head = lane_on && gl == 0;
-    uint32_t pk_out = 0;
-    uint32_t t_nxt = head ? txt32[0] : 0u;
-    for (int s = 0; s < steps; ++s) {
-        const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1, G);
-        const uint32_t t_cur = t_nxt;
-        if (head && s + 1 < n) t_nxt = txt32[s + 1];
-        const uint32_t pk = gl == 0 ? (t_cur | (2u << 24)) : recv;
-        const int j = s - gl;
-        if (lane_on && (unsigned)j < (unsigned)n) {
-            const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111), m2 = __byte_perm(pk, 0, 0x2222);
-            const uint32_t eout = word_step(w, m0, m1, m2, pk >> 24);
-            pk_out = (pk & 0x00ffffffu) | (eout << 24);
-        }
-    }
-    int v = lane_on ? word_vsum(w, m, (int64_t)gl * 64) : 0;
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, G);
-    return n + v;
-}
-
-// bins 4-5: a warp per pair, WPL words per lane, strips of 32*WPL words
-template <int WPL>
-__device__ int32_t myers_fast_warp(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
-                                   uint8_t* __restrict__ hbuf, int lane) {
-    const int64_t W = (m + 63) >> 6;
-    const int64_t STRIP = 32 * WPL;
+// G lanes per pair, WPL words per lane; strips of G*WPL words (only G = 32 ever needs more than one strip)
+template <int G, int WPL>
+__device__ int32_t myers_fast(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
+                              uint8_t* __restrict__ hbuf, int gl, bool valid) {
+    const int64_t W = valid ? ((m + 63) >> 6) : 0;
+    const int64_t STRIP = G * WPL;
     int vsum = 0;
-    for (int64_t sb = 0; sb < W; sb += STRIP) {
-        const bool first_strip = (sb == 0), last_strip = (sb + STRIP >= W);
+    int64_t n_strips = (W + STRIP - 1) / STRIP;
+    if (G < 32) n_strips = 1;            // bins guarantee W <= G*WPL; keeps the loop warp-uniform across groups
+    for (int64_t si = 0; si < n_strips; ++si) {
+        const int64_t sb = si * STRIP;
+        const bool first_strip = (si == 0), last_strip = (si + 1 >= n_strips);
         const int64_t ws_cnt = (W - sb) < STRIP ? (W - sb) : STRIP;
-        const int nl = (int)((ws_cnt + WPL - 1) / WPL);
+        const int nl = valid ? (int)((ws_cnt + WPL - 1) / WPL) : 0;
         Word32 w[WPL];
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) word_init(w[k], pat, m, (sb + (int64_t)lane * WPL + k) * 64);
-        const int steps = n + nl - 1;
-        const bool lane_on = lane < nl, head = lane == 0;
+        for (int k = 0; k < WPL; ++k) {
+            if (valid) word_init(w[k], pat, m, (sb + (int64_t)gl * WPL + k) * 64);
+            else { w[k].p0l = w[k].p0h = w[k].p1l = w[k].p1h = w[k].p2l = w[k].p2h = 0; w[k].pvl = w[k].pvh = w[k].mvl = w[k].mvh = 0; }
+        }
+        int steps = valid ? (n + nl - 1) : 0;
+        if (G < 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
+        }
+        const bool lane_on = valid && gl < nl, head = lane_on && gl == 0;
         uint32_t pk_out = 0;
         uint32_t t_nxt = head ? txt32[0] : 0u;
         uint32_t h_nxt = (head && !first_strip) ? hbuf[0] : 2u;
         for (int s = 0; s < steps; ++s) {
-            const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1);
+            const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1, G);
             const uint32_t t_cur = t_nxt, h_cur = h_nxt;
-            if (head && s + 1 < n) { t_nxt = txt32[s + 1]; if (!first_strip) h_nxt = hbuf[s + 1]; }
-            const uint32_t pk = head ? (t_cur | (h_cur << 24)) : recv;
-            const int j = s - lane;
+            if (head && s + 1 < n) { t_nxt = txt32[s + 1]; if (G == 32 && !first_strip) h_nxt = hbuf[s + 1]; }
+            const uint32_t pk = gl == 0 ? (t_cur | (h_cur << 24)) : recv;
+            const int j = s - gl;
             if (lane_on && (unsigned)j < (unsigned)n) {
                 const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111), m2 = __byte_perm(pk, 0, 0x2222);
                 uint32_t e = pk >> 24;
 #pragma unroll
                 for (int k = 0; k < WPL; ++k) e = word_step(w[k], m0, m1, m2, e);
                 pk_out = (pk & 0x00ffffffu) | (e << 24);
-                if (!last_strip && lane == 31) hbuf[j] = (uint8_t)e;
+                if (G == 32 && !last_strip && gl == 31) hbuf[j] = (uint8_t)e;
             }
         }
 #pragma unroll
-        for (int k = 0; k < WPL; ++k) vsum += lane_on ? word_vsum(w[k], m, (sb + (int64_t)lane * WPL + k) * 64) : 0;
+        for (int k = 0; k < WPL; ++k) vsum += lane_on ? word_vsum(w[k], m, (sb + (int64_t)gl * WPL + k) * 64) : 0;
         __syncwarp();
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o);
+    for (int o = G / 2; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o, G);
     return n + vsum;
 }
 
@@ -358,18 +349,21 @@ struct MyersArgs {
     const svim_csig* sig; const uint8_t* ins_blob; GenomeView g;
     const MyersWork* work; uint32_t n_work;
     int32_t* ed_out;
-    uint8_t* scratch; int64_t maxlen;         // per group: 5*maxlen (pattern codes + 4-byte text masks), +1 column buffer for the whole-warp kernels
+    uint8_t* scratch; int64_t maxlen;         // per group: 6*maxlen bytes (pattern codes, 4-byte text masks, column buffer)
     uint32_t* next;                           // work cursor
     MyersWork* fallback; uint32_t* n_fallback;   // pairs that need the 8-plane kernel
     unsigned long long* cells; uint32_t* err;
 };
 
-template <int G>
-__global__ void __launch_bounds__(128) k_myers_small(MyersArgs a) {
+// explicit string pairs (unit-test entry svimgpu_edit_distance) share the kernels below through this view
+struct StringPairs { const uint8_t* blob; const int64_t* a_off; const int32_t* a_len; const int64_t* b_off; const int32_t* b_len; const uint32_t* list; };
+
+template <int G, int WPL, bool STRINGS>
+__global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 5 * a.maxlen;
+    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 6 * a.maxlen;
     unsigned long long my_cells = 0;
     for (;;) {
         uint32_t base = 0;
@@ -381,31 +375,40 @@ __global__ void __launch_bounds__(128) k_myers_small(MyersArgs a) {
         MyersWork wk{0, 0, 0, 0};
         HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
         if (valid) {
-            wk = a.work[w];
-            if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (gl == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } valid = false; }
+            if (STRINGS) {
+                const uint32_t i = sp.list[w];
+                wk.slot = i; wk.a = i;
+                ha = HapSource{sp.blob, 0, sp.blob + sp.a_off[i], sp.a_len[i], sp.blob, 0};
+                hb = HapSource{sp.blob, 0, sp.blob + sp.b_off[i], sp.b_len[i], sp.blob, 0};
+            } else {
+                wk = a.work[w];
+                if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (gl == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } valid = false; }
+            }
         }
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
+        if (valid && (la > a.maxlen || lb > a.maxlen)) { if (gl == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } valid = false; }
         if (valid && (la == 0 || lb == 0)) { if (gl == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
         const bool a_is_pat = la >= lb;
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint32_t* txt32 = (uint32_t*)(my + a.maxlen);
-        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_txt32<G>(ht, txt32, gl, valid);
+        uint8_t* pat = my; uint32_t* txt32 = (uint32_t*)(my + a.maxlen); uint8_t* hbuf = my + 5 * a.maxlen;
+        const uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_txt32<G>(ht, txt32, gl, valid);
         __syncwarp();
         if (valid && orall >= 8) {   // symbols outside the 3-plane code space: defer to the 8-plane kernel
             if (gl == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
             valid = false;
         }
-        const int32_t ed = myers_fast_small<G>(pat, (int)m, txt32, (int)n, gl, valid);
+        const int32_t ed = myers_fast<G, WPL>(pat, m, txt32, (int)n, hbuf, gl, valid);
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
     if (my_cells) atomicAdd(a.cells, my_cells);
 }
 
-template <int WPL, int NP>
-__global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
+// any bytes: 8 bit-planes, a warp per pair, 4 words per lane, strip-mined
+template <bool STRINGS>
+__global__ void __launch_bounds__(128) k_myers_generic(MyersArgs a, StringPairs sp) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t* my = a.scratch + (size_t)warp * 6 * a.maxlen;
@@ -417,7 +420,11 @@ __global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
         if (w >= a.n_work) break;
         const MyersWork wk = a.work[w];
         HapSource ha, hb;
-        if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (lane == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } continue; }
+        if (STRINGS) {
+            const uint32_t i = wk.slot;
+            ha = HapSource{sp.blob, 0, sp.blob + sp.a_off[i], sp.a_len[i], sp.blob, 0};
+            hb = HapSource{sp.blob, 0, sp.blob + sp.b_off[i], sp.b_len[i], sp.blob, 0};
+        } else if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (lane == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } continue; }
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
         if (la > a.maxlen || lb > a.maxlen) { if (lane == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } continue; }
         if (la == 0 || lb == 0) { if (lane == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); continue; }
@@ -425,120 +432,43 @@ __global__ void __launch_bounds__(128) k_myers_warp(MyersArgs a) {
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + a.maxlen; int8_t* hbuf = (int8_t*)(my + 5 * a.maxlen);
-        int32_t ed;
-        if (NP == 3) {
-            uint32_t* txt32 = (uint32_t*)(my + a.maxlen);
-            uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_txt32<32>(ht, txt32, lane, true);
-            __syncwarp();
-            if (orall >= 8) {
-                if (lane == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
-                continue;
-            }
-            ed = myers_fast_warp<WPL>(pat, m, txt32, (int)n, (uint8_t*)hbuf, lane);
-        } else {
-            hap_write_codes<32>(hp, pat, lane, true); hap_write_codes<32>(ht, txt, lane, true);
-            __syncwarp();
-            ed = myers_run<WPL, NP>(pat, m, txt, n, hbuf, lane);
-        }
+        uint8_t* pat = my; uint8_t* txt = my + a.maxlen; int8_t* hbuf = (int8_t*)(my + 2 * a.maxlen);
+        hap_write_codes<32>(hp, pat, lane, true); hap_write_codes<32>(ht, txt, lane, true);
+        __syncwarp();
+        const int32_t ed = myers_run<4, 8>(pat, m, txt, n, hbuf, lane);
         if (lane == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
     if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
 }
 
-// unit-test entry: explicit string pairs, routed through the same bins as the pipeline
-template <int G>
-__global__ void __launch_bounds__(128) k_myers_strings_small(const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
-                                                              const int32_t* b_len, const uint32_t* list, uint32_t n_list, int32_t* out,
-                                                              uint8_t* scratch, int64_t maxlen, uint32_t* next) {
-    constexpr int GPW = 32 / G;
-    const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = scratch + ((size_t)warp * GPW + grp) * 5 * maxlen;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(next, (uint32_t)GPW);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_list) break;
-        bool valid = base + grp < n_list;
-        const uint32_t w = valid ? list[base + grp] : 0;
-        HapSource ha{blob, 0, blob + a_off[w], valid ? a_len[w] : 0, blob, 0};
-        HapSource hb{blob, 0, blob + b_off[w], valid ? b_len[w] : 0, blob, 0};
-        const int64_t la = ha.l2, lb = hb.l2;
-        if (valid && (la == 0 || lb == 0)) { if (gl == 0) out[w] = (int32_t)(la + lb); valid = false; }
-        const bool a_is_pat = la >= lb;
-        const HapSource& hp = a_is_pat ? ha : hb;
-        const HapSource& ht = a_is_pat ? hb : ha;
-        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + maxlen; uint32_t* txt32 = (uint32_t*)(my + maxlen);
-        uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_txt32<G>(ht, txt32, gl, valid);
-        __syncwarp();
-        int32_t ed;
-        if (__any_sync(0xffffffffu, valid && orall >= 8)) {   // some pair of this warp needs 8 planes: generic kernel for all of them
-            hap_write_codes<G>(ht, txt, gl, valid);
-            __syncwarp();
-            ed = myers_small<G, 8>(pat, m, txt, n, gl, valid);
-        } else ed = myers_fast_small<G>(pat, (int)m, txt32, (int)n, gl, valid);
-        if (valid && gl == 0) out[w] = ed;
-        __syncwarp();
-    }
-}
-
-template <int WPL>
-__global__ void __launch_bounds__(128) k_myers_strings_warp(const uint8_t* blob, const int64_t* a_off, const int32_t* a_len, const int64_t* b_off,
-                                                             const int32_t* b_len, const uint32_t* list, uint32_t n_list, int32_t* out,
-                                                             uint8_t* scratch, int64_t maxlen, uint32_t* next) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint8_t* my = scratch + (size_t)warp * 6 * maxlen;
-    for (;;) {
-        uint32_t i = 0;
-        if (lane == 0) i = atomicAdd(next, 1u);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= n_list) break;
-        const uint32_t w = list[i];
-        HapSource ha{blob, 0, blob + a_off[w], a_len[w], blob, 0};
-        HapSource hb{blob, 0, blob + b_off[w], b_len[w], blob, 0};
-        const int64_t la = ha.l2, lb = hb.l2;
-        if (la == 0 || lb == 0) { if (lane == 0) out[w] = (int32_t)(la + lb); continue; }
-        const bool a_is_pat = la >= lb;
-        const HapSource& hp = a_is_pat ? ha : hb;
-        const HapSource& ht = a_is_pat ? hb : ha;
-        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
-        uint8_t* pat = my; uint8_t* txt = my + maxlen; uint32_t* txt32 = (uint32_t*)(my + maxlen); int8_t* hbuf = (int8_t*)(my + 5 * maxlen);
-        uint32_t orall = hap_write_codes<32>(hp, pat, lane, true) | hap_write_txt32<32>(ht, txt32, lane, true);
-        __syncwarp();
-        int32_t ed;
-        if (orall < 8) ed = myers_fast_warp<WPL>(pat, m, txt32, (int)n, (uint8_t*)hbuf, lane);
-        else { hap_write_codes<32>(ht, txt, lane, true); __syncwarp(); ed = myers_run<WPL, 8>(pat, m, txt, n, hbuf, lane); }
-        if (lane == 0) out[w] = ed;
-        __syncwarp();
-    }
-}
-
-// launch one bin of pairs; bins 0-3 -> groups, 4/5 -> whole warp with 2/4 words per lane
-static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, DevBuf& scratch, int sms) {
+template <bool STRINGS>
+static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
     if (a.n_work == 0) return cudaSuccess;
-    const int64_t cap = bin < 5 ? (int64_t)64 * (4 << bin) : a.maxlen;   // longest haplotype in the bin
+    const MyersBin spec = bin < MYERS_BINS ? myers_bin_spec(bin) : MyersBin{32, 4, 1 << 30};
+    const int64_t cap = (bin < MYERS_BINS - 1) ? (int64_t)64 * spec.capW : a.maxlen;   // longest haplotype in the bin
     a.maxlen = (cap + 15) & ~15ll;
-    int blocks = sms * 6;
-    const int per_warp_items = bin < 3 ? (8 >> bin) : 1;
-    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * per_warp_items - 1) / (4 * per_warp_items));
-    const size_t per_warp = (size_t)(bin < 4 ? 5 * per_warp_items : 6) * a.maxlen;
-    while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)8 << 30)) blocks -= sms;
+    const int groups = 32 / spec.G;
+    int blocks = sms * 8;
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * groups - 1) / (4 * groups));
+    const size_t per_warp = (size_t)6 * groups * a.maxlen;
+    while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)16 << 30)) blocks -= sms;
     cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
     if (e != cudaSuccess) return e;
     a.scratch = scratch.as<uint8_t>();
     ctx->launches++;
     switch (bin) {
-        case 0: k_myers_small<4><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case 1: k_myers_small<8><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case 2: k_myers_small<16><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case 3: k_myers_small<32><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case 4: k_myers_warp<2, 3><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        case 5: k_myers_warp<4, 3><<<blocks, 128, 0, ctx->stream>>>(a); break;
-        default: k_myers_warp<4, 8><<<blocks, 128, 0, ctx->stream>>>(a); break;   // 6: fallback, any bytes
+        case 0: k_myers_fast<4, 1, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 1: k_myers_fast<4, 2, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 2: k_myers_fast<4, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 3: k_myers_fast<4, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 4: k_myers_fast<8, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 5: k_myers_fast<8, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 6: k_myers_fast<16, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 7: k_myers_fast<16, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 8: k_myers_fast<32, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        case 9: k_myers_fast<32, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
+        default: k_myers_generic<STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;   // MYERS_BINS: any bytes
     }
     return cudaGetLastError();
 }

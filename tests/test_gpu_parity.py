@@ -66,7 +66,8 @@ def test_edit_distance_kernel_matches_oracle(gpu_ctx):
     rng = random.Random(3)
     pairs = [(b"", b""), (b"", b"ACGT"), (b"ACGT", b""), (b"A", b"A"), (b"A", b"C"), (b"kitten", b"sitting")]
     alph = [b"ACGT", b"ACGTN", b"ACGTNRYKM=acgtn*-"]
-    for n in [1, 5, 63, 64, 65, 127, 128, 129, 500, 2047, 2048, 2049, 5000, 8191, 8192, 8193, 9000, 20000]:
+    for n in [1, 5, 63, 64, 65, 127, 128, 129, 255, 256, 257, 500, 511, 513, 767, 769, 1023, 1025, 1535, 1537, 2047, 2048, 2049,
+              3071, 3073, 4095, 4097, 5000, 6143, 6145, 8191, 8192, 8193, 9000, 12289, 20000]:
         for k in range(3):
             al = alph[k % 3]
             a = bytes(rng.choice(al) for _ in range(n))
