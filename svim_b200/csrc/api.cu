@@ -56,6 +56,8 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
     for (int i = 0; i < 12; ++i) ctx->d_myers_scratch[i].release();
+    ctx->d_stage.release(); ctx->d_stage_off.release();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -109,7 +111,11 @@ int svimgpu_set_genome(svimgpu_ctx* ctx, int32_t n, const int64_t* offsets, cons
 int svimgpu_pin_host(void* p, int64_t bytes) { return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : SVIMGPU_ERR_CUDA; }
 int svimgpu_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : SVIMGPU_ERR_CUDA; }
 
-int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s) {
+static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_seq);
+
+int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s) { return upload_alignments(ctx, s, true); }
+
+static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_seq) {
     if (!ctx || !s || s->n_aln < 0) return SVIMGPU_ERR_ARG;
     cudaSetDevice(ctx->device);
     timings_begin(ctx);
@@ -121,6 +127,7 @@ int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s) {
     {
         StageTimer t(ctx, T_H2D);
         for (int i = 0; i < 14; ++i) {
+            if (i == 12 && !with_seq) continue;   // SEQ blob stays on the host (lazy path)
             SVIM_CUDA(ctx->d_soa[i].ensure(bytes[i] + 64));
             if (bytes[i]) SVIM_CUDA(cudaMemcpyAsync(ctx->d_soa[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream));
         }
@@ -134,6 +141,7 @@ int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s) {
     ctx->cigar_words = s->cigar_words; ctx->seq_bytes = s->seq_bytes; ctx->sa_bytes = s->sa_bytes;
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_soa = true; ctx->collected = false;
+    ctx->lazy_seq = !with_seq; ctx->h_seq = with_seq ? nullptr : s->seq; ctx->h_seq_off = with_seq ? nullptr : s->seq_off; ctx->lazy_aln_base = 0;
     timings_end(ctx);
     return 0;
 }
@@ -150,9 +158,13 @@ int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats) {
 }
 
 int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats) {
-    int rc = svimgpu_upload_alignments(ctx, soa);
+    // SEQ is only read where an insertion is emitted: keep it on the host and upload just those bytes
+    int rc = upload_alignments(ctx, soa, false);
     if (rc) return rc;
-    return svimgpu_collect(ctx, stats);
+    rc = svimgpu_collect(ctx, stats);
+    ctx->have_soa = false;      // the host SEQ pointers must not outlive this call
+    ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
+    return rc;
 }
 
 int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, uint8_t* out_ins) {

@@ -130,10 +130,38 @@ SVIM_HD int fcluster_from_chain(int m, const LinkScratch& s, const int* ux, cons
 // ---- consolidation ----------------------------------------------------------------------------------
 // Correctly rounded sqrt(N / D) for exact non-negative integers (statistics.stdev goes through exact
 // rationals and _float_sqrt_of_frac).  N < 2^62, 0 < D < 2^20.
+// sign of  N/D - (m2 * 2^e)^2  for integers N >= 0, D > 0, m2 < 2^54, e <= 0 (exact, 128-bit)
+SVIM_HD int cmp_ratio_sq(uint64_t N, uint64_t D, uint64_t m2, int e) {
+    const unsigned __int128 rhs = (unsigned __int128)m2 * m2 * D;      // < 2^108 * 2^20
+    const int sh = -2 * e;                                               // compare N * 2^sh with rhs
+    if (N == 0) return rhs == 0 ? 0 : -1;
+    if (sh >= 128) return 1;
+    if (sh > 0 && (((unsigned __int128)N) >> (128 - sh)) != 0) return 1;
+    const unsigned __int128 lhs = ((unsigned __int128)N) << sh;
+    return lhs < rhs ? -1 : (lhs > rhs ? 1 : 0);
+}
+
+// Correctly rounded sqrt(N / D) for exact integers (statistics.stdev goes through exact rationals and
+// _float_sqrt_of_frac): start from the FP64 estimate and move to a neighbour if the exact value lies beyond
+// the midpoint.  N < 2^62, 0 < D < 2^20.
 SVIM_HD double sqrt_ratio(int64_t N, int64_t D) {
     if (N <= 0) return 0.0;
-    double q = (double)N / (double)D;
-    return sqrt(q);   // at most 1 ulp from the exactly rounded value; see DESIGN.md (float tolerance 1e-6)
+    double r = sqrt((double)N / (double)D);
+    for (int it = 0; it < 2; ++it) {
+        uint64_t bits; memcpy(&bits, &r, 8);
+        const int E = (int)((bits >> 52) & 0x7ff);
+        if (E == 0 || E == 0x7ff) return r;
+        const uint64_t mant = (bits & 0xfffffffffffffull) | (1ull << 52);
+        const int ex = E - 1075;                     // r = mant * 2^ex
+        if (ex - 1 > 0) return r;                     // outside the range this path is used for
+        const int up = cmp_ratio_sq((uint64_t)N, (uint64_t)D, 2 * mant + 1, ex - 1);     // value vs midpoint above
+        if (up > 0 || (up == 0 && (mant & 1))) { bits += 1; memcpy(&r, &bits, 8); continue; }
+        if (mant == (1ull << 52)) return r;           // below a power of two the spacing halves; the estimate is never that far off
+        const int dn = cmp_ratio_sq((uint64_t)N, (uint64_t)D, 2 * mant - 1, ex - 1);     // value vs midpoint below
+        if (dn < 0 || (dn == 0 && (mant & 1))) { bits -= 1; memcpy(&r, &bits, 8); continue; }
+        return r;
+    }
+    return r;
 }
 
 // sample standard deviation of v[0..n) (n >= 2).  Integral inputs (and half-integral, scale=2) take an
@@ -141,7 +169,7 @@ SVIM_HD double sqrt_ratio(int64_t N, int64_t D) {
 SVIM_HD double stdev_values(const double* v, int n, int stride) {
     bool exact = true;
     double v0 = v[0];
-    for (int i = 0; i < n; ++i) { double x = v[i * stride] * 2.0; if (x != floor(x) || fabs(x) > 9.0e15 || fabs(x - 2.0 * v0) > 2.0e9) exact = false; }
+    for (int i = 0; i < n; ++i) { double x = v[i * stride] * 2.0; if (x != floor(x) || fabs(x) > 9.0e15 || fabs(x - 2.0 * v0) > 2.0e7) exact = false; }
     if (exact) {
         int64_t s1 = 0, s2 = 0;
         for (int i = 0; i < n; ++i) { int64_t y = (int64_t)(v[i * stride] * 2.0 - v0 * 2.0); s1 += y; s2 += y * y; }

@@ -11,6 +11,7 @@
 // (B_aln = 44 + 4*n_cigar + sa_len bytes per record) and nothing else.
 #pragma once
 #include <cub/cub.cuh>
+#include <thread>
 #include "ctx.cuh"
 
 #define FULL 0xffffffffu
@@ -288,6 +289,77 @@ __global__ void __launch_bounds__(256) k_ins_gather(DevSoa a, svim_sig* recs, co
     if (lane == 0) recs[w].seq_off = dst;
 }
 
+// lazy-SEQ variant: the packed bases of every insertion were staged contiguously by the host (collect_host path);
+// stage_off[w] = byte offset of the record's first packed byte, parity = first nibble inside that byte
+__global__ void __launch_bounds__(256) k_ins_gather_staged(const uint8_t* staged, const uint64_t* stage_off, svim_sig* recs, const uint64_t* blob_off,
+                                                            uint32_t n, uint8_t* blob) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n) return;
+    if (recs[w].type != SVIM_INS) return;
+    const uint64_t par = recs[w].seq_off & 1ull; const uint32_t len = recs[w].seq_len;
+    const uint64_t dst = blob_off[w];
+    const uint8_t* seq = staged + stage_off[w];
+    for (uint32_t k = lane; k < len; k += 32) {
+        const uint64_t q = par + k;
+        const uint8_t b = seq[q >> 1];
+        const uint8_t code = (q & 1) ? (b & 15) : (b >> 4);
+        blob[dst + k] = (uint8_t)"=ACMGRSVTWYHKDBN"[code];
+    }
+    __syncwarp();
+    if (lane == 0) recs[w].seq_off = dst;
+}
+
+// Host side of the lazy-SEQ path: copy only the packed bytes the gather kernel will read into a pinned staging
+// buffer (a few threads: the ranges are scattered over the whole SEQ blob), upload them, run the staged gather.
+static int collect_gather_lazy(svimgpu_ctx* ctx, SigSet& set, uint32_t n, const uint64_t* d_ins_off) {
+    cudaStream_t st = ctx->stream;
+    std::vector<svim_sig>& h = ctx->h_lazy_recs;
+    h.resize(n);
+    SVIM_CUDA(cudaMemcpyAsync(h.data(), set.recs.p, (size_t)n * sizeof(svim_sig), cudaMemcpyDeviceToHost, st));
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    std::vector<uint64_t>& off = ctx->h_lazy_off;
+    off.assign(n, 0);
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (h[k].type != SVIM_INS || h[k].seq_len == 0) continue;
+        off[k] = total;
+        total += ((h[k].seq_off & 1ull) + h[k].seq_len + 1) >> 1;
+    }
+    if (total + 16 > ctx->h_stage_cap) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_cap = 0;
+        size_t want = (size_t)total + total / 4 + 4096;
+        SVIM_CUDA(cudaMallocHost((void**)&ctx->h_stage, want));
+        ctx->h_stage_cap = want;
+    }
+    uint8_t* stage = ctx->h_stage;
+    const uint8_t* hseq = ctx->h_seq; const uint64_t* hoff = ctx->h_seq_off;
+    auto work = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t k = lo; k < hi; ++k) {
+            if (h[k].type != SVIM_INS || h[k].seq_len == 0) continue;
+            const uint64_t first = h[k].seq_off >> 1;
+            const uint64_t nb = ((h[k].seq_off & 1ull) + h[k].seq_len + 1) >> 1;
+            memcpy(stage + off[k], hseq + hoff[h[k].aln_idx - ctx->lazy_aln_base] + first, nb);
+        }
+    };
+    const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (n < 4096 || nt == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, (uint32_t)((uint64_t)n * t / nt), (uint32_t)((uint64_t)n * (t + 1) / nt));
+        for (auto& x : th) x.join();
+    }
+    SVIM_CUDA(ctx->d_stage.ensure((size_t)total + 16)); SVIM_CUDA(ctx->d_stage_off.ensure((size_t)n * 8));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_stage.p, stage, (size_t)total, cudaMemcpyHostToDevice, st));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_stage_off.p, off.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    const uint32_t blocks = (uint32_t)(((uint64_t)n * 32 + 255) / 256);
+    { ctx->launches++; k_ins_gather_staged<<<blocks, 256, 0, st>>>(ctx->d_stage.as<uint8_t>(), ctx->d_stage_off.as<uint64_t>(), set.recs.as<svim_sig>(), d_ins_off, n,
+                                                 set.ins.as<uint8_t>()); }
+    SVIM_CUDA(cudaStreamSynchronize(st));   // the host vectors are reused by the next call
+    return 0;
+}
+
 static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     // queue[which] (arbitrary order) -> sets[which].recs in emission order + INS blob
     SigSet& set = ctx->sets[which];
@@ -320,8 +392,11 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     set.ins_bytes = (int64_t)total;
     SVIM_CUDA(set.ins.ensure((size_t)total + 16));
     if (total > 0) {
-        uint32_t blocks = (uint32_t)(((uint64_t)n * 32 + 255) / 256);
-        { ctx->launches++; k_ins_gather<<<blocks, 256, 0, st>>>(ctx->soa, set.recs.as<svim_sig>(), ins_off, n, set.ins.as<uint8_t>()); }
+        if (ctx->lazy_seq) { int rc = collect_gather_lazy(ctx, set, n, ins_off); if (rc) return rc; }
+        else {
+            uint32_t blocks = (uint32_t)(((uint64_t)n * 32 + 255) / 256);
+            { ctx->launches++; k_ins_gather<<<blocks, 256, 0, st>>>(ctx->soa, set.recs.as<svim_sig>(), ins_off, n, set.ins.as<uint8_t>()); }
+        }
     }
     SVIM_CUDA(cudaGetLastError());
     return 0;

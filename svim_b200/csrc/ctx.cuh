@@ -89,6 +89,11 @@ struct svimgpu_ctx {
     DevBuf d_soa[14];
     DevSoa soa; bool have_soa = false;
     int64_t cigar_words = 0, seq_bytes = 0, sa_bytes = 0;
+    // lazy SEQ (collect_host): SEQ stays on the host, only the bytes of emitted insertions are staged and uploaded
+    bool lazy_seq = false; const uint8_t* h_seq = nullptr; const uint64_t* h_seq_off = nullptr; uint32_t lazy_aln_base = 0;
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0;
+    std::vector<svim_sig> h_lazy_recs; std::vector<uint64_t> h_lazy_off;
+    DevBuf d_stage, d_stage_off;
 
     // collect state
     DevBuf d_counters, d_queue[2], d_work, d_sort_tmp, d_keys[2], d_vals[2], d_scan;
