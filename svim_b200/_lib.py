@@ -167,6 +167,9 @@ class Context:
             raise SvimGpuError(rc, "svimgpu_create failed (no usable CUDA device?) - there is no CPU path")
         self.h = h
         self._keep = []
+        self.genome_key = None      # bookkeeping used by svim_b200.runtime / the host mirror
+        self.resident = None
+        self.contigs_key = None
 
     def close(self):
         if getattr(self, "h", None):

@@ -18,8 +18,6 @@ def context(device: int = None) -> "_lib.Context":
     ctx = _CTX.get(device)
     if ctx is None:
         ctx = _lib.Context(device=device)
-        ctx.resident = None         # (batch id, contig names) currently uploaded / collected
-        ctx.genome_key = None
         _CTX[device] = ctx
     return ctx
 
