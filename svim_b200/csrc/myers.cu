@@ -1,20 +1,22 @@
 // K2b: haplotype edit distance (compute_haplotype_edit_distance, SVIM_clustering.py:32-45;
 // edlib.align NW distance) as a bit-parallel Myers/Hyyro kernel.
 //
-// The longer haplotype of a pair is the pattern: its rows are cut into 64-bit words that live
-// in registers, one lane per word (or WPL consecutive words per lane for long patterns).  Lanes
-// run as a systolic wavefront: at step s lane l handles text column s-l and hands the horizontal
-// delta of its bottom row to lane l+1 with one shuffle.  Pairs are binned by pattern length so
-// that short patterns share a warp: a group of G = 4/8/16/32 lanes owns one pair, 32/G pairs per
-// warp (bins 0-3, one word per lane); bins 4/5 give a whole warp 2/4 words per lane, and bin 5
-// strip-mines patterns longer than 8192 rows, parking the horizontal deltas of a strip's bottom
-// row in a per-warp column buffer.
-// Symbol equality comes from bit-planes of a compact bijective symbol code (no shared-memory Peq
-// table): 3 planes cover A,C,G,T,N (+3 more codes); pairs containing any other byte take an
-// 8-plane kernel, so arbitrary bytes stay exact.
+// * Exact work reduction first: both haplotypes of a pair carry the same 100 bp genome flanks, and a common prefix /
+//   suffix never changes a Levenshtein distance, so the window is cut to [min(start), max(start)] (pair_haps).
+// * The longer haplotype is the pattern: rows are cut into 64-bit words held in registers as 32-bit halves.
+//   A group of G lanes owns one pair with WPL consecutive words per lane; pairs are binned by pattern length into
+//   ten (G, WPL) shapes (4x1 ... 32x4) so short patterns share a warp and the per-step overhead is amortised.
+//   Bin 9 (32 lanes x 4 words) strip-mines patterns longer than 8 192 rows, parking the horizontal deltas of a
+//   strip's bottom row in a per-warp column buffer.
+// * Lanes run as a systolic wavefront: at step s lane l handles text column s-l.  The text is pre-expanded to one
+//   uint32 of byte masks per column; lane 0 injects it together with the incoming horizontal delta, every lane
+//   forwards the same word with its own bottom delta in the top byte: one shuffle per step, no per-lane loads.
+// * Symbol equality comes from 3 bit-planes of a compact bijective symbol code (A,C,G,T,N + 3); a pair holding any
+//   other byte is deferred to an 8-plane kernel, so arbitrary bytes stay exact.
+// * The distance is read from the vertical deltas of the last column: D[m][n] = n + sum_rows(Pv - Mv).
 //
-// Integer-ALU bound (~30 instructions per 64-cell word step); DRAM traffic is the two
-// haplotypes per pair.  No tensor cores: there is no dense contraction here.
+// Integer-ALU bound: ~34-40 ALU-pipe instructions per 64-cell word step (ncu: ALU pipe 90-97 % busy, FMA pipe idle);
+// DRAM traffic is the two haplotypes per pair.  No tensor cores: there is no dense contraction here.
 #pragma once
 #include "ctx.cuh"
 
@@ -138,40 +140,7 @@ __device__ __forceinline__ void build_planes(const uint8_t* __restrict__ pat, in
     }
 }
 
-// ---- bins 0-3: groups of G lanes, one word per lane, pattern <= 64*G rows -------------------------
-template <int G, int NP>
-__device__ int32_t myers_small(const uint8_t* __restrict__ pat, int64_t m, const uint8_t* __restrict__ txt, int64_t n, int gl, bool valid) {
-    uint64_t pl[NP], vm, Pv = ~0ull, Mv = 0;
-    const int nl = valid ? (int)((m + 63) >> 6) : 0;
-    if (valid) build_planes<NP>(pat, m, (int64_t)gl * 64, pl, vm);
-    else { vm = 0; for (int b = 0; b < NP; ++b) pl[b] = 0; }
-    const int l_last = nl - 1, bit_last = (int)((m - 1) & 63);
-    int steps = valid ? (int)(n + nl - 1) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
-    int carry = 0, score = 0;
-    const bool lane_on = valid && gl < nl;
-    uint8_t c_next = (lane_on && gl == 0) ? txt[0] : 0;
-    for (int s = 0; s < steps; ++s) {
-        const int recv = __shfl_up_sync(0xffffffffu, carry, 1, G);
-        const int j = s - gl;
-        const uint8_t c = c_next;
-        if (lane_on && j + 1 >= 0 && j + 1 < n) c_next = txt[j + 1];
-        if (lane_on && j >= 0 && j < n) {
-            uint64_t Eq = vm;
-#pragma unroll
-            for (int b = 0; b < NP; ++b) Eq &= ~(pl[b] ^ (0ull - (uint64_t)((c >> b) & 1u)));
-            uint64_t ph, mh;
-            const int hout = myers_word(Eq, Pv, Mv, gl == 0 ? 1 : recv, ph, mh);
-            if (gl == l_last) score += (int)((ph >> bit_last) & 1ull) - (int)((mh >> bit_last) & 1ull);
-            carry = hout;
-        }
-    }
-    score = __shfl_sync(0xffffffffu, score, l_last < 0 ? 0 : l_last, G);
-    return (int32_t)(m + score);
-}
-
-// ---- bins 4-5 and the 8-plane kernel: a whole warp per pair, WPL words per lane, strip-mined -----------
+// ---- generic kernel (NP bit-planes, any bytes): a whole warp per pair, WPL words per lane, strip-mined -----------
 template <int WPL, int NP>
 __device__ int32_t myers_run(const uint8_t* __restrict__ pat, int64_t m, const uint8_t* __restrict__ txt, int64_t n,
                              int8_t* __restrict__ hbuf, int lane) {
