@@ -40,9 +40,10 @@ def build_gpu(force=False, verbose=False):
 
 
 def build_all(force=False):
-    from . import synth
+    from . import synth, io
     build_gpu(force)
     synth.build(force)
+    io.build_bamio(force)
 
 
 if __name__ == "__main__":

@@ -84,6 +84,23 @@ def test_sam_bam_roundtrip(tmp_path):
         assert got.qname_id[0] == got.qname_id[2] != got.qname_id[1]
 
 
+def test_native_bam_reader_equals_python_reader(tmp_path):
+    """csrc_host/bamio.cpp (parallel inflate + SoA fill) against the pure-Python decoder on a synthetic BAM."""
+    from svim_b200 import synth
+    names, L = ["chr1", "chr2"], [80_000, 60_000]
+    svs, al = synth.plant_svs(L, 3, spacing=6000)
+    batch = synth.generate(names, L, 300, 3, svs, al, len_mean=3000, len_sd=600, len_min=800, len_max=6000)
+    p = str(tmp_path / "s.bam")
+    sio.write_bam(p, batch)
+    a, b = sio.read_bam_native(p, threads=4), sio.read_bam_python(p)
+    assert a.n == b.n == batch.n and a.contig_names == b.contig_names == names and a.sort_order == b.sort_order == "coordinate"
+    for name, _ in a.FIELDS:
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    for blob in ("cigar", "seq", "sa"):
+        assert np.array_equal(getattr(a, blob), getattr(b, blob)) and np.array_equal(getattr(a, blob), getattr(batch, blob))
+    assert [a.qname(int(i)) for i in a.qname_id] == [batch.qname(int(i)) for i in batch.qname_id]
+
+
 def test_fasta_fetch_clamps(tmp_path):
     g = sio.Genome(["c1", "c2"], [np.frombuffer(b"ACGTacgtNN", dtype=np.uint8), np.frombuffer(b"GG", dtype=np.uint8)])
     p = str(tmp_path / "g.fa"); g.write_fasta(p, width=4)
