@@ -1,0 +1,84 @@
+"""`python -m svim_b200 alignment <working_dir> <bam_file> <genome> [options]`
+
+Runs the two stages this package implements (COLLECT -> CLUSTER) on the GPU with the option names and defaults
+of the reference's `svim alignment` sub-command (SVIM_input_parsing.py:262-371) and writes the signature-cluster
+BED files the reference writes after CLUSTER (`signatures/*.bed`).  COMBINE / genotyping / final VCF are the
+reference's downstream stages: use `python -m svim_b200.patch alignment ...` with the reference installed to run
+the whole pipeline with these two stages replaced.
+"""
+import argparse
+import logging
+import os
+import sys
+import time
+
+
+def parse(argv):
+    ap = argparse.ArgumentParser(prog="svim_b200", description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="sub")
+    p = sub.add_parser("alignment", help="detect SV signatures and cluster them from an existing alignment")
+    p.add_argument("working_dir", type=os.path.abspath)
+    p.add_argument("bam_file")
+    p.add_argument("genome")
+    p.add_argument("--verbose", action="store_true")
+    p.add_argument("--min_mapq", type=int, default=20)
+    p.add_argument("--min_sv_size", type=int, default=40)
+    p.add_argument("--max_sv_size", type=int, default=100000)
+    p.add_argument("--segment_gap_tolerance", type=int, default=10)
+    p.add_argument("--segment_overlap_tolerance", type=int, default=5)
+    p.add_argument("--partition_max_distance", type=int, default=1000)
+    p.add_argument("--position_distance_normalizer", type=int, default=900)
+    p.add_argument("--edit_distance_normalizer", type=float, default=1.0)
+    p.add_argument("--cluster_max_distance", type=float, default=0.5)
+    p.add_argument("--all_bnds", action="store_true")
+    return ap.parse_args(argv)
+
+
+BED_FILES = (("del.bed", 0, False), ("ins.bed", 1, False), ("inv.bed", 2, False), ("dup_tan.bed", 3, True), ("dup_int.bed", 4, True),
+             ("trans.bed", 5, True))
+
+
+def write_cluster_beds(working_dir, clusters):
+    out = os.path.join(working_dir, "signatures")
+    os.makedirs(out, exist_ok=True)
+    for name, idx, bilocal in BED_FILES:
+        with open(os.path.join(out, name), "w") as fh:
+            for c in clusters[idx]:
+                for line in (c.get_bed_entries() if bilocal else (c.get_bed_entry(),)):
+                    fh.write(line + "\n")
+
+
+def main(argv=None):
+    options = parse(sys.argv[1:] if argv is None else argv)
+    if options.sub != "alignment":
+        print("usage: python -m svim_b200 alignment <working_dir> <bam_file> <genome>")
+        return 2
+    logging.basicConfig(level=logging.DEBUG if options.verbose else logging.INFO, format="%(asctime)s [%(levelname)-7.7s]  %(message)s")
+    os.makedirs(options.working_dir, exist_ok=True)
+    from .io import read_alignments
+    from .SVIM_COLLECT import analyze_alignment_file_coordsorted
+    from .SVIM_CLUSTER import cluster_sv_signatures
+    t0 = time.perf_counter()
+    batch = read_alignments(options.bam_file)
+    if batch.sort_order != "coordinate":
+        logging.warning("input is not coordinate-sorted (header SO:%s); the query-sorted mode of the reference is not implemented here", batch.sort_order)
+    logging.info("****************** STEP 1: COLLECT ******************")
+    t1 = time.perf_counter()
+    sigs, all_bnds = analyze_alignment_file_coordsorted(batch, options)
+    t2 = time.perf_counter()
+    for t in ("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"):
+        logging.info("Found {0} signatures of type {1}".format(sum(1 for s in sigs if s.type == t), t))
+    logging.info("****************** STEP 2: CLUSTER ******************")
+    clusters = cluster_sv_signatures(sigs, options)
+    if options.all_bnds:
+        extra = cluster_sv_signatures(all_bnds, options)
+        clusters = clusters[:5] + (clusters[5] + extra[5],)
+    t3 = time.perf_counter()
+    write_cluster_beds(options.working_dir, clusters)
+    logging.info("decode %.2f s, COLLECT %.2f s, CLUSTER %.2f s for %d alignment records (%d signatures, %d clusters)",
+                 t1 - t0, t2 - t1, t3 - t2, batch.n, len(sigs), sum(len(c) for c in clusters))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

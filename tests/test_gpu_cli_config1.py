@@ -43,3 +43,16 @@ def test_config1_bam_to_clusters(tmp_path):
                 assert (c.contig, c.start, c.end) == (e.contig, e.start, e.end)
             assert c.score == pytest.approx(e.score, rel=1e-6)
     assert len(res[0]) > 5 and len(res[1]) > 5
+
+
+def test_cli_writes_signature_beds(tmp_path):
+    import subprocess, sys, os
+    from conftest import ROOT
+    batch, genome, _ = synth.make_config("config1", 0.3)
+    bam = str(tmp_path / "c.bam"); fa = str(tmp_path / "g.fa"); wd = str(tmp_path / "out")
+    write_bam(bam, batch); genome.write_fasta(fa)
+    r = subprocess.run([sys.executable, "-m", "svim_b200", "alignment", wd, bam, fa], cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    dels = open(os.path.join(wd, "signatures", "del.bed")).read().splitlines()
+    assert len(dels) > 3 and all(l.split("\t")[3].startswith("DEL;") for l in dels)
+    assert os.path.exists(os.path.join(wd, "signatures", "trans.bed"))
