@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
+    ap.add_argument("--scan-variant", type=int, default=None, help="0 = 128-bit LDG streaming scan, 1 = cp.async.bulk ring (default: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -173,6 +174,8 @@ def main():
         args.warmup = 3
 
     rank, local_rank, world = env_rank()
+    if args.scan_variant is not None:
+        os.environ["SVIM_SCAN_VARIANT"] = str(args.scan_variant)
     from svim_b200 import _lib
     t_gen = time.perf_counter()
     batch, genome = make_rank_input(args.workload, args.scale, rank, world)

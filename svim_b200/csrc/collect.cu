@@ -227,6 +227,168 @@ __global__ void __launch_bounds__(256, 3) k_cigar_scan(DevSoa a, ChainParams p, 
     if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
 }
 
+// ---- bulk-copy (TMA engine) variant of the scan ---------------------------------------------------------
+// Each warp owns a ring of SCAN_STAGES shared-memory stages of 2 KiB (one 512-op block).  Lane 0 issues
+// cp.async.bulk global->shared copies that complete on a per-stage mbarrier; in-flight bytes are bounded by
+// shared memory, not registers, and the copy engine runs ahead across the records of the warp's batch.
+#define SCAN_STAGES 4
+#define SCAN_BLOCK_U4 128                  // uint4 per stage (2 KiB)
+#define SCAN_BULK_WARPS 8
+#define SCAN_BULK_BATCH 8
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(32 * SCAN_BULK_WARPS, 3) k_cigar_scan_bulk(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
+                                                                            uint32_t work_cap, uint32_t* cnt) {
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint4* ring = reinterpret_cast<uint4*>(scan_smem) + (size_t)wib * SCAN_STAGES * SCAN_BLOCK_U4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(scan_smem + (size_t)SCAN_BULK_WARPS * SCAN_STAGES * SCAN_BLOCK_U4 * 16) + wib * SCAN_STAGES;
+    if (lane == 0) {
+        for (int s = 0; s < SCAN_STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
+    const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
+    const uint32_t n_aln = (uint32_t)a.n;
+    uint32_t primaries = 0;
+    uint32_t phase = 0;                       // bit s = parity the consumer waits for on stage s
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(cnt + CNT_NEXT_ALN, (uint32_t)SCAN_BULK_BATCH);
+        first = __shfl_sync(FULL, first, 0);
+        if (first >= n_aln) break;
+        const uint32_t nrec = min((uint32_t)SCAN_BULK_BATCH, n_aln - first);
+        // per-record block counts of this batch (lane r holds record r); filtered records have none
+        uint32_t my_n = 0; const uint4* my_cg = nullptr; bool my_ok = false;
+        if (lane < nrec) {
+            const uint32_t i = first + lane;
+            const uint32_t flag = a.flag[i];
+            my_ok = !((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq);
+            if (my_ok) { my_n = a.n_cigar[i]; my_cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]); }
+        }
+        const uint32_t my_blk = (((my_n + 3) >> 2) + SCAN_BLOCK_U4 - 1) / SCAN_BLOCK_U4;
+        uint32_t tot_blk; const uint32_t blk_before = warp_excl_scan(my_blk, lane, tot_blk);
+        // producer state (lane 0 issues): global block index -> (record lane, local block)
+        uint32_t prod = 0;
+        auto issue = [&](uint32_t g) {   // executed by all lanes (shuffles), copy issued by lane 0
+            // owner = last lane with blk_before <= g and my_blk > 0
+            const unsigned own = __ballot_sync(FULL, my_blk > 0 && blk_before <= g && g < blk_before + my_blk);
+            const int ol = __ffs(own) - 1;
+            const uint32_t lb = g - __shfl_sync(FULL, blk_before, ol);
+            const uint32_t n4 = (__shfl_sync(FULL, my_n, ol) + 3) >> 2;
+            const unsigned long long base = __shfl_sync(FULL, (unsigned long long)my_cg, ol);
+            const uint32_t cnt4 = min((uint32_t)SCAN_BLOCK_U4, n4 - lb * SCAN_BLOCK_U4);
+            if (lane == 0) {
+                const int st = g % SCAN_STAGES;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage vs the async write
+                mbar_expect_tx(bars + st, cnt4 * 16);
+                bulk_g2s(ring + (size_t)st * SCAN_BLOCK_U4, reinterpret_cast<const uint4*>(base) + (size_t)lb * SCAN_BLOCK_U4, cnt4 * 16, bars + st);
+            }
+        };
+        for (; prod < tot_blk && prod < SCAN_STAGES; ++prod) issue(prod);
+        uint32_t g = 0;                        // consumer block index within the batch
+        // NOTE: stages are indexed by g % SCAN_STAGES, so the ring restarts at stage 0 every batch; the phase word keeps
+        // the per-stage parity across batches.
+        for (uint32_t ri = 0; ri < nrec; ++ri) {
+            const bool ok = __shfl_sync(FULL, (int)my_ok, ri);
+            if (!ok) continue;
+            const uint32_t i = first + ri;
+            const uint32_t flag = a.flag[i];
+            const bool primary = !(flag & 0x800u);
+            primaries += primary;
+            const uint32_t n = __shfl_sync(FULL, my_n, ri);
+            const uint32_t n4 = (n + 3) >> 2;
+            const uint32_t nb = __shfl_sync(FULL, my_blk, ri);
+            ScanRec r; r.i = i; r.qid = a.qname_id[i]; r.tid = a.tid[i]; r.ref_start = a.pos[i]; r.l_seq = a.l_seq[i];
+            EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = 0; st.n_tw = 0; st.nsum = 0; st.hsum = 0;
+            uint32_t a_ref = 0, a_read = 0, a_n = 0, a_h = 0;
+            const bool need_summary = primary && a.sa_len[i] > 0;
+            for (uint32_t b = 0; b < nb; ++b, ++g) {
+                const int stg = g % SCAN_STAGES;
+                mbar_wait(bars + stg, (phase >> stg) & 1u);
+                phase ^= 1u << stg;
+                const uint4* blk = ring + (size_t)stg * SCAN_BLOCK_U4;
+                uint4 w[4];
+                const uint32_t base4 = b * SCAN_BLOCK_U4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t idx = base4 + u * 32 + lane;
+                    w[u] = idx < n4 ? blk[u * 32 + lane] : make_uint4(0, 0, 0, 0);
+                    if (idx == n4 - 1) {
+                        const uint32_t rr = n & 3u;
+                        if (rr == 1) { w[u].y = 0; w[u].z = 0; w[u].w = 0; } else if (rr == 2) { w[u].z = 0; w[u].w = 0; } else if (rr == 3) { w[u].w = 0; }
+                    }
+                }
+                __syncwarp();                                  // every lane has its words: the stage can be refilled
+                if (prod < tot_blk) { issue(prod); ++prod; }
+                if (need_summary) {
+                    constexpr bool SUM = true;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) SCAN_GROUP(w[u])
+                } else {
+                    constexpr bool SUM = false;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) SCAN_GROUP(w[u])
+                }
+            }
+            st.nsum += a_n; st.hsum += a_h;
+            if (need_summary) {
+                const uint32_t hard = warp_sum(st.hsum);
+                if (hard == 0) {
+                    const int64_t ref_q = st.base_ref + warp_sum(a_ref);
+                    const int64_t rd = st.base_read + warp_sum(a_read);
+                    const int64_t nsum = warp_sum(st.nsum);
+                    if (lane == 0) {
+                        const uint32_t* c32 = a.cigar + a.cigar_off[i];
+                        const int64_t l_seq = r.l_seq;
+                        CigarSummary cs; cigsum_init(cs);
+                        if (l_seq == 0) {
+                            for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
+                        } else {
+                            cs.ref_len = ref_q + nsum; cs.qlen_h = rd; cs.hard = 0; cs.n_ops = (int32_t)n;
+                            uint32_t k = 0;
+                            for (; k < n; ++k) { uint32_t op = c32[k] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.lead_s += c32[k] >> 4; }
+                            for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
+                        }
+                        Seg sg; int64_t rl;
+                        cigsum_finish(cs, l_seq, r.ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
+                        uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
+                        if (slot < work_cap) {
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
+                            wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
+                            work[slot] = wk;
+                        } else atomicExch(cnt + CNT_OVERFLOW, 1u);
+                    }
+                }
+            }
+        }
+        // the ring restarts at stage 0 for the next batch: rotate the phase word so bit s still belongs to stage s
+        // (tot_blk blocks were consumed; stage s was used ceil((tot_blk - s)/STAGES) times — already folded into `phase`)
+    }
+    primaries = warp_sum(primaries);
+    if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
+}
+
 __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
                                                         SigQueue qm, SigQueue qt, uint32_t* cnt) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -431,9 +593,17 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         SigQueue qt{ctx->d_queue[1].as<svim_sig>(), ctx->d_counters.as<uint32_t>() + CNT_TWIN, ctx->params.all_bnds ? cap : 16};
         {
             StageTimer t(ctx, T_SCAN);
-            if (n > 0)
-                { ctx->launches++; k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                         ctx->d_counters.as<uint32_t>()); }
+            if (n > 0) {
+                if (ctx->scan_variant == 1) {   // cp.async.bulk ring (TMA engine)
+                    const size_t smem = (size_t)SCAN_BULK_WARPS * SCAN_STAGES * SCAN_BLOCK_U4 * 16 + (size_t)SCAN_BULK_WARPS * SCAN_STAGES * 8;
+                    SVIM_CUDA(cudaFuncSetAttribute(k_cigar_scan_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    { ctx->launches++; k_cigar_scan_bulk<<<dev_sms * 3, 32 * SCAN_BULK_WARPS, smem, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                  ctx->d_counters.as<uint32_t>()); }
+                } else {
+                    { ctx->launches++; k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                             ctx->d_counters.as<uint32_t>()); }
+                }
+            }
         }
         SVIM_CUDA(cudaGetLastError());
         SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));

@@ -99,6 +99,7 @@ struct svimgpu_ctx {
     DevBuf d_counters, d_queue[2], d_work, d_sort_tmp, d_keys[2], d_vals[2], d_scan;
     SigSet sets[2];
     bool collected = false;
+    int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
     svim_collect_stats cstats;
 
     // cluster state
