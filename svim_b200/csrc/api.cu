@@ -33,6 +33,8 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return SVIMGPU_ERR_CUDA; }
     for (int i = 0; i < 2 * T_N; ++i) cudaEventCreate(&ctx->ev[i]);
     cudaEventCreate(&ctx->user_ev[0]); cudaEventCreate(&ctx->user_ev[1]);
+    for (int i = 0; i < SVIM_AUX_STREAMS; ++i) cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking);
+    for (int i = 0; i <= SVIM_AUX_STREAMS; ++i) cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming);
     timings_begin(ctx);
     memset(&ctx->cstats, 0, sizeof(ctx->cstats)); memset(&ctx->clstats, 0, sizeof(ctx->clstats));
     myers_init_symcode();
@@ -60,6 +62,8 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     ctx->d_stage.release(); ctx->d_stage_off.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < SVIM_AUX_STREAMS; ++i) cudaStreamDestroy(ctx->aux_stream[i]);
+    for (int i = 0; i <= SVIM_AUX_STREAMS; ++i) cudaEventDestroy(ctx->aux_ev[i]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -342,22 +346,26 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         MyersArgs ma{nullptr, nullptr, GenomeView{nullptr, nullptr, 0, nullptr, 0}, nullptr, 0, d_out.as<int32_t>(), nullptr, maxlen, nullptr,
                      d_fb.as<MyersWork>(), nx + 32, (unsigned long long*)d_misc.p, (uint32_t*)d_misc.p + 4};
         uint32_t off = 0;
+        chk(myers_fork(ctx));
         for (int bin = 0; bin < MYERS_BINS && e == cudaSuccess; ++bin) {
             const uint32_t nl = (uint32_t)lists[bin].size();
             if (!nl) continue;
             uint32_t* dl = d_list.as<uint32_t>() + off; off += nl;
-            chk(cudaMemcpyAsync(dl, lists[bin].data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+            chk(cudaMemcpyAsync(dl, lists[bin].data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->aux_stream[bin % SVIM_AUX_STREAMS]));
             StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), dl};
             ma.n_work = nl; ma.next = nx + bin; ma.maxlen = maxlen;
             chk(myers_launch_bin<true>(ctx, bin, ma, sp, ctx->d_myers_scratch[bin], 148));
         }
+        chk(myers_join(ctx));
         uint32_t n_fb = 0;
         chk(cudaMemcpyAsync(&n_fb, nx + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaStreamSynchronize(ctx->stream));
         if (e == cudaSuccess && n_fb > 0) {   // pairs with bytes outside the 3-plane code space
+            chk(myers_fork(ctx));
             StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
             ma.work = d_fb.as<MyersWork>(); ma.n_work = n_fb; ma.next = nx + 40; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
             chk(myers_launch_bin<true>(ctx, MYERS_BINS, ma, sp, ctx->d_myers_scratch[MYERS_BINS], 148));
+            chk(myers_join(ctx));
         }
         chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaMemcpyAsync(&h_err, (uint32_t*)d_misc.p + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));

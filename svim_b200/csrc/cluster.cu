@@ -562,17 +562,21 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             MyersArgs ma{sorted, ctx->cluster_ins, gv, nullptr, 0, ctx->d_pair_ed.as<int32_t>(), nullptr, maxlen, nullptr, d_work + n_work, d_misc + 32,
                          (unsigned long long*)(d_misc + 12), d_misc + 9};
             StringPairs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            // longest bins first so the tail of the launch sequence is made of short pairs
+            // longest bins first so the tail of the launch sequence is made of short pairs; bins overlap on side streams
+            SVIM_CUDA(myers_fork(ctx));
             for (int bb = MYERS_BINS - 1; bb >= 0; --bb) {
                 ma.work = d_work + bin_off[bb]; ma.n_work = bin_cnt[bb]; ma.next = d_misc + 33 + bb; ma.maxlen = maxlen;
                 SVIM_CUDA(myers_launch_bin<false>(ctx, bb, ma, none, ctx->d_myers_scratch[bb], sms));
             }
+            SVIM_CUDA(myers_join(ctx));
             uint32_t n_fb = 0;
             SVIM_CUDA(cudaMemcpyAsync(&n_fb, d_misc + 32, 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
             if (n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
                 ma.work = d_work + n_work; ma.n_work = n_fb; ma.next = d_misc + 33 + MYERS_BINS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+                SVIM_CUDA(myers_fork(ctx));
                 SVIM_CUDA(myers_launch_bin<false>(ctx, MYERS_BINS, ma, none, ctx->d_myers_scratch[MYERS_BINS], sms));
+                SVIM_CUDA(myers_join(ctx));
             }
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();

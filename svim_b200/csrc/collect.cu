@@ -137,20 +137,20 @@ __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int 
     }
 
 // stream one record's CIGAR.  Main loop: whole 512-op blocks without any bounds test.
-template <bool SUM>
+template <bool SUM, int UNROLL>
 __device__ __forceinline__ void scan_cigar(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, const ChainParams& p, const ScanRec& r,
                                            EvState& st_out, uint32_t& acc_ref_out, uint32_t& acc_read_out, const DeviceEmitter& out) {
     const uint32_t n4 = (n + 3) >> 2;
-    const uint32_t full = (n >> 2) / (32 * SCAN_UNROLL) * (32 * SCAN_UNROLL);   // uint4 groups in complete 512-op blocks
+    const uint32_t full = (n >> 2) / (32 * UNROLL) * (32 * UNROLL);   // uint4 groups in complete blocks of 128*UNROLL ops
     EvState st = st_out;
     uint32_t a_ref = 0, a_read = 0, a_n = 0, a_h = 0;
     uint32_t base = 0;
-    for (; base < full; base += 32 * SCAN_UNROLL) {
-        uint4 w[SCAN_UNROLL];
+    for (; base < full; base += 32 * UNROLL) {
+        uint4 w[UNROLL];
 #pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
+        for (int u = 0; u < UNROLL; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
 #pragma unroll
-        for (int u = 0; u < SCAN_UNROLL; ++u) SCAN_GROUP(w[u])
+        for (int u = 0; u < UNROLL; ++u) SCAN_GROUP(w[u])
     }
     for (; base < n4; base += 32) {   // ragged tail: bounds-checked, words past n_cigar zeroed
         const uint32_t idx = base + lane;
@@ -165,8 +165,9 @@ __device__ __forceinline__ void scan_cigar(const uint4* __restrict__ cg, uint32_
     st_out = st; acc_ref_out = a_ref; acc_read_out = a_read;
 }
 
-__global__ void __launch_bounds__(256, 3) k_cigar_scan(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
-                                                        uint32_t work_cap, uint32_t* cnt) {
+template <int UNROLL, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work,
+                                                           uint32_t work_cap, uint32_t* cnt) {
     const int lane = threadIdx.x & 31;
     DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
     const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(256, 3) k_cigar_scan(DevSoa a, ChainParams p, 
             EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = 0; st.n_tw = 0; st.nsum = 0; st.hsum = 0;
             uint32_t acc_ref = 0, acc_read = 0;
             const bool need_summary = primary && a.sa_len[i] > 0;
-            if (need_summary) scan_cigar<true>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
-            else scan_cigar<false>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
+            if (need_summary) scan_cigar<true, UNROLL>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
+            else scan_cigar<false, UNROLL>(cg, n, thresh, lane, p, r, st, acc_ref, acc_read, out);
             // ---- primaries with an SA tag: summary for the split-read analysis -----------------
             if (need_summary) {
                 const uint32_t hard = warp_sum(st.hsum);
@@ -599,9 +600,18 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                     SVIM_CUDA(cudaFuncSetAttribute(k_cigar_scan_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     { ctx->launches++; k_cigar_scan_bulk<<<dev_sms * 3, 32 * SCAN_BULK_WARPS, smem, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 2) {   // experiment: 8 loads in flight per lane, 2 CTAs/SM
+                    { ctx->launches++; k_cigar_scan<8, 2><<<dev_sms * 6, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 3) {   // experiment: 2 loads per lane, 4 CTAs/SM
+                    { ctx->launches++; k_cigar_scan<2, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 4) {   // experiment: 4 loads per lane, 4 CTAs/SM (64 registers)
+                    { ctx->launches++; k_cigar_scan<4, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
                 } else {
-                    { ctx->launches++; k_cigar_scan<<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                             ctx->d_counters.as<uint32_t>()); }
+                    { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
                 }
             }
         }

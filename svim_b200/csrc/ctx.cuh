@@ -70,9 +70,13 @@ struct SigSet {   // one signature list on the device (main / all_bnds twins)
     int64_t n = 0, ins_bytes = 0;
 };
 
+#define SVIM_AUX_STREAMS 4
+
 struct svimgpu_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream[SVIM_AUX_STREAMS];      // concurrent Myers bins
+    cudaEvent_t aux_ev[SVIM_AUX_STREAMS + 1];
     svim_params params;
     std::string err;
     int err_code = 0;

@@ -241,10 +241,11 @@ __device__ __forceinline__ int word_vsum(const Word32& w, int64_t m, int64_t row
 }
 
 // one word step; e = hin + 1 in {0,1,2}; returns hout + 1
+template <int NP>
 __device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t e) {
     const uint32_t hneg = 1u >> e, hpos = e >> 1;
-    const uint32_t eql = ~((w.p0l ^ m0) | (w.p1l ^ m1) | (w.p2l ^ m2));
-    const uint32_t eqh = ~((w.p0h ^ m0) | (w.p1h ^ m1) | (w.p2h ^ m2));
+    const uint32_t eql = NP == 2 ? ~((w.p0l ^ m0) | (w.p1l ^ m1)) : ~((w.p0l ^ m0) | (w.p1l ^ m1) | (w.p2l ^ m2));
+    const uint32_t eqh = NP == 2 ? ~((w.p0h ^ m0) | (w.p1h ^ m1)) : ~((w.p0h ^ m0) | (w.p1h ^ m1) | (w.p2h ^ m2));
     const uint32_t xvl = eql | w.mvl, xvh = eqh | w.mvh;
     const uint32_t el = eql | hneg;
     uint32_t sl, sh;
@@ -261,7 +262,7 @@ __device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m
 }
 
 // G lanes per pair, WPL words per lane; strips of G*WPL words (only G = 32 ever needs more than one strip)
-template <int G, int WPL>
+template <int G, int WPL, int NP>
 __device__ int32_t myers_fast(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
                               uint8_t* __restrict__ hbuf, int gl, bool valid) {
     const int64_t W = valid ? ((m + 63) >> 6) : 0;
@@ -296,10 +297,11 @@ __device__ int32_t myers_fast(const uint8_t* __restrict__ pat, int64_t m, const 
             const uint32_t pk = gl == 0 ? (t_cur | (h_cur << 24)) : recv;
             const int j = s - gl;
             if (lane_on && (unsigned)j < (unsigned)n) {
-                const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111), m2 = __byte_perm(pk, 0, 0x2222);
+                const uint32_t m0 = __byte_perm(pk, 0, 0x0000), m1 = __byte_perm(pk, 0, 0x1111);
+                const uint32_t m2 = NP == 2 ? 0u : __byte_perm(pk, 0, 0x2222);
                 uint32_t e = pk >> 24;
 #pragma unroll
-                for (int k = 0; k < WPL; ++k) e = word_step(w[k], m0, m1, m2, e);
+                for (int k = 0; k < WPL; ++k) e = word_step<NP>(w[k], m0, m1, m2, e);
                 pk_out = (pk & 0x00ffffffu) | (e << 24);
                 if (G == 32 && !last_strip && gl == 31) hbuf[j] = (uint8_t)e;
             }
@@ -368,7 +370,9 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
             if (gl == 0) { uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }
             valid = false;
         }
-        const int32_t ed = myers_fast<G, WPL>(pat, m, txt32, (int)n, hbuf, gl, valid);
+        // pure A/C/G/T pairs (codes 0-3) need two planes only; the choice is warp-uniform
+        const bool three = __any_sync(0xffffffffu, valid && orall >= 4);
+        const int32_t ed = three ? myers_fast<G, WPL, 3>(pat, m, txt32, (int)n, hbuf, gl, valid) : myers_fast<G, WPL, 2>(pat, m, txt32, (int)n, hbuf, gl, valid);
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
@@ -411,6 +415,21 @@ __global__ void __launch_bounds__(128) k_myers_generic(MyersArgs a, StringPairs 
     if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
 }
 
+// the Myers bins run on SVIM_AUX_STREAMS side streams: fork from / join to the context's main stream
+static cudaError_t myers_fork(svimgpu_ctx* ctx) {
+    cudaError_t e = cudaEventRecord(ctx->aux_ev[SVIM_AUX_STREAMS], ctx->stream);
+    for (int i = 0; i < SVIM_AUX_STREAMS && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(ctx->aux_stream[i], ctx->aux_ev[SVIM_AUX_STREAMS], 0);
+    return e;
+}
+static cudaError_t myers_join(svimgpu_ctx* ctx) {
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < SVIM_AUX_STREAMS && e == cudaSuccess; ++i) {
+        e = cudaEventRecord(ctx->aux_ev[i], ctx->aux_stream[i]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[i], 0);
+    }
+    return e;
+}
+
 template <bool STRINGS>
 static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
     if (a.n_work == 0) return cudaSuccess;
@@ -426,18 +445,19 @@ static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, Stri
     if (e != cudaSuccess) return e;
     a.scratch = scratch.as<uint8_t>();
     ctx->launches++;
+    cudaStream_t stream = ctx->aux_stream[bin % SVIM_AUX_STREAMS];   // bins overlap: one kernel's tail is filled by the next
     switch (bin) {
-        case 0: k_myers_fast<4, 1, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 1: k_myers_fast<4, 2, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 2: k_myers_fast<4, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 3: k_myers_fast<4, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 4: k_myers_fast<8, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 5: k_myers_fast<8, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 6: k_myers_fast<16, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 7: k_myers_fast<16, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 8: k_myers_fast<32, 3, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        case 9: k_myers_fast<32, 4, STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;
-        default: k_myers_generic<STRINGS><<<blocks, 128, 0, ctx->stream>>>(a, sp); break;   // MYERS_BINS: any bytes
+        case 0: k_myers_fast<4, 1, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 1: k_myers_fast<4, 2, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 2: k_myers_fast<4, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 3: k_myers_fast<4, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 4: k_myers_fast<8, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 5: k_myers_fast<8, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 6: k_myers_fast<16, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 7: k_myers_fast<16, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 8: k_myers_fast<32, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 9: k_myers_fast<32, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        default: k_myers_generic<STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;   // MYERS_BINS: any bytes
     }
     return cudaGetLastError();
 }
