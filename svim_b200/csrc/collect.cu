@@ -606,11 +606,17 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                 } else if (ctx->scan_variant == 3) {   // experiment: 2 loads per lane, 4 CTAs/SM
                     { ctx->launches++; k_cigar_scan<2, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 4) {   // experiment: 4 loads per lane, 4 CTAs/SM (64 registers)
-                    { ctx->launches++; k_cigar_scan<4, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else {
+                } else if (ctx->scan_variant == 4) {   // experiment: 4 loads per lane, 3 CTAs/SM (80 registers) — the round-1 v2..v5 kernel
                     { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 5) {   // experiment: 5 CTAs/SM
+                    { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                    ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 6) {   // experiment: 6 CTAs/SM
+                    { ctx->launches++; k_cigar_scan<4, 6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                    ctx->d_counters.as<uint32_t>()); }
+                } else {                               // default: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers): 0.74 of the measured HBM peak
+                    { ctx->launches++; k_cigar_scan<4, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
                 }
             }
