@@ -228,6 +228,141 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams 
     if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
 }
 
+// ---- low-register variant: rare-path state lives in shared memory --------------------------------------------
+// The fast path only needs the four lane-private accumulators and the loaded words; everything the rare path
+// touches (running base positions, ordinals, record identity, queues, options) is parked in shared memory so the
+// kernel fits 5-6 CTAs per SM without spilling.
+struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t thresh; };
+struct ScanWarp { EvState st; ScanRec r; };
+
+template <bool SUM>
+__device__ __noinline__ void scan_events_s(const uint4 w, int lane, const ScanShared* sh, ScanWarp* ws, uint32_t acc_ref, uint32_t acc_read) {
+    DeviceEmitter out{sh->qm, sh->qt, sh->overflow};
+    const EvState old = ws->st;
+    const ScanRec r = ws->r;
+    __syncwarp();
+    EvState st = scan_events<SUM>(w, sh->thresh, lane, sh->p, r, old, acc_ref, acc_read, out);
+    if (SUM) {   // scan_events adds this lane's N/H bases; the shared copy keeps warp totals
+        st.nsum = old.nsum + warp_sum(st.nsum - old.nsum);
+        st.hsum = old.hsum + warp_sum(st.hsum - old.hsum);
+    }
+    if (lane == 0) ws->st = st;
+    __syncwarp();
+}
+
+#define SCAN_GROUP_S(W)                                                                                            \
+    {                                                                                                              \
+        const uint32_t B0 = op_bit((W).x), B1 = op_bit((W).y), B2 = op_bit((W).z), B3 = op_bit((W).w);             \
+        const bool ev = is_event((W).x, B0, thresh) | is_event((W).y, B1, thresh) | is_event((W).z, B2, thresh) |  \
+                        is_event((W).w, B3, thresh);                                                               \
+        if (__ballot_sync(FULL, ev) == 0) {                                                                        \
+            acc_op<SUM>((W).x, B0, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).y, B1, a_ref, a_read, a_n, a_h);      \
+            acc_op<SUM>((W).z, B2, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).w, B3, a_ref, a_read, a_n, a_h);      \
+        } else {                                                                                                   \
+            scan_events_s<SUM>((W), lane, sh, ws, a_ref, a_read);                                                  \
+            a_ref = 0; a_read = 0;                                                                                 \
+        }                                                                                                          \
+    }
+
+template <bool SUM>
+__device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, const ScanShared* sh, ScanWarp* ws,
+                                             uint32_t& acc_ref_out, uint32_t& acc_read_out, uint32_t& n_out, uint32_t& h_out) {
+    const uint32_t n4 = (n + 3) >> 2;
+    const uint32_t full = (n >> 2) / 128 * 128;
+    uint32_t a_ref = 0, a_read = 0, a_n = 0, a_h = 0;
+    uint32_t base = 0;
+    for (; base < full; base += 128) {
+        uint4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) SCAN_GROUP_S(w[u])
+    }
+    for (; base < n4; base += 32) {
+        const uint32_t idx = base + lane;
+        uint4 w = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
+        if (idx == n4 - 1) {
+            const uint32_t rr = n & 3u;
+            if (rr == 1) { w.y = 0; w.z = 0; w.w = 0; } else if (rr == 2) { w.z = 0; w.w = 0; } else if (rr == 3) { w.w = 0; }
+        }
+        SCAN_GROUP_S(w)
+    }
+    acc_ref_out = a_ref; acc_read_out = a_read; n_out = a_n; h_out = a_h;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
+                                                             uint32_t* cnt) {
+    __shared__ ScanShared sh_s;
+    __shared__ ScanWarp ws_s[8];
+    const int lane = threadIdx.x & 31;
+    const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
+    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.thresh = thresh; }
+    __syncthreads();
+    const ScanShared* sh = &sh_s;
+    ScanWarp* ws = &ws_s[threadIdx.x >> 5];
+    const uint32_t n_aln = (uint32_t)a.n;
+    uint32_t primaries = 0;
+    for (;;) {
+        uint32_t first = 0;
+        if (lane == 0) first = atomicAdd(cnt + CNT_NEXT_ALN, (uint32_t)SCAN_BATCH);
+        first = __shfl_sync(FULL, first, 0);
+        if (first >= n_aln) break;
+        const uint32_t last = min(first + SCAN_BATCH, n_aln);
+        for (uint32_t i = first; i < last; ++i) {
+            const uint32_t flag = a.flag[i];
+            if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;
+            const bool primary = !(flag & 0x800u);
+            primaries += primary;
+            const uint32_t n = a.n_cigar[i];
+            const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]);
+            if (lane == 0) {
+                ScanRec r; r.i = i; r.qid = a.qname_id[i]; r.tid = a.tid[i]; r.ref_start = a.pos[i]; r.l_seq = a.l_seq[i];
+                EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = 0; st.n_tw = 0; st.nsum = 0; st.hsum = 0;
+                ws->r = r; ws->st = st;
+            }
+            __syncwarp();
+            uint32_t acc_ref = 0, acc_read = 0, acc_n = 0, acc_h = 0;
+            const bool need_summary = primary && a.sa_len[i] > 0;
+            if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
+            else scan_cigar_s<false>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
+            if (need_summary) {
+                const EvState st = ws->st;     // st.nsum / st.hsum: warp totals of the rare-path groups (scan_events_s)
+                const uint32_t hard = warp_sum(acc_h) + st.hsum;
+                if (hard == 0) {
+                    const int64_t ref_q = st.base_ref + warp_sum(acc_ref);
+                    const int64_t rd = st.base_read + warp_sum(acc_read);
+                    const int64_t nsum = (int64_t)warp_sum(acc_n) + st.nsum;
+                    if (lane == 0) {
+                        const uint32_t* c32 = a.cigar + a.cigar_off[i];
+                        const int64_t l_seq = a.l_seq[i];
+                        CigarSummary cs; cigsum_init(cs);
+                        if (l_seq == 0) {
+                            for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
+                        } else {
+                            cs.ref_len = ref_q + nsum; cs.qlen_h = rd; cs.hard = 0; cs.n_ops = (int32_t)n;
+                            uint32_t k = 0;
+                            for (; k < n; ++k) { uint32_t op = c32[k] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.lead_s += c32[k] >> 4; }
+                            for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
+                        }
+                        Seg sg; int64_t rl;
+                        cigsum_finish(cs, l_seq, a.pos[i], (flag & 0x10u) ? 1 : 0, sg, rl);
+                        uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
+                        if (slot < work_cap) {
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
+                            wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
+                            work[slot] = wk;
+                        } else atomicExch(cnt + CNT_OVERFLOW, 1u);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    primaries = warp_sum(primaries);
+    if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
+}
+
 // ---- bulk-copy (TMA engine) variant of the scan ---------------------------------------------------------
 // Each warp owns a ring of SCAN_STAGES shared-memory stages of 2 KiB (one 512-op block).  Lane 0 issues
 // cp.async.bulk global->shared copies that complete on a per-stage mbarrier; in-flight bytes are bounded by
@@ -608,6 +743,15 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                                                                    ctx->d_counters.as<uint32_t>()); }
                 } else if (ctx->scan_variant == 4) {   // experiment: 4 loads per lane, 3 CTAs/SM (80 registers) — the round-1 v2..v5 kernel
                     { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
+                    { ctx->launches++; k_cigar_scan_s<5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                   ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
+                    { ctx->launches++; k_cigar_scan_s<4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                  ctx->d_counters.as<uint32_t>()); }
+                } else if (ctx->scan_variant == 9) {   // experiment: rare-path state in shared memory, 6 CTAs/SM
+                    { ctx->launches++; k_cigar_scan_s<6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
                 } else if (ctx->scan_variant == 5) {   // experiment: 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
