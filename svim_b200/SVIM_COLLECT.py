@@ -58,49 +58,89 @@ def as_batch(bam) -> AlignmentBatch:
 
 
 def materialize_signatures(sigs: np.ndarray, ins: np.ndarray, batch: AlignmentBatch):
-    """svim_sig records (+ INS blob) -> SVSignature objects."""
+    """svim_sig records (+ INS blob) -> SVSignature objects, in record order.
+
+    The per-object cost dominates once the kernels are fast, so objects are built by filling `__dict__` directly
+    (same attributes the constructors set) from column lists, one comprehension per type."""
+    n = len(sigs)
+    if n == 0:
+        return []
+    import gc
+    was_enabled = gc.isenabled()
+    gc.disable()            # hundreds of thousands of small containers: generational GC passes would dominate
+    try:
+        return _materialize(sigs, ins, batch, n)
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
+def _materialize(sigs, ins, batch, n):
     names = batch.contig_names
-    qname = batch.qname
-    ins_b = ins.tobytes()
-    out = []
-    cols = [sigs[f].tolist() for f in ("type", "flags", "contig1", "start", "end", "contig2", "pos", "qname_id", "seq_off",
-                                      "seq_len", "copies")]
-    for t, fl, c1, s, e, c2, pos, qid, so, sl, cp in zip(*cols):
-        src = "suppl" if fl & _lib.F_SUPPL else "cigar"
-        read = qname(qid)
-        if t == 0:
-            o = SignatureDeletion(names[c1], s, e, src, read)
-        elif t == 1:
-            o = SignatureInsertion(names[c1], s, e, src, read, ins_b[so:so + sl].decode("ascii"))
-        elif t == 2:
-            o = SignatureInversion(names[c1], s, e, src, read, _lib.INV_DIRECTIONS[(fl >> _lib.F_INVDIR_SHIFT) & 7])
-        elif t == 3:
-            o = SignatureDuplicationTandem(names[c1], s, e, cp, bool(fl & _lib.F_FULLY_COVERED), src, read)
-        elif t == 4:
-            # records are already in canonical breakend order; bypass the constructor's swap
-            o = SignatureTranslocation.__new__(SignatureTranslocation)
-            o.contig1, o.pos1, o.direction1 = names[c1], s, "rev" if fl & _lib.F_DIR1_REV else "fwd"
-            o.contig2, o.pos2, o.direction2 = names[c2], pos, "rev" if fl & _lib.F_DIR2_REV else "fwd"
-            o.signature, o.read, o.type = src, read, "BND"
-        else:
-            o = SignatureInsertionFrom(names[c1], s, e, names[c2], pos, src, read)
-        out.append(o)
+    typ = sigs["type"]
+    flags = sigs["flags"]
+    src_l = np.where(flags & _lib.F_SUPPL, "suppl", "cigar").tolist()
+    qid = sigs["qname_id"]
+    if batch.qnames is None:
+        reads = ["read%d" % q for q in qid.tolist()]
+    else:
+        qn = batch.qnames
+        reads = [qn[q] for q in qid.tolist()]
+    c1 = [names[t] for t in sigs["contig1"].tolist()] if len(names) > 1 else [names[0]] * n
+    start = sigs["start"].tolist(); end = sigs["end"].tolist()
+    out = [None] * n
+    new = object.__new__
+
+    def build(cls, idx, dicts):
+        for k, d in zip(idx, dicts):
+            o = new(cls)
+            o.__dict__ = d
+            out[k] = o
+
+    idx = np.nonzero(typ == 0)[0].tolist()
+    build(SignatureDeletion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k], "type": "DEL"} for k in idx])
+    idx = np.nonzero(typ == 1)[0].tolist()
+    if idx:
+        text = ins.tobytes().decode("ascii")
+        so = sigs["seq_off"].tolist(); sl = sigs["seq_len"].tolist()
+        build(SignatureInsertion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k],
+                                         "sequence": text[so[k]:so[k] + sl[k]], "type": "INS"} for k in idx])
+    idx = np.nonzero(typ == 2)[0].tolist()
+    if idx:
+        fl = flags.tolist()
+        build(SignatureInversion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k], "type": "INV",
+                                         "direction": _lib.INV_DIRECTIONS[(fl[k] >> _lib.F_INVDIR_SHIFT) & 7]} for k in idx])
+    idx = np.nonzero(typ == 3)[0].tolist()
+    if idx:
+        fl = flags.tolist(); cp = sigs["copies"].tolist()
+        build(SignatureDuplicationTandem, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "copies": cp[k],
+                                                 "fully_covered": bool(fl[k] & _lib.F_FULLY_COVERED), "signature": src_l[k], "read": reads[k],
+                                                 "type": "DUP_TAN"} for k in idx])
+    idx = np.nonzero(typ >= 4)[0].tolist()
+    if idx:
+        fl = flags.tolist(); pos = sigs["pos"].tolist(); c2 = sigs["contig2"].tolist(); tl = typ.tolist()
+        for k in idx:
+            if tl[k] == 4:      # records are already in canonical breakend order (no constructor swap)
+                o = new(SignatureTranslocation)
+                o.__dict__ = {"contig1": c1[k], "pos1": start[k], "direction1": "rev" if fl[k] & _lib.F_DIR1_REV else "fwd",
+                              "contig2": names[c2[k]], "pos2": pos[k], "direction2": "rev" if fl[k] & _lib.F_DIR2_REV else "fwd",
+                              "signature": src_l[k], "read": reads[k], "type": "BND"}
+            else:
+                o = new(SignatureInsertionFrom)
+                o.__dict__ = {"contig1": c1[k], "start": start[k], "end": end[k], "contig2": names[c2[k]], "pos": pos[k],
+                              "signature": src_l[k], "read": reads[k], "type": "DUP_INT"}
+            out[k] = o
     return out
 
 
-def collect_arrays(batch: AlignmentBatch, options=None, ctx=None, resident=False):
-    """Run the COLLECT kernels; returns (ctx, stats, (sigs, ins), (twin_sigs, twin_ins))."""
+def collect_arrays(batch: AlignmentBatch, options=None, ctx=None):
+    """Run the COLLECT kernels from host buffers; returns (ctx, stats, (sigs, ins), (twin_sigs, twin_ins))."""
     ctx = ctx or runtime.context()
     ctx.set_params(_lib.Params.from_options(options))
-    key = (id(batch), tuple(batch.contig_names))
     if getattr(ctx, "contigs_key", None) != tuple(batch.contig_names):
         ctx.set_contigs(batch.contig_names)
         ctx.contigs_key = tuple(batch.contig_names)
-    if resident and getattr(ctx, "resident", None) == key:
-        stats = ctx.collect()
-    else:
-        stats = ctx.collect_host(batch)
-        ctx.resident = key
+    stats = ctx.collect_host(batch)
     if stats.n_data_errors:
         raise _lib.SvimGpuError(-5, "%d reads carry SA tags the reference would raise on "
                                     "(unknown contig / non-integer field / empty CIGAR)" % stats.n_data_errors)

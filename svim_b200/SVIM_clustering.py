@@ -68,6 +68,17 @@ def _none_if_nan(x):
 
 def build_clusters(clusters: np.ndarray, members: np.ndarray, signatures):
     """svim_cluster records -> per-type lists of SignatureCluster objects (enum order)."""
+    import gc
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return _build_clusters(clusters, members, signatures)
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
+def _build_clusters(clusters, members, signatures):
     out = [[] for _ in range(6)]
     mem = members.tolist()
     cols = [clusters[f].tolist() for f in ("type", "start", "end", "dest_start", "dest_end", "score", "std_span", "std_pos",

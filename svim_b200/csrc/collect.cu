@@ -750,7 +750,7 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                 } else if (ctx->scan_variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
                     { ctx->launches++; k_cigar_scan_s<4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 9) {   // experiment: rare-path state in shared memory, 6 CTAs/SM
+                } else if (ctx->scan_variant == 0 || ctx->scan_variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
                     { ctx->launches++; k_cigar_scan_s<6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
                 } else if (ctx->scan_variant == 5) {   // experiment: 5 CTAs/SM
@@ -759,7 +759,7 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                 } else if (ctx->scan_variant == 6) {   // experiment: 6 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                     ctx->d_counters.as<uint32_t>()); }
-                } else {                               // default: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers): 0.74 of the measured HBM peak
+                } else {                               // variant 10+: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers): 0.74 of the measured HBM peak
                     { ctx->launches++; k_cigar_scan<4, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
                 }
