@@ -68,7 +68,12 @@ typedef struct {
 } svim_aln_soa;
 
 /* Signature types, in the reference's clustering call order (SVIM_CLUSTER.py:19-24). */
-enum { SVIM_DEL = 0, SVIM_INS = 1, SVIM_INV = 2, SVIM_DUP_TAN = 3, SVIM_BND = 4, SVIM_DUP_INT = 5 };
+enum { SVIM_DEL = 0, SVIM_INS = 1, SVIM_INV = 2, SVIM_DUP_TAN = 3, SVIM_BND = 4, SVIM_DUP_INT = 5,
+       /* cluster-stage only: a DUP_INT *candidate* (partition_and_cluster_candidates, SVIM_clustering.py:306-372):
+        * partitioned like a unilocal record on its source interval (SVCandidate.py:24-36), distance of
+        * span_position_distance_intdup_candidates (:110-119), no same-read rules; svim_csig.seq_off carries the
+        * IEEE-754 bits of the destination END (candidates store it explicitly). Counted under index 5 in the stats. */
+       SVIM_DUP_INT_CAND = 6 };
 /* svim_sig.flags */
 enum {
     SVIM_F_SUPPL = 1,          /* signature source "suppl" (else "cigar") */

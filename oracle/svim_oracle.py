@@ -630,6 +630,70 @@ def cluster(sigs, genome, p: Params, stats=None):
     return (res["DEL"], res["INS"], res["INV"], res["DUP_TAN"], res["DUP_INT"], res["BND"])
 
 
+class Cand:
+    """DUP_INT candidate value object (SVCandidate.py:424-453 fields used by the clustering twin)."""
+    __slots__ = ("type", "contig", "start", "end", "dest_contig", "dest_start", "dest_end", "members", "score", "std_span", "std_pos", "cutpaste")
+
+    def __init__(self, contig, start, end, dest_contig, dest_start, dest_end, members, score, std_span, std_pos, cutpaste=False):
+        self.type = "DUP_INT"
+        self.contig, self.start, self.end = contig, max(0, start), end
+        self.dest_contig, self.dest_start, self.dest_end = dest_contig, max(0, dest_start), dest_end
+        self.members, self.score, self.std_span, self.std_pos, self.cutpaste = members, score, std_span, std_pos, cutpaste
+
+    def key(self):                       # Candidate.get_key, SVCandidate.py:24-26
+        return (self.type, self.contig, self.end)
+
+    def gap_to(self, other):             # Candidate.downstream_distance_to, SVCandidate.py:29-36
+        if self.type == other.type and self.contig == other.contig:
+            return max(0, other.start - self.end)
+        return float("inf")
+
+    def as_tuple(self):
+        return tuple(getattr(self, f) for f in self.__slots__)
+
+
+def candidate_distance(a: Cand, b: Cand, p: Params):
+    """span_position_distance_intdup_candidates (SVIM_clustering.py:110-119)."""
+    N = p.position_distance_normalizer
+    span1, span2 = a.end - a.start, b.end - b.start
+    c1, c2 = (a.start + a.end) // 2, (b.start + b.end) // 2
+    return abs(c1 - c2) / N + abs(a.dest_start - b.dest_start) / N + abs(span1 - span2) / max(span1, span2)
+
+
+def partition_and_cluster_candidates(cands, p: Params):
+    """partition_and_cluster_candidates (SVIM_clustering.py:306-372)."""
+    from scipy.cluster.hierarchy import linkage, fcluster
+    parts = []
+    for c in sorted(cands, key=Cand.key):
+        if parts and parts[-1][-1].gap_to(c) <= p.partition_max_distance:
+            parts[-1].append(c)
+        else:
+            parts.append([c])
+    groups = []
+    random.seed(1524)
+    for part in parts:
+        if len(part) == 1:
+            groups.append([part[0]]); continue
+        sample = random.sample(part, 100) if len(part) > 100 else part
+        dist = [candidate_distance(sample[i], sample[j], p) for i in range(len(sample) - 1) for j in range(i + 1, len(sample))]
+        ids = list(fcluster(linkage(np.array(dist), method="average"), p.cluster_max_distance, criterion="distance"))
+        new = [[] for _ in range(max(ids))]
+        for c, k in zip(sample, ids):
+            new[k - 1].append(c)
+        groups.extend(new)
+    out = []
+    for g in groups:
+        n = len(g)
+        spans = [c.std_span for c in g if c.std_span is not None]
+        poss = [c.std_pos for c in g if c.std_pos is not None]
+        if g[0].type == "DUP_INT":
+            out.append(Cand(g[0].contig, int(round(sum(c.start for c in g) / n)), int(round(sum(c.end for c in g) / n)),
+                            g[0].dest_contig, int(round(sum(c.dest_start for c in g) / n)), int(round(sum(c.dest_end for c in g) / n)),
+                            [m for c in g for m in c.members], max(c.score for c in g),
+                            mean(spans) if spans else None, mean(poss) if poss else None, any(c.cutpaste for c in g)))
+    return out
+
+
 # ---------------------------------------------------------------------------
 # scipy restated (spec for the CUDA linkage kernel; verified against scipy in tests)
 # ---------------------------------------------------------------------------

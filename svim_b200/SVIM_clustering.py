@@ -134,7 +134,10 @@ def form_partitions(sv_signatures, max_distance):
         return []
     ctx = runtime.context()
     ctx.set_params(_lib.Params.from_options(None, partition_max_distance=max_distance))
-    cs, blob, names = marshal_signatures(sv_signatures)
+    if hasattr(sv_signatures[0], "source_contig") and hasattr(sv_signatures[0], "dest_contig") and not hasattr(sv_signatures[0], "read"):
+        cs = marshal_candidates(sv_signatures)     # COMBINE partitions DUP_INT candidates with the same function
+    else:
+        cs, blob, names = marshal_signatures(sv_signatures)
     ctx.set_signatures(cs, None, None)       # partitions do not depend on the inserted sequences
     ctx.partition()
     order, off = ctx.fetch_partitions(len(cs))
@@ -159,3 +162,88 @@ def partition_and_cluster(signatures, options, type):
     for t in present:
         out.extend(per_type[t])
     return out
+
+
+# ---- COMBINE-stage twin --------------------------------------------------------------
+class CandidateDuplicationInterspersed:
+    """Minimal stand-in used when the reference package is not importable: the attributes
+    partition_and_cluster_candidates reads and writes (SVCandidate.py:424-453)."""
+    type = "DUP_INT"
+
+    def __init__(self, source_contig, source_start, source_end, dest_contig, dest_start, dest_end, members, score, std_span, std_pos,
+                 cutpaste=False):
+        self.source_contig, self.source_start, self.source_end = source_contig, max(0, source_start), source_end
+        self.dest_contig, self.dest_start, self.dest_end = dest_contig, max(0, dest_start), dest_end
+        self.members, self.score, self.std_span, self.std_pos, self.cutpaste = members, score, std_span, std_pos, cutpaste
+        self.type = "DUP_INT"
+
+    def get_source(self):
+        return (self.source_contig, self.source_start, self.source_end)
+
+    def get_destination(self):
+        return (self.dest_contig, self.dest_start, self.dest_end)
+
+    def get_key(self):
+        return (self.type, self.source_contig, self.source_end)
+
+    def downstream_distance_to(self, other):
+        if self.type == other.type and self.source_contig == other.source_contig:
+            return max(0, other.source_start - self.source_end)
+        return float("inf")
+
+
+def _candidate_class():
+    try:
+        from svim.SVCandidate import CandidateDuplicationInterspersed as ref_cls      # reference installed: return its own class
+        return ref_cls
+    except Exception:
+        return CandidateDuplicationInterspersed
+
+
+def marshal_candidates(candidates):
+    """DUP_INT candidates -> svim_csig records of type SVIM_DUP_INT_CAND (unique read ids: no same-read rules)."""
+    n = len(candidates)
+    cs = np.zeros(n, dtype=_lib.CSIG_DTYPE)
+    names = sorted({c.get_source()[0] for c in candidates} | {c.get_destination()[0] for c in candidates})
+    rank = {c: i for i, c in enumerate(names)}
+    dest_end = np.zeros(n, dtype=np.float64)
+    for k, c in enumerate(candidates):
+        sc, ss, se = c.get_source()
+        dc, ds, de = c.get_destination()
+        r = cs[k]
+        r["type"] = _lib.TYPE_DUP_INT_CAND
+        r["start"], r["end"], r["dpos"] = ss, se, ds
+        r["contig_a"], r["contig_b"] = rank[sc], rank[dc]
+        r["read_id"] = k
+        dest_end[k] = de
+    cs["seq_off"] = dest_end.view(np.uint64)          # bits of the destination end (svimgpu.h, SVIM_DUP_INT_CAND)
+    return cs
+
+
+def partition_and_cluster_candidates(candidates, options, type):
+    """partition_and_cluster_candidates (SVIM_clustering.py:306-372): key sort, partitions, host-RNG sampling,
+    span_position_distance_intdup_candidates matrix, average linkage and flat cut on the GPU; the merged
+    candidate's fields (max score, concatenated members, mean of the stds, cut&paste flag) on the host."""
+    from statistics import mean
+    if len(candidates) == 0:
+        logging.info("Clustered {0}: {1} partitions and {2} clusters".format(type, 0, 0))
+        return []
+    ctx = runtime.context()
+    ctx.set_params(_lib.Params.from_options(options))
+    ctx.set_signatures(marshal_candidates(candidates), None, None)
+    stats, clusters, members = ctx.cluster()
+    logging.debug("%d out of %d partitions for %s exceeded 100 elements." % (stats.large_partitions[5], stats.n_partitions[5], candidates[0].type))
+    logging.info("Clustered {0}: {1} partitions and {2} clusters".format(type, stats.n_partitions[5], stats.n_clusters[5]))
+    cls = _candidate_class()
+    mem = members.tolist()
+    final = []
+    for off, size, s, e, ds, de in zip(*[clusters[f].tolist() for f in ("member_off", "size", "start", "end", "dest_start", "dest_end")]):
+        group = [candidates[i] for i in mem[off:off + size]]
+        if group[0].type != "DUP_INT":
+            continue
+        spans = [c.std_span for c in group if c.std_span is not None]
+        poss = [c.std_pos for c in group if c.std_pos is not None]
+        final.append(cls(group[0].get_source()[0], s, e, group[0].get_destination()[0], ds, de,
+                         [m for c in group for m in c.members], max(c.score for c in group),
+                         mean(spans) if spans else None, mean(poss) if poss else None, any(c.cutpaste for c in group)))
+    return final

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsvimgpu.so")
 
 TYPE_NAMES = ("DEL", "INS", "INV", "DUP_TAN", "BND", "DUP_INT")     # enum order of svimgpu.h
 TYPE_CODE = {n: i for i, n in enumerate(TYPE_NAMES)}
+TYPE_DUP_INT_CAND = 6                     # cluster-stage only: DUP_INT candidate (svimgpu.h)
 INV_DIRECTIONS = ("left_fwd", "left_rev", "right_fwd", "right_rev", "all")
 
 F_SUPPL, F_FULLY_COVERED, F_DIR1_REV, F_DIR2_REV, F_INVDIR_SHIFT = 1, 2, 4, 8, 4

@@ -74,7 +74,7 @@ __global__ void k_partition_heads(const svim_csig* s, const uint64_t* group, uin
     } else {
         for (int t = 0; t <= b.type; ++t) type_start[t] = 0;
     }
-    if (k == n - 1) for (int t = b.type + 1; t <= 6; ++t) type_start[t] = n;
+    if (k == n - 1) for (int t = b.type + 1; t <= 7; ++t) type_start[t] = n;
     head[k] = h ? 1 : 0;
 }
 
@@ -339,6 +339,7 @@ __global__ void k_consolidate(const svim_csig* sig /* emission order */, const u
         v[3 * i] = m.end - m.start; v[3 * i + 1] = (m.end + m.start) / 2.0;
         double ds = 0.0, de = 0.0;
         if (type == SVIM_DUP_INT) { ds = m.dpos; de = m.dpos + (m.end - m.start); }
+        else if (type == SVIM_DUP_INT_CAND) { ds = m.dpos; memcpy(&de, &m.seq_off, 8); }   // explicit destination end
         else if (type == SVIM_BND) { ds = m.dpos; de = m.dpos + 1.0; }
         sum_ds += ds; sum_de += de;
         v[3 * i + 2] = (de + ds) / 2.0;
@@ -359,7 +360,7 @@ __global__ void k_consolidate(const svim_csig* sig /* emission order */, const u
     double span = a_e - a_s, ss = sd_span, sp = sd_pos;
     if (type == SVIM_DUP_TAN) {
         cl.dest_start = cl.end; cl.dest_end = cl.end + (int64_t)max_copies * (cl.end - cl.start);
-    } else if (type == SVIM_DUP_INT) {
+    } else if (type == SVIM_DUP_INT || type == SVIM_DUP_INT_CAND) {
         const double d_s = sum_ds / (double)n, d_e = sum_de / (double)n;
         cl.dest_start = py_round_int(d_s); cl.dest_end = py_round_int(d_e);
         span = ((a_e - a_s) + (d_e - d_s)) / 2.0;                 // mean([..]) of two floats
@@ -377,7 +378,7 @@ __global__ void k_consolidate(const svim_csig* sig /* emission order */, const u
         span = 500.0;
         if (has) { ss = sd_pos; sp = stdev_values(v + 2, n, 3); }
     }
-    if (has && span == 0.0) atomicExch(err, 1u);                  // ZeroDivisionError in calculate_score
+    if (has && span == 0.0 && type != SVIM_DUP_INT_CAND) atomicExch(err, 1u);   // ZeroDivisionError in calculate_score (candidates are scored on the host)
     cl.score = cluster_score(n_eff, has, ss, sp, span);
     cl.std_span = has ? ss : nanv; cl.std_pos = has ? sp : nanv;
     clusters[c] = cl;
@@ -443,7 +444,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     const svim_csig* sorted = ctx->d_csig_sorted.as<svim_csig>();
     // ---- partitions --------------------------------------------------------------------------------------
     uint32_t P = 0;
-    uint32_t type_start[7];
+    uint32_t type_start[8];
     {
         StageTimer t(ctx, T_PARTITION);
         SVIM_CUDA(ctx->d_head.ensure(n + 64)); SVIM_CUDA(ctx->d_part_off.ensure((size_t)(n + 2) * 4)); SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
@@ -459,7 +460,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         SVIM_CUDA(cudaMemcpyAsync(h, d_ts, 16 * 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaStreamSynchronize(st));
         P = h[8];
-        memcpy(type_start, h, 7 * 4);
+        memcpy(type_start, h, 8 * 4);
         ctx->h_part_off.resize(P + 1);
         SVIM_CUDA(cudaMemcpyAsync(ctx->h_part_off.data(), ctx->d_part_off.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaStreamSynchronize(st));
@@ -480,14 +481,14 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         int32_t pick[100];
         for (uint32_t p = 0; p < P; ++p) {
             const uint32_t b = ctx->h_part_off[p], e = ctx->h_part_off[p + 1], sz = e - b;
-            int ty = 0; while (ty < 5 && b >= type_start[ty + 1]) ++ty;
+            int ty = 0; while (ty < 6 && b >= type_start[ty + 1]) ++ty;
             ptype[p] = (uint8_t)ty;
             if (ty != cur_type) { rng.seed_int(1524); cur_type = ty; }
-            cs.n_partitions[ty]++;
+            cs.n_partitions[ty > 5 ? 5 : ty]++;
             samp_off[p] = (uint32_t)samp_idx.size();
             uint32_t m = sz;
             if (sz > 100) {
-                rng.sample100(sz, pick); cs.large_partitions[ty]++; m = 100;
+                rng.sample100(sz, pick); cs.large_partitions[ty > 5 ? 5 : ty]++; m = 100;
                 for (int k = 0; k < 100; ++k) samp_idx.push_back(b + (uint32_t)pick[k]);
             } else for (uint32_t k = 0; k < sz; ++k) samp_idx.push_back(b + k);
             pair_off[p] = pair_total;
@@ -663,13 +664,13 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     }
     unsigned long long cells; memcpy(&cells, h + 12, 8);
     cs.myers_cells = (int64_t)cells;
-    for (auto& c : ctx->h_clusters) cs.n_clusters[c.type]++;
+    for (auto& c : ctx->h_clusters) cs.n_clusters[c.type > 5 ? 5 : c.type]++;
     cs.n_clusters_total = n_clusters; cs.n_members = n_members;
     // duplicate_signatures per type = sampled - kept
     {
         std::vector<uint32_t> nk(P + 1);
         SVIM_CUDA(cudaMemcpy(nk.data(), ctx->d_part_nkept.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost));
-        for (uint32_t p = ctx->shard_lo; p < ctx->shard_hi; ++p) cs.duplicate_signatures[ptype[p]] += (samp_off[p + 1] - samp_off[p]) - nk[p];
+        for (uint32_t p = ctx->shard_lo; p < ctx->shard_hi; ++p) cs.duplicate_signatures[ptype[p] > 5 ? 5 : ptype[p]] += (samp_off[p + 1] - samp_off[p]) - nk[p];
     }
     if (stats) *stats = cs;
     return 0;

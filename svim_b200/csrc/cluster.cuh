@@ -44,7 +44,7 @@ SVIM_HD double spd(int type, const SigView& a, const SigView& b, const ClusterPa
     double pd = fabs(c1 - c2) / p.pos_norm;
     if (mx == 0.0) { *err = 1; return 0.0; }
     double sd = fabs(span1 - span2) / mx;
-    if (type == SVIM_DUP_INT) {                                       // :78-86
+    if (type == SVIM_DUP_INT || type == SVIM_DUP_INT_CAND) {         // :78-86 and :110-119 (candidates)
         double pdd = fabs(a.dpos - b.dpos) / p.pos_norm;
         return pd + pdd + sd;
     }

@@ -95,3 +95,28 @@ def test_collect_then_cluster_object_surface(golden):
     assert all(hasattr(c, "direction1") and hasattr(c, "direction2") for c in bnd)
     assert all(len(c.get_bed_entries()) == 2 for c in res[3] + res[4] + res[5])
     assert all(c.get_bed_entry().count("\t") == 5 for c in res[0] + res[1] + res[2])
+
+
+def test_candidate_clustering_twin_on_gpu():
+    """partition_and_cluster_candidates (SVIM_clustering.py:306-372) through the same kernels as the signature path."""
+    import gzip, json, os
+    from conftest import GOLDEN
+    from svim_b200.SVIM_clustering import partition_and_cluster_candidates, CandidateDuplicationInterspersed, form_partitions
+    g = json.load(gzip.open(os.path.join(GOLDEN, "candidates.golden.json.gz"), "rt"))
+    cands = [CandidateDuplicationInterspersed(*r[:10], cutpaste=r[10]) for r in g["input"]]
+    got = partition_and_cluster_candidates(cands, _options(), "interspersed duplication candidates")
+    rows = [[c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end, c.members, c.score, c.std_span, c.std_pos,
+             c.cutpaste] for c in got]
+    assert rows == g["output"]
+    # form_partitions on candidates (used by COMBINE, SVIM_COMBINE.py:13): same partitions as the oracle's sort + gap split
+    from oracle import svim_oracle as orc
+    parts = form_partitions(cands, 1000)
+    ocands = [orc.Cand(*r) for r in g["input"]]
+    want = []
+    for c in sorted(range(len(ocands)), key=lambda i: ocands[i].key()):
+        if want and ocands[want[-1][-1]].gap_to(ocands[c]) <= 1000:
+            want[-1].append(c)
+        else:
+            want.append([c])
+    index_of = {id(c): i for i, c in enumerate(cands)}
+    assert [[index_of[id(c)] for c in p] for p in parts] == want

@@ -146,11 +146,45 @@ def fixtures():
     return out
 
 
+def candidate_fixture():
+    """DUP_INT candidates through the reference's partition_and_cluster_candidates (SVIM_clustering.py:306-372),
+    the COMBINE-stage twin of the clustering pipeline; also checks the oracle's restatement."""
+    import random
+    from svim.SVIM_clustering import partition_and_cluster_candidates as ref_pcc
+    from svim.SVCandidate import CandidateDuplicationInterspersed as RefCand
+    rng = random.Random(42)
+    rows = []
+    for locus in range(60):
+        contig = rng.choice(["chr1", "chr10", "chr2"]); base = rng.randint(10_000, 900_000); dbase = rng.randint(10_000, 900_000)
+        n = rng.choice([1, 1, 2, 3, 5, 8]) if locus else 140          # one partition above 100 -> sampling
+        for k in range(n):
+            s = base + rng.randint(-300, 300); ln = rng.randint(200, 900) + rng.choice([0, 0, 2000])
+            d = dbase + rng.randint(-300, 300) + rng.choice([0, 0, 5000])
+            rows.append([contig, s, s + ln, rng.choice(["chr1", "chr2"]), d, d + ln + rng.randint(-5, 5), ["m%d_%d" % (locus, k)],
+                         rng.randint(1, 40) + rng.random(), rng.choice([None, rng.random() * 30]), rng.choice([None, rng.random() * 30]),
+                         rng.random() < 0.2])
+    rng.shuffle(rows)
+    options = parse_arguments("2.0.0", ["alignment", "wd", "x.bam", "g.fa"])
+    ref = ref_pcc([RefCand(*r[:10], cutpaste=r[10]) for r in rows], options, "interspersed duplication candidates")
+    mine = orc.partition_and_cluster_candidates([orc.Cand(*r) for r in rows], orc.Params())
+    ref_rows = [[c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end, c.members, c.score, c.std_span,
+                 c.std_pos, c.cutpaste] for c in ref]
+    mine_rows = [[c.contig, c.start, c.end, c.dest_contig, c.dest_start, c.dest_end, c.members, c.score, c.std_span, c.std_pos, c.cutpaste]
+                 for c in mine]
+    if ref_rows != mine_rows:
+        raise SystemExit("ORACLE != REFERENCE on the candidate clustering twin")
+    with gzip.open(os.path.join(GOLDEN, "candidates.golden.json.gz"), "wt") as fh:
+        json.dump({"input": rows, "output": ref_rows}, fh)
+    print("candidates", len(rows), "->", len(ref_rows))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
+    if not args.only or args.only == "candidates":
+        candidate_fixture()
     for name, (batch, genome, overrides) in fixtures().items():
         if args.only and name != args.only:
             continue
