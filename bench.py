@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
+    ap.add_argument("--with-bam", action="store_true", help="also time the path starting from a BAM file on disk (native multi-threaded decode)")
     ap.add_argument("--scan-variant", type=int, default=None, help="0 = 128-bit LDG streaming scan, 1 = cp.async.bulk ring (default: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,6 +265,22 @@ def main():
         obj_s = time.perf_counter() - t0
     for a in pinned:
         ctx.unpin(a)
+    bam_leg = None
+    if args.with_bam and world == 1:
+        import tempfile
+        from svim_b200 import io as sio
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "bench.bam")
+            t0 = time.perf_counter(); sio.write_bam_native(path, batch, level=1, threads=os.cpu_count() or 8); t_w = time.perf_counter() - t0
+            size = os.path.getsize(path)
+            t0 = time.perf_counter()
+            decoded = sio.read_bam_native(path, threads=os.cpu_count() or 8)
+            t_dec = time.perf_counter() - t0
+            cst2 = ctx.collect_host(decoded)
+            ctx.use_collected(0); ctx.cluster()
+            t_all = time.perf_counter() - t0
+        bam_leg = {"value": decoded.n / t_all, "unit": UNIT, "bam_bytes": size, "decode_s": t_dec, "total_s": t_all, "bam_write_s": t_w,
+                   "note": "BAM on local disk/page cache -> native multi-threaded BGZF inflate + SoA fill -> pageable H2D -> COLLECT+CLUSTER"}
 
     if rank != 0:
         return
@@ -294,6 +311,8 @@ def main():
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
         "clocks": clocks,
     }
+    if bam_leg:
+        out["e2e_from_bam"] = bam_leg
     if clst.myers_cells and "myers_edit_distance" in out["stages_ms"]:
         out["myers"] = {"kernel": "k_myers_pairs", "bound": "int-alu", "gcups": clst.myers_cells / (out["stages_ms"]["myers_edit_distance"] * 1e-3) / 1e9}
     if world == 1 and not args.no_cpu_baseline:

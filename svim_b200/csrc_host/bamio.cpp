@@ -270,4 +270,119 @@ int bamio_fill(void* hh, bamio_out* out) {
 
 void bamio_close(void* hh) { delete (Handle*)hh; }
 
+// ---- writer: SoA -> BAM (BGZF blocks compressed in parallel).  Used to materialise the synthetic configs as files. ----
+struct bamio_in {
+    int64_t n; const int32_t* tid; const int32_t* pos; const uint16_t* flag; const uint8_t* mapq; const uint32_t* n_cigar; const uint64_t* cigar_off;
+    const int32_t* l_seq; const uint64_t* seq_off; const uint64_t* sa_off; const uint32_t* sa_len; const uint32_t* qname_id;
+    const uint32_t* cigar; const uint8_t* seq; const uint8_t* sa;
+    const char* qnames; const int64_t* qname_off;          // may be null: names are "read<id>"
+    int32_t n_contigs; const char* contig_names;           // NUL separated
+    const int64_t* contig_len; const char* sort_order;
+};
+
+static int reg2bin(int64_t beg, int64_t end) {
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+int bamio_write(const char* path, const bamio_in* in, int level, int n_threads) {
+    std::vector<uint8_t> raw;
+    auto put32 = [&](uint32_t v) { uint8_t b[4]; memcpy(b, &v, 4); raw.insert(raw.end(), b, b + 4); };
+    auto put16 = [&](uint16_t v) { uint8_t b[2]; memcpy(b, &v, 2); raw.insert(raw.end(), b, b + 2); };
+    std::string text = std::string("@HD\tVN:1.6\tSO:") + (in->sort_order ? in->sort_order : "unknown") + "\n";
+    std::vector<std::string> names;
+    const char* p = in->contig_names;
+    for (int i = 0; i < in->n_contigs; ++i) { names.emplace_back(p); p += names.back().size() + 1; }
+    for (int i = 0; i < in->n_contigs; ++i) text += "@SQ\tSN:" + names[i] + "\tLN:" + std::to_string(in->contig_len[i]) + "\n";
+    raw.insert(raw.end(), {'B', 'A', 'M', 1});
+    put32((uint32_t)text.size()); raw.insert(raw.end(), text.begin(), text.end());
+    put32((uint32_t)in->n_contigs);
+    for (int i = 0; i < in->n_contigs; ++i) {
+        put32((uint32_t)names[i].size() + 1); raw.insert(raw.end(), names[i].begin(), names[i].end()); raw.push_back(0);
+        put32((uint32_t)in->contig_len[i]);
+    }
+    // record sizes -> offsets, then parallel fill
+    const int64_t n = in->n;
+    std::vector<size_t> roff(n + 1);
+    std::vector<std::string> qn(in->qnames ? 0 : 0);
+    size_t o = raw.size();
+    auto name_len = [&](int64_t i) -> size_t {
+        if (in->qnames) return (size_t)(in->qname_off[in->qname_id[i] + 1] - in->qname_off[in->qname_id[i]]);
+        char buf[32]; return (size_t)snprintf(buf, sizeof(buf), "read%u", in->qname_id[i]);
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        roff[i] = o;
+        o += 4 + 32 + name_len(i) + 1 + 4 * (size_t)in->n_cigar[i] + (size_t)(in->l_seq[i] + 1) / 2 + (size_t)in->l_seq[i] + (in->sa_len[i] ? 4 + in->sa_len[i] : 0);
+    }
+    roff[n] = o;
+    raw.resize(o);
+    const int threads = std::max(1, n_threads);
+    parallel_for((size_t)n, threads, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i) {
+            uint8_t* r = raw.data() + roff[i];
+            const uint32_t bs = (uint32_t)(roff[i + 1] - roff[i] - 4);
+            memcpy(r, &bs, 4); r += 4;
+            const uint32_t nc = in->n_cigar[i]; const int32_t ls = in->l_seq[i];
+            const uint32_t* cg = in->cigar + in->cigar_off[i];
+            int64_t rlen = 0;
+            for (uint32_t k = 0; k < nc; ++k) { const uint32_t op = cg[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) rlen += cg[k] >> 4; }
+            char nb[32]; const char* nm; size_t nl;
+            if (in->qnames) { nm = in->qnames + in->qname_off[in->qname_id[i]]; nl = name_len(i); }
+            else { nl = (size_t)snprintf(nb, sizeof(nb), "read%u", in->qname_id[i]); nm = nb; }
+            const int32_t pos = in->pos[i];
+            const int64_t b0 = pos < 0 ? 0 : pos;
+            const uint16_t bin = (uint16_t)reg2bin(b0, b0 + (rlen ? rlen : 1));
+            int32_t f32[2] = {in->tid[i], pos}; memcpy(r, f32, 8);
+            r[8] = (uint8_t)(nl + 1); r[9] = in->mapq[i]; memcpy(r + 10, &bin, 2);
+            const uint16_t nc16 = (uint16_t)nc; memcpy(r + 12, &nc16, 2); memcpy(r + 14, &in->flag[i], 2);
+            memcpy(r + 16, &ls, 4);
+            const int32_t m1 = -1, z = 0; memcpy(r + 20, &m1, 4); memcpy(r + 24, &m1, 4); memcpy(r + 28, &z, 4);
+            uint8_t* q = r + 32;
+            memcpy(q, nm, nl); q[nl] = 0; q += nl + 1;
+            memcpy(q, cg, 4 * (size_t)nc); q += 4 * (size_t)nc;
+            memcpy(q, in->seq + in->seq_off[i], (size_t)(ls + 1) / 2); q += (size_t)(ls + 1) / 2;
+            memset(q, 0xff, (size_t)ls); q += ls;
+            if (in->sa_len[i]) { q[0] = 'S'; q[1] = 'A'; q[2] = 'Z'; memcpy(q + 3, in->sa + in->sa_off[i], in->sa_len[i]); q[3 + in->sa_len[i]] = 0; }
+        }
+    });
+    // BGZF: fixed 0xff00-byte payloads, compressed in parallel
+    const size_t CH = 0xff00;
+    const size_t nblk = (raw.size() + CH - 1) / CH;
+    std::vector<std::vector<uint8_t>> comp(nblk);
+    std::atomic<int> bad{0};
+    parallel_for(nblk, threads, [&](size_t lo, size_t hi) {
+        for (size_t b = lo; b < hi; ++b) {
+            const size_t off = b * CH, len = std::min(CH, raw.size() - off);
+            std::vector<uint8_t>& out = comp[b];
+            out.resize(18 + compressBound((uLong)len) + 8 + 64);
+            z_stream zs; memset(&zs, 0, sizeof(zs));
+            if (deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad = 1; return; }
+            zs.next_in = raw.data() + off; zs.avail_in = (uInt)len; zs.next_out = out.data() + 18; zs.avail_out = (uInt)(out.size() - 26);
+            const int rc = deflate(&zs, Z_FINISH);
+            const size_t clen = zs.total_out;
+            deflateEnd(&zs);
+            if (rc != Z_STREAM_END || clen + 26 > 65536) { bad = 1; return; }
+            const uint8_t hdr[16] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0};
+            memcpy(out.data(), hdr, 16);
+            const uint16_t bsz = (uint16_t)(clen + 25); memcpy(out.data() + 16, &bsz, 2);
+            const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), raw.data() + off, (uInt)len), isz = (uint32_t)len;
+            memcpy(out.data() + 18 + clen, &crc, 4); memcpy(out.data() + 22 + clen, &isz, 4);
+            out.resize(26 + clen);
+        }
+    });
+    if (bad) return -2;
+    FILE* fh = fopen(path, "wb");
+    if (!fh) return -1;
+    for (auto& c : comp) fwrite(c.data(), 1, c.size(), fh);
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    fwrite(eof, 1, 28, fh);
+    fclose(fh);
+    return 0;
+}
+
 }  // extern "C"

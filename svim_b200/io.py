@@ -199,6 +199,34 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
     return AlignmentBatch(names, lengths[:inf.n_contigs], arrays, cigar, seq, sa[:inf.sa_bytes], qnames, so.value.decode() or "unknown")
 
 
+def write_bam_native(path: str, batch: AlignmentBatch, level: int = 1, threads: int = 0):
+    """SoA -> BAM with parallel BGZF compression (csrc_host/bamio.cpp::bamio_write)."""
+    import ctypes as C
+    lib = _bamio_lib()
+
+    class In(C.Structure):
+        _fields_ = [("n", C.c_int64)] + [(k, C.c_void_p) for k in ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off", "sa_off",
+                                                                   "sa_len", "qname_id", "cigar", "seq", "sa", "qnames", "qname_off")] + \
+                   [("n_contigs", C.c_int32), ("contig_names", C.c_char_p), ("contig_len", C.c_void_p), ("sort_order", C.c_char_p)]
+    qblob = qoff = None
+    if batch.qnames is not None:
+        enc = [q.encode("ascii") for q in batch.qnames]
+        qoff = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum([len(e) for e in enc], out=qoff[1:])
+        qblob = np.frombuffer(b"".join(enc) + b"\x00", dtype=np.uint8)
+    names = b"\x00".join(n.encode("ascii") for n in batch.contig_names) + b"\x00"
+    clen = np.ascontiguousarray(batch.contig_lengths, dtype=np.int64)
+    sa = batch.sa if batch.sa.size else np.zeros(1, np.uint8)
+    arg = In(batch.n, *[getattr(batch, k).ctypes.data for k in ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off", "sa_off",
+                                                               "sa_len", "qname_id")], batch.cigar.ctypes.data, batch.seq.ctypes.data, sa.ctypes.data,
+             qblob.ctypes.data if qblob is not None else None, qoff.ctypes.data if qoff is not None else None,
+             len(batch.contig_names), names, clen.ctypes.data, batch.sort_order.encode("ascii"))
+    lib.bamio_write.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_int]
+    rc = lib.bamio_write(path.encode(), C.byref(arg), level, threads or min(32, os.cpu_count() or 1))
+    if rc != 0:
+        raise OSError("bamio_write(%s) failed with %d" % (path, rc))
+
+
 def read_bam(path: str) -> AlignmentBatch:
     """Native multi-threaded reader when g++/zlib are available, else the pure-Python one below."""
     try:

@@ -92,6 +92,9 @@ def test_native_bam_reader_equals_python_reader(tmp_path):
     batch = synth.generate(names, L, 300, 3, svs, al, len_mean=3000, len_sd=600, len_min=800, len_max=6000)
     p = str(tmp_path / "s.bam")
     sio.write_bam(p, batch)
+    p2 = str(tmp_path / "n.bam")
+    sio.write_bam_native(p2, batch, threads=3)
+    assert open(p, "rb").read() == open(p2, "rb").read()           # the native writer emits the same bytes as the Python one
     a, b = sio.read_bam_native(p, threads=4), sio.read_bam_python(p)
     assert a.n == b.n == batch.n and a.contig_names == b.contig_names == names and a.sort_order == b.sort_order == "coordinate"
     for name, _ in a.FIELDS:
