@@ -171,6 +171,9 @@ int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* soa);
 int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats);
 /* upload + collect */
 int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats);
+/* analyze_alignment_file_querysorted (SVIM_COLLECT.py:96-129): records grouped by read name (consecutive runs of equal
+ * qname_id, i.e. bam_iterator :8-41); a read's REAL supplementary records are its segments and are CIGAR-analysed too. */
+int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats);
 /* D2H: which = 0 main list (sv_signatures), 1 = translocation_signatures_all_bnds.
  * out_sigs[n_signatures] in the reference's emission order; out_ins[ins_bytes] ASCII. */
 int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, uint8_t* out_ins);

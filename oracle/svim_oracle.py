@@ -434,6 +434,46 @@ def collect(batch, p: Params):
     return sigs, twins
 
 
+def read_groups(batch):
+    """bam_iterator (SVIM_COLLECT.py:8-41): runs of consecutive records with the same read name ->
+    (primary indices, supplementary indices, secondary indices)."""
+    groups = []
+    qid = batch.qname_id
+    i = 0
+    while i < batch.n:
+        j = i
+        prim, sup, sec = [], [], []
+        while j < batch.n and qid[j] == qid[i]:
+            f = int(batch.flag[j])
+            (sec if f & 0x100 else sup if f & 0x800 else prim).append(j)
+            j += 1
+        groups.append((prim, sup, sec))
+        i = j
+    return groups
+
+
+def collect_querysorted(batch, p: Params):
+    """analyze_alignment_file_querysorted (SVIM_COLLECT.py:96-129): the REAL supplementary records of a read are its
+    segments (no SA parsing); CIGAR analysis runs on the primary and on every good supplementary."""
+    sigs: List[Sig] = []
+    twins: List[Sig] = []
+    for prim, sup, _sec in read_groups(batch):
+        if len(prim) != 1:
+            continue
+        i = prim[0]
+        if int(batch.flag[i]) & 0x4 or int(batch.mapq[i]) < p.min_mapq:
+            continue
+        good = [j for j in sup if not (int(batch.flag[j]) & 0x4) and int(batch.mapq[j]) >= p.min_mapq]
+        read_name = batch.qname(int(batch.qname_id[i]))
+        for j in [i] + good:
+            a, b = record_indel_signatures(batch, j, batch.qname(int(batch.qname_id[j])), p)
+            sigs += a; twins += b
+        primary, _ = segment_of_record(batch, i)
+        a, b = segment_signatures(batch, primary, [segment_of_record(batch, j)[0] for j in good], batch.sequence(i), read_name, p)
+        sigs += a; twins += b
+    return sigs, twins
+
+
 # ---------------------------------------------------------------------------
 # CLUSTER
 # ---------------------------------------------------------------------------

@@ -133,14 +133,31 @@ def _materialize(sigs, ins, batch, n):
     return out
 
 
-def collect_arrays(batch: AlignmentBatch, options=None, ctx=None):
+def bam_iterator(bam):
+    """bam_iterator (SVIM_COLLECT.py:8-41) over the flattened buffer: yields (primary, supplementary, secondary) lists of
+    RECORD INDICES for each run of consecutive records with the same read name (host helper, nothing is computed)."""
+    batch = as_batch(bam)
+    qid = batch.qname_id; flag = batch.flag
+    i = 0
+    while i < batch.n:
+        j = i
+        prim, sup, sec = [], [], []
+        while j < batch.n and qid[j] == qid[i]:
+            f = int(flag[j])
+            (sec if f & 0x100 else sup if f & 0x800 else prim).append(j)
+            j += 1
+        yield (prim, sup, sec)
+        i = j
+
+
+def collect_arrays(batch: AlignmentBatch, options=None, ctx=None, querysorted=False):
     """Run the COLLECT kernels from host buffers; returns (ctx, stats, (sigs, ins), (twin_sigs, twin_ins))."""
     ctx = ctx or runtime.context()
     ctx.set_params(_lib.Params.from_options(options))
     if getattr(ctx, "contigs_key", None) != tuple(batch.contig_names):
         ctx.set_contigs(batch.contig_names)
         ctx.contigs_key = tuple(batch.contig_names)
-    stats = ctx.collect_host(batch)
+    stats = ctx.collect_host_querysorted(batch) if querysorted else ctx.collect_host(batch)
     if stats.n_data_errors:
         raise _lib.SvimGpuError(-5, "%d reads carry SA tags the reference would raise on "
                                     "(unknown contig / non-integer field / empty CIGAR)" % stats.n_data_errors)
@@ -154,9 +171,18 @@ def collect_arrays(batch: AlignmentBatch, options=None, ctx=None):
     return ctx, stats, main, twins
 
 
+def analyze_alignment_file_querysorted(bam, options):
+    """analyze_alignment_file_querysorted (SVIM_COLLECT.py:96-129) over the CUDA path."""
+    return _analyze(bam, options, True)
+
+
 def analyze_alignment_file_coordsorted(bam, options):
+    return _analyze(bam, options, False)
+
+
+def _analyze(bam, options, querysorted):
     batch = as_batch(bam)
-    ctx, stats, (sigs, ins), (tsigs, tins) = collect_arrays(batch, options)
+    ctx, stats, (sigs, ins), (tsigs, tins) = collect_arrays(batch, options, querysorted=querysorted)
     token = object()
     ctx.collect_token = token
     ctx.collect_batch = batch

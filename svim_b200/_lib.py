@@ -92,6 +92,7 @@ EXPORTS = {
     "svimgpu_upload_alignments": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa)]),
     "svimgpu_collect": (C.c_int, [C.c_void_p, C.POINTER(CollectStats)]),
     "svimgpu_collect_host": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
+    "svimgpu_collect_host_querysorted": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
     "svimgpu_fetch_signatures": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "svimgpu_use_collected": (C.c_int, [C.c_void_p, C.c_int]),
     "svimgpu_set_signatures": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
@@ -237,6 +238,12 @@ class Context:
         soa = self.soa_of(batch)
         st = CollectStats()
         self._check(self.lib.svimgpu_collect_host(self.h, C.byref(soa), C.byref(st)))
+        return st
+
+    def collect_host_querysorted(self, batch) -> CollectStats:
+        soa = self.soa_of(batch)
+        st = CollectStats()
+        self._check(self.lib.svimgpu_collect_host_querysorted(self.h, C.byref(soa), C.byref(st)))
         return st
 
     def fetch_signatures(self, which, stats: CollectStats):

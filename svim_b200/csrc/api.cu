@@ -60,6 +60,7 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
     for (int i = 0; i < 12; ++i) ctx->d_myers_scratch[i].release();
     ctx->d_stage.release(); ctx->d_stage_off.release();
+    ctx->d_qs_info.release(); ctx->d_qs_grp.release(); ctx->d_qs_segsum.release(); ctx->d_qs_mem_off.release(); ctx->d_qs_mem_idx.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < SVIM_AUX_STREAMS; ++i) cudaStreamDestroy(ctx->aux_stream[i]);
@@ -169,6 +170,59 @@ int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect
     rc = svimgpu_collect(ctx, stats);
     ctx->have_soa = false;      // the host SEQ pointers must not outlive this call
     ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
+    return rc;
+}
+
+int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats) {
+    if (!ctx || !soa) return SVIMGPU_ERR_ARG;
+    int rc = upload_alignments(ctx, soa, false);
+    if (rc) return rc;
+    // bam_iterator (SVIM_COLLECT.py:8-41): runs of consecutive records with the same read name; a read is analysed when it has
+    // exactly one non-secondary non-supplementary record, mapped, MAPQ >= min_mapq (:108); its good supplementary records
+    // (mapped, MAPQ >= min_mapq, :112) are both CIGAR-analysed and used as segments.
+    const int64_t n = soa->n_aln;
+    std::vector<uint32_t> info((size_t)n, 0), grp((size_t)n, 0), mem_off(1, 0), mem_idx;
+    uint32_t g = 0;
+    const int32_t min_mapq = ctx->params.min_mapq;
+    for (int64_t i = 0; i < n;) {
+        int64_t j = i, prim = -1; int n_prim = 0;
+        while (j < n && soa->qname_id[j] == soa->qname_id[i]) {
+            const uint16_t f = soa->flag[j];
+            if (!(f & 0x100) && !(f & 0x800)) { ++n_prim; prim = j; }
+            ++j;
+        }
+        const size_t first_mem = mem_idx.size();
+        if (n_prim == 1 && !(soa->flag[prim] & 0x4) && (int32_t)soa->mapq[prim] >= min_mapq) {
+            uint32_t slot = 1;
+            for (int64_t k = i; k < j; ++k) {
+                const uint16_t f = soa->flag[k];
+                if ((f & 0x800) && !(f & 0x100) && !(f & 0x4) && (int32_t)soa->mapq[k] >= min_mapq) {
+                    if (slot >= 0xFFF) { ctx->set_error(SVIMGPU_ERR_LIMIT, "more than 4094 supplementary records for one read"); return SVIMGPU_ERR_LIMIT; }
+                    info[k] = 2u | (slot << 3); grp[k] = g; mem_idx.push_back((uint32_t)k); ++slot;
+                }
+            }
+            const bool chain = mem_idx.size() > first_mem;
+            info[prim] = 1u; grp[prim] = g;
+            if (chain) { info[prim] |= 4u; for (size_t m = first_mem; m < mem_idx.size(); ++m) info[mem_idx[m]] |= 4u; }
+        }
+        mem_off.push_back((uint32_t)mem_idx.size());
+        ++g; i = j;
+    }
+    cudaStream_t st = ctx->stream;
+    SVIM_CUDA(ctx->d_qs_info.ensure((size_t)n * 4 + 4)); SVIM_CUDA(ctx->d_qs_grp.ensure((size_t)n * 4 + 4));
+    SVIM_CUDA(ctx->d_qs_segsum.ensure((size_t)(n + 1) * sizeof(SegSum)));
+    SVIM_CUDA(ctx->d_qs_mem_off.ensure(mem_off.size() * 4)); SVIM_CUDA(ctx->d_qs_mem_idx.ensure(mem_idx.size() * 4 + 4));
+    if (n) {
+        SVIM_CUDA(cudaMemcpyAsync(ctx->d_qs_info.p, info.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        SVIM_CUDA(cudaMemcpyAsync(ctx->d_qs_grp.p, grp.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_qs_mem_off.p, mem_off.data(), mem_off.size() * 4, cudaMemcpyHostToDevice, st));
+    if (!mem_idx.empty()) SVIM_CUDA(cudaMemcpyAsync(ctx->d_qs_mem_idx.p, mem_idx.data(), mem_idx.size() * 4, cudaMemcpyHostToDevice, st));
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    ctx->qs_mode = true;
+    rc = svimgpu_collect(ctx, stats);
+    ctx->qs_mode = false;
+    ctx->have_soa = false; ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
     return rc;
 }
 

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams 
                         cigsum_finish(cs, l_seq, r.ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
                         uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
                         if (slot < work_cap) {
-                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = 0x80000000u | st.n_ev; wk.ord_twin = 0x80000000u | st.n_tw; wk.pad = 0;
                             wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
                             work[slot] = wk;
                         } else atomicExch(cnt + CNT_OVERFLOW, 1u);
@@ -290,9 +290,13 @@ __device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint3
     acc_ref_out = a_ref; acc_read_out = a_read; n_out = a_n; h_out = a_h;
 }
 
+// query-sorted mode (SVIM_COLLECT.py:96-129): the host grouped the records by read; qs.info[i] = role | slot << 3 with
+// role 0 = skip, 1 = the read's only primary, 2 = good supplementary, bit 2 = the read has segments to chain.
+struct QsView { const uint32_t* info; const uint32_t* grp; SegSum* segsum; };
+
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
-                                                             uint32_t* cnt) {
+                                                             uint32_t* cnt, QsView qs) {
     __shared__ ScanShared sh_s;
     __shared__ ScanWarp ws_s[8];
     const int lane = threadIdx.x & 31;
@@ -311,25 +315,32 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
         const uint32_t last = min(first + SCAN_BATCH, n_aln);
         for (uint32_t i = first; i < last; ++i) {
             const uint32_t flag = a.flag[i];
-            if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;
-            const bool primary = !(flag & 0x800u);
+            bool primary; uint32_t slot = 0; bool qs_chain = false;
+            if (qs.info) {
+                const uint32_t info = qs.info[i];
+                if ((info & 3u) == 0) continue;
+                primary = (info & 3u) == 1; qs_chain = info & 4u; slot = info >> 3;
+            } else {
+                if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;
+                primary = !(flag & 0x800u);
+            }
             primaries += primary;
             const uint32_t n = a.n_cigar[i];
             const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]);
             if (lane == 0) {
                 ScanRec r; r.i = i; r.qid = a.qname_id[i]; r.tid = a.tid[i]; r.ref_start = a.pos[i]; r.l_seq = a.l_seq[i];
-                EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = 0; st.n_tw = 0; st.nsum = 0; st.hsum = 0;
+                EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = slot << 20; st.n_tw = slot << 20; st.nsum = 0; st.hsum = 0;
                 ws->r = r; ws->st = st;
             }
             __syncwarp();
             uint32_t acc_ref = 0, acc_read = 0, acc_n = 0, acc_h = 0;
-            const bool need_summary = primary && a.sa_len[i] > 0;
+            const bool need_summary = qs.info ? qs_chain : (primary && a.sa_len[i] > 0);
             if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
             else scan_cigar_s<false>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
             if (need_summary) {
                 const EvState st = ws->st;     // st.nsum / st.hsum: warp totals of the rare-path groups (scan_events_s)
                 const uint32_t hard = warp_sum(acc_h) + st.hsum;
-                if (hard == 0) {
+                if (hard == 0 || qs.info) {     // the hard-clip rule belongs to the SA reconstruction only (SVIM_COLLECT.py:47)
                     const int64_t ref_q = st.base_ref + warp_sum(acc_ref);
                     const int64_t rd = st.base_read + warp_sum(acc_read);
                     const int64_t nsum = (int64_t)warp_sum(acc_n) + st.nsum;
@@ -347,12 +358,16 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
                         }
                         Seg sg; int64_t rl;
                         cigsum_finish(cs, l_seq, a.pos[i], (flag & 0x10u) ? 1 : 0, sg, rl);
-                        uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
-                        if (slot < work_cap) {
-                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
-                            wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
-                            work[slot] = wk;
-                        } else atomicExch(cnt + CNT_OVERFLOW, 1u);
+                        if (qs.info) { SegSum ss; ss.ref_end = sg.ref_end; ss.q_start = sg.q_start; ss.q_end = sg.q_end; ss.read_len = rl; qs.segsum[i] = ss; }
+                        if (!qs.info || primary) {
+                            uint32_t wslot = atomicAdd(cnt + CNT_WORK, 1u);
+                            if (wslot < work_cap) {
+                                ChainWork wk; wk.aln_idx = i; wk.pad = 0;
+                                wk.ord_sig = qs.info ? 0xFFF00000u : (0x80000000u | st.n_ev); wk.ord_twin = qs.info ? 0xFFF00000u : (0x80000000u | st.n_tw);
+                                wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
+                                work[wslot] = wk;
+                            } else atomicExch(cnt + CNT_OVERFLOW, 1u);
+                        }
                     }
                 }
             }
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(32 * SCAN_BULK_WARPS, 3) k_cigar_scan_bulk(Dev
                         cigsum_finish(cs, l_seq, r.ref_start, (flag & 0x10u) ? 1 : 0, sg, rl);
                         uint32_t slot = atomicAdd(cnt + CNT_WORK, 1u);
                         if (slot < work_cap) {
-                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = st.n_ev; wk.ord_twin = st.n_tw; wk.pad = 0;
+                            ChainWork wk; wk.aln_idx = i; wk.ord_sig = 0x80000000u | st.n_ev; wk.ord_twin = 0x80000000u | st.n_tw; wk.pad = 0;
                             wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
                             work[slot] = wk;
                         } else atomicExch(cnt + CNT_OVERFLOW, 1u);
@@ -545,18 +560,53 @@ __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, 
     n = parse_sa_segments(a.sa + a.sa_off[i], (int)a.sa_len[i], ct, p, a.l_seq[i], chain, n, err);
     sort_chain(chain, n);
     PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
-    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, 0x80000000u | wk.ord_sig, 0x80000000u | wk.ord_twin, err);
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err);
     if (err & CH_BAD_FIELDS) atomicAdd(cnt + CNT_BAD_FIELDS, 1u);
     if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
     if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
     if (err & CH_TOO_MANY) atomicAdd(cnt + CNT_TOO_MANY, 1u);
 }
 
-// keys for restoring the reference's emission order: (record index, ordinal)
-__global__ void k_sig_keys(const svim_sig* recs, uint32_t n, uint64_t* keys, uint32_t* vals) {
+// query-sorted mode: segments are the read's REAL supplementary records (analyze_alignment_file_querysorted,
+// SVIM_COLLECT.py:113-123), listed per read group by the host in file order
+__global__ void __launch_bounds__(128) k_segment_chain_qs(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
+                                                           const uint32_t* grp, const uint32_t* mem_off, const uint32_t* mem_idx, const SegSum* segsum,
+                                                           SigQueue qm, SigQueue qt, uint32_t* cnt) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_work) return;
+    const ChainWork wk = work[w];
+    const uint32_t i = wk.aln_idx;
+    DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
+    Seg chain[SVIM_MAX_SEGMENTS];
+    int n = 0;
+    uint32_t err = 0;
+    const int32_t rev = (a.flag[i] & 0x10u) ? 1 : 0;
+    if (rev && wk.read_len < 0) err |= CH_NO_READLEN;
+    else { Seg s; s.tid = a.tid[i]; s.ref_start = a.pos[i]; s.ref_end = wk.ref_end; s.q_start = wk.q_start; s.q_end = wk.q_end; s.rev = rev; chain[n++] = s; }
+    const uint32_t g = grp[i];
+    for (uint32_t m = mem_off[g]; m < mem_off[g + 1]; ++m) {
+        const uint32_t j = mem_idx[m];
+        const SegSum ss = segsum[j];
+        const int32_t jr = (a.flag[j] & 0x10u) ? 1 : 0;
+        if (jr && ss.read_len < 0) { err |= CH_NO_READLEN; continue; }
+        if (n >= SVIM_MAX_SEGMENTS) { err |= CH_TOO_MANY; break; }
+        Seg s; s.tid = a.tid[j]; s.ref_start = a.pos[j]; s.ref_end = ss.ref_end; s.q_start = ss.q_start; s.q_end = ss.q_end; s.rev = jr;
+        chain[n++] = s;
+    }
+    sort_chain(chain, n);
+    PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err);
+    if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
+    if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
+    if (err & CH_TOO_MANY) atomicAdd(cnt + CNT_TOO_MANY, 1u);
+}
+
+// keys for restoring the reference's emission order: (record index | read group, ordinal)
+__global__ void k_sig_keys(const svim_sig* recs, uint32_t n, const uint32_t* grp, uint64_t* keys, uint32_t* vals) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    keys[k] = ((uint64_t)recs[k].aln_idx << 32) | recs[k].ordinal;
+    const uint32_t hi = grp ? grp[recs[k].aln_idx] : recs[k].aln_idx;
+    keys[k] = ((uint64_t)hi << 32) | recs[k].ordinal;
     vals[k] = k;
 }
 
@@ -669,7 +719,7 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
     SVIM_CUDA(ctx->d_scan.ensure((size_t)(n + 1) * 8 * 2));
     cudaStream_t st = ctx->stream;
     const svim_sig* q = ctx->d_queue[which].as<svim_sig>();
-    { ctx->launches++; k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>()); }
+    { ctx->launches++; k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->qs_mode ? ctx->d_qs_grp.as<uint32_t>() : nullptr, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>()); }
     cub::DoubleBuffer<uint64_t> dk(ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>());
     cub::DoubleBuffer<uint32_t> dv(ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>());
     size_t tmp = 0;
@@ -730,33 +780,36 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         {
             StageTimer t(ctx, T_SCAN);
             if (n > 0) {
-                if (ctx->scan_variant == 1) {   // cp.async.bulk ring (TMA engine)
+                QsView qsv{nullptr, nullptr, nullptr};
+                if (ctx->qs_mode) qsv = QsView{ctx->d_qs_info.as<uint32_t>(), ctx->d_qs_grp.as<uint32_t>(), ctx->d_qs_segsum.as<SegSum>()};
+                const int variant = ctx->qs_mode ? 0 : ctx->scan_variant;   // the query-sorted mode lives in the default kernel only
+                if (variant == 1) {   // cp.async.bulk ring (TMA engine)
                     const size_t smem = (size_t)SCAN_BULK_WARPS * SCAN_STAGES * SCAN_BLOCK_U4 * 16 + (size_t)SCAN_BULK_WARPS * SCAN_STAGES * 8;
                     SVIM_CUDA(cudaFuncSetAttribute(k_cigar_scan_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     { ctx->launches++; k_cigar_scan_bulk<<<dev_sms * 3, 32 * SCAN_BULK_WARPS, smem, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 2) {   // experiment: 8 loads in flight per lane, 2 CTAs/SM
+                } else if (variant == 2) {   // experiment: 8 loads in flight per lane, 2 CTAs/SM
                     { ctx->launches++; k_cigar_scan<8, 2><<<dev_sms * 6, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 3) {   // experiment: 2 loads per lane, 4 CTAs/SM
+                } else if (variant == 3) {   // experiment: 2 loads per lane, 4 CTAs/SM
                     { ctx->launches++; k_cigar_scan<2, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 4) {   // experiment: 4 loads per lane, 3 CTAs/SM (80 registers) — the round-1 v2..v5 kernel
+                } else if (variant == 4) {   // experiment: 4 loads per lane, 3 CTAs/SM (80 registers) — the round-1 v2..v5 kernel
                     { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
+                } else if (variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan_s<5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
+                                                                   ctx->d_counters.as<uint32_t>(), qsv); }
+                } else if (variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
                     { ctx->launches++; k_cigar_scan_s<4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                  ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 0 || ctx->scan_variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
+                                                                  ctx->d_counters.as<uint32_t>(), qsv); }
+                } else if (variant == 0 || variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
                     { ctx->launches++; k_cigar_scan_s<6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 5) {   // experiment: 5 CTAs/SM
+                                                                   ctx->d_counters.as<uint32_t>(), qsv); }
+                } else if (variant == 5) {   // experiment: 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                     ctx->d_counters.as<uint32_t>()); }
-                } else if (ctx->scan_variant == 6) {   // experiment: 6 CTAs/SM
+                } else if (variant == 6) {   // experiment: 6 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                     ctx->d_counters.as<uint32_t>()); }
                 } else {                               // variant 10+: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers): 0.74 of the measured HBM peak
@@ -771,7 +824,11 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         uint32_t n_work = h_cnt[CNT_WORK];
         {
             StageTimer t(ctx, T_CHAIN);
-            if (n_work > 0)
+            if (n_work > 0 && ctx->qs_mode)
+                { ctx->launches++; k_segment_chain_qs<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work,
+                                                                        ctx->d_qs_grp.as<uint32_t>(), ctx->d_qs_mem_off.as<uint32_t>(), ctx->d_qs_mem_idx.as<uint32_t>(),
+                                                                        ctx->d_qs_segsum.as<SegSum>(), qm, qt, ctx->d_counters.as<uint32_t>()); }
+            else if (n_work > 0)
                 { ctx->launches++; k_segment_chain<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work, qm, qt,
                                                                      ctx->d_counters.as<uint32_t>()); }
         }

@@ -48,6 +48,9 @@ struct SigQueue {
     uint32_t cap;
 };
 
+// per-record segment summary (query-sorted mode)
+struct SegSum { int64_t ref_end, q_start, q_end, read_len; };
+
 // written by the CIGAR scan for every primary that has an SA tag and no hard clip
 struct ChainWork {
     uint32_t aln_idx, ord_sig, ord_twin, pad;
@@ -103,6 +106,8 @@ struct svimgpu_ctx {
     DevBuf d_counters, d_queue[2], d_work, d_sort_tmp, d_keys[2], d_vals[2], d_scan;
     SigSet sets[2];
     bool collected = false;
+    bool qs_mode = false;      // query-sorted COLLECT (SVIM_COLLECT.py:96-129)
+    DevBuf d_qs_info, d_qs_grp, d_qs_segsum, d_qs_mem_off, d_qs_mem_idx;
     int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
     svim_collect_stats cstats;
 

@@ -157,6 +157,12 @@ class AlignmentBatch:
         return int(self.n * self.ROW_BYTES + 4 * int(self.n_cigar.sum(dtype=np.int64))
                    + int(self.sa_len.sum(dtype=np.int64)))
 
+    def take(self, order, sort_order: str = "unknown") -> "AlignmentBatch":
+        """Records re-ordered by `order` (index array); blobs are shared, only the row arrays are permuted."""
+        order = np.asarray(order, dtype=np.int64)
+        arrays = {name: getattr(self, name)[order] for name, _ in self.FIELDS}
+        return AlignmentBatch(self.contig_names, self.contig_lengths, arrays, self.cigar, self.seq, self.sa, self.qnames, sort_order)
+
     def slice(self, lo: int, hi: int) -> "AlignmentBatch":
         """Records [lo, hi) sharing the blobs (offsets stay absolute)."""
         arrays = {name: getattr(self, name)[lo:hi] for name, _ in self.FIELDS}

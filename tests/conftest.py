@@ -12,6 +12,14 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = ("mini_indel", "mini_mixed", "mini_mixed_allbnds", "mini_ins", "mini_hotspot", "chimeric_kat")
+GOLDEN_QUERYSORTED = ("mini_mixed_querysorted",)
+
+
+def querysort_order(batch):
+    """Deterministic read-name order for the query-sorted fixtures: records of a read become adjacent, in a
+    pseudo-random order inside the read (the primary is not always first)."""
+    idx = np.arange(batch.n, dtype=np.int64)
+    return np.argsort(batch.qname_id.astype(np.int64) * 8 + (idx * 2654435761) % 7, kind="stable")
 
 
 def pytest_configure(config):
@@ -29,6 +37,8 @@ def load_golden(name):
     arrays = {f: z[f] for f, _ in AlignmentBatch.FIELDS}
     qnames = [str(x) for x in z["qnames"]] if "qnames" in z.files else None
     batch = AlignmentBatch(names, z["contig_lengths"], arrays, z["cigar"], z["seq"], z["sa"], qnames, "coordinate")
+    if exp.get("derive") == "querysorted":
+        batch = batch.take(querysort_order(batch), "queryname")
     blob = z["genome_blob"]
     offs = np.concatenate([[0], np.cumsum(z["contig_lengths"])]).astype(np.int64)
     genome = Genome(names, [blob[offs[i]:offs[i + 1]] for i in range(len(names))])

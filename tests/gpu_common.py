@@ -73,12 +73,12 @@ def assert_clusters_equal(got, want, float_tol=1e-6):
                     assert abs(a[i] - b[i]) <= float_tol * max(1.0, abs(b[i])), (t, k, i, a[i], b[i])
 
 
-def run_gpu(ctx, batch, genome, overrides, which=0):
+def run_gpu(ctx, batch, genome, overrides, which=0, querysorted=False):
     """COLLECT + CLUSTER through the C ABI -> (sig rows, twin rows, clusters dict for `which`)."""
     from svim_b200 import runtime
     ctx.set_params(_lib.Params.from_options(None, **overrides))
     ctx.set_contigs(batch.contig_names)
-    st = ctx.collect_host(batch)
+    st = ctx.collect_host_querysorted(batch) if querysorted else ctx.collect_host(batch)
     assert st.n_data_errors == 0
     sigs, ins = ctx.fetch_signatures(0, st)
     rows = sig_rows(sigs, ins, batch)

@@ -117,3 +117,15 @@ def test_oracle_parity_on_fresh_synthetic_inputs(gpu_ctx):
         rows, trows, clusters, st, cst = run_gpu(gpu_ctx, batch, genome, {})
         assert rows == want["signatures"], name
         assert_clusters_equal(clusters, want["clusters"])
+
+
+def test_querysorted_collect_matches_reference_golden(gpu_ctx, golden):
+    # analyze_alignment_file_querysorted (SVIM_COLLECT.py:96-129): real supplementary records as segments
+    batch, genome, exp = golden("mini_mixed_querysorted")
+    rows, trows, clusters, st, cst = run_gpu(gpu_ctx, batch, genome, exp["params"], querysorted=True)
+    assert rows == exp["signatures"]
+    assert trows == exp["all_bnds_signatures"]
+    assert_clusters_equal(clusters, exp["clusters"])
+    from svim_b200.SVIM_COLLECT import bam_iterator
+    from oracle import svim_oracle as orc
+    assert list(bam_iterator(batch)) == orc.read_groups(batch)

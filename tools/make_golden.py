@@ -22,7 +22,7 @@ refenv.activate()
 
 import numpy as np  # noqa: E402
 import pysam  # the shim  # noqa: E402
-from svim.SVIM_COLLECT import analyze_alignment_file_coordsorted  # noqa: E402
+from svim.SVIM_COLLECT import analyze_alignment_file_coordsorted, analyze_alignment_file_querysorted  # noqa: E402
 from svim.SVIM_CLUSTER import cluster_sv_signatures  # noqa: E402
 from svim.SVIM_input_parsing import parse_arguments  # noqa: E402
 
@@ -68,7 +68,7 @@ def oracle_cluster_tuple(c, index_of):
             c.std_span, c.std_pos, c.dir1, c.dir2, [index_of[id(m)] for m in c.members]]
 
 
-def run_reference(batch, genome, overrides):
+def run_reference(batch, genome, overrides, querysorted=False):
     with tempfile.TemporaryDirectory() as td:
         gpath = os.path.join(td, "genome.fa")
         pysam.register_genome(gpath, genome)
@@ -80,7 +80,7 @@ def run_reference(batch, genome, overrides):
                 argv += ["--" + k, str(v)]
         options = parse_arguments("2.0.0", argv)
         bam = pysam.AlignmentFile.from_batch(batch)
-        sigs, twins = analyze_alignment_file_coordsorted(bam, options)
+        sigs, twins = (analyze_alignment_file_querysorted if querysorted else analyze_alignment_file_coordsorted)(bam, options)
         out = {"signatures": [ref_sig_tuple(s) for s in sigs], "all_bnds_signatures": [ref_sig_tuple(s) for s in twins]}
         for key, lst in (("clusters", sigs), ("all_bnds_clusters", twins)):
             index_of = {id(s): i for i, s in enumerate(lst)}
@@ -90,9 +90,9 @@ def run_reference(batch, genome, overrides):
         return out
 
 
-def run_oracle(batch, genome, overrides):
+def run_oracle(batch, genome, overrides, querysorted=False):
     p = orc.Params(**overrides)
-    sigs, twins = orc.collect(batch, p)
+    sigs, twins = (orc.collect_querysorted if querysorted else orc.collect)(batch, p)
     out = {"signatures": [list(s.as_tuple()) for s in sigs], "all_bnds_signatures": [list(s.as_tuple()) for s in twins]}
     for key, lst in (("clusters", sigs), ("all_bnds_clusters", twins)):
         index_of = {id(s): i for i, s in enumerate(lst)}
@@ -127,6 +127,10 @@ def fixtures():
     g2 = synth.random_genome(names, L, 12)
     out["mini_mixed"] = (b2, g2, {})
     out["mini_mixed_allbnds"] = (b2, g2, {"all_bnds": True, "min_mapq": 1, "max_sv_size": 3000})
+    # 2b. the same records sorted by read name (query-sorted mode, SVIM_COLLECT.py:96-129): primary not always first
+    sys.path.insert(0, os.path.join(refenv.ROOT, "tests"))
+    from conftest import querysort_order
+    out["mini_mixed_querysorted"] = (b2.take(querysort_order(b2), "queryname"), g2, {"all_bnds": True})
     # 3. insertion heavy (haplotype edit distance)
     names, L = ["chr1"], [120_000]
     svs, al = synth.plant_svs(L, 13, spacing=4000, mix={"INS": 1.0}, ins_size_uniform=(60, 700))
@@ -188,8 +192,9 @@ def main():
     for name, (batch, genome, overrides) in fixtures().items():
         if args.only and name != args.only:
             continue
-        ref = run_reference(batch, genome, overrides)
-        mine = run_oracle(batch, genome, overrides)
+        qsort = name.endswith("_querysorted")
+        ref = run_reference(batch, genome, overrides, qsort)
+        mine = run_oracle(batch, genome, overrides, qsort)
         for key in ref:
             if ref[key] != mine[key]:
                 a, b = ref[key], mine[key]
@@ -209,7 +214,10 @@ def main():
         ref["params"] = overrides
         ref["n_records"] = batch.n
         inp = name.replace("_allbnds", "")
-        if inp == name:
+        if name.endswith("_querysorted"):       # same records as mini_mixed, permuted by tests/conftest.py::querysort_order
+            inp = "mini_mixed"
+            ref["derive"] = "querysorted"
+        elif inp == name:
             save_input(os.path.join(GOLDEN, inp + ".input.npz"), batch, genome)
         ref["input"] = inp + ".input.npz"
         with gzip.open(os.path.join(GOLDEN, name + ".golden.json.gz"), "wt") as fh:
