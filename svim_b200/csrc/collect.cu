@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
                         if (l_seq == 0) {
                             for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
                         } else {
-                            cs.ref_len = ref_q + nsum; cs.qlen_h = rd; cs.hard = 0; cs.n_ops = (int32_t)n;
+                            cs.ref_len = ref_q + nsum; cs.qlen_h = rd + hard; cs.hard = hard; cs.n_ops = (int32_t)n;   // infer_read_length counts H (query-sorted mode keeps hard-clipped records)
                             uint32_t k = 0;
                             for (; k < n; ++k) { uint32_t op = c32[k] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.lead_s += c32[k] >> 4; }
                             for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
