@@ -294,9 +294,11 @@ __device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint3
 // role 0 = skip, 1 = the read's only primary, 2 = good supplementary, bit 2 = the read has segments to chain.
 struct QsView { const uint32_t* info; const uint32_t* grp; SegSum* segsum; };
 
-template <int MINB>
+template <int MINB, bool QS>
 __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
-                                                             uint32_t* cnt, QsView qs) {
+                                                             uint32_t* cnt, QsView qs_in) {
+    QsView qs = qs_in;
+    if (!QS) qs.info = nullptr;          // compile-time: the coordinate-sorted instantiation carries none of the read-group logic
     __shared__ ScanShared sh_s;
     __shared__ ScanWarp ws_s[8];
     const int lane = threadIdx.x & 31;
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
         for (uint32_t i = first; i < last; ++i) {
             const uint32_t flag = a.flag[i];
             bool primary; uint32_t slot = 0; bool qs_chain = false;
-            if (qs.info) {
+            if (QS) {
                 const uint32_t info = qs.info[i];
                 if ((info & 3u) == 0) continue;
                 primary = (info & 3u) == 1; qs_chain = info & 4u; slot = info >> 3;
@@ -334,13 +336,13 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
             }
             __syncwarp();
             uint32_t acc_ref = 0, acc_read = 0, acc_n = 0, acc_h = 0;
-            const bool need_summary = qs.info ? qs_chain : (primary && a.sa_len[i] > 0);
+            const bool need_summary = QS ? qs_chain : (primary && a.sa_len[i] > 0);
             if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
             else scan_cigar_s<false>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
             if (need_summary) {
                 const EvState st = ws->st;     // st.nsum / st.hsum: warp totals of the rare-path groups (scan_events_s)
                 const uint32_t hard = warp_sum(acc_h) + st.hsum;
-                if (hard == 0 || qs.info) {     // the hard-clip rule belongs to the SA reconstruction only (SVIM_COLLECT.py:47)
+                if (hard == 0 || QS) {     // the hard-clip rule belongs to the SA reconstruction only (SVIM_COLLECT.py:47)
                     const int64_t ref_q = st.base_ref + warp_sum(acc_ref);
                     const int64_t rd = st.base_read + warp_sum(acc_read);
                     const int64_t nsum = (int64_t)warp_sum(acc_n) + st.nsum;
@@ -358,12 +360,12 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
                         }
                         Seg sg; int64_t rl;
                         cigsum_finish(cs, l_seq, a.pos[i], (flag & 0x10u) ? 1 : 0, sg, rl);
-                        if (qs.info) { SegSum ss; ss.ref_end = sg.ref_end; ss.q_start = sg.q_start; ss.q_end = sg.q_end; ss.read_len = rl; qs.segsum[i] = ss; }
-                        if (!qs.info || primary) {
+                        if (QS) { SegSum ss; ss.ref_end = sg.ref_end; ss.q_start = sg.q_start; ss.q_end = sg.q_end; ss.read_len = rl; qs.segsum[i] = ss; }
+                        if (!QS || primary) {
                             uint32_t wslot = atomicAdd(cnt + CNT_WORK, 1u);
                             if (wslot < work_cap) {
                                 ChainWork wk; wk.aln_idx = i; wk.pad = 0;
-                                wk.ord_sig = qs.info ? 0xFFF00000u : (0x80000000u | st.n_ev); wk.ord_twin = qs.info ? 0xFFF00000u : (0x80000000u | st.n_tw);
+                                wk.ord_sig = QS ? 0xFFF00000u : (0x80000000u | st.n_ev); wk.ord_twin = QS ? 0xFFF00000u : (0x80000000u | st.n_tw);
                                 wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
                                 work[wslot] = wk;
                             } else atomicExch(cnt + CNT_OVERFLOW, 1u);
@@ -798,13 +800,16 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                     { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>()); }
                 } else if (variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
-                    { ctx->launches++; k_cigar_scan_s<5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                    { ctx->launches++; k_cigar_scan_s<5, false><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>(), qsv); }
                 } else if (variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
-                    { ctx->launches++; k_cigar_scan_s<4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                    { ctx->launches++; k_cigar_scan_s<4, false><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                   ctx->d_counters.as<uint32_t>(), qsv); }
+                } else if (ctx->qs_mode) {      // query-sorted instantiation of the default kernel
+                    { ctx->launches++; k_cigar_scan_s<6, true><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                                                                         ctx->d_counters.as<uint32_t>(), qsv); }
                 } else if (variant == 0 || variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
-                    { ctx->launches++; k_cigar_scan_s<6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
+                    { ctx->launches++; k_cigar_scan_s<6, false><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                    ctx->d_counters.as<uint32_t>(), qsv); }
                 } else if (variant == 5) {   // experiment: 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
