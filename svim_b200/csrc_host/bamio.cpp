@@ -8,7 +8,11 @@
 //
 // File format: SAMv1 §4.1 (BGZF) and §4.2 (BAM).
 #include <zlib.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <algorithm>
+#include <memory>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
@@ -40,8 +44,17 @@ struct Block { size_t coff, clen, uoff, ulen; };
 
 struct Rec { size_t off; uint32_t sa_off_in_rec, sa_len; };
 
+// uninitialised byte buffer: pages are first touched by the worker threads, not zero-filled by one thread
+struct RawBuf {
+    std::unique_ptr<uint8_t[]> p; size_t n = 0;
+    void alloc(size_t bytes) { p.reset(new uint8_t[bytes ? bytes : 1]); n = bytes; }
+    uint8_t* data() { return p.get(); }
+    const uint8_t* data() const { return p.get(); }
+    size_t size() const { return n; }
+};
+
 struct Handle {
-    std::vector<uint8_t> data;      // inflated stream
+    RawBuf data;                    // inflated stream
     std::vector<Rec> recs;
     std::vector<std::string> contigs; std::vector<int64_t> contig_len;
     std::vector<uint32_t> qid;
@@ -100,12 +113,24 @@ extern "C" {
 
 void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, int errcap) {
     auto fail = [&](const char* m) -> void* { if (err && errcap > 0) snprintf(err, errcap, "%s", m); return nullptr; };
-    FILE* fh = fopen(path, "rb");
-    if (!fh) return fail("cannot open file");
-    fseek(fh, 0, SEEK_END); const long fsz = ftell(fh); fseek(fh, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)fsz);
-    if (fsz && fread(file.data(), 1, (size_t)fsz, fh) != (size_t)fsz) { fclose(fh); return fail("short read"); }
-    fclose(fh);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail("cannot open file");
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return fail("cannot stat file"); }
+    const size_t fsz = (size_t)sb.st_size;
+    RawBuf file; file.alloc(fsz);
+    {   // parallel pread: the file usually sits in the page cache, the copy is what costs
+        std::atomic<int> short_read{0};
+        const size_t CH = (size_t)64 << 20;
+        parallel_for((fsz + CH - 1) / CH, std::max(1, n_threads), [&](size_t lo, size_t hi) {
+            for (size_t c = lo; c < hi; ++c) {
+                size_t off = c * CH, len = std::min(CH, fsz - off);
+                while (len) { const ssize_t r = pread(fd, file.data() + off, len, (off_t)off); if (r <= 0) { short_read = 1; return; } off += (size_t)r; len -= (size_t)r; }
+            }
+        });
+        close(fd);
+        if (short_read) return fail("short read");
+    }
     // ---- BGZF block index ----------------------------------------------------------------------------
     std::vector<Block> blocks;
     size_t o = 0, uoff = 0;
@@ -127,7 +152,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
     }
     Handle* h = new Handle();
     h->threads = std::max(1, n_threads);
-    h->data.resize(uoff);
+    h->data.alloc(uoff);
     std::atomic<int> bad{0};
     parallel_for(blocks.size(), h->threads, [&](size_t lo, size_t hi) {
         z_stream zs;
@@ -143,7 +168,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         }
     });
     if (bad) { delete h; return fail("inflate failed"); }
-    std::vector<uint8_t>().swap(file);
+    file.p.reset(); file.n = 0;
     // ---- header --------------------------------------------------------------------------------------------
     const uint8_t* d = h->data.data(); const size_t n = h->data.size();
     if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete h; return fail("not a BAM stream"); }
