@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
 // length of the longer haplotype.  mode 0 counts per bin, mode 1 fills `work` at the bin cursors.
 __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint8_t* ins_blob, GenomeView g, const uint32_t* samp_off,
                                                     const uint32_t* samp_idx, const uint32_t* plist, uint32_t n_list, const uint64_t* pair_off,
-                                                    ClusterParams cp, int mode, MyersWork* work, uint32_t* bin_cursor, uint32_t* err) {
+                                                    ClusterParams cp, int mode, MyersWork* work, uint64_t* work_key, uint32_t* bin_cursor,
+                                                    uint32_t* err) {
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_list) return;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
     int i = 0, rowstart = 0;
     for (int64_t q0 = 0; q0 < npairs; q0 += 32) {
         const int64_t q = q0 + lane;
-        int bin = -1; uint32_t pa = 0, pb = 0;
+        int bin = -1; uint32_t pa = 0, pb = 0, cost = 0;
         if (q < npairs) {
             while (q >= rowstart + (m - 1 - i)) { rowstart += m - 1 - i; ++i; }
             const int j = i + 1 + (int)(q - rowstart);
@@ -280,6 +281,8 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
                 if (pair_haps(a, b, ins_blob, g, ha, hb)) {
                     const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
                     bin = myers_bin_of(la > lb ? la : lb);
+                    const uint64_t cells = (uint64_t)la * (uint64_t)lb;
+                    cost = cells >> 6 > 0xffffffffull ? 0xffffffffu : (uint32_t)(cells >> 6);
                 } else { atomicExch(err, 1u); }
             }
         }
@@ -290,7 +293,11 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
             uint32_t base = 0;
             if (lane == (__ffs(msk) - 1)) base = atomicAdd(bin_cursor + bb, (uint32_t)__popc(msk));
             base = __shfl_sync(FULL, base, __ffs(msk) - 1);
-            if (mode == 1 && bin == bb) { MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[base + __popc(msk & ((1u << lane) - 1))] = wk; }
+            if (mode == 1 && bin == bb) {
+                const uint32_t at = base + __popc(msk & ((1u << lane) - 1));
+                MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[at] = wk;
+                work_key[at] = ((uint64_t)bb << 32) | (uint64_t)(0xffffffffu - cost);   // longest pairs first inside a bin (LPT)
+            }
         }
     }
 }
@@ -539,7 +546,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             StageTimer t(ctx, T_PAIRS);
             SVIM_CUDA(cudaMemsetAsync(d_bins, 0, 16 * 4, st));
             { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, d_bins, d_misc + 9); }
+                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_bins, d_misc + 9); }
             SVIM_CUDA(cudaMemcpyAsync(bin_cnt, d_bins, MYERS_BINS * 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
         }
@@ -549,13 +556,21 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         cs.myers_pairs = n_work;
         if (n_work > 0 && !ctx->d_genome.p) { ctx->set_error(SVIMGPU_ERR_STATE, "insertion clustering needs svimgpu_set_genome"); return SVIMGPU_ERR_STATE; }
         if (n_work > 0) {
-            SVIM_CUDA(ctx->d_pairs.ensure((size_t)n_work * 2 * sizeof(MyersWork) + 16));   // work list + fallback list
+            SVIM_CUDA(ctx->d_pairs.ensure((size_t)n_work * 3 * sizeof(MyersWork) + 16));   // unsorted list, sorted list, fallback list
+            SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_work * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n_work * 8));
+            MyersWork* d_unsorted = ctx->d_pairs.as<MyersWork>() + 2 * (size_t)n_work;
             MyersWork* d_work = ctx->d_pairs.as<MyersWork>();
             {
                 StageTimer t(ctx, T_PAIRS);
                 SVIM_CUDA(cudaMemcpyAsync(d_bins, bin_off, MYERS_BINS * 4, cudaMemcpyHostToDevice, st));
                 { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_work, d_bins, d_misc + 9); }
+                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_bins, d_misc + 9); }
+                // longest-processing-time-first inside every bin: one radix sort on (bin, ~cost)
+                size_t tmp = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work, (int)n_work, 0, 36, st);
+                SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+                SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work,
+                                                          (int)n_work, 0, 36, st));
             }
             StageTimer t(ctx, T_MYERS);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
