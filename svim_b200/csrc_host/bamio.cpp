@@ -9,6 +9,7 @@
 // File format: SAMv1 §4.1 (BGZF) and §4.2 (BAM).
 #include <zlib.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
@@ -45,11 +46,31 @@ struct Block { size_t coff, clen, uoff, ulen; };
 struct Rec { size_t off; uint32_t sa_off_in_rec, sa_len; };
 
 // uninitialised byte buffer: pages are first touched by the worker threads, not zero-filled by one thread
+// Large first-touch buffers are page-fault bound with 4 KiB pages; ask for transparent huge pages.
+static void advise_huge(void* p, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+    const uintptr_t a = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+    const uintptr_t e = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
+    if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
+#endif
+}
+
 struct RawBuf {
-    std::unique_ptr<uint8_t[]> p; size_t n = 0;
-    void alloc(size_t bytes) { p.reset(new uint8_t[bytes ? bytes : 1]); n = bytes; }
-    uint8_t* data() { return p.get(); }
-    const uint8_t* data() const { return p.get(); }
+    uint8_t* ptr = nullptr; size_t n = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { release(); }
+    void release() { if (ptr) free(ptr); ptr = nullptr; n = 0; }
+    void alloc(size_t bytes) {
+        release();
+        void* q = nullptr;
+        if (posix_memalign(&q, (size_t)2 << 20, bytes ? bytes : 1) != 0) q = nullptr;
+        ptr = (uint8_t*)q; n = bytes;
+        if (ptr) advise_huge(ptr, bytes);
+    }
+    uint8_t* data() { return ptr; }
+    const uint8_t* data() const { return ptr; }
     size_t size() const { return n; }
 };
 
@@ -119,6 +140,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
     if (fstat(fd, &sb) != 0) { close(fd); return fail("cannot stat file"); }
     const size_t fsz = (size_t)sb.st_size;
     RawBuf file; file.alloc(fsz);
+    if (fsz && !file.data()) { close(fd); return fail("out of memory"); }
     {   // parallel pread: the file usually sits in the page cache, the copy is what costs
         std::atomic<int> short_read{0};
         const size_t CH = (size_t)64 << 20;
@@ -153,6 +175,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
     Handle* h = new Handle();
     h->threads = std::max(1, n_threads);
     h->data.alloc(uoff);
+    if (uoff && !h->data.data()) { delete h; return fail("out of memory"); }
     std::atomic<int> bad{0};
     parallel_for(blocks.size(), h->threads, [&](size_t lo, size_t hi) {
         z_stream zs;
@@ -168,7 +191,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         }
     });
     if (bad) { delete h; return fail("inflate failed"); }
-    file.p.reset(); file.n = 0;
+    file.release();
     // ---- header --------------------------------------------------------------------------------------------
     const uint8_t* d = h->data.data(); const size_t n = h->data.size();
     if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete h; return fail("not a BAM stream"); }
@@ -266,6 +289,7 @@ int bamio_qnames(void* hh, char* out, int64_t cap) {
 
 int bamio_fill(void* hh, bamio_out* out) {
     Handle* h = (Handle*)hh;
+    advise_huge(out->cigar, (size_t)h->info.cigar_words * 4); advise_huge(out->seq, (size_t)h->info.seq_bytes);
     const uint8_t* d = h->data.data();
     const size_t nr = h->recs.size();
     uint64_t co = 0, so = 0, sao = 0;
