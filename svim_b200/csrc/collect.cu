@@ -19,13 +19,42 @@
 struct DeviceEmitter {
     SigQueue qm, qt;
     uint32_t* overflow;
-    __device__ __forceinline__ void push(SigQueue& q, const svim_sig& s) {
-        uint32_t slot = atomicAdd(q.count, 1u);
+    uint32_t slot_m = 0xffffffffu, slot_t = 0xffffffffu;   // next pre-reserved slot of this lane (scan kernel), else one atomic per record
+    __device__ __forceinline__ void push(SigQueue& q, const svim_sig& s, uint32_t& reserved) {
+        const uint32_t slot = reserved != 0xffffffffu ? reserved++ : atomicAdd(q.count, 1u);
         if (slot < q.cap) q.recs[slot] = s; else atomicExch(overflow, 1u);
     }
-    __device__ __forceinline__ void sig(const svim_sig& s) { push(qm, s); }
-    __device__ __forceinline__ void twin(const svim_sig& s) { push(qt, s); }
+    __device__ __forceinline__ void sig(const svim_sig& s) { push(qm, s, slot_m); }
+    __device__ __forceinline__ void twin(const svim_sig& s) { push(qt, s, slot_t); }
 };
+
+// Queue slots are handed to a warp in chunks: one global atomic per SCAN_CHUNK signatures instead of one per signature
+// (event-dense CIGARs serialise on that counter otherwise).  Slots a warp reserved but never filled are marked as holes
+// and sort to the end of the queue.
+#define SCAN_CHUNK 16
+struct SlotChunk { uint32_t base, left; };
+
+__device__ __forceinline__ void mark_hole(svim_sig& r) { r.aln_idx = 0xffffffffu; r.ordinal = 0xffffffffu; r.type = 0xff; }
+
+__device__ __forceinline__ uint32_t reserve_slots(const SigQueue& q, SlotChunk* c, uint32_t need, int lane, uint32_t* holes) {
+    uint32_t base = c->base; const uint32_t left = c->left;
+    __syncwarp();
+    if (left >= need) { if (lane == 0) { c->base = base + need; c->left = left - need; } __syncwarp(); return base; }
+    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);     // abandon the remainder
+    const uint32_t take = need > SCAN_CHUNK ? need : SCAN_CHUNK;
+    uint32_t nb = 0;
+    if (lane == 0) { nb = atomicAdd(q.count, take); if (left) atomicAdd(holes, left); }
+    nb = __shfl_sync(FULL, nb, 0);
+    if (lane == 0) { c->base = nb + need; c->left = take - need; }
+    __syncwarp();
+    return nb;
+}
+
+__device__ __forceinline__ void flush_slots(const SigQueue& q, SlotChunk* c, int lane, uint32_t* holes) {
+    const uint32_t base = c->base, left = c->left;
+    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);
+    if (lane == 0 && left) atomicAdd(holes, left);
+}
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
@@ -232,8 +261,8 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams 
 // The fast path only needs the four lane-private accumulators and the loaded words; everything the rare path
 // touches (running base positions, ordinals, record identity, queues, options) is parked in shared memory so the
 // kernel fits 5-6 CTAs per SM without spilling.
-struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t thresh; };
-struct ScanWarp { EvState st; ScanRec r; };
+struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t* holes; uint32_t thresh; };
+struct ScanWarp { EvState st; ScanRec r; SlotChunk cm, ct; };
 
 template <bool SUM>
 __device__ __noinline__ void scan_events_s(const uint4 w, int lane, const ScanShared* sh, ScanWarp* ws, uint32_t acc_ref, uint32_t acc_read) {
@@ -241,6 +270,19 @@ __device__ __noinline__ void scan_events_s(const uint4 w, int lane, const ScanSh
     const EvState old = ws->st;
     const ScanRec r = ws->r;
     __syncwarp();
+    {   // reserve queue slots for every signature of this group: slot of a record = warp base + events in lower lanes
+        const uint32_t v4[4] = {w.x, w.y, w.z, w.w};
+        uint32_t my_ev = 0, my_del = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const bool e = is_event(v4[k], op_bit(v4[k]), sh->thresh); my_ev += e; my_del += e && (v4[k] & 15u) == OP_D; }
+        uint32_t tot_ev, tot_del;
+        const uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
+        out.slot_m = reserve_slots(sh->qm, &ws->cm, tot_ev, lane, sh->holes) + ex_ev;
+        if (sh->p.all_bnds) {
+            const uint32_t ex_del = warp_excl_scan(my_del, lane, tot_del);
+            if (tot_del) out.slot_t = reserve_slots(sh->qt, &ws->ct, tot_del, lane, sh->holes + 1) + ex_del;
+        }
+    }
     EvState st = scan_events<SUM>(w, sh->thresh, lane, sh->p, r, old, acc_ref, acc_read, out);
     if (SUM) {   // scan_events adds this lane's N/H bases; the shared copy keeps warp totals
         st.nsum = old.nsum + warp_sum(st.nsum - old.nsum);
@@ -303,7 +345,8 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
     __shared__ ScanWarp ws_s[8];
     const int lane = threadIdx.x & 31;
     const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
-    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.thresh = thresh; }
+    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.holes = cnt + CNT_HOLES_MAIN; sh_s.thresh = thresh; }
+    if (lane == 0) { ws_s[threadIdx.x >> 5].cm = SlotChunk{0, 0}; ws_s[threadIdx.x >> 5].ct = SlotChunk{0, 0}; }
     __syncthreads();
     const ScanShared* sh = &sh_s;
     ScanWarp* ws = &ws_s[threadIdx.x >> 5];
@@ -376,6 +419,9 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
             __syncwarp();
         }
     }
+    __syncwarp();
+    flush_slots(qm, &ws->cm, lane, cnt + CNT_HOLES_MAIN);
+    if (p.all_bnds) flush_slots(qt, &ws->ct, lane, cnt + CNT_HOLES_TWIN);
     primaries = warp_sum(primaries);
     if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
 }
@@ -607,8 +653,9 @@ __global__ void __launch_bounds__(128) k_segment_chain_qs(DevSoa a, ChainParams 
 __global__ void k_sig_keys(const svim_sig* recs, uint32_t n, const uint32_t* grp, uint64_t* keys, uint32_t* vals) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t hi = grp ? grp[recs[k].aln_idx] : recs[k].aln_idx;
-    keys[k] = ((uint64_t)hi << 32) | recs[k].ordinal;
+    const uint32_t idx = recs[k].aln_idx;
+    const uint32_t hi = (grp && idx != 0xffffffffu) ? grp[idx] : idx;     // holes (aln_idx = ~0) sort to the end
+    keys[k] = recs[k].type == 0xff ? ~0ull : (((uint64_t)hi << 32) | recs[k].ordinal);
     vals[k] = k;
 }
 
@@ -710,24 +757,25 @@ static int collect_gather_lazy(svimgpu_ctx* ctx, SigSet& set, uint32_t n, const 
     return 0;
 }
 
-static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n) {
-    // queue[which] (arbitrary order) -> sets[which].recs in emission order + INS blob
+static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n_reserved, uint32_t n_holes) {
+    // queue[which] (arbitrary order, with holes) -> sets[which].recs in emission order + INS blob
     SigSet& set = ctx->sets[which];
+    const uint32_t n_all = n_reserved, n = n_reserved - n_holes;
     set.n = n; set.ins_bytes = 0;
     if (n == 0) return 0;
     SVIM_CUDA(set.recs.ensure((size_t)n * sizeof(svim_sig)));
-    SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n * 8));
-    SVIM_CUDA(ctx->d_vals[0].ensure((size_t)n * 4)); SVIM_CUDA(ctx->d_vals[1].ensure((size_t)n * 4));
+    SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_all * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n_all * 8));
+    SVIM_CUDA(ctx->d_vals[0].ensure((size_t)n_all * 4)); SVIM_CUDA(ctx->d_vals[1].ensure((size_t)n_all * 4));
     SVIM_CUDA(ctx->d_scan.ensure((size_t)(n + 1) * 8 * 2));
     cudaStream_t st = ctx->stream;
     const svim_sig* q = ctx->d_queue[which].as<svim_sig>();
-    { ctx->launches++; k_sig_keys<<<(n + 255) / 256, 256, 0, st>>>(q, n, ctx->qs_mode ? ctx->d_qs_grp.as<uint32_t>() : nullptr, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>()); }
+    { ctx->launches++; k_sig_keys<<<(n_all + 255) / 256, 256, 0, st>>>(q, n_all, ctx->qs_mode ? ctx->d_qs_grp.as<uint32_t>() : nullptr, ctx->d_keys[0].as<uint64_t>(), ctx->d_vals[0].as<uint32_t>()); }
     cub::DoubleBuffer<uint64_t> dk(ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>());
     cub::DoubleBuffer<uint32_t> dv(ctx->d_vals[0].as<uint32_t>(), ctx->d_vals[1].as<uint32_t>());
     size_t tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 64, st);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n_all, 0, 64, st);
     SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
-    SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int)n, 0, 64, st));
+    SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, dk, dv, (int)n_all, 0, 64, st));
     uint64_t* ins_len = ctx->d_scan.as<uint64_t>();
     uint64_t* ins_off = ins_len + (n + 1);
     { ctx->launches++; k_sig_gather<<<(n + 255) / 256, 256, 0, st>>>(q, dv.Current(), n, set.recs.as<svim_sig>(), ins_len); }
@@ -765,7 +813,8 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->soa.n;
     if (n >= (int64_t)1 << 32) { ctx->set_error(SVIMGPU_ERR_LIMIT, "more than 2^32 records in one batch"); return SVIMGPU_ERR_LIMIT; }
-    uint32_t cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(1 << 16, 2 * n + 1024), 0x7fffffff);
+    // every resident scan warp may sit on up to SCAN_CHUNK-1 reserved-but-unused slots
+    uint32_t cap = (uint32_t)std::min<int64_t>(std::max<int64_t>(1 << 16, 2 * n + 1024) + (int64_t)148 * 12 * 8 * SCAN_CHUNK, 0x7fffffff);
     SVIM_CUDA(ctx->d_counters.ensure(CNT_N * 4));
     uint32_t h_cnt[CNT_N];
     ChainParams cp = make_chain_params(ctx->params);
@@ -850,8 +899,8 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
     }
     {
         StageTimer t(ctx, T_SORTBACK);
-        int rc = collect_sort_queue(ctx, 0, h_cnt[CNT_MAIN]); if (rc) return rc;
-        rc = collect_sort_queue(ctx, 1, h_cnt[CNT_TWIN]); if (rc) return rc;
+        int rc = collect_sort_queue(ctx, 0, h_cnt[CNT_MAIN], h_cnt[CNT_HOLES_MAIN]); if (rc) return rc;
+        rc = collect_sort_queue(ctx, 1, h_cnt[CNT_TWIN], h_cnt[CNT_HOLES_TWIN]); if (rc) return rc;
     }
     SVIM_CUDA(cudaStreamSynchronize(st));
     svim_collect_stats& s = ctx->cstats;

@@ -59,7 +59,7 @@ struct ChainWork {
 
 enum {  // device counters
     CNT_MAIN = 0, CNT_TWIN, CNT_WORK, CNT_NEXT_ALN, CNT_PRIMARIES, CNT_BAD_FIELDS, CNT_NO_READLEN, CNT_DATA_ERR,
-    CNT_TOO_MANY, CNT_OVERFLOW, CNT_MYERS_NEXT, CNT_N
+    CNT_TOO_MANY, CNT_OVERFLOW, CNT_MYERS_NEXT, CNT_HOLES_MAIN, CNT_HOLES_TWIN, CNT_N
 };
 
 enum {  // timing slots
