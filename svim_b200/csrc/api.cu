@@ -39,6 +39,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     memset(&ctx->cstats, 0, sizeof(ctx->cstats)); memset(&ctx->clstats, 0, sizeof(ctx->clstats));
     myers_init_symcode();
     if (const char* v = getenv("SVIM_SCAN_VARIANT")) ctx->scan_variant = atoi(v);
+    if (const char* v = getenv("SVIM_SCAN_CHUNKS")) ctx->scan_chunks = atoi(v);
     *out = ctx;
     return 0;
 }

@@ -28,34 +28,6 @@ struct DeviceEmitter {
     __device__ __forceinline__ void twin(const svim_sig& s) { push(qt, s, slot_t); }
 };
 
-// Queue slots are handed to a warp in chunks: one global atomic per SCAN_CHUNK signatures instead of one per signature
-// (event-dense CIGARs serialise on that counter otherwise).  Slots a warp reserved but never filled are marked as holes
-// and sort to the end of the queue.
-#define SCAN_CHUNK 16
-struct SlotChunk { uint32_t base, left; };
-
-__device__ __forceinline__ void mark_hole(svim_sig& r) { r.aln_idx = 0xffffffffu; r.ordinal = 0xffffffffu; r.type = 0xff; }
-
-__device__ __forceinline__ uint32_t reserve_slots(const SigQueue& q, SlotChunk* c, uint32_t need, int lane, uint32_t* holes) {
-    uint32_t base = c->base; const uint32_t left = c->left;
-    __syncwarp();
-    if (left >= need) { if (lane == 0) { c->base = base + need; c->left = left - need; } __syncwarp(); return base; }
-    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);     // abandon the remainder
-    const uint32_t take = need > SCAN_CHUNK ? need : SCAN_CHUNK;
-    uint32_t nb = 0;
-    if (lane == 0) { nb = atomicAdd(q.count, take); if (left) atomicAdd(holes, left); }
-    nb = __shfl_sync(FULL, nb, 0);
-    if (lane == 0) { c->base = nb + need; c->left = take - need; }
-    __syncwarp();
-    return nb;
-}
-
-__device__ __forceinline__ void flush_slots(const SigQueue& q, SlotChunk* c, int lane, uint32_t* holes) {
-    const uint32_t base = c->base, left = c->left;
-    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);
-    if (lane == 0 && left) atomicAdd(holes, left);
-}
-
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -89,6 +61,34 @@ __device__ __forceinline__ bool is_event(uint32_t v, uint32_t B, uint32_t thresh
 #define SCAN_UNROLL 4
 #define SCAN_BATCH 4     // alignments fetched per atomic
 
+// Queue slots are handed to a warp in chunks: one global atomic per SCAN_CHUNK signatures instead of one per signature
+// (event-dense CIGARs serialise on that counter otherwise).  Slots a warp reserved but never filled are marked as holes
+// and sort to the end of the queue.
+#define SCAN_CHUNK 16
+struct SlotChunk { uint32_t base, left; };
+
+__device__ __forceinline__ void mark_hole(svim_sig& r) { r.aln_idx = 0xffffffffu; r.ordinal = 0xffffffffu; r.type = 0xff; }
+
+__device__ __forceinline__ uint32_t reserve_slots(const SigQueue& q, SlotChunk* c, uint32_t need, int lane, uint32_t* holes) {
+    uint32_t base = c->base; const uint32_t left = c->left;
+    __syncwarp();
+    if (left >= need) { if (lane == 0) { c->base = base + need; c->left = left - need; } __syncwarp(); return base; }
+    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);     // abandon the remainder
+    const uint32_t take = need > SCAN_CHUNK ? need : SCAN_CHUNK;
+    uint32_t nb = 0;
+    if (lane == 0) { nb = atomicAdd(q.count, take); if (left) atomicAdd(holes, left); }
+    nb = __shfl_sync(FULL, nb, 0);
+    if (lane == 0) { c->base = nb + need; c->left = take - need; }
+    __syncwarp();
+    return nb;
+}
+
+__device__ __forceinline__ void flush_slots(const SigQueue& q, SlotChunk* c, int lane, uint32_t* holes) {
+    const uint32_t base = c->base, left = c->left;
+    for (uint32_t k = lane; k < left; k += 32) if (base + k < q.cap) mark_hole(q.recs[base + k]);
+    if (lane == 0 && left) atomicAdd(holes, left);
+}
+
 struct ScanRec { uint32_t i, qid; int32_t tid; int64_t ref_start, l_seq; };
 struct EvState { int64_t base_ref, base_read; uint32_t n_ev, n_tw, nsum, hsum; };
 
@@ -96,7 +96,8 @@ struct EvState { int64_t base_ref, base_read; uint32_t n_ev, n_tw, nsum, hsum; }
 // acc_ref/acc_read: lane-private consumption since the last fold; returned state has them folded in.
 template <bool SUM>
 __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int lane, const ChainParams& p, const ScanRec& r, EvState st,
-                                            uint32_t acc_ref, uint32_t acc_read, DeviceEmitter out) {
+                                            uint32_t acc_ref, uint32_t acc_read, DeviceEmitter out, SlotChunk* cm = nullptr, SlotChunk* ct = nullptr,
+                                            uint32_t* holes = nullptr) {
     const uint32_t v[4] = {w.x, w.y, w.z, w.w};
     st.base_ref += warp_sum(acc_ref); st.base_read += warp_sum(acc_read);
     uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0;
@@ -114,12 +115,15 @@ __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int 
     const uint32_t ex_read = warp_excl_scan(g_read, lane, tot_read);
     const uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
     uint32_t ord = st.n_ev + ex_ev;
+    if (cm) out.slot_m = reserve_slots(out.qm, cm, tot_ev, lane, holes) + ex_ev;   // one chunked reservation for the whole group
     uint32_t tw_before = 0;
     if (p.all_bnds) {   // twins only for deletions: count DEL events before this lane
         uint32_t my_del = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) my_del += (is_event(v[k], op_bit(v[k]), thresh) && (v[k] & 15u) == OP_D);
-        uint32_t tot_del; tw_before = st.n_tw + warp_excl_scan(my_del, lane, tot_del); st.n_tw += tot_del;
+        uint32_t tot_del; const uint32_t ex_del = warp_excl_scan(my_del, lane, tot_del);
+        tw_before = st.n_tw + ex_del; st.n_tw += tot_del;
+        if (ct && tot_del) out.slot_t = reserve_slots(out.qt, ct, tot_del, lane, holes + 1) + ex_del;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams 
 // The fast path only needs the four lane-private accumulators and the loaded words; everything the rare path
 // touches (running base positions, ordinals, record identity, queues, options) is parked in shared memory so the
 // kernel fits 5-6 CTAs per SM without spilling.
-struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t* holes; uint32_t thresh; };
+struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t* holes; uint32_t thresh; int use_chunks; };
 struct ScanWarp { EvState st; ScanRec r; SlotChunk cm, ct; };
 
 template <bool SUM>
@@ -270,20 +274,8 @@ __device__ __noinline__ void scan_events_s(const uint4 w, int lane, const ScanSh
     const EvState old = ws->st;
     const ScanRec r = ws->r;
     __syncwarp();
-    {   // reserve queue slots for every signature of this group: slot of a record = warp base + events in lower lanes
-        const uint32_t v4[4] = {w.x, w.y, w.z, w.w};
-        uint32_t my_ev = 0, my_del = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const bool e = is_event(v4[k], op_bit(v4[k]), sh->thresh); my_ev += e; my_del += e && (v4[k] & 15u) == OP_D; }
-        uint32_t tot_ev, tot_del;
-        const uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
-        out.slot_m = reserve_slots(sh->qm, &ws->cm, tot_ev, lane, sh->holes) + ex_ev;
-        if (sh->p.all_bnds) {
-            const uint32_t ex_del = warp_excl_scan(my_del, lane, tot_del);
-            if (tot_del) out.slot_t = reserve_slots(sh->qt, &ws->ct, tot_del, lane, sh->holes + 1) + ex_del;
-        }
-    }
-    EvState st = scan_events<SUM>(w, sh->thresh, lane, sh->p, r, old, acc_ref, acc_read, out);
+    EvState st = scan_events<SUM>(w, sh->thresh, lane, sh->p, r, old, acc_ref, acc_read, out, sh->use_chunks ? &ws->cm : nullptr,
+                                  sh->use_chunks ? &ws->ct : nullptr, sh->holes);
     if (SUM) {   // scan_events adds this lane's N/H bases; the shared copy keeps warp totals
         st.nsum = old.nsum + warp_sum(st.nsum - old.nsum);
         st.hsum = old.hsum + warp_sum(st.hsum - old.hsum);
@@ -338,14 +330,14 @@ struct QsView { const uint32_t* info; const uint32_t* grp; SegSum* segsum; };
 
 template <int MINB, bool QS>
 __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
-                                                             uint32_t* cnt, QsView qs_in) {
+                                                             uint32_t* cnt, QsView qs_in, int use_chunks) {
     QsView qs = qs_in;
     if (!QS) qs.info = nullptr;          // compile-time: the coordinate-sorted instantiation carries none of the read-group logic
     __shared__ ScanShared sh_s;
     __shared__ ScanWarp ws_s[8];
     const int lane = threadIdx.x & 31;
     const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
-    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.holes = cnt + CNT_HOLES_MAIN; sh_s.thresh = thresh; }
+    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.holes = cnt + CNT_HOLES_MAIN; sh_s.thresh = thresh; sh_s.use_chunks = use_chunks; }
     if (lane == 0) { ws_s[threadIdx.x >> 5].cm = SlotChunk{0, 0}; ws_s[threadIdx.x >> 5].ct = SlotChunk{0, 0}; }
     __syncthreads();
     const ScanShared* sh = &sh_s;
@@ -850,16 +842,16 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                                                                    ctx->d_counters.as<uint32_t>()); }
                 } else if (variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan_s<5, false><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>(), qsv); }
+                                                                   ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
                 } else if (variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
                     { ctx->launches++; k_cigar_scan_s<4, false><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                  ctx->d_counters.as<uint32_t>(), qsv); }
+                                                                  ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
                 } else if (ctx->qs_mode) {      // query-sorted instantiation of the default kernel
                     { ctx->launches++; k_cigar_scan_s<6, true><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                         ctx->d_counters.as<uint32_t>(), qsv); }
+                                                                         ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
                 } else if (variant == 0 || variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
                     { ctx->launches++; k_cigar_scan_s<6, false><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>(), qsv); }
+                                                                   ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
                 } else if (variant == 5) {   // experiment: 5 CTAs/SM
                     { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                     ctx->d_counters.as<uint32_t>()); }
