@@ -40,6 +40,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     myers_init_symcode();
     if (const char* v = getenv("SVIM_SCAN_VARIANT")) ctx->scan_variant = atoi(v);
     if (const char* v = getenv("SVIM_SCAN_CHUNKS")) ctx->scan_chunks = atoi(v);
+    if (const char* v = getenv("SVIM_MYERS_MODE")) ctx->myers_mode = atoi(v);
     *out = ctx;
     return 0;
 }

@@ -96,8 +96,7 @@ struct EvState { int64_t base_ref, base_read; uint32_t n_ev, n_tw, nsum, hsum; }
 // acc_ref/acc_read: lane-private consumption since the last fold; returned state has them folded in.
 template <bool SUM>
 __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int lane, const ChainParams& p, const ScanRec& r, EvState st,
-                                            uint32_t acc_ref, uint32_t acc_read, DeviceEmitter out, SlotChunk* cm = nullptr, SlotChunk* ct = nullptr,
-                                            uint32_t* holes = nullptr) {
+                                            uint32_t acc_ref, uint32_t acc_read, DeviceEmitter out) {
     const uint32_t v[4] = {w.x, w.y, w.z, w.w};
     st.base_ref += warp_sum(acc_ref); st.base_read += warp_sum(acc_read);
     uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0;
@@ -115,7 +114,6 @@ __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int 
     const uint32_t ex_read = warp_excl_scan(g_read, lane, tot_read);
     const uint32_t ex_ev = warp_excl_scan(my_ev, lane, tot_ev);
     uint32_t ord = st.n_ev + ex_ev;
-    if (cm) out.slot_m = reserve_slots(out.qm, cm, tot_ev, lane, holes) + ex_ev;   // one chunked reservation for the whole group
     uint32_t tw_before = 0;
     if (p.all_bnds) {   // twins only for deletions: count DEL events before this lane
         uint32_t my_del = 0;
@@ -123,7 +121,6 @@ __device__ __noinline__ EvState scan_events(const uint4 w, uint32_t thresh, int 
         for (int k = 0; k < 4; ++k) my_del += (is_event(v[k], op_bit(v[k]), thresh) && (v[k] & 15u) == OP_D);
         uint32_t tot_del; const uint32_t ex_del = warp_excl_scan(my_del, lane, tot_del);
         tw_before = st.n_tw + ex_del; st.n_tw += tot_del;
-        if (ct && tot_del) out.slot_t = reserve_slots(out.qt, ct, tot_del, lane, holes + 1) + ex_del;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -261,49 +258,154 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan(DevSoa a, ChainParams 
     if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
 }
 
-// ---- low-register variant: rare-path state lives in shared memory --------------------------------------------
-// The fast path only needs the four lane-private accumulators and the loaded words; everything the rare path
-// touches (running base positions, ordinals, record identity, queues, options) is parked in shared memory so the
-// kernel fits 5-6 CTAs per SM without spilling.
+// ---- default scan kernel ---------------------------------------------------------------------------------------
+// The scan moves ~11 KB of CIGAR per record at HBM speed, but per 4-byte op it also has to classify the op and add
+// its length to two running sums: with plain LOP3/ISETP/IADD code that is ~12 ALU-pipe instructions per op, and the
+// ALU pipe (one warp instruction every two cycles per SM sub-partition) saturates below the HBM roofline.  So:
+//   * one funnel shift of a 64-bit constant by the op code yields all three class bits at once
+//     (bit 0: consumes reference, bit 15: I/D, bit 31: consumes read);
+//   * one IMAD.WIDE on the otherwise idle FMA pipe adds len to both sums, kept as two fields of a 64-bit
+//     accumulator (reference in bits 0-30, read from bit 31 up; a valid record consumes < 2^31 of either);
+//   * everything the rare path needs (running positions, ordinals, record identity, queues, options) lives in
+//     shared memory, and the record metadata of a batch is fetched by four lanes at once, so the hot loop keeps
+//     only the 16 loaded words, the accumulator and the cursor in registers (6 CTAs of 256 threads per SM).
+struct ScanMeta { uint64_t cig; uint32_t i, n, bits, slot, qid; int32_t tid, pos, l_seq; };   // bits: 1 scan, 2 primary, 4 summary, 8 reverse
 struct ScanShared { ChainParams p; SigQueue qm, qt; uint32_t* overflow; uint32_t* holes; uint32_t thresh; int use_chunks; };
-struct ScanWarp { EvState st; ScanRec r; SlotChunk cm, ct; };
+struct ScanWarp { EvState st; SlotChunk cm, ct; uint32_t cur, pad; ScanMeta meta[SCAN_BATCH]; };
+__shared__ ScanShared g_scan_sh;
+__shared__ ScanWarp g_scan_ws[8];
 
+constexpr uint64_t SCAN_K = (uint64_t)SVIM_MASK_REF_QUIRK | ((uint64_t)0x6u << 15) | ((uint64_t)SVIM_MASK_READ << 31);
+constexpr uint64_t SCAN_K2 = ((uint64_t)1u << OP_N) | (((uint64_t)1u << OP_H) << 31);      // N / H lengths for the SA summary
+#define SCAN_F_MASK 0x80000001u
+#define SCAN_F_CAND 0x8000u
+
+__device__ __forceinline__ uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) {
+    uint64_t d;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t acc_lo(uint64_t acc) { return (uint32_t)acc & 0x7fffffffu; }
+__device__ __forceinline__ uint32_t acc_hi(uint64_t acc) { return (uint32_t)(acc >> 31); }
+
+// Rare path: a 128-op group with at least one SV-sized I/D.  Warp reductions (redux.sync) give the consumption before
+// each event lane; event lanes are visited in order, so ordinals and queue slots stay in emission order.
+// `acc` = the lane's consumption since the last fold.
 template <bool SUM>
-__device__ __noinline__ void scan_events_s(const uint4 w, int lane, const ScanShared* sh, ScanWarp* ws, uint32_t acc_ref, uint32_t acc_read) {
-    DeviceEmitter out{sh->qm, sh->qt, sh->overflow};
-    const EvState old = ws->st;
-    const ScanRec r = ws->r;
-    __syncwarp();
-    EvState st = scan_events<SUM>(w, sh->thresh, lane, sh->p, r, old, acc_ref, acc_read, out, sh->use_chunks ? &ws->cm : nullptr,
-                                  sh->use_chunks ? &ws->ct : nullptr, sh->holes);
-    if (SUM) {   // scan_events adds this lane's N/H bases; the shared copy keeps warp totals
-        st.nsum = old.nsum + warp_sum(st.nsum - old.nsum);
-        st.hsum = old.hsum + warp_sum(st.hsum - old.hsum);
+__device__ __noinline__ void scan_events_s(const uint4 w, int lane, uint64_t acc) {
+    const ScanShared* sh = &g_scan_sh;
+    ScanWarp* ws = &g_scan_ws[threadIdx.x >> 5];
+    const uint32_t thresh = sh->thresh;
+    const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+    uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0, pre_ref[4], pre_read[4];
+    uint32_t evbits = 0, delbits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t B = op_bit(v[k]);
+        pre_ref[k] = g_ref; pre_read[k] = g_read;
+        acc_op<SUM>(v[k], B, g_ref, g_read, g_n, g_h);
+        if (is_event(v[k], B, thresh)) { evbits |= 1u << k; if ((v[k] & 15u) == OP_D) delbits |= 1u << k; }
     }
+    unsigned m = __ballot_sync(FULL, evbits != 0);
+    EvState st = ws->st;
+    const ScanMeta r = ws->meta[ws->cur];
+    const int all_bnds = sh->p.all_bnds;
+    __syncwarp();
+    st.base_ref += __reduce_add_sync(FULL, acc_lo(acc)); st.base_read += __reduce_add_sync(FULL, acc_hi(acc));
+    while (m) {
+        const int L = __ffs(m) - 1; m &= m - 1;
+        const uint32_t ex_ref = __reduce_add_sync(FULL, lane < L ? g_ref : 0u);
+        const uint32_t ex_read = __reduce_add_sync(FULL, lane < L ? g_read : 0u);
+        const uint32_t evL = __shfl_sync(FULL, evbits, L), delL = __shfl_sync(FULL, delbits, L);
+        const uint32_t cntL = __popc(evL), ndel = all_bnds ? __popc(delL) : 0u;
+        uint32_t slot, slot_t = 0;
+        if (sh->use_chunks) { slot = reserve_slots(sh->qm, &ws->cm, cntL, lane, sh->holes); if (ndel) slot_t = reserve_slots(sh->qt, &ws->ct, ndel, lane, sh->holes + 1); }
+        else { slot = 0; if (lane == L) { slot = atomicAdd(sh->qm.count, cntL); if (ndel) slot_t = atomicAdd(sh->qt.count, ndel); } }
+        if (lane == L) {
+            uint32_t ord = st.n_ev, tord = st.n_tw;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!((evbits >> k) & 1u)) continue;
+                const uint32_t op = v[k] & 15u; const int64_t len = v[k] >> 4;
+                const int64_t pr = st.base_ref + ex_ref + pre_ref[k];
+                const int64_t pq = st.base_read + ex_read + pre_read[k];
+                svim_sig s; memset(&s, 0, sizeof(s));
+                s.contig1 = r.tid; s.contig2 = -1; s.start = (int32_t)(r.pos + pr); s.end = (int32_t)(r.pos + pr + len);
+                s.aln_idx = r.i; s.qname_id = r.qid; s.ordinal = ord++;
+                if (op == OP_D) {
+                    s.type = SVIM_DEL;
+                    if (slot < sh->qm.cap) sh->qm.recs[slot] = s; else atomicExch(sh->overflow, 1u);
+                    ++slot;
+                    if (all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
+                        svim_sig t = s; t.type = SVIM_BND; t.contig2 = r.tid; t.pos = s.end; t.end = s.start + 1; t.ordinal = tord++;
+                        if (len == 0) { t.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
+                        if (slot_t < sh->qt.cap) sh->qt.recs[slot_t] = t; else atomicExch(sh->overflow, 1u);
+                        ++slot_t;
+                    }
+                } else {
+                    s.type = SVIM_INS;
+                    int64_t lo, hi; py_slice(pq, len, (int64_t)r.l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
+                    s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
+                    if (slot < sh->qm.cap) sh->qm.recs[slot] = s; else atomicExch(sh->overflow, 1u);
+                    ++slot;
+                }
+            }
+        }
+        st.n_ev += cntL; st.n_tw += ndel;
+    }
+    st.base_ref += __reduce_add_sync(FULL, g_ref); st.base_read += __reduce_add_sync(FULL, g_read);
+    if (SUM) { st.nsum += __reduce_add_sync(FULL, g_n); st.hsum += __reduce_add_sync(FULL, g_h); }   // the shared copy keeps warp totals
+    __syncwarp();
     if (lane == 0) ws->st = st;
     __syncwarp();
 }
 
+// Class bits of the four ops of a uint4 and the warp's event ballot.  Written in PTX so that each step stays one
+// instruction: and / funnel shift / and (multiplier) / and+setp (-> LOP3 with predicate output) / setp.ge.and.
+__device__ __forceinline__ uint32_t scan_classify(const uint4 w, uint32_t thresh, uint32_t& f0, uint32_t& f1, uint32_t& f2, uint32_t& f3) {
+    uint32_t ballot;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 o, t, c;\n\t"
+        ".reg .pred pc, p0, p1, p2, p3;\n\t"
+        "and.b32 o, %5, 15;\n\t shf.r.wrap.b32 t, %10, %11, o;\n\t and.b32 %1, t, 0x80000001;\n\t and.b32 c, t, 0x8000;\n\t"
+        "setp.ne.u32 pc, c, 0;\n\t setp.ge.and.u32 p0, %5, %9, pc;\n\t"
+        "and.b32 o, %6, 15;\n\t shf.r.wrap.b32 t, %10, %11, o;\n\t and.b32 %2, t, 0x80000001;\n\t and.b32 c, t, 0x8000;\n\t"
+        "setp.ne.u32 pc, c, 0;\n\t setp.ge.and.u32 p1, %6, %9, pc;\n\t"
+        "and.b32 o, %7, 15;\n\t shf.r.wrap.b32 t, %10, %11, o;\n\t and.b32 %3, t, 0x80000001;\n\t and.b32 c, t, 0x8000;\n\t"
+        "setp.ne.u32 pc, c, 0;\n\t setp.ge.and.u32 p2, %7, %9, pc;\n\t"
+        "and.b32 o, %8, 15;\n\t shf.r.wrap.b32 t, %10, %11, o;\n\t and.b32 %4, t, 0x80000001;\n\t and.b32 c, t, 0x8000;\n\t"
+        "setp.ne.u32 pc, c, 0;\n\t setp.ge.and.u32 p3, %8, %9, pc;\n\t"
+        "or.pred p0, p0, p1;\n\t or.pred p2, p2, p3;\n\t or.pred p0, p0, p2;\n\t"
+        "vote.sync.ballot.b32 %0, p0, 0xffffffff;\n\t"
+        "}"
+        : "=r"(ballot), "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3)
+        : "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w), "r"(thresh), "r"((uint32_t)SCAN_K), "r"((uint32_t)(SCAN_K >> 32)));
+    return ballot;
+}
+__device__ __forceinline__ uint32_t scan_f2(uint32_t v) { return __funnelshift_r((uint32_t)SCAN_K2, (uint32_t)(SCAN_K2 >> 32), v & 15u) & SCAN_F_MASK; }
+
 #define SCAN_GROUP_S(W)                                                                                            \
     {                                                                                                              \
-        const uint32_t B0 = op_bit((W).x), B1 = op_bit((W).y), B2 = op_bit((W).z), B3 = op_bit((W).w);             \
-        const bool ev = is_event((W).x, B0, thresh) | is_event((W).y, B1, thresh) | is_event((W).z, B2, thresh) |  \
-                        is_event((W).w, B3, thresh);                                                               \
-        if (__ballot_sync(FULL, ev) == 0) {                                                                        \
-            acc_op<SUM>((W).x, B0, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).y, B1, a_ref, a_read, a_n, a_h);      \
-            acc_op<SUM>((W).z, B2, a_ref, a_read, a_n, a_h); acc_op<SUM>((W).w, B3, a_ref, a_read, a_n, a_h);      \
+        uint32_t f0, f1, f2, f3;                                                                                   \
+        if (scan_classify((W), thresh, f0, f1, f2, f3) == 0) {                                                     \
+            acc = mad_wide((W).x >> 4, f0, acc); acc = mad_wide((W).y >> 4, f1, acc);                              \
+            acc = mad_wide((W).z >> 4, f2, acc); acc = mad_wide((W).w >> 4, f3, acc);                              \
+            if (SUM) { acc2 = mad_wide((W).x >> 4, scan_f2((W).x), acc2); acc2 = mad_wide((W).y >> 4, scan_f2((W).y), acc2); \
+                       acc2 = mad_wide((W).z >> 4, scan_f2((W).z), acc2); acc2 = mad_wide((W).w >> 4, scan_f2((W).w), acc2); } \
         } else {                                                                                                   \
-            scan_events_s<SUM>((W), lane, sh, ws, a_ref, a_read);                                                  \
-            a_ref = 0; a_read = 0;                                                                                 \
+            scan_events_s<SUM>((W), lane, acc);                                                                    \
+            acc = 0;                                                                                               \
         }                                                                                                          \
     }
 
+// acc: reference (bits 0-30) / read (bits 31+) consumption of this lane since the last fold; acc2: N / H lengths of
+// the groups that took the fast path (SUM only)
 template <bool SUM>
-__device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, const ScanShared* sh, ScanWarp* ws,
-                                             uint32_t& acc_ref_out, uint32_t& acc_read_out, uint32_t& n_out, uint32_t& h_out) {
+__device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, uint64_t& acc_out, uint64_t& acc2_out) {
     const uint32_t n4 = (n + 3) >> 2;
-    const uint32_t full = (n >> 2) / 128 * 128;
-    uint32_t a_ref = 0, a_read = 0, a_n = 0, a_h = 0;
+    const uint32_t full = (n >> 2) & ~127u;
+    uint64_t acc = 0, acc2 = 0;
     uint32_t base = 0;
     for (; base < full; base += 128) {
         uint4 w[4];
@@ -312,16 +414,21 @@ __device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint3
 #pragma unroll
         for (int u = 0; u < 4; ++u) SCAN_GROUP_S(w[u])
     }
-    for (; base < n4; base += 32) {
-        const uint32_t idx = base + lane;
-        uint4 w = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
-        if (idx == n4 - 1) {
-            const uint32_t rr = n & 3u;
-            if (rr == 1) { w.y = 0; w.z = 0; w.w = 0; } else if (rr == 2) { w.z = 0; w.w = 0; } else if (rr == 3) { w.w = 0; }
+    if (base < n4) {   // ragged tail (< 128 uint4 + the partial one): all loads in flight together, words past n_cigar zeroed
+        uint4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint32_t idx = base + u * 32 + lane;
+            w[u] = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
+            if (idx == n4 - 1) {
+                const uint32_t rr = n & 3u;
+                if (rr == 1) { w[u].y = 0; w[u].z = 0; w[u].w = 0; } else if (rr == 2) { w[u].z = 0; w[u].w = 0; } else if (rr == 3) { w[u].w = 0; }
+            }
         }
-        SCAN_GROUP_S(w)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { if (base + u * 32 < n4) SCAN_GROUP_S(w[u]) }
     }
-    acc_ref_out = a_ref; acc_read_out = a_read; n_out = a_n; h_out = a_h;
+    acc_out = acc; acc2_out = acc2;
 }
 
 // query-sorted mode (SVIM_COLLECT.py:96-129): the host grouped the records by read; qs.info[i] = role | slot << 3 with
@@ -330,18 +437,14 @@ struct QsView { const uint32_t* info; const uint32_t* grp; SegSum* segsum; };
 
 template <int MINB, bool QS>
 __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
-                                                             uint32_t* cnt, QsView qs_in, int use_chunks) {
-    QsView qs = qs_in;
-    if (!QS) qs.info = nullptr;          // compile-time: the coordinate-sorted instantiation carries none of the read-group logic
-    __shared__ ScanShared sh_s;
-    __shared__ ScanWarp ws_s[8];
+                                                             uint32_t* cnt, QsView qs, int use_chunks) {
     const int lane = threadIdx.x & 31;
     const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
-    if (threadIdx.x == 0) { sh_s.p = p; sh_s.qm = qm; sh_s.qt = qt; sh_s.overflow = cnt + CNT_OVERFLOW; sh_s.holes = cnt + CNT_HOLES_MAIN; sh_s.thresh = thresh; sh_s.use_chunks = use_chunks; }
-    if (lane == 0) { ws_s[threadIdx.x >> 5].cm = SlotChunk{0, 0}; ws_s[threadIdx.x >> 5].ct = SlotChunk{0, 0}; }
+    ScanShared* sh = &g_scan_sh;
+    ScanWarp* ws = &g_scan_ws[threadIdx.x >> 5];
+    if (threadIdx.x == 0) { sh->p = p; sh->qm = qm; sh->qt = qt; sh->overflow = cnt + CNT_OVERFLOW; sh->holes = cnt + CNT_HOLES_MAIN; sh->thresh = thresh; sh->use_chunks = use_chunks; }
+    if (lane == 0) { ws->cm = SlotChunk{0, 0}; ws->ct = SlotChunk{0, 0}; }
     __syncthreads();
-    const ScanShared* sh = &sh_s;
-    ScanWarp* ws = &ws_s[threadIdx.x >> 5];
     const uint32_t n_aln = (uint32_t)a.n;
     uint32_t primaries = 0;
     for (;;) {
@@ -349,43 +452,57 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
         if (lane == 0) first = atomicAdd(cnt + CNT_NEXT_ALN, (uint32_t)SCAN_BATCH);
         first = __shfl_sync(FULL, first, 0);
         if (first >= n_aln) break;
-        const uint32_t last = min(first + SCAN_BATCH, n_aln);
-        for (uint32_t i = first; i < last; ++i) {
-            const uint32_t flag = a.flag[i];
-            bool primary; uint32_t slot = 0; bool qs_chain = false;
-            if (QS) {
-                const uint32_t info = qs.info[i];
-                if ((info & 3u) == 0) continue;
-                primary = (info & 3u) == 1; qs_chain = info & 4u; slot = info >> 3;
-            } else {
-                if ((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq) continue;
-                primary = !(flag & 0x800u);
+        // ---- the batch's record metadata: one lane per record, every field load in flight at once ----
+        if (lane < SCAN_BATCH) {
+            const uint32_t i = first + lane;
+            ScanMeta m; m.i = i; m.bits = 0; m.n = 0; m.cig = 0; m.slot = 0; m.qid = 0; m.tid = 0; m.pos = 0; m.l_seq = 0;
+            if (i < n_aln) {
+                const uint32_t flag = a.flag[i];
+                bool take, primary, summary;
+                if (QS) {
+                    const uint32_t info = qs.info[i];
+                    take = (info & 3u) != 0; primary = (info & 3u) == 1; summary = (info & 4u) != 0; m.slot = info >> 3;
+                } else {
+                    take = !((flag & 0x104u) || (int32_t)a.mapq[i] < p.min_mapq);      // SVIM_COLLECT.py:143
+                    primary = !(flag & 0x800u); summary = primary && a.sa_len[i] > 0;
+                }
+                if (take) {
+                    m.bits = 1u | (primary ? 2u : 0u) | (summary ? 4u : 0u) | ((flag & 0x10u) ? 8u : 0u);
+                    m.n = a.n_cigar[i]; m.cig = a.cigar_off[i]; m.qid = a.qname_id[i]; m.tid = a.tid[i]; m.pos = a.pos[i]; m.l_seq = a.l_seq[i];
+                    primaries += primary;
+                }
             }
-            primaries += primary;
-            const uint32_t n = a.n_cigar[i];
-            const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + a.cigar_off[i]);
+            ws->meta[lane] = m;
+        }
+        __syncwarp();
+        for (int b = 0; b < SCAN_BATCH; ++b) {
+            const uint32_t bits = ws->meta[b].bits;
+            if (!(bits & 1u)) continue;
+            const uint32_t n = ws->meta[b].n;
+            const uint4* cg = reinterpret_cast<const uint4*>(a.cigar + ws->meta[b].cig);
             if (lane == 0) {
-                ScanRec r; r.i = i; r.qid = a.qname_id[i]; r.tid = a.tid[i]; r.ref_start = a.pos[i]; r.l_seq = a.l_seq[i];
+                const uint32_t slot = ws->meta[b].slot;
                 EvState st; st.base_ref = 0; st.base_read = 0; st.n_ev = slot << 20; st.n_tw = slot << 20; st.nsum = 0; st.hsum = 0;
-                ws->r = r; ws->st = st;
+                ws->st = st; ws->cur = (uint32_t)b;
             }
             __syncwarp();
-            uint32_t acc_ref = 0, acc_read = 0, acc_n = 0, acc_h = 0;
-            const bool need_summary = QS ? qs_chain : (primary && a.sa_len[i] > 0);
-            if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
-            else scan_cigar_s<false>(cg, n, thresh, lane, sh, ws, acc_ref, acc_read, acc_n, acc_h);
+            uint64_t acc = 0, acc2 = 0;
+            const bool need_summary = bits & 4u;
+            if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, acc, acc2);
+            else scan_cigar_s<false>(cg, n, thresh, lane, acc, acc2);
             if (need_summary) {
                 const EvState st = ws->st;     // st.nsum / st.hsum: warp totals of the rare-path groups (scan_events_s)
-                const uint32_t hard = warp_sum(acc_h) + st.hsum;
+                const uint32_t hard = __reduce_add_sync(FULL, acc_hi(acc2)) + st.hsum;
                 if (hard == 0 || QS) {     // the hard-clip rule belongs to the SA reconstruction only (SVIM_COLLECT.py:47)
-                    const int64_t ref_q = st.base_ref + warp_sum(acc_ref);
-                    const int64_t rd = st.base_read + warp_sum(acc_read);
-                    const int64_t nsum = (int64_t)warp_sum(acc_n) + st.nsum;
+                    const int64_t ref_q = st.base_ref + __reduce_add_sync(FULL, acc_lo(acc));
+                    const int64_t rd = st.base_read + __reduce_add_sync(FULL, acc_hi(acc));
+                    const int64_t nsum = (int64_t)__reduce_add_sync(FULL, acc_lo(acc2)) + st.nsum;
                     if (lane == 0) {
-                        const uint32_t* c32 = a.cigar + a.cigar_off[i];
-                        const int64_t l_seq = a.l_seq[i];
+                        const ScanMeta m = ws->meta[b];
+                        const uint32_t* c32 = a.cigar + m.cig;
+                        const int64_t l_seq = m.l_seq;
                         CigarSummary cs; cigsum_init(cs);
-                        if (l_seq == 0) {
+                        if (l_seq == 0) {   // no SEQ: exact sequential summary (rare)
                             for (uint32_t k = 0; k < n; ++k) cigsum_add(cs, c32[k] & 15u, c32[k] >> 4);
                         } else {
                             cs.ref_len = ref_q + nsum; cs.qlen_h = rd + hard; cs.hard = hard; cs.n_ops = (int32_t)n;   // infer_read_length counts H (query-sorted mode keeps hard-clipped records)
@@ -394,12 +511,12 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
                             for (uint32_t j = n; j-- > 1;) { uint32_t op = c32[j] & 15u; if (op == OP_H) continue; if (op != OP_S) break; cs.trail_s += c32[j] >> 4; }
                         }
                         Seg sg; int64_t rl;
-                        cigsum_finish(cs, l_seq, a.pos[i], (flag & 0x10u) ? 1 : 0, sg, rl);
-                        if (QS) { SegSum ss; ss.ref_end = sg.ref_end; ss.q_start = sg.q_start; ss.q_end = sg.q_end; ss.read_len = rl; qs.segsum[i] = ss; }
-                        if (!QS || primary) {
+                        cigsum_finish(cs, l_seq, m.pos, (m.bits & 8u) ? 1 : 0, sg, rl);
+                        if (QS) { SegSum ss; ss.ref_end = sg.ref_end; ss.q_start = sg.q_start; ss.q_end = sg.q_end; ss.read_len = rl; qs.segsum[m.i] = ss; }
+                        if (!QS || (m.bits & 2u)) {
                             uint32_t wslot = atomicAdd(cnt + CNT_WORK, 1u);
                             if (wslot < work_cap) {
-                                ChainWork wk; wk.aln_idx = i; wk.pad = 0;
+                                ChainWork wk; wk.aln_idx = m.i; wk.pad = 0;
                                 wk.ord_sig = QS ? 0xFFF00000u : (0x80000000u | st.n_ev); wk.ord_twin = QS ? 0xFFF00000u : (0x80000000u | st.n_tw);
                                 wk.ref_end = sg.ref_end; wk.q_start = sg.q_start; wk.q_end = sg.q_end; wk.read_len = rl;
                                 work[wslot] = wk;
@@ -414,8 +531,8 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
     __syncwarp();
     flush_slots(qm, &ws->cm, lane, cnt + CNT_HOLES_MAIN);
     if (p.all_bnds) flush_slots(qt, &ws->ct, lane, cnt + CNT_HOLES_TWIN);
-    primaries = warp_sum(primaries);
-    if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
+    primaries = warp_sum(primaries);   // lanes counted their own records
+    if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries);
 }
 
 // ---- bulk-copy (TMA engine) variant of the scan ---------------------------------------------------------

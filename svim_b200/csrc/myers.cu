@@ -261,6 +261,61 @@ __device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m
     return eout;
 }
 
+// ---- two-plane (A/C/G/T) words: FMA-pipe formulation ------------------------------------------------------------
+// The ALU pipe (LOP3/SHF/IADD3, one warp instruction every two cycles per SM sub-partition) bounds the plain
+// formulation while the FMA pipe idles.  Here every 64-row word is two independent 32-row blocks chained through
+// their horizontal deltas, and whatever can be phrased as a multiply-add runs as IMAD on the FMA pipe:
+//   Eq      = P0 + c1*(P1-P0) + c2*(P2-P0) + c3*(P3-P0)      (c = one-hot of the text symbol; 3 IMAD, no LOP3)
+//   s       = (Eq|hn) & Pv + Pv                               (IMAD with multiplicand `one`)
+//   Ph<<1|hp = Ph*two + hp,  Mh<<1|hn = Mh*two + hn           (IMAD; bit 0 is free after the shift)
+// leaving 10 ALU-pipe and 6 FMA-pipe instructions per 32 cells instead of ~16 ALU.
+struct WordQ { uint32_t q0[2], d1[2], d2[2], d3[2], pv[2], mv[2]; };
+
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ void wordq_init(WordQ& w, const uint8_t* __restrict__ pat, int64_t m, int64_t row0) {
+    uint64_t pl[2], vm;
+    build_planes<2>(pat, m, row0, pl, vm);
+    const uint64_t P0 = ~pl[0] & ~pl[1] & vm, P1 = pl[0] & ~pl[1], P2 = ~pl[0] & pl[1], P3 = pl[0] & pl[1];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t p0 = (uint32_t)(P0 >> (32 * h));
+        w.q0[h] = p0; w.d1[h] = (uint32_t)(P1 >> (32 * h)) - p0; w.d2[h] = (uint32_t)(P2 >> (32 * h)) - p0; w.d3[h] = (uint32_t)(P3 >> (32 * h)) - p0;
+        w.pv[h] = 0xffffffffu; w.mv[h] = 0u;
+    }
+}
+
+__device__ __forceinline__ int wordq_vsum(const WordQ& w, int64_t m, int64_t row0) {
+    if (row0 >= m) return 0;
+    const int cnt = (m - row0) < 64 ? (int)(m - row0) : 64;
+    const uint64_t vm = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
+    const uint64_t pv = ((uint64_t)w.pv[1] << 32) | w.pv[0], mv = ((uint64_t)w.mv[1] << 32) | w.mv[0];
+    return __popcll(pv & vm) - __popcll(mv & vm);
+}
+
+// one 32-row block step; hp/hn = incoming horizontal delta (+1 / -1 flags), replaced by the outgoing one
+template <bool HI>
+__device__ __forceinline__ void block_step(uint32_t q0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t& pv_io, uint32_t& mv_io,
+                                           uint32_t c1, uint32_t c2, uint32_t c3, uint32_t one, uint32_t two, uint32_t& hp, uint32_t& hn) {
+    const uint32_t pv = pv_io, mv = mv_io;
+    const uint32_t eq = imad(c3, d3, imad(c2, d2, imad(c1, d1, q0)));
+    const uint32_t xv = eq | mv;
+    const uint32_t el = eq | hn;
+    const uint32_t s = imad(el & pv, one, pv);
+    const uint32_t xh = (s ^ pv) | el;
+    const uint32_t ph = mv | ~(xh | pv);
+    const uint32_t mh = pv & xh;
+    const uint32_t ph2 = imad(ph, two, hp), mh2 = imad(mh, two, hn);
+    if (HI) { hp = __umulhi(ph, two); hn = __umulhi(mh, two); }   // top bit via IMAD.HI (FMA pipe)
+    else { hp = ph >> 31; hn = mh >> 31; }
+    pv_io = mh2 | ~(xv | ph2);
+    mv_io = ph2 & xv;
+}
+
 // G lanes per pair, WPL words per lane; strips of G*WPL words (only G = 32 ever needs more than one strip)
 template <int G, int WPL, int NP>
 __device__ int32_t myers_fast(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
@@ -315,6 +370,69 @@ __device__ int32_t myers_fast(const uint8_t* __restrict__ pat, int64_t m, const 
     return n + vsum;
 }
 
+// two-plane variant of myers_fast on WordQ blocks (same wavefront, same packet format)
+template <int G, int WPL, bool HI>
+__device__ int32_t myers_fast_q(const uint8_t* __restrict__ pat, int64_t m, const uint32_t* __restrict__ txt32, int n,
+                                uint8_t* __restrict__ hbuf, int gl, bool valid, uint32_t one, uint32_t two) {
+    const int64_t W = valid ? ((m + 63) >> 6) : 0;
+    const int64_t STRIP = G * WPL;
+    int vsum = 0;
+    int64_t n_strips = (W + STRIP - 1) / STRIP;
+    if (G < 32) n_strips = 1;
+    for (int64_t si = 0; si < n_strips; ++si) {
+        const int64_t sb = si * STRIP;
+        const bool first_strip = (si == 0), last_strip = (si + 1 >= n_strips);
+        const int64_t ws_cnt = (W - sb) < STRIP ? (W - sb) : STRIP;
+        const int nl = valid ? (int)((ws_cnt + WPL - 1) / WPL) : 0;
+        WordQ w[WPL];
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) {
+            if (valid) wordq_init(w[k], pat, m, (sb + (int64_t)gl * WPL + k) * 64);
+            else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { w[k].q0[h] = w[k].d1[h] = w[k].d2[h] = w[k].d3[h] = 0; w[k].pv[h] = w[k].mv[h] = 0; }
+            }
+        }
+        int steps = valid ? (n + nl - 1) : 0;
+        if (G < 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
+        }
+        const bool lane_on = valid && gl < nl, head = lane_on && gl == 0;
+        uint32_t pk_out = 0;
+        uint32_t t_nxt = head ? txt32[0] : 0u;
+        uint32_t h_nxt = (head && !first_strip) ? hbuf[0] : 2u;
+        for (int s = 0; s < steps; ++s) {
+            const uint32_t recv = __shfl_up_sync(0xffffffffu, pk_out, 1, G);
+            const uint32_t t_cur = t_nxt, h_cur = h_nxt;
+            if (head && s + 1 < n) { t_nxt = txt32[s + 1]; if (G == 32 && !first_strip) h_nxt = hbuf[s + 1]; }
+            const uint32_t pk = gl == 0 ? (t_cur | (h_cur << 24)) : recv;
+            const int j = s - gl;
+            if (lane_on && (unsigned)j < (unsigned)n) {
+                // packet: byte 0 / byte 1 = 0xFF when bit 0 / bit 1 of the symbol code is set, byte 3 = hin + 1
+                const uint32_t b0 = pk & 1u, b1 = (pk >> 8) & 1u;
+                const uint32_t c3 = b0 & b1, c1 = b0 ^ c3, c2 = b1 ^ c3;
+                const uint32_t e = pk >> 24;
+                uint32_t hp = e >> 1, hn = 1u >> e;
+#pragma unroll
+                for (int k = 0; k < WPL; ++k) {
+                    block_step<HI>(w[k].q0[0], w[k].d1[0], w[k].d2[0], w[k].d3[0], w[k].pv[0], w[k].mv[0], c1, c2, c3, one, two, hp, hn);
+                    block_step<HI>(w[k].q0[1], w[k].d1[1], w[k].d2[1], w[k].d3[1], w[k].pv[1], w[k].mv[1], c1, c2, c3, one, two, hp, hn);
+                }
+                const uint32_t eo = 1u + hp - hn;
+                pk_out = (pk & 0x00ffffffu) | (eo << 24);
+                if (G == 32 && !last_strip && gl == 31) hbuf[j] = (uint8_t)eo;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < WPL; ++k) vsum += lane_on ? wordq_vsum(w[k], m, (sb + (int64_t)gl * WPL + k) * 64) : 0;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, o, G);
+    return n + vsum;
+}
+
 // ---- kernels -------------------------------------------------------------------------------------
 struct MyersArgs {
     const svim_csig* sig; const uint8_t* ins_blob; GenomeView g;
@@ -324,12 +442,14 @@ struct MyersArgs {
     uint32_t* next;                           // work cursor
     MyersWork* fallback; uint32_t* n_fallback;   // pairs that need the 8-plane kernel
     unsigned long long* cells; uint32_t* err;
+    uint32_t one, two;                        // 1 and 2, opaque to the compiler: multiplicands that keep adds/shifts on the FMA pipe
 };
 
 // explicit string pairs (unit-test entry svimgpu_edit_distance) share the kernels below through this view
 struct StringPairs { const uint8_t* blob; const int64_t* a_off; const int32_t* a_len; const int64_t* b_off; const int32_t* b_len; const uint32_t* list; };
 
-template <int G, int WPL, bool STRINGS>
+// MODE: 0 = ALU-pipe formulation, 1 = two-plane pairs on the FMA-pipe formulation, 2 = same with IMAD.HI for the top bits
+template <int G, int WPL, bool STRINGS, int MODE>
 __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
@@ -372,7 +492,10 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
         }
         // pure A/C/G/T pairs (codes 0-3) need two planes only; the choice is warp-uniform
         const bool three = __any_sync(0xffffffffu, valid && orall >= 4);
-        const int32_t ed = three ? myers_fast<G, WPL, 3>(pat, m, txt32, (int)n, hbuf, gl, valid) : myers_fast<G, WPL, 2>(pat, m, txt32, (int)n, hbuf, gl, valid);
+        int32_t ed;
+        if (three) ed = myers_fast<G, WPL, 3>(pat, m, txt32, (int)n, hbuf, gl, valid);
+        else if (MODE == 0) ed = myers_fast<G, WPL, 2>(pat, m, txt32, (int)n, hbuf, gl, valid);
+        else ed = myers_fast_q<G, WPL, MODE == 2>(pat, m, txt32, (int)n, hbuf, gl, valid, a.one, a.two);
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
@@ -446,18 +569,27 @@ static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, Stri
     a.scratch = scratch.as<uint8_t>();
     ctx->launches++;
     cudaStream_t stream = ctx->aux_stream[bin % SVIM_AUX_STREAMS];   // bins overlap: one kernel's tail is filled by the next
+    a.one = 1u; a.two = 2u;
+#define MYERS_LAUNCH(G_, W_)                                                                                     \
+    switch (ctx->myers_mode) {                                                                                   \
+        case 0: k_myers_fast<G_, W_, STRINGS, 0><<<blocks, 128, 0, stream>>>(a, sp); break;                      \
+        case 2: k_myers_fast<G_, W_, STRINGS, 2><<<blocks, 128, 0, stream>>>(a, sp); break;                      \
+        default: k_myers_fast<G_, W_, STRINGS, 1><<<blocks, 128, 0, stream>>>(a, sp); break;                     \
+    }                                                                                                            \
+    break;
     switch (bin) {
-        case 0: k_myers_fast<4, 1, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 1: k_myers_fast<4, 2, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 2: k_myers_fast<4, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 3: k_myers_fast<4, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 4: k_myers_fast<8, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 5: k_myers_fast<8, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 6: k_myers_fast<16, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 7: k_myers_fast<16, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 8: k_myers_fast<32, 3, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
-        case 9: k_myers_fast<32, 4, STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;
+        case 0: MYERS_LAUNCH(4, 1)
+        case 1: MYERS_LAUNCH(4, 2)
+        case 2: MYERS_LAUNCH(4, 3)
+        case 3: MYERS_LAUNCH(4, 4)
+        case 4: MYERS_LAUNCH(8, 3)
+        case 5: MYERS_LAUNCH(8, 4)
+        case 6: MYERS_LAUNCH(16, 3)
+        case 7: MYERS_LAUNCH(16, 4)
+        case 8: MYERS_LAUNCH(32, 3)
+        case 9: MYERS_LAUNCH(32, 4)
         default: k_myers_generic<STRINGS><<<blocks, 128, 0, stream>>>(a, sp); break;   // MYERS_BINS: any bytes
     }
+#undef MYERS_LAUNCH
     return cudaGetLastError();
 }
