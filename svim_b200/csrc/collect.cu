@@ -69,7 +69,7 @@ struct SlotChunk { uint32_t base, left; };
 
 __device__ __forceinline__ void mark_hole(svim_sig& r) { r.aln_idx = 0xffffffffu; r.ordinal = 0xffffffffu; r.type = 0xff; }
 
-__device__ __forceinline__ uint32_t reserve_slots(const SigQueue& q, SlotChunk* c, uint32_t need, int lane, uint32_t* holes) {
+__device__ __noinline__ uint32_t reserve_slots(const SigQueue& q, SlotChunk* c, uint32_t need, int lane, uint32_t* holes) {
     uint32_t base = c->base; const uint32_t left = c->left;
     __syncwarp();
     if (left >= need) { if (lane == 0) { c->base = base + need; c->left = left - need; } __syncwarp(); return base; }
@@ -290,71 +290,72 @@ __device__ __forceinline__ uint32_t acc_hi(uint64_t acc) { return (uint32_t)(acc
 
 // Rare path: a 128-op group with at least one SV-sized I/D.  Warp reductions (redux.sync) give the consumption before
 // each event lane; event lanes are visited in order, so ordinals and queue slots stay in emission order.
-// `acc` = the lane's consumption since the last fold.
-template <bool SUM>
-__device__ __noinline__ void scan_events_s(const uint4 w, int lane, uint64_t acc) {
+// `acc` = the lane's consumption since the last fold.  Kept small on purpose (one emission body, no unrolling): the
+// scan's hot loop shares the instruction cache with it.
+__device__ __noinline__ void scan_events_s(const uint4 w, int lane, uint64_t acc, bool sum) {
     const ScanShared* sh = &g_scan_sh;
     ScanWarp* ws = &g_scan_ws[threadIdx.x >> 5];
     const uint32_t thresh = sh->thresh;
-    const uint32_t v[4] = {w.x, w.y, w.z, w.w};
-    uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0, pre_ref[4], pre_read[4];
-    uint32_t evbits = 0, delbits = 0;
+    uint32_t g_ref = 0, g_read = 0, g_n = 0, g_h = 0, n_evt = 0, n_del = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const uint32_t B = op_bit(v[k]);
-        pre_ref[k] = g_ref; pre_read[k] = g_read;
-        acc_op<SUM>(v[k], B, g_ref, g_read, g_n, g_h);
-        if (is_event(v[k], B, thresh)) { evbits |= 1u << k; if ((v[k] & 15u) == OP_D) delbits |= 1u << k; }
+        const uint32_t vk = k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w;
+        const uint32_t B = op_bit(vk);
+        acc_op<true>(vk, B, g_ref, g_read, g_n, g_h);
+        if (is_event(vk, B, thresh)) { ++n_evt; n_del += (vk & 15u) == OP_D; }
     }
-    unsigned m = __ballot_sync(FULL, evbits != 0);
+    unsigned m = __ballot_sync(FULL, n_evt != 0);
     EvState st = ws->st;
     const ScanMeta r = ws->meta[ws->cur];
     const int all_bnds = sh->p.all_bnds;
     __syncwarp();
     st.base_ref += __reduce_add_sync(FULL, acc_lo(acc)); st.base_read += __reduce_add_sync(FULL, acc_hi(acc));
+#pragma unroll 1
     while (m) {
         const int L = __ffs(m) - 1; m &= m - 1;
         const uint32_t ex_ref = __reduce_add_sync(FULL, lane < L ? g_ref : 0u);
         const uint32_t ex_read = __reduce_add_sync(FULL, lane < L ? g_read : 0u);
-        const uint32_t evL = __shfl_sync(FULL, evbits, L), delL = __shfl_sync(FULL, delbits, L);
-        const uint32_t cntL = __popc(evL), ndel = all_bnds ? __popc(delL) : 0u;
-        uint32_t slot, slot_t = 0;
+        const uint32_t cntL = __shfl_sync(FULL, n_evt, L);
+        const uint32_t ndel = all_bnds ? __shfl_sync(FULL, n_del, L) : 0u;
+        uint32_t slot = 0, slot_t = 0;
         if (sh->use_chunks) { slot = reserve_slots(sh->qm, &ws->cm, cntL, lane, sh->holes); if (ndel) slot_t = reserve_slots(sh->qt, &ws->ct, ndel, lane, sh->holes + 1); }
-        else { slot = 0; if (lane == L) { slot = atomicAdd(sh->qm.count, cntL); if (ndel) slot_t = atomicAdd(sh->qt.count, ndel); } }
+        else if (lane == L) { slot = atomicAdd(sh->qm.count, cntL); if (ndel) slot_t = atomicAdd(sh->qt.count, ndel); }
         if (lane == L) {
-            uint32_t ord = st.n_ev, tord = st.n_tw;
-#pragma unroll
+            uint32_t ord = st.n_ev, tord = st.n_tw, cr = 0, cq = 0, dn = 0, dh = 0;
+#pragma unroll 1
             for (int k = 0; k < 4; ++k) {
-                if (!((evbits >> k) & 1u)) continue;
-                const uint32_t op = v[k] & 15u; const int64_t len = v[k] >> 4;
-                const int64_t pr = st.base_ref + ex_ref + pre_ref[k];
-                const int64_t pq = st.base_read + ex_read + pre_read[k];
-                svim_sig s; memset(&s, 0, sizeof(s));
-                s.contig1 = r.tid; s.contig2 = -1; s.start = (int32_t)(r.pos + pr); s.end = (int32_t)(r.pos + pr + len);
-                s.aln_idx = r.i; s.qname_id = r.qid; s.ordinal = ord++;
-                if (op == OP_D) {
-                    s.type = SVIM_DEL;
-                    if (slot < sh->qm.cap) sh->qm.recs[slot] = s; else atomicExch(sh->overflow, 1u);
-                    ++slot;
-                    if (all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
-                        svim_sig t = s; t.type = SVIM_BND; t.contig2 = r.tid; t.pos = s.end; t.end = s.start + 1; t.ordinal = tord++;
-                        if (len == 0) { t.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
-                        if (slot_t < sh->qt.cap) sh->qt.recs[slot_t] = t; else atomicExch(sh->overflow, 1u);
-                        ++slot_t;
+                const uint32_t vk = k == 0 ? w.x : k == 1 ? w.y : k == 2 ? w.z : w.w;
+                const uint32_t B = op_bit(vk);
+                if (is_event(vk, B, thresh)) {
+                    const int64_t len = vk >> 4;
+                    const int64_t pr = st.base_ref + ex_ref + cr;
+                    const int64_t pq = st.base_read + ex_read + cq;
+                    svim_sig s; memset(&s, 0, sizeof(s));
+                    s.contig1 = r.tid; s.contig2 = -1; s.start = (int32_t)(r.pos + pr); s.end = (int32_t)(r.pos + pr + len);
+                    s.aln_idx = r.i; s.qname_id = r.qid; s.ordinal = ord++;
+                    if ((vk & 15u) == OP_D) {
+                        s.type = SVIM_DEL;
+                        if (all_bnds) {   // SVIM_intra.py:43-44 (same contig, start < end: already canonical)
+                            svim_sig t = s; t.type = SVIM_BND; t.contig2 = r.tid; t.pos = s.end; t.end = s.start + 1; t.ordinal = tord++;
+                            if (len == 0) { t.flags = SVIM_F_DIR1_REV | SVIM_F_DIR2_REV; }   // pos1 == pos2: the else-branch flips both directions
+                            if (slot_t < sh->qt.cap) sh->qt.recs[slot_t] = t; else atomicExch(sh->overflow, 1u);
+                            ++slot_t;
+                        }
+                    } else {
+                        s.type = SVIM_INS;
+                        int64_t lo, hi; py_slice(pq, len, (int64_t)r.l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
+                        s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
                     }
-                } else {
-                    s.type = SVIM_INS;
-                    int64_t lo, hi; py_slice(pq, len, (int64_t)r.l_seq, lo, hi);   // query_sequence[pos_read:pos_read+len]
-                    s.seq_off = (uint64_t)lo; s.seq_len = (uint32_t)(hi - lo);
                     if (slot < sh->qm.cap) sh->qm.recs[slot] = s; else atomicExch(sh->overflow, 1u);
                     ++slot;
                 }
+                acc_op<true>(vk, B, cr, cq, dn, dh);
             }
         }
         st.n_ev += cntL; st.n_tw += ndel;
     }
     st.base_ref += __reduce_add_sync(FULL, g_ref); st.base_read += __reduce_add_sync(FULL, g_read);
-    if (SUM) { st.nsum += __reduce_add_sync(FULL, g_n); st.hsum += __reduce_add_sync(FULL, g_h); }   // the shared copy keeps warp totals
+    if (sum) { st.nsum += __reduce_add_sync(FULL, g_n); st.hsum += __reduce_add_sync(FULL, g_h); }   // the shared copy keeps warp totals
     __syncwarp();
     if (lane == 0) ws->st = st;
     __syncwarp();
@@ -391,42 +392,46 @@ __device__ __forceinline__ uint32_t scan_f2(uint32_t v) { return __funnelshift_r
         if (scan_classify((W), thresh, f0, f1, f2, f3) == 0) {                                                     \
             acc = mad_wide((W).x >> 4, f0, acc); acc = mad_wide((W).y >> 4, f1, acc);                              \
             acc = mad_wide((W).z >> 4, f2, acc); acc = mad_wide((W).w >> 4, f3, acc);                              \
-            if (SUM) { acc2 = mad_wide((W).x >> 4, scan_f2((W).x), acc2); acc2 = mad_wide((W).y >> 4, scan_f2((W).y), acc2); \
+            if (sum) { acc2 = mad_wide((W).x >> 4, scan_f2((W).x), acc2); acc2 = mad_wide((W).y >> 4, scan_f2((W).y), acc2); \
                        acc2 = mad_wide((W).z >> 4, scan_f2((W).z), acc2); acc2 = mad_wide((W).w >> 4, scan_f2((W).w), acc2); } \
         } else {                                                                                                   \
-            scan_events_s<SUM>((W), lane, acc);                                                                    \
+            scan_events_s((W), lane, acc, sum);                                                                    \
             acc = 0;                                                                                               \
         }                                                                                                          \
     }
 
 // acc: reference (bits 0-30) / read (bits 31+) consumption of this lane since the last fold; acc2: N / H lengths of
-// the groups that took the fast path (SUM only)
-template <bool SUM>
-__device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, uint64_t& acc_out, uint64_t& acc2_out) {
+// the groups that took the fast path (`sum`: records whose summary feeds the split-read analysis).
+// No unrolling beyond one 4-load block and a small rare path: the instruction cache is part of the budget.
+// LD = 128-bit loads in flight per lane
+template <int LD>
+__device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint32_t n, uint32_t thresh, int lane, bool sum, uint64_t& acc_out, uint64_t& acc2_out) {
     const uint32_t n4 = (n + 3) >> 2;
-    const uint32_t full = (n >> 2) & ~127u;
+    const uint32_t full = (n >> 2) / (LD * 32) * (LD * 32);
     uint64_t acc = 0, acc2 = 0;
     uint32_t base = 0;
-    for (; base < full; base += 128) {
-        uint4 w[4];
+#pragma unroll 1
+    for (; base < full; base += LD * 32) {
+        uint4 w[LD];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
+        for (int u = 0; u < LD; ++u) w[u] = __ldcs(cg + base + u * 32 + lane);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) SCAN_GROUP_S(w[u])
+        for (int u = 0; u < LD; ++u) SCAN_GROUP_S(w[u])
     }
-    if (base < n4) {   // ragged tail (< 128 uint4 + the partial one): all loads in flight together, words past n_cigar zeroed
-        uint4 w[4];
+    const uint32_t last = n4 - 1, rr = n & 3u;
+#pragma unroll 1
+    for (; base < n4; base += LD * 32) {   // ragged tail: loads in flight together, words past n_cigar zeroed
+        uint4 w[LD];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < LD; ++u) {
             const uint32_t idx = base + u * 32 + lane;
-            w[u] = (idx < n4) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
-            if (idx == n4 - 1) {
-                const uint32_t rr = n & 3u;
-                if (rr == 1) { w[u].y = 0; w[u].z = 0; w[u].w = 0; } else if (rr == 2) { w[u].z = 0; w[u].w = 0; } else if (rr == 3) { w[u].w = 0; }
-            }
+            uint4 t = (idx <= last) ? __ldcs(cg + idx) : make_uint4(0, 0, 0, 0);
+            const uint32_t valid = (idx == last && rr) ? rr : 4u;
+            t.y = valid > 1 ? t.y : 0u; t.z = valid > 2 ? t.z : 0u; t.w = valid > 3 ? t.w : 0u;
+            w[u] = t;
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { if (base + u * 32 < n4) SCAN_GROUP_S(w[u]) }
+        for (int u = 0; u < LD; ++u) { if (u == 0 || base + u * 32 < n4) SCAN_GROUP_S(w[u]) }
     }
     acc_out = acc; acc2_out = acc2;
 }
@@ -435,11 +440,10 @@ __device__ __forceinline__ void scan_cigar_s(const uint4* __restrict__ cg, uint3
 // role 0 = skip, 1 = the read's only primary, 2 = good supplementary, bit 2 = the read has segments to chain.
 struct QsView { const uint32_t* info; const uint32_t* grp; SegSum* segsum; };
 
-template <int MINB, bool QS>
+template <int MINB, bool QS, int LD>
 __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParams p, SigQueue qm, SigQueue qt, ChainWork* work, uint32_t work_cap,
-                                                             uint32_t* cnt, QsView qs, int use_chunks) {
+                                                             uint32_t* cnt, QsView qs, int use_chunks, uint32_t thresh) {
     const int lane = threadIdx.x & 31;
-    const uint32_t thresh = p.min_sv <= 0 ? 0u : (p.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)p.min_sv << 4));
     ScanShared* sh = &g_scan_sh;
     ScanWarp* ws = &g_scan_ws[threadIdx.x >> 5];
     if (threadIdx.x == 0) { sh->p = p; sh->qm = qm; sh->qt = qt; sh->overflow = cnt + CNT_OVERFLOW; sh->holes = cnt + CNT_HOLES_MAIN; sh->thresh = thresh; sh->use_chunks = use_chunks; }
@@ -488,8 +492,7 @@ __global__ void __launch_bounds__(256, MINB) k_cigar_scan_s(DevSoa a, ChainParam
             __syncwarp();
             uint64_t acc = 0, acc2 = 0;
             const bool need_summary = bits & 4u;
-            if (need_summary) scan_cigar_s<true>(cg, n, thresh, lane, acc, acc2);
-            else scan_cigar_s<false>(cg, n, thresh, lane, acc, acc2);
+            scan_cigar_s<LD>(cg, n, thresh, lane, need_summary, acc, acc2);
             if (need_summary) {
                 const EvState st = ws->st;     // st.nsum / st.hsum: warp totals of the rare-path groups (scan_events_s)
                 const uint32_t hard = __reduce_add_sync(FULL, acc_hi(acc2)) + st.hsum;
@@ -943,42 +946,32 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
                 QsView qsv{nullptr, nullptr, nullptr};
                 if (ctx->qs_mode) qsv = QsView{ctx->d_qs_info.as<uint32_t>(), ctx->d_qs_grp.as<uint32_t>(), ctx->d_qs_segsum.as<SegSum>()};
                 const int variant = ctx->qs_mode ? 0 : ctx->scan_variant;   // the query-sorted mode lives in the default kernel only
-                if (variant == 1) {   // cp.async.bulk ring (TMA engine)
+                const uint32_t thresh = cp.min_sv <= 0 ? 0u : (cp.min_sv >= (1 << 28) ? 0xffffffffu : ((uint32_t)cp.min_sv << 4));
+#define SCAN_S_LAUNCH(MB, QSF, LDN)                                                                                                     \
+    { ctx->launches++; k_cigar_scan_s<MB, QSF, LDN><<<dev_sms * MB * 2, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), \
+                                                       (uint32_t)n + 1, ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks, thresh); }
+#define SCAN_LEGACY_LAUNCH(UN, MB)                                                                                                      \
+    { ctx->launches++; k_cigar_scan<UN, MB><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1, \
+                                                                          ctx->d_counters.as<uint32_t>()); }
+                if (ctx->qs_mode) SCAN_S_LAUNCH(4, true, 4)                  // query-sorted instantiation of the default kernel
+                else if (variant == 0) SCAN_S_LAUNCH(4, false, 4)            // DEFAULT: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers, no spills in the loop)
+                else if (variant == 1) {                                     // experiment: cp.async.bulk ring (TMA engine)
                     const size_t smem = (size_t)SCAN_BULK_WARPS * SCAN_STAGES * SCAN_BLOCK_U4 * 16 + (size_t)SCAN_BULK_WARPS * SCAN_STAGES * 8;
                     SVIM_CUDA(cudaFuncSetAttribute(k_cigar_scan_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     { ctx->launches++; k_cigar_scan_bulk<<<dev_sms * 3, 32 * SCAN_BULK_WARPS, smem, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (variant == 2) {   // experiment: 8 loads in flight per lane, 2 CTAs/SM
-                    { ctx->launches++; k_cigar_scan<8, 2><<<dev_sms * 6, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (variant == 3) {   // experiment: 2 loads per lane, 4 CTAs/SM
-                    { ctx->launches++; k_cigar_scan<2, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (variant == 4) {   // experiment: 4 loads per lane, 3 CTAs/SM (80 registers) — the round-1 v2..v5 kernel
-                    { ctx->launches++; k_cigar_scan<4, 3><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
-                } else if (variant == 7) {   // experiment: rare-path state in shared memory, 5 CTAs/SM
-                    { ctx->launches++; k_cigar_scan_s<5, false><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
-                } else if (variant == 8) {   // experiment: rare-path state in shared memory, 4 CTAs/SM
-                    { ctx->launches++; k_cigar_scan_s<4, false><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                  ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
-                } else if (ctx->qs_mode) {      // query-sorted instantiation of the default kernel
-                    { ctx->launches++; k_cigar_scan_s<6, true><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                         ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
-                } else if (variant == 0 || variant == 9) {   // DEFAULT: rare-path state in shared memory, 6 CTAs/SM: 0.78 of the measured HBM peak
-                    { ctx->launches++; k_cigar_scan_s<6, false><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>(), qsv, ctx->scan_chunks); }
-                } else if (variant == 5) {   // experiment: 5 CTAs/SM
-                    { ctx->launches++; k_cigar_scan<4, 5><<<dev_sms * 10, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else if (variant == 6) {   // experiment: 6 CTAs/SM
-                    { ctx->launches++; k_cigar_scan<4, 6><<<dev_sms * 12, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                    ctx->d_counters.as<uint32_t>()); }
-                } else {                               // variant 10+: 4 x 128-bit loads per lane, 4 CTAs/SM (64 registers): 0.74 of the measured HBM peak
-                    { ctx->launches++; k_cigar_scan<4, 4><<<dev_sms * 8, 256, 0, st>>>(ctx->soa, cp, qm, qt, ctx->d_work.as<ChainWork>(), (uint32_t)n + 1,
-                                                                   ctx->d_counters.as<uint32_t>()); }
                 }
+                else if (variant == 4) SCAN_LEGACY_LAUNCH(4, 3)              // the round-1 v2..v5 kernel (80 registers, plain LOP3/IADD classification)
+                else if (variant == 7) SCAN_S_LAUNCH(5, false, 4)            // experiments: occupancy x loads in flight
+                else if (variant == 8) SCAN_S_LAUNCH(6, false, 4)
+                else if (variant == 11) SCAN_S_LAUNCH(6, false, 2)
+                else if (variant == 12) SCAN_S_LAUNCH(8, false, 2)
+                else if (variant == 13) SCAN_S_LAUNCH(5, false, 3)
+                else if (variant == 14) SCAN_S_LAUNCH(6, false, 3)
+                else if (variant == 15) SCAN_S_LAUNCH(3, false, 4)
+                else SCAN_LEGACY_LAUNCH(4, 4)                                // variant 10: the legacy kernel at 4 CTAs/SM
+#undef SCAN_S_LAUNCH
+#undef SCAN_LEGACY_LAUNCH
             }
         }
         SVIM_CUDA(cudaGetLastError());
