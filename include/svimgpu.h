@@ -132,7 +132,10 @@ typedef struct {
     int64_t n_partitions[6], n_clusters[6], large_partitions[6], duplicate_signatures[6];
     int64_t n_members;            /* total member indices */
     int64_t n_clusters_total;
-    int64_t myers_pairs, myers_cells;
+    int64_t myers_pairs, myers_cells;          /* edit distances read / cells of their full DP matrices */
+    int64_t myers_banded_pairs;                /* of those, scheduled on the banded first pass ...            */
+    int64_t myers_retry_pairs;                 /* ... and handed over to the unbanded kernels (bound exceeded) */
+    int64_t myers_band_cells;                  /* cells the banded pass computed                              */
 } svim_cluster_stats;
 
 typedef struct {

@@ -70,7 +70,8 @@ assert SIG_DTYPE.itemsize == 48 and CSIG_DTYPE.itemsize == 64 and CLUSTER_DTYPE.
 class ClusterStats(C.Structure):
     _fields_ = [("n_partitions", C.c_int64 * 6), ("n_clusters", C.c_int64 * 6), ("large_partitions", C.c_int64 * 6),
                 ("duplicate_signatures", C.c_int64 * 6), ("n_members", C.c_int64), ("n_clusters_total", C.c_int64),
-                ("myers_pairs", C.c_int64), ("myers_cells", C.c_int64)]
+                ("myers_pairs", C.c_int64), ("myers_cells", C.c_int64),
+                ("myers_banded_pairs", C.c_int64), ("myers_retry_pairs", C.c_int64), ("myers_band_cells", C.c_int64)]
 
 
 class CollectStats(C.Structure):

@@ -41,6 +41,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (const char* v = getenv("SVIM_SCAN_VARIANT")) ctx->scan_variant = atoi(v);
     if (const char* v = getenv("SVIM_SCAN_CHUNKS")) ctx->scan_chunks = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_MODE")) ctx->myers_mode = atoi(v);
+    if (const char* v = getenv("SVIM_MYERS_BAND")) { int num = 0, add = 24; if (sscanf(v, "%d,%d", &num, &add) >= 1) { ctx->myers_band_num = num; ctx->myers_band_add = add; } }
     *out = ctx;
     return 0;
 }
@@ -60,7 +61,8 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3]};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
-    for (int i = 0; i < 12; ++i) ctx->d_myers_scratch[i].release();
+    for (int i = 0; i < 24; ++i) ctx->d_myers_scratch[i].release();
+    ctx->d_myers_ctl.release();
     ctx->d_stage.release(); ctx->d_stage_off.release();
     ctx->d_qs_info.release(); ctx->d_qs_grp.release(); ctx->d_qs_segsum.release(); ctx->d_qs_mem_off.release(); ctx->d_qs_mem_idx.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -374,22 +376,29 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
                           const int32_t* b_len, int32_t* out) {
     if (!ctx || n_pairs < 0) return SVIMGPU_ERR_ARG;
     if (n_pairs == 0) return 0;
+    if (n_pairs >= 0x7fffffff) return SVIMGPU_ERR_LIMIT;
     cudaSetDevice(ctx->device);
     int64_t blob_bytes = 0, maxlen = 16;
-    std::vector<uint32_t> lists[MYERS_BINS];
+    // same scheduling as the pipeline (k_ins_pairs): banded shape if the band policy gives a smaller one, else the pattern's bin
+    std::vector<uint32_t> lists[2 * MYERS_BINS];
+    MyersPlan pl; memset(&pl, 0, sizeof(pl));
     for (int64_t i = 0; i < n_pairs; ++i) {
         blob_bytes = std::max<int64_t>(blob_bytes, std::max(a_off[i] + a_len[i], b_off[i] + b_len[i]));
-        const int64_t m = std::max(a_len[i], b_len[i]);
+        const int64_t m = std::max(a_len[i], b_len[i]), n = std::min(a_len[i], b_len[i]);
         maxlen = std::max<int64_t>(maxlen, m);
-        lists[myers_bin_of(m)].push_back((uint32_t)i);   // same binning as the pipeline (k_ins_pairs)
+        const int band = myers_band_bin(m, n, ctx->myers_band_num, ctx->myers_band_add);
+        if (band >= 0) { lists[MYERS_BINS + band].push_back((uint32_t)i); pl.retry_cap[myers_bin_of(m)]++; }
+        else lists[myers_bin_of(m)].push_back((uint32_t)i);
     }
     maxlen = (maxlen + 15) & ~15ll;
-    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_next, d_list, d_fb, d_misc;
+    std::vector<uint32_t> flat; flat.reserve((size_t)n_pairs);
+    for (int q = 0; q < 2 * MYERS_BINS; ++q) { pl.off[q] = (uint32_t)flat.size(); pl.cnt[q] = (uint32_t)lists[q].size(); flat.insert(flat.end(), lists[q].begin(), lists[q].end()); }
+    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_ctl, d_list, d_fb, d_retry, d_misc;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     chk(d_blob.ensure((size_t)blob_bytes + 16)); chk(d_ao.ensure((size_t)n_pairs * 8)); chk(d_al.ensure((size_t)n_pairs * 4)); chk(d_bo.ensure((size_t)n_pairs * 8));
-    chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_next.ensure(64 * 4)); chk(d_list.ensure((size_t)n_pairs * 4));
-    chk(d_fb.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_misc.ensure(64));
+    chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_ctl.ensure(MYERS_CTL_N * 4)); chk(d_list.ensure((size_t)n_pairs * 4));
+    chk(d_fb.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_retry.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_misc.ensure(64));
     uint32_t h_err = 0;
     if (e == cudaSuccess) {
         chk(cudaMemcpyAsync(d_blob.p, blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -397,37 +406,19 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         chk(cudaMemcpyAsync(d_al.p, a_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bo.p, b_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bl.p, b_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
-        chk(cudaMemsetAsync(d_next.p, 0, 64 * 4, ctx->stream)); chk(cudaMemsetAsync(d_misc.p, 0, 64, ctx->stream));
-        uint32_t* nx = d_next.as<uint32_t>();
-        MyersArgs ma{nullptr, nullptr, GenomeView{nullptr, nullptr, 0, nullptr, 0}, nullptr, 0, d_out.as<int32_t>(), nullptr, maxlen, nullptr,
-                     d_fb.as<MyersWork>(), nx + 32, (unsigned long long*)d_misc.p, (uint32_t*)d_misc.p + 4};
-        uint32_t off = 0;
-        chk(myers_fork(ctx));
-        for (int bin = 0; bin < MYERS_BINS && e == cudaSuccess; ++bin) {
-            const uint32_t nl = (uint32_t)lists[bin].size();
-            if (!nl) continue;
-            uint32_t* dl = d_list.as<uint32_t>() + off; off += nl;
-            chk(cudaMemcpyAsync(dl, lists[bin].data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->aux_stream[bin % SVIM_AUX_STREAMS]));
-            StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), dl};
-            ma.n_work = nl; ma.next = nx + bin; ma.maxlen = maxlen;
-            chk(myers_launch_bin<true>(ctx, bin, ma, sp, ctx->d_myers_scratch[bin], 148));
-        }
-        chk(myers_join(ctx));
-        uint32_t n_fb = 0;
-        chk(cudaMemcpyAsync(&n_fb, nx + 32, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        chk(cudaStreamSynchronize(ctx->stream));
-        if (e == cudaSuccess && n_fb > 0) {   // pairs with bytes outside the 3-plane code space
-            chk(myers_fork(ctx));
-            StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
-            ma.work = d_fb.as<MyersWork>(); ma.n_work = n_fb; ma.next = nx + 40; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
-            chk(myers_launch_bin<true>(ctx, MYERS_BINS, ma, sp, ctx->d_myers_scratch[MYERS_BINS], 148));
-            chk(myers_join(ctx));
-        }
+        chk(cudaMemcpyAsync(d_list.p, flat.data(), (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        chk(cudaMemsetAsync(d_ctl.p, 0, MYERS_CTL_N * 4, ctx->stream)); chk(cudaMemsetAsync(d_misc.p, 0, 64, ctx->stream));
+        MyersArgs ma; memset(&ma, 0, sizeof(ma));
+        ma.ed_out = d_out.as<int32_t>(); ma.maxlen = maxlen; ma.fallback = d_fb.as<MyersWork>();
+        ma.cells = (unsigned long long*)d_misc.p; ma.err = (uint32_t*)d_misc.p + 4; ma.band_cells = (unsigned long long*)d_misc.p + 4;
+        ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;
+        StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
+        chk(myers_run_plan<true>(ctx, pl, ma, sp, nullptr, d_list.as<uint32_t>(), d_retry.as<MyersWork>(), d_ctl.as<uint32_t>(), maxlen, 148));
         chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaMemcpyAsync(&h_err, (uint32_t*)d_misc.p + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaStreamSynchronize(ctx->stream));
     }
-    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_next, &d_list, &d_fb, &d_misc};
+    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_ctl, &d_list, &d_fb, &d_retry, &d_misc};
     for (DevBuf* b : all) b->release();
     if (e != cudaSuccess) { ctx->set_error(SVIMGPU_ERR_CUDA, "edit_distance: %s", cudaGetErrorString(e)); return SVIMGPU_ERR_CUDA; }
     if (h_err) { ctx->set_error(SVIMGPU_ERR_LIMIT, "edit_distance: internal length bound exceeded (%u)", h_err); return SVIMGPU_ERR_LIMIT; }

@@ -253,12 +253,13 @@ __global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
     if (__any_sync(FULL, err)) { if (lane == 0) atomicExch(a.err, 1u); }
 }
 
-// INS partitions: list the pairs whose edit distance will be read (gate at :70 passes), binned by the
-// length of the longer haplotype.  mode 0 counts per bin, mode 1 fills `work` at the bin cursors.
+// INS partitions: list the pairs whose edit distance will be read (gate at :70 passes) and schedule them: list q < 10 =
+// unbanded bin by pattern length, 10 + b = banded first pass of shape b (myers_band_bin).  mode 0 counts per list (and, per
+// unbanded bin, the banded pairs that may be handed over to it), mode 1 fills `work` at the list cursors.
 __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint8_t* ins_blob, GenomeView g, const uint32_t* samp_off,
                                                     const uint32_t* samp_idx, const uint32_t* plist, uint32_t n_list, const uint64_t* pair_off,
                                                     ClusterParams cp, int mode, MyersWork* work, uint64_t* work_key, uint32_t* bin_cursor,
-                                                    uint32_t* err) {
+                                                    uint32_t* retry_cap, int32_t band_num, int32_t band_add, uint32_t* err) {
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_list) return;
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
     int i = 0, rowstart = 0;
     for (int64_t q0 = 0; q0 < npairs; q0 += 32) {
         const int64_t q = q0 + lane;
-        int bin = -1; uint32_t pa = 0, pb = 0, cost = 0;
+        int bin = -1, rbin = -1; uint32_t pa = 0, pb = 0, cost = 0;
         if (q < npairs) {
             while (q >= rowstart + (m - 1 - i)) { rowstart += m - 1 - i; ++i; }
             const int j = i + 1 + (int)(q - rowstart);
@@ -280,14 +281,21 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
                 HapSource ha, hb;
                 if (pair_haps(a, b, ins_blob, g, ha, hb)) {
                     const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
-                    bin = myers_bin_of(la > lb ? la : lb);
-                    const uint64_t cells = (uint64_t)la * (uint64_t)lb;
-                    cost = cells >> 6 > 0xffffffffull ? 0xffffffffu : (uint32_t)(cells >> 6);
+                    const int64_t lm = la > lb ? la : lb, ln = la > lb ? lb : la;
+                    const int band = myers_band_bin(lm, ln, band_num, band_add);
+                    if (band >= 0) {
+                        bin = MYERS_BINS + band; rbin = myers_bin_of(lm);
+                        cost = (uint32_t)(ln + (lm >> 6));          // ~ wavefront steps of the banded pass
+                    } else {
+                        bin = myers_bin_of(lm);
+                        const uint64_t cells = (uint64_t)la * (uint64_t)lb;
+                        cost = cells >> 6 > 0xffffffffull ? 0xffffffffu : (uint32_t)(cells >> 6);
+                    }
                 } else { atomicExch(err, 1u); }
             }
         }
 #pragma unroll
-        for (int bb = 0; bb < MYERS_BINS; ++bb) {
+        for (int bb = 0; bb < 2 * MYERS_BINS; ++bb) {
             const unsigned msk = __ballot_sync(FULL, bin == bb);
             if (!msk) continue;
             uint32_t base = 0;
@@ -296,7 +304,14 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
             if (mode == 1 && bin == bb) {
                 const uint32_t at = base + __popc(msk & ((1u << lane) - 1));
                 MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[at] = wk;
-                work_key[at] = ((uint64_t)bb << 32) | (uint64_t)(0xffffffffu - cost);   // longest pairs first inside a bin (LPT)
+                work_key[at] = ((uint64_t)bb << 32) | (uint64_t)(0xffffffffu - cost);   // longest pairs first inside a list (LPT)
+            }
+        }
+        if (mode == 0 && __any_sync(FULL, rbin >= 0)) {
+#pragma unroll
+            for (int bb = 0; bb < MYERS_BINS; ++bb) {
+                const unsigned msk = __ballot_sync(FULL, rbin == bb);
+                if (msk && lane == (__ffs(msk) - 1)) atomicAdd(retry_cap + bb, (uint32_t)__popc(msk));
             }
         }
     }
@@ -539,61 +554,58 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         const int64_t maxlen = ((ctx->cluster_max_ins_len + (int64_t)ceil(fabs(2.0 * cp.cluster_max_distance * cp.pos_norm)) + 64) + 15) & ~15ll;
         GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs, ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
         if (!ctx->d_genome.p) { gv.n = 0; }
-        uint32_t* d_bins = d_misc + 16;        // [16..26) bin cursors; [32] n_fallback, [33..44) per-bin work cursors
-        uint32_t bin_cnt[MYERS_BINS] = {0};
+        SVIM_CUDA(ctx->d_myers_ctl.ensure(MYERS_CTL_N * 4));
+        uint32_t* d_ctl = ctx->d_myers_ctl.as<uint32_t>();   // [0,20) list cursors, [20,30) hand-over capacities, [32..) see MYERS_CTL_*
+        uint32_t h_ctl[32] = {0};
         const uint32_t pblocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
         {
             StageTimer t(ctx, T_PAIRS);
-            SVIM_CUDA(cudaMemsetAsync(d_bins, 0, 16 * 4, st));
+            SVIM_CUDA(cudaMemsetAsync(d_ctl, 0, MYERS_CTL_N * 4, st));
             { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_bins, d_misc + 9); }
-            SVIM_CUDA(cudaMemcpyAsync(bin_cnt, d_bins, MYERS_BINS * 4, cudaMemcpyDeviceToHost, st));
+                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_ctl, d_ctl + 20,
+                                                ctx->myers_band_num, ctx->myers_band_add, d_misc + 9); }
+            SVIM_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, 32 * 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
         }
-        uint32_t bin_off[MYERS_BINS + 1] = {0};
-        for (int bb = 0; bb < MYERS_BINS; ++bb) bin_off[bb + 1] = bin_off[bb] + bin_cnt[bb];
-        const uint32_t n_work = bin_off[MYERS_BINS];
+        MyersPlan pl; memset(&pl, 0, sizeof(pl));
+        uint32_t n_work = 0, n_banded = 0;
+        for (int q = 0; q < 2 * MYERS_BINS; ++q) { pl.cnt[q] = h_ctl[q]; pl.off[q] = n_work; n_work += h_ctl[q]; if (q >= MYERS_BINS) n_banded += h_ctl[q]; }
+        for (int bb = 0; bb < MYERS_BINS; ++bb) pl.retry_cap[bb] = h_ctl[20 + bb];
         cs.myers_pairs = n_work;
         if (n_work > 0 && !ctx->d_genome.p) { ctx->set_error(SVIMGPU_ERR_STATE, "insertion clustering needs svimgpu_set_genome"); return SVIMGPU_ERR_STATE; }
         if (n_work > 0) {
-            SVIM_CUDA(ctx->d_pairs.ensure((size_t)n_work * 3 * sizeof(MyersWork) + 16));   // unsorted list, sorted list, fallback list
+            SVIM_CUDA(ctx->d_pairs.ensure((size_t)n_work * 3 * sizeof(MyersWork) + 16));   // sorted list, fallback list, unsorted list (later: hand-over list)
             SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_work * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n_work * 8));
             MyersWork* d_unsorted = ctx->d_pairs.as<MyersWork>() + 2 * (size_t)n_work;
             MyersWork* d_work = ctx->d_pairs.as<MyersWork>();
             {
                 StageTimer t(ctx, T_PAIRS);
-                SVIM_CUDA(cudaMemcpyAsync(d_bins, bin_off, MYERS_BINS * 4, cudaMemcpyHostToDevice, st));
+                SVIM_CUDA(cudaMemcpyAsync(d_ctl, pl.off, 2 * MYERS_BINS * 4, cudaMemcpyHostToDevice, st));
                 { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_bins, d_misc + 9); }
-                // longest-processing-time-first inside every bin: one radix sort on (bin, ~cost)
+                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_ctl, d_ctl + 20,
+                                                    ctx->myers_band_num, ctx->myers_band_add, d_misc + 9); }
+                // longest-processing-time-first inside every list: one radix sort on (list, ~cost)
                 size_t tmp = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work, (int)n_work, 0, 36, st);
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work, (int)n_work, 0, 37, st);
                 SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
                 SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work,
-                                                          (int)n_work, 0, 36, st));
+                                                          (int)n_work, 0, 37, st));
             }
             StageTimer t(ctx, T_MYERS);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            SVIM_CUDA(cudaMemsetAsync(d_misc + 32, 0, 16 * 4, st));
-            MyersArgs ma{sorted, ctx->cluster_ins, gv, nullptr, 0, ctx->d_pair_ed.as<int32_t>(), nullptr, maxlen, nullptr, d_work + n_work, d_misc + 32,
-                         (unsigned long long*)(d_misc + 12), d_misc + 9};
+            MyersArgs ma; memset(&ma, 0, sizeof(ma));
+            ma.sig = sorted; ma.ins_blob = ctx->cluster_ins; ma.g = gv; ma.ed_out = ctx->d_pair_ed.as<int32_t>(); ma.maxlen = maxlen;
+            ma.fallback = d_work + n_work; ma.cells = (unsigned long long*)(d_misc + 12); ma.err = d_misc + 9;
+            ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add; ma.band_cells = (unsigned long long*)(d_ctl + 72);
             StringPairs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            // longest bins first so the tail of the launch sequence is made of short pairs; bins overlap on side streams
-            SVIM_CUDA(myers_fork(ctx));
-            for (int bb = MYERS_BINS - 1; bb >= 0; --bb) {
-                ma.work = d_work + bin_off[bb]; ma.n_work = bin_cnt[bb]; ma.next = d_misc + 33 + bb; ma.maxlen = maxlen;
-                SVIM_CUDA(myers_launch_bin<false>(ctx, bb, ma, none, ctx->d_myers_scratch[bb], sms));
-            }
-            SVIM_CUDA(myers_join(ctx));
-            uint32_t n_fb = 0;
-            SVIM_CUDA(cudaMemcpyAsync(&n_fb, d_misc + 32, 4, cudaMemcpyDeviceToHost, st));
+            // the unsorted list is dead after the sort: its room takes the banded pass's hand-overs
+            SVIM_CUDA(myers_run_plan<false>(ctx, pl, ma, none, d_work, nullptr, d_unsorted, d_ctl, maxlen, sms));
+            uint32_t h_retry[MYERS_BINS + 8];
+            SVIM_CUDA(cudaMemcpyAsync(h_retry, d_ctl + MYERS_CTL_RETRY, sizeof(h_retry), cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
-            if (n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
-                ma.work = d_work + n_work; ma.n_work = n_fb; ma.next = d_misc + 33 + MYERS_BINS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
-                SVIM_CUDA(myers_fork(ctx));
-                SVIM_CUDA(myers_launch_bin<false>(ctx, MYERS_BINS, ma, none, ctx->d_myers_scratch[MYERS_BINS], sms));
-                SVIM_CUDA(myers_join(ctx));
-            }
+            uint32_t n_retry = 0; for (int bb = 0; bb < MYERS_BINS; ++bb) n_retry += h_retry[bb];
+            cs.myers_banded_pairs = n_banded; cs.myers_retry_pairs = n_retry;
+            cs.myers_band_cells = (int64_t)(((uint64_t)h_retry[17] << 32) | h_retry[16]);
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();
     }

@@ -109,6 +109,7 @@ struct svimgpu_ctx {
     bool qs_mode = false;      // query-sorted COLLECT (SVIM_COLLECT.py:96-129)
     DevBuf d_qs_info, d_qs_grp, d_qs_segsum, d_qs_mem_off, d_qs_mem_idx;
     int myers_mode = 1;        // k_myers_fast formulation (env SVIM_MYERS_MODE): 0 ALU pipe, 1 FMA pipe, 2 FMA pipe + IMAD.HI
+    int myers_band_num = 174, myers_band_add = 24;   // banded first pass with k = m*num/1024 + add (env SVIM_MYERS_BAND=num,add; 0 = off)
     int scan_chunks = 1;       // per-warp chunked queue-slot reservation (env SVIM_SCAN_CHUNKS=0: one atomic per signature)
     int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
     svim_collect_stats cstats;
@@ -118,7 +119,7 @@ struct svimgpu_ctx {
     const uint8_t* cluster_ins = nullptr; int64_t cluster_ins_bytes = 0;
     int64_t n_csig = 0; bool have_csig = false;
     DevBuf d_order, d_head, d_partid, d_part_off, d_samp_off, d_samp_idx, d_labels, d_part_ncl, d_part_nkept, d_part_stats;
-    DevBuf d_plist, d_myers_scratch[12];
+    DevBuf d_plist, d_myers_scratch[24], d_myers_ctl;   // scratch: [0,10) unbanded bins, [10] 8-plane kernel, [12,22) banded shapes
     int64_t cluster_max_ins_len = 0;
     const int32_t* cluster_rank_to_tid = nullptr; int32_t cluster_n_ranks = 0;
     DevBuf d_user_rank_to_tid;

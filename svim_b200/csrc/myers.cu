@@ -19,8 +19,7 @@
 // DRAM traffic is the two haplotypes per pair.  No tensor cores: there is no dense contraction here.
 #pragma once
 #include "ctx.cuh"
-
-#define MYERS_BINS 10
+#include "myers_band.cuh"   // bins, word steps, banded wavefront (host-checkable)
 
 struct MyersWork { uint32_t a, b, slot, pad; };
 
@@ -73,21 +72,6 @@ __device__ __forceinline__ bool pair_haps(const svim_csig& a, const svim_csig& b
     ha = make_hap(contig, clen, lo < 0 ? 0 : lo, hi < 0 ? 0 : hi, s1 < 0 ? 0 : s1, ins_blob + a.seq_off, a.seq_len);
     hb = make_hap(contig, clen, lo < 0 ? 0 : lo, hi < 0 ? 0 : hi, s2 < 0 ? 0 : s2, ins_blob + b.seq_off, b.seq_len);
     return true;
-}
-
-// Bins of pairs by pattern length: a group of G lanes owns one pair with WPL words per lane (capacity G*WPL words);
-// small G with several words per lane packs more pairs into a warp and amortises the per-step overhead.
-struct MyersBin { int G, WPL, capW; };
-__host__ __device__ __forceinline__ MyersBin myers_bin_spec(int b) {
-    switch (b) {
-        case 0: return {4, 1, 4};   case 1: return {4, 2, 8};   case 2: return {4, 3, 12};  case 3: return {4, 4, 16};
-        case 4: return {8, 3, 24};  case 5: return {8, 4, 32};  case 6: return {16, 3, 48}; case 7: return {16, 4, 64};
-        case 8: return {32, 3, 96}; default: return {32, 4, 1 << 30};   // bin 9 strip-mines beyond 128 words
-    }
-}
-__host__ __device__ __forceinline__ int myers_bin_of(int64_t m) {
-    const int64_t W = (m + 63) >> 6;
-    return W <= 4 ? 0 : W <= 8 ? 1 : W <= 12 ? 2 : W <= 16 ? 3 : W <= 24 ? 4 : W <= 32 ? 5 : W <= 48 ? 6 : W <= 64 ? 7 : W <= 96 ? 8 : 9;
 }
 
 // materialise symbol codes with the G lanes of a group; returns OR of all codes (group-uniform)
@@ -221,8 +205,6 @@ __device__ __forceinline__ uint32_t hap_write_txt32(const HapSource& h, uint32_t
     return orall;
 }
 
-struct Word32 { uint32_t p0l, p0h, p1l, p1h, p2l, p2h, pvl, pvh, mvl, mvh; };
-
 __device__ __forceinline__ void word_init(Word32& w, const uint8_t* __restrict__ pat, int64_t m, int64_t row0) {
     uint64_t pl[3], vm;
     build_planes<3>(pat, m, row0, pl, vm);
@@ -240,53 +222,11 @@ __device__ __forceinline__ int word_vsum(const Word32& w, int64_t m, int64_t row
     return __popcll(pv & vm) - __popcll(mv & vm);
 }
 
-// one word step; e = hin + 1 in {0,1,2}; returns hout + 1
-template <int NP>
-__device__ __forceinline__ uint32_t word_step(Word32& w, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t e) {
-    const uint32_t hneg = 1u >> e, hpos = e >> 1;
-    const uint32_t eql = NP == 2 ? ~((w.p0l ^ m0) | (w.p1l ^ m1)) : ~((w.p0l ^ m0) | (w.p1l ^ m1) | (w.p2l ^ m2));
-    const uint32_t eqh = NP == 2 ? ~((w.p0h ^ m0) | (w.p1h ^ m1)) : ~((w.p0h ^ m0) | (w.p1h ^ m1) | (w.p2h ^ m2));
-    const uint32_t xvl = eql | w.mvl, xvh = eqh | w.mvh;
-    const uint32_t el = eql | hneg;
-    uint32_t sl, sh;
-    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(sl), "=r"(sh) : "r"(el & w.pvl), "r"(w.pvl), "r"(eqh & w.pvh), "r"(w.pvh));
-    const uint32_t xhl = (sl ^ w.pvl) | el, xhh = (sh ^ w.pvh) | eqh;
-    const uint32_t phl = w.mvl | ~(xhl | w.pvl), phh = w.mvh | ~(xhh | w.pvh);
-    const uint32_t mhl = w.pvl & xhl, mhh = w.pvh & xhh;
-    const uint32_t eout = 1u + (phh >> 31) - (mhh >> 31);
-    const uint32_t phl2 = (phl << 1) | hpos, phh2 = __funnelshift_l(phl, phh, 1);
-    const uint32_t mhl2 = (mhl << 1) | hneg, mhh2 = __funnelshift_l(mhl, mhh, 1);
-    w.pvl = mhl2 | ~(xvl | phl2); w.pvh = mhh2 | ~(xvh | phh2);
-    w.mvl = phl2 & xvl; w.mvh = phh2 & xvh;
-    return eout;
-}
-
-// ---- two-plane (A/C/G/T) words: FMA-pipe formulation ------------------------------------------------------------
-// The ALU pipe (LOP3/SHF/IADD3, one warp instruction every two cycles per SM sub-partition) bounds the plain
-// formulation while the FMA pipe idles.  Here every 64-row word is two independent 32-row blocks chained through
-// their horizontal deltas, and whatever can be phrased as a multiply-add runs as IMAD on the FMA pipe:
-//   Eq      = P0 + c1*(P1-P0) + c2*(P2-P0) + c3*(P3-P0)      (c = one-hot of the text symbol; 3 IMAD, no LOP3)
-//   s       = (Eq|hn) & Pv + Pv                               (IMAD with multiplicand `one`)
-//   Ph<<1|hp = Ph*two + hp,  Mh<<1|hn = Mh*two + hn           (IMAD; bit 0 is free after the shift)
-// leaving 10 ALU-pipe and 6 FMA-pipe instructions per 32 cells instead of ~16 ALU.
-struct WordQ { uint32_t q0[2], d1[2], d2[2], d3[2], pv[2], mv[2]; };
-
-__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
+// ---- two-plane (A/C/G/T) words on the FMA pipe (WordQ / block_step, myers_band.cuh) ----
 __device__ __forceinline__ void wordq_init(WordQ& w, const uint8_t* __restrict__ pat, int64_t m, int64_t row0) {
     uint64_t pl[2], vm;
     build_planes<2>(pat, m, row0, pl, vm);
-    const uint64_t P0 = ~pl[0] & ~pl[1] & vm, P1 = pl[0] & ~pl[1], P2 = ~pl[0] & pl[1], P3 = pl[0] & pl[1];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const uint32_t p0 = (uint32_t)(P0 >> (32 * h));
-        w.q0[h] = p0; w.d1[h] = (uint32_t)(P1 >> (32 * h)) - p0; w.d2[h] = (uint32_t)(P2 >> (32 * h)) - p0; w.d3[h] = (uint32_t)(P3 >> (32 * h)) - p0;
-        w.pv[h] = 0xffffffffu; w.mv[h] = 0u;
-    }
+    wordq_from_planes(w, pl[0], pl[1], vm, ~0ull);
 }
 
 __device__ __forceinline__ int wordq_vsum(const WordQ& w, int64_t m, int64_t row0) {
@@ -295,25 +235,6 @@ __device__ __forceinline__ int wordq_vsum(const WordQ& w, int64_t m, int64_t row
     const uint64_t vm = cnt == 64 ? ~0ull : ((1ull << cnt) - 1ull);
     const uint64_t pv = ((uint64_t)w.pv[1] << 32) | w.pv[0], mv = ((uint64_t)w.mv[1] << 32) | w.mv[0];
     return __popcll(pv & vm) - __popcll(mv & vm);
-}
-
-// one 32-row block step; hp/hn = incoming horizontal delta (+1 / -1 flags), replaced by the outgoing one
-template <bool HI>
-__device__ __forceinline__ void block_step(uint32_t q0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t& pv_io, uint32_t& mv_io,
-                                           uint32_t c1, uint32_t c2, uint32_t c3, uint32_t one, uint32_t two, uint32_t& hp, uint32_t& hn) {
-    const uint32_t pv = pv_io, mv = mv_io;
-    const uint32_t eq = imad(c3, d3, imad(c2, d2, imad(c1, d1, q0)));
-    const uint32_t xv = eq | mv;
-    const uint32_t el = eq | hn;
-    const uint32_t s = imad(el & pv, one, pv);
-    const uint32_t xh = (s ^ pv) | el;
-    const uint32_t ph = mv | ~(xh | pv);
-    const uint32_t mh = pv & xh;
-    const uint32_t ph2 = imad(ph, two, hp), mh2 = imad(mh, two, hn);
-    if (HI) { hp = __umulhi(ph, two); hn = __umulhi(mh, two); }   // top bit via IMAD.HI (FMA pipe)
-    else { hp = ph >> 31; hn = mh >> 31; }
-    pv_io = mh2 | ~(xv | ph2);
-    mv_io = ph2 & xv;
 }
 
 // G lanes per pair, WPL words per lane; strips of G*WPL words (only G = 32 ever needs more than one strip)
@@ -443,10 +364,31 @@ struct MyersArgs {
     MyersWork* fallback; uint32_t* n_fallback;   // pairs that need the 8-plane kernel
     unsigned long long* cells; uint32_t* err;
     uint32_t one, two;                        // 1 and 2, opaque to the compiler: multiplicands that keep adds/shifts on the FMA pipe
+    // banded first pass (k_myers_band): pairs whose result exceeds the bound go to `retry`, one region per unbanded bin;
+    // the unbanded kernel of that bin reads them as its second list (`extra`, count on the device)
+    const MyersWork* extra; const uint32_t* n_extra;
+    MyersWork* retry; uint32_t* n_retry; uint32_t retry_off[MYERS_BINS];
+    int32_t band_num, band_add;
+    unsigned long long* band_cells;           // cells the banded pass actually computed (statistics)
 };
 
 // explicit string pairs (unit-test entry svimgpu_edit_distance) share the kernels below through this view
 struct StringPairs { const uint8_t* blob; const int64_t* a_off; const int32_t* a_len; const int64_t* b_off; const int32_t* b_len; const uint32_t* list; };
+
+// work item w of a kernel's lists -> the two haplotypes; false (and an error flag) if the contig is unknown
+template <bool STRINGS>
+__device__ __forceinline__ bool myers_load_pair(const MyersArgs& a, const StringPairs& sp, uint32_t w, MyersWork& wk, HapSource& ha, HapSource& hb, int gl) {
+    if (STRINGS) {
+        const uint32_t i = w < a.n_work ? sp.list[w] : a.extra[w - a.n_work].slot;
+        wk.slot = i; wk.a = i; wk.b = 0; wk.pad = 0;
+        ha = HapSource{sp.blob, 0, sp.blob + sp.a_off[i], sp.a_len[i], sp.blob, 0};
+        hb = HapSource{sp.blob, 0, sp.blob + sp.b_off[i], sp.b_len[i], sp.blob, 0};
+        return true;
+    }
+    wk = w < a.n_work ? a.work[w] : a.extra[w - a.n_work];
+    if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (gl == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } return false; }
+    return true;
+}
 
 // MODE: 0 = ALU-pipe formulation, 1 = two-plane pairs on the FMA-pipe formulation, 2 = same with IMAD.HI for the top bits
 template <int G, int WPL, bool STRINGS, int MODE>
@@ -456,26 +398,17 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 6 * a.maxlen;
     unsigned long long my_cells = 0;
+    const uint32_t n_total = a.n_work + (a.n_extra ? *a.n_extra : 0u);
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(a.next, (uint32_t)GPW);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= a.n_work) break;
+        if (base >= n_total) break;
         const uint32_t w = base + grp;
-        bool valid = w < a.n_work;
+        bool valid = w < n_total;
         MyersWork wk{0, 0, 0, 0};
         HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
-        if (valid) {
-            if (STRINGS) {
-                const uint32_t i = sp.list[w];
-                wk.slot = i; wk.a = i;
-                ha = HapSource{sp.blob, 0, sp.blob + sp.a_off[i], sp.a_len[i], sp.blob, 0};
-                hb = HapSource{sp.blob, 0, sp.blob + sp.b_off[i], sp.b_len[i], sp.blob, 0};
-            } else {
-                wk = a.work[w];
-                if (!pair_haps(a.sig[wk.a], a.sig[wk.b], a.ins_blob, a.g, ha, hb)) { if (gl == 0) { atomicExch(a.err, 1u); a.ed_out[wk.slot] = 0; } valid = false; }
-            }
-        }
+        if (valid) valid = myers_load_pair<STRINGS>(a, sp, w, wk, ha, hb, gl);
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
         if (valid && (la > a.maxlen || lb > a.maxlen)) { if (gl == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } valid = false; }
         if (valid && (la == 0 || lb == 0)) { if (gl == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
@@ -500,6 +433,76 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
         __syncwarp();
     }
     if (my_cells) atomicAdd(a.cells, my_cells);
+}
+
+// Banded first pass (myers_band.cuh): G lanes rotate over the word groups the band crosses, so the shape follows the
+// band width.  Pure A/C/G/T pairs only (two planes, FMA-pipe words); anything else, and every pair whose banded
+// result exceeds its bound, is handed to the unbanded kernel of the pattern's bin.
+__host__ __device__ __forceinline__ size_t myers_band_scratch(int64_t maxlen, int WPL) {
+    return (size_t)((2 * maxlen + 24 * ((maxlen >> 6) + WPL + 1) + 15) & ~15ll);   // pattern codes, text codes, 3 plane words per pattern word
+}
+
+template <int G, int WPL, bool STRINGS, bool HI>
+__global__ void __launch_bounds__(128) k_myers_band(MyersArgs a, StringPairs sp) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * myers_band_scratch(a.maxlen, WPL);
+    uint8_t* pat = my; uint8_t* txt = my + a.maxlen; uint64_t* planes = (uint64_t*)(my + 2 * a.maxlen);
+    unsigned long long my_cells = 0, my_band = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.next, (uint32_t)GPW);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.n_work) break;
+        const uint32_t w = base + grp;
+        bool valid = w < a.n_work;
+        MyersWork wk{0, 0, 0, 0};
+        HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
+        if (valid) valid = myers_load_pair<STRINGS>(a, sp, w, wk, ha, hb, gl);
+        const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
+        if (valid && (la > a.maxlen || lb > a.maxlen)) { if (gl == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } valid = false; }
+        if (valid && (la == 0 || lb == 0)) { if (gl == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int64_t m = a_is_pat ? la : lb, n = a_is_pat ? lb : la;
+        const uint32_t orall = hap_write_codes<G>(hp, pat, gl, valid) | hap_write_codes<G>(ht, txt, gl, valid);
+        const int64_t k = myers_band_k(m, n, a.band_num, a.band_add);
+        const int rbin = myers_bin_of(m);
+        if (valid && (orall >= 4 || k < 0 || !myers_band_fits(m, n, k, G, WPL))) {   // not a banded pair after all
+            if (gl == 0) { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
+            valid = false;
+        }
+        BandGeom ge = band_geom(valid ? m : 0, valid ? n : 0, valid ? k : 0, WPL);
+        __syncwarp();
+        for (int64_t x = gl; x < (int64_t)ge.NG * WPL; x += G) band_build_word(pat, m, ge.pad, x, planes + 3 * x);
+        __syncwarp();
+        BandLane<WPL> L;
+        band_lane_init(L, ge, planes, gl, valid);
+        int steps = valid ? ge.n + ge.NG - 1 : 0;
+        if (G < 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const int t = __shfl_xor_sync(0xffffffffu, steps, o); steps = t > steps ? t : steps; }
+        }
+        uint32_t e_out = 0;
+        for (int s = 0; s < steps; ++s) {
+            const uint32_t recv = __shfl_sync(0xffffffffu, e_out, (gl - 1) & (G - 1), G);
+            e_out = band_lane_step<G, WPL, HI>(L, ge, planes, txt, s, recv, e_out, a.one, a.two);
+        }
+        int score = L.score;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) score += __shfl_xor_sync(0xffffffffu, score, o, G);
+        if (valid && gl == 0) {
+            const int64_t ed = m + score;
+            my_band += (unsigned long long)ge.n * (unsigned long long)(ge.a + ge.b + 64 * WPL);
+            if (ed <= k) { a.ed_out[wk.slot] = (int32_t)ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
+            else { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
+        }
+        __syncwarp();
+    }
+    if (my_cells) atomicAdd(a.cells, my_cells);
+    if (my_band && a.band_cells) atomicAdd(a.band_cells, my_band);
 }
 
 // any bytes: 8 bit-planes, a warp per pair, 4 words per lane, strip-mined
@@ -553,15 +556,18 @@ static cudaError_t myers_join(svimgpu_ctx* ctx) {
     return e;
 }
 
+// extra_cap = upper bound of the second list (pairs the banded pass may hand over), for grid sizing only
 template <bool STRINGS>
-static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
-    if (a.n_work == 0) return cudaSuccess;
+static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms, uint32_t extra_cap = 0) {
+    const uint64_t n_items = (uint64_t)a.n_work + extra_cap;
+    if (n_items == 0) return cudaSuccess;
+    if (extra_cap == 0) { a.extra = nullptr; a.n_extra = nullptr; }
     const MyersBin spec = bin < MYERS_BINS ? myers_bin_spec(bin) : MyersBin{32, 4, 1 << 30};
     const int64_t cap = (bin < MYERS_BINS - 1) ? (int64_t)64 * spec.capW : a.maxlen;   // longest haplotype in the bin
     a.maxlen = (cap + 15) & ~15ll;
     const int groups = 32 / spec.G;
     int blocks = sms * 8;
-    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * groups - 1) / (4 * groups));
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)n_items + 4 * groups - 1) / (4 * groups));
     const size_t per_warp = (size_t)6 * groups * a.maxlen;
     while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)16 << 30)) blocks -= sms;
     cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
@@ -592,4 +598,95 @@ static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, Stri
     }
 #undef MYERS_LAUNCH
     return cudaGetLastError();
+}
+
+// banded first pass of shape `bin`; a.maxlen = longest haplotype of the whole run (the shape bounds the band, not the pattern)
+template <bool STRINGS>
+static cudaError_t myers_launch_band(svimgpu_ctx* ctx, int bin, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
+    if (a.n_work == 0) return cudaSuccess;
+    const MyersBin spec = myers_bin_spec(bin);
+    a.maxlen = (a.maxlen + 15) & ~15ll;
+    const int groups = 32 / spec.G;
+    int blocks = sms * 8;
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 4 * groups - 1) / (4 * groups));
+    const size_t per_warp = (size_t)groups * myers_band_scratch(a.maxlen, spec.WPL);
+    while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)16 << 30)) blocks -= sms;
+    cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
+    if (e != cudaSuccess) return e;
+    a.scratch = scratch.as<uint8_t>();
+    ctx->launches++;
+    cudaStream_t stream = ctx->aux_stream[bin % SVIM_AUX_STREAMS];
+    a.one = 1u; a.two = 2u;
+#define MYERS_LAUNCH(G_, W_)                                                                                     \
+    if (ctx->myers_mode == 2) k_myers_band<G_, W_, STRINGS, true><<<blocks, 128, 0, stream>>>(a, sp);           \
+    else k_myers_band<G_, W_, STRINGS, false><<<blocks, 128, 0, stream>>>(a, sp);                               \
+    break;
+    switch (bin) {
+        case 0: MYERS_LAUNCH(4, 1)
+        case 1: MYERS_LAUNCH(4, 2)
+        case 2: MYERS_LAUNCH(4, 3)
+        case 3: MYERS_LAUNCH(4, 4)
+        case 4: MYERS_LAUNCH(8, 3)
+        case 5: MYERS_LAUNCH(8, 4)
+        case 6: MYERS_LAUNCH(16, 3)
+        case 7: MYERS_LAUNCH(16, 4)
+        case 8: MYERS_LAUNCH(32, 3)
+        default: MYERS_LAUNCH(32, 4)
+    }
+#undef MYERS_LAUNCH
+    return cudaGetLastError();
+}
+
+// ---- the whole edit-distance stage: banded shapes first, then the unbanded bins (their own pairs + the banded pass's
+// hand-overs), then the 8-plane kernel for pairs with symbols outside the code space -------------------------------------
+struct MyersPlan {
+    uint32_t cnt[2 * MYERS_BINS];     // first-pass items: [0,10) unbanded bins, [10,20) banded shapes
+    uint32_t off[2 * MYERS_BINS];     // their offsets in the work list (pipeline) / index list (string pairs)
+    uint32_t retry_cap[MYERS_BINS];   // banded items whose pattern belongs to each unbanded bin
+};
+enum { MYERS_CTL_CURSOR = 32, MYERS_CTL_RETRY = 56, MYERS_CTL_FALLBACK = 70, MYERS_CTL_N = 128 };
+
+// ctl: MYERS_CTL_N device words; retry: room for sum(retry_cap) items; ma carries sig/ins/genome, ed_out, fallback list,
+// cells / band_cells / err pointers and the band policy.  Synchronises ctx->stream.
+template <bool STRINGS>
+static cudaError_t myers_run_plan(svimgpu_ctx* ctx, const MyersPlan& pl, MyersArgs ma, StringPairs sp, const MyersWork* work, const uint32_t* list,
+                                  MyersWork* retry, uint32_t* ctl, int64_t maxlen, int sms) {
+    cudaError_t e = cudaSuccess;
+    auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    cudaStream_t st = ctx->stream;
+    chk(cudaMemsetAsync(ctl + MYERS_CTL_CURSOR, 0, (MYERS_CTL_N - MYERS_CTL_CURSOR) * 4, st));
+    ma.n_fallback = ctl + MYERS_CTL_FALLBACK; ma.n_retry = ctl + MYERS_CTL_RETRY; ma.retry = retry;
+    uint32_t acc = 0, n_banded = 0;
+    for (int bb = 0; bb < MYERS_BINS; ++bb) { ma.retry_off[bb] = acc; acc += pl.retry_cap[bb]; n_banded += pl.cnt[MYERS_BINS + bb]; }
+    if (n_banded > 0) {
+        chk(myers_fork(ctx));
+        for (int bb = MYERS_BINS - 1; bb >= 0 && e == cudaSuccess; --bb) {
+            const int q = MYERS_BINS + bb;
+            ma.work = work ? work + pl.off[q] : nullptr; sp.list = list ? list + pl.off[q] : nullptr;
+            ma.n_work = pl.cnt[q]; ma.next = ctl + MYERS_CTL_CURSOR + q; ma.maxlen = maxlen; ma.extra = nullptr; ma.n_extra = nullptr;
+            chk(myers_launch_band<STRINGS>(ctx, bb, ma, sp, ctx->d_myers_scratch[12 + bb], sms));
+        }
+        chk(myers_join(ctx));
+    }
+    // longest bins first so the tail of the launch sequence is made of short pairs; bins overlap on side streams
+    chk(myers_fork(ctx));
+    for (int bb = MYERS_BINS - 1; bb >= 0 && e == cudaSuccess; --bb) {
+        ma.work = work ? work + pl.off[bb] : nullptr; sp.list = list ? list + pl.off[bb] : nullptr;
+        ma.n_work = pl.cnt[bb]; ma.next = ctl + MYERS_CTL_CURSOR + bb; ma.maxlen = maxlen;
+        ma.extra = retry + ma.retry_off[bb]; ma.n_extra = ctl + MYERS_CTL_RETRY + bb;
+        chk(myers_launch_bin<STRINGS>(ctx, bb, ma, sp, ctx->d_myers_scratch[bb], sms, pl.retry_cap[bb]));
+    }
+    chk(myers_join(ctx));
+    uint32_t n_fb = 0;
+    chk(cudaMemcpyAsync(&n_fb, ctl + MYERS_CTL_FALLBACK, 4, cudaMemcpyDeviceToHost, st));
+    chk(cudaStreamSynchronize(st));
+    if (e == cudaSuccess && n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
+        sp.list = nullptr;
+        ma.work = ma.fallback; ma.n_work = n_fb; ma.next = ctl + MYERS_CTL_CURSOR + 2 * MYERS_BINS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+        ma.extra = nullptr; ma.n_extra = nullptr;
+        chk(myers_fork(ctx));
+        chk(myers_launch_bin<STRINGS>(ctx, MYERS_BINS, ma, sp, ctx->d_myers_scratch[MYERS_BINS], sms));
+        chk(myers_join(ctx));
+    }
+    return e;
 }

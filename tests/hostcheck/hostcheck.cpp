@@ -64,3 +64,41 @@ long long hc_round(double x) { return py_round_int(x); }
 void hc_py_slice(long long a, long long n, long long L, long long* lo, long long* hi) { int64_t l, h; py_slice(a, n, L, l, h); *lo = l; *hi = h; }
 
 }
+
+// ---- banded Myers wavefront (myers_band.cuh): replay the G lanes of one pair step by step --------------------------
+#include "../../svim_b200/csrc/myers_band.cuh"
+
+template <int G, int WPL, bool HI>
+static long long band_emulate(const uint8_t* pat, long long m, const uint8_t* txt, long long n, long long k) {
+    const BandGeom ge = band_geom(m, n, k, WPL);
+    std::vector<uint64_t> planes((size_t)3 * ge.NG * WPL);
+    for (long long w = 0; w < (long long)ge.NG * WPL; ++w) band_build_word(pat, m, ge.pad, w, planes.data() + 3 * w);
+    BandLane<WPL> L[G];
+    uint32_t e_out[G], recv[G];
+    for (int l = 0; l < G; ++l) { band_lane_init(L[l], ge, planes.data(), l, true); e_out[l] = 0; }
+    const int32_t steps = ge.n + ge.NG - 1;
+    for (int32_t s = 0; s < steps; ++s) {
+        for (int l = 0; l < G; ++l) recv[l] = e_out[(l - 1) & (G - 1)];
+        for (int l = 0; l < G; ++l) e_out[l] = band_lane_step<G, WPL, HI>(L[l], ge, planes.data(), txt, s, recv[l], e_out[l], 1u, 2u);
+    }
+    long long d = m;
+    for (int l = 0; l < G; ++l) d += L[l].score;
+    return d;
+}
+
+extern "C" {
+// pat/txt: symbol codes 0..3, m >= n >= 1.  Returns the banded result, -1 if the band does not fit the shape, -2 on bad arguments.
+long long hc_myers_banded(const uint8_t* pat, long long m, const uint8_t* txt, long long n, long long k, int bin, int hi) {
+    if (m < n || n < 1 || k < m - n || bin < 0 || bin >= MYERS_BINS) return -2;
+    const MyersBin sp = myers_bin_spec(bin);
+    if (!myers_band_fits(m, n, k, sp.G, sp.WPL)) return -1;
+#define HC_BAND(G_, W_) return hi ? band_emulate<G_, W_, true>(pat, m, txt, n, k) : band_emulate<G_, W_, false>(pat, m, txt, n, k);
+    switch (bin) {
+        case 0: HC_BAND(4, 1) case 1: HC_BAND(4, 2) case 2: HC_BAND(4, 3) case 3: HC_BAND(4, 4) case 4: HC_BAND(8, 3)
+        case 5: HC_BAND(8, 4) case 6: HC_BAND(16, 3) case 7: HC_BAND(16, 4) case 8: HC_BAND(32, 3) default: HC_BAND(32, 4)
+    }
+#undef HC_BAND
+}
+int hc_myers_band_bin(long long m, long long n, int num, int add) { return myers_band_bin(m, n, num, add); }
+long long hc_myers_band_k(long long m, long long n, int num, int add) { return myers_band_k(m, n, num, add); }
+}

@@ -92,6 +92,47 @@ def test_edit_distance_kernel_matches_oracle(gpu_ctx):
         assert g == want, (len(a), len(b), g, want)
 
 
+@pytest.mark.parametrize("band", ["174,24", "60,0", "420,100", "0"])
+def test_banded_edit_distance_matches_oracle(band, monkeypatch):
+    """The banded first pass (rotating-lane wavefront, myers_band.cuh) plus the unbanded hand-over must be exact for every
+    band policy: a tight bound sends most pairs to the second pass, a wide one keeps divergent pairs on the banded kernels."""
+    from oracle import editdist
+    from svim_b200 import _lib
+    monkeypatch.setenv("SVIM_MYERS_BAND", band)
+    ctx = _lib.Context(device=0)
+    rng = random.Random(11)
+
+    def mutate(s, rate):
+        out = bytearray()
+        for ch in s:
+            r = rng.random()
+            if r < rate / 3:
+                continue
+            if r < 2 * rate / 3:
+                out.append(rng.choice(b"ACGT")); continue
+            out.append(ch)
+            if r < rate:
+                out.append(rng.choice(b"ACGT"))
+        return bytes(out)
+    pairs = []
+    for n in [40, 130, 257, 300, 511, 700, 1000, 1025, 1500, 2000, 2600, 3100, 4000, 4100, 5000, 6200, 7000, 9000, 12500, 17000]:
+        for rate in [0.0, 0.03, 0.12, 0.2, 0.35, 0.7]:
+            a = bytes(rng.choice(b"ACGT") for _ in range(n))
+            b = mutate(a, rate)
+            if rng.random() < 0.25:
+                b = b[rng.randint(0, len(b) // 4):]                      # length difference: the band is off-centre
+            if rng.random() < 0.15:
+                a = a[:n // 2] + b"N" + a[n // 2:]                       # a symbol outside A/C/G/T leaves the banded path
+            if rng.random() < 0.1:
+                a = a.lower()
+            pairs.append((a, b if b else b"A"))
+    rng.shuffle(pairs)
+    got = ctx.edit_distance(pairs)
+    for (a, b), g in zip(pairs, got.tolist()):
+        want = editdist.edit_distance(a.upper(), b.upper())
+        assert g == want, (band, len(a), len(b), g, want)
+
+
 def test_linkage_kernel_matches_scipy(gpu_ctx):
     from scipy.cluster.hierarchy import linkage, fcluster
     rng = np.random.default_rng(5)

@@ -116,7 +116,7 @@ def test_fasta_fetch_clamps(tmp_path):
 def hc():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh")]
+    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
     lib = ctypes.CDLL(so)
@@ -325,3 +325,55 @@ def test_fcluster_postprocessing_matches_scipy(hc):
                        ctypes.c_double(0.5), T.ctypes.data_as(ctypes.c_void_p))
         want = fcluster(linkage(np.asarray(d, dtype=float), method="average"), 0.5, criterion="distance")
         assert T.tolist() == list(want)
+
+
+def test_banded_wavefront_host_replay(hc):
+    """myers_band.cuh replayed lane by lane on the host (the kernel k_myers_band runs the same functions, one lane per
+    thread): for every shape the band fits,  result <= k  =>  result == distance,  result > k  =>  distance > k."""
+    hc.hc_myers_banded.restype = ctypes.c_longlong
+    hc.hc_myers_banded.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    hc.hc_myers_band_k.restype = ctypes.c_longlong
+    hc.hc_myers_band_k.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    hc.hc_myers_band_bin.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    rng = random.Random(7)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+    def enc(s):
+        return bytes(code[c] for c in s)
+
+    def mutate(s, rate):
+        out = []
+        for ch in s:
+            r = rng.random()
+            if r < rate / 3:
+                continue
+            if r < 2 * rate / 3:
+                out.append(rng.choice("ACGT")); continue
+            out.append(ch)
+            if r < rate:
+                out.append(rng.choice("ACGT"))
+        return "".join(out)
+    exact = bounded = 0
+    for it in range(120):
+        L = rng.choice([1, 2, 30, 63, 64, 65, 128, 200, 257, 500, 700, 1000, 1500, 2200, 3000])
+        a = "".join(rng.choice("ACGT") for _ in range(L))
+        b = mutate(a, rng.choice([0, 0.02, 0.1, 0.2, 0.4, 0.8])) or "A"
+        if rng.random() < 0.2:
+            b = b[rng.randint(0, len(b) // 3):] or "A"
+        pat, txt = (a, b) if len(a) >= len(b) else (b, a)
+        m, n = len(pat), len(txt)
+        d = editdist.edit_distance(pat, txt)
+        for k in sorted({m - n, max(m - n, d - 1), max(m - n, d), d + 1, d + 9, max(m - n, d // 2), 2 * d + 3, m + n}):
+            for shape in range(10):
+                r = hc.hc_myers_banded(enc(pat), m, enc(txt), n, k, shape, it & 1)
+                if r == -1:
+                    continue            # the band does not fit this shape's rotating window
+                assert r >= 0
+                if r <= k:
+                    assert r == d, (m, n, k, shape, r, d); exact += 1
+                else:
+                    assert d > k, (m, n, k, shape, r, d); bounded += 1
+    assert exact > 1000 and bounded > 500
+    # the policy: k = m*num/1024 + add, no banded pass when k < m - n or when no smaller shape holds the band
+    assert hc.hc_myers_band_k(1000, 1000, 174, 24) == 193 and hc.hc_myers_band_k(1000, 500, 174, 24) == -1 and hc.hc_myers_band_k(1000, 1000, 0, 24) == -1
+    assert hc.hc_myers_band_bin(4000, 3990, 174, 24) == 3 and hc.hc_myers_band_bin(200, 200, 174, 24) == -1

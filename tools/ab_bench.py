@@ -1,6 +1,6 @@
 """A/B of kernel variants on one synthetic workload: every setting runs in a fresh context on the same records.
 
-    python tools/ab_bench.py --workload config2 SVIM_MYERS_MODE=0 SVIM_MYERS_MODE=1 SVIM_SCAN_VARIANT=5,SVIM_MYERS_MODE=2
+    python tools/ab_bench.py --workload config2 SVIM_MYERS_MODE=0 SVIM_MYERS_MODE=1 SVIM_SCAN_VARIANT=5+SVIM_MYERS_MODE=2
 
 Prints one JSON line per setting: resident ms/step, the scan and Myers stage times, and a checksum of the clusters
 (all settings must agree).  Development tool; bench.py is the measured contract.
@@ -23,8 +23,8 @@ def main():
     batch, genome = bench.make_rank_input(args.workload, args.scale, 0, 1)
     alg_bytes = batch.algorithmic_bytes()
     for setting in args.settings:
-        env = dict(kv.split("=") for kv in setting.split(",") if kv)
-        for k in ("SVIM_MYERS_MODE", "SVIM_SCAN_VARIANT", "SVIM_SCAN_CHUNKS"):
+        env = dict(kv.split("=") for kv in setting.split("+") if kv)
+        for k in ("SVIM_MYERS_MODE", "SVIM_MYERS_BAND", "SVIM_SCAN_VARIANT", "SVIM_SCAN_CHUNKS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ctx = _lib.Context(device=0)
@@ -44,7 +44,8 @@ def main():
         print(json.dumps({"setting": setting, "ms_per_step": round(float(np.mean(ms)), 3), "cigar_scan_ms": round(scan, 4),
                           "scan_GBps": round((alg_bytes + cst.n_signatures * 48) / scan / 1e6, 1),
                           "myers_ms": round(float(np.mean(stages.get("myers_edit_distance", [float("nan")]))), 3),
-                          "signatures": int(cst.n_signatures), "clusters": int(len(clusters)), "digest": digest}), flush=True)
+                          "pairs": int(clst.myers_pairs), "banded": int(clst.myers_banded_pairs), "retry": int(clst.myers_retry_pairs),
+                          "band_cells_frac": round(clst.myers_band_cells / max(1, clst.myers_cells), 4), "signatures": int(cst.n_signatures), "clusters": int(len(clusters)), "digest": digest}), flush=True)
         del ctx
 
 
