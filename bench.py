@@ -240,16 +240,23 @@ def main():
     # collect_host keeps SEQ on the host and uploads only the packed bases of emitted insertions (lazy SEQ)
     h2d_full = int(sum(a.nbytes for a in pinned))
     e2e_ms = []
+    e2e_stage = {}
     d2h = 0
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier_max(0.0)
         ctx.timer_start()
         cst = ctx.collect_host(batch)
+        tm = dict(ctx.timings())
         xst, (clst, clusters, members) = cluster_step()
+        tm2 = dict(ctx.timings())
         fst = xst or cst
         sigs, ins = ctx.fetch_signatures(0, fst)
         ms = ctx.timer_stop()
+        if s >= args.warmup:
+            for k, v in list(tm.items()) + list(tm2.items()):
+                if v:
+                    e2e_stage.setdefault(k, []).append(v)
         d2h = 2 * sigs.nbytes + ins.nbytes + clusters.nbytes + members.nbytes     # signature records cross twice (staging + fetch)
         h2d = h2d_full - batch.seq.nbytes + (cst.ins_bytes + 1) // 2 + 8 * cst.n_signatures
         if s >= args.warmup:
@@ -301,11 +308,14 @@ def main():
         "data": "synthetic", "gpu_launches": int(launches),
         "config": {"workload": workload_name(args), "alignments_per_gpu": batch.n, "signatures": int(n_sigs), "clusters": int(clst.n_clusters_total),
                    "myers_pairs": int(clst.myers_pairs), "myers_cells": int(clst.myers_cells),
+                   "myers_banded_pairs": int(clst.myers_banded_pairs), "myers_handed_over": int(clst.myers_retry_pairs),
+                   "myers_band_cells": int(clst.myers_band_cells),
                    "l2": "inputs larger than L2 (%.2f GB CIGAR per GPU vs 126 MB)" % (batch.cigar.nbytes / 1e9),
                    "parallelism": "records sharded by contig; 2 NCCL allgatherv" if world > 1 else "single GPU",
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_step, "python_object_materialisation_s": obj_s},
+                "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
+                "python_object_materialisation_s": obj_s},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
@@ -314,7 +324,12 @@ def main():
     if bam_leg:
         out["e2e_from_bam"] = bam_leg
     if clst.myers_cells and "myers_edit_distance" in out["stages_ms"]:
-        out["myers"] = {"kernel": "k_myers_pairs", "bound": "int-alu", "gcups": clst.myers_cells / (out["stages_ms"]["myers_edit_distance"] * 1e-3) / 1e9}
+        # gcups = cells of the full DP matrices per second (what an unbanded computation would touch); the banded first pass
+        # computes band_cells of them, pairs it hands over are recomputed in full
+        t_my = out["stages_ms"]["myers_edit_distance"] * 1e-3
+        out["myers"] = {"kernel": "k_myers_band + k_myers_fast", "bound": "int-alu", "gcups": clst.myers_cells / t_my / 1e9,
+                        "band_cells_frac": clst.myers_band_cells / clst.myers_cells, "banded_pairs": int(clst.myers_banded_pairs),
+                        "handed_over_pairs": int(clst.myers_retry_pairs)}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(batch, genome, target_seconds=args.ref_seconds)
     print(json.dumps(out))

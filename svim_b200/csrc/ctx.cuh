@@ -109,7 +109,7 @@ struct svimgpu_ctx {
     bool qs_mode = false;      // query-sorted COLLECT (SVIM_COLLECT.py:96-129)
     DevBuf d_qs_info, d_qs_grp, d_qs_segsum, d_qs_mem_off, d_qs_mem_idx;
     int myers_mode = 1;        // k_myers_fast formulation (env SVIM_MYERS_MODE): 0 ALU pipe, 1 FMA pipe, 2 FMA pipe + IMAD.HI
-    int myers_band_num = 174, myers_band_add = 24;   // banded first pass with k = m*num/1024 + add (env SVIM_MYERS_BAND=num,add; 0 = off)
+    int myers_band_num = 156, myers_band_add = 20;   // banded first pass with k = m*num/1024 + add (env SVIM_MYERS_BAND=num,add; 0 = off)
     int scan_chunks = 1;       // per-warp chunked queue-slot reservation (env SVIM_SCAN_CHUNKS=0: one atomic per signature)
     int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
     svim_collect_stats cstats;

@@ -332,7 +332,7 @@ __device__ int32_t myers_fast_q(const uint8_t* __restrict__ pat, int64_t m, cons
             if (lane_on && (unsigned)j < (unsigned)n) {
                 // packet: byte 0 / byte 1 = 0xFF when bit 0 / bit 1 of the symbol code is set, byte 3 = hin + 1
                 const uint32_t b0 = pk & 1u, b1 = (pk >> 8) & 1u;
-                const uint32_t c3 = b0 & b1, c1 = b0 ^ c3, c2 = b1 ^ c3;
+                const uint32_t c1 = b0, c2 = b1, c3 = b0 & b1;      // bilinear Eq (wordq_from_planes)
                 const uint32_t e = pk >> 24;
                 uint32_t hp = e >> 1, hn = 1u >> e;
 #pragma unroll
@@ -442,8 +442,9 @@ __host__ __device__ __forceinline__ size_t myers_band_scratch(int64_t maxlen, in
     return (size_t)((2 * maxlen + 24 * ((maxlen >> 6) + WPL + 1) + 15) & ~15ll);   // pattern codes, text codes, 3 plane words per pattern word
 }
 
+// the wavefront is a long dependent chain per warp: resident warps matter, so the register budget is pinned per WPL
 template <int G, int WPL, bool STRINGS, bool HI>
-__global__ void __launch_bounds__(128) k_myers_band(MyersArgs a, StringPairs sp) {
+__global__ void __launch_bounds__(128, WPL <= 1 ? 8 : WPL == 2 ? 6 : WPL == 3 ? 5 : 4) k_myers_band(MyersArgs a, StringPairs sp) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(128) k_myers_band(MyersArgs a, StringPairs sp)
         for (int64_t x = gl; x < (int64_t)ge.NG * WPL; x += G) band_build_word(pat, m, ge.pad, x, planes + 3 * x);
         __syncwarp();
         BandLane<WPL> L;
-        band_lane_init(L, ge, planes, gl, valid);
+        band_lane_init(L, ge, planes, txt, gl, valid);
         int steps = valid ? ge.n + ge.NG - 1 : 0;
         if (G < 32) {
 #pragma unroll
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(128) k_myers_band(MyersArgs a, StringPairs sp)
         uint32_t e_out = 0;
         for (int s = 0; s < steps; ++s) {
             const uint32_t recv = __shfl_sync(0xffffffffu, e_out, (gl - 1) & (G - 1), G);
-            e_out = band_lane_step<G, WPL, HI>(L, ge, planes, txt, s, recv, e_out, a.one, a.two);
+            e_out = band_lane_step<G, WPL, HI>(L, ge, planes, s, recv, e_out, a.one, a.two);
         }
         int score = L.score;
 #pragma unroll

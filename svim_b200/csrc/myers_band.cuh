@@ -30,6 +30,7 @@ static inline void mb_add64(uint32_t al, uint32_t bl, uint32_t ah, uint32_t bh, 
     sl = (uint32_t)s; sh = (uint32_t)(s >> 32);
 }
 static inline int mb_popcll(uint64_t x) { return __builtin_popcountll(x); }
+static inline const uint8_t* mb_ptr_inc(const uint8_t* p, uint32_t) { return p + 1; }
 #else
 __device__ __forceinline__ uint32_t mb_imad(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
@@ -42,6 +43,12 @@ __device__ __forceinline__ void mb_add64(uint32_t al, uint32_t bl, uint32_t ah, 
     asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(sl), "=r"(sh) : "r"(al), "r"(bl), "r"(ah), "r"(bh));
 }
 __device__ __forceinline__ int mb_popcll(uint64_t x) { return __popcll(x); }
+// p + 1 as IMAD.WIDE (FMA pipe; `one` is a kernel argument the compiler cannot fold)
+__device__ __forceinline__ const uint8_t* mb_ptr_inc(const uint8_t* p, uint32_t one) {
+    unsigned long long q = (unsigned long long)p;
+    asm("mad.wide.u32 %0, %1, %1, %0;" : "+l"(q) : "r"(one));
+    return (const uint8_t*)q;
+}
 #endif
 
 // ---- pair bins: a group of G lanes owns one pair with WPL words per lane ------------------------------------------
@@ -110,7 +117,7 @@ SVIM_D uint32_t word_step(Word32& w, uint32_t m0, uint32_t m1, uint32_t m2, uint
 // The ALU pipe (LOP3/SHF/IADD3, one warp instruction every two cycles per SM sub-partition) bounds the plain
 // formulation while the FMA pipe idles.  Here every 64-row word is two independent 32-row blocks chained through
 // their horizontal deltas, and whatever can be phrased as a multiply-add runs as IMAD on the FMA pipe:
-//   Eq      = P0 + c1*(P1-P0) + c2*(P2-P0) + c3*(P3-P0)      (c = one-hot of the text symbol; 3 IMAD, no LOP3)
+//   Eq      = P0 + b0*(P1-P0) + b1*(P2-P0) + b0b1*(P3-P2-P1+P0)   (b1 b0 = text symbol code; 3 IMAD, no LOP3)
 //   s       = (Eq|hn) & Pv + Pv                               (IMAD with multiplicand `one`)
 //   Ph<<1|hp = Ph*two + hp,  Mh<<1|hn = Mh*two + hn           (IMAD; bit 0 is free after the shift)
 // leaving 10 ALU-pipe and 6 FMA-pipe instructions per 32 cells instead of ~16 ALU.
@@ -124,7 +131,8 @@ SVIM_D void wordq_from_planes(WordQ& w, uint64_t pl0, uint64_t pl1, uint64_t rea
 #endif
     for (int h = 0; h < 2; ++h) {
         const uint32_t p0 = (uint32_t)(P0 >> (32 * h));
-        w.q0[h] = p0; w.d1[h] = (uint32_t)(P1 >> (32 * h)) - p0; w.d2[h] = (uint32_t)(P2 >> (32 * h)) - p0; w.d3[h] = (uint32_t)(P3 >> (32 * h)) - p0;
+        const uint32_t p1 = (uint32_t)(P1 >> (32 * h)), p2 = (uint32_t)(P2 >> (32 * h)), p3 = (uint32_t)(P3 >> (32 * h));
+        w.q0[h] = p0; w.d1[h] = p1 - p0; w.d2[h] = p2 - p0; w.d3[h] = p3 - p2 - p1 + p0;
         w.pv[h] = (uint32_t)(pv0 >> (32 * h)); w.mv[h] = 0u;
     }
 }
@@ -183,22 +191,23 @@ SVIM_HD void band_build_word(const uint8_t* pat, int64_t m, int32_t pad, int64_t
 template <int WPL>
 struct BandLane {
     WordQ w[WPL];
-    int32_t g;          // word group this lane is on
-    int32_t cs, ce;     // its columns
-    int32_t top_from;   // columns >= top_from have no upstream neighbour inside the band
-    int32_t acc_end;    // its bottom-row deltas count for columns < acc_end
+    int32_t g;            // word group this lane is on
+    int32_t s_lo, s_hi;   // wavefront steps on which that group is inside the band (group q runs column c at step c + q)
+    int32_t s_top;        // steps >= s_top have no upstream neighbour inside the band
+    int32_t s_acc;        // the group's bottom-row deltas count on steps < s_acc
     int32_t score;
+    const uint8_t* tp;    // text symbol code of this step's column
 };
 
 template <int WPL>
 SVIM_D void band_load_group(BandLane<WPL>& L, const BandGeom& ge, const uint64_t* planes) {
     const int32_t base = 64 * WPL * L.g - ge.pad;                 // pattern row of the group's first bit
     const int32_t lo = base - ge.b, hi = base + 64 * WPL - 1 + ge.a;
-    L.cs = lo > 0 ? lo : 0;
-    L.ce = hi < ge.n - 1 ? hi : ge.n - 1;
-    L.top_from = L.g == 0 ? INT32_MIN : base + ge.a;
+    L.s_lo = (lo > 0 ? lo : 0) + L.g;
+    L.s_hi = (hi < ge.n - 1 ? hi : ge.n - 1) + L.g;
+    L.s_top = L.g == 0 ? INT32_MIN : base + ge.a + L.g;
     const int32_t nxt = base + 64 * WPL - ge.b;
-    L.acc_end = (L.g + 1 < ge.NG) ? (nxt > 0 ? nxt : 0) : ge.n;
+    L.s_acc = ((L.g + 1 < ge.NG) ? (nxt > 0 ? nxt : 0) : ge.n) + L.g;
 #ifndef SVIM_HOST_ONLY
 #pragma unroll
 #endif
@@ -209,8 +218,9 @@ SVIM_D void band_load_group(BandLane<WPL>& L, const BandGeom& ge, const uint64_t
 }
 
 template <int WPL>
-SVIM_D void band_lane_init(BandLane<WPL>& L, const BandGeom& ge, const uint64_t* planes, int gl, bool valid) {
-    L.g = valid ? gl : ge.NG; L.score = 0; L.cs = 0; L.ce = -1; L.top_from = 0; L.acc_end = 0;
+SVIM_D void band_lane_init(BandLane<WPL>& L, const BandGeom& ge, const uint64_t* planes, const uint8_t* txt, int gl, bool valid) {
+    L.g = valid ? gl : ge.NG; L.score = 0; L.s_lo = L.s_hi = INT32_MAX; L.s_top = 0; L.s_acc = 0;
+    L.tp = txt - gl;                   // column of step s = s - g; never read outside [s_lo, s_hi]
     if (L.g < ge.NG) band_load_group(L, ge, planes);
     else {
 #ifndef SVIM_HOST_ONLY
@@ -222,20 +232,21 @@ SVIM_D void band_lane_init(BandLane<WPL>& L, const BandGeom& ge, const uint64_t*
 }
 
 // One wavefront step of one lane.  recv = the upstream lane's packet of the previous step, e_out = this lane's
-// packet (horizontal delta + 1 at the bottom of its group), kept when the lane idles.
+// packet (horizontal delta + 1 at the bottom of its group), kept when the lane idles.  The kernel is bound by the
+// ALU pipe, so the bookkeeping stays small: windows are kept in step space (two compares decide rotate / active),
+// the text pointer advances on the FMA pipe.
 template <int G, int WPL, bool HI>
-SVIM_D uint32_t band_lane_step(BandLane<WPL>& L, const BandGeom& ge, const uint64_t* planes, const uint8_t* txt, int32_t s, uint32_t recv,
+SVIM_D uint32_t band_lane_step(BandLane<WPL>& L, const BandGeom& ge, const uint64_t* planes, int32_t s, uint32_t recv,
                                 uint32_t e_out, uint32_t one, uint32_t two) {
-    int32_t c = s - L.g;
-    if (c > L.ce && L.g < ge.NG) {     // the band has left this group: rotate to the lane's next one
-        L.g += G; c -= G;
+    if (s > L.s_hi) {                  // the band has left this group: rotate to the lane's next one (s_hi = INT32_MAX once the lane is done)
+        L.g += G; L.tp -= G;
         if (L.g < ge.NG) band_load_group(L, ge, planes);
+        else L.s_lo = L.s_hi = INT32_MAX;
     }
-    if (L.g < ge.NG && c >= L.cs && c <= L.ce) {
-        const uint32_t code = txt[c];
-        const uint32_t b0 = code & 1u, b1 = (code >> 1) & 1u;
-        const uint32_t c3 = b0 & b1, c1 = b0 ^ c3, c2 = b1 ^ c3;
-        const uint32_t e = c >= L.top_from ? 2u : recv;
+    if (s >= L.s_lo) {
+        const uint32_t code = *L.tp;
+        const uint32_t c1 = code & 1u, c2 = code >> 1, c3 = c1 & c2;      // b0, b1, b0b1 (codes 0..3)
+        const uint32_t e = s >= L.s_top ? 2u : recv;
         uint32_t hp = e >> 1, hn = 1u >> e;
 #ifndef SVIM_HOST_ONLY
 #pragma unroll
@@ -245,7 +256,8 @@ SVIM_D uint32_t band_lane_step(BandLane<WPL>& L, const BandGeom& ge, const uint6
             block_step<HI>(L.w[k].q0[1], L.w[k].d1[1], L.w[k].d2[1], L.w[k].d3[1], L.w[k].pv[1], L.w[k].mv[1], c1, c2, c3, one, two, hp, hn);
         }
         e_out = 1u + hp - hn;
-        if (c < L.acc_end) L.score += (int32_t)hp - (int32_t)hn;
+        if (s < L.s_acc) L.score += (int32_t)hp - (int32_t)hn;
     }
+    L.tp = mb_ptr_inc(L.tp, one);
     return e_out;
 }

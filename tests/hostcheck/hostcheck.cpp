@@ -75,11 +75,11 @@ static long long band_emulate(const uint8_t* pat, long long m, const uint8_t* tx
     for (long long w = 0; w < (long long)ge.NG * WPL; ++w) band_build_word(pat, m, ge.pad, w, planes.data() + 3 * w);
     BandLane<WPL> L[G];
     uint32_t e_out[G], recv[G];
-    for (int l = 0; l < G; ++l) { band_lane_init(L[l], ge, planes.data(), l, true); e_out[l] = 0; }
+    for (int l = 0; l < G; ++l) { band_lane_init(L[l], ge, planes.data(), txt, l, true); e_out[l] = 0; }
     const int32_t steps = ge.n + ge.NG - 1;
     for (int32_t s = 0; s < steps; ++s) {
         for (int l = 0; l < G; ++l) recv[l] = e_out[(l - 1) & (G - 1)];
-        for (int l = 0; l < G; ++l) e_out[l] = band_lane_step<G, WPL, HI>(L[l], ge, planes.data(), txt, s, recv[l], e_out[l], 1u, 2u);
+        for (int l = 0; l < G; ++l) e_out[l] = band_lane_step<G, WPL, HI>(L[l], ge, planes.data(), s, recv[l], e_out[l], 1u, 2u);
     }
     long long d = m;
     for (int l = 0; l < G; ++l) d += L[l].score;
