@@ -180,6 +180,11 @@ int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, 
 /* D2H: which = 0 main list (sv_signatures), 1 = translocation_signatures_all_bnds.
  * out_sigs[n_signatures] in the reference's emission order; out_ins[ins_bytes] ASCII. */
 int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, uint8_t* out_ins);
+/* The same lists without a second copy: svimgpu_collect_host[_querysorted] starts a D2H of both lists into pinned memory
+ * owned by the context, on a copy stream, so it overlaps CLUSTER.  This call waits for that copy and returns the host
+ * pointers (valid until the next collect / exchange / destroy on this context); *sigs = NULL when there is no host copy
+ * (lists produced by svimgpu_collect on a resident buffer, or replaced by svimgpu_exchange_signatures). */
+int svimgpu_signatures_host(svimgpu_ctx* ctx, int which, const svim_sig** sigs, const uint8_t** ins);
 
 /* ---- CLUSTER: cluster_sv_signatures (SVIM_CLUSTER.py:7-26) ------------------------ */
 /* Use the device-resident result of svimgpu_collect as the clustering input. */

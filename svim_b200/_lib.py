@@ -95,6 +95,7 @@ EXPORTS = {
     "svimgpu_collect_host": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
     "svimgpu_collect_host_querysorted": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
     "svimgpu_fetch_signatures": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "svimgpu_signatures_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "svimgpu_use_collected": (C.c_int, [C.c_void_p, C.c_int]),
     "svimgpu_set_signatures": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "svimgpu_cluster": (C.c_int, [C.c_void_p, C.POINTER(ClusterStats)]),
@@ -250,6 +251,14 @@ class Context:
     def fetch_signatures(self, which, stats: CollectStats):
         n = stats.n_signatures if which == 0 else stats.n_twin_signatures
         nb = stats.ins_bytes if which == 0 else stats.twin_ins_bytes
+        # collect_host mirrors the lists into pinned host memory while CLUSTER runs: hand out views of that copy
+        # (valid until the next collect on this context; callers that keep them longer must .copy())
+        ps, pi = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.svimgpu_signatures_host(self.h, which, C.byref(ps), C.byref(pi)))
+        if ps.value:
+            sigs = np.frombuffer((C.c_uint8 * (n * SIG_DTYPE.itemsize)).from_address(ps.value), dtype=SIG_DTYPE) if n else np.zeros(0, dtype=SIG_DTYPE)
+            ins = np.frombuffer((C.c_uint8 * nb).from_address(pi.value), dtype=np.uint8) if nb else np.zeros(0, dtype=np.uint8)
+            return sigs, ins
         sigs = np.zeros(n, dtype=SIG_DTYPE)
         ins = np.zeros(nb, dtype=np.uint8)
         self._check(self.lib.svimgpu_fetch_signatures(self.h, which, _ptr(sigs), _ptr(ins)))

@@ -35,6 +35,9 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     cudaEventCreate(&ctx->user_ev[0]); cudaEventCreate(&ctx->user_ev[1]);
     for (int i = 0; i < SVIM_AUX_STREAMS; ++i) cudaStreamCreateWithFlags(&ctx->aux_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i <= SVIM_AUX_STREAMS; ++i) cudaEventCreateWithFlags(&ctx->aux_ev[i], cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_collect_done, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&ctx->ev_host_copy[i], cudaEventDisableTiming);
     timings_begin(ctx);
     memset(&ctx->cstats, 0, sizeof(ctx->cstats)); memset(&ctx->clstats, 0, sizeof(ctx->clstats));
     myers_init_symcode();
@@ -66,6 +69,9 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     ctx->d_stage.release(); ctx->d_stage_off.release();
     ctx->d_qs_info.release(); ctx->d_qs_grp.release(); ctx->d_qs_segsum.release(); ctx->d_qs_mem_off.release(); ctx->d_qs_mem_idx.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < 2; ++i) { if (ctx->h_out[i]) cudaFreeHost(ctx->h_out[i]); cudaEventDestroy(ctx->ev_host_copy[i]); }
+    cudaEventDestroy(ctx->ev_collect_done); cudaStreamDestroy(ctx->copy_stream);
     for (int i = 0; i < 2 * T_N; ++i) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < SVIM_AUX_STREAMS; ++i) cudaStreamDestroy(ctx->aux_stream[i]);
     for (int i = 0; i <= SVIM_AUX_STREAMS; ++i) cudaEventDestroy(ctx->aux_ev[i]);
@@ -159,12 +165,40 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
 int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats) {
     if (!ctx) return SVIMGPU_ERR_ARG;
     cudaSetDevice(ctx->device);
+    // a host copy of the previous lists may still be in flight on the copy stream: the lists are about to be rewritten
+    if (ctx->host_copy[0] || ctx->host_copy[1]) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
     double h2d = ctx->ms[T_H2D];
     timings_begin(ctx);
     int rc = collect_run(ctx, stats);
     timings_end(ctx);
     ctx->ms[T_H2D] = h2d;
     return rc;
+}
+
+static size_t host_copy_ins_off(const SigSet& set) { return ((size_t)set.n * sizeof(svim_sig) + 255) & ~(size_t)255; }
+
+// Start copying the collected lists to pinned host memory on the copy stream; CLUSTER (ctx->stream) runs meanwhile.
+static int start_host_copy(svimgpu_ctx* ctx) {
+    SVIM_CUDA(cudaEventRecord(ctx->ev_collect_done, ctx->stream));
+    SVIM_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_collect_done, 0));
+    for (int w = 0; w < 2; ++w) {
+        SigSet& set = ctx->sets[w];
+        ctx->host_copy[w] = false;
+        if (w == 1 && !ctx->params.all_bnds) continue;
+        const size_t ins_off = host_copy_ins_off(set), need = ins_off + (size_t)set.ins_bytes + 256;
+        if (need > ctx->h_out_cap[w]) {
+            if (ctx->h_out[w]) cudaFreeHost(ctx->h_out[w]);
+            ctx->h_out[w] = nullptr; ctx->h_out_cap[w] = 0;
+            const size_t want = need + need / 4;
+            SVIM_CUDA(cudaMallocHost((void**)&ctx->h_out[w], want));
+            ctx->h_out_cap[w] = want;
+        }
+        if (set.n) SVIM_CUDA(cudaMemcpyAsync(ctx->h_out[w], set.recs.p, (size_t)set.n * sizeof(svim_sig), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (set.ins_bytes) SVIM_CUDA(cudaMemcpyAsync(ctx->h_out[w] + ins_off, set.ins.p, (size_t)set.ins_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        SVIM_CUDA(cudaEventRecord(ctx->ev_host_copy[w], ctx->copy_stream));
+        ctx->host_copy[w] = true;
+    }
+    return 0;
 }
 
 int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats) {
@@ -174,7 +208,19 @@ int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect
     rc = svimgpu_collect(ctx, stats);
     ctx->have_soa = false;      // the host SEQ pointers must not outlive this call
     ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
+    if (!rc) rc = start_host_copy(ctx);
     return rc;
+}
+
+int svimgpu_signatures_host(svimgpu_ctx* ctx, int which, const svim_sig** sigs, const uint8_t** ins) {
+    if (!ctx || which < 0 || which > 1 || !sigs || !ins) return SVIMGPU_ERR_ARG;
+    *sigs = nullptr; *ins = nullptr;
+    if (!ctx->collected || !ctx->host_copy[which]) return 0;     // no host copy (resident collect, or the lists were exchanged): use svimgpu_fetch_signatures
+    cudaSetDevice(ctx->device);
+    SVIM_CUDA(cudaEventSynchronize(ctx->ev_host_copy[which]));
+    *sigs = (const svim_sig*)ctx->h_out[which];
+    *ins = ctx->h_out[which] + host_copy_ins_off(ctx->sets[which]);
+    return 0;
 }
 
 int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats) {
@@ -227,6 +273,7 @@ int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, 
     rc = svimgpu_collect(ctx, stats);
     ctx->qs_mode = false;
     ctx->have_soa = false; ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
+    if (!rc) rc = start_host_copy(ctx);
     return rc;
 }
 

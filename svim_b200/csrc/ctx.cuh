@@ -114,6 +114,12 @@ struct svimgpu_ctx {
     int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
     svim_collect_stats cstats;
 
+    // host copy of the collected lists (collect_host): pinned, filled on a copy stream while CLUSTER runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_collect_done = nullptr, ev_host_copy[2] = {nullptr, nullptr};
+    uint8_t* h_out[2] = {nullptr, nullptr}; size_t h_out_cap[2] = {0, 0};
+    bool host_copy[2] = {false, false};      // sets[i] is (being) mirrored in h_out[i]: records, then the INS blob at ins_off
+
     // cluster state
     DevBuf d_csig, d_csig_sorted, d_cins;   // input signatures (emission order / key order), INS blob when uploaded
     const uint8_t* cluster_ins = nullptr; int64_t cluster_ins_bytes = 0;

@@ -82,6 +82,8 @@ static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_
 
 extern "C" {
 
+static int start_host_copy(svimgpu_ctx* ctx);   // api.cu
+
 int svimgpu_nccl_unique_id(uint8_t* id_bytes) {
     if (!id_bytes) return SVIMGPU_ERR_ARG;
     ncclUniqueId id;
@@ -107,6 +109,9 @@ int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collec
     if (!ctx->collected) { ctx->set_error(SVIMGPU_ERR_STATE, "collect has not run"); return SVIMGPU_ERR_STATE; }
     if (!ctx->nccl_comm) { ctx->set_error(SVIMGPU_ERR_STATE, "svimgpu_comm_init not called"); return SVIMGPU_ERR_STATE; }
     cudaSetDevice(ctx->device);
+    // the local lists are replaced by the global ones: a host copy in flight (collect_host) is dropped and restarted at the end
+    const bool want_host = ctx->host_copy[0] || ctx->host_copy[1];
+    if (want_host) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
     timings_begin(ctx);
     const int R = ctx->nranks;
     {
@@ -141,7 +146,7 @@ int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collec
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     timings_end(ctx);
     if (stats) *stats = ctx->cstats;
-    return 0;
+    return want_host ? start_host_copy(ctx) : 0;
 }
 
 int svimgpu_barrier_max(svimgpu_ctx* ctx, double* value) {
