@@ -199,9 +199,40 @@ class AlignmentFile:
             a._tags["SA"] = sa
         return a
 
-    def fetch(self, *args, **kwargs):
-        for i in range(self._batch.n):
-            yield self.segment(i)
+    def fetch(self, *args, contig=None, start=None, stop=None, **kwargs):
+        """No region: every record in file order.  Region (htslib bam_itr semantics on a coordinate-sorted file): records of
+        `contig` with pos < stop and bam_endpos > start, in file order; bam_endpos = pos + reference length for mapped
+        records with a CIGAR (a zero length counts as 1), else pos + 1."""
+        b = self._batch
+        if contig is None:
+            for i in range(b.n):
+                yield self.segment(i)
+            return
+        tid = b.get_tid(contig)
+        if tid < 0:
+            raise ValueError("invalid contig `%s`" % contig)
+        if start is None:
+            start = 0
+        if stop is None:
+            stop = int(b.contig_lengths[tid])
+        if start > stop:
+            raise ValueError("invalid coordinates: start (%i) > stop (%i)" % (start, stop))
+        for i in range(b.n):
+            if int(b.tid[i]) != tid or int(b.pos[i]) >= stop:
+                continue
+            pos = int(b.pos[i])
+            end = pos + 1
+            if not (int(b.flag[i]) & 0x4) and int(b.n_cigar[i]) > 0:
+                rlen = sum(n for op, n in b.cigartuples(i) if op in (0, 2, 3, 7, 8))
+                end = pos + (rlen if rlen else 1)
+            if end > start:
+                yield self.segment(i)
+
+    def get_reference_length(self, contig):
+        tid = self._batch.get_tid(contig)
+        if tid < 0:
+            raise KeyError(contig)
+        return int(self._batch.contig_lengths[tid])
 
     def close(self):
         pass
