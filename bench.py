@@ -129,6 +129,70 @@ def cpu_baseline(batch, genome, target_seconds=15.0):
                       "edit distance by oracle/editdist.c Myers (edlib stand-in)" % (n, batch.n, t1 - t0, t2 - t1, len(sigs))}
 
 
+def genotype_leg(ctx, batch, clusters, members, sigs, args):
+    """SURVEY.md §8f rank 2, outside the timed step: GENOTYPE (SVIM_genotyping.py:34-93) of the DEL and INS candidates COMBINE makes
+    1:1 from this step's clusters, on the record rows the e2e step left in HBM.  Reports the one-off preparation (k_ref_end streams
+    every CIGAR again: HBM-bound), the per-call time through the C ABI from host candidate arrays, and the oracle beside it."""
+    from svim_b200 import _lib
+    from svim_b200.SVIM_genotyping import candidate_arrays_from_clusters
+    gp = _lib.GenoParams.from_options()
+    out = {"unit": "candidates/s", "types": {}}
+    prep = None
+    n_all = 0; ms_all = 0.0
+    per_type = {}
+    for tname in ("DEL", "INS"):
+        cands, var_ids, _sel = candidate_arrays_from_clusters(clusters, members, sigs, _lib.TYPE_CODE[tname])
+        if len(cands) == 0:
+            continue
+        res = ctx.genotype(_lib.TYPE_CODE[tname], gp, cands, var_ids, batch.contig_lengths)      # first call also prepares
+        tm = ctx.timings()
+        if prep is None:
+            prep = tm.get("genotype_prepare", 0.0)
+        ms = []
+        for _ in range(max(3, args.steps)):
+            ctx.timer_start()
+            res = ctx.genotype(_lib.TYPE_CODE[tname], gp, cands, var_ids, batch.contig_lengths)
+            ms.append(ctx.timer_stop())
+        m = float(np.mean(ms))
+        per_type[tname] = (cands, var_ids, res)
+        calls = {g: int((res["genotype"] == i).sum()) for i, g in enumerate(_lib.GENOTYPES)}
+        out["types"][tname] = {"candidates": int(len(cands)), "ms_per_call": round(m, 4), "records_fetched": int(res["n_fetched"].sum()),
+                               "mean_ref_reads": float(res["ref_reads"].mean()), "calls": calls}
+        n_all += len(cands); ms_all += m
+    if not n_all:
+        return None
+    out["value"] = n_all / (ms_all * 1e-3)
+    out["prepare_ms"] = prep
+    rows_bytes = batch.n * (4 + 8 + 2 + 4 + 4) + 4 * int(batch.n_cigar.sum(dtype=np.int64))
+    peak, _src = measured_peak()
+    out["prepare_note"] = ("one-off per resident buffer: k_ref_end (bam_endpos of every record, %.2f GB of CIGAR + rows) + contig row bounds + "
+                           "running maximum; %.0f GB/s if all of it were k_ref_end = %.2f of the measured HBM peak"
+                           % (rows_bytes / 1e9, rows_bytes / max(prep, 1e-6) / 1e6, rows_bytes / max(prep, 1e-6) / 1e6 / peak)) if prep else None
+    if not args.no_cpu_baseline:
+        # oracle on a bounded sample of the same candidates (about 2 s of CPU), checked against the GPU result on the way
+        from oracle import svim_oracle as orc
+        t0 = time.perf_counter(); ends = orc.record_reference_ends(batch); t_ends = time.perf_counter() - t0
+        done = 0; t_cpu = 0.0; mismatches = 0
+        for tname, (cands, var_ids, res) in per_type.items():
+            k = min(len(cands), 400)
+            ocs = []
+            for i in range(k):
+                c = cands[i]
+                ids = var_ids[int(c["variant_off"]):int(c["variant_off"]) + int(c["n_variant_reads"])]
+                ocs.append(orc.GenoCand(batch.contig_names[int(c["tid"])], int(c["start"]), int(c["end"]), 10, [batch.qname(int(q)) for q in ids]))
+            t0 = time.perf_counter(); orc.genotype(ocs, batch, tname, orc.GenoParams(), ends); t_cpu += time.perf_counter() - t0
+            for i, oc in enumerate(ocs):
+                f = float(res["support_fraction"][i])
+                got = ["." if f != f else f, _lib.GENOTYPES[int(res["genotype"][i])], int(res["ref_reads"][i]), int(res["alt_reads"][i])]
+                mismatches += got != oc.result()
+            done += k
+        out["cpu_baseline"] = {"value": done / t_cpu, "unit": "candidates/s", "cores": 1, "kind": "port",
+                               "sample": "first %d candidates per type; oracle region fetch is a numpy mask over all records; "
+                                         "+ %.2f s once for the reference ends" % (done, t_ends),
+                               "mismatches_vs_gpu": int(mismatches)}
+    return out
+
+
 def run_reference(args):
     rank, local_rank, world = env_rank()
     if rank != 0:
@@ -167,6 +231,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
     ap.add_argument("--with-bam", action="store_true", help="also time the path starting from a BAM file on disk (native multi-threaded decode)")
+    ap.add_argument("--profile-genotype", action="store_true", help="with --profile-steps: also run the GENOTYPE leg (for ncu)")
     ap.add_argument("--scan-variant", type=int, default=None, help="0 = 128-bit LDG streaming scan, 1 = cp.async.bulk ring (default: library default)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -231,6 +296,10 @@ def main():
     launches = ctx.launch_count() - launches0
     n_sigs = (xst.n_signatures if xst else cst.n_signatures)
     if args.profile_steps:
+        if args.profile_genotype and world == 1:
+            sigs, _ins = ctx.fetch_signatures(0, cst)
+            args.no_cpu_baseline = True
+            print(json.dumps(genotype_leg(ctx, batch, clusters, members, sigs, args)))
         return
 
     # ---------------- e2e: host buffers through the C ABI, copies inside the timed region --------
@@ -272,6 +341,7 @@ def main():
         obj_s = time.perf_counter() - t0
     for a in pinned:
         ctx.unpin(a)
+    geno_leg = genotype_leg(ctx, batch, clusters, members, sigs, args) if world == 1 else None
     bam_leg = None
     if args.with_bam and world == 1:
         import tempfile
@@ -323,6 +393,8 @@ def main():
     }
     if bam_leg:
         out["e2e_from_bam"] = bam_leg
+    if geno_leg:
+        out["genotype"] = geno_leg
     if clst.myers_cells and "myers_edit_distance" in out["stages_ms"]:
         # gcups = cells of the full DP matrices per second (what an unbanded computation would touch); the banded first pass
         # computes band_cells of them, pairs it hands over are recomputed in full

@@ -206,6 +206,39 @@ int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* m
  * partition order, part_off[n_partitions+1]; call after svimgpu_partition or svimgpu_cluster. */
 int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* order, uint32_t* part_off);
 
+/* ---- GENOTYPE: genotype(candidates, bam, type, options) (SVIM_genotyping.py:34-93; call sites svim:161-170) ------- */
+/* Genotyping options (SVIM_input_parsing.py:404-437); minimum_score (:39) is applied by the caller, which only submits
+ * the candidates that pass it. */
+typedef struct {
+    int32_t min_mapq;               /* 20 */
+    int32_t minimum_depth;          /* 4 */
+    double homozygous_threshold;    /* 0.8 */
+    double heterozygous_threshold;  /* 0.2 */
+} svim_geno_params;
+/* What genotype() reads from one candidate. 32 bytes. */
+typedef struct {
+    int64_t start, end;             /* get_source() for DEL/INV, get_destination() for INS/DUP_INT (:43-48) */
+    int32_t tid;                    /* contig of that locus (reference id of the record buffer) */
+    uint32_t n_variant_reads;       /* distinct read names among candidate.members (:51) = alt_reads */
+    uint64_t variant_off;           /* their qname ids: variant_qname_ids[variant_off .. +n), ascending */
+} svim_geno_cand;
+/* What genotype() writes to one candidate (:78-93). 24 bytes. */
+typedef struct {
+    double support_fraction;        /* NaN = "." */
+    int32_t ref_reads, alt_reads;
+    uint8_t genotype;               /* 0 "1/1", 1 "0/1", 2 "0/0", 3 "./." */
+    uint8_t status;                 /* 0 ok; what the reference raises: 1 TypeError (reference_end None: record without CIGAR),
+                                       2 ValueError (fetch start > stop), 3 ZeroDivisionError (no reads and minimum_depth <= 0) */
+    uint16_t pad;
+    uint32_t n_fetched;             /* records the region fetch (:49) returned before the 500-alignment cap (:57) stopped it */
+} svim_geno_result;
+/* Genotype n candidates of one type (SVIM_DEL, SVIM_INV, SVIM_INS, SVIM_DUP_INT) against the alignment records left on the
+ * device by the last svimgpu_upload_alignments / svimgpu_collect_host (rows + CIGAR; they must be coordinate-sorted, as
+ * bam.fetch needs an index: svim:93-98).  contig_lengths[n_contigs] = bam.get_reference_length (:48). */
+int svimgpu_genotype(svimgpu_ctx* ctx, int32_t type, const svim_geno_params* params, int64_t n, const svim_geno_cand* cands,
+                     const uint32_t* variant_qname_ids, int64_t n_variant_ids, const int64_t* contig_lengths, int32_t n_contigs,
+                     svim_geno_result* out);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------ */
 /* id_bytes: 128-byte ncclUniqueId from svimgpu_nccl_unique_id on rank 0. */
 int svimgpu_nccl_unique_id(uint8_t* id_bytes /*128*/);

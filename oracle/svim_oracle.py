@@ -835,3 +835,115 @@ def fcluster_distance_restated(Z, t: float, n: int):
             leader = -1
         stack.pop()
     return T
+
+
+# ---------------------------------------------------------------------------
+# GENOTYPE (SVIM_genotyping.py:34-93) — SURVEY.md §8f rank 2
+# ---------------------------------------------------------------------------
+class GenoParams:
+    """Genotyping options and defaults (SVIM_input_parsing.py:404-437)."""
+
+    def __init__(self, **kw):
+        self.min_mapq = 20
+        self.minimum_score = 3
+        self.minimum_depth = 4
+        self.homozygous_threshold = 0.8
+        self.heterozygous_threshold = 0.2
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise AttributeError(k)
+            setattr(self, k, v)
+
+
+class GenoCand:
+    """What genotype() reads from a candidate (SVIM_genotyping.py:39-51): the locus — get_source() for DEL/INV,
+    get_destination() for INS/DUP_INT (SVCandidate.py:20-21,216-217,451-452) —, the score and the member read names;
+    and the four attributes it writes (:75-93)."""
+    __slots__ = ("contig", "start", "end", "score", "reads", "support_fraction", "genotype", "ref_reads", "alt_reads")
+
+    def __init__(self, contig, start, end, score, reads):
+        self.contig, self.start, self.end, self.score, self.reads = contig, start, end, score, list(reads)
+        self.support_fraction, self.genotype, self.ref_reads, self.alt_reads = ".", "./.", None, None   # constructor defaults
+
+    def result(self):
+        return [self.support_fraction, self.genotype, self.ref_reads, self.alt_reads]
+
+
+def record_reference_ends(batch) -> np.ndarray:
+    """htslib bam_endpos per record: pos + reference length (M,D,N,=,X) for mapped records with a CIGAR, a zero length
+    counting as 1; pos + 1 otherwise.  pysam's `reference_end` is this value, or None for unmapped / CIGAR-less records."""
+    pos = np.asarray(batch.pos, dtype=np.int64)
+    consumes = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1] + [0] * 7, dtype=np.int64)
+    cs = np.zeros(batch.cigar.size + 1, dtype=np.int64)
+    np.cumsum((batch.cigar >> 4).astype(np.int64) * consumes[batch.cigar & 15], out=cs[1:])
+    off = batch.cigar_off.astype(np.int64)
+    rlen = cs[off + batch.n_cigar.astype(np.int64)] - cs[off]
+    rlen[((batch.flag & 0x4) != 0) | (batch.n_cigar == 0)] = 0
+    return pos + np.maximum(rlen, 1)
+
+
+def fetch_region(batch, ends, tid, start, stop):
+    """pysam AlignmentFile.fetch(contig, start, stop) on a coordinate-sorted, indexed file (htslib bam_itr): the records of
+    the contig with pos < stop and bam_endpos > start, in file order."""
+    if start > stop:
+        raise ValueError("invalid coordinates: start (%i) > stop (%i)" % (start, stop))
+    idx = np.nonzero((batch.tid == tid) & (batch.pos < stop) & (ends > start))[0]
+    return idx.tolist()
+
+
+def genotype(cands: List[GenoCand], batch, type: str, gp: GenoParams, ends=None):
+    """genotype (SVIM_genotyping.py:34-93).  Read identity is the read NAME (sets of query_name, :51,:53,:73,:77)."""
+    if ends is None:
+        ends = record_reference_ends(batch)
+    for cand in cands:
+        if cand.score < gp.minimum_score:                                     # :39-40
+            continue
+        contig, start, end = cand.contig, cand.start, cand.end
+        if type in ("INS", "DUP_INT"):
+            end = start                                                       # :45
+        tid = batch.get_tid(contig)
+        if tid < 0:
+            raise KeyError(contig)
+        contig_length = int(batch.contig_lengths[tid])
+        variant = set(cand.reads)                                             # :51
+        reference = set()
+        aln_no = 0
+        for i in fetch_region(batch, ends, tid, max(0, start - 1000), min(contig_length, end + 1000)):   # :49
+            if aln_no >= 500:                                                 # :57
+                break
+            name = batch.qname(int(batch.qname_id[i]))
+            if name in variant:                                               # :63-64
+                continue
+            flag = int(batch.flag[i])
+            if flag & 0x4 or flag & 0x100 or int(batch.mapq[i]) < gp.min_mapq:   # :65-66
+                continue
+            aln_no += 1
+            rs = int(batch.pos[i])
+            re_ = int(ends[i]) if int(batch.n_cigar[i]) > 0 else None         # pysam: None without a CIGAR -> TypeError if compared
+            if type in ("DEL", "INV"):                                        # :69-73
+                min_overlap = min((end - start) / 2, 2000)
+                if (rs < (end - min_overlap) and re_ > (end + 100)) or (rs < (start - 100) and re_ > (start + min_overlap)):
+                    reference.add(name)
+            if type in ("INS", "DUP_INT"):                                    # :74-76
+                if rs < (start - 100) and re_ > (end + 100):
+                    reference.add(name)
+        n_var, n_ref = len(variant), len(reference)
+        if n_var + n_ref >= gp.minimum_depth:                                 # :78-88
+            cand.support_fraction = n_var / (n_var + n_ref)
+            if cand.support_fraction >= gp.homozygous_threshold:
+                cand.genotype = "1/1"
+            elif gp.heterozygous_threshold <= cand.support_fraction < gp.homozygous_threshold:
+                cand.genotype = "0/1"
+            elif cand.support_fraction < gp.heterozygous_threshold:
+                cand.genotype = "0/0"
+            else:
+                cand.genotype = "./."
+        elif n_var + n_ref > 0:                                               # :89-91
+            cand.support_fraction = n_var / (n_var + n_ref)
+            cand.genotype = "./."
+        else:                                                                 # :92-94
+            cand.support_fraction = "."
+            cand.genotype = "./."
+        cand.ref_reads = n_ref
+        cand.alt_reads = n_var
+    return cands

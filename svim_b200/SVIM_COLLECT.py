@@ -158,6 +158,7 @@ def collect_arrays(batch: AlignmentBatch, options=None, ctx=None, querysorted=Fa
         ctx.set_contigs(batch.contig_names)
         ctx.contigs_key = tuple(batch.contig_names)
     stats = ctx.collect_host_querysorted(batch) if querysorted else ctx.collect_host(batch)
+    ctx.resident = batch            # rows + CIGAR stay in HBM (GENOTYPE reuses them, svim_b200/SVIM_genotyping.py)
     if stats.n_data_errors:
         raise _lib.SvimGpuError(-5, "%d reads carry SA tags the reference would raise on "
                                     "(unknown contig / non-integer field / empty CIGAR)" % stats.n_data_errors)

@@ -64,7 +64,28 @@ CSIG_DTYPE = np.dtype([("start", "<f8"), ("end", "<f8"), ("dpos", "<f8"), ("cont
 CLUSTER_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("dest_start", "<i8"), ("dest_end", "<i8"), ("score", "<f8"),
                           ("std_span", "<f8"), ("std_pos", "<f8"), ("member_off", "<u4"), ("size", "<u4"), ("type", "u1"),
                           ("dir1_rev", "u1"), ("dir2_rev", "u1"), ("pad0", "u1"), ("pad1", "<u4")])
+GENO_CAND_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("tid", "<i4"), ("n_variant_reads", "<u4"), ("variant_off", "<u8")])
+GENO_RESULT_DTYPE = np.dtype([("support_fraction", "<f8"), ("ref_reads", "<i4"), ("alt_reads", "<i4"), ("genotype", "u1"),
+                              ("status", "u1"), ("pad", "<u2"), ("n_fetched", "<u4")])
+GENOTYPES = ("1/1", "0/1", "0/0", "./.")
 assert SIG_DTYPE.itemsize == 48 and CSIG_DTYPE.itemsize == 64 and CLUSTER_DTYPE.itemsize == 72
+assert GENO_CAND_DTYPE.itemsize == 32 and GENO_RESULT_DTYPE.itemsize == 24
+
+
+class GenoParams(C.Structure):
+    _fields_ = [("min_mapq", C.c_int32), ("minimum_depth", C.c_int32), ("homozygous_threshold", C.c_double),
+                ("heterozygous_threshold", C.c_double)]
+
+    @classmethod
+    def from_options(cls, options=None, **kw):
+        """Genotyping options of the reference's Namespace (SVIM_input_parsing.py:404-437) or keywords."""
+        d = dict(min_mapq=20, minimum_depth=4, homozygous_threshold=0.8, heterozygous_threshold=0.2)
+        if options is not None:
+            for k in d:
+                if hasattr(options, k):
+                    d[k] = getattr(options, k)
+        d.update(kw)
+        return cls(**d)
 
 
 class ClusterStats(C.Structure):
@@ -102,6 +123,8 @@ EXPORTS = {
     "svimgpu_partition": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "svimgpu_fetch_clusters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "svimgpu_fetch_partitions": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
+    "svimgpu_genotype": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GenoParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_int32, C.c_void_p]),
     "svimgpu_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "svimgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "svimgpu_exchange_signatures": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CollectStats)]),
@@ -294,6 +317,16 @@ class Context:
         off = np.zeros(npart.value + 1, dtype=np.uint32)
         self._check(self.lib.svimgpu_fetch_partitions(self.h, C.byref(npart), _ptr(order), off.ctypes.data))
         return order, off
+
+    def genotype(self, type_code, gparams: "GenoParams", cands, variant_ids, contig_lengths):
+        """svimgpu_genotype on the resident records -> GENO_RESULT_DTYPE[len(cands)]."""
+        cands = np.ascontiguousarray(cands, dtype=GENO_CAND_DTYPE)
+        variant_ids = np.ascontiguousarray(variant_ids, dtype=np.uint32)
+        clen = np.ascontiguousarray(contig_lengths, dtype=np.int64)
+        out = np.zeros(len(cands), dtype=GENO_RESULT_DTYPE)
+        self._check(self.lib.svimgpu_genotype(self.h, type_code, C.byref(gparams), len(cands), _ptr(cands), _ptr(variant_ids), variant_ids.size,
+                                              clen.ctypes.data, clen.size, _ptr(out)))
+        return out
 
     def timings(self):
         ms = np.zeros(32, dtype=np.float64)

@@ -8,10 +8,11 @@
 #include "collect.cu"
 #include "cluster.cu"
 #include "nccl.cu"
+#include "genotype.cu"
 
 static const char* k_timing_names[T_N] = {
     "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
-    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange"};
+    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype"};
 
 extern "C" {
 
@@ -67,6 +68,7 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     for (int i = 0; i < 24; ++i) ctx->d_myers_scratch[i].release();
     ctx->d_myers_ctl.release();
     ctx->d_stage.release(); ctx->d_stage_off.release();
+    for (DevBuf* b : {&ctx->d_geno_end, &ctx->d_geno_max, &ctx->d_geno_rows, &ctx->d_geno_cand, &ctx->d_geno_out, &ctx->d_geno_var, &ctx->d_geno_clen}) b->release();
     ctx->d_qs_info.release(); ctx->d_qs_grp.release(); ctx->d_qs_segsum.release(); ctx->d_qs_mem_off.release(); ctx->d_qs_mem_idx.release();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamSynchronize(ctx->copy_stream);
@@ -157,6 +159,7 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
     ctx->cigar_words = s->cigar_words; ctx->seq_bytes = s->seq_bytes; ctx->sa_bytes = s->sa_bytes;
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->have_soa = true; ctx->collected = false;
+    ctx->rows_resident = true; ctx->geno_ready = false;
     ctx->lazy_seq = !with_seq; ctx->h_seq = with_seq ? nullptr : s->seq; ctx->h_seq_off = with_seq ? nullptr : s->seq_off; ctx->lazy_aln_base = 0;
     timings_end(ctx);
     return 0;
@@ -391,6 +394,16 @@ int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* 
 }
 
 // ---- micro entry points ------------------------------------------------------------------------
+int svimgpu_genotype(svimgpu_ctx* ctx, int32_t type, const svim_geno_params* gp, int64_t n, const svim_geno_cand* cands, const uint32_t* variant_qname_ids,
+                     int64_t n_variant_ids, const int64_t* contig_lengths, int32_t n_contigs, svim_geno_result* out) {
+    if (!ctx || !gp || n < 0 || n_contigs <= 0 || !contig_lengths || (n && (!cands || !out)) || (n_variant_ids && !variant_qname_ids)) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    timings_begin(ctx);
+    int rc = genotype_run(ctx, type, gp, n, cands, variant_qname_ids, n_variant_ids, contig_lengths, n_contigs, out);
+    timings_end(ctx);
+    return rc;
+}
+
 int svimgpu_cigar_indel(svimgpu_ctx* ctx, const uint32_t* cigar, int64_t n, int32_t min_len, int64_t* out, int64_t out_cap, int64_t* n_out) {
     if (!ctx || n < 0 || !n_out) return SVIMGPU_ERR_ARG;
     // one synthetic record at position 0 on contig 0 through the real scan kernel

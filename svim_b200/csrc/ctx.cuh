@@ -64,7 +64,7 @@ enum {  // device counters
 
 enum {  // timing slots
     T_H2D = 0, T_SCAN, T_CHAIN, T_SORTBACK, T_GATHER, T_COLLECT_D2H, T_CSIG, T_KEYSORT, T_PARTITION, T_SAMPLE, T_PAIRS,
-    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_N
+    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_N
 };
 
 struct SigSet {   // one signature list on the device (main / all_bnds twins)
@@ -137,6 +137,10 @@ struct svimgpu_ctx {
     int64_t n_partitions = 0;
     svim_cluster_stats clstats;
     bool clustered = false;
+
+    // genotype (SVIM_genotyping.py:34-93): works on the record rows + CIGAR left in HBM by the last upload
+    bool rows_resident = false, geno_ready = false; int32_t geno_contigs = 0;
+    DevBuf d_geno_end, d_geno_max, d_geno_rows, d_geno_cand, d_geno_out, d_geno_var, d_geno_clen;
 
     // multi-GPU
     void* nccl_comm = nullptr; int nranks = 1, rank = 0;

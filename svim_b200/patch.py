@@ -6,7 +6,8 @@ or  python -m svim_b200.patch alignment <workdir> <bam> <genome> [...]   # runs 
 What is replaced (and nothing else):
   svim.SVIM_COLLECT.analyze_alignment_file_coordsorted   (svim:102)
   svim.SVIM_CLUSTER.cluster_sv_signatures                (svim:132,135)
-COMBINE / genotyping / VCF keep running on the objects returned here (same attribute surface).
+  svim.SVIM_genotyping.genotype                          (svim:161-170)  - on the record rows COLLECT left in HBM
+COMBINE / VCF keep running on the objects returned here (same attribute surface).
 """
 import runpy
 import shutil
@@ -25,6 +26,16 @@ def install():
 
     ref_collect.analyze_alignment_file_coordsorted = analyze_alignment_file_coordsorted
     ref_cluster.cluster_sv_signatures = SVIM_CLUSTER.cluster_sv_signatures
+
+    import svim.SVIM_genotyping as ref_genotyping
+    from . import SVIM_genotyping, runtime
+
+    def genotype(candidates, bam, type, options):
+        # the flattened buffer of the same file is still resident from COLLECT; `bam` (pysam) is not read again
+        batch = getattr(runtime.context(), "resident", None)
+        return SVIM_genotyping.genotype(candidates, batch if batch is not None else read_alignments(options.bam_file), type, options)
+
+    ref_genotyping.genotype = genotype
 
 
 def main():

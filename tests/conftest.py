@@ -13,6 +13,7 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_NAMES = ("mini_indel", "mini_mixed", "mini_mixed_allbnds", "mini_ins", "mini_hotspot", "chimeric_kat")
 GOLDEN_QUERYSORTED = ("mini_mixed_querysorted",)
+GOLDEN_GENOTYPE = ("geno_mini_indel", "geno_mini_mixed", "geno_mini_hotspot", "geno_deep")
 
 
 def querysort_order(batch):

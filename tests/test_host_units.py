@@ -377,3 +377,32 @@ def test_banded_wavefront_host_replay(hc):
     # the policy: k = m*num/1024 + add, no banded pass when k < m - n or when no smaller shape holds the band
     assert hc.hc_myers_band_k(1000, 1000, 174, 24) == 193 and hc.hc_myers_band_k(1000, 500, 174, 24) == -1 and hc.hc_myers_band_k(1000, 1000, 0, 24) == -1
     assert hc.hc_myers_band_bin(4000, 3990, 174, 24) == 3 and hc.hc_myers_band_bin(200, 200, 174, 24) == -1
+
+
+def test_candidate_arrays_from_clusters_matches_naive():
+    # svim_b200.SVIM_genotyping.candidate_arrays_from_clusters: vectorised marshalling used by bench.py's genotype leg
+    from svim_b200 import _lib
+    from svim_b200.SVIM_genotyping import candidate_arrays_from_clusters
+    rng = np.random.default_rng(5)
+    n_sig = 400
+    sigs = np.zeros(n_sig, dtype=_lib.SIG_DTYPE)
+    sigs["qname_id"] = rng.integers(0, 60, n_sig); sigs["contig1"] = rng.integers(0, 3, n_sig)
+    sizes = rng.integers(1, 9, 70)
+    members = rng.permutation(n_sig)[: int(sizes.sum())].astype(np.uint32)
+    cl = np.zeros(len(sizes), dtype=_lib.CLUSTER_DTYPE)
+    cl["size"] = sizes; cl["member_off"] = np.cumsum(sizes) - sizes
+    cl["type"] = rng.integers(0, 3, len(sizes)); cl["score"] = rng.integers(0, 8, len(sizes))
+    cl["start"] = rng.integers(-5, 1000, len(sizes)); cl["end"] = cl["start"] + rng.integers(0, 500, len(sizes))
+    for tcode in (0, 1):
+        cands, ids, sel = candidate_arrays_from_clusters(cl, members, sigs, tcode, minimum_score=3)
+        want_sel = [k for k in range(len(cl)) if cl["type"][k] == tcode and cl["score"][k] >= 3]
+        assert sel.tolist() == want_sel
+        off = 0
+        for c, k in zip(cands, want_sel):
+            m = members[int(cl["member_off"][k]):int(cl["member_off"][k]) + int(cl["size"][k])]
+            want_ids = sorted(set(sigs["qname_id"][m].tolist()))
+            assert (int(c["start"]), int(c["end"]), int(c["tid"])) == (max(0, int(cl["start"][k])), int(cl["end"][k]), int(sigs["contig1"][m[0]]))
+            assert int(c["variant_off"]) == off and int(c["n_variant_reads"]) == len(want_ids)
+            assert ids[off:off + len(want_ids)].tolist() == want_ids
+            off += len(want_ids)
+        assert off == len(ids)

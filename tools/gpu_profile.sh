@@ -15,6 +15,8 @@ for p in $parts; do
     myers)    # the banded shapes of the second step (5 shapes carry pairs on config2), then the unbanded bins
               ncu --set full --clock-control none --import-source on -k regex:k_myers_band -s 5 -c 5 -f -o gpurun_out/prof_myers_band_${tag} \
                 python bench.py --profile-steps --steps 1 --warmup 1 > gpurun_out/prof_myers_band_${tag}.log 2>&1 ;;
+    geno)     ncu --set full --clock-control none --import-source on -k regex:"k_ref_end|k_genotype" -c 3 -f -o gpurun_out/prof_geno_${tag} \
+                python bench.py --profile-steps --profile-genotype --steps 1 --warmup 1 > gpurun_out/prof_geno_${tag}.log 2>&1 ;;
   esac
 done
 ls -la gpurun_out/

@@ -182,6 +182,80 @@ def candidate_fixture():
     print("candidates", len(rows), "->", len(ref_rows))
 
 
+GENO_TYPES = ("DEL", "INV", "INS", "DUP_INT")      # call order svim:161-170
+
+
+def genotype_fixtures():
+    """name -> (input fixture name or (batch, genome), option overrides).  GENOTYPE (SVIM_genotyping.py:34-93) through the
+    UNMODIFIED reference: COLLECT -> CLUSTER -> COMBINE (--skip_consensus: spoa is absent here) -> genotype() on the shim's
+    region fetch; the candidates (locus, score, member read names) become the fixture input, the four attributes
+    genotype() writes the expected output."""
+    fx = fixtures()
+    out = {"geno_mini_indel": (fx["mini_indel"][:2], "mini_indel", {}),
+           "geno_mini_mixed": (fx["mini_mixed"][:2], "mini_mixed", {"min_mapq": 1, "minimum_score": 1, "minimum_depth": 6,
+                                                                    "homozygous_threshold": 0.7, "heterozygous_threshold": 0.3}),
+           "geno_mini_hotspot": (fx["mini_hotspot"][:2], "mini_hotspot", {"minimum_score": 0})}
+    # deep coverage: more than 500 countable alignments per window (the aln_no cap, :57)
+    names, L = ["chrD"], [24_000]
+    svs, al = synth.plant_svs(L, 15, spacing=5000, mix={"DEL": 0.5, "INS": 0.5}, size_range=(50, 900))
+    deep = synth.generate(names, L, 4200, 15, svs, al, len_mean=3000, len_sd=600, len_min=800, len_max=6000, p_ins=0.02, p_del=0.01)
+    out["geno_deep"] = ((deep, synth.random_genome(names, L, 15)), None, {})
+    return out
+
+
+def run_reference_genotype(batch, genome, overrides):
+    from svim.SVIM_COMBINE import combine_clusters
+    from svim.SVIM_genotyping import genotype
+    with tempfile.TemporaryDirectory() as td:
+        gpath = os.path.join(td, "genome.fa")
+        pysam.register_genome(gpath, genome)
+        argv = ["alignment", td, "in.bam", gpath, "--skip_consensus"]
+        for k, v in overrides.items():
+            argv += ["--" + k, str(v)]
+        options = parse_arguments("2.0.0", argv)
+        bam = pysam.AlignmentFile.from_batch(batch)
+        sigs, _ = analyze_alignment_file_coordsorted(bam, options)
+        clusters = cluster_sv_signatures(sigs, options)
+        dels, invs, dup_ints, _tans, inss, _bnds = combine_clusters(clusters, options)
+        res = {}
+        for t, cands in (("DEL", dels), ("INV", invs), ("INS", inss), ("DUP_INT", dup_ints)):
+            genotype(cands, bam, t, options)
+            rows = []
+            for c in cands:
+                contig, start, end = c.get_destination() if t in ("INS", "DUP_INT") else c.get_source()
+                rows.append([[contig, start, end, c.score, [m.read for m in c.members]],
+                             [c.support_fraction, c.genotype, c.ref_reads, c.alt_reads]])
+            res[t] = rows
+        return res
+
+
+def genotype_goldens(only=None):
+    for name, (pair, inp, overrides) in genotype_fixtures().items():
+        if only and name != only:
+            continue
+        batch, genome = pair
+        ref = run_reference_genotype(batch, genome, overrides)
+        gp = orc.GenoParams(**{k: v for k, v in overrides.items()})
+        for t in GENO_TYPES:
+            cands = [orc.GenoCand(*row[0]) for row in ref[t]]
+            orc.genotype(cands, batch, t, gp)
+            mine = [c.result() for c in cands]
+            want = [row[1] for row in ref[t]]
+            if mine != want:
+                for i, (x, y) in enumerate(zip(want, mine)):
+                    if x != y:
+                        print("first diff", name, t, i, ref[t][i][0][:4], "\n ref", x, "\n orc", y); break
+                raise SystemExit("ORACLE != REFERENCE on genotype %s/%s" % (name, t))
+        if inp is None:
+            inp = name
+            save_input(os.path.join(GOLDEN, inp + ".input.npz"), batch, genome)
+        with gzip.open(os.path.join(GOLDEN, name + ".golden.json.gz"), "wt") as fh:
+            json.dump({"input": inp + ".input.npz", "params": overrides, "n_records": batch.n, "genotype": ref}, fh)
+        from collections import Counter
+        print(name, "records", batch.n, {t: (len(ref[t]), dict(Counter(r[1][1] for r in ref[t]))) for t in GENO_TYPES},
+              "max ref_reads", max([r[1][2] or 0 for t in GENO_TYPES for r in ref[t]] + [0]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -189,6 +263,10 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not args.only or args.only == "candidates":
         candidate_fixture()
+    if not args.only or args.only.startswith("geno"):
+        genotype_goldens(None if args.only in (None, "geno") else args.only)
+        if args.only:
+            return
     for name, (batch, genome, overrides) in fixtures().items():
         if args.only and name != args.only:
             continue
