@@ -239,6 +239,15 @@ int svimgpu_genotype(svimgpu_ctx* ctx, int32_t type, const svim_geno_params* par
                      const uint32_t* variant_qname_ids, int64_t n_variant_ids, const int64_t* contig_lengths, int32_t n_contigs,
                      svim_geno_result* out);
 
+/* Cut&paste search of COMBINE, flag_cutpaste_candidates (SVIM_merging.py:12-29): for every interval a (source of a DUP_INT
+ * cluster) the closest interval b (source of a deletion cluster) under span_position_distance_clusters
+ * (SVIM_clustering.py:99-107; contigs are not compared there).  out_index[n_a] = first index of the minimum (stable sort at
+ * :20), -1 when n_b == 0 (the reference raises IndexError); out_distance[n_a] in FP64, the reference's operation order.
+ * SVIMGPU_ERR_DATA where the reference raises ZeroDivisionError (both spans zero). */
+int svimgpu_closest_source(svimgpu_ctx* ctx, int64_t n_a, const int64_t* a_start, const int64_t* a_end, int64_t n_b,
+                           const int64_t* b_start, const int64_t* b_end, double position_distance_normalizer,
+                           int64_t* out_index, double* out_distance);
+
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------ */
 /* id_bytes: 128-byte ncclUniqueId from svimgpu_nccl_unique_id on rank 0. */
 int svimgpu_nccl_unique_id(uint8_t* id_bytes /*128*/);

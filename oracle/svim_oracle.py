@@ -947,3 +947,26 @@ def genotype(cands: List[GenoCand], batch, type: str, gp: GenoParams, ends=None)
         cand.ref_reads = n_ref
         cand.alt_reads = n_var
     return cands
+
+
+# ---------------------------------------------------------------------------
+# cut&paste search (SVIM_merging.py:12-29) — SURVEY.md §8f rank 3, second half
+# ---------------------------------------------------------------------------
+def cluster_source_distance(a_start, a_end, b_start, b_end, N):
+    """span_position_distance_clusters (SVIM_clustering.py:99-107) on two source intervals.  Contigs are NOT compared."""
+    span1, span2 = a_end - a_start, b_end - b_start
+    c1, c2 = (a_start + a_end) // 2, (b_start + b_end) // 2
+    return abs(c1 - c2) / N + abs(span1 - span2) / max(span1, span2)
+
+
+def flag_cutpaste(ins_sources, del_sources, N=900, max_distance=1.0):
+    """flag_cutpaste_candidates (SVIM_merging.py:12-29) reduced to what it decides: for every DUP_INT cluster source
+    (start, end) the index of and the distance to the closest deletion cluster — first of the minima, because
+    `sorted(..., key=distance)[0]` is stable — and the cut&paste flag `closest <= del_ins_dup_max_distance`.
+    No deletion cluster -> IndexError, zero spans on both sides -> ZeroDivisionError, like the reference."""
+    out = []
+    for (s, e) in ins_sources:
+        distances = [(j, cluster_source_distance(ds, de, s, e, N)) for j, (ds, de) in enumerate(del_sources)]
+        j, d = sorted(distances, key=lambda o: o[1])[0]
+        out.append((j, d, d <= max_distance))
+    return out

@@ -125,6 +125,8 @@ EXPORTS = {
     "svimgpu_fetch_partitions": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "svimgpu_genotype": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GenoParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int32, C.c_void_p]),
+    "svimgpu_closest_source": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_void_p, C.c_void_p]),
     "svimgpu_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "svimgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "svimgpu_exchange_signatures": (C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(CollectStats)]),
@@ -327,6 +329,15 @@ class Context:
         self._check(self.lib.svimgpu_genotype(self.h, type_code, C.byref(gparams), len(cands), _ptr(cands), _ptr(variant_ids), variant_ids.size,
                                               clen.ctypes.data, clen.size, _ptr(out)))
         return out
+
+    def closest_source(self, a_start, a_end, b_start, b_end, normalizer):
+        """svimgpu_closest_source -> (index int64[n_a], distance float64[n_a])."""
+        a_s = np.ascontiguousarray(a_start, dtype=np.int64); a_e = np.ascontiguousarray(a_end, dtype=np.int64)
+        b_s = np.ascontiguousarray(b_start, dtype=np.int64); b_e = np.ascontiguousarray(b_end, dtype=np.int64)
+        idx = np.zeros(len(a_s), dtype=np.int64); dist = np.zeros(len(a_s), dtype=np.float64)
+        self._check(self.lib.svimgpu_closest_source(self.h, len(a_s), _ptr(a_s), _ptr(a_e), len(b_s), _ptr(b_s), _ptr(b_e), float(normalizer),
+                                                    _ptr(idx), _ptr(dist)))
+        return idx, dist
 
     def timings(self):
         ms = np.zeros(32, dtype=np.float64)

@@ -12,7 +12,7 @@
 
 static const char* k_timing_names[T_N] = {
     "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
-    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype"};
+    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype", "closest_deletion"};
 
 extern "C" {
 
@@ -400,6 +400,17 @@ int svimgpu_genotype(svimgpu_ctx* ctx, int32_t type, const svim_geno_params* gp,
     cudaSetDevice(ctx->device);
     timings_begin(ctx);
     int rc = genotype_run(ctx, type, gp, n, cands, variant_qname_ids, n_variant_ids, contig_lengths, n_contigs, out);
+    timings_end(ctx);
+    return rc;
+}
+
+int svimgpu_closest_source(svimgpu_ctx* ctx, int64_t n_a, const int64_t* a_start, const int64_t* a_end, int64_t n_b, const int64_t* b_start,
+                           const int64_t* b_end, double position_distance_normalizer, int64_t* out_index, double* out_distance) {
+    if (!ctx || n_a < 0 || n_b < 0 || (n_a && (!a_start || !a_end || !out_index || !out_distance)) || (n_b && (!b_start || !b_end))) return SVIMGPU_ERR_ARG;
+    if (n_a == 0) return 0;
+    cudaSetDevice(ctx->device);
+    timings_begin(ctx);
+    int rc = closest_source_run(ctx, n_a, a_start, a_end, n_b, b_start, b_end, position_distance_normalizer, out_index, out_distance);
     timings_end(ctx);
     return rc;
 }

@@ -64,7 +64,7 @@ enum {  // device counters
 
 enum {  // timing slots
     T_H2D = 0, T_SCAN, T_CHAIN, T_SORTBACK, T_GATHER, T_COLLECT_D2H, T_CSIG, T_KEYSORT, T_PARTITION, T_SAMPLE, T_PAIRS,
-    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_N
+    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_CUTPASTE, T_N
 };
 
 struct SigSet {   // one signature list on the device (main / all_bnds twins)

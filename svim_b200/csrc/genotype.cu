@@ -244,3 +244,56 @@ static int genotype_run(svimgpu_ctx* ctx, int32_t type, const svim_geno_params* 
     SVIM_CUDA(cudaStreamSynchronize(st));
     return 0;
 }
+
+// ---- cut&paste search: flag_cutpaste_candidates (SVIM_merging.py:12-29) -----------------------------------------------------
+// For every DUP_INT cluster the closest deletion cluster under span_position_distance_clusters (SVIM_clustering.py:99-107):
+// O(#DUP_INT x #DEL) in the reference (a Python list + sort per cluster); here one warp per DUP_INT cluster strides over the
+// deletion intervals, FP64 in the reference's operation order (-fmad=false), first minimum wins like the stable sort at :20.
+__global__ void __launch_bounds__(256) k_closest_source(const int64_t* __restrict__ a_start, const int64_t* __restrict__ a_end, int64_t n_a,
+                                                        const int64_t* __restrict__ b_start, const int64_t* __restrict__ b_end, int64_t n_b,
+                                                        double normalizer, int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                        uint32_t* __restrict__ zero_div) {
+    const uint32_t lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= n_a) return;
+    const int64_t s2 = a_start[q], e2 = a_end[q];
+    const int64_t span2 = e2 - s2, c2 = (s2 + e2) >> 1;              // Python // on ints: floor
+    double best = INFINITY; int64_t best_j = INT64_MAX; uint32_t zd = 0;
+    for (int64_t j = lane; j < n_b; j += 32) {
+        const int64_t s1 = b_start[j], e1 = b_end[j];
+        const int64_t span1 = e1 - s1, c1 = (s1 + e1) >> 1;
+        const int64_t mx = span1 > span2 ? span1 : span2;
+        if (mx == 0) { zd = 1; continue; }
+        const int64_t dc = c1 > c2 ? c1 - c2 : c2 - c1, ds = span1 > span2 ? span1 - span2 : span2 - span1;
+        const double d = (double)dc / normalizer + (double)ds / (double)mx;
+        if (d < best) { best = d; best_j = j; }                       // ascending j per lane: strict < keeps the first minimum
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int64_t oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        zd |= __shfl_xor_sync(0xffffffffu, zd, o);
+        if (od < best || (od == best && oj < best_j)) { best = od; best_j = oj; }
+    }
+    if (lane == 0) { out_idx[q] = best_j == INT64_MAX ? -1 : best_j; out_dist[q] = best; if (zd) atomicOr(zero_div, 1u); }
+}
+
+static int closest_source_run(svimgpu_ctx* ctx, int64_t n_a, const int64_t* a_start, const int64_t* a_end, int64_t n_b, const int64_t* b_start,
+                              const int64_t* b_end, double normalizer, int64_t* out_idx, double* out_dist) {
+    cudaStream_t st = ctx->stream;
+    StageTimer t(ctx, T_CUTPASTE);
+    const size_t na = (size_t)n_a, nb = (size_t)n_b;
+    SVIM_CUDA(ctx->d_geno_cand.ensure((2 * na + 2 * nb) * 8 + 64)); SVIM_CUDA(ctx->d_geno_out.ensure(na * 16 + 64));
+    int64_t* d_as = ctx->d_geno_cand.as<int64_t>(); int64_t* d_ae = d_as + na; int64_t* d_bs = d_ae + na; int64_t* d_be = d_bs + nb;
+    int64_t* d_idx = ctx->d_geno_out.as<int64_t>(); double* d_dist = (double*)(d_idx + na); uint32_t* d_zd = (uint32_t*)(d_dist + na);
+    SVIM_CUDA(cudaMemcpyAsync(d_as, a_start, na * 8, cudaMemcpyHostToDevice, st)); SVIM_CUDA(cudaMemcpyAsync(d_ae, a_end, na * 8, cudaMemcpyHostToDevice, st));
+    if (nb) { SVIM_CUDA(cudaMemcpyAsync(d_bs, b_start, nb * 8, cudaMemcpyHostToDevice, st)); SVIM_CUDA(cudaMemcpyAsync(d_be, b_end, nb * 8, cudaMemcpyHostToDevice, st)); }
+    SVIM_CUDA(cudaMemsetAsync(d_zd, 0, 4, st));
+    { ctx->launches++; k_closest_source<<<(uint32_t)((na * 32 + 255) / 256), 256, 0, st>>>(d_as, d_ae, n_a, d_bs, d_be, n_b, normalizer, d_idx, d_dist, d_zd); }
+    SVIM_CUDA(cudaGetLastError());
+    uint32_t zd = 0;
+    SVIM_CUDA(cudaMemcpyAsync(out_idx, d_idx, na * 8, cudaMemcpyDeviceToHost, st)); SVIM_CUDA(cudaMemcpyAsync(out_dist, d_dist, na * 8, cudaMemcpyDeviceToHost, st));
+    SVIM_CUDA(cudaMemcpyAsync(&zd, d_zd, 4, cudaMemcpyDeviceToHost, st));
+    SVIM_CUDA(cudaStreamSynchronize(st));
+    if (zd) { ctx->set_error(SVIMGPU_ERR_DATA, "two zero-length source intervals: the reference divides by max(span1, span2) = 0"); return SVIMGPU_ERR_DATA; }
+    return 0;
+}

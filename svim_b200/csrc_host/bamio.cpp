@@ -13,6 +13,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <atomic>
 #include <cstdint>
@@ -85,6 +86,18 @@ struct Handle {
     int threads = 1;
 };
 
+// SVIM_BAMIO_TRACE=1: per-phase wall times on stderr
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("SVIM_BAMIO_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[bamio] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline uint16_t rd16(const uint8_t* p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
@@ -134,6 +147,7 @@ extern "C" {
 
 void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, int errcap) {
     auto fail = [&](const char* m) -> void* { if (err && errcap > 0) snprintf(err, errcap, "%s", m); return nullptr; };
+    Trace tr;
     const int fd = open(path, O_RDONLY);
     if (fd < 0) return fail("cannot open file");
     struct stat sb;
@@ -153,6 +167,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         close(fd);
         if (short_read) return fail("short read");
     }
+    tr.mark("read file");
     // ---- BGZF block index ----------------------------------------------------------------------------
     std::vector<Block> blocks;
     size_t o = 0, uoff = 0;
@@ -172,6 +187,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         blocks.push_back({o + 12 + xlen, total - xlen - 20, uoff, isize});
         uoff += isize; o += total;
     }
+    tr.mark("block index");
     Handle* h = new Handle();
     h->threads = std::max(1, n_threads);
     h->data.alloc(uoff);
@@ -191,7 +207,9 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         }
     });
     if (bad) { delete h; return fail("inflate failed"); }
+    tr.mark("inflate");
     file.release();
+    tr.mark("free file buffer");
     // ---- header --------------------------------------------------------------------------------------------
     const uint8_t* d = h->data.data(); const size_t n = h->data.size();
     if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete h; return fail("not a BAM stream"); }
@@ -224,6 +242,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
         p += 4 + (size_t)bs;
     }
     const size_t nr = h->recs.size();
+    tr.mark("record index (serial hop)");
     // ---- per-record sizes (parallel) ---------------------------------------------------------------------------------
     parallel_for(nr, h->threads, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
@@ -236,6 +255,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
             h->recs[i].sa_off_in_rec = so; h->recs[i].sa_len = sl;
         }
     });
+    tr.mark("SA tag search");
     // ---- read-name ids ---------------------------------------------------------------------------------------------------
     h->qid.resize(nr);
     {
@@ -249,6 +269,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
             h->qid[i] = it->second;
         }
     }
+    tr.mark("read-name ids (serial hash)");
     bamio_info& inf = h->info;
     memset(&inf, 0, sizeof(inf));
     inf.n_records = (int64_t)nr; inf.n_contigs = (int32_t)n_ref; inf.n_qnames = (int64_t)h->qnames.size();
@@ -260,6 +281,7 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
     }
     for (auto& q : h->qnames) inf.names_bytes += (int64_t)q.size() + 1;
     *info = inf;
+    tr.mark("sizes (serial)");
     return h;
 }
 
@@ -289,6 +311,7 @@ int bamio_qnames(void* hh, char* out, int64_t cap) {
 
 int bamio_fill(void* hh, bamio_out* out) {
     Handle* h = (Handle*)hh;
+    Trace tr;
     advise_huge(out->cigar, (size_t)h->info.cigar_words * 4); advise_huge(out->seq, (size_t)h->info.seq_bytes);
     const uint8_t* d = h->data.data();
     const size_t nr = h->recs.size();
@@ -300,6 +323,7 @@ int bamio_fill(void* hh, bamio_out* out) {
         out->seq_off[i] = so; so += (uint64_t)(l_seq + 1) / 2;
         out->sa_off[i] = sao; sao += h->recs[i].sa_len;
     }
+    tr.mark("offsets (serial)");
     parallel_for(nr, h->threads, [&](size_t lo, size_t hi) {
         for (size_t i = lo; i < hi; ++i) {
             const uint8_t* r = d + h->recs[i].off;
@@ -314,6 +338,7 @@ int bamio_fill(void* hh, bamio_out* out) {
             if (h->recs[i].sa_len) memcpy(out->sa + out->sa_off[i], r + h->recs[i].sa_off_in_rec, h->recs[i].sa_len);
         }
     });
+    tr.mark("SoA fill");
     return 0;
 }
 

@@ -7,6 +7,8 @@ What is replaced (and nothing else):
   svim.SVIM_COLLECT.analyze_alignment_file_coordsorted   (svim:102)
   svim.SVIM_CLUSTER.cluster_sv_signatures                (svim:132,135)
   svim.SVIM_genotyping.genotype                          (svim:161-170)  - on the record rows COLLECT left in HBM
+  svim.SVIM_merging.flag_cutpaste_candidates             (SVIM_COMBINE.py:399)  - the O(#DUP_INT x #DEL) closest-deletion search
+  svim.SVIM_clustering.partition_and_cluster_candidates  (SVIM_COMBINE.py:476)  - COMBINE-stage twin of the clustering pipeline
 COMBINE / VCF keep running on the objects returned here (same attribute surface).
 """
 import runpy
@@ -36,6 +38,18 @@ def install():
         return SVIM_genotyping.genotype(candidates, batch if batch is not None else read_alignments(options.bam_file), type, options)
 
     ref_genotyping.genotype = genotype
+
+    # COMBINE binds these two by `from ... import` (SVIM_COMBINE.py:13-14): rebind the defining modules before it is imported,
+    # and its own globals when it already was
+    import svim.SVIM_merging as ref_merging
+    import svim.SVIM_clustering as ref_clustering
+    from . import SVIM_merging, SVIM_clustering
+    ref_merging.flag_cutpaste_candidates = SVIM_merging.flag_cutpaste_candidates
+    ref_clustering.partition_and_cluster_candidates = SVIM_clustering.partition_and_cluster_candidates
+    combine = sys.modules.get("svim.SVIM_COMBINE")
+    if combine is not None:
+        combine.flag_cutpaste_candidates = SVIM_merging.flag_cutpaste_candidates
+        combine.partition_and_cluster_candidates = SVIM_clustering.partition_and_cluster_candidates
 
 
 def main():

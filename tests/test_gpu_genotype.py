@@ -169,3 +169,63 @@ def test_genotype_edge_cases():
     from svim_b200 import _lib
     with pytest.raises(_lib.SvimGpuError):
         genotype([Candidate("c", 1, 2, 9, [])], batch.take(np.arange(batch.n)[::-1], "coordinate"), "DEL", options_of())
+
+
+# ---- cut&paste search of COMBINE (SVIM_merging.py:12-29), svimgpu_closest_source ------------------------------------------
+class UniCluster:
+    def __init__(self, contig, start, end):
+        self.src = (contig, start, end)
+
+    def get_source(self):
+        return self.src
+
+
+class BiCluster(UniCluster):
+    def __init__(self, contig, start, end, dcontig, dstart, k):
+        super().__init__(contig, start, end)
+        self.dst = (dcontig, dstart, dstart + (end - start))
+        self.members, self.score, self.std_span, self.std_pos = ["m%d" % k], 4.0, None, None
+
+    def get_destination(self):
+        return self.dst
+
+
+def test_flag_cutpaste_candidates_matches_reference_golden():
+    import gzip, json, os
+    from conftest import GOLDEN
+    from svim_b200.SVIM_merging import flag_cutpaste_candidates, closest_deletion
+    g = json.load(gzip.open(os.path.join(GOLDEN, "cutpaste.golden.json.gz"), "rt"))
+    opts = types.SimpleNamespace(position_distance_normalizer=g["position_distance_normalizer"], del_ins_dup_max_distance=g["del_ins_dup_max_distance"])
+    for case in g["cases"]:
+        dels = [UniCluster(*d) for d in case["dels"]]
+        inss = [BiCluster(*row, k) for k, row in enumerate(case["inss"])]
+        got = flag_cutpaste_candidates(inss, dels, opts)
+        assert [bool(c.cutpaste) for c in got] == case["cutpaste"]
+        assert [(c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end, c.members) for c in got] == \
+               [(r[0], max(0, r[1]), r[2], r[3], max(0, r[4]), r[4] + r[2] - r[1], ["m%d" % k]) for k, r in enumerate(case["inss"])]
+        idx, dist = closest_deletion(inss, dels, opts)
+        assert [[int(i), float(d)] for i, d in zip(idx, dist)] == case["closest"]        # bit-equal FP64, first minimum
+    assert flag_cutpaste_candidates([], [], opts) == []
+    with pytest.raises(IndexError):
+        flag_cutpaste_candidates([BiCluster("c", 1, 5, "c", 9, 0)], [], opts)
+    with pytest.raises(ZeroDivisionError):
+        flag_cutpaste_candidates([BiCluster("c", 5, 5, "c", 9, 0)], [UniCluster("c", 1, 9), UniCluster("c", 7, 7)], opts)
+
+
+def test_closest_source_matches_oracle_at_scale():
+    from svim_b200 import runtime
+    rng = np.random.default_rng(11)
+    n_b, n_a = 20000, 3000
+    b_s = rng.integers(0, 250_000_000, n_b); b_e = b_s + rng.integers(40, 20000, n_b)
+    pick = rng.integers(0, n_b, n_a)
+    a_s = np.where(rng.random(n_a) < 0.5, b_s[pick] + rng.integers(-50, 50, n_a), rng.integers(0, 250_000_000, n_a))
+    a_e = a_s + np.where(rng.random(n_a) < 0.5, b_e[pick] - b_s[pick], rng.integers(40, 20000, n_a))
+    idx, dist = runtime.context().closest_source(a_s, a_e, b_s, b_e, 900)
+    # numpy restatement of the same FP64 expression (SVIM_clustering.py:99-107), first minimum
+    for k in range(0, n_a, 7):
+        span1 = (b_e - b_s); span2 = int(a_e[k] - a_s[k])
+        d = np.abs((b_s + b_e) // 2 - (int(a_s[k]) + int(a_e[k])) // 2) / 900 + np.abs(span1 - span2) / np.maximum(span1, span2)
+        j = int(np.argmin(d))
+        assert int(idx[k]) == j and float(dist[k]) == float(d[j]), k
+    want = orc.flag_cutpaste(list(zip(a_s[:40].tolist(), a_e[:40].tolist())), list(zip(b_s.tolist(), b_e.tolist())))
+    assert [(int(i), float(x)) for i, x in zip(idx[:40], dist[:40])] == [(m[0], m[1]) for m in want]

@@ -256,6 +256,49 @@ def genotype_goldens(only=None):
               "max ref_reads", max([r[1][2] or 0 for t in GENO_TYPES for r in ref[t]] + [0]))
 
 
+def cutpaste_fixture():
+    """flag_cutpaste_candidates (SVIM_merging.py:12-29) of the unmodified reference on DUP_INT / DEL clusters: the clusters the
+    reference makes from mini_mixed plus seeded random ones (ties, identical intervals, far and near deletions)."""
+    import random
+    from svim.SVIM_merging import flag_cutpaste_candidates
+    from svim.SVSignature import SignatureClusterUniLocal, SignatureClusterBiLocal
+    rng = random.Random(7)
+    cases = []
+    for case in range(4):
+        n_del = [1, 40, 700, 3][case]; n_ins = [5, 60, 150, 4][case]
+        dels = []
+        for _ in range(n_del):
+            s = rng.randint(0, 200_000); ln = rng.choice([50, 51, 300, 1000, rng.randint(40, 5000)])
+            dels.append([rng.choice(["chr1", "chr2"]), s, s + ln])
+        inss = []
+        for k in range(n_ins):
+            if dels and rng.random() < 0.5:           # sit on / near a deletion (and on duplicates of it: ties)
+                d = rng.choice(dels); s = d[1] + rng.choice([0, 0, 1, -3, 40, 900]); ln = d[2] - d[1] + rng.choice([0, 0, 2, -7, 100])
+            else:
+                s = rng.randint(0, 200_000); ln = rng.randint(40, 5000)
+            inss.append([rng.choice(["chr1", "chr2"]), s, s + max(1, ln), rng.choice(["chr1", "chr2"]), rng.randint(0, 200_000)])
+        if case == 1:
+            dels += [list(d) for d in dels[:10]]      # exact duplicates -> equal distances, first index must win
+        cases.append((dels, inss))
+    options = parse_arguments("2.0.0", ["alignment", "wd", "x.bam", "g.fa"])
+    out = []
+    for dels, inss in cases:
+        dcl = [SignatureClusterUniLocal(c, s, e, 5.0, 3, ["m"], "DEL", 1.0, 1.0) for c, s, e in dels]
+        icl = [SignatureClusterBiLocal(c, s, e, dc, dp, dp + (e - s), 4.0, 2, ["m%d" % k], "DUP_INT", None, None) for k, (c, s, e, dc, dp) in enumerate(inss)]
+        ref = flag_cutpaste_candidates(icl, dcl, options)
+        flags = [bool(c.cutpaste) for c in ref]
+        mine = orc.flag_cutpaste([(s, e) for _, s, e, _, _ in inss], [(s, e) for _, s, e in dels],
+                                 options.position_distance_normalizer, options.del_ins_dup_max_distance)
+        if flags != [m[2] for m in mine]:
+            raise SystemExit("ORACLE != REFERENCE on flag_cutpaste_candidates")
+        assert [(c.source_start, c.source_end, c.dest_start, c.dest_end) for c in ref] == [(max(0, s), e, max(0, dp), dp + (e - s)) for _, s, e, _, dp in inss]
+        out.append({"dels": dels, "inss": inss, "cutpaste": flags, "closest": [[m[0], m[1]] for m in mine]})
+    with gzip.open(os.path.join(GOLDEN, "cutpaste.golden.json.gz"), "wt") as fh:
+        json.dump({"position_distance_normalizer": options.position_distance_normalizer,
+                   "del_ins_dup_max_distance": options.del_ins_dup_max_distance, "cases": out}, fh)
+    print("cutpaste", [(len(c["dels"]), len(c["inss"]), sum(c["cutpaste"])) for c in out])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None)
@@ -263,6 +306,10 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     if not args.only or args.only == "candidates":
         candidate_fixture()
+    if not args.only or args.only == "cutpaste":
+        cutpaste_fixture()
+        if args.only:
+            return
     if not args.only or args.only.startswith("geno"):
         genotype_goldens(None if args.only in (None, "geno") else args.only)
         if args.only:
