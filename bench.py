@@ -65,39 +65,78 @@ def make_rank_input(workload, scale, rank, world):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
+
+    The timed region is a few hundred milliseconds, shorter than an `nvidia-smi` start-up, so the samples come from NVML
+    in-process (nvidia-ml-py), every 2 ms on a thread, for the GPU this rank drives (matched by PCI bus id, so
+    CUDA_VISIBLE_DEVICES does not matter).  Fallback: an `nvidia-smi -lms` child started before the warm-up."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, device):
-        self.device = device; self.proc = None; self.rows = []
+    def __init__(self, device, ctx=None):
+        self.device = device; self.proc = None; self.rows = []; self.nvml = None; self.handle = None
+        self.samples = []; self.mask = 0; self.max_mhz = None; self._stop = threading.Event(); self.t = None; self.t_start = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = ctx.pci_bus_id() if ctx is not None else None
+            self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode()) if bus else pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+            try:        # fallback, started early: nvidia-smi needs about a second before its first line
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.t = threading.Thread(target=self._read_smi, daemon=True); self.t.start()
+            except OSError:
+                self.proc = None
+
+    def _read_smi(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in ln.split(",")]))
+
+    def _poll(self):
+        n = self.nvml
+        reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mask |= int(reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.rows.append([x.strip() for x in ln.split(",")])
+        self.t_start = time.perf_counter()
+        if self.nvml:
+            self._stop.clear()
+            self.t = threading.Thread(target=self._poll, daemon=True); self.t.start()
 
     def stop(self):
+        t_stop = time.perf_counter()
+        if self.nvml:
+            self._stop.set(); self.t.join(timeout=2)
+            sm = self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": [name for bit, name in self.BITS if self.mask & bit], "samples": len(sm), "source": "nvml"}
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"], "samples": 0}
+        time.sleep(0.12)        # let the line that covers the end of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        t0 = self.t_start if self.t_start is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t_stop + 0.12 and len(r) >= 7]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for t, r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak():
@@ -278,7 +317,7 @@ def main():
     stage_ms = {}
     launches0 = 0
     res_ms = []
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, ctx)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
             barrier_max(0.0); sampler.start(); launches0 = ctx.launch_count()
@@ -311,9 +350,10 @@ def main():
     e2e_ms = []
     e2e_stage = {}
     d2h = 0
+    sampler_e2e = ClockSampler(local_rank, ctx)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
-            barrier_max(0.0)
+            barrier_max(0.0); sampler_e2e.start()
         ctx.timer_start()
         cst = ctx.collect_host(batch)
         tm = dict(ctx.timings())
@@ -330,6 +370,7 @@ def main():
         h2d = h2d_full - batch.seq.nbytes + (cst.ins_bytes + 1) // 2 + 8 * cst.n_signatures
         if s >= args.warmup:
             e2e_ms.append(barrier_max(ms))
+    clocks_e2e = sampler_e2e.stop()
     # same, plus materialising the Python SVSignature / SignatureCluster objects (what `svim alignment` consumes)
     obj_s = None
     if world == 1:
@@ -385,7 +426,7 @@ def main():
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
-                "python_object_materialisation_s": obj_s},
+                "python_object_materialisation_s": obj_s, "clocks": clocks_e2e},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},

@@ -153,6 +153,8 @@ void svimgpu_destroy(svimgpu_ctx* ctx);
 const char* svimgpu_last_error(const svimgpu_ctx* ctx);
 int svimgpu_set_params(svimgpu_ctx* ctx, const svim_params* params);
 const char* svimgpu_version(void);
+/* PCI bus id ("0000:1b:00.0") of the context's device, for matching it in NVML (bench.py clock sampling). */
+int svimgpu_pci_bus_id(svimgpu_ctx* ctx, char* out, int32_t cap);
 
 /* Contig table: names (for SA rname lookup = bam.get_tid, SVIM_COLLECT.py:79) and
  * string-order ranks (Python `str <` of SVSignature.py:194 and the tuple sort of

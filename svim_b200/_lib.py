@@ -107,6 +107,7 @@ EXPORTS = {
     "svimgpu_last_error": (C.c_char_p, [C.c_void_p]),
     "svimgpu_set_params": (C.c_int, [C.c_void_p, C.POINTER(Params)]),
     "svimgpu_version": (C.c_char_p, []),
+    "svimgpu_pci_bus_id": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32]),
     "svimgpu_set_contigs": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_void_p]),
     "svimgpu_set_genome": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "svimgpu_pin_host": (C.c_int, [C.c_void_p, C.c_int64]),
@@ -214,6 +215,11 @@ class Context:
     def _check(self, rc):
         if rc != 0:
             raise SvimGpuError(rc, self.lib.svimgpu_last_error(self.h).decode("utf-8", "replace"))
+
+    def pci_bus_id(self) -> str:
+        buf = C.create_string_buffer(64)
+        self._check(self.lib.svimgpu_pci_bus_id(self.h, buf, 64))
+        return buf.value.decode()
 
     def set_params(self, params: Params):
         self.params = params

@@ -81,6 +81,12 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
     delete ctx;
 }
 
+int svimgpu_pci_bus_id(svimgpu_ctx* ctx, char* out, int32_t cap) {
+    if (!ctx || !out || cap < 16) return SVIMGPU_ERR_ARG;
+    SVIM_CUDA(cudaDeviceGetPCIBusId(out, cap, ctx->device));
+    return 0;
+}
+
 const char* svimgpu_last_error(const svimgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int svimgpu_set_params(svimgpu_ctx* ctx, const svim_params* p) {
