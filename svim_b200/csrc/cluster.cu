@@ -491,31 +491,36 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     }
     if (partition_only) { if (stats) *stats = cs; return 0; }
     // ---- host: sampling stream + work lists ---------------------------------------------------------------
-    std::vector<uint32_t> samp_off(P + 1), samp_idx; samp_idx.reserve(n);
-    std::vector<uint32_t> list_small, list_large, list_ins;
-    std::vector<uint64_t> pair_off(P + 1, 0);
-    std::vector<uint8_t> ptype(P);
+    // (the vectors live in the context: their capacity — and their already-faulted pages — are reused from step to step)
+    std::vector<uint32_t>& samp_off = ctx->h_samp_off; std::vector<uint32_t>& samp_idx = ctx->h_samp_idx;
+    std::vector<uint32_t>& list_small = ctx->h_list_small; std::vector<uint32_t>& list_large = ctx->h_list_large; std::vector<uint32_t>& list_ins = ctx->h_list_ins;
+    std::vector<uint64_t>& pair_off = ctx->h_pair_off; std::vector<uint8_t>& ptype = ctx->h_ptype;
+    samp_off.resize(P + 1); samp_idx.resize((size_t)n + 1); pair_off.assign(P + 1, 0); ptype.resize(P);
+    list_small.clear(); list_large.clear(); list_ins.clear();
     uint64_t pair_total = 0;
     int max_m_small = 32;
     {
         StageTimer t(ctx, T_SAMPLE);
         PyRandom rng; int cur_type = -1;
         int32_t pick[100];
+        uint32_t* si = samp_idx.data(); uint32_t wr = 0;     // a sample never exceeds its partition: wr <= n
+        int ty = 0;                                          // partitions come grouped by type, in type order
         for (uint32_t p = 0; p < P; ++p) {
             const uint32_t b = ctx->h_part_off[p], e = ctx->h_part_off[p + 1], sz = e - b;
-            int ty = 0; while (ty < 6 && b >= type_start[ty + 1]) ++ty;
+            while (ty < 6 && b >= type_start[ty + 1]) ++ty;
             ptype[p] = (uint8_t)ty;
             if (ty != cur_type) { rng.seed_int(1524); cur_type = ty; }
             cs.n_partitions[ty > 5 ? 5 : ty]++;
-            samp_off[p] = (uint32_t)samp_idx.size();
+            samp_off[p] = wr;
             uint32_t m = sz;
             if (sz > 100) {
                 rng.sample100(sz, pick); cs.large_partitions[ty > 5 ? 5 : ty]++; m = 100;
-                for (int k = 0; k < 100; ++k) samp_idx.push_back(b + (uint32_t)pick[k]);
-            } else for (uint32_t k = 0; k < sz; ++k) samp_idx.push_back(b + k);
+                for (int k = 0; k < 100; ++k) si[wr++] = b + (uint32_t)pick[k];
+            } else for (uint32_t k = 0; k < sz; ++k) si[wr++] = b + k;
             pair_off[p] = pair_total;
             if (ty == SVIM_INS && m > 1) { list_ins.push_back(p); pair_total += (uint64_t)m * (m - 1) / 2; }
         }
+        samp_idx.resize(wr);
         samp_off[P] = (uint32_t)samp_idx.size();
         // multi-GPU: this rank clusters partitions [lo,hi) only (balanced by sum m^2 + pair cost)
         uint32_t lo = 0, hi = P;

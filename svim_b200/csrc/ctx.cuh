@@ -132,6 +132,8 @@ struct svimgpu_ctx {
     uint32_t shard_lo = 0, shard_hi = 0;
     DevBuf d_cl_off, d_mem_off, d_clusters, d_clusters_sorted, d_members, d_pair_off, d_pair_ed, d_pairs, d_ckeys[2], d_cvals[2];
     std::vector<uint32_t> h_part_off, h_order_cache;
+    std::vector<uint32_t> h_samp_off, h_samp_idx, h_list_small, h_list_large, h_list_ins;   // host sampling scratch, reused
+    std::vector<uint64_t> h_pair_off; std::vector<uint8_t> h_ptype;
     std::vector<svim_cluster> h_clusters;
     std::vector<uint32_t> h_members;
     int64_t n_partitions = 0;
