@@ -1,10 +1,19 @@
 // Multi-threaded BAM -> flattened record buffer (svim_aln_soa) decoder.
 //
 // once the kernels run at TB/s the end-to-end rate is set by host BAM
-// decompression.  The reference iterates pysam/htslib records one by one (SVIM_COLLECT.py:133); this reader
-// inflates all BGZF blocks in parallel (zlib raw inflate, one task per block), indexes the records with one
-// sequential hop over the block_size fields, and fills the structure-of-arrays + CIGAR / SEQ / SA blobs in
-// parallel.  Host code only — nothing here runs on the GPU path's timed kernels.
+// decompression.  The reference iterates pysam/htslib records one by one (SVIM_COLLECT.py:133).
+//
+// Streaming design (no inflated copy of the file is ever held):
+//   * the file is mmap'ed; one sequential pass over the BGZF headers indexes the blocks;
+//   * the blocks are cut into units of ~1 MiB of inflated data; worker threads claim units in order, inflate a unit into a
+//     thread-local buffer that stays cache-warm (zlib raw inflate per block), and then take their turn in a CHAIN that is
+//     ordered by unit: the chain turn prepends the bytes the previous unit left over (a record cut by the unit boundary),
+//     hops over the record block_size fields, assigns every record its row number and its offsets into the CIGAR / SEQ /
+//     SA blobs (running totals travel along the chain), and hands the tail to the next unit.  The chain turn touches a few
+//     bytes per record; everything heavy — inflate before it, the copy of CIGAR / SEQ / SA bytes into the caller's blobs
+//     after it — runs in parallel on the unit's own warm buffer.
+//   * QUAL, names (kept once, for the id table) and other aux fields never leave the unit buffer.
+// Host code only — nothing here runs on the GPU path's timed kernels.
 //
 // File format: SAMv1 §4.1 (BGZF) and §4.2 (BAM).
 #include <zlib.h>
@@ -12,6 +21,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <sched.h>
 #include <algorithm>
 #include <chrono>
 #include <memory>
@@ -28,7 +38,8 @@
 extern "C" {
 
 struct bamio_info {
-    int64_t n_records, cigar_words, seq_bytes, sa_bytes, n_qnames, names_bytes;
+    int64_t n_records, cigar_words, seq_bytes, sa_bytes, n_qnames, names_bytes;     // exact, valid after bamio_decode
+    int64_t cigar_bound_words, seq_bound_bytes;                                     // upper bounds, valid after bamio_open
     int32_t n_contigs, sorted_coordinate;
 };
 
@@ -44,9 +55,6 @@ namespace {
 
 struct Block { size_t coff, clen, uoff, ulen; };
 
-struct Rec { size_t off; uint32_t sa_off_in_rec, sa_len; };
-
-// uninitialised byte buffer: pages are first touched by the worker threads, not zero-filled by one thread
 // Large first-touch buffers are page-fault bound with 4 KiB pages; ask for transparent huge pages.
 static void advise_huge(void* p, size_t bytes) {
 #ifdef MADV_HUGEPAGE
@@ -55,36 +63,6 @@ static void advise_huge(void* p, size_t bytes) {
     if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
 #endif
 }
-
-struct RawBuf {
-    uint8_t* ptr = nullptr; size_t n = 0;
-    RawBuf() = default;
-    RawBuf(const RawBuf&) = delete;
-    RawBuf& operator=(const RawBuf&) = delete;
-    ~RawBuf() { release(); }
-    void release() { if (ptr) free(ptr); ptr = nullptr; n = 0; }
-    void alloc(size_t bytes) {
-        release();
-        void* q = nullptr;
-        if (posix_memalign(&q, (size_t)2 << 20, bytes ? bytes : 1) != 0) q = nullptr;
-        ptr = (uint8_t*)q; n = bytes;
-        if (ptr) advise_huge(ptr, bytes);
-    }
-    uint8_t* data() { return ptr; }
-    const uint8_t* data() const { return ptr; }
-    size_t size() const { return n; }
-};
-
-struct Handle {
-    RawBuf data;                    // inflated stream
-    std::vector<Rec> recs;
-    std::vector<std::string> contigs; std::vector<int64_t> contig_len;
-    std::vector<uint32_t> qid;
-    std::vector<std::string_view> qnames;
-    std::string sort_order;
-    bamio_info info;
-    int threads = 1;
-};
 
 // SVIM_BAMIO_TRACE=1: per-phase wall times on stderr
 struct Trace {
@@ -96,6 +74,36 @@ struct Trace {
         fprintf(stderr, "[bamio] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
     }
+};
+
+// one record's row, produced in the chain turn
+struct Row {
+    int32_t tid, pos; uint16_t flag; uint8_t mapq, l_rn; uint32_t n_cigar; int32_t l_seq; uint32_t sa_len;
+    uint64_t cigar_off, seq_off, sa_off;
+    uint32_t src_off, sa_src;          // record start / SA payload inside the unit's contiguous view
+    uint32_t name_off;                 // into the unit's name arena
+};
+
+struct Unit {
+    size_t b0 = 0, b1 = 0, ulen = 0;   // blocks [b0, b1), inflated bytes
+    std::vector<Row> rows;
+    std::string names;                 // NUL-terminated read names of the unit's records, in order
+    std::string sa;                    // SA tag payloads of the unit's records, concatenated (small: copied out at the end)
+    uint64_t row_base = 0, sa_base = 0;
+};
+
+struct Handle {
+    int fd = -1; const uint8_t* file = nullptr; size_t fsz = 0;
+    std::vector<Block> blocks;
+    std::vector<Unit> units;
+    std::vector<std::string> contigs; std::vector<int64_t> contig_len;
+    std::vector<uint32_t> qid;
+    std::vector<std::string_view> qnames;
+    std::string sort_order = "unknown";
+    bamio_info info;
+    int threads = 1;
+    bool header_done = false;
+    ~Handle() { if (file && fsz) munmap((void*)file, fsz); if (fd >= 0) close(fd); }
 };
 
 inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
@@ -141,38 +149,71 @@ bool find_sa(const uint8_t* rec, size_t aux_begin, size_t rec_len, uint32_t& off
     return false;
 }
 
+bool inflate_block(const uint8_t* src, size_t clen, uint8_t* dst, size_t ulen) {
+    z_stream zs; memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) return false;
+    zs.next_in = const_cast<uint8_t*>(src); zs.avail_in = (uInt)clen; zs.next_out = dst; zs.avail_out = (uInt)ulen;
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    return rc == Z_STREAM_END && zs.avail_out == 0;
+}
+
+// BAM header (magic, text, references) at the front of `d`: returns bytes consumed, 0 = not all there yet, -1 = not BAM
+int64_t parse_header(Handle* h, const uint8_t* d, size_t n) {
+    if (n < 12) return 0;
+    if (memcmp(d, "BAM\1", 4) != 0) return -1;
+    const uint32_t l_text = rd32(d + 4);
+    size_t p = 8 + (size_t)l_text;
+    if (p + 4 > n) return 0;
+    const uint32_t n_ref = rd32(d + p); p += 4;
+    std::vector<std::string> names; std::vector<int64_t> lens;
+    for (uint32_t r = 0; r < n_ref; ++r) {
+        if (p + 4 > n) return 0;
+        const uint32_t ln = rd32(d + p); p += 4;
+        if (p + (size_t)ln + 4 > n) return 0;
+        names.emplace_back((const char*)d + p, ln ? ln - 1 : 0); p += ln;
+        lens.push_back((int32_t)rd32(d + p)); p += 4;
+    }
+    std::string text((const char*)d + 8, strnlen((const char*)d + 8, l_text));
+    size_t q = text.find("@HD");
+    if (q != std::string::npos) {
+        size_t e = text.find('\n', q), s = text.find("SO:", q);
+        if (s != std::string::npos && (e == std::string::npos || s < e)) {
+            size_t t = s + 3, u = t;
+            while (u < text.size() && text[u] != '\t' && text[u] != '\n') ++u;
+            h->sort_order = text.substr(t, u - t);
+        }
+    }
+    h->contigs.swap(names); h->contig_len.swap(lens);
+    h->header_done = true;
+    return (int64_t)p;
+}
+
 }  // namespace
 
 extern "C" {
 
+// Maps the file, indexes the BGZF blocks and reads the BAM header.  info: bounds for the caller-allocated blobs.
 void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, int errcap) {
     auto fail = [&](const char* m) -> void* { if (err && errcap > 0) snprintf(err, errcap, "%s", m); return nullptr; };
     Trace tr;
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) return fail("cannot open file");
+    std::unique_ptr<Handle> h(new Handle());
+    h->threads = std::max(1, n_threads);
+    h->fd = open(path, O_RDONLY);
+    if (h->fd < 0) return fail("cannot open file");
     struct stat sb;
-    if (fstat(fd, &sb) != 0) { close(fd); return fail("cannot stat file"); }
-    const size_t fsz = (size_t)sb.st_size;
-    RawBuf file; file.alloc(fsz);
-    if (fsz && !file.data()) { close(fd); return fail("out of memory"); }
-    {   // parallel pread: the file usually sits in the page cache, the copy is what costs
-        std::atomic<int> short_read{0};
-        const size_t CH = (size_t)64 << 20;
-        parallel_for((fsz + CH - 1) / CH, std::max(1, n_threads), [&](size_t lo, size_t hi) {
-            for (size_t c = lo; c < hi; ++c) {
-                size_t off = c * CH, len = std::min(CH, fsz - off);
-                while (len) { const ssize_t r = pread(fd, file.data() + off, len, (off_t)off); if (r <= 0) { short_read = 1; return; } off += (size_t)r; len -= (size_t)r; }
-            }
-        });
-        close(fd);
-        if (short_read) return fail("short read");
+    if (fstat(h->fd, &sb) != 0) return fail("cannot stat file");
+    h->fsz = (size_t)sb.st_size;
+    if (h->fsz) {
+        void* m = mmap(nullptr, h->fsz, PROT_READ, MAP_PRIVATE, h->fd, 0);
+        if (m == MAP_FAILED) { h->fsz = 0; return fail("cannot map file"); }
+        h->file = (const uint8_t*)m;
+        madvise(m, h->fsz, MADV_WILLNEED);
     }
-    tr.mark("read file");
     // ---- BGZF block index ----------------------------------------------------------------------------
-    std::vector<Block> blocks;
     size_t o = 0, uoff = 0;
-    while (o + 18 <= file.size()) {
-        const uint8_t* p = file.data() + o;
+    while (o + 18 <= h->fsz) {
+        const uint8_t* p = h->file + o;
         if (!(p[0] == 0x1f && p[1] == 0x8b && p[2] == 8 && (p[3] & 4))) return fail("not a BGZF file");
         const uint16_t xlen = rd16(p + 10);
         size_t x = 12, xe = 12 + xlen; int bsize = -1;
@@ -181,108 +222,44 @@ void* bamio_open(const char* path, int n_threads, bamio_info* info, char* err, i
             if (p[x] == 66 && p[x + 1] == 67 && slen == 2) bsize = rd16(p + x + 4);
             x += 4 + slen;
         }
-        if (bsize < 0 || o + (size_t)bsize + 1 > file.size()) return fail("bad BGZF block");
+        if (bsize < 0 || o + (size_t)bsize + 1 > h->fsz || (size_t)bsize + 1 < (size_t)xlen + 20) return fail("bad BGZF block");
         const size_t total = (size_t)bsize + 1;
         const uint32_t isize = rd32(p + total - 4);
-        blocks.push_back({o + 12 + xlen, total - xlen - 20, uoff, isize});
+        if (isize) h->blocks.push_back({o + 12 + xlen, total - xlen - 20, uoff, isize});
         uoff += isize; o += total;
     }
-    tr.mark("block index");
-    Handle* h = new Handle();
-    h->threads = std::max(1, n_threads);
-    h->data.alloc(uoff);
-    if (uoff && !h->data.data()) { delete h; return fail("out of memory"); }
-    std::atomic<int> bad{0};
-    parallel_for(blocks.size(), h->threads, [&](size_t lo, size_t hi) {
-        z_stream zs;
-        for (size_t b = lo; b < hi; ++b) {
-            if (blocks[b].ulen == 0) continue;
-            memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-            zs.next_in = file.data() + blocks[b].coff; zs.avail_in = (uInt)blocks[b].clen;
-            zs.next_out = h->data.data() + blocks[b].uoff; zs.avail_out = (uInt)blocks[b].ulen;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) bad = 1;
-        }
-    });
-    if (bad) { delete h; return fail("inflate failed"); }
-    tr.mark("inflate");
-    file.release();
-    tr.mark("free file buffer");
-    // ---- header --------------------------------------------------------------------------------------------
-    const uint8_t* d = h->data.data(); const size_t n = h->data.size();
-    if (n < 12 || memcmp(d, "BAM\1", 4) != 0) { delete h; return fail("not a BAM stream"); }
-    const uint32_t l_text = rd32(d + 4);
-    std::string text((const char*)d + 8, strnlen((const char*)d + 8, l_text));
-    h->sort_order = "unknown";
+    tr.mark("map + block index");
+    // units of ~1 MiB inflated
+    const size_t UNIT = (size_t)1 << 20;
+    for (size_t b = 0; b < h->blocks.size();) {
+        Unit u; u.b0 = b;
+        while (b < h->blocks.size() && (u.ulen == 0 || u.ulen + h->blocks[b].ulen <= UNIT)) { u.ulen += h->blocks[b].ulen; ++b; }
+        u.b1 = b;
+        h->units.push_back(std::move(u));
+    }
+    // header: inflate leading blocks until it parses (contig names are needed before the caller can allocate anything)
     {
-        size_t p = text.find("@HD");
-        if (p != std::string::npos) {
-            size_t e = text.find('\n', p), s = text.find("SO:", p);
-            if (s != std::string::npos && (e == std::string::npos || s < e)) {
-                size_t t = s + 3; size_t q = t;
-                while (q < text.size() && text[q] != '\t' && text[q] != '\n') ++q;
-                h->sort_order = text.substr(t, q - t);
-            }
+        std::vector<uint8_t> head;
+        for (size_t b = 0; b < h->blocks.size() && !h->header_done; ++b) {
+            const size_t at = head.size();
+            head.resize(at + h->blocks[b].ulen);
+            if (!inflate_block(h->file + h->blocks[b].coff, h->blocks[b].clen, head.data() + at, h->blocks[b].ulen)) return fail("inflate failed");
+            const int64_t used = parse_header(h.get(), head.data(), head.size());
+            if (used < 0) return fail("not a BAM stream");
         }
+        if (!h->header_done) return fail("truncated BAM header");
+        h->header_done = false;      // the chain parses it again to find where the records start
     }
-    size_t p = 8 + l_text;
-    const uint32_t n_ref = rd32(d + p); p += 4;
-    for (uint32_t r = 0; r < n_ref; ++r) {
-        const uint32_t ln = rd32(d + p); p += 4;
-        h->contigs.emplace_back((const char*)d + p, ln ? ln - 1 : 0); p += ln;
-        h->contig_len.push_back((int32_t)rd32(d + p)); p += 4;
-    }
-    // ---- record index (sequential hop) ---------------------------------------------------------------------------
-    while (p + 4 <= n) {
-        const uint32_t bs = rd32(d + p);
-        if (p + 4 + bs > n) { delete h; return fail("truncated record"); }
-        h->recs.push_back({p + 4, 0, 0});
-        p += 4 + (size_t)bs;
-    }
-    const size_t nr = h->recs.size();
-    tr.mark("record index (serial hop)");
-    // ---- per-record sizes (parallel) ---------------------------------------------------------------------------------
-    parallel_for(nr, h->threads, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) {
-            const uint8_t* r = d + h->recs[i].off;
-            const uint32_t bs = rd32(r - 4);
-            const uint8_t l_rn = r[8]; const uint16_t n_cig = rd16(r + 12); const int32_t l_seq = (int32_t)rd32(r + 16);
-            const size_t aux = 32 + (size_t)l_rn + 4 * (size_t)n_cig + (size_t)(l_seq + 1) / 2 + (size_t)l_seq;
-            uint32_t so = 0, sl = 0;
-            if (aux < bs) find_sa(r, aux, bs, so, sl);
-            h->recs[i].sa_off_in_rec = so; h->recs[i].sa_len = sl;
-        }
-    });
-    tr.mark("SA tag search");
-    // ---- read-name ids ---------------------------------------------------------------------------------------------------
-    h->qid.resize(nr);
-    {
-        std::unordered_map<std::string_view, uint32_t> ids;
-        ids.reserve(nr * 2);
-        for (size_t i = 0; i < nr; ++i) {
-            const uint8_t* r = d + h->recs[i].off;
-            std::string_view nm((const char*)r + 32, r[8] ? r[8] - 1 : 0);
-            auto it = ids.find(nm);
-            if (it == ids.end()) { it = ids.emplace(nm, (uint32_t)h->qnames.size()).first; h->qnames.push_back(nm); }
-            h->qid[i] = it->second;
-        }
-    }
-    tr.mark("read-name ids (serial hash)");
     bamio_info& inf = h->info;
     memset(&inf, 0, sizeof(inf));
-    inf.n_records = (int64_t)nr; inf.n_contigs = (int32_t)n_ref; inf.n_qnames = (int64_t)h->qnames.size();
+    inf.n_contigs = (int32_t)h->contigs.size();
     inf.sorted_coordinate = h->sort_order == "coordinate";
-    for (size_t i = 0; i < nr; ++i) {
-        const uint8_t* r = d + h->recs[i].off;
-        const uint16_t n_cig = rd16(r + 12); const int32_t l_seq = (int32_t)rd32(r + 16);
-        inf.cigar_words += (n_cig + 3) & ~3; inf.seq_bytes += (l_seq + 1) / 2; inf.sa_bytes += h->recs[i].sa_len;
-    }
-    for (auto& q : h->qnames) inf.names_bytes += (int64_t)q.size() + 1;
+    const int64_t rec_bound = (int64_t)(uoff / 36) + 1;                 // a record is at least 4 + 32 bytes
+    inf.cigar_bound_words = (int64_t)(uoff / 4) + 3 * rec_bound + 4;    // + padding to multiples of 4 words
+    inf.seq_bound_bytes = (int64_t)(uoff / 3) + rec_bound + 16;         // packed SEQ is at most a third of SEQ + QUAL
     *info = inf;
-    tr.mark("sizes (serial)");
-    return h;
+    tr.mark("header + units");
+    return h.release();
 }
 
 // contig names NUL-separated into names_out (cap bytes), lengths[n_contigs]; sort order into so (16 bytes)
@@ -299,6 +276,139 @@ int bamio_header(void* hh, char* names_out, int64_t cap, int64_t* lengths, char*
     return 0;
 }
 
+// Streams the whole file: fills the caller's CIGAR / SEQ blobs (allocated to the bounds of bamio_open) and keeps the
+// per-record rows and the (small) SA payloads inside the handle; info gets the exact counts.  Returns 0, or a negative code with text in err.
+int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char* err, int errcap) {
+    Handle* h = (Handle*)hh;
+    Trace tr;
+    if (tr.on) {
+        cpu_set_t cs; CPU_ZERO(&cs);
+        const int aff = sched_getaffinity(0, sizeof(cs), &cs) == 0 ? CPU_COUNT(&cs) : -1;
+        char quota[64] = "?"; if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) { if (!fgets(quota, sizeof(quota), f)) quota[0] = 0; fclose(f); quota[strcspn(quota, "\n")] = 0; }
+        char thp[128] = "?"; if (FILE* f = fopen("/sys/kernel/mm/transparent_hugepage/enabled", "r")) { if (!fgets(thp, sizeof(thp), f)) thp[0] = 0; fclose(f); thp[strcspn(thp, "\n")] = 0; }
+        fprintf(stderr, "[bamio] threads %d, hardware %u, affinity %d, cgroup cpu.max '%s', THP '%s', %zu blocks in %zu units\n", h->threads,
+                std::thread::hardware_concurrency(), aff, quota, thp, h->blocks.size(), h->units.size());
+    }
+    advise_huge(cigar, (size_t)h->info.cigar_bound_words * 4); advise_huge(seq, (size_t)h->info.seq_bound_bytes);
+    const size_t n_units = h->units.size();
+    std::atomic<size_t> next_unit{0}, chain_turn{0};
+    std::atomic<int> failed{0};
+    const char* fail_msg = "decode failed";
+    // chain state (only touched by the thread whose turn it is)
+    std::vector<uint8_t> carry;
+    uint64_t n_rows = 0, cig_words = 0, seq_bytes = 0, sa_bytes = 0;
+    const size_t HEADROOM = (size_t)256 << 10;
+
+    auto worker = [&]() {
+        std::vector<uint8_t> buf;            // [headroom | unit data]
+        std::vector<uint8_t> joined;         // only when the carry does not fit the headroom
+        for (;;) {
+            const size_t u = next_unit.fetch_add(1);
+            if (u >= n_units) return;
+            Unit& un = h->units[u];
+            if (buf.size() < HEADROOM + un.ulen) buf.resize(HEADROOM + un.ulen);
+            bool ok = !failed.load(std::memory_order_relaxed);
+            if (ok) {
+                size_t at = HEADROOM;
+                for (size_t b = un.b0; b < un.b1 && ok; ++b) {
+                    ok = inflate_block(h->file + h->blocks[b].coff, h->blocks[b].clen, buf.data() + at, h->blocks[b].ulen);
+                    at += h->blocks[b].ulen;
+                }
+                if (!ok) { fail_msg = "inflate failed"; failed = 1; }
+            }
+            // ---- chain turn ----
+            for (unsigned spins = 0; chain_turn.load(std::memory_order_acquire) != u; ++spins) if (spins > 64) std::this_thread::yield();
+            const uint8_t* d = nullptr; size_t n = 0;
+            if (!failed.load()) {
+                if (carry.size() <= HEADROOM) {
+                    d = buf.data() + HEADROOM - carry.size();
+                    if (!carry.empty()) memcpy(buf.data() + HEADROOM - carry.size(), carry.data(), carry.size());
+                    n = carry.size() + un.ulen;
+                } else {
+                    joined.resize(carry.size() + un.ulen);
+                    memcpy(joined.data(), carry.data(), carry.size()); memcpy(joined.data() + carry.size(), buf.data() + HEADROOM, un.ulen);
+                    d = joined.data(); n = joined.size();
+                }
+                size_t p = 0;
+                if (!h->header_done) {
+                    const int64_t used = parse_header(h, d, n);
+                    if (used < 0) { fail_msg = "not a BAM stream"; failed = 1; }
+                    else p = (size_t)used;               // 0: header continues in the next unit, everything is carried
+                }
+                un.row_base = n_rows; un.sa_base = sa_bytes;
+                if (h->header_done && !failed.load()) {
+                    while (p + 4 <= n) {
+                        const uint32_t bs = rd32(d + p);
+                        if (bs < 32) { fail_msg = "corrupt record"; failed = 1; break; }
+                        if (p + 4 + (size_t)bs > n) break;
+                        const uint8_t* r = d + p + 4;
+                        Row w;
+                        w.tid = (int32_t)rd32(r); w.pos = (int32_t)rd32(r + 4); w.l_rn = r[8]; w.mapq = r[9];
+                        w.n_cigar = rd16(r + 12); w.flag = rd16(r + 14); w.l_seq = (int32_t)rd32(r + 16);
+                        const size_t aux = 32 + (size_t)w.l_rn + 4 * (size_t)w.n_cigar + (size_t)(w.l_seq + 1) / 2 + (size_t)w.l_seq;
+                        if (w.l_seq < 0 || aux > bs) { fail_msg = "corrupt record"; failed = 1; break; }
+                        uint32_t so = 0, sl = 0;
+                        if (aux < bs) find_sa(r, aux, bs, so, sl);
+                        w.sa_len = sl; w.sa_src = 0; w.src_off = (uint32_t)(p + 4);
+                        if (sl) un.sa.append((const char*)r + so, sl);
+                        w.cigar_off = cig_words; w.seq_off = seq_bytes; w.sa_off = sa_bytes;
+                        cig_words += (w.n_cigar + 3u) & ~3u; seq_bytes += (uint64_t)(w.l_seq + 1) / 2; sa_bytes += sl;
+                        w.name_off = (uint32_t)un.names.size();
+                        un.names.append((const char*)r + 32, w.l_rn ? w.l_rn - 1 : 0); un.names.push_back('\0');
+                        un.rows.push_back(w);
+                        p += 4 + (size_t)bs;
+                    }
+                    n_rows += un.rows.size();
+                }
+                carry.assign(d + p, d + n);              // the tail of a record cut by the unit boundary (or of the header)
+            }
+            chain_turn.store(u + 1, std::memory_order_release);
+            if (failed.load()) continue;
+            // ---- fill: this unit's records from the warm buffer into the caller's blobs ----
+            for (const Row& w : un.rows) {
+                const uint8_t* r = d + w.src_off;
+                const uint8_t* cg = r + 32 + w.l_rn;
+                uint32_t* dst = cigar + w.cigar_off;
+                memcpy(dst, cg, 4 * (size_t)w.n_cigar);
+                for (uint32_t k = w.n_cigar; k < ((w.n_cigar + 3u) & ~3u); ++k) dst[k] = 0;
+                memcpy(seq + w.seq_off, cg + 4 * (size_t)w.n_cigar, (size_t)(w.l_seq + 1) / 2);
+            }
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        const int nt = (int)std::min<size_t>((size_t)h->threads, std::max<size_t>(1, n_units));
+        for (int t = 1; t < nt; ++t) th.emplace_back(worker);
+        worker();
+        for (auto& x : th) x.join();
+    }
+    if (!failed && !carry.empty()) { fail_msg = h->header_done ? "truncated record" : "truncated BAM header"; failed = 1; }
+    if (failed) { if (err && errcap > 0) snprintf(err, errcap, "%s", fail_msg); return -1; }
+    tr.mark("inflate + chain + fill");
+    // ---- read-name ids -------------------------------------------------------------------------------------------------
+    const size_t nr = (size_t)n_rows;
+    h->qid.resize(nr);
+    {
+        std::unordered_map<std::string_view, uint32_t> ids;
+        ids.reserve(nr * 2);
+        size_t i = 0;
+        for (const Unit& un : h->units)
+            for (const Row& w : un.rows) {
+                std::string_view nm(un.names.data() + w.name_off, w.l_rn ? w.l_rn - 1 : 0);
+                auto it = ids.find(nm);
+                if (it == ids.end()) { it = ids.emplace(nm, (uint32_t)h->qnames.size()).first; h->qnames.push_back(nm); }
+                h->qid[i++] = it->second;
+            }
+    }
+    tr.mark("read-name ids (serial hash)");
+    bamio_info& inf = h->info;
+    inf.n_records = (int64_t)nr; inf.cigar_words = (int64_t)cig_words; inf.seq_bytes = (int64_t)seq_bytes; inf.sa_bytes = (int64_t)sa_bytes;
+    inf.n_qnames = (int64_t)h->qnames.size(); inf.names_bytes = 0;
+    for (auto& q : h->qnames) inf.names_bytes += (int64_t)q.size() + 1;
+    *info = inf;
+    return 0;
+}
+
 int bamio_qnames(void* hh, char* out, int64_t cap) {
     Handle* h = (Handle*)hh;
     int64_t o = 0;
@@ -309,36 +419,25 @@ int bamio_qnames(void* hh, char* out, int64_t cap) {
     return 0;
 }
 
+// per-record rows into caller arrays of n_records entries and the SA blob (sa_bytes); out->cigar / seq are ignored
+// (bamio_decode filled them)
 int bamio_fill(void* hh, bamio_out* out) {
     Handle* h = (Handle*)hh;
     Trace tr;
-    advise_huge(out->cigar, (size_t)h->info.cigar_words * 4); advise_huge(out->seq, (size_t)h->info.seq_bytes);
-    const uint8_t* d = h->data.data();
-    const size_t nr = h->recs.size();
-    uint64_t co = 0, so = 0, sao = 0;
-    for (size_t i = 0; i < nr; ++i) {
-        const uint8_t* r = d + h->recs[i].off;
-        const uint16_t n_cig = rd16(r + 12); const int32_t l_seq = (int32_t)rd32(r + 16);
-        out->cigar_off[i] = co; co += (n_cig + 3) & ~3;
-        out->seq_off[i] = so; so += (uint64_t)(l_seq + 1) / 2;
-        out->sa_off[i] = sao; sao += h->recs[i].sa_len;
-    }
-    tr.mark("offsets (serial)");
-    parallel_for(nr, h->threads, [&](size_t lo, size_t hi) {
-        for (size_t i = lo; i < hi; ++i) {
-            const uint8_t* r = d + h->recs[i].off;
-            const uint8_t l_rn = r[8]; const uint16_t n_cig = rd16(r + 12); const int32_t l_seq = (int32_t)rd32(r + 16);
-            out->tid[i] = (int32_t)rd32(r); out->pos[i] = (int32_t)rd32(r + 4); out->mapq[i] = r[9]; out->flag[i] = rd16(r + 14);
-            out->n_cigar[i] = n_cig; out->l_seq[i] = l_seq; out->sa_len[i] = h->recs[i].sa_len; out->qname_id[i] = h->qid[i];
-            const uint8_t* cg = r + 32 + l_rn;
-            uint32_t* dst = out->cigar + out->cigar_off[i];
-            memcpy(dst, cg, 4 * (size_t)n_cig);
-            for (uint32_t k = n_cig; k < ((n_cig + 3u) & ~3u); ++k) dst[k] = 0;
-            memcpy(out->seq + out->seq_off[i], cg + 4 * (size_t)n_cig, (size_t)(l_seq + 1) / 2);
-            if (h->recs[i].sa_len) memcpy(out->sa + out->sa_off[i], r + h->recs[i].sa_off_in_rec, h->recs[i].sa_len);
+    parallel_for(h->units.size(), h->threads, [&](size_t lo, size_t hi) {
+        for (size_t u = lo; u < hi; ++u) {
+            const Unit& un = h->units[u];
+            size_t i = (size_t)un.row_base;
+            for (const Row& w : un.rows) {
+                out->tid[i] = w.tid; out->pos[i] = w.pos; out->mapq[i] = w.mapq; out->flag[i] = w.flag;
+                out->n_cigar[i] = w.n_cigar; out->l_seq[i] = w.l_seq; out->sa_len[i] = w.sa_len; out->qname_id[i] = h->qid[i];
+                out->cigar_off[i] = w.cigar_off; out->seq_off[i] = w.seq_off; out->sa_off[i] = w.sa_off;
+                ++i;
+            }
+            if (!un.sa.empty()) memcpy(out->sa + un.sa_base, un.sa.data(), un.sa.size());
         }
     });
-    tr.mark("SoA fill");
+    tr.mark("row arrays");
     return 0;
 }
 

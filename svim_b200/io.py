@@ -156,6 +156,7 @@ def _bamio_lib():
         lib.bamio_header.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_char_p]
         lib.bamio_qnames.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         lib.bamio_fill.argtypes = [C.c_void_p, C.c_void_p]
+        lib.bamio_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         lib.bamio_close.argtypes = [C.c_void_p]
         lib.bamio_close.restype = None
         _bamio = lib
@@ -163,11 +164,14 @@ def _bamio_lib():
 
 
 def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
-    """BAM -> AlignmentBatch with parallel BGZF inflate and parallel SoA fill."""
+    """BAM -> AlignmentBatch with the streaming multi-threaded decoder (csrc_host/bamio.cpp): blocks are
+    inflated into cache-warm per-thread buffers and the CIGAR / SEQ bytes go straight into the arrays allocated here (to an
+    upper bound computed from the BGZF index; only the pages actually written are ever committed)."""
     import ctypes as C
     lib = _bamio_lib()
     class Info(C.Structure):
-        _fields_ = [(n, C.c_int64) for n in ("n_records", "cigar_words", "seq_bytes", "sa_bytes", "n_qnames", "names_bytes")] + \
+        _fields_ = [(n, C.c_int64) for n in ("n_records", "cigar_words", "seq_bytes", "sa_bytes", "n_qnames", "names_bytes",
+                                             "cigar_bound_words", "seq_bound_bytes")] + \
                    [("n_contigs", C.c_int32), ("sorted_coordinate", C.c_int32)]
     inf = Info()
     err = C.create_string_buffer(256)
@@ -183,11 +187,13 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
             raise ValueError("contig names too long")
         names = names_buf.raw.split(b"\x00")[:inf.n_contigs]
         names = [x.decode("ascii") for x in names]
+        cigar = np.empty(inf.cigar_bound_words, dtype=np.uint32)
+        seq = np.empty(inf.seq_bound_bytes, dtype=np.uint8)
+        if lib.bamio_decode(h, cigar.ctypes.data, seq.ctypes.data, C.byref(inf), err, 256) != 0:
+            raise ValueError("read_bam_native(%s): %s" % (path, err.value.decode()))
         n = inf.n_records
-        arrays = {name: np.zeros(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
-        cigar = np.zeros(inf.cigar_words, dtype=np.uint32)
-        seq = np.zeros(inf.seq_bytes, dtype=np.uint8)
-        sa = np.zeros(max(1, inf.sa_bytes), dtype=np.uint8)
+        arrays = {name: np.empty(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
+        sa = np.empty(max(1, inf.sa_bytes), dtype=np.uint8)
         ptrs = (C.c_void_p * 14)(*[arrays[k].ctypes.data for k in ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off",
                                                                  "sa_off", "sa_len", "qname_id")], cigar.ctypes.data, seq.ctypes.data, sa.ctypes.data)
         lib.bamio_fill(h, ptrs)
@@ -196,7 +202,8 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
         qnames = [x.decode("ascii") for x in qbuf.raw.split(b"\x00")[:inf.n_qnames]]
     finally:
         lib.bamio_close(h)
-    return AlignmentBatch(names, lengths[:inf.n_contigs], arrays, cigar, seq, sa[:inf.sa_bytes], qnames, so.value.decode() or "unknown")
+    return AlignmentBatch(names, lengths[:inf.n_contigs], arrays, cigar[:inf.cigar_words], seq[:inf.seq_bytes], sa[:inf.sa_bytes], qnames,
+                          so.value.decode() or "unknown")
 
 
 def write_bam_native(path: str, batch: AlignmentBatch, level: int = 1, threads: int = 0):

@@ -406,3 +406,41 @@ def test_candidate_arrays_from_clusters_matches_naive():
             assert ids[off:off + len(want_ids)].tolist() == want_ids
             off += len(want_ids)
         assert off == len(ids)
+
+
+def test_native_bam_reader_records_spanning_units(tmp_path):
+    """The streaming decoder cuts the inflated stream into ~1 MiB units; records cut by a unit boundary travel through the
+    chain's carry buffer — including records longer than the 256 KiB headroom and longer than a whole unit."""
+    from svim_b200.records import BatchBuilder
+    rng = np.random.default_rng(9)
+    b = BatchBuilder(["c1", "c2"], [50_000_000, 1000], "coordinate")
+    pos = 0
+    for k in range(60):
+        n = int(rng.choice([50, 3000, 70_000, 400_000, 1_600_000]) if k % 3 else 20_000)
+        pos += int(rng.integers(1, 1000))
+        ops = []
+        left = n
+        while left > 0:
+            ln = int(min(left, rng.integers(1, 40 + n // 500))); ops.append((int(rng.choice([0, 0, 0, 1, 7, 8])), ln)); left -= ln
+            if rng.random() < 0.3:
+                ops.append((2, int(rng.integers(1, 9))))
+        seq = "".join(rng.choice(list("ACGTN"), size=n))
+        sa = "c1,%d,+,%dM,60,0;" % (k + 1, n) if k % 4 == 0 else None
+        b.add("q%d" % (k % 45), 0 if k % 5 else 0x800, 0, pos, 60, ops, seq, sa)
+    b.add("tail", 4, -1, -1, 0, "", None)
+    batch = b.finish()
+    p = str(tmp_path / "big.bam")
+    sio.write_bam_native(p, batch, threads=4)
+    for threads in (1, 3, 8):
+        a = sio.read_bam_native(p, threads=threads)
+        assert a.n == batch.n
+        for name, _ in a.FIELDS:
+            assert np.array_equal(getattr(a, name), getattr(batch, name)), (threads, name)
+        for blob in ("cigar", "seq", "sa"):
+            assert np.array_equal(getattr(a, blob), getattr(batch, blob)), (threads, blob)
+        assert [a.qname(int(i)) for i in a.qname_id] == [batch.qname(int(i)) for i in batch.qname_id]
+    # truncated file: the reader reports it instead of returning short data
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(ValueError):
+        sio.read_bam_native(p, threads=2)
