@@ -149,13 +149,23 @@ bool find_sa(const uint8_t* rec, size_t aux_begin, size_t rec_len, uint32_t& off
     return false;
 }
 
+// One BGZF payload (raw DEFLATE, exact output size known from ISIZE).  The z_stream is per thread and reset per block:
+// inflateInit2 / inflateEnd would malloc and free the decoder state for each of the ~10^5 blocks.
+struct ZStream {
+    z_stream zs; bool ready = false;
+    ~ZStream() { if (ready) inflateEnd(&zs); }
+};
+
 bool inflate_block(const uint8_t* src, size_t clen, uint8_t* dst, size_t ulen) {
-    z_stream zs; memset(&zs, 0, sizeof(zs));
-    if (inflateInit2(&zs, -15) != Z_OK) return false;
-    zs.next_in = const_cast<uint8_t*>(src); zs.avail_in = (uInt)clen; zs.next_out = dst; zs.avail_out = (uInt)ulen;
-    const int rc = inflate(&zs, Z_FINISH);
-    inflateEnd(&zs);
-    return rc == Z_STREAM_END && zs.avail_out == 0;
+    static thread_local ZStream z;
+    if (!z.ready) {
+        memset(&z.zs, 0, sizeof(z.zs));
+        if (inflateInit2(&z.zs, -15) != Z_OK) return false;
+        z.ready = true;
+    } else if (inflateReset(&z.zs) != Z_OK) return false;
+    z.zs.next_in = const_cast<uint8_t*>(src); z.zs.avail_in = (uInt)clen; z.zs.next_out = dst; z.zs.avail_out = (uInt)ulen;
+    const int rc = inflate(&z.zs, Z_FINISH);
+    return rc == Z_STREAM_END && z.zs.avail_out == 0;
 }
 
 // BAM header (magic, text, references) at the front of `d`: returns bytes consumed, 0 = not all there yet, -1 = not BAM
@@ -299,13 +309,18 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
     uint64_t n_rows = 0, cig_words = 0, seq_bytes = 0, sa_bytes = 0;
     const size_t HEADROOM = (size_t)256 << 10;
 
+    std::atomic<int64_t> ns_inflate{0}, ns_wait{0}, ns_chain{0}, ns_fill{0};
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point a) { return (int64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - a).count(); };
     auto worker = [&]() {
+        int64_t t_inf = 0, t_wait = 0, t_chain = 0, t_fill = 0;
         std::vector<uint8_t> buf;            // [headroom | unit data]
         std::vector<uint8_t> joined;         // only when the carry does not fit the headroom
         for (;;) {
             const size_t u = next_unit.fetch_add(1);
-            if (u >= n_units) return;
+            if (u >= n_units) { ns_inflate += t_inf; ns_wait += t_wait; ns_chain += t_chain; ns_fill += t_fill; return; }
             Unit& un = h->units[u];
+            auto t0 = now();
             if (buf.size() < HEADROOM + un.ulen) buf.resize(HEADROOM + un.ulen);
             bool ok = !failed.load(std::memory_order_relaxed);
             if (ok) {
@@ -316,8 +331,10 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
                 }
                 if (!ok) { fail_msg = "inflate failed"; failed = 1; }
             }
+            t_inf += since(t0); t0 = now();
             // ---- chain turn ----
             for (unsigned spins = 0; chain_turn.load(std::memory_order_acquire) != u; ++spins) if (spins > 64) std::this_thread::yield();
+            t_wait += since(t0); t0 = now();
             const uint8_t* d = nullptr; size_t n = 0;
             if (!failed.load()) {
                 if (carry.size() <= HEADROOM) {
@@ -363,6 +380,7 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
                 carry.assign(d + p, d + n);              // the tail of a record cut by the unit boundary (or of the header)
             }
             chain_turn.store(u + 1, std::memory_order_release);
+            t_chain += since(t0); t0 = now();
             if (failed.load()) continue;
             // ---- fill: this unit's records from the warm buffer into the caller's blobs ----
             for (const Row& w : un.rows) {
@@ -373,6 +391,7 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
                 for (uint32_t k = w.n_cigar; k < ((w.n_cigar + 3u) & ~3u); ++k) dst[k] = 0;
                 memcpy(seq + w.seq_off, cg + 4 * (size_t)w.n_cigar, (size_t)(w.l_seq + 1) / 2);
             }
+            t_fill += since(t0);
         }
     };
     {
@@ -385,6 +404,8 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
     if (!failed && !carry.empty()) { fail_msg = h->header_done ? "truncated record" : "truncated BAM header"; failed = 1; }
     if (failed) { if (err && errcap > 0) snprintf(err, errcap, "%s", fail_msg); return -1; }
     tr.mark("inflate + chain + fill");
+    if (tr.on) fprintf(stderr, "[bamio]   thread-time sums: inflate %.0f ms, wait for chain turn %.0f ms, chain turn %.0f ms, fill %.0f ms\n",
+                       ns_inflate.load() / 1e6, ns_wait.load() / 1e6, ns_chain.load() / 1e6, ns_fill.load() / 1e6);
     // ---- read-name ids -------------------------------------------------------------------------------------------------
     const size_t nr = (size_t)n_rows;
     h->qid.resize(nr);
