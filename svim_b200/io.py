@@ -175,7 +175,7 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
                    [("n_contigs", C.c_int32), ("sorted_coordinate", C.c_int32)]
     inf = Info()
     err = C.create_string_buffer(256)
-    threads = threads or min(32, os.cpu_count() or 1)
+    threads = threads or min(128, os.cpu_count() or 1)
     h = lib.bamio_open(path.encode(), threads, C.byref(inf), err, 256)
     if not h:
         raise ValueError("read_bam_native(%s): %s" % (path, err.value.decode()))
