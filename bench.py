@@ -303,10 +303,14 @@ def main():
         ctx._check(ctx.lib.svimgpu_barrier_max(ctx.h, C.byref(v)))
         return v.value
 
+    xchg_ms = {}
+
     def cluster_step():
         if world > 1:
             st = _lib.CollectStats()
             ctx._check(ctx.lib.svimgpu_exchange_signatures(ctx.h, aln_base, C.byref(st)))
+            # the timing slots are reset by the next call: keep the signature exchange apart from the cluster exchange
+            xchg_ms["nccl_exchange_signatures"] = ctx.timings().get("nccl_exchange", 0.0)
             ctx.use_collected(0)
             return st, ctx.cluster(sharded=True)
         ctx.use_collected(0)
@@ -326,7 +330,7 @@ def main():
         tm = dict(ctx.timings())
         xst, (clst, clusters, members) = cluster_step()
         ms = ctx.timer_stop()
-        for k, v in list(tm.items()) + list(ctx.timings().items()):
+        for k, v in list(tm.items()) + list(ctx.timings().items()) + list(xchg_ms.items()):
             if v and s >= args.warmup:
                 stage_ms.setdefault(k, []).append(v)
         if s >= args.warmup:
@@ -363,7 +367,7 @@ def main():
         sigs, ins = ctx.fetch_signatures(0, fst)
         ms = ctx.timer_stop()
         if s >= args.warmup:
-            for k, v in list(tm.items()) + list(tm2.items()):
+            for k, v in list(tm.items()) + list(tm2.items()) + list(xchg_ms.items()):
                 if v:
                     e2e_stage.setdefault(k, []).append(v)
         d2h = 2 * sigs.nbytes + ins.nbytes + clusters.nbytes + members.nbytes     # signature records cross twice (staging + fetch)
