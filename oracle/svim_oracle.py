@@ -874,10 +874,14 @@ def record_reference_ends(batch) -> np.ndarray:
     counting as 1; pos + 1 otherwise.  pysam's `reference_end` is this value, or None for unmapped / CIGAR-less records."""
     pos = np.asarray(batch.pos, dtype=np.int64)
     consumes = np.array([1, 0, 1, 1, 0, 0, 0, 1, 1] + [0] * 7, dtype=np.int64)
-    cs = np.zeros(batch.cigar.size + 1, dtype=np.int64)
-    np.cumsum((batch.cigar >> 4).astype(np.int64) * consumes[batch.cigar & 15], out=cs[1:])
     off = batch.cigar_off.astype(np.int64)
-    rlen = cs[off + batch.n_cigar.astype(np.int64)] - cs[off]
+    cnt = batch.n_cigar.astype(np.int64)
+    lo = int(off.min()) if batch.n else 0                   # a slice shares the blob of its parent: only its own range is summed
+    hi = int((off + cnt).max()) if batch.n else 0
+    words = batch.cigar[lo:hi]
+    cs = np.zeros(words.size + 1, dtype=np.int64)
+    np.cumsum((words >> 4).astype(np.int64) * consumes[words & 15], out=cs[1:])
+    rlen = cs[off - lo + cnt] - cs[off - lo]
     rlen[((batch.flag & 0x4) != 0) | (batch.n_cigar == 0)] = 0
     return pos + np.maximum(rlen, 1)
 

@@ -1,10 +1,10 @@
 """`python -m svim_b200 alignment <working_dir> <bam_file> <genome> [options]`
 
-Runs the two stages this package implements (COLLECT -> CLUSTER) on the GPU with the option names and defaults
-of the reference's `svim alignment` sub-command (SVIM_input_parsing.py:262-371) and writes the signature-cluster
-BED files the reference writes after CLUSTER (`signatures/*.bed`).  COMBINE / genotyping / final VCF are the
-reference's downstream stages: use `python -m svim_b200.patch alignment ...` with the reference installed to run
-the whole pipeline with these two stages replaced.
+Runs COLLECT -> CLUSTER on the GPU with the option names and defaults of the reference's `svim alignment`
+sub-command (SVIM_input_parsing.py:262-371), coordinate- or queryname-sorted input (svim:89-111), and writes the
+signature-cluster BED files the reference writes after CLUSTER (`signatures/*.bed`).  COMBINE and the final VCF are the
+reference's downstream stages: `python -m svim_b200.patch alignment ...` with the reference installed runs the whole
+pipeline with COLLECT, CLUSTER, the cut&paste search, the candidate clustering and GENOTYPE rebound to this package.
 """
 import argparse
 import logging
@@ -56,15 +56,20 @@ def main(argv=None):
     logging.basicConfig(level=logging.DEBUG if options.verbose else logging.INFO, format="%(asctime)s [%(levelname)-7.7s]  %(message)s")
     os.makedirs(options.working_dir, exist_ok=True)
     from .io import read_alignments
-    from .SVIM_COLLECT import analyze_alignment_file_coordsorted
+    from .SVIM_COLLECT import analyze_alignment_file_coordsorted, analyze_alignment_file_querysorted
     from .SVIM_CLUSTER import cluster_sv_signatures
     t0 = time.perf_counter()
     batch = read_alignments(options.bam_file)
-    if batch.sort_order != "coordinate":
-        logging.warning("input is not coordinate-sorted (header SO:%s); the query-sorted mode of the reference is not implemented here", batch.sort_order)
+    # svim:89-111: coordinate-sorted and queryname-sorted inputs take different COLLECT paths, anything else is refused
+    if batch.sort_order not in ("coordinate", "queryname"):
+        logging.error("Input BAM file needs to be coordinate-sorted or queryname-sorted. The given file, however, is unsorted according to its header line.")
+        return 1
     logging.info("****************** STEP 1: COLLECT ******************")
     t1 = time.perf_counter()
-    sigs, all_bnds = analyze_alignment_file_coordsorted(batch, options)
+    if batch.sort_order == "queryname":
+        sigs, all_bnds = analyze_alignment_file_querysorted(batch, options)
+    else:
+        sigs, all_bnds = analyze_alignment_file_coordsorted(batch, options)
     t2 = time.perf_counter()
     for t in ("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"):
         logging.info("Found {0} signatures of type {1}".format(sum(1 for s in sigs if s.type == t), t))
