@@ -444,3 +444,32 @@ def test_native_bam_reader_records_spanning_units(tmp_path):
     open(p, "wb").write(raw[: len(raw) // 2])
     with pytest.raises(ValueError):
         sio.read_bam_native(p, threads=2)
+
+
+def test_genotype_marshalling_of_candidate_objects():
+    # svim_b200.SVIM_genotyping.genotype_arrays: locus per type, distinct member read NAMES -> sorted qname ids (+ sentinels for
+    # names no record carries: they still count in alt_reads, SVIM_genotyping.py:51,93)
+    from svim_b200.records import BatchBuilder
+    from svim_b200.SVIM_genotyping import genotype_arrays
+    b = BatchBuilder(["c1", "c2"], [1000, 2000])
+    for k, nm in enumerate(["zed", "amy", "bob", "amy"]):
+        b.add(nm, 0, 0, 10 * k, 60, "50M", None)
+    batch = b.finish()          # ids by first appearance: zed 0, amy 1, bob 2
+
+    class M:
+        def __init__(self, r): self.read = r
+
+    class Cand:
+        def __init__(self, src, dst, reads): self.src, self.dst, self.members = src, dst, [M(r) for r in reads]
+        def get_source(self): return self.src
+        def get_destination(self): return self.dst
+
+    cands = [Cand(("c1", 5, 9), ("c2", 100, 104), ["bob", "zed", "bob"]), Cand(("c2", 7, 8), ("c1", 1, 2), ["ghost", "amy"]), Cand(("c1", 0, 1), ("c1", 0, 1), [])]
+    arr, ids = genotype_arrays(cands, batch, "DEL")
+    assert arr["tid"].tolist() == [0, 1, 0] and arr["start"].tolist() == [5, 7, 0] and arr["end"].tolist() == [9, 8, 1]
+    assert arr["n_variant_reads"].tolist() == [2, 2, 0] and arr["variant_off"].tolist() == [0, 2, 4]
+    assert ids.tolist() == [0, 2, 1, 0xFFFFFFFF]
+    arr, ids = genotype_arrays(cands, batch, "INS")
+    assert arr["tid"].tolist() == [1, 0, 0] and arr["start"].tolist() == [100, 1, 0]
+    with pytest.raises(KeyError):
+        genotype_arrays([Cand(("nope", 1, 2), ("nope", 1, 2), [])], batch, "DEL")
