@@ -10,6 +10,7 @@ File formats follow the SAM/BAM specification (SAMv1 §1.4, §4.2).
 from __future__ import annotations
 
 import os
+import sys
 import struct
 import zlib
 from typing import List, Optional, Tuple
@@ -163,6 +164,18 @@ def _bamio_lib():
     return _bamio
 
 
+def _reserve(n: int, dtype) -> np.ndarray:
+    """Uninitialised array of `n` items whose pages are committed only when written: an anonymous MAP_NORESERVE mapping, so an
+    upper-bound allocation is not refused by the kernel's overcommit heuristic; falls back to np.empty."""
+    nbytes = max(1, int(n)) * np.dtype(dtype).itemsize
+    try:
+        import mmap
+        flags = mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | getattr(mmap, "MAP_NORESERVE", 0x4000 if sys.platform.startswith("linux") else 0)
+        return np.frombuffer(mmap.mmap(-1, nbytes, flags=flags), dtype=dtype)[:max(0, int(n))]
+    except (OSError, ValueError, AttributeError):
+        return np.empty(int(n), dtype=dtype)
+
+
 def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
     """BAM -> AlignmentBatch with the streaming multi-threaded decoder (csrc_host/bamio.cpp): blocks are
     inflated into cache-warm per-thread buffers and the CIGAR / SEQ bytes go straight into the arrays allocated here (to an
@@ -187,8 +200,8 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
             raise ValueError("contig names too long")
         names = names_buf.raw.split(b"\x00")[:inf.n_contigs]
         names = [x.decode("ascii") for x in names]
-        cigar = np.empty(inf.cigar_bound_words, dtype=np.uint32)
-        seq = np.empty(inf.seq_bound_bytes, dtype=np.uint8)
+        cigar = _reserve(inf.cigar_bound_words, np.uint32)
+        seq = _reserve(inf.seq_bound_bytes, np.uint8)
         if lib.bamio_decode(h, cigar.ctypes.data, seq.ctypes.data, C.byref(inf), err, 256) != 0:
             raise ValueError("read_bam_native(%s): %s" % (path, err.value.decode()))
         n = inf.n_records
