@@ -35,8 +35,9 @@ def _read_id(batch, index, name):
     """qname id of a read name, or None when no record carries that name (such a read can never be skipped at :63)."""
     if index is not None:
         return index.get(name)
-    if name.startswith("read") and name[4:].isdigit():      # synthetic batches: names are "read<id>"
-        return int(name[4:])
+    if name.startswith("read") and name[4:].isdigit() and len(name) <= 14:      # synthetic batches: names are "read<id>"
+        i = int(name[4:])
+        return i if i < 0xFFFFFFFF else None
     return None
 
 
