@@ -473,3 +473,186 @@ def test_genotype_marshalling_of_candidate_objects():
     assert arr["tid"].tolist() == [1, 0, 0] and arr["start"].tolist() == [100, 1, 0]
     with pytest.raises(KeyError):
         genotype_arrays([Cand(("nope", 1, 2), ("nope", 1, 2), [])], batch, "DEL")
+
+
+def test_genotype_host_mirror_against_golden_with_oracle_backed_context(golden, monkeypatch):
+    """Host logic of svim_b200.SVIM_genotyping.genotype (score filter, marshalling, result/exception mapping) without a GPU: the
+    context's `genotype` entry is replaced by one that answers from the oracle in the C ABI's array format, and the outcome must
+    equal the reference's golden outputs.  (The CUDA entry itself is checked in tests/test_gpu_genotype.py.)"""
+    import types
+    from svim_b200 import _lib, runtime
+    from svim_b200.SVIM_genotyping import genotype
+    from oracle import svim_oracle as orc
+    batch, genome, exp = golden("geno_mini_mixed")
+    ends = orc.record_reference_ends(batch)
+    calls = {"upload": 0}
+
+    class FakeCtx:
+        resident = None
+
+        def upload(self, b):
+            calls["upload"] += 1
+
+        def genotype(self, type_code, gp, cands, variant_ids, contig_lengths):
+            t = _lib.TYPE_NAMES[type_code]
+            res = np.zeros(len(cands), dtype=_lib.GENO_RESULT_DTYPE)
+            p = orc.GenoParams(min_mapq=gp.min_mapq, minimum_score=-10**9, minimum_depth=gp.minimum_depth,
+                               homozygous_threshold=gp.homozygous_threshold, heterozygous_threshold=gp.heterozygous_threshold)
+            for k, c in enumerate(cands):
+                ids = variant_ids[int(c["variant_off"]):int(c["variant_off"]) + int(c["n_variant_reads"])]
+                oc = orc.GenoCand(batch.contig_names[int(c["tid"])], int(c["start"]), int(c["end"]), 0,
+                                  [batch.qname(int(q)) if q != 0xFFFFFFFF else "\x00none%d" % i for i, q in enumerate(ids)])
+                orc.genotype([oc], batch, t, p, ends)
+                res[k]["support_fraction"] = float("nan") if oc.support_fraction == "." else oc.support_fraction
+                res[k]["genotype"] = _lib.GENOTYPES.index(oc.genotype); res[k]["ref_reads"] = oc.ref_reads; res[k]["alt_reads"] = oc.alt_reads
+            return res
+
+    fake = FakeCtx()
+    monkeypatch.setattr(runtime, "context", lambda device=None: fake)
+
+    class M:
+        def __init__(self, r): self.read = r
+
+    class Cand:
+        def __init__(self, contig, start, end, score, reads):
+            self.locus, self.score, self.members = (contig, start, end), score, [M(r) for r in reads]
+            self.support_fraction, self.genotype, self.ref_reads, self.alt_reads = ".", "./.", None, None
+        def get_source(self): return self.locus
+        def get_destination(self): return self.locus
+
+    opts = types.SimpleNamespace(min_mapq=20, minimum_score=3, minimum_depth=4, homozygous_threshold=0.8, heterozygous_threshold=0.2)
+    for k, v in exp["params"].items():
+        setattr(opts, k, v)
+    n = 0
+    for t in ("DEL", "INV", "INS", "DUP_INT"):
+        cands = [Cand(*row[0]) for row in exp["genotype"][t]]
+        genotype(cands, batch, t, opts)
+        assert [[c.support_fraction, c.genotype, c.ref_reads, c.alt_reads] for c in cands] == [row[1] for row in exp["genotype"][t]], t
+        n += len(cands)
+    assert n > 30 and calls["upload"] == 1 and fake.resident is batch          # uploaded once, then reused
+    with pytest.raises(ValueError):
+        genotype([Cand("chr1", 1, 2, 9, [])], batch, "BND", opts)
+    with pytest.raises(ValueError):
+        genotype([Cand("chr1", 1, 2, 9, [])], batch.take(np.arange(batch.n), "queryname"), "DEL", opts)
+
+
+def _oracle_backed_context(batch, genome):
+    """A stand-in for _lib.Context whose COLLECT / CLUSTER entries answer from the oracle in the C ABI's array formats, so the host
+    mirror (marshalling, materialisation, object surface) can be checked against the golden vectors without a GPU."""
+    from svim_b200 import _lib
+    from oracle import svim_oracle as orc
+    tid_of = {n: i for i, n in enumerate(batch.contig_names)}
+    qid_of = {batch.qname(i): i for i in set(batch.qname_id.tolist())}
+    inv_code = {d: i for i, d in enumerate(_lib.INV_DIRECTIONS)}
+
+    def to_arrays(sigs):
+        arr = np.zeros(len(sigs), dtype=_lib.SIG_DTYPE); blob = bytearray()
+        for k, s in enumerate(sigs):
+            r = arr[k]
+            r["type"] = _lib.TYPE_CODE[s.type]; r["contig1"] = tid_of[s.contig]; r["start"] = s.start; r["end"] = s.end
+            r["qname_id"] = qid_of[s.read]; r["contig2"] = -1
+            fl = 1 if s.signature == "suppl" else 0
+            if s.type == "INS":
+                r["seq_off"], r["seq_len"] = len(blob), len(s.sequence); blob += s.sequence.encode()
+            elif s.type == "INV":
+                fl |= inv_code[s.direction] << 4
+            elif s.type == "DUP_TAN":
+                r["copies"] = s.copies; fl |= 2 if s.fully_covered else 0
+            elif s.type == "DUP_INT":
+                r["contig2"] = tid_of[s.contig2]; r["pos"] = s.pos
+            elif s.type == "BND":
+                r["contig2"] = tid_of[s.contig2]; r["pos"] = s.pos; fl |= (4 if s.dir1 == "rev" else 0) | (8 if s.dir2 == "rev" else 0)
+            r["flags"] = fl
+        return arr, np.frombuffer(bytes(blob), dtype=np.uint8)
+
+    class Ctx:
+        resident = None; contigs_key = None; genome_key = None; collect_token = None; collect_batch = None
+
+        def set_params(self, p):
+            self.p = orc.Params(min_mapq=p.min_mapq, min_sv_size=p.min_sv_size, max_sv_size=p.max_sv_size, segment_gap_tolerance=p.segment_gap_tolerance,
+                                segment_overlap_tolerance=p.segment_overlap_tolerance, all_bnds=bool(p.all_bnds),
+                                partition_max_distance=p.partition_max_distance, position_distance_normalizer=p.position_distance_normalizer,
+                                edit_distance_normalizer=p.edit_distance_normalizer, cluster_max_distance=p.cluster_max_distance)
+
+        def set_contigs(self, names): pass
+        def set_genome(self, g): pass
+
+        def collect_host(self, b):
+            self.lists = orc.collect(b, self.p)
+            self.arrays = [to_arrays(l) for l in self.lists]
+            st = _lib.CollectStats()
+            st.n_signatures, st.n_twin_signatures = len(self.lists[0]), len(self.lists[1])
+            st.ins_bytes, st.twin_ins_bytes = self.arrays[0][1].size, self.arrays[1][1].size
+            return st
+
+        def fetch_signatures(self, which, stats): return self.arrays[which]
+        def use_collected(self, which=0): self.which = which
+
+        def cluster(self, sharded=False):
+            lst = self.lists[self.which]
+            index_of = {id(s): i for i, s in enumerate(lst)}
+            stats = {}
+            res = orc.cluster(lst, genome, self.p, stats)
+            rows, mem = [], []
+            by_type = dict(zip(("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"), res))
+            for t in _lib.TYPE_NAMES:                    # enum order of the ABI: DEL, INS, INV, DUP_TAN, BND, DUP_INT
+                for c in by_type[t]:
+                    nan = float("nan")
+                    rows.append((c.start, c.end, c.dest_start or 0, c.dest_end or 0, c.score, nan if c.std_span is None else c.std_span,
+                                 nan if c.std_pos is None else c.std_pos, len(mem), len(c.members), _lib.TYPE_CODE[t],
+                                 1 if c.dir1 == "rev" else 0, 1 if c.dir2 == "rev" else 0, 0, 0))
+                    mem += [index_of[id(m)] for m in c.members]
+            st = _lib.ClusterStats()
+            st.n_clusters_total, st.n_members = len(rows), len(mem)
+            return st, np.array(rows, dtype=_lib.CLUSTER_DTYPE) if rows else np.zeros(0, _lib.CLUSTER_DTYPE), np.array(mem, dtype=np.uint32)
+    return Ctx()
+
+
+@pytest.mark.parametrize("name", ["mini_mixed", "mini_mixed_allbnds", "mini_ins"])
+def test_collect_cluster_host_mirror_against_golden_with_oracle_backed_context(golden, monkeypatch, name):
+    """svim_b200.SVIM_COLLECT.analyze_alignment_file_coordsorted + SVIM_CLUSTER.cluster_sv_signatures (the two call sites svim:102 and
+    svim:132): records -> SVSignature objects -> cluster objects, compared attribute by attribute with the reference's golden outputs."""
+    import types
+    from svim_b200 import runtime
+    from svim_b200.SVIM_COLLECT import analyze_alignment_file_coordsorted
+    from svim_b200.SVIM_CLUSTER import cluster_sv_signatures
+    batch, genome, exp = golden(name)
+    fake = _oracle_backed_context(batch, genome)
+    monkeypatch.setattr(runtime, "context", lambda device=None: fake)
+    runtime.register_genome("golden.fa", genome)
+    opts = types.SimpleNamespace(genome="golden.fa", **exp["params"])
+    sigs, twins = analyze_alignment_file_coordsorted(batch, opts)
+
+    def sig_row(s):
+        d = dict(type=s.type, signature=s.signature, read=s.read)
+        if s.type in ("DEL", "INS", "INV", "DUP_TAN"):
+            d.update(contig=s.contig, start=s.start, end=s.end)
+            if s.type == "INS": d["sequence"] = s.sequence
+            if s.type == "INV": d["direction"] = s.direction
+            if s.type == "DUP_TAN": d.update(copies=s.copies, fully_covered=s.fully_covered)
+        elif s.type == "DUP_INT":
+            d.update(contig=s.contig1, start=s.start, end=s.end, contig2=s.contig2, pos=s.pos)
+        else:
+            d.update(contig=s.contig1, start=s.pos1, end=s.pos1 + 1, contig2=s.contig2, pos=s.pos2, dir1=s.direction1, dir2=s.direction2)
+        fields = ("type", "contig", "start", "end", "contig2", "pos", "dir1", "dir2", "direction", "copies", "fully_covered", "signature", "read", "sequence")
+        return [d.get(f) for f in fields]
+
+    assert [sig_row(s) for s in sigs] == exp["signatures"]
+    assert [sig_row(s) for s in twins] == exp["all_bnds_signatures"]
+    # object surface used downstream (SVSignature.py): keys, sources, destinations, strings
+    for s in sigs[:200]:
+        assert s.get_key()[0] == s.type and isinstance(s.as_string(), str) and len(s.get_source()) == 3
+    for lst, key in ((sigs, "clusters"), (twins, "all_bnds_clusters")):
+        res = cluster_sv_signatures(lst, opts)
+        index_of = {id(s): i for i, s in enumerate(lst)}
+        for t, cl in zip(("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"), res):
+            got = []
+            for c in cl:
+                m = [index_of[id(x)] for x in c.members]
+                if hasattr(c, "source_contig"):
+                    got.append([c.type, c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end, c.score, c.size,
+                                c.std_span, c.std_pos, getattr(c, "direction1", None), getattr(c, "direction2", None), m])
+                else:
+                    got.append([c.type, c.contig, c.start, c.end, None, None, None, c.score, c.size, c.std_span, c.std_pos, None, None, m])
+            assert got == exp[key][t], (key, t)
+        assert isinstance(res, tuple) and all(type(x) is list for x in res)      # COMBINE mutates these lists in place
