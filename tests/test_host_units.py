@@ -656,3 +656,39 @@ def test_collect_cluster_host_mirror_against_golden_with_oracle_backed_context(g
                     got.append([c.type, c.contig, c.start, c.end, None, None, None, c.score, c.size, c.std_span, c.std_pos, None, None, m])
             assert got == exp[key][t], (key, t)
         assert isinstance(res, tuple) and all(type(x) is list for x in res)      # COMBINE mutates these lists in place
+
+
+def test_flag_cutpaste_host_mirror_against_golden(monkeypatch):
+    # svim_b200.SVIM_merging.flag_cutpaste_candidates: candidate construction + flagging; the distance search answered in numpy
+    import gzip, json, types
+    from conftest import GOLDEN
+    from svim_b200 import runtime
+    from svim_b200.SVIM_merging import flag_cutpaste_candidates
+
+    class Ctx:
+        def closest_source(self, a_s, a_e, b_s, b_e, N):
+            a_s, a_e, b_s, b_e = (np.asarray(x, dtype=np.int64) for x in (a_s, a_e, b_s, b_e))
+            idx = np.zeros(len(a_s), np.int64); dist = np.zeros(len(a_s))
+            for k in range(len(a_s)):
+                d = np.abs((b_s + b_e) // 2 - (a_s[k] + a_e[k]) // 2) / N + np.abs((b_e - b_s) - (a_e[k] - a_s[k])) / np.maximum(b_e - b_s, a_e[k] - a_s[k])
+                idx[k] = int(np.argmin(d)); dist[k] = d[idx[k]]
+            return idx, dist
+    monkeypatch.setattr(runtime, "context", lambda device=None: Ctx())
+    g = json.load(gzip.open(os.path.join(GOLDEN, "cutpaste.golden.json.gz"), "rt"))
+    opts = types.SimpleNamespace(position_distance_normalizer=g["position_distance_normalizer"], del_ins_dup_max_distance=g["del_ins_dup_max_distance"])
+
+    class Uni:
+        def __init__(self, c, s, e): self.src = (c, s, e)
+        def get_source(self): return self.src
+
+    class Bi(Uni):
+        def __init__(self, c, s, e, dc, dp, k):
+            super().__init__(c, s, e); self.dst = (dc, dp, dp + e - s); self.members, self.score, self.std_span, self.std_pos = ["m%d" % k], 4.0, None, 1.5
+        def get_destination(self): return self.dst
+    for case in g["cases"]:
+        got = flag_cutpaste_candidates([Bi(*r, k) for k, r in enumerate(case["inss"])], [Uni(*d) for d in case["dels"]], opts)
+        assert [bool(c.cutpaste) for c in got] == case["cutpaste"]
+        assert all(c.type == "DUP_INT" and c.score == 4.0 and c.std_pos == 1.5 for c in got)
+    assert flag_cutpaste_candidates([], [], opts) == []
+    with pytest.raises(IndexError):
+        flag_cutpaste_candidates([Bi("c", 1, 5, "c", 9, 0)], [], opts)
