@@ -16,6 +16,10 @@ Printed JSON (rank 0, one line):
             the signature + cluster records inside the timed region, every step
   roofline  the CIGAR-scan kernel: algorithmic bytes / its CUDA-event duration vs measured HBM peak
   cpu_baseline  oracle port of the reference, 1 host thread, bounded genomic slice of the same input
+  clocks    SM clock / throttle reasons sampled through NVML every 2 ms during the timed region (also under e2e)
+  genotype  (N=1, outside the timed step) GENOTYPE of the step's DEL+INS candidates through svimgpu_genotype: candidates/s, the
+            one-off preparation (k_ref_end streams every CIGAR once more) and the oracle on a bounded sample beside it
+  e2e_from_bam  (--with-bam) the same path starting from a BAM file: native streaming decode + pageable H2D + COLLECT + CLUSTER
 """
 import argparse
 import ctypes as C
