@@ -15,6 +15,7 @@ import time
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
 import make_golden as mg  # noqa: E402  (activates the reference environment)
 
 import numpy as np  # noqa: E402
@@ -58,6 +59,50 @@ def random_case(seed):
     return batch, genome, opts, gopts
 
 
+def combine_twins(seed, tot):
+    import random
+    from svim.SVIM_clustering import partition_and_cluster_candidates as ref_pcc
+    from svim.SVCandidate import CandidateDuplicationInterspersed as RefCand
+    from svim.SVIM_merging import flag_cutpaste_candidates
+    from svim.SVSignature import SignatureClusterUniLocal, SignatureClusterBiLocal
+    from svim.SVIM_input_parsing import parse_arguments
+    rng = random.Random(50_000 + seed)
+    bad = []
+    pmd = rng.choice([100, 1000, 5000]); cmd = rng.choice([0.2, 0.5, 0.8]); pdn = rng.choice([300, 900])
+    options = parse_arguments("2.0.0", ["alignment", "wd", "x.bam", "g.fa", "--partition_max_distance", str(pmd), "--cluster_max_distance", str(cmd),
+                                        "--position_distance_normalizer", str(pdn)])
+    rows = []
+    for locus in range(rng.randint(1, 25)):
+        contig = rng.choice(["chr1", "chr10", "chr2"]); base = rng.randint(10_000, 300_000); dbase = rng.randint(10_000, 300_000)
+        for k in range(rng.choice([1, 1, 2, 3, 6, 12, 130 if locus == 0 and seed % 5 == 0 else 4])):
+            s0 = base + rng.randint(-400, 400); ln = rng.randint(100, 900) + rng.choice([0, 0, 1500]); d = dbase + rng.randint(-400, 400) + rng.choice([0, 0, 4000])
+            rows.append([contig, s0, s0 + ln, rng.choice(["chr1", "chr2"]), d, d + ln + rng.randint(-5, 5), ["m%d_%d" % (locus, k)],
+                         rng.randint(1, 40) + rng.random(), rng.choice([None, rng.random() * 30]), rng.choice([None, rng.random() * 30]), rng.random() < 0.2])
+    rng.shuffle(rows)
+    ref = ref_pcc([RefCand(*r[:10], cutpaste=r[10]) for r in rows], options, "interspersed duplication candidates")
+    mine = orc.partition_and_cluster_candidates([orc.Cand(*r) for r in rows], orc.Params(partition_max_distance=pmd, cluster_max_distance=cmd, position_distance_normalizer=pdn))
+    if [[c.source_contig, c.source_start, c.source_end, c.dest_contig, c.dest_start, c.dest_end, c.members, c.score, c.std_span, c.std_pos, c.cutpaste] for c in ref] != \
+       [[c.contig, c.start, c.end, c.dest_contig, c.dest_start, c.dest_end, c.members, c.score, c.std_span, c.std_pos, c.cutpaste] for c in mine]:
+        bad.append("candidates")
+    tot["candidates"] = tot.get("candidates", 0) + len(rows)
+    dels = [(rng.choice(["chr1", "chr2"]), s0, s0 + rng.choice([50, 300, rng.randint(40, 5000)])) for s0 in (rng.randint(0, 100_000) for _ in range(rng.randint(1, 200)))]
+    inss = []
+    for k in range(rng.randint(1, 60)):
+        if rng.random() < 0.5:
+            d = rng.choice(dels); s0 = d[1] + rng.choice([0, 1, -3, 40, 900]); ln = d[2] - d[1] + rng.choice([0, 0, 2, -7, 100])
+        else:
+            s0 = rng.randint(0, 100_000); ln = rng.randint(40, 5000)
+        inss.append((rng.choice(["chr1", "chr2"]), s0, s0 + max(1, ln), "chr1", rng.randint(0, 100_000)))
+    ddn = rng.choice([0.5, 1.0, 2.0]); options.del_ins_dup_max_distance = ddn
+    refc = flag_cutpaste_candidates([SignatureClusterBiLocal(c, s0, e, dc, dp, dp + e - s0, 4.0, 2, ["m"], "DUP_INT", None, None) for c, s0, e, dc, dp in inss],
+                                    [SignatureClusterUniLocal(c, s0, e, 5.0, 3, ["m"], "DEL", 1.0, 1.0) for c, s0, e in dels], options)
+    minec = orc.flag_cutpaste([(s0, e) for _, s0, e, _, _ in inss], [(s0, e) for _, s0, e in dels], pdn, ddn)
+    if [bool(c.cutpaste) for c in refc] != [m[2] for m in minec]:
+        bad.append("cutpaste")
+    tot["cutpaste_queries"] = tot.get("cutpaste_queries", 0) + len(inss)
+    return bad
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=40)
@@ -87,6 +132,16 @@ def main():
             if [c.result() for c in cands] != [row[1] for row in gref[t]]:
                 bad.append("genotype/" + t)
             n_g += len(cands)
+        # the same records sorted by read name through the query-sorted COLLECT (SVIM_COLLECT.py:96-129), every 3rd case
+        if seed % 3 == 0:
+            from conftest import querysort_order
+            qb = batch.take(querysort_order(batch), "queryname")
+            qref = mg.run_reference(qb, genome, opts, True)
+            qmine = mg.run_oracle(qb, genome, opts, True)
+            bad += ["querysorted/" + k for k in qref if qref[k] != qmine[k]]
+            tot["querysorted_cases"] = tot.get("querysorted_cases", 0) + 1
+        # COMBINE-stage twins on seeded random cluster-like inputs: candidate clustering and the cut&paste search
+        bad += combine_twins(seed, tot)
         n_cl = sum(len(v) for v in ref["clusters"].values()) + sum(len(v) for v in ref["all_bnds_clusters"].values())
         tot["cases"] += 1; tot["records"] += batch.n; tot["signatures"] += len(ref["signatures"]); tot["twin_signatures"] += len(ref["all_bnds_signatures"])
         tot["clusters"] += n_cl; tot["genotyped"] += n_g; tot["mismatches"] += len(bad)
