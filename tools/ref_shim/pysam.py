@@ -171,6 +171,7 @@ class AlignmentFile:
         b = self._batch
         self.header = {"HD": {"SO": b.sort_order}, "SQ": [{"SN": n, "LN": int(l)} for n, l in zip(b.contig_names, b.contig_lengths)]}
         self.references = tuple(b.contig_names)
+        self.lengths = tuple(int(l) for l in b.contig_lengths)
 
     @classmethod
     def from_batch(cls, batch):
@@ -178,6 +179,10 @@ class AlignmentFile:
 
     def get_tid(self, name):
         return self._batch.get_tid(name)
+
+    def check_index(self):
+        """svim:93-98 only asks whether an index exists; region fetch below does not need one."""
+        return True
 
     def getrname(self, tid):
         return self._batch.getrname(tid)
