@@ -2,8 +2,8 @@
 """Drop-in check of the host mirror under the reference's own CLI (build container only, no GPU):
 
   run A  the UNMODIFIED `svim alignment` script (reference tree, pysam/edlib/spoa shims) on a BAM + FASTA written to disk;
-  run B  the same script after `svim_b200.patch.install()` — COLLECT, CLUSTER, the cut&paste search and GENOTYPE rebound to
-         svim_b200's host mirror — with the CUDA context replaced by the oracle-backed stand-in of tests/test_host_units.py
+  run B  the same script after `svim_b200.patch.install()` — COLLECT, CLUSTER, the cut&paste search, the candidate clustering
+         and GENOTYPE rebound to svim_b200's host mirror — with the CUDA context replaced by the oracle-backed stand-in of tests/test_host_units.py
          (the CUDA entries themselves are compared with the same goldens in the -m gpu tests).
 
 Everything downstream of the rebound functions (COMBINE, candidate clustering, VCF / BED writers) is the reference's code and
@@ -25,6 +25,7 @@ sys.path.insert(0, os.path.join(refenv.ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 SCRIPT = os.path.join(refenv.REF, "svim", "svim")
+CALLS = {}          # how often run B went through each rebound entry (the check is void if they are not reached)
 
 
 def run_cli(argv):
@@ -95,17 +96,13 @@ def main():
             runtime.context = lambda device=None: fake
             try:
                 patch.install()
-                rcg.partition_and_cluster_candidates = saved[4]       # needs the CUDA clustering entry: stays the reference's here
-                cm = sys.modules.get("svim.SVIM_COMBINE")
-                if cm is not None:
-                    cm.partition_and_cluster_candidates = saved[4]
                 run_cli(argv(wb))
             finally:
                 runtime.context = real_context
                 rc.analyze_alignment_file_coordsorted, rcl.cluster_sv_signatures, rg.genotype, rm.flag_cutpaste_candidates, rcg.partition_and_cluster_candidates = saved
                 cm = sys.modules.get("svim.SVIM_COMBINE")
                 if cm is not None:
-                    cm.flag_cutpaste_candidates = saved[3]
+                    cm.flag_cutpaste_candidates = saved[3]; cm.partition_and_cluster_candidates = saved[4]
             n, diffs = compare_dirs(wa, wb)
             if diffs and os.environ.get("SVIM_CHECK_KEEP"):
                 import shutil
@@ -114,7 +111,8 @@ def main():
             vcf = open(os.path.join(wa, "variants.vcf")).read().count("\n")
             results.append((name, extra, n, vcf, diffs))
             print("%s %s: %d output files compared, variants.vcf %d lines -> %s" % (name, " ".join(extra), n, vcf, "IDENTICAL" if not diffs else "DIFFER: %s" % diffs), flush=True)
-    return 1 if any(r[4] for r in results) else 0
+    print("rebound entries reached in the B runs:", CALLS)
+    return 1 if any(r[4] for r in results) or not all(CALLS.get(k) for k in ("genotype", "closest_source", "candidate_clustering")) else 0
 
 
 def add_genotype_and_cutpaste(fake, batch):
@@ -124,6 +122,7 @@ def add_genotype_and_cutpaste(fake, batch):
     ends = orc.record_reference_ends(batch)
 
     def genotype(type_code, gp, cands, variant_ids, contig_lengths):
+        CALLS["genotype"] = CALLS.get("genotype", 0) + 1
         t = _lib.TYPE_NAMES[type_code]
         res = np.zeros(len(cands), dtype=_lib.GENO_RESULT_DTYPE)
         p = orc.GenoParams(min_mapq=gp.min_mapq, minimum_score=-10**9, minimum_depth=gp.minimum_depth,
@@ -138,9 +137,44 @@ def add_genotype_and_cutpaste(fake, batch):
         return res
 
     def closest_source(a_s, a_e, b_s, b_e, N):
+        CALLS["closest_source"] = CALLS.get("closest_source", 0) + 1
         got = orc.flag_cutpaste(list(zip(a_s, a_e)), list(zip(b_s, b_e)), N, 0.0)
         return np.array([g[0] for g in got], dtype=np.int64), np.array([g[1] for g in got], dtype=np.float64)
 
+    # candidate clustering twin (svimgpu_set_signatures with SVIM_DUP_INT_CAND records + svimgpu_cluster), answered by the oracle
+    state = {"cand": None}
+    collected_cluster = fake.cluster
+
+    def set_signatures(cs, blob=None, rank_to_tid=None):
+        state["cand"] = np.array(cs, copy=True)
+
+    def cluster(sharded=False):
+        cs = state["cand"]
+        if cs is None:
+            return collected_cluster(sharded)
+        state["cand"] = None
+        CALLS["candidate_clustering"] = CALLS.get("candidate_clustering", 0) + 1
+        dest_end = cs["seq_off"].view(np.float64)
+        cands = [orc.Cand(int(r["contig_a"]), int(r["start"]), int(r["end"]), int(r["contig_b"]), int(r["dpos"]), int(dest_end[k]), [k], 1.0, None, None)
+                 for k, r in enumerate(cs)]
+        merged = orc.partition_and_cluster_candidates(cands, fake.p)
+        rows, mem = [], []
+        for c in merged:
+            rows.append((c.start, c.end, c.dest_start, c.dest_end, 0.0, float("nan"), float("nan"), len(mem), len(c.members), 5, 0, 0, 0, 0))
+            mem += c.members
+        st = _lib.ClusterStats()
+        st.n_clusters_total, st.n_members = len(rows), len(mem)
+        return st, np.array(rows, dtype=_lib.CLUSTER_DTYPE) if rows else np.zeros(0, _lib.CLUSTER_DTYPE), np.array(mem, dtype=np.uint32)
+
+    use_collected = fake.use_collected
+
+    def use(which=0):
+        state["cand"] = None
+        use_collected(which)
+
+    fake.set_signatures = set_signatures
+    fake.cluster = cluster
+    fake.use_collected = use
     fake.genotype = genotype
     fake.closest_source = closest_source
     fake.upload = lambda b: None
