@@ -102,3 +102,15 @@ long long hc_myers_banded(const uint8_t* pat, long long m, const uint8_t* txt, l
 int hc_myers_band_bin(long long m, long long n, int num, int add) { return myers_band_bin(m, n, num, add); }
 long long hc_myers_band_k(long long m, long long n, int num, int add) { return myers_band_k(m, n, num, add); }
 }
+
+// ---- groundwork for the on-GPU BAM decoder (csrc_next/bgzf_core.cuh): raw DEFLATE of a BGZF payload, record-start search ----
+#include "../../svim_b200/csrc_next/bgzf_core.cuh"
+extern "C" {
+int hc_bgzf_inflate(const uint8_t* src, unsigned clen, uint8_t* dst, unsigned ulen) {
+    std::vector<uint32_t> tab(BGZF_TABLE_WORDS);
+    return bgzf_inflate_block(src, clen, dst, ulen, tab.data());
+}
+unsigned long long hc_bam_find_record_start(const uint8_t* data, unsigned long long size, unsigned long long from, int n_ref, int depth) {
+    return bam_find_record_start(data, size, from, n_ref, depth);
+}
+}

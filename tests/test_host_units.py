@@ -116,7 +116,8 @@ def test_fasta_fetch_clamps(tmp_path):
 def hc():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh")]
+    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh")] + \
+           [os.path.join(ROOT, "svim_b200", "csrc_next", "bgzf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
     lib = ctypes.CDLL(so)
@@ -692,3 +693,80 @@ def test_flag_cutpaste_host_mirror_against_golden(monkeypatch):
     assert flag_cutpaste_candidates([], [], opts) == []
     with pytest.raises(IndexError):
         flag_cutpaste_candidates([Bi("c", 1, 5, "c", 9, 0)], [], opts)
+
+
+
+def test_bgzf_core_inflate_matches_zlib(hc, tmp_path):
+    """csrc_next/bgzf_core.cuh (groundwork for the on-GPU BAM decoder): the SVIM_HD raw-DEFLATE decoder against zlib on synthetic
+    streams of every block type and on every BGZF block of a BAM file; malformed input must come back as an error code."""
+    import zlib
+    hc.hc_bgzf_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
+    rng = np.random.default_rng(4)
+
+    def deflate_raw(data, level, strategy):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+        return c.compress(data) + c.flush()
+
+    def inflate(comp, n):
+        out = np.full(n + 8, 0xAB, dtype=np.uint8)
+        rc = hc.hc_bgzf_inflate(comp, len(comp), out.ctypes.data, n)
+        assert (out[n:] == 0xAB).all()                  # nothing written past the declared size
+        return rc, out[:n].tobytes()
+
+    n_ok = n_rej = 0
+    for t in range(600):
+        n = int(rng.integers(0, 9)) if t % 7 == 0 else int(rng.integers(0, 65536))
+        mode = t % 6
+        if mode == 0: data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif mode == 1: data = rng.choice(np.frombuffer(b"ACGT", np.uint8), n).tobytes()
+        elif mode == 2: data = b"\xff" * n
+        elif mode == 3: data = bytes((120 if i % 7 < 3 else (i // 300) & 255) for i in range(n))
+        elif mode == 4: data = (rng.integers(0, 4, n, dtype=np.uint8) * (rng.random(n) < 0.1)).astype(np.uint8).tobytes()
+        else:
+            base = rng.integers(0, 64, min(n, 33000), dtype=np.uint8).tobytes(); data = (base * 3)[:n]          # far matches (distance ~ 32 k)
+        level = int(rng.integers(0, 10))
+        strategy = zlib.Z_FIXED if t % 11 == 0 else zlib.Z_HUFFMAN_ONLY if t % 13 == 0 else zlib.Z_RLE if t % 17 == 0 else zlib.Z_DEFAULT_STRATEGY
+        comp = deflate_raw(data, level, strategy)
+        rc, got = inflate(comp, len(data))
+        assert rc == 0 and got == data, (t, n, level, strategy, rc)
+        n_ok += 1
+        if n:
+            assert inflate(comp, len(data) - 1)[0] != 0 and inflate(comp, len(data) + 3)[0] != 0       # wrong ISIZE
+        if len(comp) > 4:
+            assert inflate(comp[: len(comp) - 1 - int(rng.integers(0, min(len(comp) - 1, 16)))], len(data))[0] != 0 or n == 0      # truncated
+            for _ in range(2):                                                                            # bit flips: never crash
+                bad = bytearray(comp); bad[int(rng.integers(0, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+                n_rej += inflate(bytes(bad), len(data))[0] != 0
+    assert n_ok == 600 and n_rej > 300
+    # every BGZF block of a BAM written by the native writer
+    from svim_b200 import synth
+    names, L = ["chr1", "chr2"], [90_000, 50_000]
+    svs, al = synth.plant_svs(L, 5, spacing=6000)
+    batch = synth.generate(names, L, 400, 5, svs, al, len_mean=4000, len_sd=900, len_min=800, len_max=9000)
+    p = str(tmp_path / "x.bam")
+    sio.write_bam_native(p, batch, threads=2)
+    raw = open(p, "rb").read()
+    o = 0; stream = bytearray(); n_blocks = 0
+    while o + 18 <= len(raw):
+        xlen = int.from_bytes(raw[o + 10:o + 12], "little"); bsize = int.from_bytes(raw[o + 16:o + 18], "little") + 1
+        isize = int.from_bytes(raw[o + bsize - 4:o + bsize], "little")
+        payload = raw[o + 12 + xlen:o + bsize - 8]
+        rc, got = inflate(payload, isize)
+        assert rc == 0 and got == zlib.decompress(payload, -15), n_blocks
+        stream += got; o += bsize; n_blocks += 1
+    assert n_blocks > 20
+    # record starts: from arbitrary offsets the search must land on the next true record start
+    hc.hc_bam_find_record_start.restype = ctypes.c_ulonglong
+    hc.hc_bam_find_record_start.argtypes = [ctypes.c_char_p, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int]
+    data = bytes(stream)
+    l_text = int.from_bytes(data[4:8], "little"); q = 8 + l_text; n_ref = int.from_bytes(data[q:q + 4], "little"); q += 4
+    for _ in range(n_ref):
+        ln = int.from_bytes(data[q:q + 4], "little"); q += 4 + ln + 4
+    starts = []
+    while q + 4 <= len(data):
+        starts.append(q); q += 4 + int.from_bytes(data[q:q + 4], "little")
+    assert len(starts) == batch.n
+    starts_a = np.array(starts)
+    for frm in [starts[0], starts[0] + 1, starts[5] - 3] + rng.integers(starts[0], starts[-3], 300).tolist():
+        want = int(starts_a[np.searchsorted(starts_a, frm)])
+        assert hc.hc_bam_find_record_start(data, len(data), frm, n_ref, 3) == want, frm
