@@ -272,3 +272,18 @@ SVIM_HD uint64_t bam_find_record_start(const uint8_t* data, uint64_t size, uint6
     }
     return size;
 }
+
+// Hop over block_size fields from a record start until the first record that starts at or after `limit` (the next chunk's
+// territory); counts the records that start before `limit`.  Returns that offset, `size` at the end of the stream, or
+// UINT64_MAX when a record is cut by the end of the stream (truncated file).
+SVIM_HD uint64_t bam_chain(const uint8_t* data, uint64_t size, uint64_t start, uint64_t limit, uint32_t* n_records) {
+    uint64_t o = start; uint32_t n = 0;
+    while (o < limit && o < size) {
+        if (o + 4 > size) return ~0ull;
+        uint32_t bs; memcpy(&bs, data + o, 4);
+        if (bs < 32 || o + 4ull + bs > size) return ~0ull;
+        o += 4ull + bs; ++n;
+    }
+    *n_records = n;
+    return o;
+}

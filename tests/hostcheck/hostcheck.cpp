@@ -114,3 +114,32 @@ unsigned long long hc_bam_find_record_start(const uint8_t* data, unsigned long l
     return bam_find_record_start(data, size, from, n_ref, depth);
 }
 }
+
+// The parallel record-boundary scheme of DESIGN.md §11, replayed serially: every chunk finds a speculative record start on its
+// own, chains to the next chunk's territory, and the scheme is accepted iff every chain lands on the next chunk's start.
+// Returns the total number of records, -1 if some chain did not land (the GPU path then repairs from that chunk serially),
+// -2 on a truncated stream.  starts_out (optional) receives each chunk's start.
+extern "C" long long hc_bam_chunked_starts(const uint8_t* data, unsigned long long size, unsigned long long first_record, unsigned long long chunk,
+                                           int n_ref, int depth, unsigned long long* starts_out) {
+    const unsigned long long n_chunks = (size - first_record + chunk - 1) / chunk;
+    std::vector<unsigned long long> st(n_chunks + 1), en(n_chunks);
+    std::vector<uint32_t> cnt(n_chunks);
+    for (unsigned long long c = 0; c < n_chunks; ++c)          // independent per chunk (one thread each on the GPU)
+        st[c] = c == 0 ? first_record : bam_find_record_start(data, size, first_record + c * chunk, n_ref, depth);
+    st[n_chunks] = size;
+    for (unsigned long long c = 0; c < n_chunks; ++c) {        // independent per chunk
+        const unsigned long long limit = c + 1 < n_chunks ? first_record + (c + 1) * chunk : size;
+        cnt[c] = 0;
+        en[c] = st[c] >= limit ? st[c] : bam_chain(data, size, st[c], limit, &cnt[c]);
+        if (en[c] == ~0ull) return -2;
+    }
+    // chunk 0 starts on a true record start, and a chain that starts on a true start ends on the first true start of the next
+    // territory: by induction every chunk is right iff each chain lands on the next chunk's own guess
+    long long total = 0;
+    for (unsigned long long c = 0; c < n_chunks; ++c) {
+        if (en[c] != st[c + 1]) return -1;
+        total += cnt[c];
+        if (starts_out) starts_out[c] = st[c];
+    }
+    return total;
+}

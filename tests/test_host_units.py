@@ -770,3 +770,13 @@ def test_bgzf_core_inflate_matches_zlib(hc, tmp_path):
     for frm in [starts[0], starts[0] + 1, starts[5] - 3] + rng.integers(starts[0], starts[-3], 300).tolist():
         want = int(starts_a[np.searchsorted(starts_a, frm)])
         assert hc.hc_bam_find_record_start(data, len(data), frm, n_ref, 3) == want, frm
+    # the chunk-parallel boundary scheme (speculative start per chunk, chain, "lands on the next guess" check), several chunk sizes
+    hc.hc_bam_chunked_starts.restype = ctypes.c_longlong
+    hc.hc_bam_chunked_starts.argtypes = [ctypes.c_char_p, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    for chunk in (1500, 4096, 65536, 1 << 20):
+        n_chunks = (len(data) - starts[0] + chunk - 1) // chunk
+        got_starts = np.zeros(n_chunks, dtype=np.uint64)
+        assert hc.hc_bam_chunked_starts(data, len(data), starts[0], chunk, n_ref, 3, got_starts.ctypes.data) == batch.n, chunk
+        want = [int(starts_a[np.searchsorted(starts_a, starts[0] + c * chunk)]) if starts[0] + c * chunk <= starts[-1] else len(data) for c in range(n_chunks)]
+        assert got_starts.tolist() == want, chunk
+    assert hc.hc_bam_chunked_starts(data[:-7], len(data) - 7, starts[0], 4096, n_ref, 3, None) == -2          # truncated stream
