@@ -103,6 +103,7 @@ struct Handle {
     bamio_info info;
     int threads = 1;
     bool header_done = false;
+    size_t header_bytes = 0;          // BAM header length in the inflated stream = offset of the first alignment record
     ~Handle() { if (file && fsz) munmap((void*)file, fsz); if (fd >= 0) close(fd); }
 };
 
@@ -195,7 +196,7 @@ int64_t parse_header(Handle* h, const uint8_t* d, size_t n) {
         }
     }
     h->contigs.swap(names); h->contig_len.swap(lens);
-    h->header_done = true;
+    h->header_done = true; h->header_bytes = p;
     return (int64_t)p;
 }
 
@@ -459,6 +460,20 @@ int bamio_fill(void* hh, bamio_out* out) {
         }
     });
     tr.mark("row arrays");
+    return 0;
+}
+
+// Layout for the experimental on-GPU decoder (csrc_next/bamgpu.cu): the mapped file, the BGZF block table
+// {payload offset, inflated offset, payload bytes, inflated bytes} and where the alignment records start in the inflated stream.
+struct bamio_block { uint64_t coff, uoff; uint32_t clen, ulen; };
+int bamio_layout(void* hh, const uint8_t** file, int64_t* file_bytes, int64_t* n_blocks, int64_t* first_record) {
+    Handle* h = (Handle*)hh;
+    *file = h->file; *file_bytes = (int64_t)h->fsz; *n_blocks = (int64_t)h->blocks.size(); *first_record = (int64_t)h->header_bytes;
+    return 0;
+}
+int bamio_blocks(void* hh, bamio_block* out) {
+    Handle* h = (Handle*)hh;
+    for (size_t i = 0; i < h->blocks.size(); ++i) out[i] = {h->blocks[i].coff, h->blocks[i].uoff, (uint32_t)h->blocks[i].clen, (uint32_t)h->blocks[i].ulen};
     return 0;
 }
 

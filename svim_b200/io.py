@@ -160,6 +160,8 @@ def _bamio_lib():
         lib.bamio_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         lib.bamio_close.argtypes = [C.c_void_p]
         lib.bamio_close.restype = None
+        lib.bamio_layout.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        lib.bamio_blocks.argtypes = [C.c_void_p, C.c_void_p]
         _bamio = lib
     return _bamio
 
@@ -217,6 +219,102 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
         lib.bamio_close(h)
     return AlignmentBatch(names, lengths[:inf.n_contigs], arrays, cigar[:inf.cigar_words], seq[:inf.seq_bytes], sa[:inf.sa_bytes], qnames,
                           so.value.decode() or "unknown")
+
+
+BGZF_BLOCK_DTYPE = np.dtype([("coff", "<u8"), ("uoff", "<u8"), ("clen", "<u4"), ("ulen", "<u4")])
+_BAMGPU_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc_next", "bamgpu.cu")
+_BAMGPU_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsvimbamgpu.so")
+_bamgpu = None
+
+
+def build_bamgpu(force: bool = False) -> str:
+    """nvcc build of the EXPERIMENTAL on-GPU BAM decoder (csrc_next/bamgpu.cu) into its own library."""
+    import subprocess
+    deps = [_BAMGPU_SRC, os.path.join(os.path.dirname(_BAMGPU_SRC), "bgzf_core.cuh")]
+    if force or not os.path.exists(_BAMGPU_SO) or any(os.path.getmtime(_BAMGPU_SO) < os.path.getmtime(d) for d in deps):
+        from .build import nvcc_path
+        subprocess.check_call([nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
+                               "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static",
+                               "-o", _BAMGPU_SO, _BAMGPU_SRC])
+    return _BAMGPU_SO
+
+
+def bgzf_layout(path: str):
+    """(block table as BGZF_BLOCK_DTYPE[], offset of the first alignment record in the inflated stream, contig names, contig
+    lengths, sort order) from the host-side index pass of csrc_host/bamio.cpp."""
+    import ctypes as C
+    lib = _bamio_lib()
+    inf = (C.c_int64 * 10)()
+    err = C.create_string_buffer(256)
+    h = lib.bamio_open(path.encode(), 1, inf, err, 256)
+    if not h:
+        raise ValueError("bgzf_layout(%s): %s" % (path, err.value.decode()))
+    try:
+        fp, fb, nb, first = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int64()
+        lib.bamio_layout(h, C.byref(fp), C.byref(fb), C.byref(nb), C.byref(first))
+        blocks = np.zeros(nb.value, dtype=BGZF_BLOCK_DTYPE)
+        if nb.value:
+            lib.bamio_blocks(h, blocks.ctypes.data)
+        n_contigs = C.cast(inf, C.POINTER(C.c_int32))[16]          # bamio_info: 8 int64, then n_contigs, sorted_coordinate
+        names_buf = C.create_string_buffer(max(1, 256 * n_contigs + 64))
+        lengths = np.zeros(max(1, n_contigs), dtype=np.int64)
+        so = C.create_string_buffer(16)
+        lib.bamio_header(h, names_buf, len(names_buf), lengths.ctypes.data, so)
+        names = [x.decode("ascii") for x in names_buf.raw.split(b"\x00")[:n_contigs]]
+        return blocks, first.value, names, lengths[:n_contigs], so.value.decode() or "unknown"
+    finally:
+        lib.bamio_close(h)
+
+
+def read_bam_gpu(path: str, device: int = 0, stats: dict = None) -> AlignmentBatch:
+    """EXPERIMENTAL: BAM -> AlignmentBatch with the BGZF blocks inflated and the records parsed on
+    the GPU (csrc_next/bamgpu.cu).  Same result as read_bam_native; raises when the GPU path declines (then use the host decoder)."""
+    import ctypes as C
+    global _bamgpu
+    if _bamgpu is None:
+        lib = C.CDLL(build_bamgpu())
+        lib.bamgpu_decode.restype = C.c_void_p
+        lib.bamgpu_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        lib.bamgpu_fetch.argtypes = [C.c_void_p] * 16
+        lib.bamgpu_error.restype = C.c_char_p
+        lib.bamgpu_error.argtypes = [C.c_void_p]
+        lib.bamgpu_free.argtypes = [C.c_void_p]
+        lib.bamgpu_free.restype = None
+        _bamgpu = lib
+    lib = _bamgpu
+    blocks, first, names, lengths, so = bgzf_layout(path)
+    raw = np.fromfile(path, dtype=np.uint8)
+
+    class Info(C.Structure):
+        _fields_ = [(n, C.c_int64) for n in ("n_records", "cigar_words", "seq_bytes", "sa_bytes", "names_bytes")] + \
+                   [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_parse")]
+    inf = Info(); rc = C.c_int()
+    h = lib.bamgpu_decode(raw.ctypes.data, raw.size, blocks.ctypes.data, len(blocks), first, len(names), device, C.byref(inf), C.byref(rc))
+    try:
+        if rc.value != 0:
+            raise ValueError("read_bam_gpu(%s): rc %d: %s" % (path, rc.value, lib.bamgpu_error(h).decode()))
+        n = inf.n_records
+        arrays = {name: np.empty(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
+        name_off = np.empty(n, dtype=np.uint64)
+        cigar = np.empty(inf.cigar_words, dtype=np.uint32); seq = np.empty(inf.seq_bytes, dtype=np.uint8)
+        sa = np.empty(max(1, inf.sa_bytes), dtype=np.uint8); nblob = np.empty(max(1, inf.names_bytes), dtype=np.uint8)
+        p = lambda a: a.ctypes.data
+        if lib.bamgpu_fetch(h, p(arrays["tid"]), p(arrays["pos"]), p(arrays["flag"]), p(arrays["mapq"]), p(arrays["n_cigar"]), p(arrays["cigar_off"]),
+                            p(arrays["l_seq"]), p(arrays["seq_off"]), p(arrays["sa_off"]), p(arrays["sa_len"]), p(name_off), p(cigar), p(seq), p(sa), p(nblob)) != 0:
+            raise ValueError("read_bam_gpu(%s): %s" % (path, lib.bamgpu_error(h).decode()))
+        if stats is not None:
+            stats.update(ms_h2d=inf.ms_h2d, ms_inflate=inf.ms_inflate, ms_parse=inf.ms_parse)
+    finally:
+        lib.bamgpu_free(h)
+    # read-name ids on the host (first version): dense ids in order of first appearance, like the host decoder
+    parts = nblob[:inf.names_bytes].tobytes().split(b"\x00")[:n]
+    ids = {}
+    qid = np.empty(n, dtype=np.uint32)
+    for k, nm in enumerate(parts):
+        qid[k] = ids.setdefault(nm, len(ids))
+    arrays["qname_id"] = qid
+    qnames = [x.decode("ascii") for x in ids]
+    return AlignmentBatch(names, lengths, arrays, cigar, seq, sa[:inf.sa_bytes], qnames, so)
 
 
 def write_bam_native(path: str, batch: AlignmentBatch, level: int = 1, threads: int = 0):

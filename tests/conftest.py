@@ -25,6 +25,7 @@ def querysort_order(batch):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "gpu_next: experimental GPU code that has not run on a GPU yet; only with SVIM_RUN_NEXT=1")
 
 
 def load_golden(name):

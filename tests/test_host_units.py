@@ -780,3 +780,23 @@ def test_bgzf_core_inflate_matches_zlib(hc, tmp_path):
         want = [int(starts_a[np.searchsorted(starts_a, starts[0] + c * chunk)]) if starts[0] + c * chunk <= starts[-1] else len(data) for c in range(n_chunks)]
         assert got_starts.tolist() == want, chunk
     assert hc.hc_bam_chunked_starts(data[:-7], len(data) - 7, starts[0], 4096, n_ref, 3, None) == -2          # truncated stream
+
+
+def test_bgzf_layout_for_the_gpu_decoder(tmp_path):
+    # svim_b200.io.bgzf_layout: block table + first-record offset handed to csrc_next/bamgpu.cu, checked with zlib on the CPU
+    import zlib
+    from svim_b200 import synth
+    names, L = ["chr1", "chr2"], [90_000, 50_000]
+    svs, al = synth.plant_svs(L, 5, spacing=6000)
+    batch = synth.generate(names, L, 300, 5, svs, al, len_mean=4000, len_sd=900, len_min=800, len_max=9000)
+    p = str(tmp_path / "x.bam")
+    sio.write_bam_native(p, batch, threads=2)
+    blocks, first, cn, cl, so = sio.bgzf_layout(p)
+    assert cn == names and cl.tolist() == L and so == "coordinate"
+    raw = open(p, "rb").read()
+    stream = b"".join(zlib.decompress(raw[int(b["coff"]):int(b["coff"]) + int(b["clen"])], -15) for b in blocks)
+    assert len(stream) == int(blocks["ulen"].sum()) and (np.cumsum(blocks["ulen"]) - blocks["ulen"] == blocks["uoff"]).all()
+    n, q = 0, first
+    while q + 4 <= len(stream):
+        q += 4 + int.from_bytes(stream[q:q + 4], "little"); n += 1
+    assert n == batch.n and q == len(stream)
