@@ -81,6 +81,8 @@ struct Row {
     int32_t tid, pos; uint16_t flag; uint8_t mapq, l_rn; uint32_t n_cigar; int32_t l_seq; uint32_t sa_len;
     uint64_t cigar_off, seq_off, sa_off;
     uint32_t src_off, sa_src;          // record start / SA payload inside the unit's contiguous view
+    uint32_t cig_src;                  // CIGAR words relative to the record start (core CIGAR, or the CG:B,I payload)
+    uint32_t n_cigar_core;             // operations stored in the record core (2 for a CG-tagged record): SEQ follows them
     uint32_t name_off;                 // into the unit's name arena
 };
 
@@ -118,8 +120,10 @@ void parallel_for(size_t n, int threads, F f) {
     for (auto& x : th) x.join();
 }
 
-// SA:Z payload inside the aux area -> (offset relative to record start, length), walking typed fields
-bool find_sa(const uint8_t* rec, size_t aux_begin, size_t rec_len, uint32_t& off, uint32_t& len) {
+// Walk the typed aux fields of a record: SA:Z payload -> (offset relative to record start, length); CG:B,I payload (the real
+// CIGAR of a record with more than 65535 operations, SAMv1 §4.2.2) -> (offset of its first word, number of words).
+struct AuxHits { uint32_t sa_off = 0, sa_len = 0, cg_off = 0, cg_n = 0; };
+void scan_aux(const uint8_t* rec, size_t aux_begin, size_t rec_len, AuxHits& hit) {
     size_t o = aux_begin;
     while (o + 3 <= rec_len) {
         const uint8_t t0 = rec[o], t1 = rec[o + 1], ty = rec[o + 2];
@@ -132,22 +136,22 @@ bool find_sa(const uint8_t* rec, size_t aux_begin, size_t rec_len, uint32_t& off
             case 'Z': case 'H': {
                 size_t e = o;
                 while (e < rec_len && rec[e]) ++e;
-                if (t0 == 'S' && t1 == 'A' && ty == 'Z') { off = (uint32_t)o; len = (uint32_t)(e - o); return true; }
+                if (t0 == 'S' && t1 == 'A' && ty == 'Z' && hit.sa_len == 0 && hit.sa_off == 0) { hit.sa_off = (uint32_t)o; hit.sa_len = (uint32_t)(e - o); }
                 o = e + 1;
                 continue;
             }
             case 'B': {
-                if (o + 5 > rec_len) return false;
+                if (o + 5 > rec_len) return;
                 const uint8_t sub = rec[o]; const uint32_t cnt = rd32(rec + o + 1);
                 size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                if (t0 == 'C' && t1 == 'G' && sub == 'I' && hit.cg_off == 0 && o + 5 + (size_t)cnt * 4 <= rec_len) { hit.cg_off = (uint32_t)(o + 5); hit.cg_n = cnt; }
                 o += 5 + (size_t)cnt * es;
                 continue;
             }
-            default: return false;
+            default: return;
         }
         o += sz;
     }
-    return false;
 }
 
 // One BGZF payload (raw DEFLATE, exact output size known from ISIZE).  The z_stream is per thread and reset per block:
@@ -365,10 +369,16 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
                         w.n_cigar = rd16(r + 12); w.flag = rd16(r + 14); w.l_seq = (int32_t)rd32(r + 16);
                         const size_t aux = 32 + (size_t)w.l_rn + 4 * (size_t)w.n_cigar + (size_t)(w.l_seq + 1) / 2 + (size_t)w.l_seq;
                         if (w.l_seq < 0 || aux > bs) { fail_msg = "corrupt record"; failed = 1; break; }
-                        uint32_t so = 0, sl = 0;
-                        if (aux < bs) find_sa(r, aux, bs, so, sl);
+                        AuxHits hit;
+                        if (aux < bs) scan_aux(r, aux, bs, hit);
+                        const uint32_t so = hit.sa_off, sl = hit.sa_len;
                         w.sa_len = sl; w.sa_src = 0; w.src_off = (uint32_t)(p + 4);
                         if (sl) un.sa.append((const char*)r + so, sl);
+                        w.n_cigar_core = w.n_cigar; w.cig_src = 32u + w.l_rn;
+                        if (hit.cg_n && w.n_cigar > 0 && w.tid >= 0 && w.pos >= 0) {          // htslib sam.c bam_tag2cigar
+                            const uint32_t c0 = rd32(r + 32 + w.l_rn);
+                            if ((c0 & 15u) == 4u && (int64_t)(c0 >> 4) == (int64_t)w.l_seq) { w.n_cigar = hit.cg_n; w.cig_src = hit.cg_off; }
+                        }
                         w.cigar_off = cig_words; w.seq_off = seq_bytes; w.sa_off = sa_bytes;
                         cig_words += (w.n_cigar + 3u) & ~3u; seq_bytes += (uint64_t)(w.l_seq + 1) / 2; sa_bytes += sl;
                         w.name_off = (uint32_t)un.names.size();
@@ -386,11 +396,10 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
             // ---- fill: this unit's records from the warm buffer into the caller's blobs ----
             for (const Row& w : un.rows) {
                 const uint8_t* r = d + w.src_off;
-                const uint8_t* cg = r + 32 + w.l_rn;
                 uint32_t* dst = cigar + w.cigar_off;
-                memcpy(dst, cg, 4 * (size_t)w.n_cigar);
+                memcpy(dst, r + w.cig_src, 4 * (size_t)w.n_cigar);
                 for (uint32_t k = w.n_cigar; k < ((w.n_cigar + 3u) & ~3u); ++k) dst[k] = 0;
-                memcpy(seq + w.seq_off, cg + 4 * (size_t)w.n_cigar, (size_t)(w.l_seq + 1) / 2);
+                memcpy(seq + w.seq_off, r + 32 + w.l_rn + 4 * (size_t)w.n_cigar_core, (size_t)(w.l_seq + 1) / 2);
             }
             t_fill += since(t0);
         }
@@ -526,7 +535,9 @@ int bamio_write(const char* path, const bamio_in* in, int level, int n_threads) 
     };
     for (int64_t i = 0; i < n; ++i) {
         roff[i] = o;
-        o += 4 + 32 + name_len(i) + 1 + 4 * (size_t)in->n_cigar[i] + (size_t)(in->l_seq[i] + 1) / 2 + (size_t)in->l_seq[i] + (in->sa_len[i] ? 4 + in->sa_len[i] : 0);
+        const size_t nc_all = in->n_cigar[i];
+        const size_t cig_bytes = nc_all <= 65535 ? 4 * nc_all : 8 + 8 + 4 * nc_all;      // placeholder kSmN in the core + CG:B,I tag
+        o += 4 + 32 + name_len(i) + 1 + cig_bytes + (size_t)(in->l_seq[i] + 1) / 2 + (size_t)in->l_seq[i] + (in->sa_len[i] ? 4 + in->sa_len[i] : 0);
     }
     roff[n] = o;
     raw.resize(o);
@@ -548,15 +559,20 @@ int bamio_write(const char* path, const bamio_in* in, int level, int n_threads) 
             const uint16_t bin = (uint16_t)reg2bin(b0, b0 + (rlen ? rlen : 1));
             int32_t f32[2] = {in->tid[i], pos}; memcpy(r, f32, 8);
             r[8] = (uint8_t)(nl + 1); r[9] = in->mapq[i]; memcpy(r + 10, &bin, 2);
-            const uint16_t nc16 = (uint16_t)nc; memcpy(r + 12, &nc16, 2); memcpy(r + 14, &in->flag[i], 2);
+            const bool long_cigar = nc > 65535;            // SAMv1 §4.2.2: the real CIGAR goes to CG:B,I, the core keeps <l_seq>S<rlen>N
+            const uint16_t nc16 = long_cigar ? (uint16_t)2 : (uint16_t)nc; memcpy(r + 12, &nc16, 2); memcpy(r + 14, &in->flag[i], 2);
             memcpy(r + 16, &ls, 4);
             const int32_t m1 = -1, z = 0; memcpy(r + 20, &m1, 4); memcpy(r + 24, &m1, 4); memcpy(r + 28, &z, 4);
             uint8_t* q = r + 32;
             memcpy(q, nm, nl); q[nl] = 0; q += nl + 1;
-            memcpy(q, cg, 4 * (size_t)nc); q += 4 * (size_t)nc;
+            if (long_cigar) {
+                const uint32_t core[2] = {((uint32_t)ls << 4) | 4u, ((uint32_t)rlen << 4) | 3u};
+                memcpy(q, core, 8); q += 8;
+            } else { memcpy(q, cg, 4 * (size_t)nc); q += 4 * (size_t)nc; }
             memcpy(q, in->seq + in->seq_off[i], (size_t)(ls + 1) / 2); q += (size_t)(ls + 1) / 2;
             memset(q, 0xff, (size_t)ls); q += ls;
-            if (in->sa_len[i]) { q[0] = 'S'; q[1] = 'A'; q[2] = 'Z'; memcpy(q + 3, in->sa + in->sa_off[i], in->sa_len[i]); q[3 + in->sa_len[i]] = 0; }
+            if (in->sa_len[i]) { q[0] = 'S'; q[1] = 'A'; q[2] = 'Z'; memcpy(q + 3, in->sa + in->sa_off[i], in->sa_len[i]); q[3 + in->sa_len[i]] = 0; q += 4 + in->sa_len[i]; }
+            if (long_cigar) { q[0] = 'C'; q[1] = 'G'; q[2] = 'B'; q[3] = 'I'; memcpy(q + 4, &nc, 4); memcpy(q + 8, cg, 4 * (size_t)nc); }
         }
     });
     // BGZF: fixed 0xff00-byte payloads, compressed in parallel

@@ -11,6 +11,7 @@
 //   k_rows         one thread per record: fixed fields, SA tag lookup, blob sizes;  exclusive scans -> blob offsets
 //   k_fill         one warp per record: CIGAR words (padded to 4), packed SEQ, SA text, read name -> blobs
 // Everything heavy is a thin wrapper over the SVIM_HD functions of bgzf_core.cuh, which the CPU tests replay.
+// Not handled yet (the host decoder does): CG:B,I tags of records with more than 65535 CIGAR operations.
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <stdio.h>

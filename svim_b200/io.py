@@ -111,11 +111,12 @@ def _bgzf_inflate_all(path: str) -> bytes:
         return b"".join(_bgzf_blocks(fh))
 
 
-def _aux_find_sa(aux: bytes) -> Optional[bytes]:
-    """Walk BAM aux fields, return the SA:Z payload (without NUL) if present."""
+def _aux_find(aux: bytes):
+    """Walk BAM aux fields: (SA:Z payload without NUL or None, CG:B,I payload as uint32 array or None)."""
     o, n = 0, len(aux)
     sizes = {ord("A"): 1, ord("c"): 1, ord("C"): 1, ord("s"): 2, ord("S"): 2,
              ord("i"): 4, ord("I"): 4, ord("f"): 4}
+    sa = cg = None
     while o + 3 <= n:
         tag, typ = aux[o:o + 2], aux[o + 2]
         o += 3
@@ -123,15 +124,27 @@ def _aux_find_sa(aux: bytes) -> Optional[bytes]:
             o += sizes[typ]
         elif typ in (ord("Z"), ord("H")):
             e = aux.index(b"\x00", o)
-            if tag == b"SA" and typ == ord("Z"):
-                return aux[o:e]
+            if tag == b"SA" and typ == ord("Z") and sa is None:
+                sa = aux[o:e]
             o = e + 1
         elif typ == ord("B"):
             sub = aux[o]; cnt = struct.unpack("<I", aux[o + 1:o + 5])[0]
+            if tag == b"CG" and sub == ord("I") and cg is None:
+                cg = np.frombuffer(aux, dtype="<u4", count=cnt, offset=o + 5).copy()
             o += 5 + cnt * sizes[sub]
         else:
             raise ValueError("bad aux type %r" % typ)
-    return None
+    return sa, cg
+
+
+def _aux_find_sa(aux: bytes) -> Optional[bytes]:
+    return _aux_find(aux)[0]
+
+
+def _long_cigar_core(l_seq: int, rlen: int) -> np.ndarray:
+    """SAMv1 §4.2.2: a CIGAR of more than 65535 operations is stored in the CG:B,I tag and the record carries the
+    placeholder `<l_seq>S<reference length>N` (what htslib writes and, on reading, replaces by the tag: sam.c bam_tag2cigar)."""
+    return np.array([(l_seq << 4) | 4, (rlen << 4) | 3], dtype="<u4")
 
 
 # ---- native multi-threaded reader (csrc_host/bamio.cpp) -----------------------------------------------------
@@ -381,7 +394,9 @@ def read_bam_python(path: str) -> AlignmentBatch:
         nb = (l_seq + 1) // 2
         packed = np.frombuffer(rec, dtype=np.uint8, count=nb, offset=p).copy(); p += nb
         p += l_seq  # qual
-        sa = _aux_find_sa(rec[p:])
+        sa, cg = _aux_find(rec[p:])
+        if cg is not None and n_cig > 0 and tid >= 0 and pos >= 0 and (int(cigar[0]) & 15) == 4 and (int(cigar[0]) >> 4) == l_seq:
+            cigar = cg                          # the real CIGAR of a record with more than 65535 operations (htslib bam_tag2cigar)
         b.add(qname, flag, tid, pos, mapq, cigar, None, sa.decode("ascii") if sa else None,
               packed_seq=packed, l_seq=l_seq)
     return b.finish()
@@ -416,12 +431,15 @@ def write_bam(path: str, batch: AlignmentBatch, level: int = 1):
         pos = int(batch.pos[i])
         qn = batch.qname(int(batch.qname_id[i])).encode("ascii") + b"\x00"
         l_seq = int(batch.l_seq[i]); so = int(batch.seq_off[i])
+        core = cig if nc <= 65535 else _long_cigar_core(l_seq, rlen)
         rec = struct.pack("<iiBBHHHiiii", int(batch.tid[i]), pos, len(qn), int(batch.mapq[i]),
-                          _reg2bin(max(pos, 0), max(pos, 0) + max(rlen, 1)), nc, int(batch.flag[i]), l_seq, -1, -1, 0)
-        rec += qn + cig.astype("<u4").tobytes() + batch.seq[so:so + (l_seq + 1) // 2].tobytes() + b"\xff" * l_seq
+                          _reg2bin(max(pos, 0), max(pos, 0) + max(rlen, 1)), len(core), int(batch.flag[i]), l_seq, -1, -1, 0)
+        rec += qn + core.astype("<u4").tobytes() + batch.seq[so:so + (l_seq + 1) // 2].tobytes() + b"\xff" * l_seq
         sa = batch.sa_tag(i)
         if sa:
             rec += b"SAZ" + sa.encode("ascii") + b"\x00"
+        if nc > 65535:
+            rec += b"CGBI" + struct.pack("<I", nc) + cig.astype("<u4").tobytes()
         out += struct.pack("<i", len(rec)) + rec
     with open(path, "wb") as fh:
         view = memoryview(out)

@@ -800,3 +800,38 @@ def test_bgzf_layout_for_the_gpu_decoder(tmp_path):
     while q + 4 <= len(stream):
         q += 4 + int.from_bytes(stream[q:q + 4], "little"); n += 1
     assert n == batch.n and q == len(stream)
+
+
+def test_bam_long_cigar_cg_tag_roundtrip(tmp_path):
+    """SAMv1 §4.2.2: more than 65535 CIGAR operations do not fit the record core; the real CIGAR travels in the CG:B,I tag behind the
+    placeholder <l_seq>S<rlen>N, and readers put it back (htslib sam.c bam_tag2cigar, so pysam — and the reference — never see the
+    placeholder).  Both writers emit it, both readers restore it."""
+    from svim_b200.records import BatchBuilder
+    rng = np.random.default_rng(3)
+    b = BatchBuilder(["c1"], [10_000_000], "coordinate")
+
+    def ops_for(n_ops):
+        ops = []
+        for k in range(n_ops):
+            ops.append((0 if k % 2 == 0 else int(rng.choice([1, 2])), int(rng.integers(1, 4))))
+        return ops
+
+    for k, n_ops in enumerate([10, 65535, 65536, 100_001, 3]):
+        ops = ops_for(n_ops)
+        qlen = sum(n for o, n in ops if o in (0, 1))
+        b.add("r%d" % k, 0, 0, 100 + k, 60, ops, "".join(rng.choice(list("ACGT"), size=qlen)), "c1,5,+,%dM,60,0;" % qlen if k % 2 else None)
+    b.add("clipped", 0, 0, 900, 60, [(4, 50)], "A" * 50, None)           # 50S with l_seq 50 but no CG tag: stays as it is
+    batch = b.finish()
+    assert int(batch.n_cigar.max()) == 100_001
+    p1, p2 = str(tmp_path / "py.bam"), str(tmp_path / "native.bam")
+    sio.write_bam(p1, batch); sio.write_bam_native(p2, batch, threads=2)
+    assert open(p1, "rb").read() == open(p2, "rb").read()
+    for reader in (sio.read_bam_python, lambda p: sio.read_bam_native(p, threads=3)):
+        got = reader(p1)
+        for name, _ in batch.FIELDS:
+            assert np.array_equal(getattr(got, name), getattr(batch, name)), name
+        for blob in ("cigar", "seq", "sa"):
+            assert np.array_equal(getattr(got, blob), getattr(batch, blob)), blob
+    # the record core really carries the placeholder (what a reader without CG support would see)
+    raw = sio._bgzf_inflate_all(p1)
+    assert raw.count(b"CGBI") == 2
