@@ -11,7 +11,7 @@
 //   k_rows         one thread per record: fixed fields, SA tag lookup, blob sizes;  exclusive scans -> blob offsets
 //   k_fill         one warp per record: CIGAR words (padded to 4), packed SEQ, SA text, read name -> blobs
 // Everything heavy is a thin wrapper over the SVIM_HD functions of bgzf_core.cuh, which the CPU tests replay.
-// Not handled yet (the host decoder does): CG:B,I tags of records with more than 65535 CIGAR operations.
+// CG:B,I tags of records with more than 65535 CIGAR operations are put back like htslib's bam_tag2cigar (k_rows / k_fill).
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <stdio.h>
@@ -68,10 +68,12 @@ struct BgRows {
     int32_t* tid; int32_t* pos; uint16_t* flag; uint8_t* mapq; uint32_t* n_cigar; int32_t* l_seq; uint32_t* sa_len;
     uint64_t* cig_words; uint64_t* seq_bytes; uint64_t* sa_bytes; uint64_t* name_bytes;      // per-record sizes -> scanned in place into offsets
     uint32_t* sa_src;                                                                       // SA payload offset inside the record
+    uint32_t* cig_src; uint32_t* n_core;                                                    // CIGAR words (core or CG:B,I payload) / ops in the core
 };
 
-// SA:Z payload inside the aux area (same walk as csrc_host/bamio.cpp::find_sa)
-__device__ bool bg_find_sa(const uint8_t* rec, uint64_t aux_begin, uint64_t rec_len, uint32_t& off, uint32_t& len) {
+// aux walk (same as csrc_host/bamio.cpp::scan_aux): SA:Z payload and CG:B,I payload, offsets relative to the record start
+struct BgAux { uint32_t sa_off, sa_len, cg_off, cg_n; };
+__device__ void bg_scan_aux(const uint8_t* rec, uint64_t aux_begin, uint64_t rec_len, BgAux& hit) {
     uint64_t o = aux_begin;
     while (o + 3 <= rec_len) {
         const uint8_t t0 = rec[o], t1 = rec[o + 1], ty = rec[o + 2];
@@ -84,22 +86,22 @@ __device__ bool bg_find_sa(const uint8_t* rec, uint64_t aux_begin, uint64_t rec_
             case 'Z': case 'H': {
                 uint64_t e = o;
                 while (e < rec_len && rec[e]) ++e;
-                if (t0 == 'S' && t1 == 'A' && ty == 'Z') { off = (uint32_t)o; len = (uint32_t)(e - o); return true; }
+                if (t0 == 'S' && t1 == 'A' && ty == 'Z' && hit.sa_off == 0) { hit.sa_off = (uint32_t)o; hit.sa_len = (uint32_t)(e - o); }
                 o = e + 1;
                 continue;
             }
             case 'B': {
-                if (o + 5 > rec_len) return false;
+                if (o + 5 > rec_len) return;
                 const uint8_t sub = rec[o]; uint32_t cnt; memcpy(&cnt, rec + o + 1, 4);
                 const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                if (t0 == 'C' && t1 == 'G' && sub == 'I' && hit.cg_off == 0 && o + 5 + (uint64_t)cnt * 4 <= rec_len) { hit.cg_off = (uint32_t)(o + 5); hit.cg_n = cnt; }
                 o += 5 + (uint64_t)cnt * es;
                 continue;
             }
-            default: return false;
+            default: return;
         }
         o += sz;
     }
-    return false;
 }
 
 __global__ void k_rows(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, int64_t n, BgRows r, uint32_t* __restrict__ bad) {
@@ -113,10 +115,17 @@ __global__ void k_rows(const uint8_t* __restrict__ data, const uint64_t* __restr
     const uint32_t l_rn = q[8];
     const uint64_t aux = 32ull + l_rn + 4ull * n_cig + ((uint64_t)(l_seq < 0 ? 0 : l_seq) + 1) / 2 + (uint64_t)(l_seq < 0 ? 0 : l_seq);
     if (l_seq < 0 || aux > bs) { atomicOr(bad, 4u); l_seq = 0; }
-    uint32_t so = 0, sl = 0;
-    if (aux < bs) bg_find_sa(q, aux, bs, so, sl);
-    r.tid[i] = tid; r.pos[i] = pos; r.flag[i] = flag; r.mapq[i] = q[9]; r.n_cigar[i] = n_cig; r.l_seq[i] = l_seq; r.sa_len[i] = sl; r.sa_src[i] = so;
-    r.cig_words[i] = (n_cig + 3u) & ~3u; r.seq_bytes[i] = ((uint64_t)l_seq + 1) / 2; r.sa_bytes[i] = sl; r.name_bytes[i] = l_rn ? l_rn : 1u;   // names keep their NUL
+    BgAux hit = {0, 0, 0, 0};
+    if (aux < bs) bg_scan_aux(q, aux, bs, hit);
+    const uint32_t so = hit.sa_off, sl = hit.sa_len;
+    uint32_t n_ops = n_cig, cig_src = 32u + l_rn;
+    if (hit.cg_n && n_cig > 0 && tid >= 0 && pos >= 0) {          // htslib sam.c bam_tag2cigar
+        uint32_t c0; memcpy(&c0, q + 32 + l_rn, 4);
+        if ((c0 & 15u) == 4u && (int64_t)(c0 >> 4) == (int64_t)l_seq) { n_ops = hit.cg_n; cig_src = hit.cg_off; }
+    }
+    r.tid[i] = tid; r.pos[i] = pos; r.flag[i] = flag; r.mapq[i] = q[9]; r.n_cigar[i] = n_ops; r.l_seq[i] = l_seq; r.sa_len[i] = sl; r.sa_src[i] = so;
+    r.cig_src[i] = cig_src; r.n_core[i] = n_cig;
+    r.cig_words[i] = (n_ops + 3u) & ~3u; r.seq_bytes[i] = ((uint64_t)l_seq + 1) / 2; r.sa_bytes[i] = sl; r.name_bytes[i] = l_rn ? l_rn : 1u;   // names keep their NUL
 }
 
 __global__ void __launch_bounds__(256) k_fill(const uint8_t* __restrict__ data, const uint64_t* __restrict__ rec_off, int64_t n, BgRows r,
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(256) k_fill(const uint8_t* __restrict__ data, 
     const uint8_t* q = data + rec_off[i] + 4;
     const uint32_t l_rn = q[8], n_cig = r.n_cigar[i];
     const int64_t l_seq = r.l_seq[i];
-    const uint8_t* cg = q + 32 + l_rn;                    // records are not 4-byte aligned in the stream: byte-wise assembly
+    const uint8_t* cg = q + r.cig_src[i];                 // records are not 4-byte aligned in the stream: byte-wise assembly
     uint32_t* cd = cigar + r.cig_words[i];
     const uint32_t padded = (n_cig + 3u) & ~3u;
     for (uint32_t k = lane; k < padded; k += 32) {
@@ -135,7 +144,7 @@ __global__ void __launch_bounds__(256) k_fill(const uint8_t* __restrict__ data, 
         if (k < n_cig) { const uint8_t* b = cg + 4ull * k; w = (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); }
         cd[k] = w;
     }
-    const uint8_t* sq = cg + 4ull * n_cig; uint8_t* sd = seq + r.seq_bytes[i];
+    const uint8_t* sq = q + 32 + l_rn + 4ull * r.n_core[i]; uint8_t* sd = seq + r.seq_bytes[i];
     for (int64_t k = lane; k < (l_seq + 1) / 2; k += 32) sd[k] = sq[k];
     const uint32_t sl = r.sa_len[i];
     if (sl) { const uint8_t* ss = q + r.sa_src[i]; uint8_t* dd = sa + r.sa_bytes[i]; for (uint32_t k = lane; k < sl; k += 32) dd[k] = ss[k]; }
@@ -236,6 +245,7 @@ void* bamgpu_decode(const uint8_t* file, int64_t file_bytes, const BgBlock* bloc
         BgRows& r = h->r;
         BG_ALLOC(r.tid, int32_t, n); BG_ALLOC(r.pos, int32_t, n); BG_ALLOC(r.flag, uint16_t, n); BG_ALLOC(r.mapq, uint8_t, n); BG_ALLOC(r.n_cigar, uint32_t, n);
         BG_ALLOC(r.l_seq, int32_t, n); BG_ALLOC(r.sa_len, uint32_t, n); BG_ALLOC(r.sa_src, uint32_t, n);
+        BG_ALLOC(r.cig_src, uint32_t, n); BG_ALLOC(r.n_core, uint32_t, n);
         BG_ALLOC(r.cig_words, uint64_t, n + 1); BG_ALLOC(r.seq_bytes, uint64_t, n + 1); BG_ALLOC(r.sa_bytes, uint64_t, n + 1); BG_ALLOC(r.name_bytes, uint64_t, n + 1);
         uint64_t tot[4] = {0, 0, 0, 0};
         if (n) {
