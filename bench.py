@@ -153,8 +153,9 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline(batch, genome, target_seconds=15.0):
-    """Oracle port of the reference on a contiguous genomic prefix of the same input, 1 host thread."""
+def cpu_baseline(batch, genome, target_seconds=15.0, keep=None):
+    """Oracle port of the reference on a contiguous genomic prefix of the same input, 1 host thread.
+    keep: dict that receives the prefix length and the oracle's signature / cluster rows (the parity check reuses them)."""
     from oracle import svim_oracle as orc
     p = orc.Params()
     # calibrate on 300 records, then size the slice for ~target_seconds of COLLECT (+ CLUSTER on what it emits)
@@ -165,8 +166,15 @@ def cpu_baseline(batch, genome, target_seconds=15.0):
     t0 = time.perf_counter()
     sigs, _ = orc.collect(sl, p)
     t1 = time.perf_counter()
-    orc.cluster(sigs, genome, p)
+    res = orc.cluster(sigs, genome, p)
     t2 = time.perf_counter()
+    if keep is not None:
+        index_of = {id(x): i for i, x in enumerate(sigs)}
+        keep["n"] = n
+        keep["signatures"] = [list(x.as_tuple()) for x in sigs]
+        keep["clusters"] = {name: [[c.type, c.contig, c.start, c.end, c.dest_contig, c.dest_start, c.dest_end, c.score, c.size, c.std_span, c.std_pos,
+                                    c.dir1, c.dir2, [index_of[id(m)] for m in c.members]] for c in cl]
+                            for name, cl in zip(("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND"), res)}
     return {"value": n / (t2 - t0), "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "first %d of %d coordinate-sorted records (%.1f s COLLECT + %.1f s CLUSTER, %d signatures); "
                       "edit distance by oracle/editdist.c Myers (edlib stand-in)" % (n, batch.n, t1 - t0, t2 - t1, len(sigs))}
@@ -386,15 +394,61 @@ def main():
         if s >= args.warmup:
             e2e_ms.append(barrier_max(ms))
     clocks_e2e = sampler_e2e.stop()
-    # same, plus materialising the Python SVSignature / SignatureCluster objects (what `svim alignment` consumes)
+    # ---------------- parity evidence, outside the timed regions --------------------------------------------
+    # the device's sorted order + partition offsets of the last step (svimgpu_fetch_partitions), before anything re-clusters
+    sigs = np.array(sigs); ins = np.array(ins)        # own copies: the pinned mirrors are reused by later calls
+    part_order, part_off = ctx.fetch_partitions(len(sigs))
+    parity = {"mismatches": 0}
+    if world > 1:
+        from svim_b200 import rows as svrows
+        import torch.distributed as dist
+        mine = svrows.result_digest(clusters, members, sigs)
+        digests = [None] * world
+        dist.all_gather_object(digests, mine)
+        # the same gathered signature list clustered by ONE GPU (no partition sharding, no cluster exchange) must give the same bytes
+        ctx.use_collected(0)
+        _st1, cl1, mem1 = ctx.cluster()
+        single = svrows.result_digest(cl1, mem1, sigs)
+        singles = [None] * world
+        dist.all_gather_object(singles, single)
+        parity.update({"rank_digests": digests, "ranks_agree": len(set(digests)) == 1, "sharded_equals_single_gpu_cluster": all(x == mine for x in singles),
+                       "note": "digest = blake2b-64 of (cluster records, member indices, gathered signature records); single = every rank re-clusters "
+                               "the gathered signatures alone (svimgpu_cluster) and compares"})
+        parity["mismatches"] += int(len(set(digests)) != 1) + int(any(x != mine for x in singles))
+    # ---------------- e2e_python: the reference-shaped call pair, objects included ("... to 6-tuple of cluster lists
+    # materialised in Python") — svim:102 analyze_alignment_file_coordsorted(bam, options) + svim:132 cluster_sv_signatures(sigs, options)
+    # through svim_b200's host mirror on the same pinned host buffers, wall clock, every step uploads and builds every object ----------
+    py_leg = None
     obj_s = None
     if world == 1:
-        from svim_b200.SVIM_COLLECT import materialize_signatures
-        from svim_b200.SVIM_clustering import build_clusters
-        t0 = time.perf_counter()
-        objs = materialize_signatures(sigs, ins, batch)
-        build_clusters(clusters, members, objs)
-        obj_s = time.perf_counter() - t0
+        import gc
+        from svim_b200 import runtime
+        from svim_b200.SVIM_COLLECT import analyze_alignment_file_coordsorted
+        from svim_b200.SVIM_CLUSTER import cluster_sv_signatures
+        runtime._CTX[local_rank] = ctx                      # same context (and its device buffers) as the legs above
+        os.environ["SVIM_B200_DEVICE"] = str(local_rank)
+        runtime.register_genome("bench-genome", genome)
+        ctx.genome_key = None
+        opts = argparse.Namespace(min_mapq=20, min_sv_size=40, max_sv_size=100000, segment_gap_tolerance=10, segment_overlap_tolerance=5,
+                                  partition_max_distance=1000, position_distance_normalizer=900, edit_distance_normalizer=1.0,
+                                  cluster_max_distance=0.5, all_bnds=False, genome="bench-genome")
+        py_ms = []; n_obj = 0
+        for s in range(2 + max(2, min(args.steps, 5))):
+            gc.collect()
+            t0 = time.perf_counter()
+            sv_sigs, _twins = analyze_alignment_file_coordsorted(batch, opts)
+            t1 = time.perf_counter()
+            six = cluster_sv_signatures(sv_sigs, opts)
+            t2 = time.perf_counter()
+            if s >= 2:
+                py_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
+            n_obj = len(sv_sigs) + sum(len(x) for x in six)
+            del sv_sigs, _twins, six                        # freeing 270 k objects is the caller's cost, not part of the call pair
+        m = np.mean(np.asarray(py_ms), axis=0)
+        py_leg = {"value": batch.n / (m[0] * 1e-3), "unit": UNIT, "ms_per_step": float(m[0]), "collect_call_ms": float(m[1]), "cluster_call_ms": float(m[2]),
+                  "python_objects": int(n_obj), "note": "wall clock of analyze_alignment_file_coordsorted + cluster_sv_signatures (svim_b200 host mirror) from pinned "
+                  "host record buffers to the 6-tuple of SignatureCluster lists; objects built by svim_b200/csrc_host/fastobj.c"}
+        obj_s = None
     for a in pinned:
         ctx.unpin(a)
     geno_leg = genotype_leg(ctx, batch, clusters, members, sigs, args) if world == 1 else None
@@ -441,25 +495,47 @@ def main():
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
-                "python_object_materialisation_s": obj_s, "clocks": clocks_e2e},
+                "clocks": clocks_e2e},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
         "clocks": clocks,
     }
+    if py_leg:
+        out["e2e_python"] = py_leg
     if bam_leg:
         out["e2e_from_bam"] = bam_leg
     if geno_leg:
         out["genotype"] = geno_leg
     if clst.myers_cells and "myers_edit_distance" in out["stages_ms"]:
-        # gcups = cells of the full DP matrices per second (what an unbanded computation would touch); the banded first pass
-        # computes band_cells of them, pairs it hands over are recomputed in full
+        # The time-dominant stage.  computed_cells = what the kernels really touched: window cells of the first pass (thread-per-pair
+        # windows: columns x 32 x blocks; wavefront bands) + full matrices of the pairs that run unbanded (their own + hand-overs).
+        # Peak: the block step of k_myers_tpp is 9 ALU-pipe instructions (7 LOP3 + 2 SHF) per 32 cells per lane, the ALU pipe takes one
+        # warp instruction every 2 clocks per scheduler (B300_MICROARCH.md "Pipe rates"): SMs x 4 schedulers x 32 lanes x 32 cells / 18 clk.
         t_my = out["stages_ms"]["myers_edit_distance"] * 1e-3
-        out["myers"] = {"kernel": "k_myers_band + k_myers_fast", "bound": "int-alu", "gcups": clst.myers_cells / t_my / 1e9,
-                        "band_cells_frac": clst.myers_band_cells / clst.myers_cells, "banded_pairs": int(clst.myers_banded_pairs),
-                        "handed_over_pairs": int(clst.myers_retry_pairs)}
-    if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(batch, genome, target_seconds=args.ref_seconds)
+        computed = int(clst.myers_band_cells) + int(clst.myers_unbanded_cells)
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        peak = 148 * 4 * 32 * 32 / 18.0 * sm_clock / 1e12
+        out["roofline_myers"] = {"kernel": "k_myers_tpp<B> (+ k_myers_band / k_myers_fast for what it hands over)", "bound": "int-alu",
+                                 "computed_cells": computed, "ms": t_my * 1e3, "tcups": computed / t_my / 1e12, "peak_tcups": peak,
+                                 "frac": computed / t_my / 1e12 / peak,
+                                 "peak_derivation": "148 SMs x 4 schedulers x 32 lanes x 32 cells per block step / (9 ALU-pipe instr x 2 clk) x %.0f MHz" % (sm_clock / 1e6),
+                                 "full_matrix_cells": int(clst.myers_cells), "effective_tcups": clst.myers_cells / t_my / 1e12,
+                                 "pairs": int(clst.myers_pairs), "first_pass_pairs": int(clst.myers_banded_pairs), "tpp_pairs": int(clst.myers_tpp_pairs),
+                                 "tpp_cells": int(clst.myers_tpp_cells), "handed_over_pairs": int(clst.myers_retry_pairs),
+                                 "unbanded_cells": int(clst.myers_unbanded_cells)}
+    if not args.no_cpu_baseline:
+        # rank 0's own records are the head of the gathered list, so the prefix check holds at every N (shorter prefix at N > 1,
+        # where no cpu_baseline is reported)
+        from svim_b200 import rows as svrows
+        keep = {}
+        base = cpu_baseline(batch, genome, target_seconds=args.ref_seconds if world == 1 else min(args.ref_seconds, 4.0), keep=keep)
+        if world == 1:
+            out["cpu_baseline"] = base
+        pp = svrows.prefix_parity(batch, keep["n"], sigs, ins, clusters, members, part_order, part_off, keep["signatures"], keep["clusters"])
+        parity.update(pp); parity["mismatches"] = pp["mismatches"] + (parity.get("mismatches", 0) if world > 1 else 0)
+        parity["against"] = "oracle port of the reference on the first %d records; clusters of every partition made only of their signatures" % keep["n"]
+    out["parity"] = parity
     print(json.dumps(out))
 
 

@@ -30,7 +30,8 @@ typedef enum {
     SVIMGPU_ERR_STATE = -3,     /* call sequence violated (e.g. cluster before collect) */
     SVIMGPU_ERR_LIMIT = -4,     /* a documented capacity was exceeded */
     SVIMGPU_ERR_DATA = -5,      /* input the reference itself would raise on (ZeroDivisionError, bad SA ints) */
-    SVIMGPU_ERR_NCCL = -6
+    SVIMGPU_ERR_NCCL = -6,
+    SVIMGPU_ERR_PEER = -7       /* multi-GPU: another rank failed before a collective; every rank returns an error, none keeps a result */
 } svimgpu_status;
 
 /* Hot-path options: SVIM_input_parsing.py:279-371 (defaults in comments). */
@@ -135,7 +136,9 @@ typedef struct {
     int64_t myers_pairs, myers_cells;          /* edit distances read / cells of their full DP matrices */
     int64_t myers_banded_pairs;                /* of those, scheduled on the banded first pass ...            */
     int64_t myers_retry_pairs;                 /* ... and handed over to the unbanded kernels (bound exceeded) */
-    int64_t myers_band_cells;                  /* cells the banded pass computed                              */
+    int64_t myers_band_cells;                  /* cells the banded first pass computed (wavefront + thread-per-pair) */
+    int64_t myers_tpp_pairs, myers_tpp_cells;  /* of those: pairs / cells of the thread-per-pair window kernels  */
+    int64_t myers_unbanded_cells;              /* cells the unbanded kernels computed: their own pairs + the hand-overs, full matrices */
 } svim_cluster_stats;
 
 typedef struct {

@@ -57,79 +57,57 @@ def as_batch(bam) -> AlignmentBatch:
     raise TypeError("expected an AlignmentBatch, a SAM/BAM path or an object with .batch")
 
 
+_SIG_CLASSES = (SignatureDeletion, SignatureInsertion, SignatureInversion, SignatureDuplicationTandem, SignatureTranslocation,
+                SignatureInsertionFrom)          # enum order of include/svimgpu.h
+
+
 def materialize_signatures(sigs: np.ndarray, ins: np.ndarray, batch: AlignmentBatch):
     """svim_sig records (+ INS blob) -> SVSignature objects, in record order.
 
-    The per-object cost dominates once the kernels are fast, so objects are built by filling `__dict__` directly
-    (same attributes the constructors set) from column lists, one comprehension per type."""
-    n = len(sigs)
-    if n == 0:
+    The per-object cost dominates once the kernels are fast (380 ms of Python for 257 k signatures on BASELINE configs[1]), so
+    the objects are built in one C loop (svim_b200/csrc_host/fastobj.c: tp_alloc + stores into the classes' __slots__).
+    `materialize_signatures_py` is the same thing in Python; the tests compare the two attribute by attribute."""
+    if len(sigs) == 0:
         return []
+    from . import fastobj
+    fo = fastobj.module()
     import gc
     was_enabled = gc.isenabled()
     gc.disable()            # hundreds of thousands of small containers: generational GC passes would dominate
     try:
-        return _materialize(sigs, ins, batch, n)
+        return fo.signatures(np.ascontiguousarray(sigs).view(np.uint8), np.ascontiguousarray(ins), list(batch.contig_names), batch.qnames,
+                             _SIG_CLASSES, tuple(_lib.INV_DIRECTIONS))
     finally:
         if was_enabled:
             gc.enable()
 
 
-def _materialize(sigs, ins, batch, n):
+def materialize_signatures_py(sigs: np.ndarray, ins: np.ndarray, batch: AlignmentBatch):
+    """Reference implementation of `materialize_signatures` in Python (test oracle for the C loop; not on the product path)."""
     names = batch.contig_names
-    typ = sigs["type"]
-    flags = sigs["flags"]
-    src_l = np.where(flags & _lib.F_SUPPL, "suppl", "cigar").tolist()
-    qid = sigs["qname_id"]
-    if batch.qnames is None:
-        reads = ["read%d" % q for q in qid.tolist()]
-    else:
-        qn = batch.qnames
-        reads = [qn[q] for q in qid.tolist()]
-    c1 = [names[t] for t in sigs["contig1"].tolist()] if len(names) > 1 else [names[0]] * n
-    start = sigs["start"].tolist(); end = sigs["end"].tolist()
-    out = [None] * n
-    new = object.__new__
-
-    def build(cls, idx, dicts):
-        for k, d in zip(idx, dicts):
-            o = new(cls)
-            o.__dict__ = d
-            out[k] = o
-
-    idx = np.nonzero(typ == 0)[0].tolist()
-    build(SignatureDeletion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k], "type": "DEL"} for k in idx])
-    idx = np.nonzero(typ == 1)[0].tolist()
-    if idx:
-        text = ins.tobytes().decode("ascii")
-        so = sigs["seq_off"].tolist(); sl = sigs["seq_len"].tolist()
-        build(SignatureInsertion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k],
-                                         "sequence": text[so[k]:so[k] + sl[k]], "type": "INS"} for k in idx])
-    idx = np.nonzero(typ == 2)[0].tolist()
-    if idx:
-        fl = flags.tolist()
-        build(SignatureInversion, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "signature": src_l[k], "read": reads[k], "type": "INV",
-                                         "direction": _lib.INV_DIRECTIONS[(fl[k] >> _lib.F_INVDIR_SHIFT) & 7]} for k in idx])
-    idx = np.nonzero(typ == 3)[0].tolist()
-    if idx:
-        fl = flags.tolist(); cp = sigs["copies"].tolist()
-        build(SignatureDuplicationTandem, idx, [{"contig": c1[k], "start": start[k], "end": end[k], "copies": cp[k],
-                                                 "fully_covered": bool(fl[k] & _lib.F_FULLY_COVERED), "signature": src_l[k], "read": reads[k],
-                                                 "type": "DUP_TAN"} for k in idx])
-    idx = np.nonzero(typ >= 4)[0].tolist()
-    if idx:
-        fl = flags.tolist(); pos = sigs["pos"].tolist(); c2 = sigs["contig2"].tolist(); tl = typ.tolist()
-        for k in idx:
-            if tl[k] == 4:      # records are already in canonical breakend order (no constructor swap)
-                o = new(SignatureTranslocation)
-                o.__dict__ = {"contig1": c1[k], "pos1": start[k], "direction1": "rev" if fl[k] & _lib.F_DIR1_REV else "fwd",
-                              "contig2": names[c2[k]], "pos2": pos[k], "direction2": "rev" if fl[k] & _lib.F_DIR2_REV else "fwd",
-                              "signature": src_l[k], "read": reads[k], "type": "BND"}
-            else:
-                o = new(SignatureInsertionFrom)
-                o.__dict__ = {"contig1": c1[k], "start": start[k], "end": end[k], "contig2": names[c2[k]], "pos": pos[k],
-                              "signature": src_l[k], "read": reads[k], "type": "DUP_INT"}
-            out[k] = o
+    text = ins.tobytes().decode("ascii")
+    out = []
+    for s in sigs:
+        t = int(s["type"]); fl = int(s["flags"])
+        src = "suppl" if fl & _lib.F_SUPPL else "cigar"
+        read = batch.qname(int(s["qname_id"]))
+        c1 = names[int(s["contig1"])]; st, en = int(s["start"]), int(s["end"])
+        if t == 0:
+            o = SignatureDeletion(c1, st, en, src, read)
+        elif t == 1:
+            o = SignatureInsertion(c1, st, en, src, read, text[int(s["seq_off"]):int(s["seq_off"]) + int(s["seq_len"])])
+        elif t == 2:
+            o = SignatureInversion(c1, st, en, src, read, _lib.INV_DIRECTIONS[(fl >> _lib.F_INVDIR_SHIFT) & 7])
+        elif t == 3:
+            o = SignatureDuplicationTandem(c1, st, en, int(s["copies"]), bool(fl & _lib.F_FULLY_COVERED), src, read)
+        elif t == 4:      # records are already in canonical breakend order (SVSignature.py:193-214 ran on the device): no constructor swap
+            o = object.__new__(SignatureTranslocation)
+            o.contig1, o.pos1, o.direction1 = c1, st, "rev" if fl & _lib.F_DIR1_REV else "fwd"
+            o.contig2, o.pos2, o.direction2 = names[int(s["contig2"])], int(s["pos"]), "rev" if fl & _lib.F_DIR2_REV else "fwd"
+            o.signature, o.read = src, read
+        else:
+            o = SignatureInsertionFrom(c1, st, en, names[int(s["contig2"])], int(s["pos"]), src, read)
+        out.append(o)
     return out
 
 

@@ -67,18 +67,24 @@ def _none_if_nan(x):
 
 
 def build_clusters(clusters: np.ndarray, members: np.ndarray, signatures):
-    """svim_cluster records -> per-type lists of SignatureCluster objects (enum order)."""
+    """svim_cluster records -> per-type lists of SignatureCluster objects (enum order), built in C (csrc_host/fastobj.c)."""
+    from . import fastobj
+    fo = fastobj.module()
+    if not isinstance(signatures, list):
+        signatures = list(signatures)
     import gc
     was_enabled = gc.isenabled()
     gc.disable()
     try:
-        return _build_clusters(clusters, members, signatures)
+        return fo.clusters(np.ascontiguousarray(clusters).view(np.uint8), np.ascontiguousarray(members, dtype=np.uint32).view(np.uint8), signatures,
+                           SignatureClusterUniLocal, SignatureClusterBiLocal, tuple(_lib.TYPE_NAMES))
     finally:
         if was_enabled:
             gc.enable()
 
 
-def _build_clusters(clusters, members, signatures):
+def build_clusters_py(clusters, members, signatures):
+    """Reference implementation of `build_clusters` in Python (test oracle for the C loop; not on the product path)."""
     out = [[] for _ in range(6)]
     mem = members.tolist()
     cols = [clusters[f].tolist() for f in ("type", "start", "end", "dest_start", "dest_end", "score", "std_span", "std_pos",

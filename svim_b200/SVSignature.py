@@ -12,13 +12,17 @@ _INF = float("inf")
 
 
 class Signature:
-    """A structural-variant signature observed in one read."""
+    """A structural-variant signature observed in one read.
+
+    Every class declares its attributes as __slots__ (plus __dict__, so downstream code may still attach attributes like the
+    reference's plain classes allow): svim_b200/csrc_host/fastobj.c builds hundreds of thousands of these by storing straight
+    into the slots.  `type` is a class attribute of the signature classes (the reference sets the same constant per instance)."""
+    __slots__ = ("__dict__",)
     type = None
 
     def __init__(self, contig, start, end, signature, read):
         self.contig, self.start, self.end = contig, start, end
         self.signature, self.read = signature, read
-        self.type = type(self).type
         if end < start:
             logging.warning("Signature with invalid coordinates (end < start): " + self.as_string())
 
@@ -62,22 +66,24 @@ def _checked_interval(start, end):
 
 class SignatureDeletion(Signature):
     """contig:start-end (0-based, end exclusive) is missing from the sample."""
+    __slots__ = ("contig", "start", "end", "signature", "read")
     type = "DEL"
 
     def __init__(self, contig, start, end, signature, read):
         self.contig = contig
         self.start, self.end = _checked_interval(start, end)
-        self.signature, self.read, self.type = signature, read, "DEL"
+        self.signature, self.read = signature, read
 
 
 class SignatureInsertion(Signature):
     """end-start bases (`sequence`) inserted before contig:start."""
+    __slots__ = ("contig", "start", "end", "signature", "read", "sequence")
     type = "INS"
 
     def __init__(self, contig, start, end, signature, read, sequence):
         self.contig = contig
         self.start, self.end = _checked_interval(start, end)
-        self.signature, self.read, self.sequence, self.type = signature, read, sequence, "INS"
+        self.signature, self.read, self.sequence = signature, read, sequence
 
     def get_key(self):
         return (self.type, self.contig, self.start)
@@ -88,12 +94,13 @@ class SignatureInsertion(Signature):
 
 class SignatureInversion(Signature):
     """contig:start-end is inverted; `direction` names the breakpoint seen."""
+    __slots__ = ("contig", "start", "end", "signature", "read", "direction")
     type = "INV"
 
     def __init__(self, contig, start, end, signature, read, direction):
         self.contig = contig
         self.start, self.end = _checked_interval(start, end)
-        self.signature, self.read, self.direction, self.type = signature, read, direction, "INV"
+        self.signature, self.read, self.direction = signature, read, direction
 
     def _label(self):
         return "{0};{1};{2}".format(self.type, self.direction, self.signature)
@@ -101,13 +108,14 @@ class SignatureInversion(Signature):
 
 class SignatureInsertionFrom(Signature):
     """contig1:start-end was copied to contig2:pos (interspersed duplication)."""
+    __slots__ = ("contig1", "start", "end", "contig2", "pos", "signature", "read")
     type = "DUP_INT"
 
     def __init__(self, contig1, start, end, contig2, pos, signature, read):
         self.contig1 = contig1
         self.start, self.end = _checked_interval(start, end)
         self.contig2, self.pos = contig2, pos
-        self.signature, self.read, self.type = signature, read, "DUP_INT"
+        self.signature, self.read = signature, read
 
     def get_source(self):
         return (self.contig1, self.start, self.end)
@@ -127,13 +135,14 @@ class SignatureInsertionFrom(Signature):
 
 class SignatureDuplicationTandem(Signature):
     """contig:start-end repeated `copies` more times right after `end`."""
+    __slots__ = ("contig", "start", "end", "copies", "fully_covered", "signature", "read")
     type = "DUP_TAN"
 
     def __init__(self, contig, start, end, copies, fully_covered, signature, read):
         self.contig = contig
         self.start, self.end = _checked_interval(start, end)
         self.copies, self.fully_covered = copies, fully_covered
-        self.signature, self.read, self.type = signature, read, "DUP_TAN"
+        self.signature, self.read = signature, read
 
     def get_destination(self):
         return (self.contig, self.end, self.end + self.copies * (self.end - self.start))
@@ -151,6 +160,7 @@ _FLIP = {"fwd": "rev", "rev": "fwd"}
 class SignatureTranslocation(Signature):
     """Novel adjacency contig1:pos1 -- contig2:pos2; the breakend with the smaller
     (contig name, position) comes first, which flips the directions when swapped."""
+    __slots__ = ("contig1", "pos1", "direction1", "contig2", "pos2", "direction2", "signature", "read")
     type = "BND"
 
     def __init__(self, contig1, pos1, direction1, contig2, pos2, direction2, signature, read):
@@ -159,7 +169,7 @@ class SignatureTranslocation(Signature):
                 contig2, pos2, _FLIP[direction2], contig1, pos1, _FLIP[direction1]
         self.contig1, self.pos1, self.direction1 = contig1, pos1, direction1
         self.contig2, self.pos2, self.direction2 = contig2, pos2, direction2
-        self.signature, self.read, self.type = signature, read, "BND"
+        self.signature, self.read = signature, read
 
     def get_source(self):
         return (self.contig1, self.pos1, self.pos1 + 1)
@@ -176,6 +186,7 @@ class SignatureTranslocation(Signature):
 
 class SignatureClusterUniLocal(Signature):
     """Cluster of DEL / INS / INV signatures (one locus)."""
+    __slots__ = ("contig", "start", "end", "score", "size", "members", "type", "std_span", "std_pos")
 
     def __init__(self, contig, start, end, score, size, members, type, std_span, std_pos):
         self.contig, self.start, self.end = contig, start, end
@@ -202,6 +213,8 @@ class SignatureClusterUniLocal(Signature):
 
 class SignatureClusterBiLocal(Signature):
     """Cluster of DUP_TAN / DUP_INT / BND signatures (source and destination locus)."""
+    __slots__ = ("source_contig", "source_start", "source_end", "dest_contig", "dest_start", "dest_end", "score", "size", "members", "type",
+                 "std_span", "std_pos")
 
     def __init__(self, source_contig, source_start, source_end, dest_contig, dest_start, dest_end, score, size, members,
                  type, std_span, std_pos):

@@ -2,7 +2,8 @@
 
 Runs COLLECT -> CLUSTER on the GPU with the option names and defaults of the reference's `svim alignment`
 sub-command (SVIM_input_parsing.py:262-371), coordinate- or queryname-sorted input (svim:89-111), and writes the
-signature-cluster BED files the reference writes after CLUSTER (`signatures/*.bed`).  COMBINE and the final VCF are the
+signature-cluster files the reference writes after CLUSTER (`signatures/{del,ins,inv,dup_tan_source,dup_tan_dest,dup_int,trans}.bed`
+and `signatures/all.vcf`, SVIM_CLUSTER.py:29-107).  COMBINE and the final VCF are the
 reference's downstream stages: `python -m svim_b200.patch alignment ...` with the reference installed runs the whole
 pipeline with COLLECT, CLUSTER, the cut&paste search, the candidate clustering and GENOTYPE rebound to this package.
 """
@@ -34,18 +35,54 @@ def parse(argv):
     return ap.parse_args(argv)
 
 
-BED_FILES = (("del.bed", 0, False), ("ins.bed", 1, False), ("inv.bed", 2, False), ("dup_tan.bed", 3, True), ("dup_int.bed", 4, True),
-             ("trans.bed", 5, True))
+SVIM_VERSION = "2.0.0"          # version string of the reference this package mirrors (svim:3), written into all.vcf
+
+# signatures/<file>: which list of the 6-tuple (DEL, INS, INV, DUP_TAN, DUP_INT, BND) goes where.  Unilocal clusters have one BED
+# line; bilocal ones a source and a destination line, which tandem duplications split over two files and the other two types
+# keep together (the file set of the reference's write_signature_clusters_bed, SVIM_CLUSTER.py:29-69).
+_UNILOCAL_BEDS = (("del.bed", 0), ("ins.bed", 1), ("inv.bed", 2))
+_BILOCAL_BEDS = ((3, ("dup_tan_source.bed", "dup_tan_dest.bed")), (4, ("dup_int.bed", "dup_int.bed")), (5, ("trans.bed", "trans.bed")))
+
+_VCF_HEADER = (
+    "##fileformat=VCFv4.3",
+    "##source=SVIMV{version}",
+    '##ALT=<ID=DEL,Description="Deletion">',
+    '##ALT=<ID=INV,Description="Inversion">',
+    '##ALT=<ID=DUP,Description="Duplication">',
+    '##ALT=<ID=DUP:TANDEM,Description="Tandem Duplication">',
+    '##ALT=<ID=INS,Description="Insertion">',
+    '##INFO=<ID=END,Number=1,Type=Integer,Description="End position of the variant described in this record">',
+    '##INFO=<ID=SVTYPE,Number=1,Type=String,Description="Type of structural variant">',
+    '##INFO=<ID=SVLEN,Number=.,Type=Integer,Description="Difference in length between REF and ALT alleles">',
+    "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO",
+)
 
 
 def write_cluster_beds(working_dir, clusters):
+    """signatures/*.bed, file for file what the reference writes after CLUSTER (SVIM_CLUSTER.py:29-69)."""
     out = os.path.join(working_dir, "signatures")
     os.makedirs(out, exist_ok=True)
-    for name, idx, bilocal in BED_FILES:
+    lines = {}
+    for name, idx in _UNILOCAL_BEDS:
+        lines[name] = [c.get_bed_entry() for c in clusters[idx]]
+    for idx, (src_file, dst_file) in _BILOCAL_BEDS:
+        lines.setdefault(src_file, []); lines.setdefault(dst_file, [])
+        for c in clusters[idx]:
+            src, dst = c.get_bed_entries()
+            lines[src_file].append(src); lines[dst_file].append(dst)
+    for name, rows in lines.items():
         with open(os.path.join(out, name), "w") as fh:
-            for c in clusters[idx]:
-                for line in (c.get_bed_entries() if bilocal else (c.get_bed_entry(),)):
-                    fh.write(line + "\n")
+            fh.writelines(r + "\n" for r in rows)
+
+
+def write_cluster_vcf(working_dir, clusters, version=SVIM_VERSION):
+    """signatures/all.vcf (SVIM_CLUSTER.py:72-107): DEL, INS, INV and DUP_TAN clusters, sorted by their source triple."""
+    out = os.path.join(working_dir, "signatures")
+    os.makedirs(out, exist_ok=True)
+    records = sorted(((c.get_source(), c.get_vcf_entry()) for idx in (0, 1, 2, 3) for c in clusters[idx]), key=lambda pair: pair[0])
+    with open(os.path.join(out, "all.vcf"), "w") as fh:
+        fh.writelines(h.format(version=version) + "\n" for h in _VCF_HEADER)
+        fh.writelines(str(entry) + "\n" for _src, entry in records)
 
 
 def main(argv=None):
@@ -80,6 +117,7 @@ def main(argv=None):
         clusters = clusters[:5] + (clusters[5] + extra[5],)
     t3 = time.perf_counter()
     write_cluster_beds(options.working_dir, clusters)
+    write_cluster_vcf(options.working_dir, clusters)
     logging.info("decode %.2f s, COLLECT %.2f s, CLUSTER %.2f s for %d alignment records (%d signatures, %d clusters)",
                  t1 - t0, t2 - t1, t3 - t2, batch.n, len(sigs), sum(len(c) for c in clusters))
     return 0

@@ -92,7 +92,8 @@ class ClusterStats(C.Structure):
     _fields_ = [("n_partitions", C.c_int64 * 6), ("n_clusters", C.c_int64 * 6), ("large_partitions", C.c_int64 * 6),
                 ("duplicate_signatures", C.c_int64 * 6), ("n_members", C.c_int64), ("n_clusters_total", C.c_int64),
                 ("myers_pairs", C.c_int64), ("myers_cells", C.c_int64),
-                ("myers_banded_pairs", C.c_int64), ("myers_retry_pairs", C.c_int64), ("myers_band_cells", C.c_int64)]
+                ("myers_banded_pairs", C.c_int64), ("myers_retry_pairs", C.c_int64), ("myers_band_cells", C.c_int64),
+                ("myers_tpp_pairs", C.c_int64), ("myers_tpp_cells", C.c_int64), ("myers_unbanded_cells", C.c_int64)]
 
 
 class CollectStats(C.Structure):

@@ -22,6 +22,19 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def run_atomic(cmd, out):
+    """Run a compiler command whose output argument is the literal string "@OUT@", writing beside `out` and renaming into place:
+    a concurrent rank (torchrun) or a gpurun snapshot never sees a half-written library."""
+    tmp = "%s.tmp%d" % (out, os.getpid())
+    try:
+        subprocess.check_call([tmp if a == "@OUT@" else a for a in cmd])
+        os.replace(tmp, out)
+    finally:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
+    return out
+
+
 def needs_build():
     if not os.path.exists(SO):
         return True
@@ -34,11 +47,10 @@ def build_gpu(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-           "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static", "-o", SO, os.path.join(SRC, "api.cu"), "-lnccl"]
+           "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static", "-o", "@OUT@", os.path.join(SRC, "api.cu"), "-lnccl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
-    return SO
+    return run_atomic(cmd, SO)
 
 
 def build_all(force=False):

@@ -45,6 +45,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (const char* v = getenv("SVIM_SCAN_VARIANT")) ctx->scan_variant = atoi(v);
     if (const char* v = getenv("SVIM_SCAN_CHUNKS")) ctx->scan_chunks = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_MODE")) ctx->myers_mode = atoi(v);
+    if (const char* v = getenv("SVIM_MYERS_TPP")) ctx->myers_tpp = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_BAND")) { int num = 0, add = 24; if (sscanf(v, "%d,%d", &num, &add) >= 1) { ctx->myers_band_num = num; ctx->myers_band_add = add; } }
     *out = ctx;
     return 0;
@@ -62,11 +63,13 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_samp_idx, &ctx->d_labels, &ctx->d_part_ncl, &ctx->d_part_nkept, &ctx->d_part_stats, &ctx->d_plist,
                       &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
                       &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
-                      &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3]};
+                      &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3], &ctx->d_xchg[4], &ctx->d_xchg[5], &ctx->d_xchg[6], &ctx->d_xchg[7],
+                      &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
-    for (int i = 0; i < 24; ++i) ctx->d_myers_scratch[i].release();
+    for (int i = 0; i < 48; ++i) ctx->d_myers_scratch[i].release();
     ctx->d_myers_ctl.release();
+    ctx->h_hdr.release(); ctx->h_picks.release(); ctx->h_clusters.release(); ctx->h_members.release();
     ctx->d_stage.release(); ctx->d_stage_off.release();
     for (DevBuf* b : {&ctx->d_geno_end, &ctx->d_geno_max, &ctx->d_geno_rows, &ctx->d_geno_cand, &ctx->d_geno_out, &ctx->d_geno_var, &ctx->d_geno_clen}) b->release();
     ctx->d_qs_info.release(); ctx->d_qs_grp.release(); ctx->d_qs_segsum.release(); ctx->d_qs_mem_off.release(); ctx->d_qs_mem_idx.release();
@@ -384,8 +387,8 @@ int svimgpu_cluster_sharded(svimgpu_ctx* ctx, svim_cluster_stats* stats) {
 int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* members) {
     if (!ctx) return SVIMGPU_ERR_ARG;
     if (!ctx->clustered) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster has not run"); return SVIMGPU_ERR_STATE; }
-    if (clusters && !ctx->h_clusters.empty()) memcpy(clusters, ctx->h_clusters.data(), ctx->h_clusters.size() * sizeof(svim_cluster));
-    if (members && !ctx->h_members.empty()) memcpy(members, ctx->h_members.data(), ctx->h_members.size() * 4);
+    if (clusters && ctx->n_clusters_host) memcpy(clusters, ctx->h_clusters.p, (size_t)ctx->n_clusters_host * sizeof(svim_cluster));
+    if (members && ctx->n_members_host) memcpy(members, ctx->h_members.p, (size_t)ctx->n_members_host * 4);
     return 0;
 }
 
@@ -395,7 +398,10 @@ int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* 
     cudaSetDevice(ctx->device);
     if (n_partitions) *n_partitions = ctx->n_partitions;
     if (order && ctx->n_csig) SVIM_CUDA(cudaMemcpy(order, ctx->d_order.p, (size_t)ctx->n_csig * 4, cudaMemcpyDeviceToHost));
-    if (part_off && !ctx->h_part_off.empty()) memcpy(part_off, ctx->h_part_off.data(), ctx->h_part_off.size() * 4);
+    if (part_off) {
+        if (ctx->n_partitions) SVIM_CUDA(cudaMemcpy(part_off, ctx->d_part_off.p, (size_t)ctx->n_partitions * 4, cudaMemcpyDeviceToHost));
+        part_off[ctx->n_partitions] = (uint32_t)ctx->n_csig;
+    }
     return 0;
 }
 
@@ -457,19 +463,21 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
     cudaSetDevice(ctx->device);
     int64_t blob_bytes = 0, maxlen = 16;
     // same scheduling as the pipeline (k_ins_pairs): banded shape if the band policy gives a smaller one, else the pattern's bin
-    std::vector<uint32_t> lists[2 * MYERS_BINS];
+    std::vector<uint32_t> lists[MYERS_LISTS];
     MyersPlan pl; memset(&pl, 0, sizeof(pl));
     for (int64_t i = 0; i < n_pairs; ++i) {
         blob_bytes = std::max<int64_t>(blob_bytes, std::max(a_off[i] + a_len[i], b_off[i] + b_len[i]));
         const int64_t m = std::max(a_len[i], b_len[i]), n = std::min(a_len[i], b_len[i]);
         maxlen = std::max<int64_t>(maxlen, m);
-        const int band = myers_band_bin(m, n, ctx->myers_band_num, ctx->myers_band_add);
-        if (band >= 0) { lists[MYERS_BINS + band].push_back((uint32_t)i); pl.retry_cap[myers_bin_of(m)]++; }
+        const int tq = ctx->myers_tpp ? tpp_bucket_of(tpp_plan(m, n, ctx->myers_band_num, ctx->myers_band_add).B) : -1;
+        const int band = tq >= 0 ? -1 : myers_band_bin(m, n, ctx->myers_band_num, ctx->myers_band_add);
+        if (tq >= 0) { lists[2 * MYERS_BINS + tq].push_back((uint32_t)i); pl.retry_cap[myers_bin_of(m)]++; }
+        else if (band >= 0) { lists[MYERS_BINS + band].push_back((uint32_t)i); pl.retry_cap[myers_bin_of(m)]++; }
         else lists[myers_bin_of(m)].push_back((uint32_t)i);
     }
     maxlen = (maxlen + 15) & ~15ll;
     std::vector<uint32_t> flat; flat.reserve((size_t)n_pairs);
-    for (int q = 0; q < 2 * MYERS_BINS; ++q) { pl.off[q] = (uint32_t)flat.size(); pl.cnt[q] = (uint32_t)lists[q].size(); flat.insert(flat.end(), lists[q].begin(), lists[q].end()); }
+    for (int q = 0; q < MYERS_LISTS; ++q) { pl.off[q] = (uint32_t)flat.size(); pl.cnt[q] = (uint32_t)lists[q].size(); flat.insert(flat.end(), lists[q].begin(), lists[q].end()); }
     DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_ctl, d_list, d_fb, d_retry, d_misc;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
@@ -487,7 +495,7 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         chk(cudaMemsetAsync(d_ctl.p, 0, MYERS_CTL_N * 4, ctx->stream)); chk(cudaMemsetAsync(d_misc.p, 0, 64, ctx->stream));
         MyersArgs ma; memset(&ma, 0, sizeof(ma));
         ma.ed_out = d_out.as<int32_t>(); ma.maxlen = maxlen; ma.fallback = d_fb.as<MyersWork>();
-        ma.cells = (unsigned long long*)d_misc.p; ma.err = (uint32_t*)d_misc.p + 4; ma.band_cells = (unsigned long long*)d_misc.p + 4;
+        ma.cells = (unsigned long long*)d_misc.p; ma.err = (uint32_t*)d_misc.p + 4;
         ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;
         StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
         chk(myers_run_plan<true>(ctx, pl, ma, sp, nullptr, d_list.as<uint32_t>(), d_retry.as<MyersWork>(), d_ctl.as<uint32_t>(), maxlen, 148));

@@ -21,7 +21,7 @@
 #include "myers.cu"
 
 // multi-GPU hook (nccl.cu): allgatherv of the per-shard cluster records before the final ordering
-static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_members);
+static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_members, int local_status);
 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_sig_to_csig(const svim_sig* s, uint32_t n, const int32_t* rank, svim_csig* out) {
@@ -79,6 +79,123 @@ __global__ void k_partition_heads(const svim_csig* s, const uint64_t* group, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// Partition plan on the device.  The host used to walk every partition (sizes, sample offsets, pair offsets, work lists,
+// shard cuts): O(P + n) per step on every rank.  Now it sees a 256-word header and the sizes of the partitions above 100 —
+// the only thing the sequential sampling stream (seed(1524) / sample(partition, 100), SVIM_clustering.py:129-134) consumes.
+struct PMeta { unsigned long long pairs, cost; uint32_t m, large; };      // per partition; scanned with operator+
+struct PMetaSum { __host__ __device__ __forceinline__ PMeta operator()(const PMeta& a, const PMeta& b) const {
+    PMeta r; r.pairs = a.pairs + b.pairs; r.cost = a.cost + b.cost; r.m = a.m + b.m; r.large = a.large + b.large; return r; } };
+struct LargePart { uint32_t p, size, type; };
+
+enum { HDR_NLARGE = 0, HDR_NSAMP = 1, HDR_PAIRS = 2 /* 64-bit */, HDR_LO = 4, HDR_HI = 5, HDR_NSMALL = 6, HDR_NBIG = 7, HDR_NINS = 8,
+       HDR_NPART_T = 16, HDR_NLARGE_T = 24, HDR_DUP_T = 32, HDR_NCL_T = 40, HDR_CUTS = 64, HDR_WORDS = 256, HDR_MAX_RANKS = 128,
+       HDR_LARGE_INLINE = 2048 };
+
+// sample size, pair count, cost estimate of every partition (+ a zero element at P so the exclusive scan ends on the totals)
+__global__ void k_part_meta(const svim_csig* s, const uint32_t* part_off, uint32_t P, uint32_t n, PMeta* meta, uint8_t* ptype, uint32_t* hdr,
+                            int32_t band_num, int32_t band_add) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    PMeta me; me.pairs = 0; me.cost = 0; me.m = 0; me.large = 0;
+    int type = -1;
+    if (p < P) {
+        const uint32_t b = part_off[p], e = p + 1 < P ? part_off[p + 1] : n, sz = e - b;
+        type = s[b].type;
+        const uint32_t m = sz > 100 ? 100u : sz;
+        me.m = m; me.large = sz > 100 ? 1u : 0u;
+        ptype[p] = (uint8_t)type;
+        // cost in ~lane-cycles: linkage ~ m^2; insertion pairs ~ columns x window blocks of the edit-distance kernel, from the
+        // mean inserted length of (up to) the first 128 members and the spread of their start positions
+        unsigned long long cost = 64ull + 50ull * m * m;
+        if (type == SVIM_INS && m > 1) {
+            me.pairs = (unsigned long long)m * (m - 1) / 2;
+            const uint32_t cnt = sz > 128 ? 128u : sz;
+            unsigned long long sum = 0;
+            for (uint32_t k = 0; k < cnt; ++k) sum += s[b + k].seq_len;
+            const double spread = s[b + cnt - 1].start - s[b].start;
+            unsigned long long L = sum / cnt + (unsigned long long)(spread > 0 ? spread / 3.0 : 0.0);
+            const unsigned long long band = band_num > 0 ? ((L * (unsigned long long)band_num) >> 10) + (unsigned long long)(band_add > 0 ? band_add : 0) + 63ull : L + 31ull;
+            cost += me.pairs * (L * (band < L + 31ull ? band : L + 31ull)) / 57ull;
+        }
+        me.cost = cost;
+    }
+    if (p <= P) meta[p] = me;
+    // per-type partition counts: partitions come grouped by type, so a warp rarely holds more than one
+    const int t = type < 0 ? -1 : (type > 5 ? 5 : type);
+    const unsigned grp = __match_any_sync(0xffffffffu, t);
+    if (t >= 0) {
+        const int lane = threadIdx.x & 31;
+        if (lane == __ffs(grp) - 1) atomicAdd(hdr + HDR_NPART_T + t, (uint32_t)__popc(grp));
+        const unsigned lg = __ballot_sync(grp, me.large != 0);
+        if (lg && lane == __ffs(grp) - 1) atomicAdd(hdr + HDR_NLARGE_T + t, (uint32_t)__popc(lg));
+    }
+}
+
+// shard cuts by cost (every rank computes the same cuts from the same scan), totals
+__global__ void k_part_plan(const PMeta* pref, uint32_t P, int shard_rank, int shard_n, uint32_t* hdr) {
+    const int r = threadIdx.x;
+    __shared__ uint32_t cut[HDR_MAX_RANKS + 1];
+    if (r <= shard_n) {
+        uint32_t c = r == 0 ? 0u : P;
+        if (r > 0 && r < shard_n) {
+            const unsigned long long total = pref[P].cost;
+            const unsigned long long target = (total / (unsigned)shard_n) * (unsigned)r + ((total % (unsigned)shard_n) * (unsigned)r) / (unsigned)shard_n;
+            uint32_t lo = 0, hi = P;                       // first p with pref[p].cost >= target
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (pref[mid].cost < target) lo = mid + 1; else hi = mid; }
+            c = lo;
+        }
+        cut[r] = c;
+    }
+    __syncthreads();
+    if (r == 0) {
+        for (int q = 1; q <= shard_n; ++q) if (cut[q] < cut[q - 1]) cut[q] = cut[q - 1];
+        for (int q = 0; q <= shard_n; ++q) hdr[HDR_CUTS + q] = cut[q];
+        hdr[HDR_LO] = cut[shard_rank]; hdr[HDR_HI] = cut[shard_rank + 1];
+        hdr[HDR_NLARGE] = pref[P].large; hdr[HDR_NSAMP] = pref[P].m;
+        const unsigned long long pt = pref[P].pairs;
+        hdr[HDR_PAIRS] = (uint32_t)pt; hdr[HDR_PAIRS + 1] = (uint32_t)(pt >> 32);
+    }
+}
+
+// dense offset arrays for the kernels downstream, the list of partitions above 100 (all of them: the sampling stream is
+// sequential per type), and this rank's three work lists  [linkage m <= 32 | linkage m > 32 | insertion pair lists]
+__global__ void k_part_lists(const PMeta* meta, const PMeta* pref, const uint8_t* ptype, const uint32_t* part_off, uint32_t P, uint32_t n,
+                             uint32_t* samp_off, uint64_t* pair_off, LargePart* large_list, uint32_t* plist, uint32_t* hdr) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int which = -1; bool ins = false;
+    if (p <= P) {
+        const PMeta pr = pref[p];
+        samp_off[p] = pr.m; pair_off[p] = pr.pairs;
+        if (p < P) {
+            const PMeta me = meta[p];
+            if (me.large) { const uint32_t b = part_off[p], e = p + 1 < P ? part_off[p + 1] : n; large_list[pr.large] = LargePart{p, e - b, ptype[p]}; }
+            if (p >= hdr[HDR_LO] && p < hdr[HDR_HI]) { which = me.m <= 32 ? 0 : 1; ins = me.pairs != 0; }
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+        const bool mine = l < 2 ? which == l : ins;
+        const unsigned msk = __ballot_sync(0xffffffffu, mine);
+        if (!msk) continue;
+        uint32_t base = 0;
+        if (lane == __ffs(msk) - 1) base = atomicAdd(hdr + HDR_NSMALL + l, (uint32_t)__popc(msk));
+        base = __shfl_sync(0xffffffffu, base, __ffs(msk) - 1);
+        if (mine) plist[(size_t)l * P + base + __popc(msk & ((1u << lane) - 1))] = p;
+    }
+}
+
+// sample slots of this rank's partitions: all members in key order, or the host's 100 picks (sample order = member order, :172-175)
+__global__ void __launch_bounds__(128) k_fill_samples(const uint32_t* part_off, const uint32_t* samp_off, const PMeta* meta, const PMeta* pref, uint32_t lo,
+                                                       uint32_t hi, const int32_t* picks, uint32_t* samp_idx) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p >= hi) return;
+    const uint32_t b = part_off[p], s0 = samp_off[p], m = meta[p].m;
+    if (meta[p].large) { const int32_t* pk = picks + (size_t)pref[p].large * 100; for (uint32_t k = lane; k < m; k += 32) samp_idx[s0 + k] = b + (uint32_t)pk[k]; }
+    else for (uint32_t k = lane; k < m; k += 32) samp_idx[s0 + k] = b + k;
+}
+
+// ---------------------------------------------------------------------------------------------
 // per-partition layout in shared memory (one warp per CTA)
 struct PartSmem {
     double* start; double* end; double* dpos; uint32_t* read; uint8_t* dirs; uint8_t* dup; int* kidx;
@@ -119,6 +236,7 @@ struct LinkArgs {
     int32_t* labels;                 // per sample slot: flat cluster id, 0 = same-read duplicate
     uint32_t* part_ncl; uint32_t* part_nkept;
     uint32_t* err;
+    uint32_t* dup_t;                 // per type: sampled signatures dropped as same-read duplicates
 };
 
 // nn-chain average linkage on the condensed matrix D (mk points) -> unsorted merge rows
@@ -249,7 +367,7 @@ __global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
         }
         ncl = __shfl_sync(FULL, ncl, 0);
     }
-    if (lane == 0) { a.part_ncl[p] = (uint32_t)ncl; a.part_nkept[p] = (uint32_t)mk; }
+    if (lane == 0) { a.part_ncl[p] = (uint32_t)ncl; a.part_nkept[p] = (uint32_t)mk; if (m > mk && a.dup_t) atomicAdd(a.dup_t + (type > 5 ? 5 : type), (uint32_t)(m - mk)); }
     if (__any_sync(FULL, err)) { if (lane == 0) atomicExch(a.err, 1u); }
 }
 
@@ -259,7 +377,7 @@ __global__ void __launch_bounds__(32) k_linkage(LinkArgs a, int M) {
 __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const uint8_t* ins_blob, GenomeView g, const uint32_t* samp_off,
                                                     const uint32_t* samp_idx, const uint32_t* plist, uint32_t n_list, const uint64_t* pair_off,
                                                     ClusterParams cp, int mode, MyersWork* work, uint64_t* work_key, uint32_t* bin_cursor,
-                                                    uint32_t* retry_cap, int32_t band_num, int32_t band_add, uint32_t* err) {
+                                                    uint32_t* retry_cap, int32_t band_num, int32_t band_add, int32_t use_tpp, uint32_t* err) {
     const int lane = threadIdx.x & 31;
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_list) return;
@@ -282,8 +400,13 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
                 if (pair_haps(a, b, ins_blob, g, ha, hb)) {
                     const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
                     const int64_t lm = la > lb ? la : lb, ln = la > lb ? lb : la;
-                    const int band = myers_band_bin(lm, ln, band_num, band_add);
-                    if (band >= 0) {
+                    const TppPlan tp = tpp_plan(lm, ln, band_num, band_add);
+                    const int tq = use_tpp ? tpp_bucket_of(tp.B) : -1;
+                    const int band = tq >= 0 ? -1 : myers_band_bin(lm, ln, band_num, band_add);
+                    if (tq >= 0) {                                   // thread-per-pair window (banded or whole pattern)
+                        bin = 2 * MYERS_BINS + tq; rbin = myers_bin_of(lm);
+                        cost = (uint32_t)ln;                         // columns
+                    } else if (band >= 0) {
                         bin = MYERS_BINS + band; rbin = myers_bin_of(lm);
                         cost = (uint32_t)(ln + (lm >> 6));          // ~ wavefront steps of the banded pass
                     } else {
@@ -294,17 +417,19 @@ __global__ void __launch_bounds__(128) k_ins_pairs(const svim_csig* sig, const u
                 } else { atomicExch(err, 1u); }
             }
         }
-#pragma unroll
-        for (int bb = 0; bb < 2 * MYERS_BINS; ++bb) {
-            const unsigned msk = __ballot_sync(FULL, bin == bb);
-            if (!msk) continue;
-            uint32_t base = 0;
-            if (lane == (__ffs(msk) - 1)) base = atomicAdd(bin_cursor + bb, (uint32_t)__popc(msk));
-            base = __shfl_sync(FULL, base, __ffs(msk) - 1);
-            if (mode == 1 && bin == bb) {
-                const uint32_t at = base + __popc(msk & ((1u << lane) - 1));
-                MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[at] = wk;
-                work_key[at] = ((uint64_t)bb << 32) | (uint64_t)(0xffffffffu - cost);   // longest pairs first inside a list (LPT)
+        // lanes of the same list reserve their slots with one atomic (match.any groups them)
+        {
+            const unsigned grp = __match_any_sync(FULL, bin);
+            if (bin >= 0) {
+                const int leader = __ffs(grp) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(bin_cursor + bin, (uint32_t)__popc(grp));
+                base = __shfl_sync(grp, base, leader);
+                if (mode == 1) {
+                    const uint32_t at = base + __popc(grp & ((1u << lane) - 1));
+                    MyersWork wk{pa, pb, (uint32_t)(pair_off[p] + q), 0}; work[at] = wk;
+                    work_key[at] = ((uint64_t)bin << 32) | (uint64_t)(0xffffffffu - cost);   // longest pairs first inside a list (LPT)
+                }
             }
         }
         if (mode == 0 && __any_sync(FULL, rbin >= 0)) {
@@ -407,8 +532,11 @@ __global__ void k_consolidate(const svim_csig* sig /* emission order */, const u
 }
 
 // final list order: unilocal types sorted by (contig, (end+start)/2), bilocal keep partition order
-__global__ void k_final_keys(const svim_cluster* cl, const svim_csig* sig, const uint32_t* members, uint32_t n, uint64_t* k1, uint64_t* k2, uint32_t* idx) {
+__global__ void k_final_keys(const svim_cluster* cl, const svim_csig* sig, const uint32_t* members, uint32_t n, uint64_t* k1, uint64_t* k2, uint32_t* idx, uint32_t* ncl_t) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ty = c < n ? (cl[c].type > 5 ? 5 : cl[c].type) : -1;
+    const unsigned grp = __match_any_sync(0xffffffffu, ty);
+    if (ty >= 0 && (int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(ncl_t + ty, (uint32_t)__popc(grp));
     if (c >= n) return;
     const svim_cluster x = cl[c];
     const bool uni = x.type == SVIM_DEL || x.type == SVIM_INS || x.type == SVIM_INV;
@@ -438,11 +566,16 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     const uint32_t n = (uint32_t)ctx->n_csig;
     svim_cluster_stats& cs = ctx->clstats;
     memset(&cs, 0, sizeof(cs));
-    ctx->h_clusters.clear(); ctx->h_members.clear(); ctx->h_part_off.clear(); ctx->n_partitions = 0;
+    ctx->n_clusters_host = 0; ctx->n_members_host = 0; ctx->n_partitions = 0;
     ctx->clustered = true;
     if (n == 0) { if (stats) *stats = cs; return 0; }
     ClusterParams cp{ctx->params.partition_max_distance, ctx->params.position_distance_normalizer, ctx->params.edit_distance_normalizer,
                      ctx->params.cluster_max_distance};
+    uint32_t n_clusters = 0, n_members = 0;
+    bool stop_after_partition = false;
+    // Everything up to the consolidated clusters of this rank's partitions.  In sharded mode a failure here must not return before the
+    // other ranks have been told (they would wait in the exchange for ever): the status travels with the exchange's count all-gather.
+    auto local = [&]() -> int {
     const uint32_t nb = (n + 255) / 256;
     // ---- sort by get_key -------------------------------------------------------------------------------
     uint64_t* gkey_sorted = nullptr; uint32_t* order = nullptr;
@@ -466,7 +599,6 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     const svim_csig* sorted = ctx->d_csig_sorted.as<svim_csig>();
     // ---- partitions --------------------------------------------------------------------------------------
     uint32_t P = 0;
-    uint32_t type_start[8];
     {
         StageTimer t(ctx, T_PARTITION);
         SVIM_CUDA(ctx->d_head.ensure(n + 64)); SVIM_CUDA(ctx->d_part_off.ensure((size_t)(n + 2) * 4)); SVIM_CUDA(ctx->d_part_stats.ensure(64 * 4));
@@ -478,104 +610,101 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         cub::DeviceSelect::Flagged(nullptr, tmp, cnt_it, ctx->d_head.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), d_ts + 8, (int)n, st);
         SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
         SVIM_CUDA(cub::DeviceSelect::Flagged(ctx->d_sort_tmp.p, tmp, cnt_it, ctx->d_head.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), d_ts + 8, (int)n, st));
-        uint32_t h[16];
-        SVIM_CUDA(cudaMemcpyAsync(h, d_ts, 16 * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(ctx->h_hdr.ensure((HDR_WORDS + 3 * HDR_LARGE_INLINE) * 4));
+        uint32_t* h = ctx->h_hdr.as<uint32_t>();
+        SVIM_CUDA(cudaMemcpyAsync(h, d_ts + 8, 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaStreamSynchronize(st));
-        P = h[8];
-        memcpy(type_start, h, 8 * 4);
-        ctx->h_part_off.resize(P + 1);
-        SVIM_CUDA(cudaMemcpyAsync(ctx->h_part_off.data(), ctx->d_part_off.p, (size_t)P * 4, cudaMemcpyDeviceToHost, st));
-        SVIM_CUDA(cudaStreamSynchronize(st));
-        ctx->h_part_off[P] = n;
+        P = h[0];
         ctx->n_partitions = P;
     }
-    if (partition_only) { if (stats) *stats = cs; return 0; }
-    // ---- host: sampling stream + work lists ---------------------------------------------------------------
-    // (the vectors live in the context: their capacity — and their already-faulted pages — are reused from step to step)
-    std::vector<uint32_t>& samp_off = ctx->h_samp_off; std::vector<uint32_t>& samp_idx = ctx->h_samp_idx;
-    std::vector<uint32_t>& list_small = ctx->h_list_small; std::vector<uint32_t>& list_large = ctx->h_list_large; std::vector<uint32_t>& list_ins = ctx->h_list_ins;
-    std::vector<uint64_t>& pair_off = ctx->h_pair_off; std::vector<uint8_t>& ptype = ctx->h_ptype;
-    samp_off.resize(P + 1); samp_idx.resize((size_t)n + 1); pair_off.assign(P + 1, 0); ptype.resize(P);
-    list_small.clear(); list_large.clear(); list_ins.clear();
+    if (partition_only) { stop_after_partition = true; return 0; }
+    if (shard_n > HDR_MAX_RANKS) { ctx->set_error(SVIMGPU_ERR_LIMIT, "more than %d ranks", (int)HDR_MAX_RANKS); return SVIMGPU_ERR_LIMIT; }
+    // ---- plan on the device: sample sizes, pair offsets, shard cuts, work lists; host: the sampling stream ----------------
+    uint32_t n_samp = 0, n_small = 0, n_big = 0, n_ins = 0, lo = 0, hi = P;
     uint64_t pair_total = 0;
-    int max_m_small = 32;
+    const int max_m_small = 32;
     {
         StageTimer t(ctx, T_SAMPLE);
-        PyRandom rng; int cur_type = -1;
-        int32_t pick[100];
-        uint32_t* si = samp_idx.data(); uint32_t wr = 0;     // a sample never exceeds its partition: wr <= n
-        int ty = 0;                                          // partitions come grouped by type, in type order
-        for (uint32_t p = 0; p < P; ++p) {
-            const uint32_t b = ctx->h_part_off[p], e = ctx->h_part_off[p + 1], sz = e - b;
-            while (ty < 6 && b >= type_start[ty + 1]) ++ty;
-            ptype[p] = (uint8_t)ty;
-            if (ty != cur_type) { rng.seed_int(1524); cur_type = ty; }
-            cs.n_partitions[ty > 5 ? 5 : ty]++;
-            samp_off[p] = wr;
-            uint32_t m = sz;
-            if (sz > 100) {
-                rng.sample100(sz, pick); cs.large_partitions[ty > 5 ? 5 : ty]++; m = 100;
-                for (int k = 0; k < 100; ++k) si[wr++] = b + (uint32_t)pick[k];
-            } else for (uint32_t k = 0; k < sz; ++k) si[wr++] = b + k;
-            pair_off[p] = pair_total;
-            if (ty == SVIM_INS && m > 1) { list_ins.push_back(p); pair_total += (uint64_t)m * (m - 1) / 2; }
-        }
-        samp_idx.resize(wr);
-        samp_off[P] = (uint32_t)samp_idx.size();
-        // multi-GPU: this rank clusters partitions [lo,hi) only (balanced by sum m^2 + pair cost)
-        uint32_t lo = 0, hi = P;
-        if (shard_n > 1) {
-            std::vector<double> w(P + 1, 0.0);
-            for (uint32_t p = 0; p < P; ++p) { double m = samp_off[p + 1] - samp_off[p]; w[p + 1] = w[p] + 1.0 + m * m * (ptype[p] == SVIM_INS ? 50.0 : 1.0); }
-            auto cut = [&](int r) { double target = w[P] * r / shard_n; return (uint32_t)(std::lower_bound(w.begin(), w.end(), target) - w.begin()); };
-            lo = shard_rank == 0 ? 0 : std::min(P, cut(shard_rank)); hi = shard_rank == shard_n - 1 ? P : std::min(P, cut(shard_rank + 1));
-            if (hi < lo) hi = lo;
-            std::vector<uint32_t> li;
-            for (uint32_t p : list_ins) if (p >= lo && p < hi) li.push_back(p);
-            list_ins.swap(li);
-        }
+        const uint32_t pb = (P + 1 + 255) / 256;
+        SVIM_CUDA(ctx->d_pmeta.ensure((size_t)(P + 1) * sizeof(PMeta))); SVIM_CUDA(ctx->d_ppref.ensure((size_t)(P + 1) * sizeof(PMeta)));
+        SVIM_CUDA(ctx->d_ptype.ensure(P + 16)); SVIM_CUDA(ctx->d_hdr.ensure(HDR_WORDS * 4));
+        SVIM_CUDA(ctx->d_samp_off.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_pair_off.ensure((size_t)(P + 1) * 8));
+        SVIM_CUDA(ctx->d_plist.ensure((size_t)3 * P * 4 + 16)); SVIM_CUDA(ctx->d_samp_idx.ensure((size_t)n * 4 + 4));
+        uint32_t* d_hdr = ctx->d_hdr.as<uint32_t>();
+        PMeta* meta = ctx->d_pmeta.as<PMeta>(); PMeta* pref = ctx->d_ppref.as<PMeta>();
+        SVIM_CUDA(cudaMemsetAsync(d_hdr, 0, HDR_WORDS * 4, st));
+        { ctx->launches++; k_part_meta<<<pb, 256, 0, st>>>(sorted, ctx->d_part_off.as<uint32_t>(), P, n, meta, ctx->d_ptype.as<uint8_t>(), d_hdr,
+                                                            ctx->myers_band_num, ctx->myers_band_add); }
+        size_t tmp = 0;
+        PMeta zero; zero.pairs = 0; zero.cost = 0; zero.m = 0; zero.large = 0;
+        cub::DeviceScan::ExclusiveScan(nullptr, tmp, meta, pref, PMetaSum(), zero, (int)P + 1, st);
+        SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+        SVIM_CUDA(cub::DeviceScan::ExclusiveScan(ctx->d_sort_tmp.p, tmp, meta, pref, PMetaSum(), zero, (int)P + 1, st));
+        { ctx->launches++; k_part_plan<<<1, HDR_MAX_RANKS + 1, 0, st>>>(pref, P, shard_n > 1 ? shard_rank : 0, shard_n > 1 ? shard_n : 1, d_hdr); }
+        // the list of partitions above 100 cannot be longer than n / 101
+        SVIM_CUDA(ctx->d_large_list.ensure(((size_t)n / 101 + 2) * sizeof(LargePart)));
+        { ctx->launches++; k_part_lists<<<pb, 256, 0, st>>>(meta, pref, ctx->d_ptype.as<uint8_t>(), ctx->d_part_off.as<uint32_t>(), P, n, ctx->d_samp_off.as<uint32_t>(),
+                                                             ctx->d_pair_off.as<uint64_t>(), ctx->d_large_list.as<LargePart>(), ctx->d_plist.as<uint32_t>(), d_hdr); }
+        uint32_t* h = ctx->h_hdr.as<uint32_t>();
+        SVIM_CUDA(cudaMemcpyAsync(h, d_hdr, HDR_WORDS * 4, cudaMemcpyDeviceToHost, st));
+        const size_t inline_cap = std::min<size_t>(HDR_LARGE_INLINE, (size_t)n / 101 + 1);
+        SVIM_CUDA(cudaMemcpyAsync(h + HDR_WORDS, ctx->d_large_list.p, inline_cap * sizeof(LargePart), cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        const uint32_t n_large = h[HDR_NLARGE];
+        n_samp = h[HDR_NSAMP]; pair_total = ((uint64_t)h[HDR_PAIRS + 1] << 32) | h[HDR_PAIRS];
+        lo = h[HDR_LO]; hi = h[HDR_HI]; n_small = h[HDR_NSMALL]; n_big = h[HDR_NBIG]; n_ins = h[HDR_NINS];
+        for (int ty = 0; ty < 6; ++ty) { cs.n_partitions[ty] = h[HDR_NPART_T + ty]; cs.large_partitions[ty] = h[HDR_NLARGE_T + ty]; }
         ctx->shard_lo = lo; ctx->shard_hi = hi;
-        for (uint32_t p = lo; p < hi; ++p) { uint32_t m = samp_off[p + 1] - samp_off[p]; (m <= (uint32_t)max_m_small ? list_small : list_large).push_back(p); }
+        if (n_large) {
+            SVIM_CUDA(ctx->h_picks.ensure((size_t)n_large * (100 * 4 + sizeof(LargePart))));
+            int32_t* picks = ctx->h_picks.as<int32_t>();
+            LargePart* lp = (LargePart*)(picks + (size_t)n_large * 100);
+            const uint32_t got = (uint32_t)std::min<size_t>(n_large, inline_cap);
+            memcpy(lp, h + HDR_WORDS, (size_t)got * sizeof(LargePart));
+            if (n_large > got) {
+                SVIM_CUDA(cudaMemcpyAsync(lp + got, ctx->d_large_list.as<LargePart>() + got, (size_t)(n_large - got) * sizeof(LargePart), cudaMemcpyDeviceToHost, st));
+                SVIM_CUDA(cudaStreamSynchronize(st));
+            }
+            PyRandom rng; int cur_type = -1;                 // seed(1524) once per type (:129), one sample() per partition above 100 (:133)
+            for (uint32_t k = 0; k < n_large; ++k) {
+                if ((int)lp[k].type != cur_type) { rng.seed_int(1524); cur_type = (int)lp[k].type; }
+                rng.sample100(lp[k].size, picks + (size_t)k * 100);
+            }
+            SVIM_CUDA(ctx->d_picks.ensure((size_t)n_large * 400));
+            SVIM_CUDA(cudaMemcpyAsync(ctx->d_picks.p, picks, (size_t)n_large * 400, cudaMemcpyHostToDevice, st));
+        }
+        if (hi > lo) { ctx->launches++; k_fill_samples<<<(uint32_t)(((uint64_t)(hi - lo) * 32 + 127) / 128), 128, 0, st>>>(ctx->d_part_off.as<uint32_t>(), ctx->d_samp_off.as<uint32_t>(), meta, pref, lo, hi,
+                                                                                            ctx->d_picks.as<int32_t>(), ctx->d_samp_idx.as<uint32_t>()); }
     }
-    const uint32_t n_samp = samp_off[P];
-    SVIM_CUDA(ctx->d_samp_off.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_samp_idx.ensure((size_t)n_samp * 4 + 4));
-    SVIM_CUDA(cudaMemcpyAsync(ctx->d_samp_off.p, samp_off.data(), (size_t)(P + 1) * 4, cudaMemcpyHostToDevice, st));
-    SVIM_CUDA(cudaMemcpyAsync(ctx->d_samp_idx.p, samp_idx.data(), (size_t)n_samp * 4, cudaMemcpyHostToDevice, st));
-    SVIM_CUDA(ctx->d_pair_off.ensure((size_t)(P + 1) * 8));
-    SVIM_CUDA(cudaMemcpyAsync(ctx->d_pair_off.p, pair_off.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, st));
-    // partition lists: [small | large | ins]
-    std::vector<uint32_t> lists; lists.insert(lists.end(), list_small.begin(), list_small.end());
-    lists.insert(lists.end(), list_large.begin(), list_large.end()); lists.insert(lists.end(), list_ins.begin(), list_ins.end());
-    SVIM_CUDA(ctx->d_plist.ensure(lists.size() * 4 + 4));
-    SVIM_CUDA(cudaMemcpyAsync(ctx->d_plist.p, lists.data(), lists.size() * 4, cudaMemcpyHostToDevice, st));
-    const uint32_t* d_small = ctx->d_plist.as<uint32_t>(); const uint32_t* d_large = d_small + list_small.size();
-    const uint32_t* d_ins = d_large + list_large.size();
+    const uint32_t* d_small = ctx->d_plist.as<uint32_t>(); const uint32_t* d_large = d_small + P;
+    const uint32_t* d_ins = d_large + P;
     uint32_t* d_misc = ctx->d_part_stats.as<uint32_t>();
     // ---- INS: edit distances ---------------------------------------------------------------------------------
     const int32_t* d_pair_ed = nullptr;
-    if (!list_ins.empty()) {
+    if (n_ins > 0) {
         if (pair_total >= 0xffffffffull) { ctx->set_error(SVIMGPU_ERR_LIMIT, "too many insertion pairs"); return SVIMGPU_ERR_LIMIT; }
         SVIM_CUDA(ctx->d_pair_ed.ensure((size_t)pair_total * 4 + 4));
         const int64_t maxlen = ((ctx->cluster_max_ins_len + (int64_t)ceil(fabs(2.0 * cp.cluster_max_distance * cp.pos_norm)) + 64) + 15) & ~15ll;
         GenomeView gv{ctx->d_genome.as<uint8_t>(), ctx->d_genome_off.as<int64_t>(), ctx->genome_contigs, ctx->cluster_rank_to_tid, ctx->cluster_n_ranks};
         if (!ctx->d_genome.p) { gv.n = 0; }
         SVIM_CUDA(ctx->d_myers_ctl.ensure(MYERS_CTL_N * 4));
-        uint32_t* d_ctl = ctx->d_myers_ctl.as<uint32_t>();   // [0,20) list cursors, [20,30) hand-over capacities, [32..) see MYERS_CTL_*
-        uint32_t h_ctl[32] = {0};
-        const uint32_t pblocks = (uint32_t)((list_ins.size() * 32 + 127) / 128);
+        uint32_t* d_ctl = ctx->d_myers_ctl.as<uint32_t>();   // list counts, hand-over capacities, cursors: see MYERS_CTL_* (myers.cu)
+        uint32_t h_ctl[64] = {0};
+        const uint32_t pblocks = (uint32_t)(((uint64_t)n_ins * 32 + 127) / 128);
         {
             StageTimer t(ctx, T_PAIRS);
             SVIM_CUDA(cudaMemsetAsync(d_ctl, 0, MYERS_CTL_N * 4, st));
             { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_ctl, d_ctl + 20,
-                                                ctx->myers_band_num, ctx->myers_band_add, d_misc + 9); }
-            SVIM_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, 32 * 4, cudaMemcpyDeviceToHost, st));
+                                                n_ins, ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_ctl, d_ctl + MYERS_CTL_CAP,
+                                                ctx->myers_band_num, ctx->myers_band_add, ctx->myers_tpp, d_misc + 9); }
+            SVIM_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, 64 * 4, cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
         }
         MyersPlan pl; memset(&pl, 0, sizeof(pl));
         uint32_t n_work = 0, n_banded = 0;
-        for (int q = 0; q < 2 * MYERS_BINS; ++q) { pl.cnt[q] = h_ctl[q]; pl.off[q] = n_work; n_work += h_ctl[q]; if (q >= MYERS_BINS) n_banded += h_ctl[q]; }
-        for (int bb = 0; bb < MYERS_BINS; ++bb) pl.retry_cap[bb] = h_ctl[20 + bb];
+        uint32_t n_tpp = 0;
+        for (int q = 0; q < MYERS_LISTS; ++q) { pl.cnt[q] = h_ctl[q]; pl.off[q] = n_work; n_work += h_ctl[q]; if (q >= MYERS_BINS) n_banded += h_ctl[q]; if (q >= 2 * MYERS_BINS) n_tpp += h_ctl[q]; }
+        for (int bb = 0; bb < MYERS_BINS; ++bb) pl.retry_cap[bb] = h_ctl[MYERS_CTL_CAP + bb];
         cs.myers_pairs = n_work;
         if (n_work > 0 && !ctx->d_genome.p) { ctx->set_error(SVIMGPU_ERR_STATE, "insertion clustering needs svimgpu_set_genome"); return SVIMGPU_ERR_STATE; }
         if (n_work > 0) {
@@ -585,32 +714,35 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             MyersWork* d_work = ctx->d_pairs.as<MyersWork>();
             {
                 StageTimer t(ctx, T_PAIRS);
-                SVIM_CUDA(cudaMemcpyAsync(d_ctl, pl.off, 2 * MYERS_BINS * 4, cudaMemcpyHostToDevice, st));
+                SVIM_CUDA(cudaMemcpyAsync(d_ctl, pl.off, MYERS_LISTS * 4, cudaMemcpyHostToDevice, st));
                 { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
-                                                    (uint32_t)list_ins.size(), ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_ctl, d_ctl + 20,
-                                                    ctx->myers_band_num, ctx->myers_band_add, d_misc + 9); }
+                                                    n_ins, ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_ctl, d_ctl + MYERS_CTL_CAP,
+                                                    ctx->myers_band_num, ctx->myers_band_add, ctx->myers_tpp, d_misc + 9); }
                 // longest-processing-time-first inside every list: one radix sort on (list, ~cost)
                 size_t tmp = 0;
-                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work, (int)n_work, 0, 37, st);
+                cub::DeviceRadixSort::SortPairs(nullptr, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work, (int)n_work, 0, 38, st);
                 SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
                 SVIM_CUDA(cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp, ctx->d_keys[0].as<uint64_t>(), ctx->d_keys[1].as<uint64_t>(), d_unsorted, d_work,
-                                                          (int)n_work, 0, 37, st));
+                                                          (int)n_work, 0, 38, st));
             }
             StageTimer t(ctx, T_MYERS);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
             MyersArgs ma; memset(&ma, 0, sizeof(ma));
             ma.sig = sorted; ma.ins_blob = ctx->cluster_ins; ma.g = gv; ma.ed_out = ctx->d_pair_ed.as<int32_t>(); ma.maxlen = maxlen;
             ma.fallback = d_work + n_work; ma.cells = (unsigned long long*)(d_misc + 12); ma.err = d_misc + 9;
-            ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add; ma.band_cells = (unsigned long long*)(d_ctl + 72);
+            ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;
             StringPairs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
             // the unsorted list is dead after the sort: its room takes the banded pass's hand-overs
             SVIM_CUDA(myers_run_plan<false>(ctx, pl, ma, none, d_work, nullptr, d_unsorted, d_ctl, maxlen, sms));
-            uint32_t h_retry[MYERS_BINS + 8];
+            uint32_t h_retry[MYERS_CTL_FALLBACK - MYERS_CTL_RETRY];
             SVIM_CUDA(cudaMemcpyAsync(h_retry, d_ctl + MYERS_CTL_RETRY, sizeof(h_retry), cudaMemcpyDeviceToHost, st));
             SVIM_CUDA(cudaStreamSynchronize(st));
             uint32_t n_retry = 0; for (int bb = 0; bb < MYERS_BINS; ++bb) n_retry += h_retry[bb];
-            cs.myers_banded_pairs = n_banded; cs.myers_retry_pairs = n_retry;
-            cs.myers_band_cells = (int64_t)(((uint64_t)h_retry[17] << 32) | h_retry[16]);
+            cs.myers_banded_pairs = n_banded; cs.myers_retry_pairs = n_retry; cs.myers_tpp_pairs = n_tpp;
+            uint64_t bc, tc; memcpy(&bc, h_retry + (MYERS_CTL_BANDCELLS - MYERS_CTL_RETRY), 8); memcpy(&tc, h_retry + (MYERS_CTL_TPPCELLS - MYERS_CTL_RETRY), 8);
+            cs.myers_band_cells = (int64_t)(bc + tc);        // cells the first pass computed: wavefront bands + thread-per-pair windows
+            cs.myers_tpp_cells = (int64_t)tc;
+            uint64_t uc; memcpy(&uc, h_retry + (MYERS_CTL_UNBCELLS - MYERS_CTL_RETRY), 8); cs.myers_unbanded_cells = (int64_t)uc;
         }
         d_pair_ed = ctx->d_pair_ed.as<int32_t>();
     }
@@ -620,21 +752,20 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     {
         StageTimer t(ctx, T_LINKAGE);
         LinkArgs la{sorted, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), nullptr, 0, ctx->d_pair_off.as<uint64_t>(), d_pair_ed, cp,
-                    ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_part_nkept.as<uint32_t>(), d_misc + 9};
-        if (!list_small.empty()) {
-            la.plist = d_small; la.n_list = (uint32_t)list_small.size();
+                    ctx->d_labels.as<int32_t>(), ctx->d_part_ncl.as<uint32_t>(), ctx->d_part_nkept.as<uint32_t>(), d_misc + 9, ctx->d_hdr.as<uint32_t>() + HDR_DUP_T};
+        if (n_small) {
+            la.plist = d_small; la.n_list = n_small;
             { ctx->launches++; k_linkage<<<la.n_list, 32, part_smem_bytes(max_m_small), st>>>(la, max_m_small); }
         }
-        if (!list_large.empty()) {
+        if (n_big) {
             size_t sm = part_smem_bytes(100);
             SVIM_CUDA(cudaFuncSetAttribute(k_linkage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            la.plist = d_large; la.n_list = (uint32_t)list_large.size();
+            la.plist = d_large; la.n_list = n_big;
             { ctx->launches++; k_linkage<<<la.n_list, 32, sm, st>>>(la, 100); }
         }
         SVIM_CUDA(cudaGetLastError());
     }
     // ---- consolidate ----------------------------------------------------------------------------------------------
-    uint32_t n_clusters = 0, n_members = 0;
     {
         StageTimer t(ctx, T_CONSOLIDATE);
         SVIM_CUDA(ctx->d_cl_off.ensure((size_t)(P + 1) * 4)); SVIM_CUDA(ctx->d_mem_off.ensure((size_t)(P + 1) * 4));
@@ -661,9 +792,22 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         }
         SVIM_CUDA(cudaGetLastError());
     }
-    if (shard_n > 1) { int rc = cluster_exchange(ctx, &n_clusters, &n_members); if (rc) return rc; }
+    if (shard_n > 1) {          // data errors of this shard (zero span, mixed BND directions, haplotype bound) count as a failure of the rank
+        uint32_t flag = 0;
+        SVIM_CUDA(cudaMemcpyAsync(&flag, ctx->d_part_stats.as<uint32_t>() + 9, 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaStreamSynchronize(st));
+        if (flag) { ctx->set_error(SVIMGPU_ERR_DATA, "cluster: data error %u in this rank's partitions", flag); return SVIMGPU_ERR_DATA; }
+    }
+    return 0;
+    };
+    const int rc_local = local();
+    if (stop_after_partition) { if (stats) *stats = cs; return rc_local; }
+    if (shard_n > 1) { int rc = cluster_exchange(ctx, &n_clusters, &n_members, rc_local); if (rc) return rc; }
+    else if (rc_local) return rc_local;
+    uint32_t* d_misc = ctx->d_part_stats.as<uint32_t>();
     // ---- final order + D2H -------------------------------------------------------------------------------------------
-    ctx->h_clusters.resize(n_clusters); ctx->h_members.resize(n_members);
+    SVIM_CUDA(ctx->h_clusters.ensure((size_t)(n_clusters + 1) * sizeof(svim_cluster))); SVIM_CUDA(ctx->h_members.ensure((size_t)(n_members + 1) * 4));
+    ctx->n_clusters_host = n_clusters; ctx->n_members_host = n_members;
     if (n_clusters > 0) {
         StageTimer t(ctx, T_ORDER);
         const uint32_t cb = (n_clusters + 255) / 256;
@@ -671,7 +815,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_clusters * 8));
         uint64_t* k2 = ctx->d_keys[0].as<uint64_t>();
         { ctx->launches++; k_final_keys<<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), ctx->d_csig.as<svim_csig>(), ctx->d_members.as<uint32_t>(), n_clusters,
-                                         ctx->d_ckeys[0].as<uint64_t>(), k2, ctx->d_cvals[0].as<uint32_t>()); }
+                                         ctx->d_ckeys[0].as<uint64_t>(), k2, ctx->d_cvals[0].as<uint32_t>(), ctx->d_hdr.as<uint32_t>() + HDR_NCL_T); }
         uint64_t* k_out; uint32_t* v_out;
         int rc = sort_pairs_u64(ctx, ctx->d_ckeys, ctx->d_cvals, n_clusters, 64, &k_out, &v_out); if (rc) return rc;
         { ctx->launches++; k_gather<uint64_t><<<cb, 256, 0, st>>>(k2, v_out, n_clusters, ctx->d_ckeys[1].as<uint64_t>()); }
@@ -680,14 +824,16 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         { ctx->launches++; k_gather<svim_cluster><<<cb, 256, 0, st>>>(ctx->d_clusters.as<svim_cluster>(), v_out, n_clusters, ctx->d_clusters_sorted.as<svim_cluster>()); }
         SVIM_CUDA(cudaGetLastError());
     }
+    uint32_t* hh = ctx->h_hdr.as<uint32_t>();          // [0, HDR_WORDS) plan header incl. per-type counters, then 16 words of d_misc
     {
-        StageTimer t(ctx, T_CLUSTER_D2H);
-        if (n_clusters) SVIM_CUDA(cudaMemcpyAsync(ctx->h_clusters.data(), ctx->d_clusters_sorted.p, (size_t)n_clusters * sizeof(svim_cluster), cudaMemcpyDeviceToHost, st));
-        if (n_members) SVIM_CUDA(cudaMemcpyAsync(ctx->h_members.data(), ctx->d_members.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost, st));
+        StageTimer t(ctx, T_CLUSTER_D2H);              // page-locked destinations: the copies run at PCIe rate and do not stage through the driver
+        if (n_clusters) SVIM_CUDA(cudaMemcpyAsync(ctx->h_clusters.p, ctx->d_clusters_sorted.p, (size_t)n_clusters * sizeof(svim_cluster), cudaMemcpyDeviceToHost, st));
+        if (n_members) SVIM_CUDA(cudaMemcpyAsync(ctx->h_members.p, ctx->d_members.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaMemcpyAsync(hh, ctx->d_hdr.p, HDR_WORDS * 4, cudaMemcpyDeviceToHost, st));
+        SVIM_CUDA(cudaMemcpyAsync(hh + HDR_WORDS, d_misc, 16 * 4, cudaMemcpyDeviceToHost, st));
     }
-    uint32_t h[16];
-    SVIM_CUDA(cudaMemcpyAsync(h, d_misc, 16 * 4, cudaMemcpyDeviceToHost, st));
     SVIM_CUDA(cudaStreamSynchronize(st));
+    const uint32_t* h = hh + HDR_WORDS;
     if (h[9]) {
         const char* why = h[9] == 2 ? "haplotype longer than the scratch bound" : h[9] == 3 ? "BND cluster with mixed directions (assertion in consolidate_clusters_bilocal)"
                                     : "division by zero span (ZeroDivisionError in the reference) or contig missing from the genome";
@@ -696,14 +842,8 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     }
     unsigned long long cells; memcpy(&cells, h + 12, 8);
     cs.myers_cells = (int64_t)cells;
-    for (auto& c : ctx->h_clusters) cs.n_clusters[c.type > 5 ? 5 : c.type]++;
+    for (int ty = 0; ty < 6; ++ty) { cs.n_clusters[ty] = hh[HDR_NCL_T + ty]; cs.duplicate_signatures[ty] = hh[HDR_DUP_T + ty]; }   // duplicates: this rank's partitions
     cs.n_clusters_total = n_clusters; cs.n_members = n_members;
-    // duplicate_signatures per type = sampled - kept
-    {
-        std::vector<uint32_t> nk(P + 1);
-        SVIM_CUDA(cudaMemcpy(nk.data(), ctx->d_part_nkept.p, (size_t)(P + 1) * 4, cudaMemcpyDeviceToHost));
-        for (uint32_t p = ctx->shard_lo; p < ctx->shard_hi; ++p) cs.duplicate_signatures[ptype[p] > 5 ? 5 : ptype[p]] += (samp_off[p + 1] - samp_off[p]) - nk[p];
-    }
     if (stats) *stats = cs;
     return 0;
 }

@@ -34,6 +34,22 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+struct PinBuf {     // page-locked host buffer that only grows (D2H / H2D at full PCIe rate, async on a stream)
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
 struct DevSoa {
     int64_t n;
     const int32_t* tid; const int32_t* pos; const uint16_t* flag; const uint8_t* mapq;
@@ -73,7 +89,7 @@ struct SigSet {   // one signature list on the device (main / all_bnds twins)
     int64_t n = 0, ins_bytes = 0;
 };
 
-#define SVIM_AUX_STREAMS 4
+#define SVIM_AUX_STREAMS 20     // every edit-distance bucket on its own stream: the block scheduler packs their CTAs side by side
 
 struct svimgpu_ctx {
     int device = 0;
@@ -109,6 +125,7 @@ struct svimgpu_ctx {
     bool qs_mode = false;      // query-sorted COLLECT (SVIM_COLLECT.py:96-129)
     DevBuf d_qs_info, d_qs_grp, d_qs_segsum, d_qs_mem_off, d_qs_mem_idx;
     int myers_mode = 1;        // k_myers_fast formulation (env SVIM_MYERS_MODE): 0 ALU pipe, 1 FMA pipe, 2 FMA pipe + IMAD.HI
+    int myers_tpp = 1;         // thread-per-pair banded kernels for pairs whose window fits 28 blocks (env SVIM_MYERS_TPP=0: wavefront kernels only)
     int myers_band_num = 156, myers_band_add = 20;   // banded first pass with k = m*num/1024 + add (env SVIM_MYERS_BAND=num,add; 0 = off)
     int scan_chunks = 1;       // per-warp chunked queue-slot reservation (env SVIM_SCAN_CHUNKS=0: one atomic per signature)
     int scan_variant = 0;      // 0: 128-bit LDG streaming, 1: cp.async.bulk ring (env SVIM_SCAN_VARIANT)
@@ -125,17 +142,17 @@ struct svimgpu_ctx {
     const uint8_t* cluster_ins = nullptr; int64_t cluster_ins_bytes = 0;
     int64_t n_csig = 0; bool have_csig = false;
     DevBuf d_order, d_head, d_partid, d_part_off, d_samp_off, d_samp_idx, d_labels, d_part_ncl, d_part_nkept, d_part_stats;
-    DevBuf d_plist, d_myers_scratch[24], d_myers_ctl;   // scratch: [0,10) unbanded bins, [10] 8-plane kernel, [12,22) banded shapes
+    DevBuf d_plist, d_myers_scratch[48], d_myers_ctl;   // scratch: [0,10) unbanded bins, [10] 8-plane kernel, [12,22) banded shapes, [24,42) thread-per-pair buckets
     int64_t cluster_max_ins_len = 0;
     const int32_t* cluster_rank_to_tid = nullptr; int32_t cluster_n_ranks = 0;
     DevBuf d_user_rank_to_tid;
     uint32_t shard_lo = 0, shard_hi = 0;
     DevBuf d_cl_off, d_mem_off, d_clusters, d_clusters_sorted, d_members, d_pair_off, d_pair_ed, d_pairs, d_ckeys[2], d_cvals[2];
-    std::vector<uint32_t> h_part_off, h_order_cache;
-    std::vector<uint32_t> h_samp_off, h_samp_idx, h_list_small, h_list_large, h_list_ins;   // host sampling scratch, reused
-    std::vector<uint64_t> h_pair_off; std::vector<uint8_t> h_ptype;
-    std::vector<svim_cluster> h_clusters;
-    std::vector<uint32_t> h_members;
+    // partition plan on the device (cluster.cu): per-partition scan, shard cuts, work lists; the host only sees a small header, the
+    // sizes of the partitions above 100 (it owns the sampling stream) and the final records
+    DevBuf d_pmeta, d_ppref, d_ptype, d_hdr, d_large_list, d_picks;
+    PinBuf h_hdr, h_picks, h_clusters, h_members;
+    uint32_t n_clusters_host = 0, n_members_host = 0;
     int64_t n_partitions = 0;
     svim_cluster_stats clstats;
     bool clustered = false;
@@ -146,7 +163,7 @@ struct svimgpu_ctx {
 
     // multi-GPU
     void* nccl_comm = nullptr; int nranks = 1, rank = 0;
-    DevBuf d_xchg[4];
+    DevBuf d_xchg[8];          // [0,4) gathered arrays, [4] packed send/receive slots, [5] count gather, [6] barrier word
 
     // timing
     cudaEvent_t ev[2 * T_N];

@@ -20,6 +20,7 @@
 #pragma once
 #include "ctx.cuh"
 #include "myers_band.cuh"   // bins, word steps, banded wavefront (host-checkable)
+#include "myers_tpp.cuh"    // thread-per-pair banded window (host-checkable)
 
 struct MyersWork { uint32_t a, b, slot, pad; };
 
@@ -370,6 +371,8 @@ struct MyersArgs {
     MyersWork* retry; uint32_t* n_retry; uint32_t retry_off[MYERS_BINS];
     int32_t band_num, band_add;
     unsigned long long* band_cells;           // cells the banded pass actually computed (statistics)
+    unsigned long long* tpp_cells;            // cells the thread-per-pair kernels computed (columns x 32 x window blocks)
+    unsigned long long* unb_cells;            // cells the unbanded kernels computed (full matrices: own pairs + hand-overs)
 };
 
 // explicit string pairs (unit-test entry svimgpu_edit_distance) share the kernels below through this view
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
-    if (my_cells) atomicAdd(a.cells, my_cells);
+    if (my_cells) { atomicAdd(a.cells, my_cells); if (a.unb_cells) atomicAdd(a.unb_cells, my_cells); }
 }
 
 // Banded first pass (myers_band.cuh): G lanes rotate over the word groups the band crosses, so the shape follows the
@@ -506,6 +509,169 @@ __global__ void __launch_bounds__(128, WPL <= 1 ? 8 : WPL == 2 ? 6 : WPL == 3 ? 
     if (my_band && a.band_cells) atomicAdd(a.band_cells, my_band);
 }
 
+// ---- thread-per-pair banded window (myers_tpp.cuh) -----------------------------------------------------------------------
+// A warp takes 32 pairs at a time.  Preparation is cooperative (coalesced): for each of the 32 pairs all lanes turn the
+// pattern into symbol codes and then into per-block match masks (one lane per 32-row block), and the text into pre-scaled
+// symbol bytes stored at column index j + phase; then every lane runs tpp_thread on its own pair.  Pairs holding a symbol
+// outside A/C/G/T, or not fitting this bucket after all, are handed to the unbanded kernel of their pattern's bin, and so
+// is every banded pair whose result exceeds its bound.
+template <int B>
+struct TppEq {
+    uint32_t* base;                                   // shared memory of this warp, + lane; layout [block][symbol][lane]
+    __device__ __forceinline__ void put(int slot, const uint32_t v[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) base[(slot * 4 + c) * 32] = v[c];
+    }
+    // sym = code * 32.  The load is a volatile asm so that it stays where tpp_thread puts it — TPP_AHEAD block steps before its use;
+    // left to the compiler it sinks next to the use and puts ~30 cycles of shared-memory latency on every step of the carry chain.
+    __device__ __forceinline__ uint32_t get(int slot, uint32_t sym) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sbase + (sym + slot * 128) * 4u));
+        return v;
+    }
+    uint32_t sbase;                                   // shared-window address of `base`
+    __device__ __forceinline__ void shift_up() {
+#pragma unroll
+        for (int i = 0; i + 1 < B; ++i) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) base[(i * 4 + c) * 32] = base[((i + 1) * 4 + c) * 32];
+        }
+    }
+};
+struct TppPeq {
+    const uint4* blocks; int32_t nblk;
+    __device__ __forceinline__ void block(int b, uint32_t v[4]) const {
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (b >= 0 && b < nblk) x = blocks[b];
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+    }
+};
+struct TppTxt {
+    const uint8_t* t;                                 // 4-byte aligned, index = column + phase
+    __device__ __forceinline__ uint32_t byte(int s) const { return t[s]; }
+    __device__ __forceinline__ uint32_t word(int s) const { return *(const uint32_t*)(t + s); }
+};
+
+__host__ __device__ __forceinline__ size_t tpp_pair_scratch(int64_t maxlen) {   // masks, pattern codes, text symbols of one pair
+    return (size_t)(16 * ((maxlen + 31) / 32 + 1) + ((maxlen + 32 + 15) & ~15ll) + ((maxlen + 64 + 15) & ~15ll));
+}
+
+__device__ __forceinline__ HapSource hap_bcast(const HapSource& h, int src) {
+    HapSource r;
+    r.p1 = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)h.p1, src); r.l1 = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)h.l1, src);
+    r.p2 = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)h.p2, src); r.l2 = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)h.l2, src);
+    r.p3 = (const uint8_t*)__shfl_sync(0xffffffffu, (unsigned long long)h.p3, src); r.l3 = (int64_t)__shfl_sync(0xffffffffu, (unsigned long long)h.l3, src);
+    return r;
+}
+
+// all lanes: symbol codes ((c & 0xDF) >> 1) & 3 of A/C/G/T (either case), shifted left by `shift`; returns (per lane) whether a
+// symbol outside A/C/G/T was seen
+__device__ __forceinline__ uint32_t tpp_write_codes(const HapSource& h, int32_t len, uint8_t* dst, int lane, int shift) {
+    uint32_t bad = 0;
+    const int32_t l1 = (int32_t)h.l1, l12 = (int32_t)(h.l1 + h.l2);
+    for (int32_t k0 = 0; k0 < len; k0 += 128) {
+        uint8_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t k = k0 + 32 * u + lane;
+            c[u] = 'A';
+            if (k < len) c[u] = k < l1 ? h.p1[k] : (k < l12 ? h.p2[k - l1] : h.p3[k - l12]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int32_t k = k0 + 32 * u + lane;
+            const uint32_t up = c[u] & 0xDFu;
+            bad |= (uint32_t)!(up == 'A' || up == 'C' || up == 'G' || up == 'T');
+            if (k < len) dst[k] = (uint8_t)(((up >> 1) & 3u) << shift);
+        }
+    }
+    return bad;
+}
+
+// one lane: match masks of pattern block `blk` from its 32 symbol codes (16-byte aligned)
+__device__ __forceinline__ uint4 tpp_block_masks(const uint8_t* codes, int32_t m, int32_t blk) {
+    const uint4 lo = *(const uint4*)(codes + 32 * blk), hi = *(const uint4*)(codes + 32 * blk + 16);
+    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t p0 = 0, p1 = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {   // bit 0 / bit 1 of the four code bytes of w[q] -> four adjacent bits (multiply-gather)
+        p0 |= ((((w[q]) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
+        p1 |= ((((w[q] >> 1) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
+    }
+    const int32_t cnt = m - 32 * blk;
+    const uint32_t real = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    return make_uint4(~p0 & ~p1 & real, p0 & ~p1 & real, ~p0 & p1 & real, p0 & p1 & real);
+}
+
+#ifndef TPP_MINB
+#define TPP_MINB(B) ((B) <= 8 ? 8 : (B) <= 12 ? 6 : (B) <= 20 ? 5 : 4)      // CTAs per SM the register budget is cut for
+#endif
+template <int B, bool STRINGS, bool HI>
+__global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, StringPairs sp) {
+    extern __shared__ __align__(16) uint32_t tpp_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t per_pair = tpp_pair_scratch(a.maxlen);
+    uint8_t* wscr = a.scratch + (size_t)warp * 32 * per_pair;
+    const size_t off_codes = (size_t)16 * ((a.maxlen + 31) / 32 + 1), off_txt = off_codes + (size_t)((a.maxlen + 32 + 15) & ~15ll);
+    TppEq<B> eq; eq.base = tpp_smem + wib * (B * 128) + lane; eq.sbase = (uint32_t)__cvta_generic_to_shared(eq.base);
+    unsigned long long my_cells = 0, my_comp = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.next, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.n_work) break;
+        const uint32_t w = base + lane;
+        bool valid = w < a.n_work;
+        MyersWork wk{0, 0, 0, 0};
+        HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
+        if (valid) valid = myers_load_pair<STRINGS>(a, sp, w, wk, ha, hb, 0);
+        const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
+        if (valid && (la > a.maxlen || lb > a.maxlen)) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; valid = false; }
+        if (valid && (la == 0 || lb == 0)) { a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
+        const bool a_is_pat = la >= lb;
+        const HapSource& hp = a_is_pat ? ha : hb;
+        const HapSource& ht = a_is_pat ? hb : ha;
+        const int32_t m = (int32_t)(a_is_pat ? la : lb), n = (int32_t)(a_is_pat ? lb : la);
+        const TppPlan plan = tpp_plan(valid ? m : 1, valid ? n : 1, a.band_num, a.band_add);
+        const int64_t k = myers_band_k(m, n, a.band_num, a.band_add);
+        const int rbin = myers_bin_of(m);
+        bool hand_over = valid && plan.B > B;            // not a pair of this bucket after all
+        const int32_t phase = plan.a >= 0 ? ((-plan.a) & 31) : 0;
+        // ---- cooperative preparation of the 32 pairs --------------------------------------------------------
+        const uint32_t todo = __ballot_sync(0xffffffffu, valid && !hand_over);
+        for (uint32_t rest = todo; rest; rest &= rest - 1) {
+            const int p = __ffs(rest) - 1;
+            const HapSource pp = hap_bcast(hp, p), pt = hap_bcast(ht, p);
+            const int32_t pm = __shfl_sync(0xffffffffu, m, p), pn = __shfl_sync(0xffffffffu, n, p), pph = __shfl_sync(0xffffffffu, phase, p);
+            uint8_t* slot = wscr + (size_t)p * per_pair;
+            uint32_t bad = tpp_write_codes(pp, pm, slot + off_codes, lane, 0);
+            bad |= tpp_write_codes(pt, pn, slot + off_txt + pph, lane, 5);
+            __syncwarp();
+            const int32_t nblk = (pm + 31) >> 5;
+            for (int32_t blk = lane; blk < nblk; blk += 32) ((uint4*)slot)[blk] = tpp_block_masks(slot + off_codes, pm, blk);
+            if (__any_sync(0xffffffffu, bad) && lane == p) hand_over = true;
+        }
+        __syncwarp();
+        if (hand_over) { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; valid = false; }
+        // ---- one pair per lane ------------------------------------------------------------------------------------
+        if (valid) {
+            const uint8_t* slot = wscr + (size_t)lane * per_pair;
+            TppPeq peq{(const uint4*)slot, (m + 31) >> 5};
+            TppTxt txt{slot + off_txt};
+            const int32_t ed = tpp_thread<B, HI>(m, n, plan.a, eq, peq, txt, a.one, a.two);
+            my_comp += (unsigned long long)n * (unsigned long long)(32 * B);
+            if (plan.a < 0 || ed <= k) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
+            else { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { my_cells += __shfl_xor_sync(0xffffffffu, my_cells, o); my_comp += __shfl_xor_sync(0xffffffffu, my_comp, o); }
+    if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
+    if (lane == 0 && my_comp && a.tpp_cells) atomicAdd(a.tpp_cells, my_comp);
+}
+
 // any bytes: 8 bit-planes, a warp per pair, 4 words per lane, strip-mined
 template <bool STRINGS>
 __global__ void __launch_bounds__(128) k_myers_generic(MyersArgs a, StringPairs sp) {
@@ -539,7 +705,7 @@ __global__ void __launch_bounds__(128) k_myers_generic(MyersArgs a, StringPairs 
         if (lane == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
-    if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
+    if (lane == 0 && my_cells) { atomicAdd(a.cells, my_cells); if (a.unb_cells) atomicAdd(a.unb_cells, my_cells); }
 }
 
 // the Myers bins run on SVIM_AUX_STREAMS side streams: fork from / join to the context's main stream
@@ -638,14 +804,66 @@ static cudaError_t myers_launch_band(svimgpu_ctx* ctx, int bin, MyersArgs a, Str
     return cudaGetLastError();
 }
 
+// longest pattern a pair of TPP bucket q can have under the band policy (bounds the per-pair scratch)
+static int64_t tpp_bucket_maxlen(int q, int64_t maxlen, int32_t num, int32_t add) {
+    const int64_t B = tpp_bucket_B(q);
+    int64_t cap = 32 * B;                                             // unbanded pairs of the bucket
+    if (num > 0) {
+        const int64_t K = 32 * B - 31;                                // banded: a + b <= 32B - 32, a + b in {k-1, k}
+        if (K >= add) cap = std::max<int64_t>(cap, ((K - add + 1) * 1024 + num - 1) / num + 1);
+    }
+    return std::min<int64_t>(maxlen, cap + 64);
+}
+
+template <bool STRINGS>
+static cudaError_t myers_launch_tpp(svimgpu_ctx* ctx, int q, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
+    if (a.n_work == 0) return cudaSuccess;
+    const int B = tpp_bucket_B(q);
+    a.maxlen = (tpp_bucket_maxlen(q, a.maxlen, a.band_num, a.band_add) + 15) & ~15ll;
+    const int occ = B <= 8 ? 8 : B <= 12 ? 6 : B <= 20 ? 5 : 4;
+    int blocks = sms * occ;
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 127) / 128);
+    const size_t per_warp = (size_t)32 * tpp_pair_scratch(a.maxlen);
+    while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)8 << 30)) blocks -= sms;
+    cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
+    if (e != cudaSuccess) return e;
+    a.scratch = scratch.as<uint8_t>();
+    a.extra = nullptr; a.n_extra = nullptr;
+    ctx->launches++;
+    cudaStream_t stream = ctx->aux_stream[q % SVIM_AUX_STREAMS];
+    a.one = 1u; a.two = 2u;
+    const size_t smem = (size_t)4 * B * 128 * 4;
+#define TPP_LAUNCH(B_)                                                                                                     \
+    case B_:                                                                                                              \
+        if (ctx->myers_mode == 2) {                                                                                       \
+            e = cudaFuncSetAttribute(k_myers_tpp<B_, STRINGS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) k_myers_tpp<B_, STRINGS, true><<<blocks, 128, smem, stream>>>(a, sp);                    \
+        } else {                                                                                                          \
+            e = cudaFuncSetAttribute(k_myers_tpp<B_, STRINGS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e == cudaSuccess) k_myers_tpp<B_, STRINGS, false><<<blocks, 128, smem, stream>>>(a, sp);                   \
+        }                                                                                                                 \
+        break;
+    switch (B) {
+        TPP_LAUNCH(2) TPP_LAUNCH(3) TPP_LAUNCH(4) TPP_LAUNCH(5) TPP_LAUNCH(6) TPP_LAUNCH(7) TPP_LAUNCH(8) TPP_LAUNCH(9) TPP_LAUNCH(10)
+        TPP_LAUNCH(12) TPP_LAUNCH(14) TPP_LAUNCH(16) TPP_LAUNCH(18) TPP_LAUNCH(20) TPP_LAUNCH(22) TPP_LAUNCH(24) TPP_LAUNCH(26) TPP_LAUNCH(28)
+        default: return cudaErrorInvalidValue;
+    }
+#undef TPP_LAUNCH
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
 // ---- the whole edit-distance stage: banded shapes first, then the unbanded bins (their own pairs + the banded pass's
 // hand-overs), then the 8-plane kernel for pairs with symbols outside the code space -------------------------------------
+#define MYERS_LISTS (2 * MYERS_BINS + TPP_BUCKETS)
 struct MyersPlan {
-    uint32_t cnt[2 * MYERS_BINS];     // first-pass items: [0,10) unbanded bins, [10,20) banded shapes
-    uint32_t off[2 * MYERS_BINS];     // their offsets in the work list (pipeline) / index list (string pairs)
-    uint32_t retry_cap[MYERS_BINS];   // banded items whose pattern belongs to each unbanded bin
+    uint32_t cnt[MYERS_LISTS];        // first-pass items: [0,10) unbanded bins, [10,20) banded wavefront shapes, [20,38) thread-per-pair buckets
+    uint32_t off[MYERS_LISTS];        // their offsets in the work list (pipeline) / index list (string pairs)
+    uint32_t retry_cap[MYERS_BINS];   // banded / thread-per-pair items whose pattern belongs to each unbanded bin
 };
-enum { MYERS_CTL_CURSOR = 32, MYERS_CTL_RETRY = 56, MYERS_CTL_FALLBACK = 70, MYERS_CTL_N = 128 };
+// control words on the device: [0, MYERS_LISTS) list counts of k_ins_pairs, [MYERS_CTL_CAP, +10) hand-over capacities,
+// [MYERS_CTL_CURSOR, +MYERS_LISTS+1) work cursors, [MYERS_CTL_RETRY, +10) hand-over counts, then 64-bit statistics
+enum { MYERS_CTL_CAP = 40, MYERS_CTL_CURSOR = 64, MYERS_CTL_RETRY = 112, MYERS_CTL_BANDCELLS = 128, MYERS_CTL_TPPCELLS = 130, MYERS_CTL_UNBCELLS = 132, MYERS_CTL_FALLBACK = 136,
+       MYERS_CTL_N = 160 };
 
 // ctl: MYERS_CTL_N device words; retry: room for sum(retry_cap) items; ma carries sig/ins/genome, ed_out, fallback list,
 // cells / band_cells / err pointers and the band policy.  Synchronises ctx->stream.
@@ -659,8 +877,16 @@ static cudaError_t myers_run_plan(svimgpu_ctx* ctx, const MyersPlan& pl, MyersAr
     ma.n_fallback = ctl + MYERS_CTL_FALLBACK; ma.n_retry = ctl + MYERS_CTL_RETRY; ma.retry = retry;
     uint32_t acc = 0, n_banded = 0;
     for (int bb = 0; bb < MYERS_BINS; ++bb) { ma.retry_off[bb] = acc; acc += pl.retry_cap[bb]; n_banded += pl.cnt[MYERS_BINS + bb]; }
+    for (int q = 0; q < TPP_BUCKETS; ++q) n_banded += pl.cnt[2 * MYERS_BINS + q];
+    ma.band_cells = (unsigned long long*)(ctl + MYERS_CTL_BANDCELLS); ma.tpp_cells = (unsigned long long*)(ctl + MYERS_CTL_TPPCELLS); ma.unb_cells = (unsigned long long*)(ctl + MYERS_CTL_UNBCELLS);
     if (n_banded > 0) {
         chk(myers_fork(ctx));
+        for (int q = TPP_BUCKETS - 1; q >= 0 && e == cudaSuccess; --q) {      // widest windows first: their batches run longest
+            const int li = 2 * MYERS_BINS + q;
+            ma.work = work ? work + pl.off[li] : nullptr; sp.list = list ? list + pl.off[li] : nullptr;
+            ma.n_work = pl.cnt[li]; ma.next = ctl + MYERS_CTL_CURSOR + li; ma.maxlen = maxlen; ma.extra = nullptr; ma.n_extra = nullptr;
+            chk(myers_launch_tpp<STRINGS>(ctx, q, ma, sp, ctx->d_myers_scratch[24 + q], sms));
+        }
         for (int bb = MYERS_BINS - 1; bb >= 0 && e == cudaSuccess; --bb) {
             const int q = MYERS_BINS + bb;
             ma.work = work ? work + pl.off[q] : nullptr; sp.list = list ? list + pl.off[q] : nullptr;
@@ -683,7 +909,7 @@ static cudaError_t myers_run_plan(svimgpu_ctx* ctx, const MyersPlan& pl, MyersAr
     chk(cudaStreamSynchronize(st));
     if (e == cudaSuccess && n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
         sp.list = nullptr;
-        ma.work = ma.fallback; ma.n_work = n_fb; ma.next = ctl + MYERS_CTL_CURSOR + 2 * MYERS_BINS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
+        ma.work = ma.fallback; ma.n_work = n_fb; ma.next = ctl + MYERS_CTL_CURSOR + MYERS_LISTS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;
         ma.extra = nullptr; ma.n_extra = nullptr;
         chk(myers_fork(ctx));
         chk(myers_launch_bin<STRINGS>(ctx, MYERS_BINS, ma, sp, ctx->d_myers_scratch[MYERS_BINS], sms));

@@ -30,6 +30,19 @@ static inline void mb_add64(uint32_t al, uint32_t bl, uint32_t ah, uint32_t bh, 
     sl = (uint32_t)s; sh = (uint32_t)(s >> 32);
 }
 static inline int mb_popcll(uint64_t x) { return __builtin_popcountll(x); }
+static inline int mb_popc(uint32_t x) { return __builtin_popcount(x); }
+template <int LUT> static inline uint32_t mb_lop3(uint32_t a, uint32_t b, uint32_t c) {      // truth table: a = 0xF0, b = 0xCC, c = 0xAA
+    uint32_t r = 0;
+    if (LUT & 0x80) r |= a & b & c;
+    if (LUT & 0x40) r |= a & b & ~c;
+    if (LUT & 0x20) r |= a & ~b & c;
+    if (LUT & 0x10) r |= a & ~b & ~c;
+    if (LUT & 0x08) r |= ~a & b & c;
+    if (LUT & 0x04) r |= ~a & b & ~c;
+    if (LUT & 0x02) r |= ~a & ~b & c;
+    if (LUT & 0x01) r |= ~a & ~b & ~c;
+    return r;
+}
 static inline const uint8_t* mb_ptr_inc(const uint8_t* p, uint32_t) { return p + 1; }
 #else
 __device__ __forceinline__ uint32_t mb_imad(uint32_t a, uint32_t b, uint32_t c) {
@@ -43,6 +56,12 @@ __device__ __forceinline__ void mb_add64(uint32_t al, uint32_t bl, uint32_t ah, 
     asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, %5;" : "=r"(sl), "=r"(sh) : "r"(al), "r"(bl), "r"(ah), "r"(bh));
 }
 __device__ __forceinline__ int mb_popcll(uint64_t x) { return __popcll(x); }
+__device__ __forceinline__ int mb_popc(uint32_t x) { return __popc(x); }
+template <int LUT> __device__ __forceinline__ uint32_t mb_lop3(uint32_t a, uint32_t b, uint32_t c) {   // one LOP3, as written
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+    return d;
+}
 // p + 1 as IMAD.WIDE (FMA pipe; `one` is a kernel argument the compiler cannot fold)
 __device__ __forceinline__ const uint8_t* mb_ptr_inc(const uint8_t* p, uint32_t one) {
     unsigned long long q = (unsigned long long)p;

@@ -25,8 +25,8 @@ static void nccl_teardown(svimgpu_ctx* ctx) {
 
 // all-gather `count` int64 values per rank (host in/out through a device bounce buffer)
 static int nccl_allgather_i64(svimgpu_ctx* ctx, const int64_t* mine, int count, int64_t* all) {
-    SVIM_CUDA(ctx->d_xchg[3].ensure((size_t)(ctx->nranks + 1) * count * 8));
-    int64_t* d = ctx->d_xchg[3].as<int64_t>();
+    SVIM_CUDA(ctx->d_xchg[5].ensure((size_t)(ctx->nranks + 1) * count * 8));
+    int64_t* d = ctx->d_xchg[5].as<int64_t>();
     SVIM_CUDA(cudaMemcpyAsync(d + (size_t)ctx->nranks * count, mine, (size_t)count * 8, cudaMemcpyHostToDevice, ctx->stream));
     SVIM_NCCL(ncclAllGather(d + (size_t)ctx->nranks * count, d, (size_t)count, ncclInt64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     SVIM_CUDA(cudaMemcpyAsync(all, d, (size_t)ctx->nranks * count * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -34,15 +34,35 @@ static int nccl_allgather_i64(svimgpu_ctx* ctx, const int64_t* mine, int count, 
     return 0;
 }
 
-// dst[off[r] .. off[r]+bytes[r]) <- rank r's src, for every r
-static int nccl_allgatherv_bytes(svimgpu_ctx* ctx, const void* src, const std::vector<int64_t>& bytes, const std::vector<int64_t>& off, uint8_t* dst) {
-    SVIM_NCCL(ncclGroupStart());
-    for (int r = 0; r < ctx->nranks; ++r) {
-        if (bytes[r] == 0) continue;
-        const void* s = (r == ctx->rank) ? src : (const void*)(dst + off[r]);
-        SVIM_NCCL(ncclBroadcast(s, dst + off[r], (size_t)bytes[r], ncclUint8, r, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+// Variable-size all-gather of K byte arrays per rank with ONE collective: the K arrays of a rank are packed back to back into a
+// send slot padded to the largest rank's total, one ncclAllGather moves all slots (NCCL's tuned ring / NVLS path instead of R
+// grouped broadcasts), and device-to-device copies lay every array out contiguously in rank order.
+//   bytes[r*K + k] : size of array k on rank r (from the count all-gather)     src[k] : this rank's arrays
+//   dst[k]         : receives rank 0's array k, rank 1's array k, ...  (caller sized it)
+static int nccl_allgatherv_packed(svimgpu_ctx* ctx, int K, const void* const* src, const int64_t* bytes, uint8_t* const* dst) {
+    const int R = ctx->nranks;
+    auto pad = [](int64_t x) { return (x + 15) & ~15ll; };
+    int64_t slot = 16;
+    for (int r = 0; r < R; ++r) { int64_t t = 0; for (int k = 0; k < K; ++k) t += pad(bytes[r * K + k]); slot = std::max(slot, t); }
+    SVIM_CUDA(ctx->d_xchg[4].ensure((size_t)slot * (R + 1) + 64));
+    uint8_t* recv = ctx->d_xchg[4].as<uint8_t>();
+    uint8_t* send = recv + (size_t)slot * R;
+    int64_t at = 0;
+    for (int k = 0; k < K; ++k) {
+        const int64_t b = bytes[ctx->rank * K + k];
+        if (b) SVIM_CUDA(cudaMemcpyAsync(send + at, src[k], (size_t)b, cudaMemcpyDeviceToDevice, ctx->stream));
+        at += pad(b);
     }
-    SVIM_NCCL(ncclGroupEnd());
+    SVIM_NCCL(ncclAllGather(send, recv, (size_t)slot, ncclUint8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    std::vector<int64_t> out_at(K, 0);
+    for (int r = 0; r < R; ++r) {
+        int64_t in_at = 0;
+        for (int k = 0; k < K; ++k) {
+            const int64_t b = bytes[r * K + k];
+            if (b) SVIM_CUDA(cudaMemcpyAsync(dst[k] + out_at[k], recv + (size_t)slot * r + in_at, (size_t)b, cudaMemcpyDeviceToDevice, ctx->stream));
+            in_at += pad(b); out_at[k] += b;
+        }
+    }
     return 0;
 }
 
@@ -58,22 +78,33 @@ __global__ void k_rebase_clusters(svim_cluster* c, uint32_t n, uint32_t mem_add)
     if (k < n) c[k].member_off += mem_add;
 }
 
-static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_members) {
-    if (!ctx->nccl_comm) { ctx->set_error(SVIMGPU_ERR_STATE, "svimgpu_comm_init not called"); return SVIMGPU_ERR_STATE; }
+// all-gather-v of this rank's cluster records + member indices; `local_status` != 0 (this rank failed before the exchange) is
+// agreed on first, so that either every rank enters the payload gather or none does
+static int cluster_exchange(svimgpu_ctx* ctx, uint32_t* n_clusters, uint32_t* n_members, int local_status) {
+    if (!ctx->nccl_comm) { if (local_status) return local_status; ctx->set_error(SVIMGPU_ERR_STATE, "svimgpu_comm_init not called"); return SVIMGPU_ERR_STATE; }
     StageTimer t(ctx, T_EXCHANGE);
     const int R = ctx->nranks;
-    int64_t mine[2] = {(int64_t)*n_clusters, (int64_t)*n_members};
-    std::vector<int64_t> all(2 * R);
-    int rc = nccl_allgather_i64(ctx, mine, 2, all.data()); if (rc) return rc;
-    std::vector<int64_t> cb(R), co(R), mb(R), mo(R);
-    int64_t ct = 0, mt = 0;
-    for (int r = 0; r < R; ++r) { co[r] = ct * (int64_t)sizeof(svim_cluster); cb[r] = all[2 * r] * (int64_t)sizeof(svim_cluster); mo[r] = mt * 4; mb[r] = all[2 * r + 1] * 4; ct += all[2 * r]; mt += all[2 * r + 1]; }
+    int64_t mine[3] = {(int64_t)*n_clusters, (int64_t)*n_members, (int64_t)local_status};
+    std::vector<int64_t> all(3 * R);
+    int rc = nccl_allgather_i64(ctx, mine, 3, all.data()); if (rc) return local_status ? local_status : rc;
+    for (int r = 0; r < R; ++r)
+        if (all[3 * r + 2]) {
+            if (!local_status) ctx->set_error(SVIMGPU_ERR_PEER, "cluster: rank %d failed with status %lld; no rank keeps a result", r, (long long)all[3 * r + 2]);
+            return local_status ? local_status : SVIMGPU_ERR_PEER;
+        }
+    std::vector<int64_t> bytes(2 * R);
+    int64_t ct = 0, mt = 0, my_mem_base = 0;
+    for (int r = 0; r < R; ++r) {
+        bytes[2 * r] = all[3 * r] * (int64_t)sizeof(svim_cluster); bytes[2 * r + 1] = all[3 * r + 1] * 4;
+        if (r < ctx->rank) my_mem_base += all[3 * r + 1];
+        ct += all[3 * r]; mt += all[3 * r + 1];
+    }
     // rebase this rank's member offsets to the global member array, then gather both arrays
-    const uint32_t my_mem_base = (uint32_t)(mo[ctx->rank] / 4);
-    if (*n_clusters) { ctx->launches++; k_rebase_clusters<<<(*n_clusters + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_clusters.as<svim_cluster>(), *n_clusters, my_mem_base); }
+    if (*n_clusters) { ctx->launches++; k_rebase_clusters<<<(*n_clusters + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_clusters.as<svim_cluster>(), *n_clusters, (uint32_t)my_mem_base); }
     SVIM_CUDA(ctx->d_xchg[0].ensure((size_t)(ct + 1) * sizeof(svim_cluster))); SVIM_CUDA(ctx->d_xchg[1].ensure((size_t)(mt + 1) * 4));
-    rc = nccl_allgatherv_bytes(ctx, ctx->d_clusters.p, cb, co, ctx->d_xchg[0].as<uint8_t>()); if (rc) return rc;
-    rc = nccl_allgatherv_bytes(ctx, ctx->d_members.p, mb, mo, ctx->d_xchg[1].as<uint8_t>()); if (rc) return rc;
+    const void* src[2] = {ctx->d_clusters.p, ctx->d_members.p};
+    uint8_t* dst[2] = {ctx->d_xchg[0].as<uint8_t>(), ctx->d_xchg[1].as<uint8_t>()};
+    rc = nccl_allgatherv_packed(ctx, 2, src, bytes.data(), dst); if (rc) return rc;
     std::swap(ctx->d_clusters, ctx->d_xchg[0]); std::swap(ctx->d_members, ctx->d_xchg[1]);
     SVIM_CUDA(ctx->d_clusters_sorted.ensure((size_t)(ct + 1) * sizeof(svim_cluster)));
     *n_clusters = (uint32_t)ct; *n_members = (uint32_t)mt;
@@ -120,23 +151,29 @@ int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collec
                             ctx->cstats.n_sa_bad_fields, ctx->cstats.n_no_read_length, ctx->cstats.n_primaries, ctx->cstats.n_data_errors, 0, 0, 0};
         std::vector<int64_t> all(12 * R);
         int rc = nccl_allgather_i64(ctx, mine, 12, all.data()); if (rc) return rc;
+        // both lists (main, --all_bnds twins), records and INS blobs: four arrays per rank, one collective
+        std::vector<int64_t> bytes(4 * R);
+        int64_t nt[2] = {0, 0}, it[2] = {0, 0}, my_blob_base[2] = {0, 0};
+        for (int r = 0; r < R; ++r)
+            for (int w = 0; w < 2; ++w) {
+                bytes[4 * r + 2 * w] = all[12 * r + 2 * w] * (int64_t)sizeof(svim_sig); bytes[4 * r + 2 * w + 1] = all[12 * r + 2 * w + 1];
+                if (r < ctx->rank) my_blob_base[w] += all[12 * r + 2 * w + 1];
+                nt[w] += all[12 * r + 2 * w]; it[w] += all[12 * r + 2 * w + 1];
+            }
+        const void* src[4]; uint8_t* dst[4];
         for (int w = 0; w < 2; ++w) {
             SigSet& set = ctx->sets[w];
-            std::vector<int64_t> rb(R), ro(R), ib(R), io(R);
-            int64_t nt = 0, it = 0;
-            for (int r = 0; r < R; ++r) {
-                ro[r] = nt * (int64_t)sizeof(svim_sig); rb[r] = all[12 * r + 2 * w] * (int64_t)sizeof(svim_sig);
-                io[r] = it; ib[r] = all[12 * r + 2 * w + 1];
-                nt += all[12 * r + 2 * w]; it += all[12 * r + 2 * w + 1];
-            }
             // make local records global before sending: record index += aln_base, INS offset += blob base
-            if (set.n) { ctx->launches++; k_rebase_sigs<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, aln_base, (uint64_t)io[ctx->rank]); }
-            SVIM_CUDA(ctx->d_xchg[0].ensure((size_t)(nt + 1) * sizeof(svim_sig))); SVIM_CUDA(ctx->d_xchg[1].ensure((size_t)it + 16));
-            rc = nccl_allgatherv_bytes(ctx, set.recs.p, rb, ro, ctx->d_xchg[0].as<uint8_t>()); if (rc) return rc;
-            rc = nccl_allgatherv_bytes(ctx, set.ins.p, ib, io, ctx->d_xchg[1].as<uint8_t>()); if (rc) return rc;
-            SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
-            std::swap(set.recs, ctx->d_xchg[0]); std::swap(set.ins, ctx->d_xchg[1]);
-            set.n = nt; set.ins_bytes = it;
+            if (set.n) { ctx->launches++; k_rebase_sigs<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, aln_base, (uint64_t)my_blob_base[w]); }
+            SVIM_CUDA(ctx->d_xchg[2 * w].ensure((size_t)(nt[w] + 1) * sizeof(svim_sig))); SVIM_CUDA(ctx->d_xchg[2 * w + 1].ensure((size_t)it[w] + 16));
+            src[2 * w] = set.recs.p; src[2 * w + 1] = set.ins.p;
+            dst[2 * w] = ctx->d_xchg[2 * w].as<uint8_t>(); dst[2 * w + 1] = ctx->d_xchg[2 * w + 1].as<uint8_t>();
+        }
+        rc = nccl_allgatherv_packed(ctx, 4, src, bytes.data(), dst); if (rc) return rc;
+        for (int w = 0; w < 2; ++w) {
+            SigSet& set = ctx->sets[w];
+            std::swap(set.recs, ctx->d_xchg[2 * w]); std::swap(set.ins, ctx->d_xchg[2 * w + 1]);
+            set.n = nt[w]; set.ins_bytes = it[w];
         }
         svim_collect_stats& s = ctx->cstats;
         s.n_signatures = ctx->sets[0].n; s.ins_bytes = ctx->sets[0].ins_bytes; s.n_twin_signatures = ctx->sets[1].n; s.twin_ins_bytes = ctx->sets[1].ins_bytes;
@@ -153,10 +190,10 @@ int svimgpu_barrier_max(svimgpu_ctx* ctx, double* value) {
     if (!ctx || !value) return SVIMGPU_ERR_ARG;
     if (!ctx->nccl_comm) return 0;
     cudaSetDevice(ctx->device);
-    SVIM_CUDA(ctx->d_xchg[2].ensure(16));
-    SVIM_CUDA(cudaMemcpyAsync(ctx->d_xchg[2].p, value, 8, cudaMemcpyHostToDevice, ctx->stream));
-    SVIM_NCCL(ncclAllReduce(ctx->d_xchg[2].p, ctx->d_xchg[2].p, 1, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-    SVIM_CUDA(cudaMemcpyAsync(value, ctx->d_xchg[2].p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(ctx->d_xchg[6].ensure(16));
+    SVIM_CUDA(cudaMemcpyAsync(ctx->d_xchg[6].p, value, 8, cudaMemcpyHostToDevice, ctx->stream));
+    SVIM_NCCL(ncclAllReduce(ctx->d_xchg[6].p, ctx->d_xchg[6].p, 1, ncclDouble, ncclMax, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    SVIM_CUDA(cudaMemcpyAsync(value, ctx->d_xchg[6].p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

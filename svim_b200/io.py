@@ -156,7 +156,8 @@ _bamio = None
 def build_bamio(force: bool = False) -> str:
     import subprocess
     if force or not os.path.exists(_BAMIO_SO) or (os.path.exists(_BAMIO_SRC) and os.path.getmtime(_BAMIO_SO) < os.path.getmtime(_BAMIO_SRC)):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", _BAMIO_SO, _BAMIO_SRC, "-lz"])
+        from .build import run_atomic
+        run_atomic(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", "@OUT@", _BAMIO_SRC, "-lz"], _BAMIO_SO)
     return _BAMIO_SO
 
 
@@ -245,10 +246,10 @@ def build_bamgpu(force: bool = False) -> str:
     import subprocess
     deps = [_BAMGPU_SRC, os.path.join(os.path.dirname(_BAMGPU_SRC), "bgzf_core.cuh")]
     if force or not os.path.exists(_BAMGPU_SO) or any(os.path.getmtime(_BAMGPU_SO) < os.path.getmtime(d) for d in deps):
-        from .build import nvcc_path
-        subprocess.check_call([nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
-                               "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static",
-                               "-o", _BAMGPU_SO, _BAMGPU_SRC])
+        from .build import nvcc_path, run_atomic
+        run_atomic([nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
+                    "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static",
+                    "-o", "@OUT@", _BAMGPU_SRC], _BAMGPU_SO)
     return _BAMGPU_SO
 
 
@@ -360,9 +361,10 @@ def write_bam_native(path: str, batch: AlignmentBatch, level: int = 1, threads: 
 
 def read_bam(path: str) -> AlignmentBatch:
     """Native multi-threaded reader when g++/zlib are available, else the pure-Python one below."""
+    import subprocess
     try:
         return read_bam_native(path)
-    except (OSError, ImportError, FileNotFoundError) as e:     # toolchain missing: fall back to the Python decoder
+    except (OSError, ImportError, FileNotFoundError, subprocess.SubprocessError) as e:     # toolchain missing or the build failed: fall back to the Python decoder
         if isinstance(e, FileNotFoundError) and not os.path.exists(path):
             raise
         return read_bam_python(path)

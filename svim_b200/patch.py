@@ -22,9 +22,20 @@ def install():
     from . import SVIM_COLLECT, SVIM_CLUSTER
     from .io import read_alignments
 
+    def bam_path(bam, options):
+        # `bam` is the pysam.AlignmentFile the CLI opened (svim:91; in `reads` mode svim:80,87 open the aligner's output and
+        # there is no options.bam_file): decode the same file into the flattened buffer
+        name = getattr(bam, "filename", None)
+        if isinstance(name, bytes):
+            name = name.decode()
+        if not name:
+            name = getattr(options, "bam_file", None)
+        if not name:
+            raise ValueError("svim_b200.patch: cannot tell which alignment file the AlignmentFile object reads")
+        return name
+
     def analyze_alignment_file_coordsorted(bam, options):
-        # `bam` is the pysam.AlignmentFile the CLI opened; decode the same file into the flattened buffer
-        return SVIM_COLLECT.analyze_alignment_file_coordsorted(read_alignments(options.bam_file), options)
+        return SVIM_COLLECT.analyze_alignment_file_coordsorted(read_alignments(bam_path(bam, options)), options)
 
     ref_collect.analyze_alignment_file_coordsorted = analyze_alignment_file_coordsorted
     ref_cluster.cluster_sv_signatures = SVIM_CLUSTER.cluster_sv_signatures
@@ -35,7 +46,7 @@ def install():
     def genotype(candidates, bam, type, options):
         # the flattened buffer of the same file is still resident from COLLECT; `bam` (pysam) is not read again
         batch = getattr(runtime.context(), "resident", None)
-        return SVIM_genotyping.genotype(candidates, batch if batch is not None else read_alignments(options.bam_file), type, options)
+        return SVIM_genotyping.genotype(candidates, batch if batch is not None else read_alignments(bam_path(bam, options)), type, options)
 
     ref_genotyping.genotype = genotype
 

@@ -23,7 +23,8 @@ _SRC = os.path.join(_HERE, "synth.cpp")
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or (os.path.exists(_SRC) and os.path.getmtime(_SO) < os.path.getmtime(_SRC)):
-        subprocess.check_call(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", _SO, _SRC])
+        from ..build import run_atomic
+        run_atomic(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-std=c++17", "-o", "@OUT@", _SRC], _SO)
     return _SO
 
 

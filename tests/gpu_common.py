@@ -6,55 +6,7 @@ import numpy as np
 
 from svim_b200 import _lib
 
-SIG_FIELDS = ("type", "contig", "start", "end", "contig2", "pos", "dir1", "dir2", "direction", "copies", "fully_covered",
-              "signature", "read", "sequence")
-TYPES_RETURN_ORDER = ("DEL", "INS", "INV", "DUP_TAN", "DUP_INT", "BND")
-
-
-def sig_rows(sigs, ins, batch):
-    """svim_sig records -> golden-style rows (list per signature, field order of oracle.Sig.__slots__)."""
-    names = batch.contig_names
-    blob = ins.tobytes()
-    rows = []
-    for s in sigs:
-        t = _lib.TYPE_NAMES[s["type"]]
-        fl = int(s["flags"])
-        d = dict.fromkeys(SIG_FIELDS)
-        d.update(type=t, contig=names[s["contig1"]], start=int(s["start"]), end=int(s["end"]),
-                 signature="suppl" if fl & 1 else "cigar", read=batch.qname(int(s["qname_id"])))
-        if t == "INS":
-            d["sequence"] = blob[int(s["seq_off"]):int(s["seq_off"]) + int(s["seq_len"])].decode("ascii")
-        elif t == "INV":
-            d["direction"] = _lib.INV_DIRECTIONS[(fl >> 4) & 7]
-        elif t == "DUP_TAN":
-            d.update(copies=int(s["copies"]), fully_covered=bool(fl & 2))
-        elif t == "DUP_INT":
-            d.update(contig2=names[s["contig2"]], pos=int(s["pos"]))
-        elif t == "BND":
-            d.update(contig2=names[s["contig2"]], pos=int(s["pos"]), dir1="rev" if fl & 4 else "fwd", dir2="rev" if fl & 8 else "fwd")
-        rows.append([d[f] for f in SIG_FIELDS])
-    return rows
-
-
-def cluster_rows(clusters, members, sig_rows_list):
-    """svim_cluster records -> {type: [golden-style cluster rows]}"""
-    out = {t: [] for t in TYPES_RETURN_ORDER}
-    mem = members.tolist()
-    for c in clusters:
-        t = _lib.TYPE_NAMES[c["type"]]
-        ms = mem[int(c["member_off"]):int(c["member_off"]) + int(c["size"])]
-        first = sig_rows_list[ms[0]]
-        sd_span = None if math.isnan(c["std_span"]) else float(c["std_span"])
-        sd_pos = None if math.isnan(c["std_pos"]) else float(c["std_pos"])
-        row = [t, first[1], int(c["start"]), int(c["end"]), None, None, None, float(c["score"]), int(c["size"]), sd_span, sd_pos, None, None, ms]
-        if t == "DUP_TAN":
-            row[4:7] = [first[1], int(c["dest_start"]), int(c["dest_end"])]
-        elif t in ("DUP_INT", "BND"):
-            row[4:7] = [first[4], int(c["dest_start"]), int(c["dest_end"])]
-            if t == "BND":
-                row[11:13] = ["rev" if c["dir1_rev"] else "fwd", "rev" if c["dir2_rev"] else "fwd"]
-        out[t].append(row)
-    return out
+from svim_b200.rows import SIG_FIELDS, TYPES_RETURN_ORDER, sig_rows, cluster_rows  # noqa: F401,E402
 
 
 def assert_clusters_equal(got, want, float_tol=1e-6):

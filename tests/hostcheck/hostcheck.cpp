@@ -103,6 +103,58 @@ int hc_myers_band_bin(long long m, long long n, int num, int add) { return myers
 long long hc_myers_band_k(long long m, long long n, int num, int add) { return myers_band_k(m, n, num, add); }
 }
 
+// ---- thread-per-pair banded Myers (myers_tpp.cuh): the per-thread program of k_myers_tpp, run on the host ------------------
+#include "../../svim_b200/csrc/myers_tpp.cuh"
+
+template <int B> struct HostEq {
+    uint32_t v[B][4];
+    void put(int slot, const uint32_t x[4]) { for (int c = 0; c < 4; ++c) v[slot][c] = x[c]; }
+    uint32_t get(int slot, uint32_t sym) const { return v[slot][sym >> 5]; }          // symbols arrive pre-scaled by 32
+    void shift_up() { for (int i = 0; i + 1 < B; ++i) for (int c = 0; c < 4; ++c) v[i][c] = v[i + 1][c]; }
+};
+struct HostPeq {
+    const uint8_t* pat; long long m;
+    void block(int b, uint32_t v[4]) const {
+        v[0] = v[1] = v[2] = v[3] = 0u;
+        if (b < 0 || 32ll * b >= m) return;
+        const long long left = m - 32ll * b;
+        tpp_masks_from_codes(pat + 32ll * b, (int)(left < 32 ? left : 32), v);
+    }
+};
+struct HostTxt {
+    std::vector<uint8_t> t;     // index s = j + phase, symbol * 32
+    uint32_t byte(int s) const { return t[s]; }
+    uint32_t word(int s) const { return (uint32_t)t[s] | ((uint32_t)t[s + 1] << 8) | ((uint32_t)t[s + 2] << 16) | ((uint32_t)t[s + 3] << 24); }
+};
+template <int B>
+static long long tpp_emulate(const uint8_t* pat, long long m, const uint8_t* txt, long long n, int a) {
+    HostEq<B> eq; HostPeq peq{pat, m}; HostTxt tx;
+    const int phase = a >= 0 ? ((-a) & 31) : 0;
+    tx.t.assign((size_t)(phase + n + 8), 0);
+    for (long long j = 0; j < n; ++j) tx.t[(size_t)(phase + j)] = (uint8_t)(txt[j] * 32);
+    return tpp_thread<B, false>((int32_t)m, (int32_t)n, a, eq, peq, tx, 1u, 2u) ;
+}
+extern "C" {
+// pat/txt: symbol codes 0..3, m >= n >= 1.  k < 0: unbanded.  Runs in the smallest bucket that holds the pair (or `force_B` blocks);
+// returns the result (exact iff unbanded or <= k), -1 if no bucket holds it, -2 on bad arguments.
+long long hc_myers_tpp(const uint8_t* pat, long long m, const uint8_t* txt, long long n, long long k, int force_B) {
+    if (m < n || n < 1 || (k >= 0 && k < m - n)) return -2;
+    int a = -1; long long B = tpp_blocks_full(m);
+    if (k >= 0) { B = tpp_blocks_band(m, n, k); a = (int)((k - (m - n)) / 2); }
+    if (force_B > 0) { if (force_B < B) return -1; B = force_B; }
+    const int q = tpp_bucket_of((int)(B > 1000 ? 1000 : B));
+    if (q < 0) return -1;
+    switch (tpp_bucket_B(q)) {
+#define HC_TPP(B_) case B_: return tpp_emulate<B_>(pat, m, txt, n, a);
+        HC_TPP(2) HC_TPP(3) HC_TPP(4) HC_TPP(5) HC_TPP(6) HC_TPP(7) HC_TPP(8) HC_TPP(9) HC_TPP(10) HC_TPP(12) HC_TPP(14) HC_TPP(16)
+        HC_TPP(18) HC_TPP(20) HC_TPP(22) HC_TPP(24) HC_TPP(26) HC_TPP(28)
+#undef HC_TPP
+    }
+    return -1;
+}
+int hc_tpp_plan(long long m, long long n, int num, int add, int* a_out) { const TppPlan p = tpp_plan(m, n, num, add); *a_out = p.a; return p.B; }
+}
+
 // ---- groundwork for the on-GPU BAM decoder (csrc_next/bgzf_core.cuh): raw DEFLATE of a BGZF payload, record-start search ----
 #include "../../svim_b200/csrc_next/bgzf_core.cuh"
 extern "C" {

@@ -116,7 +116,7 @@ def test_fasta_fetch_clamps(tmp_path):
 def hc():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
-    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh")] + \
+    deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh", "myers_tpp.cuh")] + \
            [os.path.join(ROOT, "svim_b200", "csrc_next", "bgzf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
@@ -378,6 +378,65 @@ def test_banded_wavefront_host_replay(hc):
     # the policy: k = m*num/1024 + add, no banded pass when k < m - n or when no smaller shape holds the band
     assert hc.hc_myers_band_k(1000, 1000, 174, 24) == 193 and hc.hc_myers_band_k(1000, 500, 174, 24) == -1 and hc.hc_myers_band_k(1000, 1000, 0, 24) == -1
     assert hc.hc_myers_band_bin(4000, 3990, 174, 24) == 3 and hc.hc_myers_band_bin(200, 200, 174, 24) == -1
+
+
+def test_thread_per_pair_band_host_replay(hc):
+    """myers_tpp.cuh: the per-thread program of k_myers_tpp (sliding window of B 32-row blocks, D0-form block step, phase-shifted
+    columns, virtual rows above and below the pattern) run on the host:  unbanded => exact;  banded: result <= k => exact,
+    result > k => distance > k; in the smallest bucket and in wider ones."""
+    hc.hc_myers_tpp.restype = ctypes.c_longlong
+    hc.hc_myers_tpp.argtypes = [ctypes.c_char_p, ctypes.c_longlong, ctypes.c_char_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int]
+    hc.hc_tpp_plan.argtypes = [ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    rng = random.Random(11)
+    code = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+    def enc(s):
+        return bytes(code[c] for c in s)
+
+    def mutate(s, rate):
+        out = []
+        for ch in s:
+            r = rng.random()
+            if r < rate / 3:
+                continue
+            if r < 2 * rate / 3:
+                out.append(rng.choice("ACGT")); continue
+            out.append(ch)
+            if r < rate:
+                out.append(rng.choice("ACGT"))
+        return "".join(out)
+    exact = bounded = unbanded = 0
+    for it in range(160):
+        L = rng.choice([1, 2, 30, 31, 32, 33, 63, 64, 65, 128, 200, 257, 500, 700, 895, 896, 897, 1000, 1500, 2200, 3000])
+        a = "".join(rng.choice("ACGT") for _ in range(L))
+        b = mutate(a, rng.choice([0, 0.02, 0.1, 0.2, 0.4, 0.8])) or "A"
+        if rng.random() < 0.2:
+            b = b[rng.randint(0, len(b) // 3):] or "A"
+        if rng.random() < 0.15:
+            b = "".join(rng.choice("ACGT") for _ in range(rng.randint(1, 40))) + b     # a shifted diagonal
+        pat, txt = (a, b) if len(a) >= len(b) else (b, a)
+        m, n = len(pat), len(txt)
+        d = editdist.edit_distance(pat, txt)
+        r = hc.hc_myers_tpp(enc(pat), m, enc(txt), n, -1, 0)
+        if r != -1:
+            assert r == d, ("unbanded", m, n, r, d); unbanded += 1
+            if m <= 32 * 20:
+                assert hc.hc_myers_tpp(enc(pat), m, enc(txt), n, -1, 28) == d
+        for k in sorted({m - n, max(m - n, d - 1), max(m - n, d), d + 1, d + 9, max(m - n, d // 2), 2 * d + 3, max(m - n, (m * 156 >> 10) + 20)}):
+            for force in (0, 12, 28):
+                r = hc.hc_myers_tpp(enc(pat), m, enc(txt), n, k, force)
+                if r == -1:
+                    continue            # no bucket holds the band
+                assert r >= 0
+                if r <= k:
+                    assert r == d, (m, n, k, force, r, d); exact += 1
+                else:
+                    assert d > k, (m, n, k, force, r, d); bounded += 1
+    assert exact > 1000 and bounded > 300 and unbanded > 60
+    a_out = ctypes.c_int(0)
+    assert hc.hc_tpp_plan(1000, 1000, 156, 20, ctypes.byref(a_out)) == 7 and a_out.value == 86       # k = 172: 7 blocks instead of 32
+    assert hc.hc_tpp_plan(60, 55, 156, 20, ctypes.byref(a_out)) == 2 and a_out.value == -1           # whole pattern in 2 blocks: unbanded
+    assert hc.hc_tpp_plan(1000, 500, 156, 20, ctypes.byref(a_out)) == 32 and a_out.value == -1        # k < m - n: no band
 
 
 def test_candidate_arrays_from_clusters_matches_naive():
@@ -835,3 +894,88 @@ def test_bam_long_cigar_cg_tag_roundtrip(tmp_path):
     # the record core really carries the placeholder (what a reader without CG support would see)
     raw = sio._bgzf_inflate_all(p1)
     assert raw.count(b"CGBI") == 2
+
+
+# ---- host mirror: object building in C, CLI writers ------------------------------------------------------------------
+def _random_sig_records(n, seed=5):
+    from svim_b200 import _lib
+    rng = np.random.default_rng(seed)
+    sigs = np.zeros(n, dtype=_lib.SIG_DTYPE)
+    sigs["type"] = rng.integers(0, 6, n); sigs["start"] = rng.integers(0, 1 << 28, n); sigs["end"] = sigs["start"] + rng.integers(0, 5000, n)
+    sigs["pos"] = rng.integers(0, 1 << 28, n); sigs["contig1"] = rng.integers(0, 3, n); sigs["contig2"] = rng.integers(0, 3, n)
+    sigs["qname_id"] = rng.integers(0, 500, n); sigs["flags"] = rng.integers(0, 256, n) & 0x4f; sigs["copies"] = rng.integers(1, 5, n)
+    lens = np.where(sigs["type"] == 1, rng.integers(0, 300, n), 0)
+    sigs["seq_len"] = lens; sigs["seq_off"] = np.concatenate([[0], np.cumsum(lens)])[:-1]
+    ins = rng.choice(np.frombuffer(b"ACGTNacgt=", dtype=np.uint8), size=int(lens.sum()))
+    return sigs, ins, rng
+
+
+def _slots_of(o):
+    d = {k: getattr(o, k) for c in type(o).__mro__ for k in getattr(c, "__slots__", ()) if k != "__dict__" and hasattr(o, k)}
+    d.update(getattr(o, "__dict__", {})); d["type"] = o.type; d["class"] = type(o).__name__
+    return d
+
+
+def test_c_object_builder_equals_python_builder():
+    """svim_b200/csrc_host/fastobj.c (what analyze_alignment_file_coordsorted / cluster_sv_signatures return) against the same
+    marshalling written in Python: every attribute of every object, the per-type cluster lists and their member identity."""
+    from svim_b200 import _lib
+    from svim_b200.SVIM_COLLECT import materialize_signatures, materialize_signatures_py
+    from svim_b200.SVIM_clustering import build_clusters, build_clusters_py
+
+    class Batch:
+        contig_names = ["chr1", "chr10", "chr2"]
+        qnames = ["q%d" % i for i in range(500)]
+
+        def qname(self, i):
+            return self.qnames[i] if self.qnames is not None else "read%d" % i
+    sigs, ins, rng = _random_sig_records(4000)
+    for named in (True, False):
+        b = Batch()
+        if not named:
+            b.qnames = None
+        got = materialize_signatures(sigs, ins, b); want = materialize_signatures_py(sigs, ins, b)
+        assert len(got) == len(want) and all(_slots_of(x) == _slots_of(y) for x, y in zip(got, want))
+    got[0].anything = 3                       # downstream code may attach attributes (plain classes in the reference)
+    assert got[0].anything == 3 and got[0].get_key()[0] == got[0].type
+    nc = 700
+    cl = np.zeros(nc, dtype=_lib.CLUSTER_DTYPE)
+    sizes = rng.integers(1, 12, nc); off = np.concatenate([[0], np.cumsum(sizes)])
+    members = rng.integers(0, len(sigs), int(off[-1])).astype(np.uint32)
+    cl["size"] = sizes; cl["member_off"] = off[:-1]; cl["type"] = sigs["type"][members[off[:-1]]]
+    cl["start"] = rng.integers(0, 1 << 40, nc); cl["end"] = cl["start"] + 7; cl["dest_start"] = rng.integers(0, 1 << 40, nc); cl["dest_end"] = cl["dest_start"] + 3
+    cl["score"] = rng.random(nc); cl["std_span"] = np.where(sizes > 1, rng.random(nc), np.nan); cl["std_pos"] = np.where(sizes > 1, rng.random(nc), np.nan)
+    cl["dir1_rev"] = rng.integers(0, 2, nc); cl["dir2_rev"] = rng.integers(0, 2, nc)
+    a = build_clusters(cl, members, got); p = build_clusters_py(cl, members, got)
+    for t in range(6):
+        assert len(a[t]) == len(p[t])
+        for x, y in zip(a[t], p[t]):
+            dx, dy = _slots_of(x), _slots_of(y)
+            assert [id(m) for m in dx.pop("members")] == [id(m) for m in dy.pop("members")] and dx == dy
+    assert isinstance(a[0], list) and a[4][0].direction1 in ("fwd", "rev")
+    with pytest.raises((ValueError, IndexError)):
+        bad = cl.copy(); bad["member_off"][0] = len(members); build_clusters(bad, members, got)
+
+
+def test_cli_writes_the_reference_file_set(tmp_path):
+    """`python -m svim_b200 alignment` writes signatures/{del,ins,inv,dup_tan_source,dup_tan_dest,dup_int,trans}.bed and all.vcf;
+    tests/golden/cli_signatures/ holds what the reference's own writers (SVIM_CLUSTER.py:29-107) produce for these clusters."""
+    from svim_b200.SVSignature import (SignatureDeletion, SignatureInsertion, SignatureInversion, SignatureDuplicationTandem, SignatureInsertionFrom,
+                                       SignatureTranslocation, SignatureClusterUniLocal as U, SignatureClusterBiLocal as Bi)
+    from svim_b200.__main__ import write_cluster_beds, write_cluster_vcf
+    d1 = SignatureDeletion("chr2", 100, 200, "cigar", "r1"); d2 = SignatureDeletion("chr10", 50, 90, "suppl", "r2")
+    i1 = SignatureInsertion("chr1", 10, 60, "cigar", "r3", "ACGT" * 12)
+    v1 = SignatureInversion("chr1", 500, 900, "suppl", "r4", "left_fwd")
+    t1 = SignatureDuplicationTandem("chr1", 1000, 1500, 2, True, "suppl", "r5")
+    f1 = SignatureInsertionFrom("chr1", 100, 300, "chr2", 700, "suppl", "r6")
+    b1 = SignatureTranslocation("chr1", 100, "fwd", "chr2", 700, "rev", "suppl", "r7")
+    clusters = ([U("chr2", 100, 200, 3.5, 2, [d1, d1], "DEL", 1.5, 2.5), U("chr10", 50, 90, 1.0, 1, [d2], "DEL", None, None)],
+                [U("chr1", 10, 60, 1.0, 1, [i1], "INS", None, None)], [U("chr1", 500, 900, 1.0, 1, [v1], "INV", None, None)],
+                [Bi("chr1", 1000, 1500, "chr1", 1500, 2500, 2.0, 1, [t1], "DUP_TAN", None, None), Bi("chr1", 10, 15, "chr1", 15, 25, 2.0, 1, [t1], "DUP_TAN", 0.5, 0.25)],
+                [Bi("chr1", 100, 300, "chr2", 700, 900, 1.0, 1, [f1], "DUP_INT", None, None)],
+                [Bi("chr1", 100, 101, "chr2", 700, 701, 1.0, 1, [b1], "BND", None, None)])
+    write_cluster_beds(str(tmp_path), clusters); write_cluster_vcf(str(tmp_path), clusters)
+    gold = os.path.join(ROOT, "tests", "golden", "cli_signatures")
+    assert sorted(os.listdir(tmp_path / "signatures")) == sorted(os.listdir(gold))
+    for f in os.listdir(gold):
+        assert (tmp_path / "signatures" / f).read_text() == open(os.path.join(gold, f)).read(), f

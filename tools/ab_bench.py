@@ -24,7 +24,7 @@ def main():
     alg_bytes = batch.algorithmic_bytes()
     for setting in args.settings:
         env = dict(kv.split("=") for kv in setting.split("+") if kv)
-        for k in ("SVIM_MYERS_MODE", "SVIM_MYERS_BAND", "SVIM_SCAN_VARIANT", "SVIM_SCAN_CHUNKS"):
+        for k in ("SVIM_MYERS_MODE", "SVIM_MYERS_BAND", "SVIM_MYERS_TPP", "SVIM_SCAN_VARIANT", "SVIM_SCAN_CHUNKS"):
             os.environ.pop(k, None)
         os.environ.update(env)
         ctx = _lib.Context(device=0)
@@ -45,7 +45,7 @@ def main():
                           "scan_GBps": round((alg_bytes + cst.n_signatures * 48) / scan / 1e6, 1),
                           "myers_ms": round(float(np.mean(stages.get("myers_edit_distance", [float("nan")]))), 3),
                           "pairs": int(clst.myers_pairs), "banded": int(clst.myers_banded_pairs), "retry": int(clst.myers_retry_pairs),
-                          "band_cells_frac": round(clst.myers_band_cells / max(1, clst.myers_cells), 4), "signatures": int(cst.n_signatures), "clusters": int(len(clusters)), "digest": digest}), flush=True)
+                          "tpp_pairs": int(clst.myers_tpp_pairs), "tpp_cells": int(clst.myers_tpp_cells), "band_cells": int(clst.myers_band_cells), "band_cells_frac": round(clst.myers_band_cells / max(1, clst.myers_cells), 4), "signatures": int(cst.n_signatures), "clusters": int(len(clusters)), "digest": digest}), flush=True)
         del ctx
 
 
