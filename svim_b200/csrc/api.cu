@@ -46,6 +46,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (const char* v = getenv("SVIM_SCAN_CHUNKS")) ctx->scan_chunks = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_MODE")) ctx->myers_mode = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_TPP")) ctx->myers_tpp = atoi(v);
+    if (const char* v = getenv("SVIM_MYERS_TRACE")) ctx->myers_trace = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_BAND")) { int num = 0, add = 24; if (sscanf(v, "%d,%d", &num, &add) >= 1) { ctx->myers_band_num = num; ctx->myers_band_add = add; } }
     *out = ctx;
     return 0;
@@ -64,7 +65,7 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
                       &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
                       &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3], &ctx->d_xchg[4], &ctx->d_xchg[5], &ctx->d_xchg[6], &ctx->d_xchg[7],
-                      &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
+                      &ctx->d_genome_codes, &ctx->d_ins_codes, &ctx->d_myers_trace, &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
     for (int i = 0; i < 48; ++i) ctx->d_myers_scratch[i].release();
@@ -132,6 +133,10 @@ int svimgpu_set_genome(svimgpu_ctx* ctx, int32_t n, const int64_t* offsets, cons
     SVIM_CUDA(cudaMemcpy(ctx->d_genome.p, bytes, (size_t)offsets[n], cudaMemcpyHostToDevice));
     SVIM_CUDA(cudaMemcpy(ctx->d_genome_off.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice));
     ctx->genome_bytes = offsets[n]; ctx->genome_contigs = n;
+    // symbol-code image for the thread-per-pair edit-distance kernels (myers.cu, k_tpp_encode): once per genome
+    SVIM_CUDA(ctx->d_genome_codes.ensure((size_t)offsets[n] + 16));
+    if (offsets[n] > 0) { ctx->launches++; k_tpp_encode<<<(unsigned)(((size_t)offsets[n] + 16 * 256 - 1) / (16 * 256)), 256, 0, ctx->stream>>>(ctx->d_genome.as<uint8_t>(), offsets[n], ctx->d_genome_codes.as<uint8_t>()); }
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -478,15 +483,16 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
     maxlen = (maxlen + 15) & ~15ll;
     std::vector<uint32_t> flat; flat.reserve((size_t)n_pairs);
     for (int q = 0; q < MYERS_LISTS; ++q) { pl.off[q] = (uint32_t)flat.size(); pl.cnt[q] = (uint32_t)lists[q].size(); flat.insert(flat.end(), lists[q].begin(), lists[q].end()); }
-    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_ctl, d_list, d_fb, d_retry, d_misc;
+    DevBuf d_blob, d_ao, d_al, d_bo, d_bl, d_out, d_ctl, d_list, d_fb, d_retry, d_misc, d_codes;
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    chk(d_blob.ensure((size_t)blob_bytes + 16)); chk(d_ao.ensure((size_t)n_pairs * 8)); chk(d_al.ensure((size_t)n_pairs * 4)); chk(d_bo.ensure((size_t)n_pairs * 8));
+    chk(d_blob.ensure((size_t)blob_bytes + 16)); chk(d_codes.ensure((size_t)blob_bytes + 16)); chk(d_ao.ensure((size_t)n_pairs * 8)); chk(d_al.ensure((size_t)n_pairs * 4)); chk(d_bo.ensure((size_t)n_pairs * 8));
     chk(d_bl.ensure((size_t)n_pairs * 4)); chk(d_out.ensure((size_t)n_pairs * 4)); chk(d_ctl.ensure(MYERS_CTL_N * 4)); chk(d_list.ensure((size_t)n_pairs * 4));
     chk(d_fb.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_retry.ensure((size_t)n_pairs * sizeof(MyersWork))); chk(d_misc.ensure(64));
     uint32_t h_err = 0;
     if (e == cudaSuccess) {
         chk(cudaMemcpyAsync(d_blob.p, blob, (size_t)blob_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (blob_bytes > 0) k_tpp_encode<<<(unsigned)(((size_t)blob_bytes + 16 * 256 - 1) / (16 * 256)), 256, 0, ctx->stream>>>(d_blob.as<uint8_t>(), blob_bytes, d_codes.as<uint8_t>());
         chk(cudaMemcpyAsync(d_ao.p, a_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_al.p, a_len, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, ctx->stream));
         chk(cudaMemcpyAsync(d_bo.p, b_off, (size_t)n_pairs * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -497,13 +503,14 @@ int svimgpu_edit_distance(svimgpu_ctx* ctx, int64_t n_pairs, const uint8_t* blob
         ma.ed_out = d_out.as<int32_t>(); ma.maxlen = maxlen; ma.fallback = d_fb.as<MyersWork>();
         ma.cells = (unsigned long long*)d_misc.p; ma.err = (uint32_t*)d_misc.p + 4;
         ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;
+        ma.str_codes = d_codes.as<uint8_t>(); ma.ins_base = d_blob.as<uint8_t>();
         StringPairs sp{d_blob.as<uint8_t>(), d_ao.as<int64_t>(), d_al.as<int32_t>(), d_bo.as<int64_t>(), d_bl.as<int32_t>(), nullptr};
         chk(myers_run_plan<true>(ctx, pl, ma, sp, nullptr, d_list.as<uint32_t>(), d_retry.as<MyersWork>(), d_ctl.as<uint32_t>(), maxlen, 148));
         chk(cudaMemcpyAsync(out, d_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaMemcpyAsync(&h_err, (uint32_t*)d_misc.p + 4, 4, cudaMemcpyDeviceToHost, ctx->stream));
         chk(cudaStreamSynchronize(ctx->stream));
     }
-    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_ctl, &d_list, &d_fb, &d_retry, &d_misc};
+    DevBuf* all[] = {&d_blob, &d_ao, &d_al, &d_bo, &d_bl, &d_out, &d_ctl, &d_list, &d_fb, &d_retry, &d_misc, &d_codes};
     for (DevBuf* b : all) b->release();
     if (e != cudaSuccess) { ctx->set_error(SVIMGPU_ERR_CUDA, "edit_distance: %s", cudaGetErrorString(e)); return SVIMGPU_ERR_CUDA; }
     if (h_err) { ctx->set_error(SVIMGPU_ERR_LIMIT, "edit_distance: internal length bound exceeded (%u)", h_err); return SVIMGPU_ERR_LIMIT; }

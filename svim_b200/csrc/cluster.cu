@@ -728,6 +728,10 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             StageTimer t(ctx, T_MYERS);
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
             MyersArgs ma; memset(&ma, 0, sizeof(ma));
+            // symbol-code image of the INS blob for the thread-per-pair kernels (the genome's is built by svimgpu_set_genome)
+            SVIM_CUDA(ctx->d_ins_codes.ensure((size_t)ctx->cluster_ins_bytes + 16));
+            if (ctx->cluster_ins_bytes > 0) { ctx->launches++; k_tpp_encode<<<(unsigned)(((size_t)ctx->cluster_ins_bytes + 16 * 256 - 1) / (16 * 256)), 256, 0, st>>>(ctx->cluster_ins, ctx->cluster_ins_bytes, ctx->d_ins_codes.as<uint8_t>()); }
+            ma.genome_codes = ctx->d_genome_codes.as<uint8_t>(); ma.ins_codes = ctx->d_ins_codes.as<uint8_t>(); ma.ins_base = ctx->cluster_ins;
             ma.sig = sorted; ma.ins_blob = ctx->cluster_ins; ma.g = gv; ma.ed_out = ctx->d_pair_ed.as<int32_t>(); ma.maxlen = maxlen;
             ma.fallback = d_work + n_work; ma.cells = (unsigned long long*)(d_misc + 12); ma.err = d_misc + 9;
             ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;

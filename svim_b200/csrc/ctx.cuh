@@ -104,7 +104,7 @@ struct svimgpu_ctx {
     int32_t n_contigs = 0;
     std::vector<int32_t> h_rank, h_rank_to_tid;
     DevBuf d_names, d_name_off, d_rank, d_rank_to_tid;
-    DevBuf d_genome, d_genome_off;
+    DevBuf d_genome, d_genome_off, d_genome_codes, d_ins_codes;     // *_codes: k_tpp_encode images for the thread-per-pair kernels
     int64_t genome_bytes = 0;
     int32_t genome_contigs = 0;
 
@@ -125,6 +125,8 @@ struct svimgpu_ctx {
     bool qs_mode = false;      // query-sorted COLLECT (SVIM_COLLECT.py:96-129)
     DevBuf d_qs_info, d_qs_grp, d_qs_segsum, d_qs_mem_off, d_qs_mem_idx;
     int myers_mode = 1;        // k_myers_fast formulation (env SVIM_MYERS_MODE): 0 ALU pipe, 1 FMA pipe, 2 FMA pipe + IMAD.HI
+    int myers_trace = 0;       // env SVIM_MYERS_TRACE=1: per-launch start/end times of the edit-distance kernels on stderr
+    DevBuf d_myers_trace;
     int myers_tpp = 1;         // thread-per-pair banded kernels for pairs whose window fits 28 blocks (env SVIM_MYERS_TPP=0: wavefront kernels only)
     int myers_band_num = 156, myers_band_add = 20;   // banded first pass with k = m*num/1024 + add (env SVIM_MYERS_BAND=num,add; 0 = off)
     int scan_chunks = 1;       // per-warp chunked queue-slot reservation (env SVIM_SCAN_CHUNKS=0: one atomic per signature)

@@ -32,6 +32,36 @@ struct HapSource {
 
 struct GenomeView { const uint8_t* bytes; const int64_t* off; int32_t n; const int32_t* rank_to_tid; int32_t n_ranks; };
 
+// Symbol codes of the thread-per-pair kernels: ((c & 0xDF) >> 1 & 3) << 5 for A/C/G/T in either case (the value Eq is indexed
+// with), bit 7 set for any other byte.  The genome is encoded once per upload, the INS blob once per cluster call; a pair's two
+// haplotypes are then assembled from code bytes by plain copies (k_myers_tpp), instead of classifying every base of every pair again.
+__global__ void k_tpp_encode(const uint8_t* __restrict__ src, int64_t n, uint8_t* __restrict__ dst) {
+    const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    if (i0 + 16 <= n && (((uintptr_t)(src + i0) | (uintptr_t)(dst + i0)) & 15) == 0) {
+        const uint4 v = *(const uint4*)(src + i0);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w}, o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const uint32_t up = (w[q] >> (8 * b)) & 0xDFu;
+                const uint32_t ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+                r |= ((((up >> 1) & 3u) << 5) | (ok ? 0u : 0x80u)) << (8 * b);
+            }
+            o[q] = r;
+        }
+        *(uint4*)(dst + i0) = make_uint4(o[0], o[1], o[2], o[3]);
+        return;
+    }
+    for (int64_t i = i0; i < n && i < i0 + 16; ++i) {
+        const uint32_t up = src[i] & 0xDFu;
+        const uint32_t ok = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+        dst[i] = (uint8_t)((((up >> 1) & 3u) << 5) | (ok ? 0u : 0x80u));
+    }
+}
+
 __constant__ uint8_t c_symcode[256];
 
 static void myers_init_symcode() {
@@ -373,6 +403,12 @@ struct MyersArgs {
     unsigned long long* band_cells;           // cells the banded pass actually computed (statistics)
     unsigned long long* tpp_cells;            // cells the thread-per-pair kernels computed (columns x 32 x window blocks)
     unsigned long long* unb_cells;            // cells the unbanded kernels computed (full matrices: own pairs + hand-overs)
+    // second wave (pairs the first pass handed over): MyersWork.pad == 1 marks a pair holding symbols outside A/C/G/T.
+    uint32_t tpp_second;                      // k_myers_tpp: take the `extra` list, run every unmarked pair unbanded
+    unsigned long long* trace;                // debug (SVIM_MYERS_TRACE=1): [2k] first start / [2k+1] last end of launch k, %globaltimer ns
+    uint32_t trace_slot;
+    const uint8_t* genome_codes; const uint8_t* ins_codes; const uint8_t* ins_base; const uint8_t* str_codes;   // k_tpp_encode images of g.bytes / the INS blob / the string blob
+    uint32_t extra_marked_only;               // k_myers_fast: of the `extra` list take only the marked pairs
 };
 
 // explicit string pairs (unit-test entry svimgpu_edit_distance) share the kernels below through this view
@@ -400,6 +436,7 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), grp = lane / G;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     uint8_t* my = a.scratch + ((size_t)warp * GPW + grp) * 6 * a.maxlen;
+    if (a.trace && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(a.trace + 2 * a.trace_slot, t); }
     unsigned long long my_cells = 0;
     const uint32_t n_total = a.n_work + (a.n_extra ? *a.n_extra : 0u);
     for (;;) {
@@ -412,6 +449,7 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
         MyersWork wk{0, 0, 0, 0};
         HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
         if (valid) valid = myers_load_pair<STRINGS>(a, sp, w, wk, ha, hb, gl);
+        if (valid && a.extra_marked_only && w >= a.n_work && wk.pad == 0) valid = false;      // the thread-per-pair second wave takes it
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
         if (valid && (la > a.maxlen || lb > a.maxlen)) { if (gl == 0) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; } valid = false; }
         if (valid && (la == 0 || lb == 0)) { if (gl == 0) a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
@@ -435,6 +473,7 @@ __global__ void __launch_bounds__(128) k_myers_fast(MyersArgs a, StringPairs sp)
         if (valid && gl == 0) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
         __syncwarp();
     }
+    if (a.trace && lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(a.trace + 2 * a.trace_slot + 1, t); }
     if (my_cells) { atomicAdd(a.cells, my_cells); if (a.unb_cells) atomicAdd(a.unb_cells, my_cells); }
 }
 
@@ -475,7 +514,7 @@ __global__ void __launch_bounds__(128, WPL <= 1 ? 8 : WPL == 2 ? 6 : WPL == 3 ? 
         const int64_t k = myers_band_k(m, n, a.band_num, a.band_add);
         const int rbin = myers_bin_of(m);
         if (valid && (orall >= 4 || k < 0 || !myers_band_fits(m, n, k, G, WPL))) {   // not a banded pair after all
-            if (gl == 0) { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
+            if (gl == 0) { wk.pad = orall >= 4 ? 1u : 0u; const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
             valid = false;
         }
         BandGeom ge = band_geom(valid ? m : 0, valid ? n : 0, valid ? k : 0, WPL);
@@ -564,39 +603,44 @@ __device__ __forceinline__ HapSource hap_bcast(const HapSource& h, int src) {
     return r;
 }
 
-// all lanes: symbol codes ((c & 0xDF) >> 1) & 3 of A/C/G/T (either case), shifted left by `shift`; returns (per lane) whether a
-// symbol outside A/C/G/T was seen
-__device__ __forceinline__ uint32_t tpp_write_codes(const HapSource& h, int32_t len, uint8_t* dst, int lane, int shift) {
-    uint32_t bad = 0;
-    const int32_t l1 = (int32_t)h.l1, l12 = (int32_t)(h.l1 + h.l2);
-    for (int32_t k0 = 0; k0 < len; k0 += 128) {
-        uint8_t c[4];
+// all lanes: dst[lead, lead + len) = the three pieces of a haplotype, read from their code images (k_tpp_encode); dst[0, lead) = 0.
+// Returns (per lane) the OR of what was copied — bit 7 set means a symbol outside A/C/G/T.  `dst` is 4-byte aligned; every lane
+// assembles whole words.
+__device__ __forceinline__ uint32_t tpp_copy_codes(const uint8_t* c1, int32_t l1, const uint8_t* c2, int32_t l2, const uint8_t* c3, int32_t l3,
+                                                   uint8_t* dst, int32_t lead, int lane) {
+    uint32_t seen = 0;
+    const int32_t len = l1 + l2 + l3, l12 = l1 + l2;
+    for (int32_t k0 = 4 * lane; k0 < lead + len; k0 += 128) {
+        uint32_t w = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int32_t k = k0 + 32 * u + lane;
-            c[u] = 'A';
-            if (k < len) c[u] = k < l1 ? h.p1[k] : (k < l12 ? h.p2[k - l1] : h.p3[k - l12]);
+        for (int b = 0; b < 4; ++b) {
+            const int32_t k = k0 + b - lead;
+            uint32_t c = 0;
+            if (k >= 0 && k < len) c = k < l1 ? c1[k] : (k < l12 ? c2[k - l1] : c3[k - l12]);
+            w |= c << (8 * b);
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int32_t k = k0 + 32 * u + lane;
-            const uint32_t up = c[u] & 0xDFu;
-            bad |= (uint32_t)!(up == 'A' || up == 'C' || up == 'G' || up == 'T');
-            if (k < len) dst[k] = (uint8_t)(((up >> 1) & 3u) << shift);
-        }
+        seen |= w;
+        *(uint32_t*)(dst + k0) = w;
     }
-    return bad;
+    return seen;
 }
 
-// one lane: match masks of pattern block `blk` from its 32 symbol codes (16-byte aligned)
+// code image of a haplotype piece: same offset as the raw bytes, in the image of the array the piece lives in
+template <bool STRINGS>
+__device__ __forceinline__ const uint8_t* tpp_code_ptr(const MyersArgs& a, const uint8_t* raw, int is_ins) {
+    if (STRINGS) return a.str_codes + (raw - a.ins_base);           // explicit string pairs: everything lives in one blob
+    return is_ins ? a.ins_codes + (raw - a.ins_base) : a.genome_codes + (raw - a.g.bytes);
+}
+
+// one lane: match masks of pattern block `blk` from its 32 symbol codes (code << 5 per byte, 16-byte aligned)
 __device__ __forceinline__ uint4 tpp_block_masks(const uint8_t* codes, int32_t m, int32_t blk) {
     const uint4 lo = *(const uint4*)(codes + 32 * blk), hi = *(const uint4*)(codes + 32 * blk + 16);
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     uint32_t p0 = 0, p1 = 0;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {   // bit 0 / bit 1 of the four code bytes of w[q] -> four adjacent bits (multiply-gather)
-        p0 |= ((((w[q]) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
-        p1 |= ((((w[q] >> 1) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
+        p0 |= ((((w[q] >> 5) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
+        p1 |= ((((w[q] >> 6) & 0x01010101u) * 0x00204081u >> 21) & 0xFu) << (4 * q);
     }
     const int32_t cnt = m - 32 * blk;
     const uint32_t real = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
@@ -606,7 +650,7 @@ __device__ __forceinline__ uint4 tpp_block_masks(const uint8_t* codes, int32_t m
 #ifndef TPP_MINB
 #define TPP_MINB(B) ((B) <= 8 ? 8 : (B) <= 12 ? 6 : (B) <= 20 ? 5 : 4)      // CTAs per SM the register budget is cut for
 #endif
-template <int B, bool STRINGS, bool HI>
+template <int B, bool STRINGS>
 __global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, StringPairs sp) {
     extern __shared__ __align__(16) uint32_t tpp_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -615,17 +659,21 @@ __global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, Str
     uint8_t* wscr = a.scratch + (size_t)warp * 32 * per_pair;
     const size_t off_codes = (size_t)16 * ((a.maxlen + 31) / 32 + 1), off_txt = off_codes + (size_t)((a.maxlen + 32 + 15) & ~15ll);
     TppEq<B> eq; eq.base = tpp_smem + wib * (B * 128) + lane; eq.sbase = (uint32_t)__cvta_generic_to_shared(eq.base);
+    unsigned long long t_begin = 0;
+    if (a.trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin)); if (threadIdx.x == 0) atomicMin(a.trace + 2 * a.trace_slot, t_begin); }
     unsigned long long my_cells = 0, my_comp = 0;
+    const uint32_t n_total = a.n_work + (a.n_extra ? *a.n_extra : 0u);
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(a.next, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= a.n_work) break;
+        if (base >= n_total) break;
         const uint32_t w = base + lane;
-        bool valid = w < a.n_work;
+        bool valid = w < n_total;
         MyersWork wk{0, 0, 0, 0};
         HapSource ha{nullptr, 0, nullptr, 0, nullptr, 0}, hb = ha;
         if (valid) valid = myers_load_pair<STRINGS>(a, sp, w, wk, ha, hb, 0);
+        if (valid && a.tpp_second && wk.pad) valid = false;            // marked pairs run on the plane kernels
         const int64_t la = ha.l1 + ha.l2 + ha.l3, lb = hb.l1 + hb.l2 + hb.l3;
         if (valid && (la > a.maxlen || lb > a.maxlen)) { atomicExch(a.err, 2u); a.ed_out[wk.slot] = 0; valid = false; }
         if (valid && (la == 0 || lb == 0)) { a.ed_out[wk.slot] = (int32_t)(la + lb); valid = false; }
@@ -633,7 +681,8 @@ __global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, Str
         const HapSource& hp = a_is_pat ? ha : hb;
         const HapSource& ht = a_is_pat ? hb : ha;
         const int32_t m = (int32_t)(a_is_pat ? la : lb), n = (int32_t)(a_is_pat ? lb : la);
-        const TppPlan plan = tpp_plan(valid ? m : 1, valid ? n : 1, a.band_num, a.band_add);
+        TppPlan plan = tpp_plan(valid ? m : 1, valid ? n : 1, a.band_num, a.band_add);
+        if (a.tpp_second) { plan.a = -1; plan.B = (int32_t)tpp_blocks_full(valid ? m : 1); }      // second wave: the whole pattern
         const int64_t k = myers_band_k(m, n, a.band_num, a.band_add);
         const int rbin = myers_bin_of(m);
         bool hand_over = valid && plan.B > B;            // not a pair of this bucket after all
@@ -643,23 +692,31 @@ __global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, Str
         for (uint32_t rest = todo; rest; rest &= rest - 1) {
             const int p = __ffs(rest) - 1;
             const HapSource pp = hap_bcast(hp, p), pt = hap_bcast(ht, p);
-            const int32_t pm = __shfl_sync(0xffffffffu, m, p), pn = __shfl_sync(0xffffffffu, n, p), pph = __shfl_sync(0xffffffffu, phase, p);
+            const int32_t pm = __shfl_sync(0xffffffffu, m, p), pph = __shfl_sync(0xffffffffu, phase, p);
             uint8_t* slot = wscr + (size_t)p * per_pair;
-            uint32_t bad = tpp_write_codes(pp, pm, slot + off_codes, lane, 0);
-            bad |= tpp_write_codes(pt, pn, slot + off_txt + pph, lane, 5);
+            // text symbols start at column index `phase`: the word-aligned copy begins at the aligned offset below it
+            uint32_t bad = tpp_copy_codes(tpp_code_ptr<STRINGS>(a, pp.p1, 0), (int32_t)pp.l1, tpp_code_ptr<STRINGS>(a, pp.p2, 1), (int32_t)pp.l2,
+                                          tpp_code_ptr<STRINGS>(a, pp.p3, 0), (int32_t)pp.l3, slot + off_codes, 0, lane);
+            bad |= tpp_copy_codes(tpp_code_ptr<STRINGS>(a, pt.p1, 0), (int32_t)pt.l1, tpp_code_ptr<STRINGS>(a, pt.p2, 1), (int32_t)pt.l2,
+                                  tpp_code_ptr<STRINGS>(a, pt.p3, 0), (int32_t)pt.l3, slot + off_txt + (pph & ~3), pph & 3, lane);
+            bad &= 0x80808080u;
             __syncwarp();
             const int32_t nblk = (pm + 31) >> 5;
             for (int32_t blk = lane; blk < nblk; blk += 32) ((uint4*)slot)[blk] = tpp_block_masks(slot + off_codes, pm, blk);
             if (__any_sync(0xffffffffu, bad) && lane == p) hand_over = true;
         }
         __syncwarp();
-        if (hand_over) { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; valid = false; }
+        if (hand_over) {
+            if (a.tpp_second) { const uint32_t f = atomicAdd(a.n_fallback, 1u); a.fallback[f] = wk; }       // cannot happen for a well-formed plan: exact any-byte kernel
+            else { wk.pad = plan.B > B ? 0u : 1u; const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
+            valid = false;
+        }
         // ---- one pair per lane ------------------------------------------------------------------------------------
         if (valid) {
             const uint8_t* slot = wscr + (size_t)lane * per_pair;
             TppPeq peq{(const uint4*)slot, (m + 31) >> 5};
             TppTxt txt{slot + off_txt};
-            const int32_t ed = tpp_thread<B, HI>(m, n, plan.a, eq, peq, txt, a.one, a.two);
+            const int32_t ed = tpp_thread<B>(m, n, plan.a, eq, peq, txt, a.one, a.two);
             my_comp += (unsigned long long)n * (unsigned long long)(32 * B);
             if (plan.a < 0 || ed <= k) { a.ed_out[wk.slot] = ed; my_cells += (unsigned long long)la * (unsigned long long)lb; }
             else { const uint32_t f = atomicAdd(a.n_retry + rbin, 1u); a.retry[a.retry_off[rbin] + f] = wk; }
@@ -670,6 +727,10 @@ __global__ void __launch_bounds__(128, TPP_MINB(B)) k_myers_tpp(MyersArgs a, Str
     for (int o = 16; o > 0; o >>= 1) { my_cells += __shfl_xor_sync(0xffffffffu, my_cells, o); my_comp += __shfl_xor_sync(0xffffffffu, my_comp, o); }
     if (lane == 0 && my_cells) atomicAdd(a.cells, my_cells);
     if (lane == 0 && my_comp && a.tpp_cells) atomicAdd(a.tpp_cells, my_comp);
+    if (a.trace && lane == 0) {
+        unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(a.trace + 2 * a.trace_slot + 1, t);
+        atomicAdd(a.trace + 128 + 2 * a.trace_slot, t - t_begin); atomicAdd(a.trace + 128 + 2 * a.trace_slot + 1, 1ull);      // warp residency: sum, count
+    }
 }
 
 // any bytes: 8 bit-planes, a warp per pair, 4 words per lane, strip-mined
@@ -743,6 +804,7 @@ static cudaError_t myers_launch_bin(svimgpu_ctx* ctx, int bin, MyersArgs a, Stri
     ctx->launches++;
     cudaStream_t stream = ctx->aux_stream[bin % SVIM_AUX_STREAMS];   // bins overlap: one kernel's tail is filled by the next
     a.one = 1u; a.two = 2u;
+    a.trace = ctx->myers_trace ? ctx->d_myers_trace.as<unsigned long long>() : nullptr; a.trace_slot = 20u + (uint32_t)bin;
 #define MYERS_LAUNCH(G_, W_)                                                                                     \
     switch (ctx->myers_mode) {                                                                                   \
         case 0: k_myers_fast<G_, W_, STRINGS, 0><<<blocks, 128, 0, stream>>>(a, sp); break;                      \
@@ -815,33 +877,33 @@ static int64_t tpp_bucket_maxlen(int q, int64_t maxlen, int32_t num, int32_t add
     return std::min<int64_t>(maxlen, cap + 64);
 }
 
+// second_bin >= 0: second wave — the pairs the first pass handed over to unbanded bin `second_bin` (patterns up to 64 * capW
+// rows, i.e. 8 * (second_bin + 1) blocks), whole pattern in the window; extra_cap bounds their number for the grid size
 template <bool STRINGS>
-static cudaError_t myers_launch_tpp(svimgpu_ctx* ctx, int q, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms) {
-    if (a.n_work == 0) return cudaSuccess;
+static cudaError_t myers_launch_tpp(svimgpu_ctx* ctx, int q, MyersArgs a, StringPairs sp, DevBuf& scratch, int sms, int second_bin = -1, uint32_t extra_cap = 0) {
+    const uint64_t n_items = second_bin >= 0 ? (uint64_t)extra_cap : (uint64_t)a.n_work;
+    if (n_items == 0) return cudaSuccess;
     const int B = tpp_bucket_B(q);
-    a.maxlen = (tpp_bucket_maxlen(q, a.maxlen, a.band_num, a.band_add) + 15) & ~15ll;
+    if (second_bin >= 0) { a.maxlen = std::min<int64_t>(a.maxlen, 32 * B); a.tpp_second = 1u; a.n_work = 0; a.work = nullptr; sp.list = nullptr; }
+    else { a.maxlen = tpp_bucket_maxlen(q, a.maxlen, a.band_num, a.band_add); a.tpp_second = 0u; a.extra = nullptr; a.n_extra = nullptr; }
+    a.maxlen = (a.maxlen + 15) & ~15ll;
     const int occ = B <= 8 ? 8 : B <= 12 ? 6 : B <= 20 ? 5 : 4;
     int blocks = sms * occ;
-    blocks = (int)std::min<int64_t>(blocks, ((int64_t)a.n_work + 127) / 128);
+    blocks = (int)std::min<int64_t>(blocks, ((int64_t)n_items + 127) / 128);
     const size_t per_warp = (size_t)32 * tpp_pair_scratch(a.maxlen);
     while (blocks > sms && (size_t)blocks * 4 * per_warp > ((size_t)8 << 30)) blocks -= sms;
     cudaError_t e = scratch.ensure((size_t)blocks * 4 * per_warp);
     if (e != cudaSuccess) return e;
     a.scratch = scratch.as<uint8_t>();
-    a.extra = nullptr; a.n_extra = nullptr;
     ctx->launches++;
     cudaStream_t stream = ctx->aux_stream[q % SVIM_AUX_STREAMS];
     a.one = 1u; a.two = 2u;
+    a.trace = ctx->myers_trace ? ctx->d_myers_trace.as<unsigned long long>() : nullptr; a.trace_slot = second_bin >= 0 ? 40u + second_bin : (uint32_t)q;
     const size_t smem = (size_t)4 * B * 128 * 4;
 #define TPP_LAUNCH(B_)                                                                                                     \
     case B_:                                                                                                              \
-        if (ctx->myers_mode == 2) {                                                                                       \
-            e = cudaFuncSetAttribute(k_myers_tpp<B_, STRINGS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e == cudaSuccess) k_myers_tpp<B_, STRINGS, true><<<blocks, 128, smem, stream>>>(a, sp);                    \
-        } else {                                                                                                          \
-            e = cudaFuncSetAttribute(k_myers_tpp<B_, STRINGS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e == cudaSuccess) k_myers_tpp<B_, STRINGS, false><<<blocks, 128, smem, stream>>>(a, sp);                   \
-        }                                                                                                                 \
+        e = cudaFuncSetAttribute(k_myers_tpp<B_, STRINGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        if (e == cudaSuccess) k_myers_tpp<B_, STRINGS><<<blocks, 128, smem, stream>>>(a, sp);                              \
         break;
     switch (B) {
         TPP_LAUNCH(2) TPP_LAUNCH(3) TPP_LAUNCH(4) TPP_LAUNCH(5) TPP_LAUNCH(6) TPP_LAUNCH(7) TPP_LAUNCH(8) TPP_LAUNCH(9) TPP_LAUNCH(10)
@@ -873,6 +935,11 @@ static cudaError_t myers_run_plan(svimgpu_ctx* ctx, const MyersPlan& pl, MyersAr
     cudaError_t e = cudaSuccess;
     auto chk = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     cudaStream_t st = ctx->stream;
+    if (ctx->myers_trace) {
+        chk(ctx->d_myers_trace.ensure(64 * 32));
+        unsigned long long init[256]; for (int k = 0; k < 64; ++k) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; init[128 + 2 * k] = 0ull; init[128 + 2 * k + 1] = 0ull; }
+        chk(cudaMemcpyAsync(ctx->d_myers_trace.p, init, sizeof(init), cudaMemcpyHostToDevice, st)); chk(cudaStreamSynchronize(st));
+    }
     chk(cudaMemsetAsync(ctl + MYERS_CTL_CURSOR, 0, (MYERS_CTL_N - MYERS_CTL_CURSOR) * 4, st));
     ma.n_fallback = ctl + MYERS_CTL_FALLBACK; ma.n_retry = ctl + MYERS_CTL_RETRY; ma.retry = retry;
     uint32_t acc = 0, n_banded = 0;
@@ -896,17 +963,35 @@ static cudaError_t myers_run_plan(svimgpu_ctx* ctx, const MyersPlan& pl, MyersAr
         chk(myers_join(ctx));
     }
     // longest bins first so the tail of the launch sequence is made of short pairs; bins overlap on side streams
+    // Second wave.  Hand-overs with patterns up to 768 rows run unbanded on the thread-per-pair kernels of 8 / 16 / 24 blocks (their
+    // unbanded bins 0-2 then only take the pairs marked as holding symbols outside A/C/G/T); longer ones on the wavefront kernels.
     chk(myers_fork(ctx));
     for (int bb = MYERS_BINS - 1; bb >= 0 && e == cudaSuccess; --bb) {
+        const bool second_tpp = ctx->myers_tpp && bb <= 2 && pl.retry_cap[bb] > 0;
         ma.work = work ? work + pl.off[bb] : nullptr; sp.list = list ? list + pl.off[bb] : nullptr;
         ma.n_work = pl.cnt[bb]; ma.next = ctl + MYERS_CTL_CURSOR + bb; ma.maxlen = maxlen;
         ma.extra = retry + ma.retry_off[bb]; ma.n_extra = ctl + MYERS_CTL_RETRY + bb;
+        ma.extra_marked_only = second_tpp ? 1u : 0u;
         chk(myers_launch_bin<STRINGS>(ctx, bb, ma, sp, ctx->d_myers_scratch[bb], sms, pl.retry_cap[bb]));
+        if (second_tpp) {
+            ma.next = ctl + MYERS_CTL_CURSOR + MYERS_LISTS + 1 + bb; ma.maxlen = maxlen; ma.extra_marked_only = 0u;
+            chk(myers_launch_tpp<STRINGS>(ctx, tpp_bucket_of(8 * (bb + 1)), ma, sp, ctx->d_myers_scratch[42 + bb], sms, bb, pl.retry_cap[bb]));
+        }
     }
+    ma.extra_marked_only = 0u; ma.tpp_second = 0u;
     chk(myers_join(ctx));
     uint32_t n_fb = 0;
     chk(cudaMemcpyAsync(&n_fb, ctl + MYERS_CTL_FALLBACK, 4, cudaMemcpyDeviceToHost, st));
     chk(cudaStreamSynchronize(st));
+    if (ctx->myers_trace && e == cudaSuccess) {
+        unsigned long long tr[256];
+        if (cudaMemcpy(tr, ctx->d_myers_trace.p, sizeof(tr), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            unsigned long long t0 = ~0ull; for (int k = 0; k < 64; ++k) if (tr[2 * k] < t0) t0 = tr[2 * k];
+            for (int k = 0; k < 64; ++k) if (tr[2 * k + 1]) fprintf(stderr, "[myers trace] %s %2d  items %8u  start %8.3f ms  end %8.3f ms  warps %6llu  mean warp residency %8.3f ms\n", k < 20 ? "tpp  B" : k < 40 ? "fast bin" : "tpp2 bin",
+                                                              k < 20 ? tpp_bucket_B(k) : k < 40 ? k - 20 : k - 40, k < 20 ? pl.cnt[2 * MYERS_BINS + k] : k < 40 ? pl.cnt[k - 20] : pl.retry_cap[k - 40], (tr[2 * k] - t0) * 1e-6, (tr[2 * k + 1] - t0) * 1e-6,
+                                                              tr[128 + 2 * k + 1], tr[128 + 2 * k + 1] ? tr[128 + 2 * k] * 1e-6 / tr[128 + 2 * k + 1] : 0.0);
+        }
+    }
     if (e == cudaSuccess && n_fb > 0) {   // pairs with symbols outside A,C,G,T,N(+3): exact 8-plane kernel
         sp.list = nullptr;
         ma.work = ma.fallback; ma.n_work = n_fb; ma.next = ctl + MYERS_CTL_CURSOR + MYERS_LISTS; ma.maxlen = maxlen; ma.fallback = nullptr; ma.n_fallback = nullptr;

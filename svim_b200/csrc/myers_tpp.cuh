@@ -64,7 +64,6 @@ SVIM_HD TppPlan tpp_plan(int64_t m, int64_t n, int32_t num, int32_t add) {
 
 // one 32-row block step, D0 form.  hp/hn: incoming horizontal delta flags (+1 / -1) at the block's top, replaced by the
 // outgoing ones at its bottom.  `one`, `two` are opaque 1 and 2 (multiplicands that keep add and shifts on the FMA pipe).
-template <bool HI>
 SVIM_D void tpp_block(uint32_t eq, uint32_t& vp_io, uint32_t& vn_io, uint32_t& hp, uint32_t& hn, uint32_t one, uint32_t two) {
     const uint32_t vp = vp_io, vn = vn_io;
     const uint32_t t = mb_lop3<0xA8>(eq, hn, vp);            // (eq | hn) & vp
@@ -74,8 +73,7 @@ SVIM_D void tpp_block(uint32_t eq, uint32_t& vp_io, uint32_t& vn_io, uint32_t& h
     const uint32_t ph = mb_lop3<0xF1>(vn, d0, vp);           // vn | ~(d0 | vp)
     const uint32_t mh = d0 & vp;
     const uint32_t ph2 = mb_imad(ph, two, hp), mh2 = mb_imad(mh, two, hn);
-    if (HI) { hp = mb_umulhi(ph, two); hn = mb_umulhi(mh, two); }      // top bits as IMAD.HI: FMA pipe instead of the ALU pipe's SHF
-    else { hp = ph >> 31; hn = mh >> 31; }
+    hp = ph >> 31; hn = mh >> 31;                          // (as IMAD.HI on the FMA pipe this measured slower: 25.0 vs 23.2 ms on config2)
     vp_io = mb_lop3<0xF1>(mh2, d0, ph2);                      // mh2 | ~(d0 | ph2)
     vn_io = d0 & ph2;
 }
@@ -96,7 +94,7 @@ SVIM_D void tpp_load_column(const Eq& eq, uint32_t sym, uint32_t (&E)[B]) {
 
 // One pair, one thread.  Eq: window store (put / get / shift_up), Peq: match masks of pattern block b (zeros outside the
 // pattern), Txt: text symbols at shifted column index s = j + phase, pre-scaled for Eq::get (byte(s), word(s) = 4 bytes).
-template <int B, bool HI, class Eq, class Peq, class Txt>
+template <int B, class Eq, class Peq, class Txt>
 SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& peq, const Txt& txt, uint32_t one, uint32_t two) {
     const bool banded = a >= 0;
     const int32_t phase = banded ? ((-a) & 31) : 0;
@@ -111,6 +109,10 @@ SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& pe
     }
     int32_t score = 32 * B - A;
     const int32_t s_end = phase + n;
+    // global loads are issued one unit ahead of their use: the masks of the block that enters at the next slide, and the next word
+    // of text symbols (the scratch is padded, reading one word past the text is harmless)
+    uint32_t v_next[4]; peq.block(1 - (A >> 5) + B - 1, v_next);
+    uint32_t w_next = txt.word((phase + 3) & ~3);
     for (int32_t c = 0; 32 * c < s_end; ++c) {
         if (c > 0 && banded) {                            // slide: the top block leaves, a block of fresh rows enters
 #ifndef SVIM_HOST_ONLY
@@ -119,7 +121,8 @@ SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& pe
             for (int i = 0; i + 1 < B; ++i) { vp[i] = vp[i + 1]; vn[i] = vn[i + 1]; }
             vp[B - 1] = 0xffffffffu; vn[B - 1] = 0u;
             eq.shift_up();
-            uint32_t v[4]; peq.block(c - (A >> 5) + B - 1, v); eq.put(B - 1, v);
+            eq.put(B - 1, v_next);
+            peq.block(c + 1 - (A >> 5) + B - 1, v_next);
             score += 32;
         }
         int32_t s = 32 * c > phase ? 32 * c : phase;
@@ -128,7 +131,8 @@ SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& pe
             if ((s & 3) == 0 && s + 4 <= s_hi) {
                 // four columns from one text word = 4*B block steps in program order.  The match masks are loaded TPP_AHEAD block
                 // steps before their use (a small ring of registers), so the shared-memory latency stays off the carry chain.
-                const uint32_t w = txt.word(s);
+                const uint32_t w = w_next;
+                w_next = txt.word(s + 4);
                 uint32_t ring[TPP_AHEAD];
 #ifndef SVIM_HOST_ONLY
 #pragma unroll
@@ -141,7 +145,7 @@ SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& pe
                 for (int t = 0; t < 4 * B; ++t) {
                     const uint32_t e = ring[t % TPP_AHEAD];
                     if (t + TPP_AHEAD < 4 * B) ring[t % TPP_AHEAD] = eq.get((t + TPP_AHEAD) % B, (w >> (8 * ((t + TPP_AHEAD) / B))) & 0xffu);
-                    tpp_block<HI>(e, vp[t % B], vn[t % B], hp, hn, one, two);
+                    tpp_block(e, vp[t % B], vn[t % B], hp, hn, one, two);
                     if (t % B == B - 1) { score += (int32_t)hp - (int32_t)hn; hp = 1u; hn = 0u; }
                 }
                 s += 4;
@@ -151,7 +155,7 @@ SVIM_D int32_t tpp_thread(int32_t m, int32_t n, int32_t a, Eq& eq, const Peq& pe
 #ifndef SVIM_HOST_ONLY
 #pragma unroll
 #endif
-                for (int i = 0; i < B; ++i) tpp_block<HI>(eq.get(i, sym), vp[i], vn[i], hp, hn, one, two);
+                for (int i = 0; i < B; ++i) tpp_block(eq.get(i, sym), vp[i], vn[i], hp, hn, one, two);
                 score += (int32_t)hp - (int32_t)hn;
                 ++s;
             }

@@ -132,7 +132,7 @@ static long long tpp_emulate(const uint8_t* pat, long long m, const uint8_t* txt
     const int phase = a >= 0 ? ((-a) & 31) : 0;
     tx.t.assign((size_t)(phase + n + 8), 0);
     for (long long j = 0; j < n; ++j) tx.t[(size_t)(phase + j)] = (uint8_t)(txt[j] * 32);
-    return tpp_thread<B, false>((int32_t)m, (int32_t)n, a, eq, peq, tx, 1u, 2u) ;
+    return tpp_thread<B>((int32_t)m, (int32_t)n, a, eq, peq, tx, 1u, 2u) ;
 }
 extern "C" {
 // pat/txt: symbol codes 0..3, m >= n >= 1.  k < 0: unbanded.  Runs in the smallest bucket that holds the pair (or `force_B` blocks);
