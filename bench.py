@@ -68,6 +68,18 @@ def make_rank_input(workload, scale, rank, world):
     return batch, genome
 
 
+def make_sharded_input(workload, scale, rank, world):
+    """--shard records: ONE coordinate-sorted input of the workload (config4: 24 contigs chr1..chr22, chrX, chrY), cut into `world`
+    contiguous record ranges balanced by CIGAR volume (svim_b200.parallel.shard_ranges); this rank materialises only its range.
+    Returns (batch, genome, first record index, total records)."""
+    from svim_b200 import synth
+    names, lengths, reads, seed, plant_kw, gen_kw = synth.config_layout(workload, scale)
+    svs, alleles = synth.plant_svs(lengths, seed, **plant_kw)
+    batch, lo, total = synth.generate_shard(names, lengths, reads, seed, svs, alleles, rank, world, **gen_kw)
+    genome = synth.random_genome(names, lengths, 1524 + seed)
+    return batch, genome, lo, total
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line).
 
@@ -273,8 +285,17 @@ def run_reference(args):
                       "cpu_baseline": base, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+WORKLOAD_TEXT = {"config2": "BASELINE.json configs[1]: 1 contig, 500k alignments, 15 kb CLR-like reads",
+                 "config3": "BASELINE.json configs[2]: insertion-heavy, 200-5000 bp inserted sequences",
+                 "config4": "BASELINE.json configs[3]: 24 contigs chr1..chr22,chrX,chrY, 5 M alignments, 30x whole-genome scale",
+                 "config5": "BASELINE.json configs[4]: 1 contig at 100x, 2 M alignments, hotspot partitions up to 50 k signatures",
+                 "config1": "BASELINE.json configs[0]: 1 contig, 1000 reads"}
+
+
 def workload_name(args):
-    return "%s x%g per GPU (BASELINE.json configs[1]: 1 contig, 500k alignments, 15 kb CLR-like reads)" % (args.workload, args.scale)
+    if args.shard == "records":
+        return "%s x%g, ONE coordinate-sorted input cut into contiguous record ranges, one per GPU (%s)" % (args.workload, args.scale, WORKLOAD_TEXT.get(args.workload, ""))
+    return "%s x%g per GPU (%s)" % (args.workload, args.scale, WORKLOAD_TEXT.get(args.workload, ""))
 
 
 def main():
@@ -285,8 +306,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config2")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink genome and read count together (testing only)")
+    ap.add_argument("--shard", default="contigs", choices=["contigs", "records"],
+                    help="contigs (default): every rank holds its own contig of the workload (weak scaling); records: one input of the "
+                         "workload, contiguous record ranges balanced by CIGAR volume (strong scaling)")
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cigar16", action="store_true", help="e2e legs upload BAM's uint32 CIGAR words instead of the 16-bit packed stream")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
     ap.add_argument("--with-bam", action="store_true", help="also time the path starting from a BAM file on disk (native multi-threaded decode)")
     ap.add_argument("--profile-genotype", action="store_true", help="with --profile-steps: also run the GENOTYPE leg (for ncu)")
@@ -302,7 +327,10 @@ def main():
         os.environ["SVIM_SCAN_VARIANT"] = str(args.scan_variant)
     from svim_b200 import _lib
     t_gen = time.perf_counter()
-    batch, genome = make_rank_input(args.workload, args.scale, rank, world)
+    if args.shard == "records":
+        batch, genome, shard_lo, shard_total = make_sharded_input(args.workload, args.scale, rank, world)
+    else:
+        batch, genome = make_rank_input(args.workload, args.scale, rank, world)
     t_gen = time.perf_counter() - t_gen
 
     ctx = _lib.Context(device=local_rank)
@@ -314,6 +342,8 @@ def main():
         dist.init_process_group("gloo")
         parallel.init_comm(ctx)
         aln_base, total_aln, _sizes = parallel.exchange_layout(batch.n)
+        if args.shard == "records":
+            assert aln_base == shard_lo and total_aln == shard_total, "record ranges do not tile the input"
     else:
         aln_base = 0; total_aln = batch.n
 
@@ -365,7 +395,13 @@ def main():
         return
 
     # ---------------- e2e: host buffers through the C ABI, copies inside the timed region --------
-    pinned = [batch.cigar, batch.seq, batch.sa] + [getattr(batch, f) for f, _ in batch.FIELDS]
+    # the record buffer crosses PCIe with its CIGAR blob in the 16-bit packed form of include/svimgpu.h (svim_aln_soa.cigar16: what
+    # svim_b200's decoders hand over; re-encoded here once, outside the timed region) and is expanded to BAM's uint32 words in HBM
+    t_pack = time.perf_counter()
+    if not args.no_cigar16:
+        batch.pack_cigar16()
+    t_pack = time.perf_counter() - t_pack
+    pinned = ([batch.cigar16, batch.cigar16_off] if batch.cigar16 is not None else [batch.cigar]) + [batch.seq, batch.sa] + [getattr(batch, f) for f, _ in batch.FIELDS]
     for a in pinned:
         ctx.pin(a)
     # collect_host keeps SEQ on the host and uploads only the packed bases of emitted insertions (lazy SEQ)
@@ -484,17 +520,20 @@ def main():
             traffic = t["dram_bytes_per_launch"]
     out = {
         "metric": METRIC, "value": total_aln / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 CIGAR words / i64 coordinates / f64 distances",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.shard == "records" else "weak", "vs_baseline": None, "dtype": "u32 CIGAR words / i64 coordinates / f64 distances",
         "data": "synthetic", "gpu_launches": int(launches),
         "config": {"workload": workload_name(args), "alignments_per_gpu": batch.n, "signatures": int(n_sigs), "clusters": int(clst.n_clusters_total),
                    "myers_pairs": int(clst.myers_pairs), "myers_cells": int(clst.myers_cells),
                    "myers_banded_pairs": int(clst.myers_banded_pairs), "myers_handed_over": int(clst.myers_retry_pairs),
                    "myers_band_cells": int(clst.myers_band_cells),
                    "l2": "inputs larger than L2 (%.2f GB CIGAR per GPU vs 126 MB)" % (batch.cigar.nbytes / 1e9),
-                   "parallelism": "records sharded by contig; 2 NCCL allgatherv" if world > 1 else "single GPU",
+                   "parallelism": ("contiguous record ranges of one input balanced by CIGAR volume; 2 NCCL allgatherv" if args.shard == "records" else
+                                   "records sharded by contig; 2 NCCL allgatherv") if world > 1 else "single GPU",
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
+                "cigar_upload": ("16-bit packed stream (svim_aln_soa.cigar16), %.2f GB; expanded on the device" % (batch.cigar16.nbytes / 1e9)) if batch.cigar16 is not None
+                                else "uint32 BAM words, %.2f GB" % (batch.cigar.nbytes / 1e9),
                 "clocks": clocks_e2e},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},

@@ -66,6 +66,13 @@ typedef struct {
     const uint32_t* cigar; int64_t cigar_words;  /* BAM encoding len<<4|op */
     const uint8_t* seq; int64_t seq_bytes;       /* BAM 4-bit packing */
     const uint8_t* sa; int64_t sa_bytes;         /* SA tag text */
+    /* Optional 16-bit packed CIGAR stream — half the PCIe bytes of `cigar` for long reads.  When cigar16 is set the library
+     * uploads it instead of `cigar` (which may then be NULL) and expands it to the uint32 words on the device.
+     * Word = len << 4 | op for len < 4096; words with op nibble 0xF carry 12 more significant length bits each and precede
+     * the op word; every record's stream starts at cigar16_off[i] (uint16 units, multiple of 8) and is padded with 0x000F.
+     * svim_b200.io's BAM decoders and bamio_pack_cigar16 (csrc_host/bamio.cpp) produce it. */
+    const uint16_t* cigar16; int64_t cigar16_words;
+    const uint64_t* cigar16_off;                 /* n_aln + 1 entries */
 } svim_aln_soa;
 
 /* Signature types, in the reference's clustering call order (SVIM_CLUSTER.py:19-24). */
@@ -176,6 +183,27 @@ int svimgpu_unpin_host(void* p);
 /* H2D of the record buffer (pageable or pinned host memory). */
 int svimgpu_upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* soa);
 /* CIGAR scan + SA/segment analysis + INS sequence gather on the resident buffer. */
+/* ---- BAM file -> resident record buffer on the GPU (the step in front of the path: bam.fetch(until_eof=True), SVIM_COLLECT.py:133) ----
+ * One BGZF block of the file: payload offset / inflated offset / payload bytes / inflated bytes (ISIZE).  The host indexes the
+ * block headers (svim_b200/csrc_host/bamio.cpp: bamio_open + bamio_blocks) and reads the BAM header; everything else runs on
+ * the device: raw DEFLATE, record boundaries, rows, CIGAR / SEQ / SA blobs, read-name ids (first-appearance numbering). */
+typedef struct { uint64_t coff, uoff; uint32_t clen, ulen; } svim_bgzf_block;
+typedef struct { int64_t n_records, cigar_words, seq_bytes, sa_bytes, names_bytes, n_names, inflated_bytes; } svim_bam_info;
+/* file: the whole .bam in host memory (mapped or read); first_record: offset of the first alignment record in the inflated
+ * stream; n_ref: contigs in the header.  Leaves the records resident exactly like svimgpu_upload_alignments (svimgpu_collect,
+ * svimgpu_genotype run on them).  SVIMGPU_ERR_DATA when the file is malformed or the decoder declines it (a speculative record
+ * boundary or a read-name hash did not verify): decode on the host then — the call never guesses. */
+int svimgpu_decode_bam(svimgpu_ctx* ctx, const uint8_t* file, int64_t file_bytes, const svim_bgzf_block* blocks, int64_t n_blocks,
+                       int64_t first_record, int32_t n_ref, svim_bam_info* info);
+/* names: names_bytes of NUL-terminated read names in record order; name_off[n]; rec_of_id[n_names]: first record of every id;
+ * qname_id[n] (any pointer may be NULL) */
+int svimgpu_fetch_bam_names(svimgpu_ctx* ctx, uint8_t* names, uint64_t* name_off, uint32_t* rec_of_id, uint32_t* qname_id);
+/* The resident record buffer back on the host (any pointer may be NULL); sizes from svim_bam_info / the uploaded svim_aln_soa. */
+int svimgpu_download_alignments(svimgpu_ctx* ctx, int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, uint32_t* n_cigar,
+                                uint64_t* cigar_off, int32_t* l_seq, uint64_t* seq_off, uint64_t* sa_off, uint32_t* sa_len,
+                                uint32_t* qname_id, uint32_t* cigar, uint8_t* seq, uint8_t* sa);
+/* Copy the resident uint32 CIGAR blob back (tests: the device expansion of svim_aln_soa.cigar16 must equal the caller's `cigar`). */
+int svimgpu_download_cigar(svimgpu_ctx* ctx, uint32_t* out, int64_t words);
 int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats);
 /* upload + collect */
 int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect_stats* stats);

@@ -13,12 +13,18 @@ def cluster_sv_signatures(sv_signatures, options):
     token = getattr(sv_signatures, "_svimgpu_token", None)
     if isinstance(sv_signatures, SignatureList) and token is not None and token is getattr(ctx, "collect_token", None):
         # the list is exactly what COLLECT returned: cluster the device-resident records
-        ctx.set_params(_lib.Params.from_options(options))
-        batch = ctx.collect_batch
-        genome = runtime.genome_for(options.genome)
-        runtime.ensure_genome(ctx, genome, batch.contig_names)
-        ctx.use_collected(getattr(sv_signatures, "_svimgpu_which", 0))
-        stats, clusters, members = ctx.cluster()
+        which = getattr(sv_signatures, "_svimgpu_which", 0)
+        pre = getattr(ctx, "cluster_prefetch", None)
+        ctx.cluster_prefetch = None
+        done = pre.take(options, which) if pre is not None else None      # CLUSTER already ran while COLLECT's objects were being built
+        if done is None:
+            ctx.set_params(_lib.Params.from_options(options))
+            batch = ctx.collect_batch
+            genome = runtime.genome_for(options.genome)
+            runtime.ensure_genome(ctx, genome, batch.contig_names)
+            ctx.use_collected(which)
+            done = ctx.cluster()
+        stats, clusters, members = done
         per_type = build_clusters(clusters, members, sv_signatures)
     else:
         if len(sv_signatures) == 0:

@@ -159,12 +159,53 @@ def analyze_alignment_file_coordsorted(bam, options):
     return _analyze(bam, options, False)
 
 
+class _ClusterPrefetch:
+    """CLUSTER of the list COLLECT is about to return, started on a host thread while the Python objects are built.
+
+    `svim` calls cluster_sv_signatures(sv_signatures, options) right after analyze_alignment_file_* with the same options object
+    (svim:102,132).  The kernels need nothing from the host but the options, so the device works on CLUSTER (ctypes releases the
+    GIL for the call) while the interpreter materialises a quarter of a million Signature objects; cluster_sv_signatures takes the
+    finished records if list, options and genome are still the ones this was started with, and recomputes otherwise."""
+
+    def __init__(self, ctx, options, which):
+        import threading
+        self.key = self.options_key(options)
+        self.which = which
+        self.result = self.error = None
+        self.t = threading.Thread(target=self._run, args=(ctx, options), daemon=True)
+        self.t.start()
+
+    @staticmethod
+    def options_key(options):
+        return tuple((k, getattr(options, k, None)) for k in ("partition_max_distance", "position_distance_normalizer", "edit_distance_normalizer",
+                                                                "cluster_max_distance", "genome"))
+
+    def _run(self, ctx, options):
+        try:
+            genome = runtime.genome_for(options.genome)
+            runtime.ensure_genome(ctx, genome, ctx.collect_batch.contig_names)
+            ctx.use_collected(self.which)
+            self.result = ctx.cluster()
+        except BaseException as e:          # surfaces (again) when cluster_sv_signatures recomputes
+            self.error = e
+
+    def take(self, options, which):
+        self.t.join()
+        if self.error is not None or which != self.which or self.options_key(options) != self.key:
+            return None
+        return self.result
+
+
 def _analyze(bam, options, querysorted):
     batch = as_batch(bam)
     ctx, stats, (sigs, ins), (tsigs, tins) = collect_arrays(batch, options, querysorted=querysorted)
     token = object()
     ctx.collect_token = token
     ctx.collect_batch = batch
+    ctx.cluster_prefetch = None
+    if len(sigs) and getattr(options, "genome", None) is not None:
+        sigs = np.array(sigs); ins = np.array(ins)      # own copies: the pinned mirrors belong to the context the thread is using
+        ctx.cluster_prefetch = _ClusterPrefetch(ctx, options, 0)
     main = SignatureList(materialize_signatures(sigs, ins, batch), token=token)
     main._svimgpu_which = 0
     twins = SignatureList(materialize_signatures(tsigs, tins, batch), token=token)

@@ -52,7 +52,8 @@ class AlnSoa(C.Structure):
     _fields_ = [("n_aln", C.c_int64)] + [(n, C.c_void_p) for n in
                 ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off", "sa_off", "sa_len", "qname_id")] + \
                [("cigar", C.c_void_p), ("cigar_words", C.c_int64), ("seq", C.c_void_p), ("seq_bytes", C.c_int64),
-                ("sa", C.c_void_p), ("sa_bytes", C.c_int64)]
+                ("sa", C.c_void_p), ("sa_bytes", C.c_int64),
+                ("cigar16", C.c_void_p), ("cigar16_words", C.c_int64), ("cigar16_off", C.c_void_p)]
 
 
 SIG_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("pos", "<i4"), ("contig1", "<i4"), ("contig2", "<i4"),
@@ -96,6 +97,10 @@ class ClusterStats(C.Structure):
                 ("myers_tpp_pairs", C.c_int64), ("myers_tpp_cells", C.c_int64), ("myers_unbanded_cells", C.c_int64)]
 
 
+class BamInfo(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_records", "cigar_words", "seq_bytes", "sa_bytes", "names_bytes", "n_names", "inflated_bytes")]
+
+
 class CollectStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("n_signatures", "n_twin_signatures", "ins_bytes", "twin_ins_bytes", "n_sa_bad_fields",
                                          "n_no_read_length", "n_primaries", "n_data_errors")]
@@ -114,6 +119,10 @@ EXPORTS = {
     "svimgpu_pin_host": (C.c_int, [C.c_void_p, C.c_int64]),
     "svimgpu_unpin_host": (C.c_int, [C.c_void_p]),
     "svimgpu_upload_alignments": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa)]),
+    "svimgpu_download_cigar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "svimgpu_decode_bam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.POINTER(BamInfo)]),
+    "svimgpu_fetch_bam_names": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svimgpu_download_alignments": (C.c_int, [C.c_void_p] * 15),
     "svimgpu_collect": (C.c_int, [C.c_void_p, C.POINTER(CollectStats)]),
     "svimgpu_collect_host": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
     "svimgpu_collect_host_querysorted": (C.c_int, [C.c_void_p, C.POINTER(AlnSoa), C.POINTER(CollectStats)]),
@@ -247,6 +256,9 @@ class Context:
         s.cigar = _ptr(batch.cigar); s.cigar_words = batch.cigar.size
         s.seq = _ptr(batch.seq); s.seq_bytes = batch.seq.size
         s.sa = _ptr(batch.sa); s.sa_bytes = batch.sa.size
+        c16 = getattr(batch, "cigar16", None)
+        if c16 is not None:          # packed CIGAR stream (AlignmentBatch.pack_cigar16): uploaded instead of the uint32 words
+            s.cigar16 = _ptr(c16); s.cigar16_words = c16.size; s.cigar16_off = _ptr(batch.cigar16_off)
         return s
 
     def pin(self, arr):
@@ -262,6 +274,34 @@ class Context:
     def upload(self, batch):
         soa = self.soa_of(batch)
         self._check(self.lib.svimgpu_upload_alignments(self.h, C.byref(soa)))
+
+    def decode_bam(self, file_bytes, blocks, first_record, n_ref) -> BamInfo:
+        """file_bytes: uint8 array (or memmap) of the whole .bam; blocks: io.BGZF_BLOCK_DTYPE table.  Leaves the records resident."""
+        info = BamInfo()
+        self._check(self.lib.svimgpu_decode_bam(self.h, file_bytes.ctypes.data, file_bytes.size, blocks.ctypes.data if len(blocks) else None, len(blocks),
+                                                first_record, n_ref, C.byref(info)))
+        return info
+
+    def fetch_bam_names(self, info: BamInfo):
+        names = np.zeros(max(1, info.names_bytes), dtype=np.uint8); off = np.zeros(info.n_records, dtype=np.uint64)
+        rec = np.zeros(info.n_names, dtype=np.uint32); qid = np.zeros(info.n_records, dtype=np.uint32)
+        self._check(self.lib.svimgpu_fetch_bam_names(self.h, _ptr(names), _ptr(off), _ptr(rec), _ptr(qid)))
+        return names[:info.names_bytes], off, rec, qid
+
+    def download_alignments(self, info: BamInfo):
+        from .records import AlignmentBatch
+        n = info.n_records
+        arrays = {name: np.zeros(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
+        cigar = np.zeros(info.cigar_words, dtype=np.uint32); seq = np.zeros(info.seq_bytes, dtype=np.uint8); sa = np.zeros(info.sa_bytes, dtype=np.uint8)
+        p = lambda a: _ptr(a)
+        self._check(self.lib.svimgpu_download_alignments(self.h, *[p(arrays[k]) for k in ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off",
+                                                                                           "sa_off", "sa_len", "qname_id")], p(cigar), p(seq), p(sa)))
+        return arrays, cigar, seq, sa
+
+    def download_cigar(self, words: int):
+        out = np.zeros(words, dtype=np.uint32)
+        self._check(self.lib.svimgpu_download_cigar(self.h, _ptr(out), words))
+        return out
 
     def collect(self) -> CollectStats:
         st = CollectStats()

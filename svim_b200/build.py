@@ -3,7 +3,7 @@
   svim_b200/libsvimgpu.so          CUDA kernels + C ABI (include/svimgpu.h), sm_100a only
   svim_b200/synth/libsvimsynth.so  synthetic-input generator (host C++)
   svim_b200/libsvimio.so           BAM reader / writer (host C++)
-  svim_b200/libsvimbamgpu.so       EXPERIMENTAL on-GPU BAM decoder (csrc_next/, opt-in: svim_b200.io.read_bam_gpu)
+  svim_b200/_svimfastobj.so        CPython extension: Signature / SignatureCluster objects built in one C loop (csrc_host/fastobj.c)
 """
 import os
 import shutil
@@ -58,7 +58,8 @@ def build_all(force=False):
     build_gpu(force)
     synth.build(force)
     io.build_bamio(force)
-    io.build_bamgpu(force)          # experimental on-GPU BAM decoder: its own library, never loaded by the default path
+    from . import fastobj
+    fastobj.build(force)
 
 
 if __name__ == "__main__":

@@ -9,10 +9,12 @@
 #include "cluster.cu"
 #include "nccl.cu"
 #include "genotype.cu"
+#include "bam.cu"
 
 static const char* k_timing_names[T_N] = {
     "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
-    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype", "closest_deletion"};
+    "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype", "closest_deletion",
+    "bam_h2d+inflate", "bam_record_bounds", "bam_rows", "bam_fill", "bam_read_names"};
 
 extern "C" {
 
@@ -65,7 +67,7 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
                       &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
                       &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3], &ctx->d_xchg[4], &ctx->d_xchg[5], &ctx->d_xchg[6], &ctx->d_xchg[7],
-                      &ctx->d_genome_codes, &ctx->d_ins_codes, &ctx->d_myers_trace, &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
+                      &ctx->d_genome_codes, &ctx->d_ins_codes, &ctx->d_myers_trace, &ctx->d_big_list, &ctx->d_big_caps, &ctx->d_big_scratch, &ctx->d_cig16, &ctx->d_cig16_off, &ctx->d_cig16_err, &ctx->d_bam_names, &ctx->d_bam_name_off, &ctx->d_bam_rec_of_id, &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
     for (int i = 0; i < 48; ++i) ctx->d_myers_scratch[i].release();
@@ -158,10 +160,27 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
                               (size_t)n * 8, (size_t)n * 4, (size_t)n * 4, (size_t)s->cigar_words * 4, (size_t)s->seq_bytes, (size_t)s->sa_bytes};
     {
         StageTimer t(ctx, T_H2D);
+        const bool packed = s->cigar16 != nullptr && s->cigar16_off != nullptr;
         for (int i = 0; i < 14; ++i) {
             if (i == 12 && !with_seq) continue;   // SEQ blob stays on the host (lazy path)
             SVIM_CUDA(ctx->d_soa[i].ensure(bytes[i] + 64));
+            if (i == 11 && packed) continue;      // CIGAR crosses as the 16-bit stream below
             if (bytes[i]) SVIM_CUDA(cudaMemcpyAsync(ctx->d_soa[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (packed) {
+            // half the PCIe bytes: upload the packed stream, expand it to BAM's uint32 words in HBM (k_expand_cigar16 reads 2 B and
+            // writes 4 B per operation at HBM speed, ~25x the PCIe rate the copy just ran at)
+            SVIM_CUDA(ctx->d_cig16.ensure((size_t)s->cigar16_words * 2 + 64)); SVIM_CUDA(ctx->d_cig16_off.ensure((size_t)(n + 1) * 8));
+            SVIM_CUDA(ctx->d_cig16_err.ensure(16)); SVIM_CUDA(cudaMemsetAsync(ctx->d_cig16_err.p, 0, 4, ctx->stream));
+            if (s->cigar16_words) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16.p, s->cigar16, (size_t)s->cigar16_words * 2, cudaMemcpyHostToDevice, ctx->stream));
+            SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16_off.p, s->cigar16_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            if (n > 0) {
+                int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+                ctx->launches++;
+                k_expand_cigar16<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
+                                                                 ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                SVIM_CUDA(cudaGetLastError());
+            }
         }
     }
     DevSoa& d = ctx->soa;
@@ -171,11 +190,62 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
     d.seq_off = ctx->d_soa[7].as<uint64_t>(); d.sa_off = ctx->d_soa[8].as<uint64_t>(); d.sa_len = ctx->d_soa[9].as<uint32_t>();
     d.qname_id = ctx->d_soa[10].as<uint32_t>(); d.cigar = ctx->d_soa[11].as<uint32_t>(); d.seq = ctx->d_soa[12].as<uint8_t>(); d.sa = ctx->d_soa[13].as<uint8_t>();
     ctx->cigar_words = s->cigar_words; ctx->seq_bytes = s->seq_bytes; ctx->sa_bytes = s->sa_bytes;
+    uint32_t bad16 = 0;
+    if (s->cigar16 && s->cigar16_off && n > 0) SVIM_CUDA(cudaMemcpyAsync(&bad16, ctx->d_cig16_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (bad16) { ctx->have_soa = false; ctx->set_error(SVIMGPU_ERR_ARG, "cigar16: a record's packed stream does not hold n_cigar operations"); return SVIMGPU_ERR_ARG; }
     ctx->have_soa = true; ctx->collected = false;
     ctx->rows_resident = true; ctx->geno_ready = false;
     ctx->lazy_seq = !with_seq; ctx->h_seq = with_seq ? nullptr : s->seq; ctx->h_seq_off = with_seq ? nullptr : s->seq_off; ctx->lazy_aln_base = 0;
     timings_end(ctx);
+    return 0;
+}
+
+int svimgpu_decode_bam(svimgpu_ctx* ctx, const uint8_t* file, int64_t file_bytes, const svim_bgzf_block* blocks, int64_t n_blocks, int64_t first_record,
+                       int32_t n_ref, svim_bam_info* info) {
+    if (!ctx || (file_bytes > 0 && !file) || n_blocks < 0 || (n_blocks > 0 && !blocks) || first_record < 0) return SVIMGPU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->host_copy[0] || ctx->host_copy[1]) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
+    ctx->have_soa = false; ctx->rows_resident = false;
+    static_assert(sizeof(svim_bgzf_block) == sizeof(BgBlock), "block table layout");
+    timings_begin(ctx);
+    const int rc = bam_decode_run(ctx, file, file_bytes, (const BgBlock*)blocks, n_blocks, first_record, n_ref, info);
+    timings_end(ctx);
+    return rc;
+}
+
+int svimgpu_fetch_bam_names(svimgpu_ctx* ctx, uint8_t* names, uint64_t* name_off, uint32_t* rec_of_id, uint32_t* qname_id) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    if (!ctx->rows_resident || !ctx->d_bam_names.p) { ctx->set_error(SVIMGPU_ERR_STATE, "no BAM-decoded record buffer is resident"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->soa.n;
+    if (names && ctx->bam_names_bytes) SVIM_CUDA(cudaMemcpyAsync(names, ctx->d_bam_names.p, (size_t)ctx->bam_names_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (name_off && n) SVIM_CUDA(cudaMemcpyAsync(name_off, ctx->d_bam_name_off.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rec_of_id && ctx->bam_n_names) SVIM_CUDA(cudaMemcpyAsync(rec_of_id, ctx->d_bam_rec_of_id.p, (size_t)ctx->bam_n_names * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (qname_id && n) SVIM_CUDA(cudaMemcpyAsync(qname_id, ctx->d_soa[10].p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// the resident record buffer back on the host (tests: the GPU decoder against the host decoder; callers that want an AlignmentBatch)
+int svimgpu_download_alignments(svimgpu_ctx* ctx, int32_t* tid, int32_t* pos, uint16_t* flag, uint8_t* mapq, uint32_t* n_cigar, uint64_t* cigar_off, int32_t* l_seq,
+                                uint64_t* seq_off, uint64_t* sa_off, uint32_t* sa_len, uint32_t* qname_id, uint32_t* cigar, uint8_t* seq, uint8_t* sa) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    if (!ctx->rows_resident || !ctx->have_soa) { ctx->set_error(SVIMGPU_ERR_STATE, "no record buffer is resident"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)ctx->soa.n;
+    void* dst[14] = {tid, pos, flag, mapq, n_cigar, cigar_off, l_seq, seq_off, sa_off, sa_len, qname_id, cigar, seq, sa};
+    const size_t bytes[14] = {n * 4, n * 4, n * 2, n, n * 4, n * 8, n * 4, n * 8, n * 8, n * 4, n * 4, (size_t)ctx->cigar_words * 4, (size_t)ctx->seq_bytes, (size_t)ctx->sa_bytes};
+    for (int i = 0; i < 14; ++i) if (dst[i] && bytes[i]) SVIM_CUDA(cudaMemcpyAsync(dst[i], ctx->d_soa[i].p, bytes[i], cudaMemcpyDeviceToHost, ctx->stream));
+    SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int svimgpu_download_cigar(svimgpu_ctx* ctx, uint32_t* out, int64_t words) {
+    if (!ctx || !out || words < 0) return SVIMGPU_ERR_ARG;
+    if (!ctx->rows_resident || words > ctx->cigar_words) { ctx->set_error(SVIMGPU_ERR_STATE, "no resident record buffer of that size"); return SVIMGPU_ERR_STATE; }
+    cudaSetDevice(ctx->device);
+    if (words) SVIM_CUDA(cudaMemcpy(out, ctx->d_soa[11].p, (size_t)words * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -1,4 +1,4 @@
-// Groundwork for the on-GPU BAM decoder — NOT on the product path yet.
+// Host+device core of the on-GPU BAM decoder (bam.cu / bam_kernels.cu).
 //
 // Host+device (SVIM_HD) building blocks, written so that one GPU thread (lane 0 of a warp that owns a BGZF block, tables in
 // shared memory) and the host test harness run the same code:

@@ -700,8 +700,68 @@ __global__ void __launch_bounds__(32 * SCAN_BULK_WARPS, 3) k_cigar_scan_bulk(Dev
     if (lane == 0 && primaries) atomicAdd(cnt + CNT_PRIMARIES, primaries / 32);
 }
 
+// svim_aln_soa.cigar16 -> BAM uint32 CIGAR words (include/svimgpu.h).  One warp per record: every lane takes 8 packed words
+// (one 128-bit load) per round; a word without the 0xF nibble is its own uint32 image, so the common case is a widening copy
+// at HBM speed.  Rounds that hold a length-extension word (operations of 4096 bases and more) are decoded by lane 0 in order.
+__global__ void __launch_bounds__(256) k_expand_cigar16(const uint16_t* __restrict__ c16, const uint64_t* __restrict__ off16, const uint32_t* __restrict__ n_cigar,
+                                                         const uint64_t* __restrict__ cigar_off, int64_t n, uint32_t* __restrict__ cigar, uint32_t* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint16_t* src = c16 + off16[i];
+        const uint64_t nw = off16[i + 1] - off16[i];
+        uint32_t* dst = cigar + cigar_off[i];
+        const uint32_t nc = n_cigar[i];
+        uint64_t out = 0;            // operations written so far (warp-uniform)
+        uint64_t acc = 0;            // pending length-extension bits (warp-uniform: only lane 0's slow path changes it, then broadcasts)
+        for (uint64_t base = 0; base < nw; base += 256) {
+            const uint64_t at = base + (uint64_t)lane * 8;
+            uint4 v = make_uint4(0x000F000Fu, 0x000F000Fu, 0x000F000Fu, 0x000F000Fu);
+            if (at < nw) v = *(const uint4*)(src + at);
+            const uint32_t w2[4] = {v.x, v.y, v.z, v.w};
+            uint32_t w[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { w[2 * k] = w2[k] & 0xffffu; w[2 * k + 1] = w2[k] >> 16; }
+            uint32_t ext = 0, real_ext = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const uint32_t e = (w[k] & 15u) == 15u; ext |= e << k; real_ext |= (e && w[k] != 0x000Fu) ? 1u : 0u; }
+            if (__any_sync(0xffffffffu, real_ext) || acc) {
+                // in-order decode of this round by lane 0 (rare: only operations of >= 4096 bases need extension words)
+                uint64_t o = out, a = acc;
+                for (int l = 0; l < 32; ++l) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t x = __shfl_sync(0xffffffffu, w[k], l);
+                        if (lane == 0) {
+                            if ((x & 15u) == 15u) a = (a << 12) | (x >> 4);
+                            else { const uint64_t len = (a << 12) | (x >> 4); if (o < nc) dst[o] = (uint32_t)((len << 4) | (x & 15u)); ++o; a = 0; if (len >= (1ull << 28)) atomicExch(bad, 1u); }
+                        }
+                    }
+                }
+                out = __shfl_sync(0xffffffffu, o, 0); acc = __shfl_sync(0xffffffffu, a, 0);
+                continue;
+            }
+            const uint32_t cnt = 8u - (uint32_t)__popc(ext);
+            uint32_t pre = cnt;                              // inclusive warp scan
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const uint64_t mine = out + pre - cnt;
+            if (cnt == 8u && mine + 8 <= nc && ((mine & 3) == 0)) {
+                *(uint4*)(dst + mine) = make_uint4(w[0], w[1], w[2], w[3]); *(uint4*)(dst + mine + 4) = make_uint4(w[4], w[5], w[6], w[7]);
+            } else {
+                uint64_t o2 = mine;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (!((ext >> k) & 1u)) { if (o2 < nc) dst[o2] = w[k]; ++o2; }
+            }
+            out += __shfl_sync(0xffffffffu, pre, 31);
+        }
+        if (out != nc || acc) { if (lane == 0) atomicExch(bad, 1u); }
+        for (uint32_t k = nc + lane; k < ((nc + 3u) & ~3u); k += 32) dst[k] = 0u;      // records are padded to 16 bytes with zero words
+    }
+}
+
 __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
-                                                        SigQueue qm, SigQueue qt, uint32_t* cnt) {
+                                                        SigQueue qm, SigQueue qt, uint32_t* cnt, uint32_t* big_list) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_work) return;
     const ChainWork wk = work[w];
@@ -718,20 +778,21 @@ __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, 
         chain[n++] = s;
     }
     n = parse_sa_segments(a.sa + a.sa_off[i], (int)a.sa_len[i], ct, p, a.l_seq[i], chain, n, err);
+    if (err & CH_TOO_MANY) { big_list[atomicAdd(cnt + CNT_TOO_MANY, 1u)] = w; return; }      // more segments than the local arrays hold: nothing emitted here
     sort_chain(chain, n);
     PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
-    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err);
+    Junction junc[SVIM_MAX_SEGMENTS]; Tandem tand[SVIM_MAX_SEGMENTS];
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err, junc, tand);
     if (err & CH_BAD_FIELDS) atomicAdd(cnt + CNT_BAD_FIELDS, 1u);
     if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
     if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
-    if (err & CH_TOO_MANY) atomicAdd(cnt + CNT_TOO_MANY, 1u);
 }
 
 // query-sorted mode: segments are the read's REAL supplementary records (analyze_alignment_file_querysorted,
 // SVIM_COLLECT.py:113-123), listed per read group by the host in file order
 __global__ void __launch_bounds__(128) k_segment_chain_qs(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
                                                            const uint32_t* grp, const uint32_t* mem_off, const uint32_t* mem_idx, const SegSum* segsum,
-                                                           SigQueue qm, SigQueue qt, uint32_t* cnt) {
+                                                           SigQueue qm, SigQueue qt, uint32_t* cnt, uint32_t* big_list) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_work) return;
     const ChainWork wk = work[w];
@@ -749,16 +810,65 @@ __global__ void __launch_bounds__(128) k_segment_chain_qs(DevSoa a, ChainParams 
         const SegSum ss = segsum[j];
         const int32_t jr = (a.flag[j] & 0x10u) ? 1 : 0;
         if (jr && ss.read_len < 0) { err |= CH_NO_READLEN; continue; }
-        if (n >= SVIM_MAX_SEGMENTS) { err |= CH_TOO_MANY; break; }
+        if (n >= SVIM_MAX_SEGMENTS) { big_list[atomicAdd(cnt + CNT_TOO_MANY, 1u)] = w; return; }
         Seg s; s.tid = a.tid[j]; s.ref_start = a.pos[j]; s.ref_end = ss.ref_end; s.q_start = ss.q_start; s.q_end = ss.q_end; s.rev = jr;
         chain[n++] = s;
     }
     sort_chain(chain, n);
     PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
-    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err);
+    Junction junc[SVIM_MAX_SEGMENTS]; Tandem tand[SVIM_MAX_SEGMENTS];
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err, junc, tand);
     if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
     if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
-    if (err & CH_TOO_MANY) atomicAdd(cnt + CNT_TOO_MANY, 1u);
+}
+
+// ---- large-read pass: reads with more than SVIM_MAX_SEGMENTS segments (the reference has no limit, SVIM_inter.py:24-49) --------------
+// k_chain_big_caps sizes each listed read's arrays (an SA entry is at least 13 characters: "c,1,+,1M,0,0;"), the host lays them out in
+// one scratch buffer, k_segment_chain_big runs the same chain logic as the fast kernels with its arrays in that buffer, one thread
+// per read.  Rare by construction; the NO_READLEN skips of the fast attempt are counted here instead (the fast kernel returned early).
+__global__ void k_chain_big_caps(DevSoa a, const ChainWork* work, const uint32_t* big_list, uint32_t n_big, const uint32_t* grp, const uint32_t* mem_off,
+                                 uint32_t* caps) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_big) return;
+    const uint32_t i = work[big_list[k]].aln_idx;
+    caps[k] = grp ? (mem_off[grp[i] + 1] - mem_off[grp[i]]) + 2u : a.sa_len[i] / 13u + 3u;
+}
+
+struct BigScratch { Seg* seg; Junction* junc; Tandem* tand; const uint64_t* off; };
+
+__global__ void __launch_bounds__(64) k_segment_chain_big(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, const uint32_t* big_list, uint32_t n_big,
+                                                           const uint32_t* grp, const uint32_t* mem_off, const uint32_t* mem_idx, const SegSum* segsum,
+                                                           BigScratch sc, SigQueue qm, SigQueue qt, uint32_t* cnt) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_big) return;
+    const ChainWork wk = work[big_list[k]];
+    const uint32_t i = wk.aln_idx;
+    DeviceEmitter out{qm, qt, cnt + CNT_OVERFLOW};
+    const int cap = (int)(sc.off[k + 1] - sc.off[k]);
+    Seg* chain = sc.seg + sc.off[k]; Junction* junc = sc.junc + sc.off[k]; Tandem* tand = sc.tand + sc.off[k];
+    int n = 0;
+    uint32_t err = 0;
+    const int32_t rev = (a.flag[i] & 0x10u) ? 1 : 0;
+    if (rev && wk.read_len < 0) err |= CH_NO_READLEN;
+    else { Seg s; s.tid = a.tid[i]; s.ref_start = a.pos[i]; s.ref_end = wk.ref_end; s.q_start = wk.q_start; s.q_end = wk.q_end; s.rev = rev; chain[n++] = s; }
+    if (grp) {
+        const uint32_t g = grp[i];
+        for (uint32_t m = mem_off[g]; m < mem_off[g + 1] && n < cap; ++m) {
+            const uint32_t j = mem_idx[m];
+            const SegSum ss = segsum[j];
+            const int32_t jr = (a.flag[j] & 0x10u) ? 1 : 0;
+            if (jr && ss.read_len < 0) { err |= CH_NO_READLEN; continue; }
+            Seg s; s.tid = a.tid[j]; s.ref_start = a.pos[j]; s.ref_end = ss.ref_end; s.q_start = ss.q_start; s.q_end = ss.q_end; s.rev = jr;
+            chain[n++] = s;
+        }
+    } else n = parse_sa_segments(a.sa + a.sa_off[i], (int)a.sa_len[i], ct, p, a.l_seq[i], chain, n, err, cap);
+    if (err & CH_TOO_MANY) { atomicAdd(cnt + CNT_DATA_ERR, 1u); return; }      // cannot happen: cap bounds the entry count
+    sort_chain(chain, n);
+    PrimaryInfo pi; pi.aln_idx = i; pi.qname_id = a.qname_id[i]; pi.l_seq = a.l_seq[i]; pi.read_len = wk.read_len;
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, wk.ord_sig, wk.ord_twin, err, junc, tand);
+    if (err & CH_BAD_FIELDS) atomicAdd(cnt + CNT_BAD_FIELDS, 1u);
+    if (err & CH_NO_READLEN) atomicAdd(cnt + CNT_NO_READLEN, 1u);
+    if (err & CH_DATA_ERROR) atomicAdd(cnt + CNT_DATA_ERR, 1u);
 }
 
 // keys for restoring the reference's emission order: (record index | read group, ordinal)
@@ -980,24 +1090,44 @@ static int collect_run(svimgpu_ctx* ctx, svim_collect_stats* stats) {
         uint32_t n_work = h_cnt[CNT_WORK];
         {
             StageTimer t(ctx, T_CHAIN);
+            SVIM_CUDA(ctx->d_big_list.ensure((size_t)(n_work + 1) * 4));
             if (n_work > 0 && ctx->qs_mode)
                 { ctx->launches++; k_segment_chain_qs<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work,
                                                                         ctx->d_qs_grp.as<uint32_t>(), ctx->d_qs_mem_off.as<uint32_t>(), ctx->d_qs_mem_idx.as<uint32_t>(),
-                                                                        ctx->d_qs_segsum.as<SegSum>(), qm, qt, ctx->d_counters.as<uint32_t>()); }
+                                                                        ctx->d_qs_segsum.as<SegSum>(), qm, qt, ctx->d_counters.as<uint32_t>(), ctx->d_big_list.as<uint32_t>()); }
             else if (n_work > 0)
                 { ctx->launches++; k_segment_chain<<<(n_work + 127) / 128, 128, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), n_work, qm, qt,
-                                                                     ctx->d_counters.as<uint32_t>()); }
+                                                                     ctx->d_counters.as<uint32_t>(), ctx->d_big_list.as<uint32_t>()); }
         }
         SVIM_CUDA(cudaGetLastError());
         SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaStreamSynchronize(st));
+        if (const uint32_t n_big = h_cnt[CNT_TOO_MANY]) {          // reads with more segments than the fast path's arrays hold
+            StageTimer t(ctx, T_CHAIN);
+            const uint32_t* grp = ctx->qs_mode ? ctx->d_qs_grp.as<uint32_t>() : nullptr;
+            SVIM_CUDA(ctx->d_big_caps.ensure((size_t)(n_big + 2) * 12));
+            uint32_t* d_caps = ctx->d_big_caps.as<uint32_t>();
+            { ctx->launches++; k_chain_big_caps<<<(n_big + 127) / 128, 128, 0, st>>>(ctx->soa, ctx->d_work.as<ChainWork>(), ctx->d_big_list.as<uint32_t>(), n_big, grp,
+                                                                     ctx->d_qs_mem_off.as<uint32_t>(), d_caps); }
+            std::vector<uint32_t> caps(n_big); std::vector<uint64_t> off(n_big + 1, 0);
+            SVIM_CUDA(cudaMemcpyAsync(caps.data(), d_caps, (size_t)n_big * 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaStreamSynchronize(st));
+            for (uint32_t k = 0; k < n_big; ++k) off[k + 1] = off[k] + caps[k];
+            uint64_t* d_off = (uint64_t*)(d_caps + ((n_big + 2) & ~1u));
+            SVIM_CUDA(cudaMemcpyAsync(d_off, off.data(), (size_t)(n_big + 1) * 8, cudaMemcpyHostToDevice, st));
+            const size_t tot = (size_t)off[n_big];
+            SVIM_CUDA(ctx->d_big_scratch.ensure(tot * (sizeof(Seg) + sizeof(Junction) + sizeof(Tandem)) + 64));
+            BigScratch sc; sc.seg = ctx->d_big_scratch.as<Seg>(); sc.junc = (Junction*)(sc.seg + tot); sc.tand = (Tandem*)(sc.junc + tot); sc.off = d_off;
+            { ctx->launches++; k_segment_chain_big<<<(n_big + 63) / 64, 64, 0, st>>>(ctx->soa, cp, ct, ctx->d_work.as<ChainWork>(), ctx->d_big_list.as<uint32_t>(), n_big, grp,
+                                                                      ctx->d_qs_mem_off.as<uint32_t>(), ctx->d_qs_mem_idx.as<uint32_t>(), ctx->d_qs_segsum.as<SegSum>(), sc, qm, qt,
+                                                                      ctx->d_counters.as<uint32_t>()); }
+            SVIM_CUDA(cudaGetLastError());
+            SVIM_CUDA(cudaMemcpyAsync(h_cnt, ctx->d_counters.p, CNT_N * 4, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaStreamSynchronize(st));
+        }
         if (!h_cnt[CNT_OVERFLOW]) break;
         if (attempt == 5 || cap == 0x7fffffff) { ctx->set_error(SVIMGPU_ERR_LIMIT, "signature queue overflow"); return SVIMGPU_ERR_LIMIT; }
         cap = (uint32_t)std::min<uint64_t>((uint64_t)std::max(h_cnt[CNT_MAIN], h_cnt[CNT_TWIN]) + 1024, 0x7fffffffull);
-    }
-    if (h_cnt[CNT_TOO_MANY]) {
-        ctx->set_error(SVIMGPU_ERR_LIMIT, "%u reads have more than %d alignment segments", h_cnt[CNT_TOO_MANY], SVIM_MAX_SEGMENTS);
-        return SVIMGPU_ERR_LIMIT;
     }
     {
         StageTimer t(ctx, T_SORTBACK);

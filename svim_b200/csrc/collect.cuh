@@ -61,7 +61,7 @@ SVIM_HD int cigar_char_op(uint8_t c) {
 // retrieve_other_alignments: append the SA-derived segments that pass the MAPQ
 // filter of SVIM_COLLECT.py:154.  `chain[0]` is the primary.  Returns new count.
 SVIM_HD int parse_sa_segments(const uint8_t* sa, int sa_len, const ContigTable& ct, const ChainParams& p,
-                              int64_t prim_l_seq, Seg* chain, int n, uint32_t& err) {
+                              int64_t prim_l_seq, Seg* chain, int n, uint32_t& err, int cap = SVIM_MAX_SEGMENTS) {
     int i = 0;
     while (i < sa_len) {
         int e = i;
@@ -96,7 +96,7 @@ SVIM_HD int parse_sa_segments(const uint8_t* sa, int sa_len, const ContigTable& 
                         Seg s; int64_t rl; s.tid = tid;
                         cigsum_finish(cs, prim_l_seq, pos - 1, rev ? 1 : 0, s, rl);
                         if (rev && rl < 0) err |= CH_NO_READLEN;      // SVIM_inter.py:31-34: skipped
-                        else if (n >= SVIM_MAX_SEGMENTS) err |= CH_TOO_MANY;
+                        else if (n >= cap) err |= CH_TOO_MANY;       // the caller's arrays are full: the read goes to the large-read pass
                         else chain[n++] = s;
                     }
                 }
@@ -140,9 +140,8 @@ SVIM_HD void emit_bnd(E& out, bool twin, const ContigTable& ct, const PrimaryInf
 // ord_sig / ord_twin: running emission ordinals (bit 31 set by the caller).
 template <class E>
 SVIM_HD void analyze_chain(const Seg* chain, int n, const PrimaryInfo& pi, const ChainParams& p, const ContigTable& ct,
-                           E& out, uint32_t ord_sig, uint32_t ord_twin, uint32_t& err) {
-    Junction junc[SVIM_MAX_SEGMENTS]; int nj = 0;
-    Tandem tand[SVIM_MAX_SEGMENTS]; int nt = 0;
+                           E& out, uint32_t ord_sig, uint32_t ord_twin, uint32_t& err, Junction* junc, Tandem* tand) {
+    int nj = 0, nt = 0;            // junc / tand: room for n entries each (caller's storage)
     const int64_t lo = p.min_sv, hi = p.max_sv, tol_o = p.tol_o, tol_g = p.tol_g;
 
     for (int k = 0; k + 1 < n; ++k) {

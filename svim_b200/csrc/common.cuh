@@ -29,7 +29,7 @@ enum { OP_M = 0, OP_I = 1, OP_D = 2, OP_N = 3, OP_S = 4, OP_H = 5, OP_P = 6, OP_
 #define SVIM_MASK_REF_TRUE 0x18Du    // M D N = X
 #define SVIM_MASK_QLEN_H 0x1B3u      // M I S H = X
 
-static const int SVIM_MAX_SEGMENTS = 64;   // primary + SA entries analysed per read (documented limit)
+static const int SVIM_MAX_SEGMENTS = 64;   // primary + SA entries a read may have on the per-thread fast path; longer chains take the large-read pass
 
 // What SVIM_inter.py:28-47 reads from one alignment.
 struct Seg {

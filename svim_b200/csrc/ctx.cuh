@@ -80,7 +80,8 @@ enum {  // device counters
 
 enum {  // timing slots
     T_H2D = 0, T_SCAN, T_CHAIN, T_SORTBACK, T_GATHER, T_COLLECT_D2H, T_CSIG, T_KEYSORT, T_PARTITION, T_SAMPLE, T_PAIRS,
-    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_CUTPASTE, T_N
+    T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_CUTPASTE,
+    T_BAM_INFLATE, T_BAM_BOUNDS, T_BAM_ROWS, T_BAM_FILL, T_BAM_NAMES, T_N
 };
 
 struct SigSet {   // one signature list on the device (main / all_bnds twins)
@@ -110,6 +111,9 @@ struct svimgpu_ctx {
 
     // alignments
     DevBuf d_soa[14];
+    DevBuf d_cig16, d_cig16_off, d_cig16_err;
+    DevBuf d_bam_names, d_bam_name_off, d_bam_rec_of_id;   // svimgpu_decode_bam: read names (NUL-terminated), their offsets, first record of every name id
+    int64_t bam_names_bytes = 0; uint32_t bam_n_names = 0;      // 16-bit packed CIGAR stream as uploaded (svim_aln_soa.cigar16), expanded into d_soa[11]
     DevSoa soa; bool have_soa = false;
     int64_t cigar_words = 0, seq_bytes = 0, sa_bytes = 0;
     // lazy SEQ (collect_host): SEQ stays on the host, only the bytes of emitted insertions are staged and uploaded
@@ -119,6 +123,7 @@ struct svimgpu_ctx {
     DevBuf d_stage, d_stage_off;
 
     // collect state
+    DevBuf d_big_list, d_big_caps, d_big_scratch;    // large-read pass of the segment chain (reads above SVIM_MAX_SEGMENTS)
     DevBuf d_counters, d_queue[2], d_work, d_sort_tmp, d_keys[2], d_vals[2], d_scan;
     SigSet sets[2];
     bool collected = false;

@@ -610,4 +610,44 @@ int bamio_write(const char* path, const bamio_in* in, int level, int n_threads) 
     return 0;
 }
 
+
+// ---- 16-bit packed CIGAR (svim_aln_soa.cigar16, include/svimgpu.h) ------------------------------------------------------------
+// The record buffer crosses PCIe as CIGAR words; BAM's uint32 (len << 4 | op) is mostly zeros for long reads (mean run ~5 bases).
+// Packed form: uint16 (len << 4 | op) for len < 4096; a longer length is split: words with op nibble 0xF carry 12 more
+// significant bits each and precede the op word (decoder: acc = acc << 12 | hi12 on 0xF words; len = acc << 12 | hi12 on the
+// op word).  Every record's stream is padded to a multiple of 8 words with 0x000F (no-ops), so records stay 16-byte aligned.
+// Pass 1 (out16 == nullptr): off16[i] for every record and off16[n] = total words.  Pass 2: fills out16.
+int bamio_pack_cigar16(int64_t n, const uint32_t* n_cigar, const uint64_t* cigar_off, const uint32_t* cigar, uint64_t* off16, uint16_t* out16, int n_threads) {
+    if (n < 0 || (n > 0 && (!n_cigar || !cigar_off || !cigar || !off16))) return -1;
+    if (n_threads < 1) n_threads = 1;
+    auto words_of = [&](int64_t i) {
+        uint64_t w = 0;
+        const uint32_t* c = cigar + cigar_off[i];
+        for (uint32_t k = 0; k < n_cigar[i]; ++k) { const uint32_t len = c[k] >> 4; w += 1 + (len >= (1u << 12)) + (len >= (1u << 24)); }
+        return (w + 7) & ~7ull;
+    };
+    if (!out16) {
+        std::vector<uint64_t> cnt((size_t)n);
+        parallel_for((size_t)n, n_threads, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) cnt[i] = words_of((int64_t)i); });
+        uint64_t at = 0;
+        for (int64_t i = 0; i < n; ++i) { off16[i] = at; at += cnt[(size_t)i]; }
+        off16[n] = at;
+        return 0;
+    }
+    parallel_for((size_t)n, n_threads, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) {
+        const uint32_t* c = cigar + cigar_off[i];
+        uint16_t* o = out16 + off16[i];
+        uint64_t w = 0;
+        for (uint32_t k = 0; k < n_cigar[i]; ++k) {
+            const uint32_t len = c[k] >> 4, op = c[k] & 15u;
+            if (len >= (1u << 24)) o[w++] = (uint16_t)(((len >> 24) << 4) | 15u);
+            if (len >= (1u << 12)) o[w++] = (uint16_t)((((len >> 12) & 0xFFFu) << 4) | 15u);
+            o[w++] = (uint16_t)(((len & 0xFFFu) << 4) | op);
+        }
+        const uint64_t end = off16[i + 1] - off16[i];
+        while (w < end) o[w++] = 0x000F;
+    } });
+    return 0;
+}
+
 }  // extern "C"

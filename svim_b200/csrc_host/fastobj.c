@@ -58,7 +58,8 @@ static PyObject* fo_signatures(PyObject* self, PyObject* args) {
     PyObject *names, *qnames, *classes, *invdirs;
     if (!PyArg_ParseTuple(args, "y*y*OOOO", &sb, &ib, &names, &qnames, &classes, &invdirs)) return NULL;
     PyObject* out = NULL;
-    PyObject *s_cigar = NULL, *s_suppl = NULL, *s_fwd = NULL, *s_rev = NULL, *read_cache = NULL;
+    PyObject *s_cigar = NULL, *s_suppl = NULL, *s_fwd = NULL, *s_rev = NULL;
+    PyObject** name_cache = NULL; size_t name_cap = 0;
     const Py_ssize_t n = sb.len / (Py_ssize_t)sizeof(sig_t);
     const sig_t* sg = (const sig_t*)sb.buf;
     const char* ins = (const char*)ib.buf;
@@ -90,7 +91,13 @@ static PyObject* fo_signatures(PyObject* self, PyObject* args) {
     const int have_q = qnames != Py_None;
     if (have_q && !PyList_Check(qnames)) { PyErr_SetString(PyExc_TypeError, "qnames must be a list or None"); goto fail0; }
     const Py_ssize_t n_q = have_q ? PyList_GET_SIZE(qnames) : 0;
-    if (!have_q) read_cache = PyDict_New();
+    if (!have_q) {
+        uint32_t mx = 0;
+        for (Py_ssize_t k = 0; k < n; ++k) if (sg[k].qname_id > mx) mx = sg[k].qname_id;
+        name_cap = (size_t)mx + 1;
+        name_cache = (PyObject**)calloc(name_cap, sizeof(PyObject*));
+        if (!name_cache) { PyErr_NoMemory(); goto fail0; }
+    }
     out = PyList_New(n);
     if (!out) goto fail0;
     for (Py_ssize_t k = 0; k < n; ++k) {
@@ -104,16 +111,17 @@ static PyObject* fo_signatures(PyObject* self, PyObject* args) {
         if (have_q) {
             if ((Py_ssize_t)s->qname_id >= n_q) { PyErr_Format(PyExc_IndexError, "signature %zd: read id %u out of range", k, s->qname_id); goto fail; }
             PUT(o, o_read[t], PyList_GET_ITEM(qnames, s->qname_id));
-        } else {
-            PyObject* key = PyLong_FromUnsignedLong(s->qname_id);
-            if (!key) goto fail;
-            PyObject* r = PyDict_GetItem(read_cache, key);
+        } else {                               /* synthetic input without a name table: "read<id>", one string per id */
+            const uint32_t id = s->qname_id;
+            if (id >= name_cap) { PyErr_SetString(PyExc_RuntimeError, "signatures(): read id above the scanned maximum"); goto fail; }
+            PyObject* r = name_cache[id];
             if (!r) {
-                r = PyUnicode_FromFormat("read%u", s->qname_id);
-                if (!r || PyDict_SetItem(read_cache, key, r) < 0) { Py_XDECREF(r); Py_DECREF(key); goto fail; }
-                Py_DECREF(r);               /* the cache keeps it alive */
+                char buf[24];
+                const int len = snprintf(buf, sizeof buf, "read%u", id);
+                r = PyUnicode_FromStringAndSize(buf, len);
+                if (!r) goto fail;
+                name_cache[id] = r;             /* the cache owns one reference, released at the end */
             }
-            Py_DECREF(key);
             PUT(o, o_read[t], r);
         }
         PyObject* c1 = PyList_GET_ITEM(names, s->contig1);
@@ -148,7 +156,8 @@ fail:
     Py_CLEAR(out);
 fail0:
 done:
-    Py_XDECREF(s_cigar); Py_XDECREF(s_suppl); Py_XDECREF(s_fwd); Py_XDECREF(s_rev); Py_XDECREF(read_cache);
+    Py_XDECREF(s_cigar); Py_XDECREF(s_suppl); Py_XDECREF(s_fwd); Py_XDECREF(s_rev);
+    if (name_cache) { for (size_t k = 0; k < name_cap; ++k) Py_XDECREF(name_cache[k]); free(name_cache); }
     PyBuffer_Release(&sb); PyBuffer_Release(&ib);
     return out;
 }

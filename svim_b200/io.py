@@ -176,6 +176,7 @@ def _bamio_lib():
         lib.bamio_close.restype = None
         lib.bamio_layout.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.bamio_blocks.argtypes = [C.c_void_p, C.c_void_p]
+        lib.bamio_pack_cigar16.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _bamio = lib
     return _bamio
 
@@ -236,21 +237,37 @@ def read_bam_native(path: str, threads: int = 0) -> AlignmentBatch:
 
 
 BGZF_BLOCK_DTYPE = np.dtype([("coff", "<u8"), ("uoff", "<u8"), ("clen", "<u4"), ("ulen", "<u4")])
-_BAMGPU_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc_next", "bamgpu.cu")
-_BAMGPU_SO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsvimbamgpu.so")
-_bamgpu = None
 
 
-def build_bamgpu(force: bool = False) -> str:
-    """nvcc build of the EXPERIMENTAL on-GPU BAM decoder (csrc_next/bamgpu.cu) into its own library."""
-    import subprocess
-    deps = [_BAMGPU_SRC, os.path.join(os.path.dirname(_BAMGPU_SRC), "bgzf_core.cuh")]
-    if force or not os.path.exists(_BAMGPU_SO) or any(os.path.getmtime(_BAMGPU_SO) < os.path.getmtime(d) for d in deps):
-        from .build import nvcc_path, run_atomic
-        run_atomic([nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler",
-                    "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static",
-                    "-o", "@OUT@", _BAMGPU_SRC], _BAMGPU_SO)
-    return _BAMGPU_SO
+def pack_cigar16(batch, threads: int = 0):
+    """(cigar16, cigar16_off) of a batch: the 16-bit packed CIGAR stream of include/svimgpu.h, built by csrc_host/bamio.cpp."""
+    lib = _bamio_lib()
+    threads = threads or (os.cpu_count() or 8)
+    n = batch.n
+    off = np.zeros(n + 1, dtype=np.uint64)
+    args = (n, batch.n_cigar.ctypes.data, batch.cigar_off.ctypes.data, batch.cigar.ctypes.data if batch.cigar.size else None)
+    if lib.bamio_pack_cigar16(*args, off.ctypes.data, None, threads) != 0:
+        raise ValueError("pack_cigar16: bad arguments")
+    out = np.empty(int(off[n]), dtype=np.uint16)
+    if lib.bamio_pack_cigar16(*args, off.ctypes.data, out.ctypes.data if out.size else None, threads) != 0:
+        raise ValueError("pack_cigar16: bad arguments")
+    return out, off
+
+
+def unpack_cigar16(cigar16, off16, n_cigar):
+    """Inverse of pack_cigar16 in numpy/Python (tests): list of uint32 arrays, one per record."""
+    out = []
+    for i in range(len(n_cigar)):
+        w = cigar16[int(off16[i]):int(off16[i + 1])].astype(np.uint64)
+        ops = []; acc = 0
+        for x in w.tolist():
+            if x & 15 == 15:
+                acc = (acc << 12) | (x >> 4)
+            else:
+                ops.append((((acc << 12) | (x >> 4)) << 4) | (x & 15)); acc = 0
+        assert len(ops) == int(n_cigar[i])
+        out.append(np.asarray(ops, dtype=np.uint32))
+    return out
 
 
 def bgzf_layout(path: str):
@@ -280,55 +297,77 @@ def bgzf_layout(path: str):
         lib.bamio_close(h)
 
 
-def read_bam_gpu(path: str, device: int = 0, stats: dict = None) -> AlignmentBatch:
-    """EXPERIMENTAL: BAM -> AlignmentBatch with the BGZF blocks inflated and the records parsed on
-    the GPU (csrc_next/bamgpu.cu).  Same result as read_bam_native; raises when the GPU path declines (then use the host decoder)."""
-    import ctypes as C
-    global _bamgpu
-    if _bamgpu is None:
-        lib = C.CDLL(build_bamgpu())
-        lib.bamgpu_decode.restype = C.c_void_p
-        lib.bamgpu_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
-        lib.bamgpu_fetch.argtypes = [C.c_void_p] * 16
-        lib.bamgpu_error.restype = C.c_char_p
-        lib.bamgpu_error.argtypes = [C.c_void_p]
-        lib.bamgpu_free.argtypes = [C.c_void_p]
-        lib.bamgpu_free.restype = None
-        _bamgpu = lib
-    lib = _bamgpu
-    blocks, first, names, lengths, so = bgzf_layout(path)
-    raw = np.fromfile(path, dtype=np.uint8)
+#: how often the GPU BAM decoder was used / declined a file and the host decoder took over (never silent: see decode_bam_resident)
+BAM_DECODE_COUNTS = {"gpu": 0, "host_fallback": 0}
 
-    class Info(C.Structure):
-        _fields_ = [(n, C.c_int64) for n in ("n_records", "cigar_words", "seq_bytes", "sa_bytes", "names_bytes")] + \
-                   [(n, C.c_double) for n in ("ms_h2d", "ms_inflate", "ms_parse")]
-    inf = Info(); rc = C.c_int()
-    h = lib.bamgpu_decode(raw.ctypes.data, raw.size, blocks.ctypes.data, len(blocks), first, len(names), device, C.byref(inf), C.byref(rc))
+
+class ResidentBatch:
+    """What `decode_bam_resident` returns: the record buffer lives in HBM (filled by svimgpu_decode_bam), the host keeps the header
+    and fetches read names only when somebody asks for them.  Quacks like AlignmentBatch where the host mirror needs it
+    (contig_names, contig_lengths, n, sort_order, qnames / qname)."""
+
+    def __init__(self, ctx, info, contig_names, contig_lengths, sort_order):
+        self.ctx, self.info = ctx, info
+        self.contig_names = list(contig_names); self.contig_lengths = np.asarray(contig_lengths, dtype=np.int64)
+        self.n = int(info.n_records); self.sort_order = sort_order
+        self._qnames = None
+
+    @property
+    def qnames(self):
+        """list[str] indexed by qname_id (first-appearance numbering, like the host decoders)"""
+        if self._qnames is None:
+            names, off, rec, _qid = self.ctx.fetch_bam_names(self.info)
+            blob = names.tobytes()
+            starts = off[rec].tolist()
+            self._qnames = [blob[s:blob.index(b"\x00", s)].decode("ascii") for s in starts]
+        return self._qnames
+
+    def qname(self, qid: int) -> str:
+        return self.qnames[qid]
+
+    def to_batch(self) -> AlignmentBatch:
+        """D2H of everything (tests; callers that want the flattened buffer on the host)."""
+        arrays, cigar, seq, sa = self.ctx.download_alignments(self.info)
+        return AlignmentBatch(self.contig_names, self.contig_lengths, arrays, cigar, seq, sa, self.qnames, self.sort_order)
+
+
+def decode_bam_resident(path: str, ctx=None, stats: dict = None, fallback: bool = True):
+    """BAM file -> record buffer resident in HBM, decoded on the GPU (svimgpu_decode_bam: the compressed file crosses PCIe, BGZF inflate,
+    record boundaries, rows, blobs and read-name ids run on the device).  Returns a ResidentBatch; svimgpu_collect runs on it directly.
+    When the device decoder declines the file (malformed stream, a speculative record boundary or a name hash that does not verify)
+    the host decoder takes over — counted in BAM_DECODE_COUNTS and logged, never silent — and an AlignmentBatch is returned."""
+    import logging
+    import time
+    from . import _lib, runtime
+    ctx = ctx or runtime.context()
+    t0 = time.perf_counter()
+    blocks, first, names, lengths, so = bgzf_layout(path)
+    t1 = time.perf_counter()
+    raw = np.memmap(path, dtype=np.uint8, mode="r") if os.path.getsize(path) else np.zeros(0, np.uint8)
     try:
-        if rc.value != 0:
-            raise ValueError("read_bam_gpu(%s): rc %d: %s" % (path, rc.value, lib.bamgpu_error(h).decode()))
-        n = inf.n_records
-        arrays = {name: np.empty(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
-        name_off = np.empty(n, dtype=np.uint64)
-        cigar = np.empty(inf.cigar_words, dtype=np.uint32); seq = np.empty(inf.seq_bytes, dtype=np.uint8)
-        sa = np.empty(max(1, inf.sa_bytes), dtype=np.uint8); nblob = np.empty(max(1, inf.names_bytes), dtype=np.uint8)
-        p = lambda a: a.ctypes.data
-        if lib.bamgpu_fetch(h, p(arrays["tid"]), p(arrays["pos"]), p(arrays["flag"]), p(arrays["mapq"]), p(arrays["n_cigar"]), p(arrays["cigar_off"]),
-                            p(arrays["l_seq"]), p(arrays["seq_off"]), p(arrays["sa_off"]), p(arrays["sa_len"]), p(name_off), p(cigar), p(seq), p(sa), p(nblob)) != 0:
-            raise ValueError("read_bam_gpu(%s): %s" % (path, lib.bamgpu_error(h).decode()))
-        if stats is not None:
-            stats.update(ms_h2d=inf.ms_h2d, ms_inflate=inf.ms_inflate, ms_parse=inf.ms_parse)
+        info = ctx.decode_bam(raw, blocks, first, len(names))
+    except _lib.SvimGpuError as e:
+        if not fallback or e.code != -5:
+            raise
+        BAM_DECODE_COUNTS["host_fallback"] += 1
+        logging.warning("GPU BAM decoder declined %s (%s): decoding on the host", path, e)
+        return read_bam_native(path)
+    BAM_DECODE_COUNTS["gpu"] += 1
+    if stats is not None:
+        stats.update({k: v for k, v in ctx.timings().items() if k.startswith("bam_")})
+        stats.update(index_s=t1 - t0, decode_s=time.perf_counter() - t1, bam_bytes=int(raw.size), inflated_bytes=int(info.inflated_bytes))
+    return ResidentBatch(ctx, info, names, lengths, so)
+
+
+def read_bam_gpu(path: str, device: int = 0, stats: dict = None) -> AlignmentBatch:
+    """BAM -> AlignmentBatch with the BGZF blocks inflated and the records parsed on the GPU, then copied back.
+    Same result as read_bam_native (tests/test_gpu_bam.py); raises when the GPU path declines the file."""
+    from . import _lib
+    ctx = _lib.Context(device=device)
+    try:
+        return decode_bam_resident(path, ctx, stats, fallback=False).to_batch()
     finally:
-        lib.bamgpu_free(h)
-    # read-name ids on the host (first version): dense ids in order of first appearance, like the host decoder
-    parts = nblob[:inf.names_bytes].tobytes().split(b"\x00")[:n]
-    ids = {}
-    qid = np.empty(n, dtype=np.uint32)
-    for k, nm in enumerate(parts):
-        qid[k] = ids.setdefault(nm, len(ids))
-    arrays["qname_id"] = qid
-    qnames = [x.decode("ascii") for x in ids]
-    return AlignmentBatch(names, lengths, arrays, cigar, seq, sa[:inf.sa_bytes], qnames, so)
+        ctx.close()
 
 
 def write_bam_native(path: str, batch: AlignmentBatch, level: int = 1, threads: int = 0):

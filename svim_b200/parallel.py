@@ -27,8 +27,9 @@ def shard_ranges(n_cigar: np.ndarray, world: int):
 
 
 def shard_batch(batch: AlignmentBatch, rank: int, world: int) -> AlignmentBatch:
+    """This rank's record range with its own blobs (offsets rebased): only the shard is uploaded and held in HBM."""
     lo, hi = shard_ranges(batch.n_cigar, world)[rank]
-    return batch.slice(lo, hi)
+    return batch.compact_slice(lo, hi)
 
 
 def exchange_layout(n_local: int):

@@ -116,6 +116,8 @@ class AlignmentBatch:
         self.sa = np.ascontiguousarray(sa, dtype=np.uint8)
         self.qnames = qnames  # list[str] indexed by qname_id, or None (synthetic: "read<id>")
         self.sort_order = sort_order
+        self.cigar16 = None       # optional 16-bit packed CIGAR stream + per-record offsets (pack_cigar16); what crosses PCIe when present
+        self.cigar16_off = None
         self._tid_of = {n: i for i, n in enumerate(self.contig_names)}
 
     # -- header-like helpers (what the reference asks of `bam`) -------------
@@ -157,6 +159,13 @@ class AlignmentBatch:
         return int(self.n * self.ROW_BYTES + 4 * int(self.n_cigar.sum(dtype=np.int64))
                    + int(self.sa_len.sum(dtype=np.int64)))
 
+    def pack_cigar16(self, threads: int = 0) -> "AlignmentBatch":
+        """Build the 16-bit packed CIGAR stream of include/svimgpu.h (svim_aln_soa.cigar16) for this batch's records; the C ABI then
+        uploads it instead of the uint32 words (half the PCIe bytes) and expands it on the device.  Host-side re-encoding only."""
+        from . import io as sio
+        self.cigar16, self.cigar16_off = sio.pack_cigar16(self, threads)
+        return self
+
     def take(self, order, sort_order: str = "unknown") -> "AlignmentBatch":
         """Records re-ordered by `order` (index array); blobs are shared, only the row arrays are permuted."""
         order = np.asarray(order, dtype=np.int64)
@@ -168,6 +177,30 @@ class AlignmentBatch:
         arrays = {name: getattr(self, name)[lo:hi] for name, _ in self.FIELDS}
         return AlignmentBatch(self.contig_names, self.contig_lengths, arrays,
                               self.cigar, self.seq, self.sa, self.qnames, self.sort_order)
+
+
+def _compact_slice(batch: "AlignmentBatch", lo: int, hi: int) -> "AlignmentBatch":
+    """Records [lo, hi) with their OWN blobs: the CIGAR / SEQ / SA sub-ranges are cut out and the offsets rebased, so a rank that
+    uploads the result moves (and holds) only its shard.  Requires the blobs to be laid out in record order (true for every reader
+    and generator in this package)."""
+    arrays = {name: getattr(batch, name)[lo:hi].copy() for name, _ in batch.FIELDS}
+    if hi <= lo:
+        return AlignmentBatch(batch.contig_names, batch.contig_lengths, arrays, np.zeros(0, np.uint32), np.zeros(0, np.uint8), np.zeros(0, np.uint8),
+                              batch.qnames, batch.sort_order)
+    blobs = {}
+    for blob, off, length in (("cigar", "cigar_off", (batch.n_cigar[lo:hi].astype(np.int64) + 3) & ~3),
+                              ("seq", "seq_off", (batch.l_seq[lo:hi].astype(np.int64) + 1) // 2),
+                              ("sa", "sa_off", batch.sa_len[lo:hi].astype(np.int64))):
+        o = getattr(batch, off)[lo:hi].astype(np.int64)
+        b0 = int(o.min()); b1 = int((o + length).max())
+        if (np.diff(o) < 0).any():
+            raise ValueError("compact slice needs the %s blob in record order" % blob)
+        blobs[blob] = getattr(batch, blob)[b0:b1].copy()
+        arrays[off] = (o - b0).astype(np.uint64)
+    return AlignmentBatch(batch.contig_names, batch.contig_lengths, arrays, blobs["cigar"], blobs["seq"], blobs["sa"], batch.qnames, batch.sort_order)
+
+
+AlignmentBatch.compact_slice = _compact_slice
 
 
 class BatchBuilder:

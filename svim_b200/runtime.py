@@ -19,6 +19,9 @@ def context(device: int = None) -> "_lib.Context":
     if ctx is None:
         ctx = _lib.Context(device=device)
         _CTX[device] = ctx
+    pre = getattr(ctx, "cluster_prefetch", None)
+    if pre is not None:           # a CLUSTER started behind COLLECT's object building (SVIM_COLLECT._ClusterPrefetch) owns the context until it ends
+        pre.t.join()
     return ctx
 
 

@@ -73,6 +73,12 @@ def _get():
         lib.synth_fill.argtypes = [ctypes.POINTER(_Config), ctypes.c_void_p, ctypes.POINTER(_Out)]
         lib.synth_free.restype = None
         lib.synth_free.argtypes = [ctypes.c_void_p]
+        lib.synth_plan_ncigar.restype = None
+        lib.synth_plan_ncigar.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        lib.synth_range_sizes.restype = None
+        lib.synth_range_sizes.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(_Sizes)]
+        lib.synth_fill_range.restype = None
+        lib.synth_fill_range.argtypes = [ctypes.POINTER(_Config), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(_Out)]
         _lib = lib
     return _lib
 
@@ -173,6 +179,56 @@ def generate(names, lengths, n_reads, seed, svs, alleles, len_mean=15000, len_sd
     lib.synth_fill(ctypes.byref(cfg), handle, ctypes.byref(out))
     lib.synth_free(handle)
     return AlignmentBatch(names, clen, arrays, cigar, seq, sa[:sizes.sa_bytes], None, "coordinate")
+
+
+def generate_shard(names, lengths, n_reads, seed, svs, alleles, rank, world, len_mean=15000, len_sd=3000, len_min=1000, len_max=40000,
+                   p_ins=0.07, p_del=0.04, geo_ins=0.75, geo_del=0.80, p_lowmapq=0.02, p_secondary=0.01, p_unmapped=0.005, p_split=0.4):
+    """Rank `rank`'s contiguous record range of the same coordinate-sorted output `generate` would produce: the whole input is
+    planned (every rank plans the same reads), the range is cut by CIGAR volume (svim_b200.parallel.shard_ranges) and only its
+    records are materialised.  Returns (batch of the range with range-relative blob offsets, first record index, total records)."""
+    from ..parallel import shard_ranges
+    lib = _get()
+    clen = np.asarray(lengths, dtype=np.int64)
+    names_b = b"\x00".join(n.encode() for n in names) + b"\x00"
+    svs = np.ascontiguousarray(svs); alleles = np.ascontiguousarray(alleles, dtype=np.uint8)
+    cfg = _Config(seed, len(names), 0, clen.ctypes.data, names_b, n_reads, len_mean, len_sd, len_min, len_max,
+                  p_ins, p_del, geo_ins, geo_del, p_lowmapq, p_secondary, p_unmapped, p_split,
+                  len(svs), svs.ctypes.data, alleles.ctypes.data)
+    sizes = _Sizes()
+    handle = lib.synth_plan(ctypes.byref(cfg), ctypes.byref(sizes))
+    total = sizes.n_records
+    n_cigar = np.zeros(total, dtype=np.uint32)
+    lib.synth_plan_ncigar(handle, n_cigar.ctypes.data)
+    lo, hi = shard_ranges(n_cigar, world)[rank]
+    rs = _Sizes()
+    lib.synth_range_sizes(handle, lo, hi, ctypes.byref(rs))
+    n = hi - lo
+    arrays = {name: np.zeros(n, dtype=dt) for name, dt in AlignmentBatch.FIELDS}
+    cigar = np.zeros(rs.cigar_words, dtype=np.uint32)
+    seq = np.zeros(rs.seq_bytes, dtype=np.uint8)
+    sa = np.zeros(max(1, rs.sa_bytes), dtype=np.uint8)
+    out = _Out(*[arrays[k].ctypes.data for k in ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off",
+                                                  "sa_off", "sa_len", "qname_id")], cigar.ctypes.data, seq.ctypes.data, sa.ctypes.data)
+    lib.synth_fill_range(ctypes.byref(cfg), handle, lo, hi, ctypes.byref(out))
+    lib.synth_free(handle)
+    return AlignmentBatch(names, clen, arrays, cigar, seq, sa[:rs.sa_bytes], None, "coordinate"), lo, total
+
+
+def config_layout(name: str, scale: float = 1.0):
+    """(contig names, lengths, reads, seed, planting keywords, generator keywords) of a BASELINE config at `scale`."""
+    c = dict(CONFIGS[name])
+    n_contigs = c.pop("contigs"); G = int(c.pop("genome") * scale); reads = max(10, int(c.pop("reads") * scale))
+    seed = c.pop("seed")
+    if n_contigs == 1:
+        names, lengths = ["chr1"], [G]
+    else:
+        tot = sum(_HUMAN)
+        names = ["chr%d" % (i + 1) for i in range(22)] + ["chrX", "chrY"]
+        lengths = [max(200_000, int(G * h / tot)) for h in _HUMAN]
+    hotspots = int(round(c.pop("hotspots", 0) * scale)) if "hotspots" in c else 0
+    plant_kw = {k: c.pop(k) for k in ("spacing", "mix", "ins_size_uniform", "hotspot_svs") if k in c}
+    plant_kw["hotspots"] = hotspots
+    return names, lengths, reads, seed, plant_kw, c
 
 
 # human chr1-22,X,Y lengths (Mb, rounded) used only as proportions for config 4

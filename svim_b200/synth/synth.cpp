@@ -241,7 +241,7 @@ struct Gen {
         if (unmapped) {
             RecMeta& m = plan->rec[plan->n_rec++];
             m = RecMeta{-1, -1, 4, 0, 0, (int32_t)std::min<int64_t>(L, 2000), 0, (uint32_t)r, 0};
-            if (out) {
+            if (out && (*slots)[0] >= 0) {
                 int64_t k = (*slots)[0];
                 fill_fixed(out, k, m);
                 fill_random_seq(out->seq + out->seq_off[k], m.l_seq, mix(c.seed ^ 0x5eed, (uint64_t)r));
@@ -423,6 +423,7 @@ struct Gen {
             if (!out) continue;
             // ---- fill ---------------------------------------------------------------------------
             int64_t slot = (*slots)[k];
+            if (slot < 0) continue;                       // record outside the range being filled (synth_fill_range)
             fill_fixed(out, slot, m);
             uint32_t* cg = out->cigar + out->cigar_off[slot];
             size_t w = 0;
@@ -534,6 +535,43 @@ void synth_fill(const SynthConfig* cfg, void* handle, SynthOut* out) {
     for (int64_t r = 0; r < cfg->n_reads; ++r) {
         ReadPlan tmp;
         std::vector<int64_t> slots(st->slot_of.begin() + r * 4, st->slot_of.begin() + r * 4 + 4);
+        gen.make_read(r, &tmp, out, &slots);
+    }
+}
+
+// n_cigar of every planned record, in output order (callers shard the record range by CIGAR volume before filling)
+void synth_plan_ncigar(void* handle, uint32_t* out) {
+    PlanState* st = (PlanState*)handle;
+    for (size_t i = 0; i < st->sorted.size(); ++i) out[i] = st->sorted[i].n_cigar;
+}
+
+// Blob sizes of the record range [lo, hi) of the plan.
+void synth_range_sizes(void* handle, int64_t lo, int64_t hi, SynthSizes* sizes) {
+    PlanState* st = (PlanState*)handle;
+    SynthSizes s{hi - lo, 0, 0, 0};
+    for (int64_t i = lo; i < hi; ++i) { const RecMeta& m = st->sorted[(size_t)i]; s.cigar_words += (m.n_cigar + 3) & ~3u; s.seq_bytes += (m.l_seq + 1) / 2; s.sa_bytes += m.sa_len; }
+    *sizes = s;
+}
+
+// Phase 2 for one contiguous record range [lo, hi) of the coordinate-sorted output: rows and blobs of those records only, offsets
+// relative to the range (one rank's shard of a large input; the other records are never materialised).
+void synth_fill_range(const SynthConfig* cfg, void* handle, int64_t lo, int64_t hi, SynthOut* out) {
+    PlanState* st = (PlanState*)handle;
+    Gen gen(*cfg);
+    uint64_t co = 0, so = 0, sao = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+        const RecMeta& m = st->sorted[(size_t)i];
+        out->cigar_off[i - lo] = co; co += (m.n_cigar + 3) & ~3u;
+        out->seq_off[i - lo] = so; so += (m.l_seq + 1) / 2;
+        out->sa_off[i - lo] = sao; sao += m.sa_len;
+    }
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t r = 0; r < cfg->n_reads; ++r) {
+        std::vector<int64_t> slots(4, -1);
+        bool any = false;
+        for (int k = 0; k < 4; ++k) { const int64_t sl = st->slot_of[(size_t)r * 4 + k]; if (sl >= lo && sl < hi) { slots[k] = sl - lo; any = true; } }
+        if (!any) continue;
+        ReadPlan tmp;
         gen.make_read(r, &tmp, out, &slots);
     }
 }

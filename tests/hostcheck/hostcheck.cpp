@@ -35,7 +35,8 @@ int hc_chain(int32_t tid, int32_t pos, uint32_t flag, int64_t l_seq, const uint3
     } else if (!(rev && rl < 0)) chain[n++] = s;
     sort_chain(chain, n);
     PrimaryInfo pi{0, 0, l_seq, rl};
-    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, 0x80000000u, 0x80000000u, err);
+    Junction junc[SVIM_MAX_SEGMENTS]; Tandem tand[SVIM_MAX_SEGMENTS];
+    if (n >= 2) analyze_chain(chain, n, pi, p, ct, out, 0x80000000u, 0x80000000u, err, junc, tand);
     *n_main = (int32_t)out.m.size(); *n_twin = (int32_t)out.t.size();
     for (size_t k = 0; k < out.m.size() && (int)k < cap; ++k) out_main[k] = out.m[k];
     for (size_t k = 0; k < out.t.size() && (int)k < cap; ++k) out_twin[k] = out.t[k];
@@ -155,8 +156,8 @@ long long hc_myers_tpp(const uint8_t* pat, long long m, const uint8_t* txt, long
 int hc_tpp_plan(long long m, long long n, int num, int add, int* a_out) { const TppPlan p = tpp_plan(m, n, num, add); *a_out = p.a; return p.B; }
 }
 
-// ---- groundwork for the on-GPU BAM decoder (csrc_next/bgzf_core.cuh): raw DEFLATE of a BGZF payload, record-start search ----
-#include "../../svim_b200/csrc_next/bgzf_core.cuh"
+// ---- host+device core of the on-GPU BAM decoder (csrc/bgzf_core.cuh): raw DEFLATE of a BGZF payload, record-start search ----
+#include "../../svim_b200/csrc/bgzf_core.cuh"
 extern "C" {
 int hc_bgzf_inflate(const uint8_t* src, unsigned clen, uint8_t* dst, unsigned ulen) {
     std::vector<uint32_t> tab(BGZF_TABLE_WORDS);

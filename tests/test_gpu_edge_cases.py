@@ -2,6 +2,7 @@
 (empty / ragged input, missing SEQ, hard clips, N operations, malformed SA entries, MAPQ overflow,
 Python slice clamping, --all_bnds twins) — CUDA path vs oracle, plus the error codes for inputs the
 reference itself raises on."""
+import numpy as np
 import pytest
 
 from gpu_common import run_gpu, sig_rows
@@ -100,12 +101,43 @@ def test_inputs_the_reference_raises_on_return_errors(gpu_ctx):
         gpu_ctx.set_contigs(batch.contig_names)
         st = gpu_ctx.collect_host(batch)
         assert st.n_data_errors == 1
-    # more than SVIM_MAX_SEGMENTS alignment segments in one read is a documented limit
-    b = BatchBuilder(NAMES, [10**6] * 3)
-    b.add("y", 0, 0, 10000, 60, "100M9900S", seq, "".join("chr1,%d,+,%dS100M%dS,60,0;" % (20000 + 300 * k, 100 + 100 * k, 9800 - 100 * k) for k in range(70)))
-    with pytest.raises(_lib.SvimGpuError) as e:
-        gpu_ctx.collect_host(b.finish())
-    assert e.value.code == -4
+
+
+def test_reads_with_hundreds_of_segments_take_the_large_read_pass(gpu_ctx):
+    """The reference has no limit on the segments of a read (SVIM_inter.py:24-49).  Reads above the 64 the per-thread arrays hold
+    (70, 200 and 700 SA entries here: deletions, tandem duplications, junctions to other contigs and strands) go through
+    k_segment_chain_big and must still be the oracle's signatures, in emission order, next to ordinary reads."""
+    import random
+    rng = random.Random(5)
+    seq = "ACGT" * 25000
+    b = BatchBuilder(NAMES, [10**7] * 3)
+    b.add("small", 0, 0, 5000, 60, "5000M5000S", seq[:10000], "chr1,20001,+,5000S5000M,60,10;")
+    for name, k_seg in (("y70", 70), ("y200", 200), ("y700", 700)):
+        step = 100000 // (k_seg + 1)
+        sa = []
+        ref = 200000
+        for k in range(k_seg):
+            lead = step * (k + 1)
+            kind = rng.random()
+            contig, strand = "chr1", "+"
+            if kind < 0.5:
+                ref += step + rng.choice([0, 60, 500, 7000])            # next segment downstream: nothing / deletion of various sizes
+            elif kind < 0.7:
+                ref -= rng.choice([80, 300, 2000])                      # overlap on the reference: tandem duplication
+            elif kind < 0.85:
+                contig = rng.choice(["chr10", "chr2"]); ref = rng.randrange(1000, 900000)
+            else:
+                strand = "-"
+            sa.append("%s,%d,%s,%dS%dM%dS,60,0;" % (contig, ref + 1, strand, lead, step, 100000 - lead - step))
+        b.add(name, 0, 0, 100000, 60, "%dM%dS" % (step, 100000 - step), seq, "".join(sa))
+    b.add("small2", 0, 0, 300000, 60, "5000M5000S", seq[:10000], "chr1,320001,+,5000S5000M,60,10;")
+    batch = b.finish()
+    for kw in ({}, {"all_bnds": True}, {"max_sv_size": 3000}):
+        st, rows, tw = _collect(gpu_ctx, batch, **kw)
+        want, want_t = _oracle(batch, **kw)
+        assert rows == want, kw
+        assert tw == want_t, kw
+        assert st.n_data_errors == 0 and len(rows) > 300
 
 
 def test_cluster_state_errors(gpu_ctx):
@@ -116,3 +148,43 @@ def test_cluster_state_errors(gpu_ctx):
     with pytest.raises(_lib.SvimGpuError):
         ctx.use_collected(0)
     ctx.close()
+
+
+def test_packed_cigar16_upload_expands_to_the_same_words(gpu_ctx, golden):
+    """svim_aln_soa.cigar16 (16-bit packed CIGAR stream, half the PCIe bytes): the device expansion must give back the caller's
+    uint32 words record for record — zero padding included — and COLLECT must not notice the difference.  Operations of 4096,
+    2^24 and 2^28-1 bases take the extension words; a stream that does not hold n_cigar operations is refused."""
+    from svim_b200 import io as sio
+    rng = np.random.default_rng(3)
+    b = BatchBuilder(NAMES, [10**9] * 3)
+    b.add("long", 0, 0, 100, 60, [(0, 5), (2, 4095), (0, 1), (2, 4096), (1, 70000), (3, 20000000), (0, 3), (4, 2**28 - 1)], None, None)
+    b.add("nine", 0, 0, 200, 60, [(0, 10)] * 9, None, None)
+    b.add("empty", 4, -1, -1, 0, "", None, None)
+    for k in range(300):
+        n = int(rng.choice([1, 7, 8, 9, 255, 256, 257, 1000, 3000]))
+        ops = [(int(rng.choice([0, 0, 0, 1, 2, 7, 8, 4])), int(rng.choice([1, 2, 3, 10, 50, 4095, 4096, 5000]))) for _ in range(n)]
+        b.add("r%d" % k, 0, 0, 1000 + k, 60, ops, None, None)
+    batch = b.finish()
+    packed = batch.pack_cigar16(3)
+    un = sio.unpack_cigar16(packed.cigar16, packed.cigar16_off, batch.n_cigar)
+    for i in range(batch.n):
+        assert np.array_equal(un[i], batch.cigar[int(batch.cigar_off[i]):int(batch.cigar_off[i]) + int(batch.n_cigar[i])])
+    gpu_ctx.set_params(_lib.Params.from_options(None)); gpu_ctx.set_contigs(batch.contig_names)
+    gpu_ctx.upload(packed)
+    assert np.array_equal(gpu_ctx.download_cigar(batch.cigar.size), batch.cigar)
+    # a stream that does not decode to n_cigar operations
+    broken = b.finish().pack_cigar16(1)
+    broken.cigar16[int(broken.cigar16_off[1])] = 0x000F
+    with pytest.raises(_lib.SvimGpuError):
+        gpu_ctx.upload(broken)
+    # COLLECT + CLUSTER from the packed upload == golden (plain upload is what every other test uses)
+    from gpu_common import run_gpu, assert_clusters_equal
+    for name in ("mini_mixed", "mini_hotspot"):
+        gb, genome, exp = golden(name)
+        gb.pack_cigar16(2)
+        try:
+            rows, trows, clusters, st, cst = run_gpu(gpu_ctx, gb, genome, exp["params"])
+        finally:
+            gb.cigar16 = None; gb.cigar16_off = None
+        assert rows == exp["signatures"]
+        assert_clusters_equal(clusters, exp["clusters"])

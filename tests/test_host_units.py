@@ -117,7 +117,7 @@ def hc():
     src = os.path.join(ROOT, "tests", "hostcheck", "hostcheck.cpp")
     so = os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so")
     deps = [src] + [os.path.join(ROOT, "svim_b200", "csrc", f) for f in ("common.cuh", "collect.cuh", "cluster.cuh", "myers_band.cuh", "myers_tpp.cuh")] + \
-           [os.path.join(ROOT, "svim_b200", "csrc_next", "bgzf_core.cuh")]
+           [os.path.join(ROOT, "svim_b200", "csrc", "bgzf_core.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src])
     lib = ctypes.CDLL(so)
@@ -756,7 +756,7 @@ def test_flag_cutpaste_host_mirror_against_golden(monkeypatch):
 
 
 def test_bgzf_core_inflate_matches_zlib(hc, tmp_path):
-    """csrc_next/bgzf_core.cuh (groundwork for the on-GPU BAM decoder): the SVIM_HD raw-DEFLATE decoder against zlib on synthetic
+    """csrc/bgzf_core.cuh (host+device core of the on-GPU BAM decoder): the SVIM_HD raw-DEFLATE decoder against zlib on synthetic
     streams of every block type and on every BGZF block of a BAM file; malformed input must come back as an error code."""
     import zlib
     hc.hc_bgzf_inflate.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_uint]
@@ -842,7 +842,7 @@ def test_bgzf_core_inflate_matches_zlib(hc, tmp_path):
 
 
 def test_bgzf_layout_for_the_gpu_decoder(tmp_path):
-    # svim_b200.io.bgzf_layout: block table + first-record offset handed to csrc_next/bamgpu.cu, checked with zlib on the CPU
+    # svim_b200.io.bgzf_layout: block table + first-record offset handed to svimgpu_decode_bam (csrc/bam.cu), checked with zlib on the CPU
     import zlib
     from svim_b200 import synth
     names, L = ["chr1", "chr2"], [90_000, 50_000]

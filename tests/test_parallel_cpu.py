@@ -25,7 +25,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     batch, genome, exp = load_golden("mini_mixed")
     lo, hi = parallel.shard_ranges(batch.n_cigar, world)[rank]
-    shard = batch.slice(lo, hi)
+    shard = parallel.shard_batch(batch, rank, world)          # compact: the rank's own blobs, offsets rebased
+    assert shard.n == hi - lo and shard.cigar.size < batch.cigar.size and shard.cigartuples(0) == batch.cigartuples(lo)
     base, total, sizes = parallel.exchange_layout(shard.n)
     sigs, _ = orc.collect(shard, orc.Params())
     rows = [list(s.as_tuple()) for s in sigs]
@@ -64,3 +65,26 @@ def test_shard_ranges_balance_and_cover():
         assert r[0][0] == 0 and r[-1][1] == len(n_cigar) and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         loads = [int(n_cigar[a:b].sum()) for a, b in r]
         assert max(loads) < 1.1 * (sum(loads) / world) + 5000
+
+
+def test_compact_slice_and_generated_shards_equal_the_whole_input():
+    """AlignmentBatch.compact_slice (what parallel.shard_batch uploads) and synth.generate_shard (bench.py --shard records: a rank
+    materialises only its record range of ONE coordinate-sorted input) against the full batch, record for record."""
+    from svim_b200 import synth
+    names, lengths, reads, seed, pkw, gkw = synth.config_layout("config4", 0.002)
+    assert names[:3] == ["chr1", "chr2", "chr3"] and names[-2:] == ["chrX", "chrY"] and len(names) == 24
+    svs, alleles = synth.plant_svs(lengths, seed, **pkw)
+    full = synth.generate(names, lengths, reads, seed, svs, alleles, **gkw)
+    at = 0
+    for r in range(3):
+        sh, lo, total = synth.generate_shard(names, lengths, reads, seed, svs, alleles, r, 3, **gkw)
+        cs = full.compact_slice(lo, lo + sh.n)
+        assert total == full.n and lo == at
+        for f, _ in full.FIELDS:
+            assert np.array_equal(getattr(sh, f), getattr(cs, f)), f
+        for blob in ("cigar", "seq", "sa"):
+            assert np.array_equal(getattr(sh, blob), getattr(cs, blob)), blob
+        for i in (0, sh.n // 2, sh.n - 1):
+            assert sh.cigartuples(i) == full.cigartuples(lo + i) and sh.sa_tag(i) == full.sa_tag(lo + i) and sh.sequence(i) == full.sequence(lo + i)
+        at += sh.n
+    assert at == full.n
