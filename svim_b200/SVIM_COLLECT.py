@@ -197,6 +197,17 @@ class _ClusterPrefetch:
 
 
 def _analyze(bam, options, querysorted):
+    try:
+        return _analyze_inner(bam, options, querysorted)
+    except KeyboardInterrupt:
+        # The reference stops collecting at the record it had reached and goes on with what it has (SVIM_COLLECT.py:126-128, 164-166).
+        # COLLECT here is one device pass of a fraction of a second, so the granularity is the whole pass: an interrupt that
+        # arrives before its records are on the host leaves nothing to go on with.
+        logging.warning('Execution interrupted by user. Stop detection and continue with next step..')
+        return SignatureList([]), SignatureList([])
+
+
+def _analyze_inner(bam, options, querysorted):
     batch = as_batch(bam)
     ctx, stats, (sigs, ins), (tsigs, tins) = collect_arrays(batch, options, querysorted=querysorted)
     token = object()
@@ -204,7 +215,7 @@ def _analyze(bam, options, querysorted):
     ctx.collect_batch = batch
     ctx.cluster_prefetch = None
     if len(sigs) and getattr(options, "genome", None) is not None:
-        sigs = np.array(sigs); ins = np.array(ins)      # own copies: the pinned mirrors belong to the context the thread is using
+        # (sigs / ins are views of the context's pinned mirrors: use_collected + cluster never touch those, only the next collect does)
         ctx.cluster_prefetch = _ClusterPrefetch(ctx, options, 0)
     main = SignatureList(materialize_signatures(sigs, ins, batch), token=token)
     main._svimgpu_which = 0

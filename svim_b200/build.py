@@ -47,7 +47,7 @@ def build_gpu(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-           "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static", "-o", "@OUT@", os.path.join(SRC, "api.cu"), "-lnccl"]
+           "-Xcompiler", "-fPIC,-Wno-deprecated-declarations", "-diag-suppress", "177,550,1444", "-shared", "-cudart", "static", "-o", "@OUT@", os.path.join(SRC, "api.cu"), "-lnccl", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     return run_atomic(cmd, SO)

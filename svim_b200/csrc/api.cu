@@ -11,7 +11,7 @@
 #include "genotype.cu"
 #include "bam.cu"
 
-static const char* k_timing_names[T_N] = {
+const char* const k_stage_names[T_N] = {
     "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
     "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype", "closest_deletion",
     "bam_h2d+inflate", "bam_record_bounds", "bam_rows", "bam_fill", "bam_read_names"};
@@ -663,6 +663,6 @@ int svimgpu_timer_stop(svimgpu_ctx* ctx, double* ms) {
 
 int64_t svimgpu_launch_count(svimgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-const char* svimgpu_timing_name(int32_t i) { return (i >= 0 && i < T_N) ? k_timing_names[i] : ""; }
+const char* svimgpu_timing_name(int32_t i) { return (i >= 0 && i < T_N) ? k_stage_names[i] : ""; }
 
 }  // extern "C"

@@ -86,7 +86,9 @@ static int bam_decode_run(svimgpu_ctx* ctx, const uint8_t* file, int64_t file_by
     {
         StageTimer t(ctx, T_BAM_INFLATE);
         const int64_t SLICE = (int64_t)256 << 20;
-        const int inline_mode = getenv("SVIM_BAM_INLINE") ? atoi(getenv("SVIM_BAM_INLINE")) : 1;
+        // expanding near matches on the decoding lane (SVIM_BAM_INLINE=1) loses on BAM streams: 82 % of their matches reach further back than the
+        // 8-byte register tail (measured: 33.7 M of 41.3 M on BASELINE configs[1]), and each of those then costs a queue drain
+        const int inline_mode = getenv("SVIM_BAM_INLINE") ? atoi(getenv("SVIM_BAM_INLINE")) : 0;
         int64_t b0 = 0;
         cudaEvent_t ev_done[2]; cudaEventCreateWithFlags(&ev_done[0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_done[1], cudaEventDisableTiming);
         SVIM_CUDA(cudaEventRecord(ctx->aux_ev[SVIM_AUX_STREAMS], st));

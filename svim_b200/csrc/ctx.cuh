@@ -1,6 +1,7 @@
 // Context, device buffers, error plumbing.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a tool (nsys / ncu --nvtx) is attached
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -188,10 +189,12 @@ inline void svimgpu_ctx::set_error(int code, const char* fmt, ...) {
     err = buf; err_code = code;
 }
 
-struct StageTimer {
+extern const char* const k_stage_names[];      // api.cu: one name per timing slot, also the NVTX range of the stage
+
+struct StageTimer {      // CUDA-event timing of one stage on the context's stream + an NVTX range around its host side
     svimgpu_ctx* c; int slot;
-    StageTimer(svimgpu_ctx* ctx, int s) : c(ctx), slot(s) { cudaEventRecord(c->ev[2 * s], c->stream); c->ev_rec[s] = true; }
-    ~StageTimer() { cudaEventRecord(c->ev[2 * slot + 1], c->stream); }
+    StageTimer(svimgpu_ctx* ctx, int s) : c(ctx), slot(s) { nvtxRangePushA(k_stage_names[s]); cudaEventRecord(c->ev[2 * s], c->stream); c->ev_rec[s] = true; }
+    ~StageTimer() { cudaEventRecord(c->ev[2 * slot + 1], c->stream); nvtxRangePop(); }
 };
 
 inline void timings_begin(svimgpu_ctx* ctx) { for (int i = 0; i < T_N; ++i) { ctx->ev_rec[i] = false; ctx->ms[i] = 0.0; } }
