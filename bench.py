@@ -362,15 +362,16 @@ def main():
             # the timing slots are reset by the next call: keep the signature exchange apart from the cluster exchange
             xchg_ms["nccl_exchange_signatures"] = ctx.timings().get("nccl_exchange", 0.0)
             ctx.use_collected(0)
-            return st, ctx.cluster(sharded=True)
+            return st, ctx.cluster(sharded=True, view=True)
         ctx.use_collected(0)
-        return None, ctx.cluster()
+        return None, ctx.cluster(view=True)       # the context's pinned result arrays, no second host copy
 
     # ---------------- resident: record buffer already in HBM -------------------------------------
     ctx.upload(batch)
     stage_ms = {}
     launches0 = 0
     res_ms = []
+    own_ms = []
     sampler = ClockSampler(local_rank, ctx)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
@@ -384,8 +385,22 @@ def main():
             if v and s >= args.warmup:
                 stage_ms.setdefault(k, []).append(v)
         if s >= args.warmup:
+            own_ms.append(ms)
             res_ms.append(barrier_max(ms))
     clocks = sampler.stop()
+    clusters = np.array(clusters); members = np.array(members)      # own copies of the last step's result
+    per_rank = None
+    if world > 1:
+        # every rank's own step time and stage table (the headline is the max over ranks): where the ranks differ, and how much of
+        # a rank's step no stage accounts for
+        import torch.distributed as dist
+        st_mine = {k: round(float(np.mean(v)), 3) for k, v in stage_ms.items()}
+        mine = {"rank": rank, "step_ms": round(float(np.mean(own_ms)), 3), "stages_sum_ms": round(sum(st_mine.values()), 3),
+                "myers": st_mine.get("myers_edit_distance", 0.0), "linkage": st_mine.get("linkage", 0.0),
+                "exchange_signatures": st_mine.get("nccl_exchange_signatures", 0.0), "exchange_clusters": st_mine.get("nccl_exchange", 0.0),
+                "cluster_d2h": st_mine.get("cluster_d2h", 0.0), "myers_pairs": int(clst.myers_pairs), "myers_band_cells": int(clst.myers_band_cells)}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     launches = ctx.launch_count() - launches0
     n_sigs = (xst.n_signatures if xst else cst.n_signatures)
     if args.profile_steps:
@@ -434,6 +449,7 @@ def main():
     # ---------------- parity evidence, outside the timed regions --------------------------------------------
     # the device's sorted order + partition offsets of the last step (svimgpu_fetch_partitions), before anything re-clusters
     sigs = np.array(sigs); ins = np.array(ins)        # own copies: the pinned mirrors are reused by later calls
+    clusters = np.array(clusters); members = np.array(members)
     part_order, part_off = ctx.fetch_partitions(len(sigs))
     parity = {"mismatches": 0}
     if world > 1:
@@ -564,6 +580,8 @@ def main():
         "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in stage_ms.items()},
         "clocks": clocks,
     }
+    if per_rank:
+        out["per_rank"] = per_rank
     if py_leg:
         out["e2e_python"] = py_leg
     if bam_leg:

@@ -235,6 +235,9 @@ int svimgpu_partition(svimgpu_ctx* ctx, int64_t* n_partitions);
 /* D2H: clusters[n_clusters_total] grouped by type in order DEL, INS, INV, DUP_TAN,
  * BND, DUP_INT (each group in the reference's list order); members[n_members]. */
 int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* members);
+/* The same arrays without a second copy: svimgpu_cluster[_sharded] leaves its result in pinned host memory owned by the
+ * context; this returns those pointers (valid until the next cluster / destroy on this context). */
+int svimgpu_clusters_host(svimgpu_ctx* ctx, const svim_cluster** clusters, const uint32_t** members);
 /* form_partitions only (SVIM_clustering.py:17-29): order[n] = signature indices in
  * partition order, part_off[n_partitions+1]; call after svimgpu_partition or svimgpu_cluster. */
 int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* order, uint32_t* part_off);

@@ -23,7 +23,7 @@ def cluster_sv_signatures(sv_signatures, options):
             genome = runtime.genome_for(options.genome)
             runtime.ensure_genome(ctx, genome, batch.contig_names)
             ctx.use_collected(which)
-            done = ctx.cluster()
+            done = ctx.cluster(view=True)
         stats, clusters, members = done
         per_type = build_clusters(clusters, members, sv_signatures)
     else:

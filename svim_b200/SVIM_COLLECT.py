@@ -185,7 +185,7 @@ class _ClusterPrefetch:
             genome = runtime.genome_for(options.genome)
             runtime.ensure_genome(ctx, genome, ctx.collect_batch.contig_names)
             ctx.use_collected(self.which)
-            self.result = ctx.cluster()
+            self.result = ctx.cluster(view=True)       # consumed by build_clusters before the next cluster on this context
         except BaseException as e:          # surfaces (again) when cluster_sv_signatures recomputes
             self.error = e
 

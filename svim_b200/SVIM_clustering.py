@@ -130,7 +130,7 @@ def cluster_objects(signatures, options, ctx=None):
     elif getattr(options, "genome", None) is not None:
         runtime.genome_for(options.genome)   # the reference opens the FASTA for every type (SVIM_clustering.py:377)
     ctx.set_signatures(cs, blob, rank_to_tid)
-    stats, clusters, members = ctx.cluster()
+    stats, clusters, members = ctx.cluster(view=True)
     return ctx, stats, build_clusters(clusters, members, signatures)
 
 
@@ -237,7 +237,7 @@ def partition_and_cluster_candidates(candidates, options, type):
     ctx = runtime.context()
     ctx.set_params(_lib.Params.from_options(options))
     ctx.set_signatures(marshal_candidates(candidates), None, None)
-    stats, clusters, members = ctx.cluster()
+    stats, clusters, members = ctx.cluster(view=True)
     logging.debug("%d out of %d partitions for %s exceeded 100 elements." % (stats.large_partitions[5], stats.n_partitions[5], candidates[0].type))
     logging.info("Clustered {0}: {1} partitions and {2} clusters".format(type, stats.n_partitions[5], stats.n_clusters[5]))
     cls = _candidate_class()

@@ -133,6 +133,7 @@ EXPORTS = {
     "svimgpu_cluster": (C.c_int, [C.c_void_p, C.POINTER(ClusterStats)]),
     "svimgpu_partition": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "svimgpu_fetch_clusters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "svimgpu_clusters_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "svimgpu_fetch_partitions": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "svimgpu_genotype": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GenoParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int32, C.c_void_p]),
@@ -345,10 +346,20 @@ class Context:
         r2t = np.ascontiguousarray(rank_to_tid, dtype=np.int32) if rank_to_tid is not None else np.zeros(0, np.int32)
         self._check(self.lib.svimgpu_set_signatures(self.h, len(csig), _ptr(csig), _ptr(ins), ins.size, _ptr(r2t), r2t.size))
 
-    def cluster(self, sharded=False):
+    def cluster(self, sharded=False, view=False):
+        """CLUSTER on the selected signatures -> (stats, clusters, members).  `view=True` hands out the context's own pinned
+        result arrays instead of copies: valid until the next cluster on this context (callers that keep them must .copy())."""
         st = ClusterStats()
         fn = self.lib.svimgpu_cluster_sharded if sharded else self.lib.svimgpu_cluster
         self._check(fn(self.h, C.byref(st)))
+        if view:
+            pc, pm = C.c_void_p(), C.c_void_p()
+            self._check(self.lib.svimgpu_clusters_host(self.h, C.byref(pc), C.byref(pm)))
+            nc, nm = st.n_clusters_total, st.n_members
+            clusters = (np.frombuffer((C.c_uint8 * (nc * CLUSTER_DTYPE.itemsize)).from_address(pc.value), dtype=CLUSTER_DTYPE)
+                        if nc and pc.value else np.zeros(0, dtype=CLUSTER_DTYPE))
+            members = np.frombuffer((C.c_uint32 * nm).from_address(pm.value), dtype=np.uint32) if nm and pm.value else np.zeros(0, dtype=np.uint32)
+            return st, clusters, members
         clusters = np.zeros(st.n_clusters_total, dtype=CLUSTER_DTYPE)
         members = np.zeros(st.n_members, dtype=np.uint32)
         self._check(self.lib.svimgpu_fetch_clusters(self.h, _ptr(clusters), _ptr(members)))

@@ -467,6 +467,14 @@ int svimgpu_fetch_clusters(svimgpu_ctx* ctx, svim_cluster* clusters, uint32_t* m
     return 0;
 }
 
+int svimgpu_clusters_host(svimgpu_ctx* ctx, const svim_cluster** clusters, const uint32_t** members) {
+    if (!ctx || !clusters || !members) return SVIMGPU_ERR_ARG;
+    if (!ctx->clustered) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster has not run"); return SVIMGPU_ERR_STATE; }
+    *clusters = ctx->n_clusters_host ? ctx->h_clusters.as<svim_cluster>() : nullptr;
+    *members = ctx->n_members_host ? ctx->h_members.as<uint32_t>() : nullptr;
+    return 0;
+}
+
 int svimgpu_fetch_partitions(svimgpu_ctx* ctx, int64_t* n_partitions, uint32_t* order, uint32_t* part_off) {
     if (!ctx) return SVIMGPU_ERR_ARG;
     if (!ctx->clustered) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster has not run"); return SVIMGPU_ERR_STATE; }

@@ -561,7 +561,11 @@ static int sort_pairs_u64(svimgpu_ctx* ctx, DevBuf* keys, DevBuf* vals, uint32_t
 }
 
 static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_rank, int shard_n, bool partition_only = false) {
-    if (!ctx->have_csig) { ctx->set_error(SVIMGPU_ERR_STATE, "no signatures selected for clustering"); return SVIMGPU_ERR_STATE; }
+    if (!ctx->have_csig) {
+        ctx->set_error(SVIMGPU_ERR_STATE, "no signatures selected for clustering");
+        if (shard_n > 1) { uint32_t z0 = 0, z1 = 0; cluster_exchange(ctx, &z0, &z1, SVIMGPU_ERR_STATE); }      // the other ranks are on their way into the exchange
+        return SVIMGPU_ERR_STATE;
+    }
     cudaStream_t st = ctx->stream;
     const uint32_t n = (uint32_t)ctx->n_csig;
     svim_cluster_stats& cs = ctx->clstats;
@@ -576,6 +580,8 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     // Everything up to the consolidated clusters of this rank's partitions.  In sharded mode a failure here must not return before the
     // other ranks have been told (they would wait in the exchange for ever): the status travels with the exchange's count all-gather.
     auto local = [&]() -> int {
+    if (const char* f = getenv("SVIM_TEST_FAIL_RANK"))            // test hook (tests/multi_gpu_check.py): this rank fails before the exchange
+        if (shard_n > 1 && atoi(f) == shard_rank) { ctx->set_error(SVIMGPU_ERR_DATA, "cluster: injected failure on rank %d", shard_rank); return SVIMGPU_ERR_DATA; }
     const uint32_t nb = (n + 255) / 256;
     // ---- sort by get_key -------------------------------------------------------------------------------
     uint64_t* gkey_sorted = nullptr; uint32_t* order = nullptr;

@@ -33,6 +33,24 @@ def main():
         assert [int(x) for x in sigs["aln_idx"]] == sorted(int(x) for x in sigs["aln_idx"])
         if rank == 0:
             print("multi-gpu ok:", name, "world", world, "signatures", len(rows), "clusters", int(clst.n_clusters_total), flush=True)
+    # a rank that fails before the cluster exchange must not leave the others waiting in it, and nobody may keep a result:
+    # the failing rank reports its own error, every other rank SVIMGPU_ERR_PEER (-7); the next call works again
+    if world > 1:
+        os.environ["SVIM_TEST_FAIL_RANK"] = str(world - 1)
+        ctx.collect()
+        xst = _lib.CollectStats()
+        ctx._check(ctx.lib.svimgpu_exchange_signatures(ctx.h, base, __import__("ctypes").byref(xst)))
+        ctx.use_collected(0)
+        try:
+            ctx.cluster(sharded=True)
+            raise AssertionError("sharded cluster returned a result although rank %d failed" % (world - 1))
+        except _lib.SvimGpuError as e:
+            assert e.code == (-5 if rank == world - 1 else -7), (rank, e.code, str(e))
+        del os.environ["SVIM_TEST_FAIL_RANK"]
+        cst, xst, clst, clusters, members = parallel.collect_and_cluster(ctx, base)
+        assert int(clst.n_clusters_total) > 0
+        if rank == 0:
+            print("multi-gpu ok: rank failure is collective", flush=True)
     dist.barrier()
     dist.destroy_process_group()
     ctx.close()

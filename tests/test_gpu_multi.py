@@ -26,4 +26,4 @@ def test_two_ranks_reproduce_golden():
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("multi-gpu ok") == 4
+    assert r.stdout.count("multi-gpu ok") == 5

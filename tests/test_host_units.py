@@ -648,7 +648,7 @@ def _oracle_backed_context(batch, genome):
         def fetch_signatures(self, which, stats): return self.arrays[which]
         def use_collected(self, which=0): self.which = which
 
-        def cluster(self, sharded=False):
+        def cluster(self, sharded=False, view=False):
             lst = self.lists[self.which]
             index_of = {id(s): i for i, s in enumerate(lst)}
             stats = {}
