@@ -425,6 +425,10 @@ def main():
     e2e_ms = []
     e2e_stage = {}
     d2h = 0
+    if world > 1:
+        # the job's result lands on ONE host: rank 0 mirrors the gathered records and every rank's insertion bytes (what the objects
+        # are built from), the other ranks the gathered records and the cluster arrays only
+        ctx._check(ctx.lib.svimgpu_mirror_gathered_ins(ctx.h, 1 if rank == 0 else 0))
     sampler_e2e = ClockSampler(local_rank, ctx)
     for s in range(args.warmup + args.steps):
         if s == args.warmup:
@@ -442,10 +446,17 @@ def main():
                 if v:
                     e2e_stage.setdefault(k, []).append(v)
         d2h = 2 * sigs.nbytes + ins.nbytes + clusters.nbytes + members.nbytes     # signature records cross twice (staging + fetch)
+        if world > 1:
+            d2h = 48 * cst.n_signatures + sigs.nbytes + ins.nbytes + clusters.nbytes + members.nbytes      # collect's staging + the gathered lists (this is rank 0)
         h2d = h2d_full - batch.seq.nbytes + (cst.ins_bytes + 1) // 2 + 8 * cst.n_signatures
         if s >= args.warmup:
             e2e_ms.append(barrier_max(ms))
     clocks_e2e = sampler_e2e.stop()
+    if world > 1:
+        ctx._check(ctx.lib.svimgpu_mirror_gathered_ins(ctx.h, 1))
+        if rank != 0:       # the parity block below compares full lists on every rank (no rank has collected again: the peers' bytes are intact)
+            sigs, ins = (np.zeros(xst.n_signatures, dtype=_lib.SIG_DTYPE), np.zeros(xst.ins_bytes, dtype=np.uint8))
+            ctx._check(ctx.lib.svimgpu_fetch_signatures(ctx.h, 0, sigs.ctypes.data, ins.ctypes.data))
     # ---------------- parity evidence, outside the timed regions --------------------------------------------
     # the device's sorted order + partition offsets of the last step (svimgpu_fetch_partitions), before anything re-clusters
     sigs = np.array(sigs); ins = np.array(ins)        # own copies: the pinned mirrors are reused by later calls
@@ -574,6 +585,8 @@ def main():
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
                 "cigar_upload": ("16-bit packed stream (svim_aln_soa.cigar16), %.2f GB; expanded on the device" % (batch.cigar16.nbytes / 1e9)) if batch.cigar16 is not None
                                 else "uint32 BAM words, %.2f GB" % (batch.cigar.nbytes / 1e9),
+                "result_on_host": ("rank 0: gathered signature records + every rank's insertion bytes + cluster arrays; other ranks: gathered records + cluster arrays"
+                                   if world > 1 else "signature records + insertion bytes + cluster arrays"),
                 "clocks": clocks_e2e},
         "roofline": {"kernel": "k_cigar_scan", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": scan_ms},

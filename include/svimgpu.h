@@ -288,9 +288,19 @@ int svimgpu_closest_source(svimgpu_ctx* ctx, int64_t n_a, const int64_t* a_start
 /* id_bytes: 128-byte ncclUniqueId from svimgpu_nccl_unique_id on rank 0. */
 int svimgpu_nccl_unique_id(uint8_t* id_bytes /*128*/);
 int svimgpu_comm_init(svimgpu_ctx* ctx, int nranks, int rank, const uint8_t* id_bytes);
-/* allgatherv of the collected signature records (+ INS blobs) of all ranks; after
- * it every rank holds the full lists (record indices made global with aln_base). */
+/* allgatherv of the collected signature records of all ranks: after it every rank holds the full lists (record indices made
+ * global with aln_base, seq_off pointing into the concatenation of all ranks' INS blobs in rank order).  The INS bytes themselves
+ * are not moved: each rank keeps its piece and the others map it (CUDA IPC over NVLink / NVSwitch peer memory).
+ * svimgpu_cluster[_sharded] reads from the peers only the sequences its own partitions compare; svimgpu_fetch_signatures and the
+ * host mirror of svimgpu_signatures_host assemble the whole blob from the peers on demand.  Consequence: a rank must not start its
+ * next collect while another rank may still be reading its piece - the exchange inside svimgpu_cluster_sharded orders the cluster
+ * calls; put a barrier (svimgpu_barrier_max) between a fetch of the gathered lists and the next collect.
+ * SVIM_PEER_INS=0 in the environment of every rank: gather the INS blobs as well (every rank holds a private full copy). */
 int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collect_stats* stats);
+/* After the exchange the host mirror of svimgpu_signatures_host is restarted for the gathered lists (when the lists came from
+ * svimgpu_collect_host).  with_ins = 0: this rank mirrors the gathered RECORDS only (*ins = NULL) - for the ranks of a job that do
+ * not build the Signature objects; the default (1) also pulls every rank's INS bytes to this host. */
+int svimgpu_mirror_gathered_ins(svimgpu_ctx* ctx, int with_ins);
 /* restrict clustering to partitions [p*rank/n, p*(rank+1)/n) and allgatherv the
  * cluster records so every rank ends with the full result. */
 int svimgpu_cluster_sharded(svimgpu_ctx* ctx, svim_cluster_stats* stats);

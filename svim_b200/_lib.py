@@ -134,6 +134,7 @@ EXPORTS = {
     "svimgpu_partition": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "svimgpu_fetch_clusters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "svimgpu_clusters_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "svimgpu_mirror_gathered_ins": (C.c_int, [C.c_void_p, C.c_int]),
     "svimgpu_fetch_partitions": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "svimgpu_genotype": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GenoParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int32, C.c_void_p]),
@@ -330,7 +331,8 @@ class Context:
         self._check(self.lib.svimgpu_signatures_host(self.h, which, C.byref(ps), C.byref(pi)))
         if ps.value:
             sigs = np.frombuffer((C.c_uint8 * (n * SIG_DTYPE.itemsize)).from_address(ps.value), dtype=SIG_DTYPE) if n else np.zeros(0, dtype=SIG_DTYPE)
-            ins = np.frombuffer((C.c_uint8 * nb).from_address(pi.value), dtype=np.uint8) if nb else np.zeros(0, dtype=np.uint8)
+            # pi is NULL on a rank that mirrors the gathered records only (svimgpu_mirror_gathered_ins)
+            ins = np.frombuffer((C.c_uint8 * nb).from_address(pi.value), dtype=np.uint8) if nb and pi.value else np.zeros(0, dtype=np.uint8)
             return sigs, ins
         sigs = np.zeros(n, dtype=SIG_DTYPE)
         ins = np.zeros(nb, dtype=np.uint8)

@@ -14,7 +14,7 @@
 const char* const k_stage_names[T_N] = {
     "h2d_alignments", "cigar_scan", "segment_chain", "sort_back+ins_gather", "ins_gather", "collect_d2h", "sig_to_csig", "key_sort",
     "partition", "host_sampling", "ins_pair_list", "myers_edit_distance", "linkage", "consolidate", "final_order", "cluster_d2h", "nccl_exchange", "genotype_prepare", "genotype", "closest_deletion",
-    "bam_h2d+inflate", "bam_record_bounds", "bam_rows", "bam_fill", "bam_read_names"};
+    "bam_h2d+inflate", "bam_record_bounds", "bam_rows", "bam_fill", "bam_read_names", "ins_peer_fetch"};
 
 extern "C" {
 
@@ -49,6 +49,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (const char* v = getenv("SVIM_MYERS_MODE")) ctx->myers_mode = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_TPP")) ctx->myers_tpp = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_TRACE")) ctx->myers_trace = atoi(v);
+    if (const char* v = getenv("SVIM_PEER_INS")) ctx->peer_ins = atoi(v) != 0;
     if (const char* v = getenv("SVIM_MYERS_BAND")) { int num = 0, add = 24; if (sscanf(v, "%d,%d", &num, &add) >= 1) { ctx->myers_band_num = num; ctx->myers_band_add = add; } }
     *out = ctx;
     return 0;
@@ -67,7 +68,8 @@ void svimgpu_destroy(svimgpu_ctx* ctx) {
                       &ctx->d_user_rank_to_tid, &ctx->d_cl_off, &ctx->d_mem_off, &ctx->d_clusters, &ctx->d_clusters_sorted,
                       &ctx->d_members, &ctx->d_pair_off, &ctx->d_pair_ed, &ctx->d_pairs, &ctx->d_ckeys[0], &ctx->d_ckeys[1], &ctx->d_cvals[0],
                       &ctx->d_cvals[1], &ctx->d_xchg[0], &ctx->d_xchg[1], &ctx->d_xchg[2], &ctx->d_xchg[3], &ctx->d_xchg[4], &ctx->d_xchg[5], &ctx->d_xchg[6], &ctx->d_xchg[7],
-                      &ctx->d_genome_codes, &ctx->d_ins_codes, &ctx->d_myers_trace, &ctx->d_big_list, &ctx->d_big_caps, &ctx->d_big_scratch, &ctx->d_cig16, &ctx->d_cig16_off, &ctx->d_cig16_err, &ctx->d_bam_names, &ctx->d_bam_name_off, &ctx->d_bam_rec_of_id, &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks};
+                      &ctx->d_genome_codes, &ctx->d_ins_codes, &ctx->d_myers_trace, &ctx->d_big_list, &ctx->d_big_caps, &ctx->d_big_scratch, &ctx->d_cig16, &ctx->d_cig16_off, &ctx->d_cig16_err, &ctx->d_bam_names, &ctx->d_bam_name_off, &ctx->d_bam_rec_of_id, &ctx->d_pmeta, &ctx->d_ppref, &ctx->d_ptype, &ctx->d_hdr, &ctx->d_large_list, &ctx->d_picks,
+                      &ctx->d_seg_tab, &ctx->d_shard_ins, &ctx->d_shard_len};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 14; ++i) ctx->d_soa[i].release();
     for (int i = 0; i < 48; ++i) ctx->d_myers_scratch[i].release();
@@ -254,6 +256,7 @@ int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats) {
     cudaSetDevice(ctx->device);
     // a host copy of the previous lists may still be in flight on the copy stream: the lists are about to be rewritten
     if (ctx->host_copy[0] || ctx->host_copy[1]) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
+    ctx->host_copy_pending = false;
     double h2d = ctx->ms[T_H2D];
     timings_begin(ctx);
     int rc = collect_run(ctx, stats);
@@ -263,6 +266,23 @@ int svimgpu_collect(svimgpu_ctx* ctx, svim_collect_stats* stats) {
 }
 
 static size_t host_copy_ins_off(const SigSet& set) { return ((size_t)set.n * sizeof(svim_sig) + 255) & ~(size_t)255; }
+
+// INS blob of a list -> host.  A segmented list (after the exchange) is read piece by piece from the ranks that hold it: the copy
+// engine pulls a peer's piece over NVLink and writes it out over this GPU's PCIe link.  The peers must not have started their next
+// collect (include/svimgpu.h, svimgpu_exchange_signatures).
+static int copy_ins_to_host(svimgpu_ctx* ctx, const SigSet& set, uint8_t* dst, cudaStream_t s) {
+    if (!set.segmented) {
+        if (set.ins_bytes) SVIM_CUDA(cudaMemcpyAsync(dst, set.ins.p, (size_t)set.ins_bytes, cudaMemcpyDeviceToHost, s));
+        return 0;
+    }
+    for (size_t r = 0; r + 1 < set.seg_base.size(); ++r) {
+        const int64_t len = set.seg_base[r + 1] - set.seg_base[r];
+        if (len <= 0) continue;
+        if (!set.seg_ptr[r]) { ctx->set_error(SVIMGPU_ERR_STATE, "the insertion bytes of rank %d are not mapped", (int)r); return SVIMGPU_ERR_STATE; }
+        SVIM_CUDA(cudaMemcpyAsync(dst + set.seg_base[r], set.seg_ptr[r], (size_t)len, cudaMemcpyDefault, s));
+    }
+    return 0;
+}
 
 // Start copying the collected lists to pinned host memory on the copy stream; CLUSTER (ctx->stream) runs meanwhile.
 static int start_host_copy(svimgpu_ctx* ctx) {
@@ -281,7 +301,8 @@ static int start_host_copy(svimgpu_ctx* ctx) {
             ctx->h_out_cap[w] = want;
         }
         if (set.n) SVIM_CUDA(cudaMemcpyAsync(ctx->h_out[w], set.recs.p, (size_t)set.n * sizeof(svim_sig), cudaMemcpyDeviceToHost, ctx->copy_stream));
-        if (set.ins_bytes) SVIM_CUDA(cudaMemcpyAsync(ctx->h_out[w] + ins_off, set.ins.p, (size_t)set.ins_bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        ctx->host_copy_has_ins[w] = !set.segmented || ctx->mirror_gathered_ins;
+        if (ctx->host_copy_has_ins[w]) { int rc = copy_ins_to_host(ctx, set, ctx->h_out[w] + ins_off, ctx->copy_stream); if (rc) return rc; }
         SVIM_CUDA(cudaEventRecord(ctx->ev_host_copy[w], ctx->copy_stream));
         ctx->host_copy[w] = true;
     }
@@ -295,7 +316,8 @@ int svimgpu_collect_host(svimgpu_ctx* ctx, const svim_aln_soa* soa, svim_collect
     rc = svimgpu_collect(ctx, stats);
     ctx->have_soa = false;      // the host SEQ pointers must not outlive this call
     ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
-    if (!rc) rc = start_host_copy(ctx);
+    // one process per GPU: the lists are about to be replaced by the gathered ones, which svimgpu_exchange_signatures mirrors instead
+    if (!rc) { if (ctx->nccl_comm) { ctx->host_copy[0] = ctx->host_copy[1] = false; ctx->host_copy_pending = true; } else rc = start_host_copy(ctx); }
     return rc;
 }
 
@@ -306,7 +328,13 @@ int svimgpu_signatures_host(svimgpu_ctx* ctx, int which, const svim_sig** sigs, 
     cudaSetDevice(ctx->device);
     SVIM_CUDA(cudaEventSynchronize(ctx->ev_host_copy[which]));
     *sigs = (const svim_sig*)ctx->h_out[which];
-    *ins = ctx->h_out[which] + host_copy_ins_off(ctx->sets[which]);
+    *ins = ctx->host_copy_has_ins[which] ? ctx->h_out[which] + host_copy_ins_off(ctx->sets[which]) : nullptr;
+    return 0;
+}
+
+int svimgpu_mirror_gathered_ins(svimgpu_ctx* ctx, int with_ins) {
+    if (!ctx) return SVIMGPU_ERR_ARG;
+    ctx->mirror_gathered_ins = with_ins != 0;
     return 0;
 }
 
@@ -360,7 +388,7 @@ int svimgpu_collect_host_querysorted(svimgpu_ctx* ctx, const svim_aln_soa* soa, 
     rc = svimgpu_collect(ctx, stats);
     ctx->qs_mode = false;
     ctx->have_soa = false; ctx->lazy_seq = false; ctx->h_seq = nullptr; ctx->h_seq_off = nullptr;
-    if (!rc) rc = start_host_copy(ctx);
+    if (!rc) { if (ctx->nccl_comm) { ctx->host_copy[0] = ctx->host_copy[1] = false; ctx->host_copy_pending = true; } else rc = start_host_copy(ctx); }
     return rc;
 }
 
@@ -370,7 +398,7 @@ int svimgpu_fetch_signatures(svimgpu_ctx* ctx, int which, svim_sig* out_sigs, ui
     cudaSetDevice(ctx->device);
     SigSet& set = ctx->sets[which];
     if (set.n && out_sigs) SVIM_CUDA(cudaMemcpyAsync(out_sigs, set.recs.p, (size_t)set.n * sizeof(svim_sig), cudaMemcpyDeviceToHost, ctx->stream));
-    if (set.ins_bytes && out_ins) SVIM_CUDA(cudaMemcpyAsync(out_ins, set.ins.p, (size_t)set.ins_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ins) { int rc = copy_ins_to_host(ctx, set, out_ins, ctx->stream); if (rc) return rc; }
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -408,7 +436,8 @@ int svimgpu_use_collected(svimgpu_ctx* ctx, int which) {
         if (set.n) { ctx->launches++; k_sig_to_csig<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, ctx->d_rank.as<int32_t>(),
                                                                                            ctx->d_csig.as<svim_csig>()); }
     }
-    ctx->cluster_ins = set.ins.as<uint8_t>(); ctx->cluster_ins_bytes = set.ins_bytes;
+    if (set.segmented) { ctx->cluster_ins = nullptr; ctx->cluster_ins_bytes = 0; ctx->cluster_seg = which; }     // cluster_run pulls what its partitions need
+    else { ctx->cluster_ins = set.ins.as<uint8_t>(); ctx->cluster_ins_bytes = set.ins_bytes; ctx->cluster_seg = -1; }
     ctx->cluster_rank_to_tid = ctx->d_rank_to_tid.as<int32_t>(); ctx->cluster_n_ranks = ctx->n_contigs;
     return finish_csig(ctx);
 }
@@ -424,7 +453,7 @@ int svimgpu_set_signatures(svimgpu_ctx* ctx, int64_t n, const svim_csig* sigs, c
     if (n) SVIM_CUDA(cudaMemcpyAsync(ctx->d_csig.p, sigs, (size_t)n * sizeof(svim_csig), cudaMemcpyHostToDevice, ctx->stream));
     SVIM_CUDA(ctx->d_cins.ensure((size_t)ins_bytes + 16));
     if (ins_bytes && ins_blob) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cins.p, ins_blob, (size_t)ins_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->cluster_ins = ctx->d_cins.as<uint8_t>(); ctx->cluster_ins_bytes = ins_bytes;
+    ctx->cluster_ins = ctx->d_cins.as<uint8_t>(); ctx->cluster_ins_bytes = ins_bytes; ctx->cluster_seg = -1;
     ctx->cluster_rank_to_tid = nullptr; ctx->cluster_n_ranks = 0;
     if (rank_to_tid && n_ranks > 0) {
         SVIM_CUDA(ctx->d_user_rank_to_tid.ensure((size_t)n_ranks * 4));

@@ -87,7 +87,7 @@ struct PMetaSum { __host__ __device__ __forceinline__ PMeta operator()(const PMe
     PMeta r; r.pairs = a.pairs + b.pairs; r.cost = a.cost + b.cost; r.m = a.m + b.m; r.large = a.large + b.large; return r; } };
 struct LargePart { uint32_t p, size, type; };
 
-enum { HDR_NLARGE = 0, HDR_NSAMP = 1, HDR_PAIRS = 2 /* 64-bit */, HDR_LO = 4, HDR_HI = 5, HDR_NSMALL = 6, HDR_NBIG = 7, HDR_NINS = 8,
+enum { HDR_NLARGE = 0, HDR_NSAMP = 1, HDR_PAIRS = 2 /* 64-bit */, HDR_LO = 4, HDR_HI = 5, HDR_NSMALL = 6, HDR_NBIG = 7, HDR_NINS = 8, HDR_SLO = 9, HDR_SHI = 10 /* sample slots of this rank's partitions */,
        HDR_NPART_T = 16, HDR_NLARGE_T = 24, HDR_DUP_T = 32, HDR_NCL_T = 40, HDR_CUTS = 64, HDR_WORDS = 256, HDR_MAX_RANKS = 128,
        HDR_LARGE_INLINE = 2048 };
 
@@ -150,6 +150,7 @@ __global__ void k_part_plan(const PMeta* pref, uint32_t P, int shard_rank, int s
         for (int q = 1; q <= shard_n; ++q) if (cut[q] < cut[q - 1]) cut[q] = cut[q - 1];
         for (int q = 0; q <= shard_n; ++q) hdr[HDR_CUTS + q] = cut[q];
         hdr[HDR_LO] = cut[shard_rank]; hdr[HDR_HI] = cut[shard_rank + 1];
+        hdr[HDR_SLO] = pref[cut[shard_rank]].m; hdr[HDR_SHI] = pref[cut[shard_rank + 1]].m;
         hdr[HDR_NLARGE] = pref[P].large; hdr[HDR_NSAMP] = pref[P].m;
         const unsigned long long pt = pref[P].pairs;
         hdr[HDR_PAIRS] = (uint32_t)pt; hdr[HDR_PAIRS + 1] = (uint32_t)(pt >> 32);
@@ -193,6 +194,52 @@ __global__ void __launch_bounds__(128) k_fill_samples(const uint32_t* part_off, 
     const uint32_t b = part_off[p], s0 = samp_off[p], m = meta[p].m;
     if (meta[p].large) { const int32_t* pk = picks + (size_t)pref[p].large * 100; for (uint32_t k = lane; k < m; k += 32) samp_idx[s0 + k] = b + (uint32_t)pk[k]; }
     else for (uint32_t k = lane; k < m; k += 32) samp_idx[s0 + k] = b + k;
+}
+
+// ---- segmented INS blob (multi-GPU): the bytes of a signature's inserted sequence live on the rank that collected it -------------
+// Each rank copies the sequences its own partitions will compare (the sample slots [s_lo, s_lo + S)) into one compact blob and
+// points those records at it; everything downstream (pair lists, code image, edit-distance kernels) reads that blob as before.
+struct SegTab { const int64_t* base; const uint8_t* const* ptr; int R; };
+
+__device__ __forceinline__ int seg_rank_of(const SegTab& t, int64_t off) {
+    int r = 0;
+    while (r + 1 < t.R && off >= t.base[r + 1]) ++r;
+    return r;
+}
+
+// slot bytes per sample: the sequence plus its source's misalignment, in whole 16-byte words (so the copy is aligned word for word)
+__global__ void k_shard_ins_len(const svim_csig* sorted, const uint32_t* samp_idx, uint32_t s_lo, uint32_t S, SegTab t, uint64_t* len) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > S) return;
+    uint64_t v = 0;
+    if (k < S) {
+        const svim_csig c = sorted[samp_idx[s_lo + k]];
+        if (c.type == SVIM_INS && c.seq_len > 0) {
+            const int r = seg_rank_of(t, (int64_t)c.seq_off);
+            const uint64_t mis = (uint64_t)((int64_t)c.seq_off - t.base[r]) & 15ull;
+            v = (mis + (uint64_t)c.seq_len + 15ull) & ~15ull;
+        }
+    }
+    len[k] = v;
+}
+
+// one warp per sample: 16-byte loads from the owner's blob (own HBM, or a peer's over NVLink), record re-pointed
+__global__ void __launch_bounds__(256) k_shard_ins_copy(svim_csig* sorted, const uint32_t* samp_idx, uint32_t s_lo, uint32_t S, SegTab t,
+                                                         const uint64_t* off, uint8_t* dst) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= S) return;
+    const uint32_t idx = samp_idx[s_lo + w];
+    const svim_csig c = sorted[idx];
+    if (c.type != SVIM_INS || c.seq_len == 0) return;
+    const int r = seg_rank_of(t, (int64_t)c.seq_off);
+    const int64_t rel = (int64_t)c.seq_off - t.base[r];
+    const int64_t mis = rel & 15;
+    const uint4* src = (const uint4*)(t.ptr[r] + (rel - mis));
+    uint4* d = (uint4*)(dst + off[w]);
+    const uint32_t words = (uint32_t)((mis + (int64_t)c.seq_len + 15) >> 4);
+    for (uint32_t q = lane; q < words; q += 32) d[q] = src[q];
+    if (lane == 0) sorted[idx].seq_off = off[w] + (uint64_t)mis;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -682,6 +729,38 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         if (hi > lo) { ctx->launches++; k_fill_samples<<<(uint32_t)(((uint64_t)(hi - lo) * 32 + 127) / 128), 128, 0, st>>>(ctx->d_part_off.as<uint32_t>(), ctx->d_samp_off.as<uint32_t>(), meta, pref, lo, hi,
                                                                                             ctx->d_picks.as<int32_t>(), ctx->d_samp_idx.as<uint32_t>()); }
     }
+    // ---- the inserted sequences this rank's partitions compare ------------------------------------------------------------
+    const uint8_t* ins_blob = ctx->cluster_ins; int64_t ins_blob_bytes = ctx->cluster_ins_bytes;
+    if (ctx->cluster_seg >= 0) {
+        const SigSet& set = ctx->sets[ctx->cluster_seg];
+        if (!set.segmented) { ctx->set_error(SVIMGPU_ERR_STATE, "cluster: the selected list was collected again since svimgpu_use_collected"); return SVIMGPU_ERR_STATE; }
+        if (ctx->peer_failed) { ctx->set_error(SVIMGPU_ERR_NCCL, "cluster: a peer rank's insertion bytes could not be mapped (CUDA IPC); run with SVIM_PEER_INS=0"); return SVIMGPU_ERR_NCCL; }
+        const uint32_t* h = ctx->h_hdr.as<uint32_t>();
+        const uint32_t s_lo = h[HDR_SLO], S = h[HDR_SHI] - h[HDR_SLO];
+        const int R = (int)set.seg_ptr.size();
+        ins_blob = nullptr; ins_blob_bytes = 0;
+        if (S > 0 && n_ins > 0) {
+            StageTimer t(ctx, T_PEER_INS);
+            SVIM_CUDA(ctx->d_seg_tab.ensure((size_t)(2 * R + 1) * 8));
+            SVIM_CUDA(cudaMemcpyAsync(ctx->d_seg_tab.p, set.seg_base.data(), (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st));
+            SVIM_CUDA(cudaMemcpyAsync(ctx->d_seg_tab.as<int64_t>() + R + 1, set.seg_ptr.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+            SegTab tab{ctx->d_seg_tab.as<int64_t>(), (const uint8_t* const*)(ctx->d_seg_tab.as<int64_t>() + R + 1), R};
+            SVIM_CUDA(ctx->d_shard_len.ensure((size_t)(S + 1) * 16));
+            uint64_t* len = ctx->d_shard_len.as<uint64_t>(); uint64_t* off = len + (S + 1);
+            { ctx->launches++; k_shard_ins_len<<<(S + 1 + 255) / 256, 256, 0, st>>>(sorted, ctx->d_samp_idx.as<uint32_t>(), s_lo, S, tab, len); }
+            size_t tmp = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp, len, off, (int)S + 1, st);
+            SVIM_CUDA(ctx->d_sort_tmp.ensure(tmp));
+            SVIM_CUDA(cub::DeviceScan::ExclusiveSum(ctx->d_sort_tmp.p, tmp, len, off, (int)S + 1, st));
+            uint64_t total = 0;
+            SVIM_CUDA(cudaMemcpyAsync(&total, off + S, 8, cudaMemcpyDeviceToHost, st));
+            SVIM_CUDA(cudaStreamSynchronize(st));
+            SVIM_CUDA(ctx->d_shard_ins.ensure((size_t)total + 16));
+            if (total > 0) { ctx->launches++; k_shard_ins_copy<<<(uint32_t)(((uint64_t)S * 32 + 255) / 256), 256, 0, st>>>(ctx->d_csig_sorted.as<svim_csig>(), ctx->d_samp_idx.as<uint32_t>(), s_lo, S, tab, off,
+                                                                                                                  ctx->d_shard_ins.as<uint8_t>()); }
+            ins_blob = ctx->d_shard_ins.as<uint8_t>(); ins_blob_bytes = (int64_t)total;
+        }
+    }
     const uint32_t* d_small = ctx->d_plist.as<uint32_t>(); const uint32_t* d_large = d_small + P;
     const uint32_t* d_ins = d_large + P;
     uint32_t* d_misc = ctx->d_part_stats.as<uint32_t>();
@@ -700,7 +779,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
         {
             StageTimer t(ctx, T_PAIRS);
             SVIM_CUDA(cudaMemsetAsync(d_ctl, 0, MYERS_CTL_N * 4, st));
-            { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
+            { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ins_blob, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
                                                 n_ins, ctx->d_pair_off.as<uint64_t>(), cp, 0, nullptr, nullptr, d_ctl, d_ctl + MYERS_CTL_CAP,
                                                 ctx->myers_band_num, ctx->myers_band_add, ctx->myers_tpp, d_misc + 9); }
             SVIM_CUDA(cudaMemcpyAsync(h_ctl, d_ctl, 64 * 4, cudaMemcpyDeviceToHost, st));
@@ -721,7 +800,7 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             {
                 StageTimer t(ctx, T_PAIRS);
                 SVIM_CUDA(cudaMemcpyAsync(d_ctl, pl.off, MYERS_LISTS * 4, cudaMemcpyHostToDevice, st));
-                { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ctx->cluster_ins, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
+                { ctx->launches++; k_ins_pairs<<<pblocks, 128, 0, st>>>(sorted, ins_blob, gv, ctx->d_samp_off.as<uint32_t>(), ctx->d_samp_idx.as<uint32_t>(), d_ins,
                                                     n_ins, ctx->d_pair_off.as<uint64_t>(), cp, 1, d_unsorted, ctx->d_keys[0].as<uint64_t>(), d_ctl, d_ctl + MYERS_CTL_CAP,
                                                     ctx->myers_band_num, ctx->myers_band_add, ctx->myers_tpp, d_misc + 9); }
                 // longest-processing-time-first inside every list: one radix sort on (list, ~cost)
@@ -735,10 +814,10 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
             int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
             MyersArgs ma; memset(&ma, 0, sizeof(ma));
             // symbol-code image of the INS blob for the thread-per-pair kernels (the genome's is built by svimgpu_set_genome)
-            SVIM_CUDA(ctx->d_ins_codes.ensure((size_t)ctx->cluster_ins_bytes + 16));
-            if (ctx->cluster_ins_bytes > 0) { ctx->launches++; k_tpp_encode<<<(unsigned)(((size_t)ctx->cluster_ins_bytes + 16 * 256 - 1) / (16 * 256)), 256, 0, st>>>(ctx->cluster_ins, ctx->cluster_ins_bytes, ctx->d_ins_codes.as<uint8_t>()); }
-            ma.genome_codes = ctx->d_genome_codes.as<uint8_t>(); ma.ins_codes = ctx->d_ins_codes.as<uint8_t>(); ma.ins_base = ctx->cluster_ins;
-            ma.sig = sorted; ma.ins_blob = ctx->cluster_ins; ma.g = gv; ma.ed_out = ctx->d_pair_ed.as<int32_t>(); ma.maxlen = maxlen;
+            SVIM_CUDA(ctx->d_ins_codes.ensure((size_t)ins_blob_bytes + 16));
+            if (ins_blob_bytes > 0) { ctx->launches++; k_tpp_encode<<<(unsigned)(((size_t)ins_blob_bytes + 16 * 256 - 1) / (16 * 256)), 256, 0, st>>>(ins_blob, ins_blob_bytes, ctx->d_ins_codes.as<uint8_t>()); }
+            ma.genome_codes = ctx->d_genome_codes.as<uint8_t>(); ma.ins_codes = ctx->d_ins_codes.as<uint8_t>(); ma.ins_base = ins_blob;
+            ma.sig = sorted; ma.ins_blob = ins_blob; ma.g = gv; ma.ed_out = ctx->d_pair_ed.as<int32_t>(); ma.maxlen = maxlen;
             ma.fallback = d_work + n_work; ma.cells = (unsigned long long*)(d_misc + 12); ma.err = d_misc + 9;
             ma.band_num = ctx->myers_band_num; ma.band_add = ctx->myers_band_add;
             StringPairs none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -818,6 +897,13 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     // ---- final order + D2H -------------------------------------------------------------------------------------------
     SVIM_CUDA(ctx->h_clusters.ensure((size_t)(n_clusters + 1) * sizeof(svim_cluster))); SVIM_CUDA(ctx->h_members.ensure((size_t)(n_members + 1) * 4));
     ctx->n_clusters_host = n_clusters; ctx->n_members_host = n_members;
+    // the member array is final here: its D2H runs on a side stream under the ordering of the cluster records
+    cudaStream_t side = ctx->aux_stream[0];
+    if (n_members) {
+        SVIM_CUDA(cudaEventRecord(ctx->aux_ev[0], st));
+        SVIM_CUDA(cudaStreamWaitEvent(side, ctx->aux_ev[0], 0));
+        SVIM_CUDA(cudaMemcpyAsync(ctx->h_members.p, ctx->d_members.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost, side));
+    }
     if (n_clusters > 0) {
         StageTimer t(ctx, T_ORDER);
         const uint32_t cb = (n_clusters + 255) / 256;
@@ -838,11 +924,11 @@ static int cluster_run(svimgpu_ctx* ctx, svim_cluster_stats* stats, int shard_ra
     {
         StageTimer t(ctx, T_CLUSTER_D2H);              // page-locked destinations: the copies run at PCIe rate and do not stage through the driver
         if (n_clusters) SVIM_CUDA(cudaMemcpyAsync(ctx->h_clusters.p, ctx->d_clusters_sorted.p, (size_t)n_clusters * sizeof(svim_cluster), cudaMemcpyDeviceToHost, st));
-        if (n_members) SVIM_CUDA(cudaMemcpyAsync(ctx->h_members.p, ctx->d_members.p, (size_t)n_members * 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaMemcpyAsync(hh, ctx->d_hdr.p, HDR_WORDS * 4, cudaMemcpyDeviceToHost, st));
         SVIM_CUDA(cudaMemcpyAsync(hh + HDR_WORDS, d_misc, 16 * 4, cudaMemcpyDeviceToHost, st));
     }
     SVIM_CUDA(cudaStreamSynchronize(st));
+    if (n_members) SVIM_CUDA(cudaStreamSynchronize(side));
     const uint32_t* h = hh + HDR_WORDS;
     if (h[9]) {
         const char* why = h[9] == 2 ? "haplotype longer than the scratch bound" : h[9] == 3 ? "BND cluster with mixed directions (assertion in consolidate_clusters_bilocal)"

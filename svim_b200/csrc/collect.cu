@@ -983,7 +983,7 @@ static int collect_sort_queue(svimgpu_ctx* ctx, int which, uint32_t n_reserved, 
     // queue[which] (arbitrary order, with holes) -> sets[which].recs in emission order + INS blob
     SigSet& set = ctx->sets[which];
     const uint32_t n_all = n_reserved, n = n_reserved - n_holes;
-    set.n = n; set.ins_bytes = 0;
+    set.n = n; set.ins_bytes = 0; set.segmented = false;
     if (n == 0) return 0;
     SVIM_CUDA(set.recs.ensure((size_t)n * sizeof(svim_sig)));
     SVIM_CUDA(ctx->d_keys[0].ensure((size_t)n_all * 8)); SVIM_CUDA(ctx->d_keys[1].ensure((size_t)n_all * 8));

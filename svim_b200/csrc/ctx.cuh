@@ -82,14 +82,22 @@ enum {  // device counters
 enum {  // timing slots
     T_H2D = 0, T_SCAN, T_CHAIN, T_SORTBACK, T_GATHER, T_COLLECT_D2H, T_CSIG, T_KEYSORT, T_PARTITION, T_SAMPLE, T_PAIRS,
     T_MYERS, T_LINKAGE, T_CONSOLIDATE, T_ORDER, T_CLUSTER_D2H, T_EXCHANGE, T_GENO_PREP, T_GENO, T_CUTPASTE,
-    T_BAM_INFLATE, T_BAM_BOUNDS, T_BAM_ROWS, T_BAM_FILL, T_BAM_NAMES, T_N
+    T_BAM_INFLATE, T_BAM_BOUNDS, T_BAM_ROWS, T_BAM_FILL, T_BAM_NAMES, T_PEER_INS, T_N
 };
 
 struct SigSet {   // one signature list on the device (main / all_bnds twins)
     DevBuf recs;        // svim_sig[n], emission order
     DevBuf ins;         // INS blob
     int64_t n = 0, ins_bytes = 0;
+    // After svimgpu_exchange_signatures (peer mode): recs holds every rank's records, ins_bytes is the size of the GLOBAL blob the
+    // records' seq_off point into, but the bytes stay where they were produced: rank r's piece [seg_base[r], seg_base[r+1]) is read
+    // through seg_ptr[r] (this rank's own `ins`, or a CUDA-IPC mapping of the peer's buffer: NVLink loads).
+    bool segmented = false;
+    std::vector<int64_t> seg_base;
+    std::vector<const uint8_t*> seg_ptr;
 };
+
+struct PeerMap { cudaIpcMemHandle_t handle; void* p = nullptr; };   // an opened mapping of a peer rank's INS blob
 
 #define SVIM_AUX_STREAMS 20     // every edit-distance bucket on its own stream: the block scheduler packs their CTAs side by side
 
@@ -171,6 +179,14 @@ struct svimgpu_ctx {
 
     // multi-GPU
     void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+    bool peer_ins = true;                  // SVIM_PEER_INS=0: all-gather the INS blobs too (every rank holds a full copy)
+    bool mirror_gathered_ins = true;       // svimgpu_mirror_gathered_ins
+    bool host_copy_has_ins[2] = {true, true};
+    bool host_copy_pending = false;        // collect_host on a rank of a multi-GPU job: the mirror starts after the exchange
+    bool peer_failed = false;              // a mapping could not be opened: the next sharded cluster reports it through its status agreement
+    std::vector<PeerMap> peer_map[2];
+    int cluster_seg = -1;                  // >= 0: the clustering input is the segmented set `cluster_seg` (cluster_ins is filled per call)
+    DevBuf d_seg_tab, d_shard_ins, d_shard_len;
     DevBuf d_xchg[8];          // [0,4) gathered arrays, [4] packed send/receive slots, [5] count gather, [6] barrier word
 
     // timing

@@ -20,6 +20,12 @@
     } while (0)
 
 static void nccl_teardown(svimgpu_ctx* ctx) {
+    for (int w = 0; w < 2; ++w) {
+        for (PeerMap& m : ctx->peer_map[w]) if (m.p) cudaIpcCloseMemHandle(m.p);
+        ctx->peer_map[w].clear();
+        ctx->sets[w].segmented = false; ctx->sets[w].seg_ptr.clear(); ctx->sets[w].seg_base.clear();
+    }
+    ctx->peer_failed = false;
     if (ctx->nccl_comm) { ncclCommDestroy((ncclComm_t)ctx->nccl_comm); ctx->nccl_comm = nullptr; }
 }
 
@@ -141,44 +147,86 @@ int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collec
     if (!ctx->nccl_comm) { ctx->set_error(SVIMGPU_ERR_STATE, "svimgpu_comm_init not called"); return SVIMGPU_ERR_STATE; }
     cudaSetDevice(ctx->device);
     // the local lists are replaced by the global ones: a host copy in flight (collect_host) is dropped and restarted at the end
-    const bool want_host = ctx->host_copy[0] || ctx->host_copy[1];
-    if (want_host) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
+    const bool want_host = ctx->host_copy[0] || ctx->host_copy[1] || ctx->host_copy_pending;
+    if (ctx->host_copy[0] || ctx->host_copy[1]) { cudaStreamSynchronize(ctx->copy_stream); ctx->host_copy[0] = ctx->host_copy[1] = false; }
+    ctx->host_copy_pending = false;
     timings_begin(ctx);
     const int R = ctx->nranks;
     {
         StageTimer t(ctx, T_EXCHANGE);
-        int64_t mine[12] = {ctx->sets[0].n, ctx->sets[0].ins_bytes, ctx->sets[1].n, ctx->sets[1].ins_bytes, (int64_t)aln_base,
+        // counts, and (peer mode) the CUDA-IPC handle of each list's INS blob: the bytes are not moved here.  Every rank later reads
+        // the sequences its own partitions compare straight from the rank that holds them (cluster.cu, k_shard_ins_copy).
+        constexpr int NW = 12 + 2 * 8;
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        const bool peer = ctx->peer_ins;
+        int64_t mine[NW] = {ctx->sets[0].n, ctx->sets[0].ins_bytes, ctx->sets[1].n, ctx->sets[1].ins_bytes, (int64_t)aln_base,
                             ctx->cstats.n_sa_bad_fields, ctx->cstats.n_no_read_length, ctx->cstats.n_primaries, ctx->cstats.n_data_errors, 0, 0, 0};
-        std::vector<int64_t> all(12 * R);
-        int rc = nccl_allgather_i64(ctx, mine, 12, all.data()); if (rc) return rc;
-        // both lists (main, --all_bnds twins), records and INS blobs: four arrays per rank, one collective
-        std::vector<int64_t> bytes(4 * R);
+        if (peer)
+            for (int w = 0; w < 2; ++w)
+                if (ctx->sets[w].ins_bytes > 0 && ctx->sets[w].ins.p) {
+                    cudaIpcMemHandle_t hd;
+                    if (cudaIpcGetMemHandle(&hd, ctx->sets[w].ins.p) == cudaSuccess) { memcpy(mine + 12 + 8 * w, &hd, 64); mine[9 + w] = 1; }
+                    else cudaGetLastError();                 // the peers see "no handle" and fail in their cluster call
+                }
+        std::vector<int64_t> all((size_t)NW * R);
+        int rc = nccl_allgather_i64(ctx, mine, NW, all.data()); if (rc) return rc;
+        const int K = peer ? 2 : 4;        // arrays per rank in the payload gather: records of both lists (+ the INS blobs)
+        std::vector<int64_t> bytes((size_t)K * R);
         int64_t nt[2] = {0, 0}, it[2] = {0, 0}, my_blob_base[2] = {0, 0};
         for (int r = 0; r < R; ++r)
             for (int w = 0; w < 2; ++w) {
-                bytes[4 * r + 2 * w] = all[12 * r + 2 * w] * (int64_t)sizeof(svim_sig); bytes[4 * r + 2 * w + 1] = all[12 * r + 2 * w + 1];
-                if (r < ctx->rank) my_blob_base[w] += all[12 * r + 2 * w + 1];
-                nt[w] += all[12 * r + 2 * w]; it[w] += all[12 * r + 2 * w + 1];
+                if (peer) bytes[2 * r + w] = all[(size_t)NW * r + 2 * w] * (int64_t)sizeof(svim_sig);
+                else { bytes[4 * r + 2 * w] = all[(size_t)NW * r + 2 * w] * (int64_t)sizeof(svim_sig); bytes[4 * r + 2 * w + 1] = all[(size_t)NW * r + 2 * w + 1]; }
+                if (r < ctx->rank) my_blob_base[w] += all[(size_t)NW * r + 2 * w + 1];
+                nt[w] += all[(size_t)NW * r + 2 * w]; it[w] += all[(size_t)NW * r + 2 * w + 1];
             }
+        if (peer) {
+            ctx->peer_failed = false;
+            for (int w = 0; w < 2; ++w) {
+                SigSet& set = ctx->sets[w];
+                set.seg_base.assign((size_t)R + 1, 0); set.seg_ptr.assign((size_t)R, nullptr);
+                ctx->peer_map[w].resize((size_t)R);
+                for (int r = 0; r < R; ++r) {
+                    const int64_t len = all[(size_t)NW * r + 2 * w + 1];
+                    set.seg_base[r + 1] = set.seg_base[r] + len;
+                    if (len <= 0) continue;
+                    if (r == ctx->rank) { set.seg_ptr[r] = set.ins.as<uint8_t>(); continue; }
+                    PeerMap& m = ctx->peer_map[w][r];
+                    const void* hd = &all[(size_t)NW * r + 12 + 8 * w];
+                    if (!all[(size_t)NW * r + 9 + w]) { ctx->peer_failed = true; continue; }
+                    if (!m.p || memcmp(&m.handle, hd, 64) != 0) {          // first time, or the peer's buffer was reallocated
+                        if (m.p) { cudaIpcCloseMemHandle(m.p); m.p = nullptr; }
+                        memcpy(&m.handle, hd, 64);
+                        if (cudaIpcOpenMemHandle(&m.p, m.handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); m.p = nullptr; ctx->peer_failed = true; continue; }
+                    }
+                    set.seg_ptr[r] = (const uint8_t*)m.p;
+                }
+            }
+        }
         const void* src[4]; uint8_t* dst[4];
         for (int w = 0; w < 2; ++w) {
             SigSet& set = ctx->sets[w];
             // make local records global before sending: record index += aln_base, INS offset += blob base
             if (set.n) { ctx->launches++; k_rebase_sigs<<<(uint32_t)((set.n + 255) / 256), 256, 0, ctx->stream>>>(set.recs.as<svim_sig>(), (uint32_t)set.n, aln_base, (uint64_t)my_blob_base[w]); }
-            SVIM_CUDA(ctx->d_xchg[2 * w].ensure((size_t)(nt[w] + 1) * sizeof(svim_sig))); SVIM_CUDA(ctx->d_xchg[2 * w + 1].ensure((size_t)it[w] + 16));
-            src[2 * w] = set.recs.p; src[2 * w + 1] = set.ins.p;
-            dst[2 * w] = ctx->d_xchg[2 * w].as<uint8_t>(); dst[2 * w + 1] = ctx->d_xchg[2 * w + 1].as<uint8_t>();
+            SVIM_CUDA(ctx->d_xchg[2 * w].ensure((size_t)(nt[w] + 1) * sizeof(svim_sig)));
+            if (peer) { src[w] = set.recs.p; dst[w] = ctx->d_xchg[2 * w].as<uint8_t>(); }
+            else {
+                SVIM_CUDA(ctx->d_xchg[2 * w + 1].ensure((size_t)it[w] + 16));
+                src[2 * w] = set.recs.p; src[2 * w + 1] = set.ins.p;
+                dst[2 * w] = ctx->d_xchg[2 * w].as<uint8_t>(); dst[2 * w + 1] = ctx->d_xchg[2 * w + 1].as<uint8_t>();
+            }
         }
-        rc = nccl_allgatherv_packed(ctx, 4, src, bytes.data(), dst); if (rc) return rc;
+        rc = nccl_allgatherv_packed(ctx, K, src, bytes.data(), dst); if (rc) return rc;
         for (int w = 0; w < 2; ++w) {
             SigSet& set = ctx->sets[w];
-            std::swap(set.recs, ctx->d_xchg[2 * w]); std::swap(set.ins, ctx->d_xchg[2 * w + 1]);
-            set.n = nt[w]; set.ins_bytes = it[w];
+            std::swap(set.recs, ctx->d_xchg[2 * w]);
+            if (!peer) std::swap(set.ins, ctx->d_xchg[2 * w + 1]);
+            set.n = nt[w]; set.ins_bytes = it[w]; set.segmented = peer;
         }
         svim_collect_stats& s = ctx->cstats;
         s.n_signatures = ctx->sets[0].n; s.ins_bytes = ctx->sets[0].ins_bytes; s.n_twin_signatures = ctx->sets[1].n; s.twin_ins_bytes = ctx->sets[1].ins_bytes;
         s.n_sa_bad_fields = s.n_no_read_length = s.n_primaries = s.n_data_errors = 0;
-        for (int r = 0; r < R; ++r) { s.n_sa_bad_fields += all[12 * r + 5]; s.n_no_read_length += all[12 * r + 6]; s.n_primaries += all[12 * r + 7]; s.n_data_errors += all[12 * r + 8]; }
+        for (int r = 0; r < R; ++r) { s.n_sa_bad_fields += all[(size_t)NW * r + 5]; s.n_no_read_length += all[(size_t)NW * r + 6]; s.n_primaries += all[(size_t)NW * r + 7]; s.n_data_errors += all[(size_t)NW * r + 8]; }
     }
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
     timings_end(ctx);

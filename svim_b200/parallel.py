@@ -59,7 +59,9 @@ def init_comm(ctx: "_lib.Context"):
 
 
 def collect_and_cluster(ctx: "_lib.Context", aln_base: int, which: int = 0):
-    """collect (local shard, already uploaded) -> exchange -> sharded cluster; every rank returns the full result."""
+    """collect (local shard, already uploaded) -> exchange -> sharded cluster; every rank returns the full result.
+    The inserted sequences stay on the rank that collected them (include/svimgpu.h, svimgpu_exchange_signatures): barrier between
+    a `fetch_signatures` of the gathered lists and the next collect of any rank."""
     cst = ctx.collect()
     xst = _lib.CollectStats()
     ctx._check(ctx.lib.svimgpu_exchange_signatures(ctx.h, aln_base, C.byref(xst)))

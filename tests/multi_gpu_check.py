@@ -36,6 +36,7 @@ def main():
     # a rank that fails before the cluster exchange must not leave the others waiting in it, and nobody may keep a result:
     # the failing rank reports its own error, every other rank SVIMGPU_ERR_PEER (-7); the next call works again
     if world > 1:
+        dist.barrier()          # the other ranks may still be fetching this rank's insertion bytes (include/svimgpu.h, exchange)
         os.environ["SVIM_TEST_FAIL_RANK"] = str(world - 1)
         ctx.collect()
         xst = _lib.CollectStats()
