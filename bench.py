@@ -581,8 +581,10 @@ def main():
                    "myers_banded_pairs": int(clst.myers_banded_pairs), "myers_handed_over": int(clst.myers_retry_pairs),
                    "myers_band_cells": int(clst.myers_band_cells),
                    "l2": "inputs larger than L2 (%.2f GB CIGAR per GPU vs 126 MB)" % (batch.cigar.nbytes / 1e9),
-                   "parallelism": ("contiguous record ranges of one input balanced by CIGAR volume; 2 NCCL allgatherv" if args.shard == "records" else
-                                   "records sharded by contig; 2 NCCL allgatherv") if world > 1 else "single GPU",
+                   "parallelism": (("contiguous record ranges of one input balanced by CIGAR volume" if args.shard == "records" else "records sharded by contig")
+                                   + "; 2 NCCL allgatherv (signature records, cluster records); inserted sequences "
+                                   + ("read from the owning rank through NVSwitch peer memory (CUDA IPC)" if ctx.lib.svimgpu_peer_ins_active(ctx.h) else "gathered with the records")
+                                   ) if world > 1 else "single GPU",
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},

@@ -287,7 +287,10 @@ int svimgpu_closest_source(svimgpu_ctx* ctx, int64_t n_a, const int64_t* a_start
 /* ---- multi-GPU (one process per GPU) ------------------------------------------------ */
 /* id_bytes: 128-byte ncclUniqueId from svimgpu_nccl_unique_id on rank 0. */
 int svimgpu_nccl_unique_id(uint8_t* id_bytes /*128*/);
+/* Also probes CUDA IPC between the ranks once; if any rank cannot map a peer's memory all ranks agree to gather the INS blobs
+ * instead (see svimgpu_exchange_signatures).  svimgpu_peer_ins_active: 1 = peer-mapped, 0 = gathered. */
 int svimgpu_comm_init(svimgpu_ctx* ctx, int nranks, int rank, const uint8_t* id_bytes);
+int svimgpu_peer_ins_active(svimgpu_ctx* ctx);
 /* allgatherv of the collected signature records of all ranks: after it every rank holds the full lists (record indices made
  * global with aln_base, seq_off pointing into the concatenation of all ranks' INS blobs in rank order).  The INS bytes themselves
  * are not moved: each rank keeps its piece and the others map it (CUDA IPC over NVLink / NVSwitch peer memory).

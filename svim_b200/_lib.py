@@ -135,6 +135,7 @@ EXPORTS = {
     "svimgpu_fetch_clusters": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "svimgpu_clusters_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "svimgpu_mirror_gathered_ins": (C.c_int, [C.c_void_p, C.c_int]),
+    "svimgpu_peer_ins_active": (C.c_int, [C.c_void_p]),
     "svimgpu_fetch_partitions": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]),
     "svimgpu_genotype": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(GenoParams), C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                   C.c_int32, C.c_void_p]),

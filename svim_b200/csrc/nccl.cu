@@ -138,8 +138,42 @@ int svimgpu_comm_init(svimgpu_ctx* ctx, int nranks, int rank, const uint8_t* id_
     ncclComm_t comm;
     SVIM_NCCL(ncclCommInitRank(&comm, nranks, id, rank));
     ctx->nccl_comm = comm; ctx->nranks = nranks; ctx->rank = rank;
+    if (const char* v = getenv("SVIM_PEER_INS")) ctx->peer_ins = atoi(v) != 0; else ctx->peer_ins = true;
+    // Peer-mapped INS blobs need CUDA IPC between the ranks' processes.  Try it once on a probe buffer and let the ranks agree: if any
+    // mapping fails (no P2P path, IPC not permitted in this container) every rank gathers the blobs instead.
+    if (ctx->peer_ins && nranks > 1) {
+        DevBuf probe;
+        int64_t mine[9] = {0};
+        cudaIpcMemHandle_t hd;
+        if (probe.ensure(256) == cudaSuccess && cudaIpcGetMemHandle(&hd, probe.p) == cudaSuccess) { memcpy(mine + 1, &hd, 64); mine[0] = 1; }
+        else cudaGetLastError();
+        std::vector<int64_t> all((size_t)9 * nranks);
+        int rc = nccl_allgather_i64(ctx, mine, 9, all.data()); if (rc) { probe.release(); return rc; }
+        int64_t ok = 1;
+        std::vector<void*> opened;
+        for (int r = 0; r < nranks; ++r) {
+            if (!all[(size_t)9 * r]) { ok = 0; continue; }
+            if (r == rank) continue;
+            cudaIpcMemHandle_t h; memcpy(&h, &all[(size_t)9 * r + 1], 64);
+            void* p = nullptr; uint32_t word = 0;
+            if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; continue; }
+            opened.push_back(p);
+            if (cudaMemcpy(&word, p, 4, cudaMemcpyDefault) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+        }
+        std::vector<int64_t> oks((size_t)nranks);
+        rc = nccl_allgather_i64(ctx, &ok, 1, oks.data());        // also: every rank is done with the probes before any is freed
+        for (void* p : opened) cudaIpcCloseMemHandle(p);
+        if (rc) { probe.release(); return rc; }
+        for (int r = 0; r < nranks; ++r) if (!oks[r]) ctx->peer_ins = false;
+        int64_t done = 1;
+        rc = nccl_allgather_i64(ctx, &done, 1, oks.data());       // mappings closed everywhere
+        probe.release();
+        if (rc) return rc;
+    }
     return 0;
 }
+
+int svimgpu_peer_ins_active(svimgpu_ctx* ctx) { return ctx && ctx->nccl_comm && ctx->nranks > 1 && ctx->peer_ins ? 1 : 0; }
 
 int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collect_stats* stats) {
     if (!ctx) return SVIMGPU_ERR_ARG;

@@ -16,6 +16,8 @@ def main():
     dist.init_process_group("gloo")
     ctx = _lib.Context(device=local)
     parallel.init_comm(ctx)
+    if rank == 0:
+        print("inserted sequences:", "peer memory" if ctx.lib.svimgpu_peer_ins_active(ctx.h) else "gathered", flush=True)
     for name in ("mini_mixed", "mini_ins", "mini_hotspot", "mini_mixed_allbnds"):
         batch, genome, exp = load_golden(name)
         ctx.set_params(_lib.Params.from_options(None, **exp["params"]))

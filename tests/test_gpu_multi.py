@@ -20,10 +20,14 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-def test_two_ranks_reproduce_golden():
+@pytest.mark.parametrize("peer_ins", ["1", "0"])
+def test_two_ranks_reproduce_golden(peer_ins):
+    """peer_ins=1: the inserted sequences stay on the rank that collected them and are read through peer memory;
+    peer_ins=0: they are gathered with the records.  Both must reproduce the goldens on every rank."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, SVIM_PEER_INS=peer_ins))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("multi-gpu ok") == 5
+    assert ("inserted sequences: peer memory" in r.stdout) == (peer_ins == "1"), r.stdout[-2000:]
