@@ -311,7 +311,8 @@ def main():
                          "workload, contiguous record ranges balanced by CIGAR volume (strong scaling)")
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-cigar16", action="store_true", help="e2e legs upload BAM's uint32 CIGAR words instead of the 16-bit packed stream")
+    ap.add_argument("--no-cigar16", action="store_true", help="e2e legs upload BAM's uint32 CIGAR words instead of a packed stream (same as --cigar-pack 32)")
+    ap.add_argument("--cigar-pack", type=int, choices=[8, 16, 32], default=16, help="CIGAR stream of the e2e legs: 8 = svim_aln_soa.cigar8, 16 = cigar16, 32 = BAM's uint32 words")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
     ap.add_argument("--no-bam", action="store_true", help="skip the e2e_from_bam leg (writes a BAM of the workload to a temporary directory)")
     ap.add_argument("--with-bam", action="store_true", help=argparse.SUPPRESS)        # round-1 spelling: the leg is on by default now
@@ -411,13 +412,18 @@ def main():
         return
 
     # ---------------- e2e: host buffers through the C ABI, copies inside the timed region --------
-    # the record buffer crosses PCIe with its CIGAR blob in the 16-bit packed form of include/svimgpu.h (svim_aln_soa.cigar16: what
-    # svim_b200's decoders hand over; re-encoded here once, outside the timed region) and is expanded to BAM's uint32 words in HBM
+    # the record buffer crosses PCIe with its CIGAR blob in a packed form of include/svimgpu.h (svim_aln_soa.cigar8 / cigar16), re-encoded
+    # by the host ONCE, outside the timed region (csrc_host/bamio.cpp, multi-threaded; its time is reported as e2e.cigar_pack_s), and is
+    # expanded to BAM's uint32 words in HBM inside it
     t_pack = time.perf_counter()
-    if not args.no_cigar16:
+    pack = 32 if args.no_cigar16 else args.cigar_pack
+    if pack == 16:
         batch.pack_cigar16()
+    elif pack == 8:
+        batch.pack_cigar8()
     t_pack = time.perf_counter() - t_pack
-    pinned = ([batch.cigar16, batch.cigar16_off] if batch.cigar16 is not None else [batch.cigar]) + [batch.seq, batch.sa] + [getattr(batch, f) for f, _ in batch.FIELDS]
+    packed_arrays = [batch.cigar8, batch.cigar8_off] if batch.cigar8 is not None else [batch.cigar16, batch.cigar16_off] if batch.cigar16 is not None else [batch.cigar]
+    pinned = packed_arrays + [batch.seq, batch.sa] + [getattr(batch, f) for f, _ in batch.FIELDS]
     for a in pinned:
         ctx.pin(a)
     # collect_host keeps SEQ on the host and uploads only the packed bases of emitted insertions (lazy SEQ)
@@ -588,8 +594,10 @@ def main():
                    "input_generation_s": round(t_gen, 1)},
         "e2e": {"value": total_aln / (e2e_step * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_step, "stages_ms": {k: round(float(np.mean(v)), 4) for k, v in e2e_stage.items()},
-                "cigar_upload": ("16-bit packed stream (svim_aln_soa.cigar16), %.2f GB; expanded on the device" % (batch.cigar16.nbytes / 1e9)) if batch.cigar16 is not None
+                "cigar_upload": ("8-bit packed stream (svim_aln_soa.cigar8), %.2f GB; expanded on the device" % (batch.cigar8.nbytes / 1e9)) if batch.cigar8 is not None
+                                else ("16-bit packed stream (svim_aln_soa.cigar16), %.2f GB; expanded on the device" % (batch.cigar16.nbytes / 1e9)) if batch.cigar16 is not None
                                 else "uint32 BAM words, %.2f GB" % (batch.cigar.nbytes / 1e9),
+                "cigar_pack_s": round(t_pack, 3),
                 "result_on_host": ("rank 0: gathered signature records + every rank's insertion bytes + cluster arrays; other ranks: gathered records + cluster arrays"
                                    if world > 1 else "signature records + insertion bytes + cluster arrays"),
                 "clocks": clocks_e2e},

@@ -70,9 +70,16 @@ typedef struct {
      * uploads it instead of `cigar` (which may then be NULL) and expands it to the uint32 words on the device.
      * Word = len << 4 | op for len < 4096; words with op nibble 0xF carry 12 more significant length bits each and precede
      * the op word; every record's stream starts at cigar16_off[i] (uint16 units, multiple of 8) and is padded with 0x000F.
-     * svim_b200.io's BAM decoders and bamio_pack_cigar16 (csrc_host/bamio.cpp) produce it. */
+     * bamio_pack_cigar16 (csrc_host/bamio.cpp; AlignmentBatch.pack_cigar16) produces it. */
     const uint16_t* cigar16; int64_t cigar16_words;
     const uint64_t* cigar16_off;                 /* n_aln + 1 entries */
+    /* Optional 8-bit packed CIGAR stream, taken in preference to cigar16 / cigar when set: noisy long reads have almost only short
+     * operations (91 % under 16 bases on the CLR-like workloads), so one byte per operation carries them: 1.09 bytes per operation
+     * on BASELINE configs[1] against 2 and 4.  Byte = len << 4 | op for len < 16; bytes with op nibble 0xF carry 4 more
+     * significant length bits each and precede the operation byte (most significant first, no leading zero extension);
+     * every record's stream starts at cigar8_off[i] (bytes, multiple of 16) and is padded with 0x0F.  bamio_pack_cigar8. */
+    const uint8_t* cigar8; int64_t cigar8_bytes;
+    const uint64_t* cigar8_off;                  /* n_aln + 1 entries */
 } svim_aln_soa;
 
 /* Signature types, in the reference's clustering call order (SVIM_CLUSTER.py:19-24). */

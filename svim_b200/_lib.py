@@ -53,7 +53,8 @@ class AlnSoa(C.Structure):
                 ("tid", "pos", "flag", "mapq", "n_cigar", "cigar_off", "l_seq", "seq_off", "sa_off", "sa_len", "qname_id")] + \
                [("cigar", C.c_void_p), ("cigar_words", C.c_int64), ("seq", C.c_void_p), ("seq_bytes", C.c_int64),
                 ("sa", C.c_void_p), ("sa_bytes", C.c_int64),
-                ("cigar16", C.c_void_p), ("cigar16_words", C.c_int64), ("cigar16_off", C.c_void_p)]
+                ("cigar16", C.c_void_p), ("cigar16_words", C.c_int64), ("cigar16_off", C.c_void_p),
+                ("cigar8", C.c_void_p), ("cigar8_bytes", C.c_int64), ("cigar8_off", C.c_void_p)]
 
 
 SIG_DTYPE = np.dtype([("start", "<i4"), ("end", "<i4"), ("pos", "<i4"), ("contig1", "<i4"), ("contig2", "<i4"),
@@ -262,6 +263,9 @@ class Context:
         c16 = getattr(batch, "cigar16", None)
         if c16 is not None:          # packed CIGAR stream (AlignmentBatch.pack_cigar16): uploaded instead of the uint32 words
             s.cigar16 = _ptr(c16); s.cigar16_words = c16.size; s.cigar16_off = _ptr(batch.cigar16_off)
+        c8 = getattr(batch, "cigar8", None)
+        if c8 is not None:           # 8-bit packed stream (AlignmentBatch.pack_cigar8): preferred over cigar16
+            s.cigar8 = _ptr(c8); s.cigar8_bytes = c8.size; s.cigar8_off = _ptr(batch.cigar8_off)
         return s
 
     def pin(self, arr):

@@ -162,25 +162,31 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
                               (size_t)n * 8, (size_t)n * 4, (size_t)n * 4, (size_t)s->cigar_words * 4, (size_t)s->seq_bytes, (size_t)s->sa_bytes};
     {
         StageTimer t(ctx, T_H2D);
-        const bool packed = s->cigar16 != nullptr && s->cigar16_off != nullptr;
+        const bool packed8 = s->cigar8 != nullptr && s->cigar8_off != nullptr;
+        const bool packed = !packed8 && s->cigar16 != nullptr && s->cigar16_off != nullptr;
         for (int i = 0; i < 14; ++i) {
             if (i == 12 && !with_seq) continue;   // SEQ blob stays on the host (lazy path)
             SVIM_CUDA(ctx->d_soa[i].ensure(bytes[i] + 64));
-            if (i == 11 && packed) continue;      // CIGAR crosses as the 16-bit stream below
+            if (i == 11 && (packed || packed8)) continue;      // CIGAR crosses as a packed stream below
             if (bytes[i]) SVIM_CUDA(cudaMemcpyAsync(ctx->d_soa[i].p, src[i], bytes[i], cudaMemcpyHostToDevice, ctx->stream));
         }
-        if (packed) {
-            // half the PCIe bytes: upload the packed stream, expand it to BAM's uint32 words in HBM (k_expand_cigar16 reads 2 B and
+        if (packed || packed8) {
+            // a half / a quarter of the PCIe bytes: upload the packed stream, expand it to BAM's uint32 words in HBM (the expansion
             // writes 4 B per operation at HBM speed, ~25x the PCIe rate the copy just ran at)
-            SVIM_CUDA(ctx->d_cig16.ensure((size_t)s->cigar16_words * 2 + 64)); SVIM_CUDA(ctx->d_cig16_off.ensure((size_t)(n + 1) * 8));
+            const size_t pbytes = packed8 ? (size_t)s->cigar8_bytes : (size_t)s->cigar16_words * 2;
+            const void* psrc = packed8 ? (const void*)s->cigar8 : (const void*)s->cigar16;
+            const uint64_t* poff = packed8 ? s->cigar8_off : s->cigar16_off;
+            SVIM_CUDA(ctx->d_cig16.ensure(pbytes + 64)); SVIM_CUDA(ctx->d_cig16_off.ensure((size_t)(n + 1) * 8));
             SVIM_CUDA(ctx->d_cig16_err.ensure(16)); SVIM_CUDA(cudaMemsetAsync(ctx->d_cig16_err.p, 0, 4, ctx->stream));
-            if (s->cigar16_words) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16.p, s->cigar16, (size_t)s->cigar16_words * 2, cudaMemcpyHostToDevice, ctx->stream));
-            SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16_off.p, s->cigar16_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+            if (pbytes) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16.p, psrc, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+            SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16_off.p, poff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
             if (n > 0) {
                 int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
                 ctx->launches++;
-                k_expand_cigar16<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
-                                                                 ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                if (packed8) k_expand_cigar8<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
+                                                                               ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                else k_expand_cigar16<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
+                                                                        ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
                 SVIM_CUDA(cudaGetLastError());
             }
         }
@@ -193,9 +199,10 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
     d.qname_id = ctx->d_soa[10].as<uint32_t>(); d.cigar = ctx->d_soa[11].as<uint32_t>(); d.seq = ctx->d_soa[12].as<uint8_t>(); d.sa = ctx->d_soa[13].as<uint8_t>();
     ctx->cigar_words = s->cigar_words; ctx->seq_bytes = s->seq_bytes; ctx->sa_bytes = s->sa_bytes;
     uint32_t bad16 = 0;
-    if (s->cigar16 && s->cigar16_off && n > 0) SVIM_CUDA(cudaMemcpyAsync(&bad16, ctx->d_cig16_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const bool any_packed = (s->cigar16 && s->cigar16_off) || (s->cigar8 && s->cigar8_off);
+    if (any_packed && n > 0) SVIM_CUDA(cudaMemcpyAsync(&bad16, ctx->d_cig16_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     SVIM_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (bad16) { ctx->have_soa = false; ctx->set_error(SVIMGPU_ERR_ARG, "cigar16: a record's packed stream does not hold n_cigar operations"); return SVIMGPU_ERR_ARG; }
+    if (bad16) { ctx->have_soa = false; ctx->set_error(SVIMGPU_ERR_ARG, "cigar8 / cigar16: a record's packed stream does not hold n_cigar operations"); return SVIMGPU_ERR_ARG; }
     ctx->have_soa = true; ctx->collected = false;
     ctx->rows_resident = true; ctx->geno_ready = false;
     ctx->lazy_seq = !with_seq; ctx->h_seq = with_seq ? nullptr : s->seq; ctx->h_seq_off = with_seq ? nullptr : s->seq_off; ctx->lazy_aln_base = 0;

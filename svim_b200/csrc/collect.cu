@@ -760,6 +760,42 @@ __global__ void __launch_bounds__(256) k_expand_cigar16(const uint16_t* __restri
     }
 }
 
+// svim_aln_soa.cigar8 -> BAM uint32 CIGAR words.  One warp per record, 16 bytes (one 128-bit load) per lane and round.  A lane needs
+// two things from its neighbours: where its first operation lands (warp scan of the per-lane operation counts) and the extension
+// bits left pending by the bytes before it (the previous lane's c8_tail; lane 0 takes lane 31's of the previous round).
+__global__ void __launch_bounds__(256) k_expand_cigar8(const uint8_t* __restrict__ c8, const uint64_t* __restrict__ off8, const uint32_t* __restrict__ n_cigar,
+                                                        const uint64_t* __restrict__ cigar_off, int64_t n, uint32_t* __restrict__ cigar, uint32_t* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint8_t* src = c8 + off8[i];
+        const uint64_t nb = off8[i + 1] - off8[i];
+        uint32_t* dst = cigar + cigar_off[i];
+        const uint64_t nc = n_cigar[i];
+        uint64_t out = 0;            // operations written so far (warp-uniform)
+        uint32_t carry = 0;          // extension bits pending at the end of the previous round (warp-uniform)
+        uint32_t err = 0;
+        for (uint64_t base = 0; base < nb; base += 512) {
+            const uint64_t at = base + (uint64_t)lane * 16;
+            uint4 v = make_uint4(0x0F0F0F0Fu, 0x0F0F0F0Fu, 0x0F0F0F0Fu, 0x0F0F0F0Fu);
+            if (at < nb) v = *(const uint4*)(src + at);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t cnt = 16u - c8_ext_bytes(w);
+            uint32_t pre = cnt;                              // inclusive warp scan
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const uint32_t tail = c8_tail(w);
+            uint32_t init = __shfl_up_sync(0xffffffffu, tail, 1);
+            if (lane == 0) init = carry;
+            c8_decode_lane(w, init, out + pre - cnt, nc, dst, &err);
+            out += __shfl_sync(0xffffffffu, pre, 31);
+            carry = __shfl_sync(0xffffffffu, tail, 31);
+        }
+        if (__any_sync(0xffffffffu, err) || out != nc || carry) { if (lane == 0) atomicExch(bad, 1u); }
+        for (uint32_t k = (uint32_t)nc + lane; k < (((uint32_t)nc + 3u) & ~3u); k += 32) dst[k] = 0u;      // records are padded to 16 bytes with zero words
+    }
+}
+
 __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
                                                         SigQueue qm, SigQueue qt, uint32_t* cnt, uint32_t* big_list) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;

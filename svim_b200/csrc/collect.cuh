@@ -281,3 +281,46 @@ SVIM_HD void sort_chain(Seg* c, int n) {
         c[j + 1] = x;
     }
 }
+
+// ---- svim_aln_soa.cigar8 (include/svimgpu.h): byte = len4 << 4 | op; op nibble 0xF = a length-extension byte whose high nibble
+// carries 4 more significant bits, extension bytes precede the operation byte (most significant first), pad = 0x0F.
+// k_expand_cigar8 gives every lane 16 bytes per round; these are the per-lane pieces (replayed on the host by tests/hostcheck).
+SVIM_HD uint32_t c8_ext_bytes(const uint32_t w[4]) {            // how many of the 16 bytes are extension / pad bytes
+    uint32_t n = 0;
+    for (int q = 0; q < 4; ++q) {
+        uint32_t e = ((w[q] & 0x0F0F0F0Fu) + 0x01010101u) & 0x10101010u;      // bit 4 of a byte set <=> its low nibble is 0xF
+        e = (e >> 4) * 0x01010101u;                                            // byte sum in the top byte
+        n += e >> 24;
+    }
+    return n;
+}
+
+SVIM_HD uint32_t c8_byte(const uint32_t w[4], int k) { return (w[k >> 2] >> (8 * (k & 3))) & 0xFFu; }
+
+// value accumulated by the run of extension bytes that ends the lane's 16 bytes (0 when the last byte is an operation):
+// the operation it belongs to is the first one of the NEXT lane
+SVIM_HD uint32_t c8_tail(const uint32_t w[4]) {
+    int s = 16;
+    while (s > 0 && (c8_byte(w, s - 1) & 15u) == 15u) --s;
+    uint32_t acc = 0;
+    for (int k = s; k < 16; ++k) acc = (acc << 4) | (c8_byte(w, k) >> 4);
+    return acc;
+}
+
+// decode the lane's 16 bytes in order: `init` = pending extension bits from the previous lane, operations go to dst[out], dst[out+1], ...
+// (nothing at or beyond nc); returns the number of operations seen; *bad is set for a length of 2^28 or more
+SVIM_HD uint32_t c8_decode_lane(const uint32_t w[4], uint32_t init, uint64_t out, uint64_t nc, uint32_t* dst, uint32_t* bad) {
+    uint32_t acc = init, n = 0;
+    for (int k = 0; k < 16; ++k) {
+        const uint32_t x = c8_byte(w, k), hi = x >> 4;
+        if ((x & 15u) == 15u) { if (acc >> 20) *bad = 1u; acc = (acc << 4) | hi; }
+        else {
+            if (acc >> 24) *bad = 1u;
+            const uint32_t len = (acc << 4) | hi;
+            if (out + n < nc) dst[out + n] = (len << 4) | (x & 15u);
+            ++n; acc = 0;
+        }
+    }
+    return n;
+}
+

@@ -650,4 +650,41 @@ int bamio_pack_cigar16(int64_t n, const uint32_t* n_cigar, const uint64_t* cigar
     return 0;
 }
 
+// ---- 8-bit packed CIGAR (svim_aln_soa.cigar8, include/svimgpu.h) -------------------------------------------------------------
+// One byte per operation of fewer than 16 bases (len << 4 | op); longer ones are preceded by extension bytes (op nibble 0xF,
+// 4 more significant length bits each, most significant first, no leading zero extension).  Every record's stream is padded to a
+// multiple of 16 bytes with 0x0F.  Pass 1 (out8 == nullptr): off8[i] and off8[n] = total bytes.  Pass 2: fills out8.
+int bamio_pack_cigar8(int64_t n, const uint32_t* n_cigar, const uint64_t* cigar_off, const uint32_t* cigar, uint64_t* off8, uint8_t* out8, int n_threads) {
+    if (n < 0 || (n > 0 && (!n_cigar || !cigar_off || !cigar || !off8))) return -1;
+    if (n_threads < 1) n_threads = 1;
+    auto ext_of = [](uint32_t len) { int e = 0; while (len >= 16u) { len >>= 4; ++e; } return e; };     // extension bytes of a length
+    auto bytes_of = [&](int64_t i) {
+        uint64_t w = 0;
+        const uint32_t* c = cigar + cigar_off[i];
+        for (uint32_t k = 0; k < n_cigar[i]; ++k) w += 1 + (uint64_t)ext_of(c[k] >> 4);
+        return (w + 15) & ~15ull;
+    };
+    if (!out8) {
+        std::vector<uint64_t> cnt((size_t)n);
+        parallel_for((size_t)n, n_threads, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) cnt[i] = bytes_of((int64_t)i); });
+        uint64_t at = 0;
+        for (int64_t i = 0; i < n; ++i) { off8[i] = at; at += cnt[(size_t)i]; }
+        off8[n] = at;
+        return 0;
+    }
+    parallel_for((size_t)n, n_threads, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) {
+        const uint32_t* c = cigar + cigar_off[i];
+        uint8_t* o = out8 + off8[i];
+        uint64_t w = 0;
+        for (uint32_t k = 0; k < n_cigar[i]; ++k) {
+            const uint32_t len = c[k] >> 4, op = c[k] & 15u;
+            for (int e = ext_of(len); e > 0; --e) o[w++] = (uint8_t)((((len >> (4 * e)) & 15u) << 4) | 15u);
+            o[w++] = (uint8_t)(((len & 15u) << 4) | op);
+        }
+        const uint64_t end = off8[i + 1] - off8[i];
+        while (w < end) o[w++] = 0x0F;
+    } });
+    return 0;
+}
+
 }  // extern "C"

@@ -177,6 +177,7 @@ def _bamio_lib():
         lib.bamio_layout.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         lib.bamio_blocks.argtypes = [C.c_void_p, C.c_void_p]
         lib.bamio_pack_cigar16.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.bamio_pack_cigar8.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         _bamio = lib
     return _bamio
 
@@ -266,6 +267,36 @@ def unpack_cigar16(cigar16, off16, n_cigar):
             else:
                 ops.append((((acc << 12) | (x >> 4)) << 4) | (x & 15)); acc = 0
         assert len(ops) == int(n_cigar[i])
+        out.append(np.asarray(ops, dtype=np.uint32))
+    return out
+
+
+def pack_cigar8(batch, threads: int = 0):
+    """(cigar8, cigar8_off) of a batch: the 8-bit packed CIGAR stream of include/svimgpu.h, built by csrc_host/bamio.cpp."""
+    lib = _bamio_lib()
+    threads = threads or (os.cpu_count() or 8)
+    n = batch.n
+    off = np.zeros(n + 1, dtype=np.uint64)
+    args = (n, batch.n_cigar.ctypes.data, batch.cigar_off.ctypes.data, batch.cigar.ctypes.data if batch.cigar.size else None)
+    if lib.bamio_pack_cigar8(*args, off.ctypes.data, None, threads) != 0:
+        raise ValueError("pack_cigar8: bad arguments")
+    out = np.empty(int(off[n]), dtype=np.uint8)
+    if lib.bamio_pack_cigar8(*args, off.ctypes.data, out.ctypes.data if out.size else None, threads) != 0:
+        raise ValueError("pack_cigar8: bad arguments")
+    return out, off
+
+
+def unpack_cigar8(cigar8, off8, n_cigar):
+    """Inverse of pack_cigar8 in numpy/Python (tests): list of uint32 arrays, one per record."""
+    out = []
+    for i in range(len(n_cigar)):
+        ops = []; acc = 0
+        for x in cigar8[int(off8[i]):int(off8[i + 1])].tolist():
+            if x & 15 == 15:
+                acc = (acc << 4) | (x >> 4)
+            else:
+                ops.append((((acc << 4) | (x >> 4)) << 4) | (x & 15)); acc = 0
+        assert len(ops) == int(n_cigar[i]) and acc == 0
         out.append(np.asarray(ops, dtype=np.uint32))
     return out
 

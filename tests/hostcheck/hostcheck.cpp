@@ -196,3 +196,28 @@ extern "C" long long hc_bam_chunked_starts(const uint8_t* data, unsigned long lo
     }
     return total;
 }
+
+// ---- svim_aln_soa.cigar8 expansion: the warp loop of k_expand_cigar8 (collect.cu) replayed with 32 sequential "lanes" ----
+extern "C" int hc_expand_cigar8(const uint8_t* src, unsigned long long nb, unsigned long long nc, uint32_t* dst) {
+    unsigned long long out = 0; uint32_t carry = 0, err = 0;
+    for (unsigned long long base = 0; base < nb; base += 512) {
+        uint32_t w[32][4], cnt[32], pre[32], tail[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            const unsigned long long at = base + (unsigned long long)lane * 16;
+            for (int q = 0; q < 4; ++q) w[lane][q] = 0x0F0F0F0Fu;
+            if (at < nb) memcpy(w[lane], src + at, 16);
+            cnt[lane] = 16u - c8_ext_bytes(w[lane]);
+            tail[lane] = c8_tail(w[lane]);
+        }
+        uint32_t run = 0;
+        for (int lane = 0; lane < 32; ++lane) { run += cnt[lane]; pre[lane] = run; }
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint32_t init = lane == 0 ? carry : tail[lane - 1];
+            const uint32_t got = c8_decode_lane(w[lane], init, out + pre[lane] - cnt[lane], nc, dst, &err);
+            if (got != cnt[lane]) return -2;          // the scan's count and the decoder's must agree
+        }
+        out += pre[31]; carry = tail[31];
+    }
+    return (err || out != nc || carry) ? 1 : 0;
+}
+

@@ -188,3 +188,47 @@ def test_packed_cigar16_upload_expands_to_the_same_words(gpu_ctx, golden):
             gb.cigar16 = None; gb.cigar16_off = None
         assert rows == exp["signatures"]
         assert_clusters_equal(clusters, exp["clusters"])
+
+
+def test_packed_cigar8_upload_expands_to_the_same_words(gpu_ctx, golden):
+    """svim_aln_soa.cigar8 (one byte per operation under 16 bases, extension bytes before the longer ones): the device expansion
+    must give back the caller's uint32 words record for record — zero padding included — wherever the extension chains fall
+    (inside a lane's 16 bytes, across lanes, across the 512-byte rounds), and COLLECT must not notice the difference.
+    The same warp loop is replayed on the host in tests/test_host_units.py."""
+    from svim_b200 import io as sio
+    rng = np.random.default_rng(8)
+    b = BatchBuilder(NAMES, [10**9] * 3)
+    b.add("long", 0, 0, 100, 60, [(0, 5), (2, 15), (0, 16), (2, 255), (1, 256), (3, 20000000), (0, 3), (4, 2**28 - 1), (0, 0)], None, None)
+    b.add("sixext", 0, 0, 150, 60, [(2, 2**28 - 1)] * 100, None, None)
+    b.add("nine", 0, 0, 200, 60, [(0, 10)] * 9, None, None)
+    b.add("empty", 4, -1, -1, 0, "", None, None)
+    for k in range(400):
+        n = int(rng.choice([1, 15, 16, 17, 31, 32, 33, 511, 512, 513, 1000, 3000]))
+        p_ext = float(rng.choice([0.0, 0.1, 0.5]))
+        ops = [(int(rng.integers(0, 9)), int(rng.choice([16, 200, 4096, 70000, 2**27])) if rng.random() < p_ext else int(rng.integers(0, 16))) for _ in range(n)]
+        b.add("r%d" % k, 0, 0, 1000 + k, 60, ops, None, None)
+    batch = b.finish()
+    packed = batch.pack_cigar8(3)
+    un = sio.unpack_cigar8(packed.cigar8, packed.cigar8_off, batch.n_cigar)
+    for i in range(batch.n):
+        assert np.array_equal(un[i], batch.cigar[int(batch.cigar_off[i]):int(batch.cigar_off[i]) + int(batch.n_cigar[i])])
+    gpu_ctx.set_params(_lib.Params.from_options(None)); gpu_ctx.set_contigs(batch.contig_names)
+    gpu_ctx.upload(packed)
+    assert np.array_equal(gpu_ctx.download_cigar(batch.cigar.size), batch.cigar)
+    # a stream that does not decode to n_cigar operations
+    broken = b.finish().pack_cigar8(1)
+    broken.cigar8[int(broken.cigar8_off[2])] = 0x0F
+    with pytest.raises(_lib.SvimGpuError):
+        gpu_ctx.upload(broken)
+    # COLLECT + CLUSTER from the packed upload == golden
+    from gpu_common import run_gpu, assert_clusters_equal
+    for name in ("mini_mixed", "mini_hotspot"):
+        gb, genome, exp = golden(name)
+        gb.pack_cigar8(2)
+        try:
+            rows, trows, clusters, st, cst = run_gpu(gpu_ctx, gb, genome, exp["params"])
+        finally:
+            gb.cigar8 = None; gb.cigar8_off = None
+        assert rows == exp["signatures"]
+        assert_clusters_equal(clusters, exp["clusters"])
+

@@ -979,3 +979,52 @@ def test_cli_writes_the_reference_file_set(tmp_path):
     assert sorted(os.listdir(tmp_path / "signatures")) == sorted(os.listdir(gold))
     for f in os.listdir(gold):
         assert (tmp_path / "signatures" / f).read_text() == open(os.path.join(gold, f)).read(), f
+
+
+# ---- svim_aln_soa.cigar8: host packer, Python inverse, and the device expansion's warp loop replayed on the host ----------------
+def _cigar8_cases(rng):
+    """Records whose packed streams put extension chains everywhere: inside a lane, across 16-byte lane boundaries, across the
+    512-byte round boundary, at the very start and the very end; lengths up to 2^28 - 1; empty records."""
+    recs = []
+    for _ in range(60):
+        n = rng.choice([0, 1, 2, 7, 15, 16, 17, 31, 200, 511, 512, 513, 700, 1500])
+        ops = []
+        for _k in range(n):
+            r = rng.random()
+            ln = (rng.randint(1, 15) if r < 0.80 else rng.randint(16, 255) if r < 0.92 else rng.randint(256, 70000) if r < 0.98
+                  else rng.randint(1 << 20, (1 << 28) - 1))
+            ops.append((ln << 4) | rng.randint(0, 8))
+        recs.append(ops)
+    recs.append([((1 << 28) - 1) << 4 | 2] * 40)             # every operation needs six extension bytes
+    recs.append([(0 << 4) | 0, (16 << 4) | 1, (15 << 4) | 8])  # zero length, first length that needs an extension
+    return recs
+
+
+def test_cigar8_pack_roundtrip_and_device_loop_replay(hc):
+    from svim_b200.records import BatchBuilder
+    rng = random.Random(808)
+    recs = _cigar8_cases(rng)
+    b = BatchBuilder(["c"], [1 << 30])
+    for i, ops in enumerate(recs):
+        b.add(tid=0, pos=10 * i, flag=0, mapq=60, cigar=np.asarray(ops, dtype=np.uint32), seq="", sa="", qname="r%d" % i)
+    batch = b.finish().pack_cigar8(3)
+    assert batch.cigar8.dtype == np.uint8 and (batch.cigar8_off % 16 == 0).all()
+    un = sio.unpack_cigar8(batch.cigar8, batch.cigar8_off, batch.n_cigar)
+    hc.hc_expand_cigar8.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_void_p]
+    for i, ops in enumerate(recs):
+        assert un[i].tolist() == ops
+        lo, hi = int(batch.cigar8_off[i]), int(batch.cigar8_off[i + 1])
+        src = np.ascontiguousarray(batch.cigar8[lo:hi])
+        dst = np.full(len(ops) + 4, 0xDEADBEEF, dtype=np.uint32)
+        rc = hc.hc_expand_cigar8(src.ctypes.data if src.size else None, hi - lo, len(ops), dst.ctypes.data)
+        assert rc == 0, (i, rc)
+        assert dst[:len(ops)].tolist() == ops and (dst[len(ops):] == 0xDEADBEEF).all()
+    # a stream that does not hold n_cigar operations, and a dangling extension byte, are reported
+    lo, hi = int(batch.cigar8_off[5]), int(batch.cigar8_off[6])
+    src = np.ascontiguousarray(batch.cigar8[lo:hi]); n5 = len(recs[5])
+    dst = np.zeros(n5 + 8, dtype=np.uint32)
+    assert hc.hc_expand_cigar8(src.ctypes.data, hi - lo, n5 + 1, dst.ctypes.data) == 1
+    bad = src.copy(); bad[-1] = 0x1F
+    assert hc.hc_expand_cigar8(bad.ctypes.data, hi - lo, n5, dst.ctypes.data) == 1
+    assert batch.cigar8.size < 2 * batch.cigar.size      # bytes against uint32 words: under half the bytes even on this extension-heavy mix
+
