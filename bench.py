@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cigar16", action="store_true", help="e2e legs upload BAM's uint32 CIGAR words instead of a packed stream (same as --cigar-pack 32)")
-    ap.add_argument("--cigar-pack", type=int, choices=[8, 16, 32], default=16, help="CIGAR stream of the e2e legs: 8 = svim_aln_soa.cigar8, 16 = cigar16, 32 = BAM's uint32 words")
+    ap.add_argument("--cigar-pack", type=int, choices=[8, 16, 32], default=8, help="CIGAR stream of the e2e legs: 8 = svim_aln_soa.cigar8, 16 = cigar16, 32 = BAM's uint32 words")
     ap.add_argument("--profile-steps", action="store_true", help="only run resident steps (for ncu)")
     ap.add_argument("--no-bam", action="store_true", help="skip the e2e_from_bam leg (writes a BAM of the workload to a temporary directory)")
     ap.add_argument("--with-bam", action="store_true", help=argparse.SUPPRESS)        # round-1 spelling: the leg is on by default now

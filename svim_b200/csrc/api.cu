@@ -178,15 +178,33 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
             const uint64_t* poff = packed8 ? s->cigar8_off : s->cigar16_off;
             SVIM_CUDA(ctx->d_cig16.ensure(pbytes + 64)); SVIM_CUDA(ctx->d_cig16_off.ensure((size_t)(n + 1) * 8));
             SVIM_CUDA(ctx->d_cig16_err.ensure(16)); SVIM_CUDA(cudaMemsetAsync(ctx->d_cig16_err.p, 0, 4, ctx->stream));
-            if (pbytes) SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16.p, psrc, pbytes, cudaMemcpyHostToDevice, ctx->stream));
             SVIM_CUDA(cudaMemcpyAsync(ctx->d_cig16_off.p, poff, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
             if (n > 0) {
+                // the stream crosses in slices of whole records on the copy stream while the slices already there are expanded on the
+                // main stream: the expansion (4 B written per operation) hides behind the PCIe copy instead of following it
                 int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-                ctx->launches++;
-                if (packed8) k_expand_cigar8<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
-                                                                               ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
-                else k_expand_cigar16<<<sms * 8, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>(), ctx->d_soa[4].as<uint32_t>(),
-                                                                        ctx->d_soa[5].as<uint64_t>(), n, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                const size_t unit = packed8 ? 1 : 2;                      // bytes per offset unit
+                const int max_slices = SVIM_AUX_STREAMS;                  // one event per slice (aux_ev)
+                const uint64_t total_units = poff[n];
+                const uint64_t per = std::max<uint64_t>((total_units + max_slices - 1) / max_slices, (uint64_t)(4u << 20) / unit);
+                int64_t r0 = 0; int slice = 0;
+                while (r0 < n) {
+                    int64_t r1;
+                    if (slice == max_slices - 1) r1 = n;
+                    else { const uint64_t want = poff[r0] + per; r1 = std::upper_bound(poff + r0, poff + n + 1, want) - poff; if (r1 <= r0) r1 = r0 + 1; if (r1 > n) r1 = n; }
+                    const size_t b0 = (size_t)poff[r0] * unit, b1 = (size_t)poff[r1] * unit;
+                    if (b1 > b0) SVIM_CUDA(cudaMemcpyAsync((uint8_t*)ctx->d_cig16.p + b0, (const uint8_t*)psrc + b0, b1 - b0, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    SVIM_CUDA(cudaEventRecord(ctx->aux_ev[slice], ctx->copy_stream));
+                    SVIM_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_ev[slice], 0));
+                    const int64_t nr = r1 - r0;
+                    const int blocks = (int)std::min<int64_t>((int64_t)sms * 8, (nr + 7) / 8);
+                    ctx->launches++;
+                    if (packed8) k_expand_cigar8<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
+                                                                                  ctx->d_soa[5].as<uint64_t>() + r0, nr, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                    else k_expand_cigar16<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
+                                                                           ctx->d_soa[5].as<uint64_t>() + r0, nr, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                    r0 = r1; ++slice;
+                }
                 SVIM_CUDA(cudaGetLastError());
             }
         }
