@@ -50,6 +50,7 @@ int svimgpu_create(svimgpu_ctx** out, int device, const svim_params* params) {
     if (const char* v = getenv("SVIM_MYERS_TPP")) ctx->myers_tpp = atoi(v);
     if (const char* v = getenv("SVIM_MYERS_TRACE")) ctx->myers_trace = atoi(v);
     if (const char* v = getenv("SVIM_PEER_INS")) ctx->peer_ins = atoi(v) != 0;
+    if (const char* v = getenv("SVIM_EXPAND8_STAGED")) ctx->expand8_staged = atoi(v) != 0;
     if (const char* v = getenv("SVIM_MYERS_BAND")) { int num = 0, add = 24; if (sscanf(v, "%d,%d", &num, &add) >= 1) { ctx->myers_band_num = num; ctx->myers_band_add = add; } }
     *out = ctx;
     return 0;
@@ -199,7 +200,9 @@ static int upload_alignments(svimgpu_ctx* ctx, const svim_aln_soa* s, bool with_
                     const int64_t nr = r1 - r0;
                     const int blocks = (int)std::min<int64_t>((int64_t)sms * 8, (nr + 7) / 8);
                     ctx->launches++;
-                    if (packed8) k_expand_cigar8<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
+                    if (packed8 && ctx->expand8_staged) k_expand_cigar8_staged<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
+                                                                                  ctx->d_soa[5].as<uint64_t>() + r0, nr, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
+                    else if (packed8) k_expand_cigar8<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint8_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
                                                                                   ctx->d_soa[5].as<uint64_t>() + r0, nr, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());
                     else k_expand_cigar16<<<blocks, 256, 0, ctx->stream>>>(ctx->d_cig16.as<uint16_t>(), ctx->d_cig16_off.as<uint64_t>() + r0, ctx->d_soa[4].as<uint32_t>() + r0,
                                                                            ctx->d_soa[5].as<uint64_t>() + r0, nr, ctx->d_soa[11].as<uint32_t>(), ctx->d_cig16_err.as<uint32_t>());

@@ -796,6 +796,49 @@ __global__ void __launch_bounds__(256) k_expand_cigar8(const uint8_t* __restrict
     }
 }
 
+// The same expansion with the round's words staged in shared memory: the lanes decode into the warp's 512-word staging area (their
+// slots are ~15 words apart: an odd stride, few bank conflicts) and the warp then writes the round out as whole 128-byte lines.
+// k_expand_cigar8 stores straight from the decode loop instead: a warp store instruction touches ~16 lines there.
+__global__ void __launch_bounds__(256) k_expand_cigar8_staged(const uint8_t* __restrict__ c8, const uint64_t* __restrict__ off8, const uint32_t* __restrict__ n_cigar,
+                                                               const uint64_t* __restrict__ cigar_off, int64_t n, uint32_t* __restrict__ cigar, uint32_t* __restrict__ bad) {
+    __shared__ uint32_t stage_all[8][512];
+    uint32_t* stage = stage_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += n_warps) {
+        const uint8_t* src = c8 + off8[i];
+        const uint64_t nb = off8[i + 1] - off8[i];
+        uint32_t* dst = cigar + cigar_off[i];
+        const uint64_t nc = n_cigar[i];
+        uint64_t out = 0;
+        uint32_t carry = 0, err = 0;
+        for (uint64_t base = 0; base < nb; base += 512) {
+            const uint64_t at = base + (uint64_t)lane * 16;
+            uint4 v = make_uint4(0x0F0F0F0Fu, 0x0F0F0F0Fu, 0x0F0F0F0Fu, 0x0F0F0F0Fu);
+            if (at < nb) v = *(const uint4*)(src + at);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            const uint32_t cnt = 16u - c8_ext_bytes(w);
+            uint32_t pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+            const uint32_t tail = c8_tail(w);
+            uint32_t init = __shfl_up_sync(0xffffffffu, tail, 1);
+            if (lane == 0) init = carry;
+            c8_decode_lane(w, init, pre - cnt, 512, stage, &err);
+            __syncwarp();
+            const uint32_t total = __shfl_sync(0xffffffffu, pre, 31);
+            const int shift = (int)(((uintptr_t)(dst + out) >> 2) & 31u);      // lanes line up with the 128-byte lines of the destination
+            for (int k = lane - shift; k < (int)total; k += 32)
+                if (k >= 0 && out + (uint64_t)k < nc) dst[out + (uint64_t)k] = stage[k];
+            __syncwarp();
+            out += total;
+            carry = __shfl_sync(0xffffffffu, tail, 31);
+        }
+        if (__any_sync(0xffffffffu, err) || out != nc || carry) { if (lane == 0) atomicExch(bad, 1u); }
+        for (uint32_t k = (uint32_t)nc + lane; k < (((uint32_t)nc + 3u) & ~3u); k += 32) dst[k] = 0u;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_segment_chain(DevSoa a, ChainParams p, ContigTable ct, const ChainWork* work, uint32_t n_work,
                                                         SigQueue qm, SigQueue qt, uint32_t* cnt, uint32_t* big_list) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;

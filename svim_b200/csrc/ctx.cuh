@@ -179,6 +179,7 @@ struct svimgpu_ctx {
 
     // multi-GPU
     void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+    bool expand8_staged = true;            // k_expand_cigar8_staged (shared-memory staged write-out); SVIM_EXPAND8_STAGED=0: k_expand_cigar8
     bool peer_ins = true;                  // SVIM_PEER_INS=0: all-gather the INS blobs too (every rank holds a full copy)
     bool mirror_gathered_ins = true;       // svimgpu_mirror_gathered_ins
     bool host_copy_has_ins[2] = {true, true};

@@ -221,3 +221,33 @@ extern "C" int hc_expand_cigar8(const uint8_t* src, unsigned long long nb, unsig
     return (err || out != nc || carry) ? 1 : 0;
 }
 
+// k_expand_cigar8_staged: same round, words staged in a 512-word area and written out in 32-word rows aligned to the destination
+extern "C" int hc_expand_cigar8_staged(const uint8_t* src, unsigned long long nb, unsigned long long nc, uint32_t* dst, unsigned dst_word_phase) {
+    unsigned long long out = 0; uint32_t carry = 0, err = 0;
+    std::vector<uint32_t> stage(512);
+    for (unsigned long long base = 0; base < nb; base += 512) {
+        uint32_t w[32][4], cnt[32], pre[32], tail[32];
+        for (int lane = 0; lane < 32; ++lane) {
+            const unsigned long long at = base + (unsigned long long)lane * 16;
+            for (int q = 0; q < 4; ++q) w[lane][q] = 0x0F0F0F0Fu;
+            if (at < nb) memcpy(w[lane], src + at, 16);
+            cnt[lane] = 16u - c8_ext_bytes(w[lane]);
+            tail[lane] = c8_tail(w[lane]);
+        }
+        uint32_t run = 0;
+        for (int lane = 0; lane < 32; ++lane) { run += cnt[lane]; pre[lane] = run; }
+        for (uint32_t& x : stage) x = 0xABABABABu;
+        for (int lane = 0; lane < 32; ++lane) {
+            const uint32_t init = lane == 0 ? carry : tail[lane - 1];
+            c8_decode_lane(w[lane], init, pre[lane] - cnt[lane], 512, stage.data(), &err);
+        }
+        const uint32_t total = pre[31];
+        const int shift = (int)((dst_word_phase + out) & 31u);
+        for (int lane = 0; lane < 32; ++lane)
+            for (int k = lane - shift; k < (int)total; k += 32)
+                if (k >= 0 && out + (unsigned long long)k < nc) dst[out + (unsigned long long)k] = stage[k];
+        out += total; carry = tail[31];
+    }
+    return (err || out != nc || carry) ? 1 : 0;
+}
+

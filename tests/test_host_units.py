@@ -1011,6 +1011,7 @@ def test_cigar8_pack_roundtrip_and_device_loop_replay(hc):
     assert batch.cigar8.dtype == np.uint8 and (batch.cigar8_off % 16 == 0).all()
     un = sio.unpack_cigar8(batch.cigar8, batch.cigar8_off, batch.n_cigar)
     hc.hc_expand_cigar8.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_void_p]
+    hc.hc_expand_cigar8_staged.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_uint]
     for i, ops in enumerate(recs):
         assert un[i].tolist() == ops
         lo, hi = int(batch.cigar8_off[i]), int(batch.cigar8_off[i + 1])
@@ -1019,6 +1020,10 @@ def test_cigar8_pack_roundtrip_and_device_loop_replay(hc):
         rc = hc.hc_expand_cigar8(src.ctypes.data if src.size else None, hi - lo, len(ops), dst.ctypes.data)
         assert rc == 0, (i, rc)
         assert dst[:len(ops)].tolist() == ops and (dst[len(ops):] == 0xDEADBEEF).all()
+        # the staged variant (k_expand_cigar8_staged): every word written exactly once whatever the destination's line phase
+        dst2 = np.full(len(ops) + 4, 0xDEADBEEF, dtype=np.uint32)
+        rc = hc.hc_expand_cigar8_staged(src.ctypes.data if src.size else None, hi - lo, len(ops), dst2.ctypes.data, (7 * i) % 32)
+        assert rc == 0 and np.array_equal(dst2, dst), (i, rc)
     # a stream that does not hold n_cigar operations, and a dangling extension byte, are reported
     lo, hi = int(batch.cigar8_off[5]), int(batch.cigar8_off[6])
     src = np.ascontiguousarray(batch.cigar8[lo:hi]); n5 = len(recs[5])
