@@ -305,6 +305,8 @@ int svimgpu_peer_ins_active(svimgpu_ctx* ctx);
  * host mirror of svimgpu_signatures_host assemble the whole blob from the peers on demand.  Consequence: a rank must not start its
  * next collect while another rank may still be reading its piece - the exchange inside svimgpu_cluster_sharded orders the cluster
  * calls; put a barrier (svimgpu_barrier_max) between a fetch of the gathered lists and the next collect.
+ * A rank's INS buffer only grows (it is reallocated when a later collect emits more inserted bases than any before; the peers
+ * re-map it at the next exchange, and nobody reads the old mapping in between).
  * SVIM_PEER_INS=0 in the environment of every rank: gather the INS blobs as well (every rank holds a private full copy). */
 int svimgpu_exchange_signatures(svimgpu_ctx* ctx, uint32_t aln_base, svim_collect_stats* stats);
 /* After the exchange the host mirror of svimgpu_signatures_host is restarted for the gathered lists (when the lists came from
