@@ -162,7 +162,7 @@ def add_genotype_and_cutpaste(fake, batch):
     def set_signatures(cs, blob=None, rank_to_tid=None):
         state["cand"] = np.array(cs, copy=True)
 
-    def cluster(sharded=False):
+    def cluster(sharded=False, view=False):
         cs = state["cand"]
         if cs is None:
             return collected_cluster(sharded)
