@@ -412,9 +412,10 @@ def main():
         return
 
     # ---------------- e2e: host buffers through the C ABI, copies inside the timed region --------
-    # the record buffer crosses PCIe with its CIGAR blob in a packed form of include/svimgpu.h (svim_aln_soa.cigar8 / cigar16), re-encoded
-    # by the host ONCE, outside the timed region (csrc_host/bamio.cpp, multi-threaded; its time is reported as e2e.cigar_pack_s), and is
-    # expanded to BAM's uint32 words in HBM inside it
+    # the record buffer crosses PCIe with its CIGAR blob in a packed form of include/svimgpu.h (svim_aln_soa.cigar8 / cigar16): what the
+    # host BAM decoder emits while it decodes (io.read_bam_native(pack_cigar=8)).  The synthetic batch never was a BAM file, so it is
+    # re-encoded here ONCE, outside the timed region (csrc_host/bamio.cpp; its time is reported as e2e.cigar_pack_s); the expansion to
+    # BAM's uint32 words in HBM is inside it
     t_pack = time.perf_counter()
     pack = 32 if args.no_cigar16 else args.cigar_pack
     if pack == 16:

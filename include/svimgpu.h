@@ -77,7 +77,8 @@ typedef struct {
      * operations (91 % under 16 bases on the CLR-like workloads), so one byte per operation carries them: 1.09 bytes per operation
      * on BASELINE configs[1] against 2 and 4.  Byte = len << 4 | op for len < 16; bytes with op nibble 0xF carry 4 more
      * significant length bits each and precede the operation byte (most significant first, no leading zero extension);
-     * every record's stream starts at cigar8_off[i] (bytes, multiple of 16) and is padded with 0x0F.  bamio_pack_cigar8. */
+     * every record's stream starts at cigar8_off[i] (bytes, multiple of 16) and is padded with 0x0F.  svim_b200's host BAM decoder
+     * emits it while decoding (csrc_host/bamio.cpp, bamio_set_pack); bamio_pack_cigar8 is the stand-alone packer. */
     const uint8_t* cigar8; int64_t cigar8_bytes;
     const uint64_t* cigar8_off;                  /* n_aln + 1 entries */
 } svim_aln_soa;

@@ -84,6 +84,7 @@ struct Row {
     uint32_t cig_src;                  // CIGAR words relative to the record start (core CIGAR, or the CG:B,I payload)
     uint32_t n_cigar_core;             // operations stored in the record core (2 for a CG-tagged record): SEQ follows them
     uint32_t name_off;                 // into the unit's name arena
+    uint32_t c8_len = 0;               // bytes of the record's 8-bit packed CIGAR stream (multiple of 16), when asked for
 };
 
 struct Unit {
@@ -92,6 +93,7 @@ struct Unit {
     std::string names;                 // NUL-terminated read names of the unit's records, in order
     std::string sa;                    // SA tag payloads of the unit's records, concatenated (small: copied out at the end)
     uint64_t row_base = 0, sa_base = 0;
+    std::vector<uint8_t> c8;           // svim_aln_soa.cigar8 streams of the unit's records, back to back (bamio_set_pack(h, 8))
 };
 
 struct Handle {
@@ -106,6 +108,7 @@ struct Handle {
     int threads = 1;
     bool header_done = false;
     size_t header_bytes = 0;          // BAM header length in the inflated stream = offset of the first alignment record
+    int pack = 0;                     // 8: also emit the 8-bit packed CIGAR stream while the unit is warm (bamio_set_pack)
     ~Handle() { if (file && fsz) munmap((void*)file, fsz); if (fd >= 0) close(fd); }
 };
 
@@ -401,6 +404,29 @@ int bamio_decode(void* hh, uint32_t* cigar, uint8_t* seq, bamio_info* info, char
                 for (uint32_t k = w.n_cigar; k < ((w.n_cigar + 3u) & ~3u); ++k) dst[k] = 0;
                 memcpy(seq + w.seq_off, r + 32 + w.l_rn + 4 * (size_t)w.n_cigar_core, (size_t)(w.l_seq + 1) / 2);
             }
+            if (h->pack == 8) {
+                // the 8-bit packed stream of include/svimgpu.h (bamio_pack_cigar8 below is the stand-alone version), from the same warm bytes
+                size_t len8 = 0;
+                un.c8.resize(std::max<size_t>(un.c8.size(), un.ulen / 3 + 64));
+                for (Row& w : un.rows) {
+                    const size_t worst = len8 + (size_t)w.n_cigar * 7 + 16;              // 28-bit length: six extension bytes + the operation byte
+                    if (un.c8.size() < worst) un.c8.resize(std::max(worst, un.c8.size() * 2));
+                    uint8_t* o = un.c8.data() + len8;
+                    const uint8_t* cg = d + w.src_off + w.cig_src;
+                    size_t q = 0;
+                    for (uint32_t k = 0; k < w.n_cigar; ++k) {
+                        const uint32_t c = rd32(cg + 4 * (size_t)k), len = c >> 4;
+                        if (len >= 16u) {
+                            int e = 0; for (uint32_t l = len; l >= 16u; l >>= 4) ++e;
+                            for (; e > 0; --e) o[q++] = (uint8_t)((((len >> (4 * e)) & 15u) << 4) | 15u);
+                        }
+                        o[q++] = (uint8_t)(((len & 15u) << 4) | (c & 15u));
+                    }
+                    while (q & 15u) o[q++] = 0x0F;
+                    w.c8_len = (uint32_t)q; len8 += q;
+                }
+                un.c8.resize(len8);
+            }
             t_fill += since(t0);
         }
     };
@@ -469,6 +495,36 @@ int bamio_fill(void* hh, bamio_out* out) {
         }
     });
     tr.mark("row arrays");
+    return 0;
+}
+
+// 8-bit packed CIGAR stream emitted by the decode itself.  bamio_set_pack(h, 8) before bamio_decode; afterwards
+// bamio_cigar8_bytes = total stream bytes, bamio_cigar8_fill writes off8[n + 1] (bytes) and the stream.
+int bamio_set_pack(void* hh, int bits) { Handle* h = (Handle*)hh; if (bits != 0 && bits != 8) return -1; h->pack = bits; return 0; }
+
+int64_t bamio_cigar8_bytes(void* hh) {
+    Handle* h = (Handle*)hh;
+    int64_t t = 0;
+    for (const Unit& un : h->units) t += (int64_t)un.c8.size();
+    return t;
+}
+
+int bamio_cigar8_fill(void* hh, uint64_t* off8, uint8_t* out8) {
+    Handle* h = (Handle*)hh;
+    if (h->pack != 8 || !off8) return -1;
+    std::vector<uint64_t> ubase(h->units.size() + 1, 0);
+    for (size_t u = 0; u < h->units.size(); ++u) ubase[u + 1] = ubase[u] + h->units[u].c8.size();
+    parallel_for(h->units.size(), h->threads, [&](size_t lo, size_t hi) {
+        for (size_t u = lo; u < hi; ++u) {
+            const Unit& un = h->units[u];
+            size_t i = (size_t)un.row_base; uint64_t at = ubase[u];
+            for (const Row& w : un.rows) { off8[i++] = at; at += w.c8_len; }
+            if (out8 && !un.c8.empty()) memcpy(out8 + ubase[u], un.c8.data(), un.c8.size());
+        }
+    });
+    uint64_t n = 0;
+    for (const Unit& un : h->units) n += un.rows.size();
+    off8[n] = ubase.back();
     return 0;
 }
 

@@ -499,6 +499,11 @@ def test_native_bam_reader_records_spanning_units(tmp_path):
         for blob in ("cigar", "seq", "sa"):
             assert np.array_equal(getattr(a, blob), getattr(batch, blob)), (threads, blob)
         assert [a.qname(int(i)) for i in a.qname_id] == [batch.qname(int(i)) for i in batch.qname_id]
+        # the decode can emit the 8-bit packed CIGAR stream itself: same bytes as the stand-alone packer
+        a8 = sio.read_bam_native(p, threads=threads, pack_cigar=8)
+        want8, want_off = sio.pack_cigar8(batch, 2)
+        assert np.array_equal(a8.cigar8_off, want_off) and np.array_equal(a8.cigar8, want8), threads
+        assert np.array_equal(a8.cigar, batch.cigar)
     # truncated file: the reader reports it instead of returning short data
     raw = open(p, "rb").read()
     open(p, "wb").write(raw[: len(raw) // 2])
@@ -891,6 +896,9 @@ def test_bam_long_cigar_cg_tag_roundtrip(tmp_path):
             assert np.array_equal(getattr(got, name), getattr(batch, name)), name
         for blob in ("cigar", "seq", "sa"):
             assert np.array_equal(getattr(got, blob), getattr(batch, blob)), blob
+    got8 = sio.read_bam_native(p1, threads=3, pack_cigar=8)          # CG:B,I records: the packed stream holds the REAL operations
+    want8, want_off = sio.pack_cigar8(batch, 2)
+    assert np.array_equal(got8.cigar8_off, want_off) and np.array_equal(got8.cigar8, want8)
     # the record core really carries the placeholder (what a reader without CG support would see)
     raw = sio._bgzf_inflate_all(p1)
     assert raw.count(b"CGBI") == 2
